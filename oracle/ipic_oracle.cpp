@@ -1,0 +1,1469 @@
+// =============================================================================
+// ipic_oracle.cpp -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE)
+//
+// A plain C++17/OpenMP restatement of the implicit-PIC inner loop of
+// nsavard01/ImplicitPic1D (trees OpenMP/NGP and OpenMP/CIC).  It exists only
+// to check the CUDA path (tests/, __graft_entry__.smoke(), bench.py's
+// cpu_baseline / --impl reference leg).  Nothing under implicitpic1d_b200/
+// may import, link or call it.
+//
+// PARITY STATUS: "parity unpinned" against the Fortran binary -- the reference
+// ships no golden vectors for this path, cannot be compiled here (no Fortran
+// compiler, Intel-only modules, MKL) and seeds its RNG from the OS.  The
+// oracle is pinned instead on the reference's own acceptance invariants
+// (main.f90:93-114: energy error, Gauss error, charge-continuity error) and on
+// analytic known-answer tests (tests/test_oracle_*.py).
+//
+// Conventions: arrays are 1-based like the Fortran (index 0 is padding) so
+// that every loop bound and stencil reads like the file:line it restates.
+// Thread-slab layout phaseSpace(4, finalIdx, T), per-thread private grid
+// copies and the thread-ordered / species-ordered reduction are kept, so the
+// summation order is the reference's.  Compiled WITHOUT fast-math.
+// =============================================================================
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+// constants.f90:7-15
+constexpr double eps_0 = 8.8541878128e-12;
+constexpr double m_amu = 1.66053906660e-27;
+constexpr double m_e   = 9.1093837015e-31;
+constexpr double e_c   = 1.602176634e-19;
+const double pi = 4.0 * std::atan(1.0);
+
+inline double fsign(double a, double b) { return std::signbit(b) ? -std::fabs(a) : std::fabs(a); }  // Fortran SIGN(a,b)
+
+typedef std::vector<double> dvec;
+typedef std::vector<int> ivec;
+
+// ---- mod_BasicFunctions.f90:45-58  ran2 (Park-Miller / Schrage) -------------
+inline double ran2(int32_t &irand) {
+    const int32_t ia = 16807, im = 2147483647, iq = 127773, ir = 2836;
+    const double am = 1.0 / im;
+    int32_t k = irand / iq;
+    irand = ia * (irand - k * iq) - ir * k;
+    if (irand < 0) irand += im;
+    return am * irand;
+}
+
+// ---- mod_BasicFunctions.f90:76-96  randPCG ----------------------------------
+inline double randPCG(uint64_t &state) {
+    uint64_t x = state;
+    state = x * 6364136223846793005ULL + 1442695040888963407ULL;
+    x ^= x >> 18;
+    int32_t x_shifted = (int32_t)(uint32_t)(x >> 27);
+    int32_t count = (int32_t)(x >> 59);
+    uint32_t xs = (uint32_t)x_shifted;
+    uint32_t rn = (xs >> count) | (xs << ((-count) & 31));
+    double res = (double)(int32_t)rn + 2147483648.0;
+    return res / 4294967296.0;
+}
+
+struct Domain {
+    int scheme = 0;           // 0 NGP, 1 CIC
+    int Nx = 0, Nh = 0;       // NumberXNodes, NumberXHalfNodes
+    int T = 1;                // numThread
+    dvec grid, dx_dl, nodeVol, centerDiff;
+    ivec bc;                  // boundaryConditions: NGP size Nx, CIC size Nh
+    double L_domain = 0, startX = 0, endX = 0;
+    bool smooth = false;
+    int nTN = 0, nTH = 0;
+    ivec tnL, tnR, thL, thR;  // threadNodeIndx / threadHalfNodeIndx (1-based thread)
+};
+
+// NGP mod_domain.f90:62-100 / CIC mod_domain.f90:59-98: node slices per thread
+static void make_slices(int N, int T, int &num, ivec &L, ivec &R) {
+    num = (T < N) ? T : N;
+    L.assign(num + 1, 0); R.assign(num + 1, 0);
+    int spacing = N / num - 1, modT = N % num, k = 1;
+    for (int i = 1; i <= num; ++i) {
+        L[i] = k;
+        if (i <= modT) k += spacing + 1; else k += spacing;
+        R[i] = k;
+        k += 1;
+    }
+}
+
+// domain_constructor: NGP mod_domain.f90:46-101, CIC mod_domain.f90:43-100
+static void domain_init(Domain &w, int scheme, int Nx, int bcL, int bcR, int T) {
+    w.scheme = scheme; w.Nx = Nx; w.T = T;
+    w.Nh = (scheme == 0) ? Nx - 1 : Nx + 1;      // NGP :370 / CIC :355
+    int nb = (scheme == 0) ? Nx : w.Nh;
+    w.grid.assign(Nx + 2, 0.0);
+    w.dx_dl.assign(std::max(Nx, w.Nh) + 2, 1.0);
+    w.nodeVol.assign(Nx + 2, 1.0);
+    w.centerDiff.assign(Nx + 2, 0.0);
+    w.bc.assign(nb + 2, 0);
+    w.bc[1] = bcL; w.bc[nb] = bcR;
+    if (bcL == 3 || bcR == 3) { w.bc[1] = 3; w.bc[nb] = 3; }
+    make_slices(Nx, T, w.nTN, w.tnL, w.tnR);
+    make_slices(w.Nh, T, w.nTH, w.thL, w.thR);
+}
+
+// Grid constructors.  NGP mod_domain.f90:104-265; CIC mod_domain.f90:103-252.
+// Returns 0 ok, nonzero = the reference would `stop`.
+static int domain_grid(Domain &w, double del_x, double L, int gridType) {
+    const int Nx = w.Nx, Nh = w.Nh;
+    if (w.scheme == 0) {
+        w.grid[1] = 0.0; w.grid[Nx] = L;
+        switch (gridType) {
+        case 0:  // constructUniformGrid :216-225
+            for (int i = 2; i <= Nh; ++i) w.grid[i] = (i - 1) * L / Nh;
+            break;
+        case 1:  // constructSineGrid :127-144
+            if (del_x / L >= 1.0 / ((double)Nx - 1.0)) return 1;
+            for (int i = 2; i <= Nh; ++i)
+                w.grid[i] = L * (((double)i - 1.0) / ((double)Nx - 1.0) - (1.0 / ((double)Nx - 1.0) - del_x / L)
+                                 * std::sin(2 * pi * (i - 1) / (Nx - 1)) / std::sin(2 * pi / (Nx - 1)));
+            break;
+        case 2:  // constructHalfSineGrid :166-186
+            if (del_x / L >= 1.0 / ((double)Nx - 1.0)) return 1;
+            if (w.bc[1] == 3) return 2;
+            w.grid[Nx] = L / 2.0;
+            for (int i = 2; i <= Nh; ++i)
+                w.grid[i] = L * (((double)i - 1.0) / ((double)Nx - 1.0) / 2.0 - (1.0 / ((double)Nx - 1.0) / 2.0 - del_x / L)
+                                 * std::sin(pi * ((double)i - 1) / ((double)Nx - 1)) / std::sin(pi / ((double)Nx - 1.0)));
+            break;
+        case 3: {  // constructExpHalfGrid :188-214
+            double F = 100.0 * del_x;
+            if (F / L > 0.5) return 1;
+            if (w.bc[1] == 3) return 2;
+            double k = 2.0 * std::log(L / F - 1.0) / (double)(float)Nh;
+            double A = L / (std::exp(k * (double)Nh) - 1.0);
+            for (int i = 2; i <= Nh; ++i) w.grid[i] = A * (std::exp(k * (double)(i - 1)) - 1.0);
+            break; }
+        case 5:  // constructInvSineGrid :146-164
+            if (del_x / L >= 1.0 / ((double)Nx - 1.0)) return 1;
+            for (int i = 2; i <= Nh; ++i) {
+                double phase = (double)((float)(i - 1) / (float)Nh);   // real(i-1)/real(N_h): single precision
+                w.grid[i] = L * (phase + (1.0 - (double)Nx * del_x / L) * std::sin(2.0 * pi * phase) / 2.0 / pi);
+            }
+            break;
+        default: return 3;
+        }
+        // makeArraysFromGrid :251-265
+        for (int i = 1; i <= Nh; ++i) w.dx_dl[i] = w.grid[i + 1] - w.grid[i];
+        for (int i = 2; i <= Nh; ++i) w.nodeVol[i] = (w.dx_dl[i - 1] + w.dx_dl[i]) / 2.0;
+        w.nodeVol[1] = 0.5 * w.dx_dl[1];
+        w.nodeVol[Nx] = 0.5 * w.dx_dl[Nh];
+        w.startX = w.grid[1]; w.endX = w.grid[Nx];
+        w.L_domain = w.endX - w.startX;
+    } else {
+        const int NN = Nx + 1;   // number of field faces
+        dvec gf(NN + 2, 0.0);
+        gf[1] = 0.0; gf[NN] = L;
+        switch (gridType) {
+        case 0:  // CIC constructUniformGrid :236-252
+            for (int i = 2; i <= NN - 1; ++i) gf[i] = (i - 1) * L / (NN - 1);
+            break;
+        case 1:  // CIC constructSineGrid :128-151
+            if (del_x / L >= 1.0 / ((double)NN - 1.0)) return 1;
+            for (int i = 2; i <= NN - 1; ++i)
+                gf[i] = L * (((double)i - 1.0) / ((double)NN - 1.0) - (1.0 / ((double)NN - 1.0) - del_x / L)
+                             * std::sin(2 * pi * (i - 1) / (NN - 1)) / std::sin(2 * pi / (NN - 1)));
+            break;
+        case 2:  // CIC constructHalfSineGrid :179-201
+            if (del_x / L >= 1.0 / ((double)NN - 1.0)) return 1;
+            gf[NN] = L / 2.0;
+            for (int i = 2; i <= NN - 1; ++i)
+                gf[i] = L * (((double)i - 1.0) / ((double)NN - 1.0) / 2.0 - (1.0 / ((double)NN - 1.0) / 2.0 - del_x / L)
+                             * std::sin(pi * ((double)i - 1) / ((double)NN - 1)) / std::sin(pi / ((double)NN - 1.0)));
+            break;
+        case 5:  // CIC constructInvSineGrid :154-177
+            if (del_x / L >= 1.0 / ((double)Nh - 1.0)) return 1;
+            for (int i = 2; i <= Nx; ++i) {
+                double phase = (double)((float)(i - 1) / (float)Nx);
+                gf[i] = L * (phase + (1.0 - (double)Nh * del_x / L) * std::sin(2.0 * pi * phase) / 2.0 / pi);
+            }
+            break;
+        default: return 3;   // CIC exp grid (type 3) reads unset memory in the reference (:226) -> unsupported
+        }
+        for (int i = 1; i <= NN - 1; ++i) w.dx_dl[i] = gf[i + 1] - gf[i];
+        for (int i = 1; i <= Nx; ++i) w.grid[i] = 0.5 * (gf[i] + gf[i + 1]);
+        for (int i = 1; i <= Nx - 1; ++i) w.centerDiff[i] = w.grid[i + 1] - w.grid[i];
+        // constructGrid :123-125
+        w.startX = w.grid[1] - 0.5 * w.dx_dl[1];
+        w.endX = w.grid[Nx] + 0.5 * w.dx_dl[Nx];
+        w.L_domain = w.endX - w.startX;
+    }
+    return 0;
+}
+
+// getLFromX: NGP mod_domain.f90:275-296 ; CIC mod_domain.f90:254-279
+static double getLFromX(const Domain &w, double x) {
+    int lo = 1, hi = w.Nx;
+    if (w.scheme == 0) {
+        while (lo != hi - 1) {
+            int mid = (lo + hi) / 2;
+            if (w.grid[mid] <= x) lo = mid; else hi = mid;
+        }
+        return lo + (x - w.grid[lo]) / w.dx_dl[lo];
+    }
+    while (lo != hi - 1) {
+        int mid = (lo + hi) / 2;
+        if (w.grid[mid] - 0.5 * w.dx_dl[mid] <= x) lo = mid; else hi = mid;
+    }
+    if (w.grid[lo] + 0.5 * w.dx_dl[lo] <= x) lo = hi;
+    return lo + 0.5 + (x - w.grid[lo]) / w.dx_dl[lo];
+}
+
+// getXFromL: NGP :267-273 ; CIC :281-287
+static double getXFromL(const Domain &w, double l) {
+    int il = (int)l;
+    if (w.scheme == 0) return w.grid[il] + w.dx_dl[il] * (l - il);
+    return w.grid[il] + w.dx_dl[il] * (l - il - 0.5);
+}
+
+// smoothField: NGP mod_domain.f90:298-324 ; CIC mod_domain.f90:289-312
+static void smoothField(const Domain &w, const double *raw, double *out) {
+    const int Nh = w.Nh, Nx = w.Nx;
+    if (w.scheme == 0) {
+        for (int i = 1; i <= Nh; ++i) {
+            int bv = w.bc[i + 1] - w.bc[i];
+            switch (bv) {
+            case 0: out[i] = 0.25 * (raw[i - 1] + 2.0 * raw[i] + raw[i + 1]); break;
+            case -1: case -4: out[i] = 0.25 * (3.0 * raw[1] + raw[2]); break;
+            case 1: case 4: out[i] = 0.25 * (3.0 * raw[Nh] + raw[Nh - 1]); break;
+            case -2: out[i] = 0.25 * (raw[1] + raw[2]); break;
+            case 2: out[i] = 0.25 * (raw[Nh] + raw[Nh - 1]); break;
+            case -3: out[i] = 0.25 * (raw[Nh] + 2.0 * raw[1] + raw[2]); break;
+            case 3: out[i] = 0.25 * (raw[Nh - 1] + 2.0 * raw[Nh] + raw[1]); break;
+            default: break;
+            }
+        }
+    } else {
+        switch (w.bc[1]) {
+        case 1: case 4: out[1] = 0.25 * (2.0 * raw[1] + 2.0 * raw[2]); break;
+        case 2: out[1] = 0.0; break;
+        case 3: out[1] = 0.25 * (raw[Nh - 1] + 2.0 * raw[1] + raw[2]); break;
+        }
+        switch (w.bc[Nh]) {
+        case 1: case 4: out[Nh] = 0.25 * (2.0 * raw[Nh] + 2.0 * raw[Nh - 1]); break;
+        case 2: out[Nh] = 0.0; break;
+        case 3: out[Nh] = out[1]; break;
+        }
+        for (int i = 2; i <= Nx; ++i) out[i] = 0.25 * (raw[i - 1] + 2.0 * raw[i] + raw[i + 1]);
+    }
+}
+
+// ---- mod_particle.f90:15-74  type Particle ----------------------------------
+struct Species {
+    double mass = 0, q = 0, w_p = 1, q_over_m = 0, q_times_wp = 0;
+    int finalIdx = 0, T = 1, maxNodes = 0, Nx = 0;
+    dvec ps;                    // phaseSpace(4, finalIdx, T)
+    ivec N_p, delIdx, refIdx, numToCollide, refRecordIdx;
+    int refRecLen = 0;
+    dvec wallLoss, energyLoss, momentumLoss;   // (2,T)
+    dvec workSpace, densities;  // (maxNodes,T), (Nx,T), 1-based first index
+    double numFuncEvalAve = 0, numSubStepsAve = 0;
+    double accumEnergyLoss[2] = {0, 0};
+    int accumWallLoss[2] = {0, 0};
+    long long substepsDeposit = 0;   // oracle-only instrumentation: do-while trips in the last depositJ
+    long long substepsMove = 0, funcEvalsMove = 0;
+    inline double &P(int k, int i, int t) { return ps[(size_t)(k - 1) + 4 * ((size_t)(i - 1) + (size_t)finalIdx * (size_t)(t - 1))]; }
+    inline double &WS(int i, int t) { return workSpace[(size_t)i + (size_t)(maxNodes + 2) * (size_t)(t - 1)]; }
+    inline double &DN(int i, int t) { return densities[(size_t)i + (size_t)(Nx + 2) * (size_t)(t - 1)]; }
+    inline double &WL(int s, int t) { return wallLoss[(s - 1) + 2 * (t - 1)]; }
+    inline double &EL(int s, int t) { return energyLoss[(s - 1) + 2 * (t - 1)]; }
+    inline double &ML(int s, int t) { return momentumLoss[(s - 1) + 2 * (t - 1)]; }
+    long long sumNp() const { long long s = 0; for (int t = 1; t <= T; ++t) s += N_p[t]; return s; }
+    long long sumDel() const { long long s = 0; for (int t = 1; t <= T; ++t) s += delIdx[t]; return s; }
+};
+
+struct Solver {   // NGP mod_potentialSolver.f90:17-22 ; CIC :17-23
+    dvec phi, phi_f, J, rho, EField, a_tri, b_tri, c_tri;
+    double rho_const = 0, RF_rad_frequency = 0, RF_half_amplitude = 0;
+    double RF_voltage = 0, boundPhi[3] = {0, 0, 0}, sourceTermVals[3] = {0, 0, 0};  // CIC only, 1-based
+    int RF_indx = 0;
+    bool RF_bool = false;
+};
+
+struct NonLin {   // mod_nonLinSolvers.f90:29-35
+    int iterNumPicard = 0, iterNumAdaptiveSteps = 0, amountTimeSplits = 0;
+    int maxIter = 100, solverType = 0, m_Anderson = 10;
+    double Beta_k = 0.5, eps_r = 0, eps_a = 1e-8;
+    dvec Residual_k, phi_k, fitMat;   // (Nx, m+1), (Nx, m+1), (Nx, m)
+    double moverSeconds = 0, potSeconds = 0;
+    long long sweeps = 0;         // number of depositJ calls in the last solvePotential
+    long long substeps = 0;       // total do-while trips (depositJ sweeps + final moveParticles)
+    dvec normHist;                // residual norms of the last solveDivAmpereAnderson
+};
+
+struct Oracle {
+    Domain world;
+    Solver solver;
+    std::vector<Species> plist;
+    NonLin nl;
+    dvec particleTimeStep;        // CIC (Nx, nSpecies)
+    int err = 0;
+};
+
+// particle_constructor mod_particle.f90:46-74
+static void species_init(Species &s, const Domain &w, double mass, double q, double w_p, int N_p, int finalIdx) {
+    s.mass = mass; s.q = q; s.w_p = w_p; s.q_over_m = q / mass; s.q_times_wp = q * w_p;
+    s.finalIdx = finalIdx; s.T = w.T; s.Nx = w.Nx;
+    s.maxNodes = std::max(w.Nx, w.Nh);
+    s.ps.assign((size_t)4 * finalIdx * w.T, 0.0);
+    s.refRecLen = finalIdx / 10;
+    s.refRecordIdx.assign((size_t)(s.refRecLen + 1) * (w.T + 1), 0);
+    s.N_p.assign(w.T + 1, N_p); s.delIdx.assign(w.T + 1, 0); s.refIdx.assign(w.T + 1, 0);
+    s.numToCollide.assign(w.T + 1, 0);
+    s.wallLoss.assign(2 * w.T, 0.0); s.energyLoss.assign(2 * w.T, 0.0); s.momentumLoss.assign(2 * w.T, 0.0);
+    s.workSpace.assign((size_t)(s.maxNodes + 2) * w.T, 0.0);
+    s.densities.assign((size_t)(w.Nx + 2) * w.T, 0.0);
+}
+
+// initializeRandUniform mod_particle.f90:84-97
+static void initializeRandUniform(Species &s, const Domain &w, int32_t *irand) {
+#pragma omp parallel for schedule(static, 1)
+    for (int iThread = 1; iThread <= w.T; ++iThread) {
+        for (int i = 1; i <= s.N_p[iThread]; ++i) {
+            double x_pos = ran2(irand[iThread]) * w.L_domain + w.startX;
+            s.P(1, i, iThread) = getLFromX(w, x_pos);
+        }
+    }
+}
+
+// initializeRandCosine / initializeRandSine mod_particle.f90:99-151 (sine=true -> :126-151)
+static void initializeRandTrig(Species &s, const Domain &w, int32_t *irand, double alpha, bool sine) {
+#pragma omp parallel for schedule(static, 1)
+    for (int iThread = 1; iThread <= w.T; ++iThread) {
+        int32_t randNum = irand[iThread];
+        for (int i = 1; i <= s.N_p[iThread]; ++i) {
+            double R1 = ran2(randNum), R2 = ran2(randNum);
+            double val = (1.0 + alpha * (sine ? std::sin(2 * pi * R2) : std::cos(2 * pi * R2))) / (1.0 + alpha);
+            while (R1 > val) {
+                R1 = ran2(randNum); R2 = ran2(randNum);
+                val = (1.0 + alpha * (sine ? std::sin(2 * pi * R2) : std::cos(2 * pi * R2))) / (1.0 + alpha);
+            }
+            double x_pos = R2 * w.L_domain + w.startX;
+            s.P(1, i, iThread) = getLFromX(w, x_pos);
+        }
+        irand[iThread] = randNum;
+    }
+}
+
+// generate3DMaxwellian mod_particle.f90:156-191
+static void generate3DMaxwellian(Species &s, const Domain &w, double T, int32_t *irand, double alpha, int distType, double v_drift) {
+    double v_therm = std::sqrt(T * e_c / s.mass);
+#pragma omp parallel for schedule(static, 1)
+    for (int iThread = 1; iThread <= w.T; ++iThread) {
+        int32_t ir = irand[iThread];
+        for (int i = 1; i <= s.N_p[iThread]; ++i) {
+            double U1 = ran2(ir), U2 = ran2(ir), U3 = ran2(ir), U4 = ran2(ir);
+            double v_extra = 0.0, x_pos;
+            switch (distType) {
+            case 0: v_extra = v_drift; break;
+            case 1: x_pos = getXFromL(w, s.P(1, i, iThread)) / w.L_domain; v_extra = v_drift * (1.0 + alpha * std::cos(2 * pi * x_pos)); break;
+            case 2: x_pos = getXFromL(w, s.P(1, i, iThread)) / w.L_domain; v_extra = v_drift * (1.0 - alpha * std::sin(2 * pi * x_pos)); break;
+            }
+            s.P(2, i, iThread) = v_therm * std::sqrt(-2.0 * std::log(U1)) * std::cos(2.0 * pi * U2) + v_extra;
+            s.P(3, i, iThread) = v_therm * std::sqrt(-2.0 * std::log(U1)) * std::sin(2.0 * pi * U2);
+            s.P(4, i, iThread) = v_therm * std::sqrt(-2.0 * std::log(U3)) * std::sin(2.0 * pi * U4);
+        }
+        irand[iThread] = ir;
+    }
+}
+
+// getTotalKE mod_particle.f90:218-230 (thread partial sums added in thread order)
+static double getSumV2(Species &s) {
+    dvec part(s.T + 1, 0.0);
+#pragma omp parallel for schedule(static, 1)
+    for (int t = 1; t <= s.T; ++t) {
+        double r = 0.0;
+        for (int i = 1; i <= s.N_p[t]; ++i)
+            for (int k = 2; k <= 4; ++k) r += s.P(k, i, t) * s.P(k, i, t);
+        part[t] = r;
+    }
+    double res = 0.0;
+    for (int t = 1; t <= s.T; ++t) res += part[t];
+    return res;
+}
+static double getTotalKE(Species &s) { return getSumV2(s) * s.mass * 0.5 * s.w_p; }
+// getKEAve :193-204
+static double getKEAve(Species &s) { return getSumV2(s) * s.mass * 0.5 / e_c / (double)s.sumNp(); }
+// getTotalMomentum :206-216
+static void getTotalMomentum(Species &s, double res[3]) {
+    double tmp[3] = {0, 0, 0};
+    for (int t = 1; t <= s.T; ++t) {
+        double a[3] = {0, 0, 0};
+        for (int i = 1; i <= s.N_p[t]; ++i)
+            for (int k = 0; k < 3; ++k) a[k] += s.P(k + 2, i, t);
+        for (int k = 0; k < 3; ++k) tmp[k] += a[k];
+    }
+    for (int k = 0; k < 3; ++k) res[k] = tmp[k] * s.w_p * s.mass;
+}
+
+// ---- potentialSolver constructor: NGP mod_potentialSolver.f90:50-86 ; CIC :49-90
+static void construct_diagMatrix(Oracle &o);
+static int solver_init(Oracle &o, double leftV, double rightV, double RF_frequency, double timeCurrent) {
+    Domain &w = o.world; Solver &s = o.solver;
+    const int Nx = w.Nx, Nh = w.Nh;
+    s.J.assign(Nh + 2, 0.0); s.rho.assign(Nx + 2, 0.0); s.phi.assign(Nx + 2, 0.0); s.phi_f.assign(Nx + 2, 0.0);
+    s.EField.assign(Nh + 2, 0.0);
+    s.a_tri.assign(std::max(Nx, Nh) + 2, 0.0); s.b_tri.assign(Nx + 2, 0.0); s.c_tri.assign(std::max(Nx, Nh) + 2, 0.0);
+    s.rho_const = 0.0; s.RF_half_amplitude = 0.0;
+    s.RF_rad_frequency = 2.0 * pi * RF_frequency;
+    if (w.scheme == 0) {
+        construct_diagMatrix(o);
+        if (w.bc[1] == 1) s.phi[1] = leftV;
+        if (w.bc[1] == 4) { s.RF_half_amplitude = leftV; s.phi[1] = s.RF_half_amplitude * std::sin(timeCurrent * s.RF_rad_frequency); }
+        if (w.bc[Nx] == 1) s.phi[Nx] = rightV;
+        if (w.bc[Nx] == 4) {
+            if (s.RF_half_amplitude != 0) return 1;   // two RF boundaries -> stop
+            s.RF_half_amplitude = rightV;
+            s.phi[Nx] = s.RF_half_amplitude * std::sin(timeCurrent * s.RF_rad_frequency);
+        }
+        if (w.bc[1] == 3) { s.phi[1] = leftV; s.phi[Nx] = leftV; }
+        s.RF_bool = s.RF_rad_frequency > 0 && s.RF_half_amplitude > 0 && (w.bc[1] == 4 || w.bc[Nx] == 4);
+        s.phi_f = s.phi;
+    } else {
+        s.boundPhi[1] = s.boundPhi[2] = 0.0; s.sourceTermVals[1] = s.sourceTermVals[2] = 0.0;
+        s.RF_voltage = 0.0;   // (uninitialised in the reference when no RF wall; never read then)
+        if (w.bc[1] == 1) { s.boundPhi[1] = leftV; s.sourceTermVals[1] = -s.boundPhi[1] * 2.0 / w.dx_dl[1]; }
+        else if (w.bc[1] == 4) { s.RF_half_amplitude = leftV; s.RF_voltage = s.RF_half_amplitude * std::sin(timeCurrent * s.RF_rad_frequency); s.RF_indx = 1; }
+        if (w.bc[Nh] == 1) { s.boundPhi[2] = rightV; s.sourceTermVals[2] = -s.boundPhi[2] * 2.0 / w.dx_dl[Nx]; }
+        else if (w.bc[Nh] == 4) { s.RF_half_amplitude = rightV; s.RF_voltage = s.RF_half_amplitude * std::sin(timeCurrent * s.RF_rad_frequency); s.RF_indx = 2; }
+        s.RF_bool = s.RF_rad_frequency > 0 && s.RF_half_amplitude > 0 && (w.bc[1] == 4 || w.bc[Nh] == 4);
+        construct_diagMatrix(o);
+    }
+    return 0;
+}
+
+// construct_diagMatrix: NGP :88-128 ; CIC :92-126
+static void construct_diagMatrix(Oracle &o) {
+    Domain &w = o.world; Solver &s = o.solver;
+    const int Nx = w.Nx;
+    std::fill(s.a_tri.begin(), s.a_tri.end(), 0.0);
+    std::fill(s.b_tri.begin(), s.b_tri.end(), 0.0);
+    std::fill(s.c_tri.begin(), s.c_tri.end(), 0.0);
+    if (w.scheme == 0) {
+        for (int i = 1; i <= Nx; ++i) {
+            switch (w.bc[i]) {
+            case 0:
+                if (i < Nx) s.c_tri[i] = 1.0 / w.dx_dl[i];
+                if (i > 1) s.a_tri[i - 1] = 1.0 / w.dx_dl[i - 1];
+                s.b_tri[i] = -(1.0 / w.dx_dl[i - 1] + 1.0 / w.dx_dl[i]);
+                break;
+            case 1: case 4: s.b_tri[i] = 1.0; break;
+            case 2:
+                if (i == 1) { s.c_tri[i] = 2.0 / w.dx_dl[i]; s.b_tri[i] = -(2.0 / w.dx_dl[i]); }
+                else if (i == Nx) { s.a_tri[i - 1] = 2.0 / w.dx_dl[i - 1]; s.b_tri[i] = -(2.0 / w.dx_dl[i - 1]); }
+                else o.err = 10;
+                break;
+            case 3: s.b_tri[i] = 1.0; break;
+            default: break;
+            }
+        }
+    } else {
+        for (int i = 1; i <= Nx; ++i) {
+            switch (w.bc[i + 1] - w.bc[i]) {
+            case 0:
+                s.b_tri[i] = -2.0 * (1.0 / (w.dx_dl[i - 1] + w.dx_dl[i]) + 1.0 / (w.dx_dl[i + 1] + w.dx_dl[i]));
+                s.a_tri[i - 1] = 2.0 / (w.dx_dl[i - 1] + w.dx_dl[i]);
+                s.c_tri[i] = 2.0 / (w.dx_dl[i] + w.dx_dl[i + 1]);
+                break;
+            case -1: case -4: case -3:
+                s.b_tri[i] = -2.0 * (1.0 / (w.dx_dl[i + 1] + w.dx_dl[i]) + 1.0 / w.dx_dl[i]);
+                s.c_tri[i] = 2.0 / (w.dx_dl[i + 1] + w.dx_dl[i]);
+                s.sourceTermVals[1] = -s.boundPhi[1] * 2.0 / w.dx_dl[1];
+                break;
+            case 1: case 4: case 3:
+                s.b_tri[i] = -2.0 * (1.0 / (w.dx_dl[i - 1] + w.dx_dl[i]) + 1.0 / w.dx_dl[i]);
+                s.a_tri[i - 1] = 2.0 / (w.dx_dl[i - 1] + w.dx_dl[i]);
+                s.sourceTermVals[2] = -s.boundPhi[2] * 2.0 / w.dx_dl[Nx];
+                break;
+            case -2:
+                s.b_tri[i] = -2.0 / (w.dx_dl[i + 1] + w.dx_dl[i]);
+                s.c_tri[i] = 2.0 / (w.dx_dl[i + 1] + w.dx_dl[i]);
+                break;
+            case 2:
+                s.b_tri[i] = -2.0 / (w.dx_dl[i - 1] + w.dx_dl[i]);
+                s.a_tri[i - 1] = 2.0 / (w.dx_dl[i - 1] + w.dx_dl[i]);
+                break;
+            }
+        }
+    }
+}
+
+// interpolateParticleToNodes: NGP mod_Scheme.f90:50-65 ; CIC mod_Scheme.f90:21-66
+static void interpolateParticleToNodes(Species &p, const Domain &w, int t) {
+    if (w.scheme == 0) {
+        for (int j = 1; j <= p.N_p[t]; ++j) {
+            double l = p.P(1, j, t);
+            int l_left = (int)l, l_right = l_left + 1;
+            double d = l - (double)l_left;
+            p.DN(l_left, t) += (1.0 - d);
+            p.DN(l_right, t) += d;
+        }
+    } else {
+        const int Nx = w.Nx;
+        for (int j = 1; j <= p.N_p[t]; ++j) {
+            double l = p.P(1, j, t);
+            int lc = (int)l; double d = l - (double)lc;
+            p.DN(lc, t) += (-d * d + d + 0.5);
+            int lr = lc + 1, ll = lc - 1;
+            switch (w.bc[lr] - w.bc[lc]) {
+            case 0: p.DN(ll, t) += 0.5 * (1.0 - d) * (1.0 - d); p.DN(lr, t) += 0.5 * d * d; break;
+            case -1: case -4: p.DN(lc, t) -= 0.5 * (1.0 - d) * (1.0 - d); p.DN(lr, t) += 0.5 * d * d; break;
+            case 1: case 4: p.DN(lc, t) -= 0.5 * d * d; p.DN(ll, t) += 0.5 * (1.0 - d) * (1.0 - d); break;
+            case -2: p.DN(lc, t) += 0.5 * (1.0 - d) * (1.0 - d); p.DN(lr, t) += 0.5 * d * d; break;
+            case 2: p.DN(lc, t) += 0.5 * d * d; p.DN(ll, t) += 0.5 * (1.0 - d) * (1.0 - d); break;
+            case -3: p.DN(Nx, t) += 0.5 * (1.0 - d) * (1.0 - d); p.DN(lr, t) += 0.5 * d * d; break;
+            case 3: p.DN(ll, t) += 0.5 * (1.0 - d) * (1.0 - d); p.DN(1, t) += 0.5 * d * d; break;
+            }
+        }
+    }
+}
+
+// cross-thread sliced reduction of a per-thread grid copy, species-ordered scaling
+// (NGP mod_particleMover.f90:145-149, mod_potentialSolver.f90:145-149; CIC twins)
+template <class GET>
+static void reduce_slices(Oracle &o, int nSlices, const ivec &L, const ivec &R, GET get) {
+    const int T = o.world.T, nS = (int)o.plist.size();
+#pragma omp parallel for schedule(static, 1)
+    for (int it = 1; it <= T; ++it) {
+        if (it <= nSlices) {
+            for (int i = L[it]; i <= R[it]; ++i) {
+                double s = 0.0;
+                for (int t = 1; t <= T; ++t) s += get(o.plist[0], i, t);
+                double acc = s * o.plist[0].q_times_wp;
+                for (int j = 1; j < nS; ++j) {
+                    double sj = 0.0;
+                    for (int t = 1; t <= T; ++t) sj += get(o.plist[j], i, t);
+                    acc = acc + sj * o.plist[j].q_times_wp;
+                }
+                get(o.plist[0], i, 1) = acc;
+            }
+        }
+    }
+}
+
+// depositRho: NGP mod_potentialSolver.f90:130-188 ; CIC :128-173
+static void depositRho(Oracle &o) {
+    Domain &w = o.world; Solver &s = o.solver;
+    const int Nx = w.Nx, Nh = w.Nh, T = w.T;
+#pragma omp parallel for schedule(static, 1)
+    for (int it = 1; it <= T; ++it) {
+        for (auto &p : o.plist) {
+            for (int i = 0; i <= Nx + 1; ++i) p.DN(i, it) = 0.0;
+            interpolateParticleToNodes(p, w, it);
+        }
+    }
+    reduce_slices(o, w.nTN, w.tnL, w.tnR, [](Species &p, int i, int t) -> double & { return p.DN(i, t); });
+    Species &p1 = o.plist[0];
+    auto D = [&](int i) -> double & { return p1.DN(i, 1); };
+    if (w.scheme == 0) {
+        switch (w.bc[1]) {
+        case 1: case 4: D(1) = 0.0; break;
+        case 2: D(1) = 2.0 * D(1); break;
+        case 3: D(1) = D(1) + D(Nx); break;
+        }
+        switch (w.bc[Nx]) {
+        case 1: case 4: D(Nx) = 0.0; break;
+        case 2: D(Nx) = 2.0 * D(Nx); break;
+        case 3: D(Nx) = D(1); break;
+        }
+        if (w.smooth) {
+            for (int i = 1; i <= Nx; ++i) {
+                switch (w.bc[i]) {
+                case 0: s.rho[i] = 0.25 * (D(i - 1) + 2.0 * D(i) + D(i + 1)); break;
+                case 1: case 4: s.rho[i] = 0.0; break;
+                case 2:
+                    if (i == 1) s.rho[i] = 0.25 * (2.0 * D(1) + 2.0 * D(2));
+                    else s.rho[i] = 0.25 * (2.0 * D(Nx) + 2.0 * D(Nh));
+                    break;
+                case 3: s.rho[i] = 0.25 * (D(Nh) + 2.0 * D(1) + D(2)); break;
+                }
+            }
+        } else {
+            for (int i = 1; i <= Nx; ++i) s.rho[i] = D(i);
+        }
+    } else {
+        if (w.smooth) {
+            for (int i = 1; i <= Nx; ++i) {
+                switch (w.bc[i + 1] - w.bc[i]) {
+                case 0: s.rho[i] = 0.25 * (D(i - 1) + 2.0 * D(i) + D(i + 1)); break;
+                case -1: case -4: s.rho[i] = 0.25 * (D(1) + D(2)); break;
+                case 1: case 4: s.rho[i] = 0.25 * (D(Nx) + D(Nx - 1)); break;
+                case -2: s.rho[i] = 0.25 * (3.0 * D(1) + D(2)); break;
+                case 2: s.rho[i] = 0.25 * (3.0 * D(Nx) + D(Nx - 1)); break;
+                case -3: s.rho[i] = 0.25 * (D(Nx) + 2.0 * D(1) + D(2)); break;
+                case 3: s.rho[i] = 0.25 * (D(1) + 2.0 * D(Nx) + D(Nx - 1)); break;
+                }
+            }
+        } else {
+            for (int i = 1; i <= Nx; ++i) s.rho[i] = D(i);
+        }
+    }
+}
+
+// Thomas sweep shared by Poisson/Ampere (NGP :203-221, :308-328 ; CIC :192-210, :282-299)
+static void thomas(const Solver &s, int Nx, const dvec &d, dvec &x) {
+    dvec cp(Nx + 2), dp(Nx + 2);
+    cp[1] = s.c_tri[1] / s.b_tri[1];
+    dp[1] = d[1] / s.b_tri[1];
+    for (int i = 2; i <= Nx - 1; ++i) {
+        double m = s.b_tri[i] - cp[i - 1] * s.a_tri[i - 1];
+        cp[i] = s.c_tri[i] / m;
+        dp[i] = (d[i] - dp[i - 1] * s.a_tri[i - 1]) / m;
+    }
+    double m = s.b_tri[Nx] - cp[Nx - 1] * s.a_tri[Nx - 1];
+    dp[Nx] = (d[Nx] - dp[Nx - 1] * s.a_tri[Nx - 1]) / m;
+    x[Nx] = dp[Nx];
+    for (int i = Nx - 1; i >= 1; --i) x[i] = dp[i] - cp[i] * x[i + 1];
+}
+
+// solve_tridiag_Poisson: NGP :190-226 ; CIC :175-218
+static void solve_tridiag_Poisson(Oracle &o, double timeCurrent) {
+    Domain &w = o.world; Solver &s = o.solver;
+    const int Nx = w.Nx;
+    dvec d(Nx + 2, 0.0);
+    if (w.scheme == 0) {
+        for (int i = 1; i <= Nx; ++i) {
+            switch (w.bc[i]) {
+            case 0: case 2: d[i] = (-s.rho[i] - s.rho_const) / eps_0; break;
+            case 1: case 3: d[i] = s.phi[i]; break;
+            case 4: d[i] = s.RF_half_amplitude * std::sin(s.RF_rad_frequency * timeCurrent); break;
+            }
+        }
+    } else {
+        if (s.RF_bool) {
+            if (s.RF_indx == 1) { s.boundPhi[1] = s.RF_half_amplitude * std::sin(s.RF_rad_frequency * timeCurrent); s.sourceTermVals[1] = -s.boundPhi[1] * 2.0 / w.dx_dl[1]; }
+            else { s.boundPhi[2] = s.RF_half_amplitude * std::sin(s.RF_rad_frequency * timeCurrent); s.sourceTermVals[2] = -s.boundPhi[2] * 2.0 / w.dx_dl[Nx]; }
+        }
+        for (int i = 1; i <= Nx; ++i) d[i] = (-s.rho[i] - s.rho_const) / eps_0;
+        d[1] = d[1] + s.sourceTermVals[1];
+        d[Nx] = d[Nx] + s.sourceTermVals[2];
+    }
+    thomas(s, Nx, d, s.phi);
+    s.phi_f = s.phi;
+}
+
+// triMul mod_BasicFunctions.f90:205-216
+static void triMul(int n, const dvec &lo, const dvec &up, const dvec &di, const dvec &x, dvec &res) {
+    res[1] = x[1] * di[1] + x[2] * up[1];
+    for (int i = 2; i <= n - 1; ++i) res[i] = x[i] * di[i] + x[i - 1] * lo[i - 1] + x[i + 1] * up[i];
+    res[n] = x[n] * di[n] + x[n - 1] * lo[n - 1];
+}
+
+// getError_tridiag_Poisson: NGP :240-265 ; CIC :232-244
+static double getError_tridiag_Poisson(Oracle &o) {
+    Domain &w = o.world; Solver &s = o.solver;
+    const int Nx = w.Nx;
+    dvec Ax(Nx + 2, 0.0);
+    triMul(Nx, s.a_tri, s.c_tri, s.b_tri, s.phi_f, Ax);
+    double res = 0.0;
+    if (w.scheme == 0) {
+        for (int i = 1; i <= Nx; ++i) {
+            switch (w.bc[i]) {
+            case 0: case 2:
+                if (s.rho[i] + s.rho_const != 0) { double v = Ax[i] * eps_0 / (-s.rho[i] - s.rho_const) - 1.0; res += v * v; }
+                else { double v = Ax[i] * eps_0; res += v * v; }
+                break;
+            case 1: case 3: case 4:
+                if (s.phi_f[i] != 0) { double v = Ax[i] / s.phi_f[i] - 1.0; res += v * v; }
+                else res += Ax[i] * Ax[i];
+                break;
+            }
+        }
+        return std::sqrt(res / Nx);
+    }
+    dvec d(Nx + 2);
+    for (int i = 1; i <= Nx; ++i) d[i] = (-s.rho[i] - s.rho_const) / eps_0;
+    d[1] += s.sourceTermVals[1]; d[Nx] += s.sourceTermVals[2];
+    for (int i = 1; i <= Nx; ++i) { double v = 1.0 - Ax[i] / d[i]; res += v * v; }
+    return std::sqrt(res / Nx);
+}
+
+// makeConstSourceTerm: NGP :267-286 ; CIC :246-270
+static void makeConstSourceTerm(Oracle &o) {
+    Domain &w = o.world; Solver &s = o.solver;
+    const int Nx = w.Nx;
+    if (w.scheme == 0) {
+        for (int i = 1; i <= Nx; ++i) {
+            switch (w.bc[i]) {
+            case 0: s.rho[i] = -(s.phi[i] - s.phi[i - 1]) / w.dx_dl[i - 1] + (s.phi[i + 1] - s.phi[i]) / w.dx_dl[i]; break;
+            case 1: case 3: case 4: s.rho[i] = s.phi_f[i]; break;
+            case 2:
+                if (i == 1) s.rho[i] = -2.0 * (s.phi[i] - s.phi[i + 1]) / w.dx_dl[i];
+                else if (i == Nx) s.rho[i] = -2.0 * (s.phi[i] - s.phi[i - 1]) / w.dx_dl[i - 1];
+                break;
+            }
+        }
+    } else {
+        for (int i = 1; i <= Nx; ++i) {
+            switch (w.bc[i + 1] - w.bc[i]) {
+            case 0: s.rho[i] = -(s.phi[i] - s.phi[i + 1]) / (w.grid[i + 1] - w.grid[i]) + (s.phi[i - 1] - s.phi[i]) / (w.grid[i] - w.grid[i - 1]); break;
+            case -1: case -4: s.rho[i] = -(s.phi[i] - s.phi[i + 1]) / (w.grid[i + 1] - w.grid[i]) + 2.0 * (s.boundPhi[1] - s.phi[1]) / w.dx_dl[1] + s.sourceTermVals[1]; break;
+            case 1: case 4: s.rho[i] = -2.0 * (s.phi[Nx] - s.boundPhi[2]) / w.dx_dl[Nx] + (s.phi[i - 1] - s.phi[i]) / (w.grid[i] - w.grid[i - 1]) + s.sourceTermVals[2]; break;
+            case -2: s.rho[i] = -(s.phi[i] - s.phi[i + 1]) / (w.grid[i + 1] - w.grid[i]); break;
+            case 2: s.rho[i] = (s.phi[i - 1] - s.phi[i]) / (w.grid[i] - w.grid[i - 1]); break;
+            case -3: s.rho[i] = -(s.phi[i] - s.phi[i + 1]) / (w.grid[i + 1] - w.grid[i]) + 2.0 * (s.phi[Nx] - s.phi[1]) / (w.dx_dl[1] + w.dx_dl[Nx]); break;
+            case 3: s.rho[i] = -2.0 * (s.phi[Nx] - s.phi[1]) / (w.dx_dl[1] + w.dx_dl[Nx]) + (s.phi[i - 1] - s.phi[i]) / (w.grid[i] - w.grid[i - 1]); break;
+            }
+        }
+    }
+}
+
+// solve_tridiag_Ampere: NGP :288-330 ; CIC :272-301
+static void solve_tridiag_Ampere(Oracle &o, double del_t) {
+    Domain &w = o.world; Solver &s = o.solver;
+    const int Nx = w.Nx;
+    dvec d(Nx + 2, 0.0);
+    if (w.scheme == 0) {
+        for (int i = 1; i <= Nx; ++i) {
+            switch (w.bc[i]) {
+            case 0: d[i] = (s.J[i] - s.J[i - 1]) * del_t / eps_0; break;
+            case 1: case 3: case 4: d[i] = 0.0; break;
+            case 2:
+                if (i == 1) d[i] = 2.0 * (del_t * s.J[i] / eps_0);
+                else if (i == Nx) d[i] = 2.0 * (-del_t * s.J[i - 1] / eps_0);
+                break;
+            }
+            d[i] = d[i] + s.rho[i];
+        }
+    } else {
+        for (int i = 1; i <= Nx; ++i) d[i] = (s.J[i + 1] - s.J[i]) * del_t / eps_0 + s.rho[i];
+    }
+    thomas(s, Nx, d, s.phi_f);
+}
+
+// getChargeContinuityError: NGP :358-390 ; CIC :315-331
+static double getChargeContinuityError(Oracle &o, const double *rho_i /*1-based*/, double del_t) {
+    Domain &w = o.world; Solver &s = o.solver;
+    const int Nx = w.Nx, Nh = w.Nh;
+    double ce = 0.0; int k = 0;
+    for (int i = 1; i <= Nx; ++i) {
+        double dR = s.rho[i] - rho_i[i];
+        if (dR != 0) {
+            if (w.scheme == 0) {
+                switch (w.bc[i]) {
+                case 0: { double v = 1.0 + del_t * (s.J[i] - s.J[i - 1]) / dR; ce += v * v; k++; break; }
+                case 1: case 4: break;
+                case 2:
+                    if (i == 1) { double v = 1.0 + 2.0 * del_t * s.J[1] / dR; ce += v * v; }
+                    else { double v = 1.0 - 2.0 * del_t * s.J[Nh] / dR; ce += v * v; }
+                    k++; break;
+                case 3:
+                    if (i == 1) { double v = 1.0 + del_t * (s.J[1] - s.J[Nh]) / dR; ce += v * v; }
+                    break;
+                }
+            } else {
+                double v = 1.0 + del_t * (s.J[i + 1] - s.J[i]) / dR; ce += v * v; k++;
+            }
+        }
+    }
+    return std::sqrt(ce / k);
+}
+
+// makeHalfTimeEField: NGP :392-406 ; CIC :333-366
+static void makeHalfTimeEField(Oracle &o, double *work /*1-based, Nh*/) {
+    Domain &w = o.world; Solver &s = o.solver;
+    const int Nx = w.Nx, Nh = w.Nh;
+    if (w.scheme == 0) {
+        for (int i = 1; i <= Nh; ++i) work[i] = 0.5 * (s.phi_f[i] + s.phi[i] - s.phi_f[i + 1] - s.phi[i + 1]);
+        if (w.smooth) {
+            smoothField(w, work, s.EField.data());
+            for (int i = 1; i <= Nh; ++i) s.EField[i] = s.EField[i] / w.dx_dl[i];
+        } else {
+            for (int i = 1; i <= Nh; ++i) s.EField[i] = work[i] / w.dx_dl[i];
+        }
+    } else {
+        switch (w.bc[1]) {
+        case 1: work[1] = (2.0 * s.boundPhi[1] - s.phi[1] - s.phi_f[1]); break;
+        case 2: work[1] = 0.0; break;
+        case 3: work[1] = 0.5 * (s.phi[Nx] + s.phi_f[Nx] - s.phi[1] - s.phi_f[1]); break;
+        case 4: work[1] = (s.boundPhi[1] + s.RF_voltage - s.phi[1] - s.phi_f[1]); break;
+        }
+        switch (w.bc[Nh]) {
+        case 1: work[Nh] = s.phi[Nx] + s.phi_f[Nx] - 2.0 * s.boundPhi[2]; break;
+        case 2: work[Nh] = 0.0; break;
+        case 3: work[Nh] = work[1]; break;
+        case 4: work[Nh] = s.phi[Nx] + s.phi_f[Nx] - s.boundPhi[2] - s.RF_voltage; break;
+        }
+        for (int i = 2; i <= Nx; ++i) work[i] = 0.5 * (s.phi_f[i - 1] + s.phi[i - 1] - s.phi_f[i] - s.phi[i]);
+        if (w.smooth) smoothField(w, work, s.EField.data());
+        else for (int i = 1; i <= Nh; ++i) s.EField[i] = work[i];
+    }
+}
+
+// getTotalPE: NGP :408-420 ; CIC :369-413
+static double getTotalPE(Oracle &o, bool future) {
+    Domain &w = o.world; Solver &s = o.solver;
+    const int Nx = w.Nx, Nh = w.Nh;
+    const dvec &ph = future ? s.phi_f : s.phi;
+    double sum = 0.0;
+    if (w.scheme == 0) {
+        for (int i = 1; i <= Nh; ++i) { double dphi = ph[i + 1] - ph[i]; sum += dphi * dphi / w.dx_dl[i]; }
+        return 0.5f * eps_0 * sum;   // literal 0.5 is default-real in the Fortran; exactly representable
+    }
+    for (int i = 1; i <= Nx - 1; ++i) { double dphi = ph[i + 1] - ph[i]; sum += dphi * dphi / (w.grid[i + 1] - w.grid[i]); }
+    double res = 0.5f * eps_0 * sum;
+    if (future) {
+        switch (w.bc[1]) {
+        case 1: res += eps_0 * (s.boundPhi[1] - ph[1]) * (s.boundPhi[1] - ph[1]) / w.dx_dl[1]; break;
+        case 3: res += eps_0 * (ph[Nx] - ph[1]) * (ph[Nx] - ph[1]) / (w.dx_dl[1] + w.dx_dl[Nx]); break;
+        case 4: res += eps_0 * (s.RF_voltage - ph[1]) * (s.RF_voltage - ph[1]) / w.dx_dl[1]; break;
+        }
+        switch (w.bc[Nh]) {
+        case 1: res += eps_0 * (s.boundPhi[2] - ph[Nx]) * (s.boundPhi[2] - ph[Nx]) / w.dx_dl[Nx]; break;
+        case 4: res += eps_0 * (s.RF_voltage - ph[Nx]) * (s.RF_voltage - ph[Nx]) / w.dx_dl[Nx]; break;
+        }
+    } else {
+        switch (w.bc[1]) {
+        case 1: case 4: res += eps_0 * (s.boundPhi[1] - ph[1]) * (s.boundPhi[1] - ph[1]) / w.dx_dl[1]; break;
+        case 3: res += eps_0 * (ph[Nx] - ph[1]) * (ph[Nx] - ph[1]) / (w.dx_dl[1] + w.dx_dl[Nx]); break;
+        }
+        switch (w.bc[Nh]) {
+        case 1: case 4: res += eps_0 * (s.boundPhi[2] - ph[Nx]) * (s.boundPhi[2] - ph[Nx]) / w.dx_dl[Nx]; break;
+        }
+    }
+    return res;
+}
+
+// getJdotE: NGP :422-430 ; CIC :415-426
+static double getJdotE(Oracle &o, double del_t) {
+    Domain &w = o.world; Solver &s = o.solver;
+    double res = 0.0;
+    if (w.scheme == 0) {
+        for (int i = 1; i <= w.Nh; ++i) res += s.EField[i] * w.dx_dl[i] * s.J[i];
+        return res * del_t;
+    }
+    for (int i = 2; i <= w.Nx; ++i) res += s.J[i] * s.EField[i];
+    res = res + 0.5 * s.J[1] * s.EField[1] + s.J[w.Nh] * s.EField[w.Nh] * 0.5;
+    return res * del_t;
+}
+
+// getEnergyFromBoundary: NGP :432-442 ; CIC :428-456
+static double getEnergyFromBoundary(Oracle &o, double del_t) {
+    Domain &w = o.world; Solver &s = o.solver;
+    const int Nx = w.Nx, Nh = w.Nh;
+    if (w.scheme == 0) {
+        double res = del_t * s.J[1];
+        res = res + eps_0 * ((s.phi_f[1] - s.phi_f[2]) - (s.phi[1] - s.phi[2])) / w.dx_dl[1];
+        res = res * (s.phi_f[1] + s.phi[1] - s.phi_f[Nx] - s.phi[Nx]) * 0.5;
+        return res;
+    }
+    double lA = 0, rA = 0;
+    switch (w.bc[1]) { case 1: lA = s.boundPhi[1]; break; case 2: case 3: lA = 0; break; case 4: lA = 0.5 * (s.RF_voltage + s.boundPhi[1]); break; }
+    switch (w.bc[Nh]) { case 1: rA = s.boundPhi[2]; break; case 2: case 3: rA = 0; break; case 4: rA = 0.5 * (s.RF_voltage + s.boundPhi[2]); break; }
+    double res = del_t * s.J[2] + eps_0 * ((s.phi_f[1] - s.phi_f[2]) - (s.phi[1] - s.phi[2])) / (w.grid[2] - w.grid[1]);
+    return res * (lA - rA);
+}
+
+// setRFVoltage: NGP :444-453 ; CIC :458-470
+static void setRFVoltage(Oracle &o, double timeFuture) {
+    Domain &w = o.world; Solver &s = o.solver;
+    if (w.scheme == 0) {
+        if (w.bc[1] == 4) s.phi_f[1] = s.RF_half_amplitude * std::sin(s.RF_rad_frequency * timeFuture);
+        else s.phi_f[w.Nx] = s.RF_half_amplitude * std::sin(s.RF_rad_frequency * timeFuture);
+    } else {
+        s.RF_voltage = s.RF_half_amplitude * std::sin(s.RF_rad_frequency * timeFuture);
+        if (s.RF_indx == 1) s.sourceTermVals[1] = -s.RF_voltage * 2.0 / w.dx_dl[1];
+        else s.sourceTermVals[2] = -s.RF_voltage * 2.0 / w.dx_dl[w.Nx];
+    }
+}
+
+// resetVoltage: NGP :455-459 ; CIC :472-478
+static void resetVoltage(Oracle &o) {
+    Solver &s = o.solver;
+    s.phi = s.phi_f;
+    if (o.world.scheme == 1 && s.RF_bool) s.boundPhi[s.RF_indx] = s.RF_voltage;
+}
+
+// ---- NGP particleSubStepNoBField  OpenMP/NGP/src/mod_particleMover.f90:21-63 --
+static inline void particleSubStepNoBField(double l_sub, double v_sub, double &l_f, double &v_f, double &del_tau, double E_x,
+                                           double q_over_m, double dx_dl, int l_cell, bool &FutureAtBoundaryBool, int &l_boundary) {
+    double a = q_over_m * E_x;
+    v_f = v_sub + a * del_tau;
+    l_f = l_sub + 0.5 * (v_sub + v_f) * del_tau / dx_dl;
+    bool inCellBool = ((int)l_f == l_cell);
+    bool equalVSignBool = ((v_sub > 0) == (v_f > 0));
+    FutureAtBoundaryBool = (!inCellBool) || (!equalVSignBool);
+    if (FutureAtBoundaryBool) {
+        if (v_sub > 0) l_boundary = l_cell + 1; else l_boundary = l_cell;
+        double diff_PE = 2.0 * a * ((double)l_boundary - l_sub) * dx_dl;
+        double v_i_sqr = v_sub * v_sub;
+        FutureAtBoundaryBool = (diff_PE > -v_i_sqr);
+        if (FutureAtBoundaryBool) {
+            l_f = (double)l_boundary;
+            v_f = fsign(1.0, v_sub) * std::sqrt(diff_PE + v_i_sqr);
+            del_tau = (v_f - v_sub) / a;
+        } else if (!inCellBool) {
+            FutureAtBoundaryBool = true;
+            l_boundary = 2 * l_cell + 1 - l_boundary;
+            l_f = (double)l_boundary;
+            diff_PE = 2.0 * a * (l_f - l_sub) * dx_dl;
+            v_f = -fsign(1.0, v_sub) * std::sqrt(diff_PE + v_i_sqr);
+            del_tau = (v_f - v_sub) / a;
+        }
+    }
+}
+
+// ---- CIC particleSubStepPicard  OpenMP/CIC/src/mod_particleMoverPicard.f90:17-65
+static inline void particleSubStepPicard(double l_sub, double v_sub, double &l_f, double &v_f, double &d_half, double &del_tau,
+                                         double E_left, double E_right, double dx_dl, double q_over_m, int l_cell,
+                                         bool &FutureAtBoundaryBool, int &l_boundary, int &numIter) {
+    const int maxPartIter = 50;
+    double accel = 0, v_half = 0, l_f_prev = l_sub;
+    int i;
+    for (i = 1; i <= maxPartIter; ++i) {
+        d_half = (l_sub + l_f_prev) * 0.5;
+        accel = q_over_m * (E_left * (1.0 - d_half) + E_right * d_half);
+        v_half = v_sub + 0.5 * accel * del_tau / dx_dl;
+        l_f = l_sub + v_half * del_tau / dx_dl;
+        FutureAtBoundaryBool = ((l_f <= 0) || (l_f >= 1));
+        if (FutureAtBoundaryBool) { if (v_half < 0) l_f = 0.0; else l_f = 1.0; }
+        if (std::fabs(l_f - l_f_prev) < 1.e-10) break;
+        l_f_prev = l_f;
+    }
+    numIter = i;   // Fortran: loop variable is maxPartIter+1 after an exhausted loop
+    if (!FutureAtBoundaryBool) {
+        v_f = 2.0 * v_half - v_sub;
+    } else {
+        if (l_f != l_sub) {
+            v_f = fsign(1.0, v_half) * std::sqrt(2.0 * accel * (l_f - l_sub) + v_sub * v_sub);
+            del_tau = (l_f - l_sub) * dx_dl / v_half;
+            numIter = numIter + 1;
+        } else {
+            del_tau = -2.0 * v_sub * dx_dl / accel;
+            v_f = -v_sub;
+        }
+        l_boundary = (int)l_f + l_cell;
+    }
+    l_f = l_f + (double)l_cell;
+}
+
+// CIC per-cell sub-step cap table  mod_particleMoverPicard.f90:92-94, 212-214
+static void makeParticleTimeStep(Oracle &o) {
+    Domain &w = o.world; Solver &s = o.solver;
+    const int Nx = w.Nx, nS = (int)o.plist.size();
+    o.particleTimeStep.resize((size_t)(Nx + 2) * nS);
+    for (int j = 0; j < nS; ++j)
+        for (int i = 1; i <= Nx; ++i)
+            o.particleTimeStep[(size_t)i + (size_t)(Nx + 2) * j] =
+                0.1 * w.dx_dl[i] / std::sqrt(std::fabs(o.plist[j].q_over_m * (s.EField[i] - s.EField[i + 1])));
+}
+
+// depositJ: NGP mod_particleMover.f90:67-157 ; CIC mod_particleMoverPicard.f90:77-195
+static void depositJ(Oracle &o, double del_t) {
+    Domain &w = o.world; Solver &s = o.solver;
+    const int Nx = w.Nx, Nh = w.Nh, T = w.T, nS = (int)o.plist.size();
+    const bool cic = (w.scheme == 1);
+    const double f_tol = del_t * (cic ? 1.e-10 : 1.e-15);
+    const int NB = cic ? Nh : Nx;   // wall index on the right
+    makeHalfTimeEField(o, &o.plist[0].WS(0, 1));
+    if (cic) makeParticleTimeStep(o);
+    for (auto &p : o.plist) p.substepsDeposit = 0;
+#pragma omp parallel for schedule(static, 1)
+    for (int iThread = 1; iThread <= T; ++iThread) {
+        for (int j = 0; j < nS; ++j) {
+            Species &p = o.plist[j];
+            long long trips = 0;
+            for (int i = 1; i <= Nh; ++i) p.WS(i, iThread) = 0.0;
+            const double *pts = cic ? &o.particleTimeStep[(size_t)(Nx + 2) * j] : nullptr;
+            for (int i = 1; i <= p.N_p[iThread]; ++i) {
+                double v_sub = p.P(2, i, iThread), l_sub = p.P(1, i, iThread);
+                double timePassed = 0.0, l_f = 0, v_f = 0, d_half = 0;
+                int l_cell = (int)(l_sub + fsign(1.e-12, v_sub));
+                double del_tau = del_t;
+                bool atB = false; int l_boundary = 0, numIter = 0;
+                while (del_tau > f_tol) {
+                    ++trips;
+                    double dx = w.dx_dl[l_cell];
+                    if (!cic) {
+                        double E_x = s.EField[l_cell];
+                        particleSubStepNoBField(l_sub, v_sub, l_f, v_f, del_tau, E_x, p.q_over_m, dx, l_cell, atB, l_boundary);
+                        p.WS(l_cell, iThread) = p.WS(l_cell, iThread) + l_f - l_sub;
+                    } else {
+                        del_tau = std::min(del_tau, pts[l_cell]);
+                        particleSubStepPicard(l_sub - (double)l_cell, v_sub, l_f, v_f, d_half, del_tau, s.EField[l_cell], s.EField[l_cell + 1],
+                                              dx, p.q_over_m, l_cell, atB, l_boundary, numIter);
+                        double J_part = l_f - l_sub;
+                        p.WS(l_cell, iThread) = p.WS(l_cell, iThread) + (1.0 - d_half) * J_part;
+                        p.WS(l_cell + 1, iThread) = p.WS(l_cell + 1, iThread) + J_part * d_half;
+                    }
+                    if (atB) {
+                        int b = w.bc[l_boundary];
+                        if (b == 0) l_cell = l_cell + (int)fsign(1.0, v_f);
+                        else if (b == 1 || b == 4) break;
+                        else if (b == 2) {
+                            if (l_boundary == NB) { if (v_f > 0) v_f = -v_f; }
+                            else { if (v_f < 0) v_f = -v_f; }
+                        } else if (b == 3) {
+                            l_f = (double)std::abs(l_boundary - NB - 1);
+                            l_cell = std::abs(l_cell - NB);
+                        }
+                    }
+                    timePassed = timePassed + del_tau;
+                    del_tau = del_t - timePassed;
+                    l_sub = l_f; v_sub = v_f;
+                }
+            }
+#pragma omp atomic
+            p.substepsDeposit += trips;
+        }
+    }
+    reduce_slices(o, w.nTH, w.thL, w.thR, [](Species &p, int i, int t) -> double & { return p.WS(i, t); });
+    Species &p1 = o.plist[0];
+    if (cic) {   // wall fix-ups :173-188
+        switch (w.bc[1]) {
+        case 1: case 4: p1.WS(1, 1) = 2.0 * p1.WS(1, 1); break;
+        case 2: p1.WS(1, 1) = 0.0; break;
+        case 3: p1.WS(1, 1) = p1.WS(1, 1) + p1.WS(Nh, 1); break;
+        }
+        switch (w.bc[Nh]) {
+        case 1: case 4: p1.WS(Nh, 1) = 2.0 * p1.WS(Nh, 1); break;
+        case 2: p1.WS(Nh, 1) = 0.0; break;
+        case 3: p1.WS(Nh, 1) = p1.WS(1, 1); break;
+        }
+    }
+    if (w.smooth) {
+        smoothField(w, &p1.WS(0, 1), s.J.data());
+        for (int i = 1; i <= Nh; ++i) s.J[i] = s.J[i] / del_t;
+    } else {
+        for (int i = 1; i <= Nh; ++i) s.J[i] = p1.WS(i, 1) / del_t;
+    }
+    o.nl.sweeps += 1;
+    for (auto &p : o.plist) o.nl.substeps += p.substepsDeposit;
+}
+
+// moveParticles: NGP mod_particleMover.f90:162-270 ; CIC mod_particleMoverPicard.f90:198-317
+static void moveParticles(Oracle &o, double del_t) {
+    Domain &w = o.world; Solver &s = o.solver;
+    const int Nx = w.Nx, Nh = w.Nh, T = w.T, nS = (int)o.plist.size();
+    const bool cic = (w.scheme == 1);
+    const double f_tol = del_t * (cic ? 1.e-10 : 1.e-15);
+    const int NB = cic ? Nh : Nx;
+    std::vector<long long> numSubStepAve(nS, 0), funcEvalCounter(nS, 0);
+    makeHalfTimeEField(o, &o.plist[0].WS(0, 1));
+    if (cic) makeParticleTimeStep(o);
+#pragma omp parallel for schedule(static, 1)
+    for (int iThread = 1; iThread <= T; ++iThread) {
+        for (int j = 0; j < nS; ++j) {
+            Species &p = o.plist[j];
+            long long trips = 0, fevals = 0;
+            int delIdx = 0, refIdx = 0;
+            p.WL(1, iThread) = 0; p.WL(2, iThread) = 0;
+            p.EL(1, iThread) = 0.0; p.EL(2, iThread) = 0.0;
+            const int N_p = p.N_p[iThread];
+            const double *pts = cic ? &o.particleTimeStep[(size_t)(Nx + 2) * j] : nullptr;
+            for (int i = 1; i <= N_p; ++i) {
+                double v_sub = p.P(2, i, iThread), l_sub = p.P(1, i, iThread);
+                double timePassed = 0.0, l_f = 0, v_f = 0, d_half = 0;
+                bool refluxedBool = false;
+                int l_cell = (int)(l_sub + fsign(1.e-12, v_sub));
+                double del_tau = del_t;
+                bool convergeTimeBool = true, atB = false;
+                int l_boundary = 0, numIter = 0;
+                while (convergeTimeBool) {
+                    ++trips;
+                    double dx = w.dx_dl[l_cell];
+                    if (!cic) {
+                        double E_x = s.EField[l_cell];
+                        particleSubStepNoBField(l_sub, v_sub, l_f, v_f, del_tau, E_x, p.q_over_m, dx, l_cell, atB, l_boundary);
+                    } else {
+                        del_tau = std::min(del_tau, pts[l_cell]);
+                        particleSubStepPicard(l_sub - (double)l_cell, v_sub, l_f, v_f, d_half, del_tau, s.EField[l_cell], s.EField[l_cell + 1],
+                                              dx, p.q_over_m, l_cell, atB, l_boundary, numIter);
+                        fevals += numIter;
+                    }
+                    if (atB) {
+                        int b = w.bc[l_boundary];
+                        if (b == 0) l_cell = l_cell + (int)fsign(1.0, v_f);
+                        else if (b == 1 || b == 4) {
+                            delIdx = delIdx + 1;
+                            if (l_boundary == 1) {
+                                p.EL(1, iThread) = p.EL(1, iThread) + v_f * v_f + (p.P(3, i, iThread) * p.P(3, i, iThread) + p.P(4, i, iThread) * p.P(4, i, iThread));
+                                p.WL(1, iThread) = p.WL(1, iThread) + 1;
+                                p.ML(1, iThread) = p.ML(1, iThread) + v_f;
+                            } else if (l_boundary == NB) {
+                                p.EL(2, iThread) = p.EL(2, iThread) + v_f * v_f + (p.P(3, i, iThread) * p.P(3, i, iThread) + p.P(4, i, iThread) * p.P(4, i, iThread));
+                                p.WL(2, iThread) = p.WL(2, iThread) + 1;
+                                p.ML(2, iThread) = p.ML(2, iThread) + v_f;
+                            }
+                            break;
+                        } else if (b == 2) {
+                            if (l_boundary == NB) { if (v_f > 0) v_f = -v_f; }
+                            else { if (v_f < 0) v_f = -v_f; }
+                            if (!refluxedBool) {
+                                refIdx = refIdx + 1;
+                                if (refIdx <= p.refRecLen) p.refRecordIdx[(size_t)refIdx + (size_t)(p.refRecLen + 1) * iThread] = i - delIdx;
+                                refluxedBool = true;
+                            }
+                        } else if (b == 3) {
+                            l_f = (double)std::abs(l_boundary - NB - 1);
+                            l_cell = std::abs(l_cell - NB);
+                        }
+                    }
+                    timePassed = timePassed + del_tau;
+                    del_tau = del_t - timePassed;
+                    convergeTimeBool = del_tau > f_tol;
+                    l_sub = l_f; v_sub = v_f;
+                }
+                if (!convergeTimeBool) {
+                    double vy = p.P(3, i, iThread), vz = p.P(4, i, iThread);
+                    p.P(1, i - delIdx, iThread) = l_f;
+                    p.P(2, i - delIdx, iThread) = v_f;
+                    p.P(3, i - delIdx, iThread) = vy;
+                    p.P(4, i - delIdx, iThread) = vz;
+                }
+            }
+            p.N_p[iThread] = N_p - delIdx;
+            p.delIdx[iThread] = delIdx;
+            p.refIdx[iThread] = refIdx;
+#pragma omp critical
+            { numSubStepAve[j] += trips; funcEvalCounter[j] += fevals; }
+        }
+    }
+    for (int j = 0; j < nS; ++j) {
+        Species &p = o.plist[j];
+        for (int t = 1; t <= T; ++t) p.numToCollide[t] = p.N_p[t];
+        // real(int)/real(int): default-real (single precision) division in the Fortran (:265-266)
+        float denom = (float)(int)(p.sumNp() + p.sumDel());
+        p.numSubStepsAve = (double)((float)(int)numSubStepAve[j] / denom);
+        p.numFuncEvalAve = (double)((float)(int)funcEvalCounter[j] / denom);
+        for (int sd = 1; sd <= 2; ++sd) {
+            double se = 0.0, sw = 0.0;
+            for (int t = 1; t <= T; ++t) { se += p.EL(sd, t); sw += p.WL(sd, t); }
+            p.accumEnergyLoss[sd - 1] += se;
+            p.accumWallLoss[sd - 1] += (int)sw;
+        }
+        p.substepsMove = numSubStepAve[j]; p.funcEvalsMove = funcEvalCounter[j];
+        o.nl.substeps += numSubStepAve[j];
+    }
+}
+
+// solveGaussElimination + solveNormalEquation  mod_BasicFunctions.f90:218-265
+// A is (m x n) column-major 1-based via lambda; returns alpha[1..n]
+static void solveNormalEquation(const double *A /*col-major m x n, 0-based storage*/, const double *b, int m, int n, double *out /*0-based n*/) {
+    std::vector<double> An((size_t)n * n), bn(n);
+    for (int j = 0; j < n; ++j) { double s = 0.0; for (int i = 0; i < m; ++i) s += A[(size_t)i + (size_t)m * j] * b[i]; bn[j] = s; }
+    for (int k = 0; k < n; ++k)
+        for (int j = 0; j < n; ++j) { double s = 0.0; for (int i = 0; i < m; ++i) s += A[(size_t)i + (size_t)m * j] * A[(size_t)i + (size_t)m * k]; An[(size_t)j + (size_t)n * k] = s; }
+    auto a = [&](int i, int j) -> double & { return An[(size_t)(i - 1) + (size_t)n * (j - 1)]; };
+    for (int k = 1; k <= n - 1; ++k) {
+        double k1 = a(k, k);
+        for (int i = k + 1; i <= n; ++i) a(i, k) = a(i, k) / k1;
+        for (int j = k + 1; j <= n; ++j) {
+            double k2 = a(k, j);
+            for (int i = k + 1; i <= n; ++i) a(i, j) = a(i, j) - a(i, k) * k2;
+        }
+    }
+    for (int i = 1; i <= n; ++i) for (int j = 1; j <= i - 1; ++j) bn[i - 1] = bn[i - 1] - a(i, j) * bn[j - 1];
+    for (int i = n; i >= 1; --i) {
+        for (int j = i + 1; j <= n; ++j) bn[i - 1] = bn[i - 1] - a(i, j) * bn[j - 1];
+        bn[i - 1] = bn[i - 1] / a(i, i);
+    }
+    for (int i = 0; i < n; ++i) out[i] = bn[i];
+}
+
+static inline int fmodulo(int a, int p) { int r = a % p; return (r < 0) ? r + p : r; }
+
+static double wtime() {
+#ifdef _OPENMP
+    return omp_get_wtime();
+#else
+    return 0.0;
+#endif
+}
+
+// solveDivAmpereAnderson  mod_nonLinSolvers.f90:85-160
+static void solveDivAmpereAnderson(Oracle &o, double del_t) {
+    Solver &s = o.solver; NonLin &nl = o.nl;
+    const int Nx = o.world.Nx, m = nl.m_Anderson, M1 = m + 1;
+    auto PK = [&](int i, int c) -> double & { return nl.phi_k[(size_t)(i - 1) + (size_t)Nx * (c - 1)]; };
+    auto RK = [&](int i, int c) -> double & { return nl.Residual_k[(size_t)(i - 1) + (size_t)Nx * (c - 1)]; };
+    dvec normResidual(M1 + 1, 0.0), alpha(M1 + 1, 0.0);
+    nl.normHist.clear();
+    makeConstSourceTerm(o);
+    for (int i = 1; i <= Nx; ++i) PK(i, 1) = s.phi_f[i];
+    double t0 = wtime(); depositJ(o, del_t); nl.moverSeconds += wtime() - t0;
+    t0 = wtime(); solve_tridiag_Ampere(o, del_t); nl.potSeconds += wtime() - t0;
+    for (int i = 1; i <= Nx; ++i) { PK(i, 2) = s.phi_f[i]; RK(i, 1) = PK(i, 2) - PK(i, 1); }
+    { double sm = 0.0; for (int i = 1; i <= Nx; ++i) sm += RK(i, 1) * RK(i, 1); normResidual[1] = std::sqrt(sm); }
+    nl.normHist.push_back(normResidual[1]);
+    double eps_tol = nl.eps_r * normResidual[1] + nl.eps_a * (double)std::sqrt((float)Nx)   /* SQRT(real(N)) is single precision */;
+    for (int i = 1; i <= nl.maxIter; ++i) {
+        int index = fmodulo(i, M1) + 1;
+        int m_k = std::min(i, m);
+        t0 = wtime(); depositJ(o, del_t); nl.moverSeconds += wtime() - t0;
+        t0 = wtime(); solve_tridiag_Ampere(o, del_t); nl.potSeconds += wtime() - t0;
+        for (int k = 1; k <= Nx; ++k) RK(k, index) = s.phi_f[k] - PK(k, index);
+        { double sm = 0.0; for (int k = 1; k <= Nx; ++k) sm += RK(k, index) * RK(k, index); normResidual[index] = std::sqrt(sm); }
+        nl.normHist.push_back(normResidual[index]);
+        if (normResidual[index] < eps_tol) {
+            t0 = wtime(); moveParticles(o, del_t); nl.moverSeconds += wtime() - t0;
+            nl.iterNumPicard = i + 1;
+            return;
+        }
+        if (i > m) {
+            double sumPast;
+            if (m > 3) {
+                sumPast = normResidual[fmodulo(i - 1, M1) + 1] + normResidual[fmodulo(i - 2, M1) + 1] + normResidual[fmodulo(i - 3, M1) + 1];
+                sumPast = sumPast / 3.0;
+            } else sumPast = normResidual[fmodulo(i - 1, M1) + 1];
+            if (normResidual[index] > sumPast) { nl.iterNumPicard = nl.maxIter; return; }
+        }
+        for (int j = 0; j <= m_k - 1; ++j) {
+            int cj = fmodulo(i - m_k + j, M1) + 1;
+            for (int k = 1; k <= Nx; ++k) nl.fitMat[(size_t)(k - 1) + (size_t)Nx * j] = RK(k, index) - RK(k, cj);
+        }
+        solveNormalEquation(nl.fitMat.data(), &RK(1, index), Nx, m_k, &alpha[1]);
+        { double sa = 0.0; for (int j = 1; j <= m_k; ++j) sa += alpha[j]; alpha[m_k + 1] = 1.0 - sa; }
+        int cn = fmodulo(i + 1, M1) + 1, c0 = fmodulo(i - m_k, M1) + 1;
+        for (int k = 1; k <= Nx; ++k) PK(k, cn) = alpha[1] * (nl.Beta_k * RK(k, c0) + PK(k, c0));
+        for (int j = 1; j <= m_k; ++j) {
+            int cj = fmodulo(i - m_k + j, M1) + 1;
+            for (int k = 1; k <= Nx; ++k) PK(k, cn) = PK(k, cn) + alpha[j + 1] * (nl.Beta_k * RK(k, cj) + PK(k, cj));
+        }
+        for (int k = 1; k <= Nx; ++k) s.phi_f[k] = PK(k, cn);
+    }
+    // loop exhausted: the reference leaves iterNumPicard untouched (:112-158)
+}
+
+// adaptiveSolveDivAmpereAnderson  mod_nonLinSolvers.f90:162-196 ; returns nonzero where the reference `stop`s
+static int adaptiveSolveDivAmpereAnderson(Oracle &o, double del_t, double &remainDel_t, double &currDel_t, double timeCurrent) {
+    NonLin &nl = o.nl;
+    currDel_t = remainDel_t;
+    if (o.solver.RF_bool) setRFVoltage(o, timeCurrent + remainDel_t);
+    solveDivAmpereAnderson(o, remainDel_t);
+    if (nl.iterNumPicard < nl.maxIter) {
+        remainDel_t = del_t;
+    } else {
+        nl.amountTimeSplits += 1;
+        nl.iterNumAdaptiveSteps = 0;
+        while (nl.iterNumPicard == nl.maxIter) {
+            currDel_t = currDel_t / 2.0;
+            nl.iterNumAdaptiveSteps += 1;
+            if (nl.iterNumAdaptiveSteps > 4) return 1;
+            if (o.solver.RF_bool) setRFVoltage(o, timeCurrent + currDel_t);
+            solveDivAmpereAnderson(o, currDel_t);
+        }
+        remainDel_t = remainDel_t - currDel_t;
+    }
+    return 0;
+}
+
+// solvePotential  mod_nonLinSolvers.f90:198-215 (Anderson branch)
+static int solvePotential(Oracle &o, double del_t, double &remainDel_t, double &currDel_t, double timeCurrent) {
+    o.nl.sweeps = 0; o.nl.substeps = 0;
+    resetVoltage(o);
+    if (o.nl.solverType == 0) return adaptiveSolveDivAmpereAnderson(o, del_t, remainDel_t, currDel_t, timeCurrent);
+    return 2;   // JFNK: not restated in this file
+}
+
+}  // namespace
+
+// =============================================================================
+// C ABI for the test harness (ctypes).  0-based plain arrays at this boundary.
+// =============================================================================
+extern "C" {
+
+void *orc_create(int scheme, int Nx, double L_domain, int gridType, double del_x, int bcL, int bcR, int smooth, int T) {
+    Oracle *o = new Oracle();
+    if (bcL == 3 || bcR == 3) { bcL = 3; bcR = 3; }
+    domain_init(o->world, scheme, Nx, bcL, bcR, T);
+    int rc = domain_grid(o->world, del_x, L_domain, gridType);
+    if (rc) { delete o; return nullptr; }
+    o->world.smooth = smooth != 0;
+    return o;
+}
+void orc_destroy(void *h) { delete (Oracle *)h; }
+int orc_Nx(void *h) { return ((Oracle *)h)->world.Nx; }
+int orc_Nh(void *h) { return ((Oracle *)h)->world.Nh; }
+int orc_T(void *h) { return ((Oracle *)h)->world.T; }
+double orc_L_domain(void *h) { return ((Oracle *)h)->world.L_domain; }
+void orc_get_grid(void *h, double *grid, double *dx_dl, int *bc) {
+    Oracle *o = (Oracle *)h; Domain &w = o->world;
+    for (int i = 1; i <= w.Nx; ++i) grid[i - 1] = w.grid[i];
+    int nd = (w.scheme == 0) ? w.Nh : w.Nx;
+    for (int i = 1; i <= nd; ++i) dx_dl[i - 1] = w.dx_dl[i];
+    int nb = (w.scheme == 0) ? w.Nx : w.Nh;
+    for (int i = 1; i <= nb; ++i) bc[i - 1] = w.bc[i];
+}
+void orc_get_slices(void *h, int *half_lr /*2*nTH*/, int *node_lr /*2*nTN*/, int *nTH, int *nTN) {
+    Domain &w = ((Oracle *)h)->world;
+    *nTH = w.nTH; *nTN = w.nTN;
+    for (int i = 1; i <= w.nTH; ++i) { half_lr[2 * (i - 1)] = w.thL[i]; half_lr[2 * (i - 1) + 1] = w.thR[i]; }
+    for (int i = 1; i <= w.nTN; ++i) { node_lr[2 * (i - 1)] = w.tnL[i]; node_lr[2 * (i - 1) + 1] = w.tnR[i]; }
+}
+double orc_getLFromX(void *h, double x) { return getLFromX(((Oracle *)h)->world, x); }
+double orc_getXFromL(void *h, double l) { return getXFromL(((Oracle *)h)->world, l); }
+
+int orc_init_solver(void *h, double leftV, double rightV, double RF_frequency, double timeCurrent) {
+    return solver_init(*(Oracle *)h, leftV, rightV, RF_frequency, timeCurrent);
+}
+// species: mass in kg, charge in C.  Returns species index.
+int orc_add_species(void *h, double mass, double q, int N_p_per_thread, int finalIdx) {
+    Oracle *o = (Oracle *)h;
+    o->plist.emplace_back();
+    species_init(o->plist.back(), o->world, mass, q, 1.0, N_p_per_thread, finalIdx);
+    return (int)o->plist.size() - 1;
+}
+// initialize_n_ave  mod_particle.f90:76-82
+void orc_initialize_n_ave(void *h, int sp, double n_ave) {
+    Oracle *o = (Oracle *)h; Species &s = o->plist[sp];
+    s.w_p = n_ave * o->world.L_domain / (double)s.sumNp();
+    s.q_times_wp = s.q * s.w_p;
+}
+void orc_set_weight(void *h, int sp, double w_p) { Species &s = ((Oracle *)h)->plist[sp]; s.w_p = w_p; s.q_times_wp = s.q * w_p; }
+double orc_get_weight(void *h, int sp) { return ((Oracle *)h)->plist[sp].w_p; }
+// loader with per-slab ran2 seeds (irand has T entries, updated in place) -- mod_particle.f90:352-369
+void orc_load_particles(void *h, int sp, int32_t *irand, double T_eV, double alpha, int distType, double v_drift) {
+    Oracle *o = (Oracle *)h; Species &s = o->plist[sp];
+    std::vector<int32_t> ir(o->world.T + 1);
+    for (int t = 1; t <= o->world.T; ++t) ir[t] = irand[t - 1];
+    switch (distType) {
+    case 0: initializeRandUniform(s, o->world, ir.data()); break;
+    case 1: initializeRandTrig(s, o->world, ir.data(), alpha, false); break;
+    case 2: initializeRandTrig(s, o->world, ir.data(), alpha, true); break;
+    }
+    generate3DMaxwellian(s, o->world, T_eV, ir.data(), (sp == 0) ? alpha : 1.236, distType, v_drift);
+    for (int t = 1; t <= o->world.T; ++t) irand[t - 1] = ir[t];
+}
+double *orc_phase_space(void *h, int sp) { return ((Oracle *)h)->plist[sp].ps.data(); }   // (4, finalIdx, T) Fortran order
+int orc_final_idx(void *h, int sp) { return ((Oracle *)h)->plist[sp].finalIdx; }
+void orc_get_Np(void *h, int sp, int *N_p) { Species &s = ((Oracle *)h)->plist[sp]; for (int t = 1; t <= s.T; ++t) N_p[t - 1] = s.N_p[t]; }
+void orc_set_Np(void *h, int sp, const int *N_p) { Species &s = ((Oracle *)h)->plist[sp]; for (int t = 1; t <= s.T; ++t) s.N_p[t] = N_p[t - 1]; }
+void orc_get_counters(void *h, int sp, int *delIdx, int *refIdx, double *wallLoss, double *energyLoss, double *momentumLoss) {
+    Species &s = ((Oracle *)h)->plist[sp];
+    for (int t = 1; t <= s.T; ++t) {
+        delIdx[t - 1] = s.delIdx[t]; refIdx[t - 1] = s.refIdx[t];
+        for (int sd = 1; sd <= 2; ++sd) {
+            wallLoss[(sd - 1) + 2 * (t - 1)] = s.WL(sd, t);
+            energyLoss[(sd - 1) + 2 * (t - 1)] = s.EL(sd, t);
+            momentumLoss[(sd - 1) + 2 * (t - 1)] = s.ML(sd, t);
+        }
+    }
+}
+void orc_get_ref_record(void *h, int sp, int t /*1-based*/, int *out, int n) {
+    Species &s = ((Oracle *)h)->plist[sp];
+    for (int k = 1; k <= n && k <= s.refRecLen; ++k) out[k - 1] = s.refRecordIdx[(size_t)k + (size_t)(s.refRecLen + 1) * t];
+}
+void orc_get_move_stats(void *h, int sp, double *numSubStepsAve, double *numFuncEvalAve, long long *substepsMove, long long *funcEvalsMove,
+                        long long *substepsDeposit) {
+    Species &s = ((Oracle *)h)->plist[sp];
+    *numSubStepsAve = s.numSubStepsAve; *numFuncEvalAve = s.numFuncEvalAve;
+    *substepsMove = s.substepsMove; *funcEvalsMove = s.funcEvalsMove; *substepsDeposit = s.substepsDeposit;
+}
+void orc_config_solver(void *h, double eps_a, double eps_r, int solverType, int m_Anderson, double Beta_k, int maxIter) {
+    Oracle *o = (Oracle *)h; NonLin &nl = o->nl;
+    nl.eps_a = eps_a; nl.eps_r = eps_r; nl.solverType = solverType; nl.m_Anderson = m_Anderson; nl.Beta_k = Beta_k; nl.maxIter = maxIter;
+    const int Nx = o->world.Nx;
+    nl.Residual_k.assign((size_t)Nx * (m_Anderson + 1), 0.0);
+    nl.phi_k.assign((size_t)Nx * (m_Anderson + 1), 0.0);
+    nl.fitMat.assign((size_t)Nx * std::max(1, m_Anderson), 0.0);
+}
+
+void orc_deposit_rho(void *h) { depositRho(*(Oracle *)h); }
+void orc_solve_tridiag_poisson(void *h, double t) { solve_tridiag_Poisson(*(Oracle *)h, t); }
+void orc_solve_initial_potential(void *h, double t) { depositRho(*(Oracle *)h); solve_tridiag_Poisson(*(Oracle *)h, t); }
+void orc_make_const_source_term(void *h) { makeConstSourceTerm(*(Oracle *)h); }
+void orc_make_half_time_efield(void *h) { Oracle *o = (Oracle *)h; makeHalfTimeEField(*o, &o->plist[0].WS(0, 1)); }
+void orc_deposit_J(void *h, double del_t) { depositJ(*(Oracle *)h, del_t); }
+void orc_solve_tridiag_ampere(void *h, double del_t) { solve_tridiag_Ampere(*(Oracle *)h, del_t); }
+void orc_move_particles(void *h, double del_t) { moveParticles(*(Oracle *)h, del_t); }
+void orc_reset_voltage(void *h) { resetVoltage(*(Oracle *)h); }
+void orc_set_rf_voltage(void *h, double t) { setRFVoltage(*(Oracle *)h, t); }
+int orc_solve_potential(void *h, double del_t, double *remainDel_t, double *currDel_t, double timeCurrent) {
+    return solvePotential(*(Oracle *)h, del_t, *remainDel_t, *currDel_t, timeCurrent);
+}
+void orc_solve_div_ampere_anderson(void *h, double del_t) { solveDivAmpereAnderson(*(Oracle *)h, del_t); }
+
+// field getters/setters (0-based out arrays). which: 0 phi, 1 phi_f, 2 J, 3 rho, 4 EField, 5 a_tri, 6 b_tri, 7 c_tri
+static dvec *field_ptr(Oracle *o, int which, int *n) {
+    Solver &s = o->solver; const int Nx = o->world.Nx, Nh = o->world.Nh;
+    switch (which) {
+    case 0: *n = Nx; return &s.phi;
+    case 1: *n = Nx; return &s.phi_f;
+    case 2: *n = Nh; return &s.J;
+    case 3: *n = Nx; return &s.rho;
+    case 4: *n = Nh; return &s.EField;
+    case 5: *n = Nx - 1; return &s.a_tri;
+    case 6: *n = Nx; return &s.b_tri;
+    case 7: *n = Nx - 1; return &s.c_tri;
+    }
+    *n = 0; return nullptr;
+}
+int orc_get_field(void *h, int which, double *out) {
+    int n; dvec *v = field_ptr((Oracle *)h, which, &n);
+    if (!v) return 0;
+    for (int i = 1; i <= n; ++i) out[i - 1] = (*v)[i];
+    return n;
+}
+int orc_set_field(void *h, int which, const double *in) {
+    int n; dvec *v = field_ptr((Oracle *)h, which, &n);
+    if (!v) return 0;
+    for (int i = 1; i <= n; ++i) (*v)[i] = in[i - 1];
+    return n;
+}
+// CIC wall scalars: boundPhi(2), sourceTermVals(2), RF_voltage
+void orc_get_cic_walls(void *h, double *out5) {
+    Solver &s = ((Oracle *)h)->solver;
+    out5[0] = s.boundPhi[1]; out5[1] = s.boundPhi[2]; out5[2] = s.sourceTermVals[1]; out5[3] = s.sourceTermVals[2]; out5[4] = s.RF_voltage;
+}
+void orc_get_rf(void *h, double *rad_freq, double *half_amp, int *rf_bool, int *rf_indx) {
+    Solver &s = ((Oracle *)h)->solver;
+    *rad_freq = s.RF_rad_frequency; *half_amp = s.RF_half_amplitude; *rf_bool = s.RF_bool ? 1 : 0; *rf_indx = s.RF_indx;
+}
+void orc_get_particle_time_step(void *h, int sp, double *out /*Nx*/) {
+    Oracle *o = (Oracle *)h; const int Nx = o->world.Nx;
+    for (int i = 1; i <= Nx; ++i) out[i - 1] = o->particleTimeStep[(size_t)i + (size_t)(Nx + 2) * sp];
+}
+
+// diagnostics (main.f90:58-114)
+double orc_total_PE(void *h, int future) { return getTotalPE(*(Oracle *)h, future != 0); }
+double orc_total_KE(void *h, int sp) { return getTotalKE(((Oracle *)h)->plist[sp]); }
+double orc_KE_ave(void *h, int sp) { return getKEAve(((Oracle *)h)->plist[sp]); }
+void orc_total_momentum(void *h, int sp, double *out3) { getTotalMomentum(((Oracle *)h)->plist[sp], out3); }
+double orc_JdotE(void *h, double del_t) { return getJdotE(*(Oracle *)h, del_t); }
+double orc_energy_from_boundary(void *h, double del_t) { return getEnergyFromBoundary(*(Oracle *)h, del_t); }
+double orc_gauss_error(void *h) { return getError_tridiag_Poisson(*(Oracle *)h); }
+double orc_charge_error(void *h, const double *rho_i /*0-based Nx*/, double del_t) {
+    Oracle *o = (Oracle *)h; dvec r(o->world.Nx + 2, 0.0);
+    for (int i = 1; i <= o->world.Nx; ++i) r[i] = rho_i[i - 1];
+    return getChargeContinuityError(*o, r.data(), del_t);
+}
+double orc_lost_energy_sum(void *h, int sp) {   // SUM(energyLoss) as used in main.f90:83
+    Species &s = ((Oracle *)h)->plist[sp]; double r = 0.0;
+    for (int t = 1; t <= s.T; ++t) for (int sd = 1; sd <= 2; ++sd) r += s.EL(sd, t);
+    return r;
+}
+void orc_get_solver_stats(void *h, int *iterNumPicard, int *iterNumAdaptiveSteps, int *amountTimeSplits, long long *sweeps, long long *substeps,
+                          double *moverSeconds, double *potSeconds) {
+    NonLin &nl = ((Oracle *)h)->nl;
+    *iterNumPicard = nl.iterNumPicard; *iterNumAdaptiveSteps = nl.iterNumAdaptiveSteps; *amountTimeSplits = nl.amountTimeSplits;
+    *sweeps = nl.sweeps; *substeps = nl.substeps; *moverSeconds = nl.moverSeconds; *potSeconds = nl.potSeconds;
+}
+int orc_get_norm_history(void *h, double *out, int nmax) {
+    NonLin &nl = ((Oracle *)h)->nl; int n = (int)nl.normHist.size();
+    for (int i = 0; i < n && i < nmax; ++i) out[i] = nl.normHist[i];
+    return n;
+}
+void orc_solve_normal_equation(const double *A, const double *b, int m, int n, double *out) { solveNormalEquation(A, b, m, n, out); }
+double orc_ran2(int32_t *irand) { return ran2(*irand); }
+double orc_randPCG(uint64_t *state) { return randPCG(*state); }
+void orc_species_scalars(void *h, int sp, double *out5) {
+    Species &s = ((Oracle *)h)->plist[sp];
+    out5[0] = s.mass; out5[1] = s.q; out5[2] = s.w_p; out5[3] = s.q_over_m; out5[4] = s.q_times_wp;
+}
+int orc_max_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+}  // extern "C"
