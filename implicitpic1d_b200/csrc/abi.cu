@@ -1,0 +1,593 @@
+// C ABI of the B200 implicit-PIC library (include/ipic1d_b200.h): context management, the reference's
+// module procedures as entry points, the Anderson / adaptive-step driver and the NCCL plumbing.
+//
+// Reference semantics restated here (never copied): OpenMP/SharedModules/src/mod_nonLinSolvers.f90:41-215,
+// OpenMP/{NGP,CIC}/src/mod_potentialSolver.f90 (constructor, setRFVoltage, resetVoltage).
+#include "ipic_common.cuh"
+#include <cmath>
+#include <cstring>
+#include <dlfcn.h>
+#include <mutex>
+
+namespace ipic {
+
+static thread_local std::string g_err;
+void set_error(const std::string &s) { g_err = s; }
+
+// ---- NCCL through dlopen: no link-time dependency; inside a torch process this resolves to the
+// already-loaded libnccl.so.2, stand-alone to the system library. ---------------------------------------
+struct NcclUid { char b[128]; };   // ncclUniqueId, passed by value
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclUid, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+    if (g_nccl.lib) return IPIC_OK;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { set_error(std::string("dlopen libnccl.so.2 failed: ") + dlerror()); return IPIC_ERR_NCCL; }
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
+    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) { set_error("libnccl: missing symbols"); return IPIC_ERR_NCCL; }
+    g_nccl.lib = h;
+    return IPIC_OK;
+}
+constexpr int kNcclUint64 = 5, kNcclSum = 0;
+
+static int allreduce_acc(Ctx &c) {
+    if (c.nranks <= 1 || !c.nccl_comm) return IPIC_OK;
+    const size_t count = (size_t)c.sp.size() * (std::max(c.Nx, c.Nh) + 2);
+    int rc = g_nccl.AllReduce(c.d_acc, c.d_acc, count, kNcclUint64, kNcclSum, c.nccl_comm, c.stream);
+    if (rc != 0) { set_error(std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?")); return IPIC_ERR_NCCL; }
+    return IPIC_OK;
+}
+
+// ---- timing with an event pool: no synchronisation on the hot path ----------------------------------------
+struct PendingTiming { std::string name; cudaEvent_t e0, e1; };
+static std::map<Ctx *, std::vector<PendingTiming>> g_pending;
+static std::map<Ctx *, std::vector<cudaEvent_t>> g_pool;
+static cudaEvent_t pool_get(Ctx &c) {
+    auto &p = g_pool[&c];
+    if (!p.empty()) { cudaEvent_t e = p.back(); p.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+struct Timed {
+    Ctx &c; const char *name; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    Timed(Ctx &c_, const char *n) : c(c_), name(n) {
+        if (c.timing_on) { e0 = pool_get(c); e1 = pool_get(c); cudaEventRecord(e0, c.stream); }
+    }
+    ~Timed() {
+        if (!e0) return;
+        cudaEventRecord(e1, c.stream);
+        g_pending[&c].push_back({name, e0, e1});
+    }
+};
+static void resolve_timing(Ctx &c) {
+    auto &pend = g_pending[&c];
+    if (pend.empty()) return;
+    cudaStreamSynchronize(c.stream);
+    for (auto &p : pend) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) { Timing &t = c.timing[p.name]; t.ms += ms; t.launches += 1; }
+        g_pool[&c].push_back(p.e0); g_pool[&c].push_back(p.e1);
+    }
+    pend.clear();
+}
+
+static int check(Ctx *c) { if (!c) { set_error("null handle"); return IPIC_ERR_ARG; } cudaSetDevice(c->device); return IPIC_OK; }
+#define CTX(h) Ctx *c = reinterpret_cast<Ctx *>(h); { int _rc = check(c); if (_rc) return _rc; }
+#define RC(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
+
+static int zero_counters(Ctx &c) {
+    IPIC_CUDA(cudaMemsetAsync(c.d_counters, 0, NSP_MAX * 8 * sizeof(unsigned long long), c.stream));
+    return IPIC_OK;
+}
+static int read_counters(Ctx &c, unsigned long long *out /* NSP_MAX*8 */) {
+    IPIC_CUDA(cudaMemcpyAsync(out, c.d_counters, NSP_MAX * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
+    IPIC_CUDA(cudaStreamSynchronize(c.stream));
+    return IPIC_OK;
+}
+
+// one particle sweep of all species into the fixed-point grids (+ all-reduce across ranks)
+static int sweep_deposit(Ctx &c, double del_t) {
+    {
+        Timed t(c, "depositJ_kernels");
+        for (int s = 0; s < (int)c.sp.size(); ++s) {
+            Timed ts(c, s == 0 ? "depositJ_sp0" : (s == 1 ? "depositJ_sp1" : "depositJ_spN"));
+            RC(launch_deposit(c, s, del_t));
+        }
+    }
+    if (c.nranks > 1) { Timed t(c, "allreduce_J"); RC(allreduce_acc(c)); }
+    c.sweeps += 1;
+    return IPIC_OK;
+}
+
+static int move_all(Ctx &c, double del_t) {
+    // slots 1..5 belong to the mover; slot 0 keeps accumulating deposit sub-steps across sweeps
+    for (int s = 0; s < (int)c.sp.size(); ++s)
+        IPIC_CUDA(cudaMemsetAsync(c.d_counters + (size_t)s * 8 + 1, 0, 5 * sizeof(unsigned long long), c.stream));
+    {
+        Timed t(c, "moveParticles_kernels");
+        for (int s = 0; s < (int)c.sp.size(); ++s) RC(launch_move(c, s, del_t));
+    }
+    unsigned long long cnt[NSP_MAX * 8];
+    RC(read_counters(c, cnt));
+    {
+        Timed t(c, "compaction");
+        for (int s = 0; s < (int)c.sp.size(); ++s) {
+            SpeciesDev &S = c.sp[s];
+            ipic_move_stats &st = S.stats;
+            const unsigned long long *k = cnt + s * 8;
+            st.numSubSteps = (int64_t)k[5]; st.numFuncEvals = (int64_t)k[1];
+            st.wallLoss[0] = (double)k[2]; st.wallLoss[1] = (double)k[3];
+            st.delIdx = (int64_t)(k[2] + k[3]); st.refIdx = (int64_t)k[4];
+            st.energyLoss[0] = st.energyLoss[1] = 0.0;
+            if (st.delIdx > 0) RC(compact_species(c, s));
+            st.N_p = S.n;
+            if (c.nranks > 1) { /* per-rank statistics; callers all-reduce the scalars they need */ }
+            // real(int)/real(int): single-precision division as in mod_particleMover.f90:265-266
+            const float denom = (float)(int)(st.N_p + st.delIdx);
+            st.numSubStepsAve = (double)((float)(int)st.numSubSteps / denom);
+            st.numFuncEvalAve = (double)((float)(int)st.numFuncEvals / denom);
+            st.accumEnergyLoss[0] += st.energyLoss[0]; st.accumEnergyLoss[1] += st.energyLoss[1];
+            st.accumWallLoss[0] += (int64_t)k[2]; st.accumWallLoss[1] += (int64_t)k[3];
+            c.substeps += (long long)k[5];
+        }
+    }
+    return IPIC_OK;
+}
+
+// setRFVoltage: NGP mod_potentialSolver.f90:444-453 ; CIC :458-470
+static int set_rf_voltage(Ctx &c, double timeFuture) {
+    const double v = c.RF_half_amplitude * std::sin(c.RF_rad_frequency * timeFuture);
+    if (c.scheme == IPIC_SCHEME_NGP) {
+        const int idx = (c.h_bc[0] == 4) ? 0 : c.Nx - 1;
+        c.h_scal[32] = v;
+        IPIC_CUDA(cudaMemcpyAsync(c.d_phi_f + idx, c.h_scal + 32, sizeof(double), cudaMemcpyHostToDevice, c.stream));
+        IPIC_CUDA(cudaStreamSynchronize(c.stream));
+    } else {
+        c.RF_voltage = v;
+        if (c.RF_indx == 1) c.sourceTermVals[0] = -c.RF_voltage * 2.0 / c.h_dx[0];
+        else c.sourceTermVals[1] = -c.RF_voltage * 2.0 / c.h_dx[c.Nx - 1];
+    }
+    return IPIC_OK;
+}
+
+// resetVoltage: NGP :455-459 ; CIC :472-478
+static int reset_voltage(Ctx &c) {
+    IPIC_CUDA(cudaMemcpyAsync(c.d_phi, c.d_phi_f, c.Nx * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+    if (c.scheme == IPIC_SCHEME_CIC && c.RF_bool) c.boundPhi[c.RF_indx - 1] = c.RF_voltage;
+    return IPIC_OK;
+}
+
+// solveDivAmpereAnderson  mod_nonLinSolvers.f90:85-160
+static int solve_div_ampere_anderson(Ctx &c, double del_t) {
+    const int m = c.m_Anderson, M1 = m + 1;
+    std::vector<double> normResidual(M1 + 1, 0.0);
+    auto fmodulo = [](int a, int p) { int r = a % p; return r < 0 ? r + p : r; };
+    c.normHist.clear();
+    int status = 0; double norm = 0.0;
+    { Timed t(c, "field_kernels"); RC(field_anderson_begin(c)); }
+    RC(sweep_deposit(c, del_t));
+    { Timed t(c, "field_kernels"); RC(field_anderson_step(c, 0, 0, del_t, &status, &norm)); }
+    normResidual[1] = norm;
+    c.normHist.push_back(norm);
+    // eps_a * SQRT(real(NumberXNodes)): single-precision square root in the reference (:111)
+    const double eps_tol = c.eps_r * normResidual[1] + c.eps_a * (double)std::sqrt((float)c.Nx);
+    for (int i = 1; i <= c.maxIter; ++i) {
+        const int index = fmodulo(i, M1) + 1;
+        RC(sweep_deposit(c, del_t));
+        { Timed t(c, "field_kernels"); RC(field_anderson_step(c, i, 1, del_t, &status, &norm)); }
+        normResidual[index] = norm;
+        c.normHist.push_back(norm);
+        c.lastNorm = norm;
+        if (norm < eps_tol) {
+            { Timed t(c, "field_kernels"); RC(field_anderson_step(c, i, 3, del_t, &status, &norm)); }
+            RC(move_all(c, del_t));
+            c.iterNumPicard = i + 1;
+            return IPIC_OK;
+        }
+        if (i > m) {
+            double sumPast;
+            if (m > 3) {
+                sumPast = normResidual[fmodulo(i - 1, M1) + 1] + normResidual[fmodulo(i - 2, M1) + 1] + normResidual[fmodulo(i - 3, M1) + 1];
+                sumPast = sumPast / 3.0;
+            } else {
+                sumPast = normResidual[fmodulo(i - 1, M1) + 1];
+            }
+            if (normResidual[index] > sumPast) { c.iterNumPicard = c.maxIter; return IPIC_OK; }
+        }
+        { Timed t(c, "field_kernels"); RC(field_anderson_step(c, i, 2, del_t, &status, &norm)); }
+    }
+    return IPIC_OK;   // loop exhausted: iterNumPicard left untouched, as in the reference
+}
+
+// adaptiveSolveDivAmpereAnderson  mod_nonLinSolvers.f90:162-196
+static int adaptive_anderson(Ctx &c, double del_t, double &remainDel_t, double &currDel_t, double timeCurrent) {
+    currDel_t = remainDel_t;
+    if (c.RF_bool) RC(set_rf_voltage(c, timeCurrent + remainDel_t));
+    RC(solve_div_ampere_anderson(c, remainDel_t));
+    if (c.iterNumPicard < c.maxIter) {
+        remainDel_t = del_t;
+    } else {
+        c.amountTimeSplits += 1;
+        c.iterNumAdaptiveSteps = 0;
+        while (c.iterNumPicard == c.maxIter) {
+            currDel_t = currDel_t / 2.0;
+            c.iterNumAdaptiveSteps += 1;
+            if (c.iterNumAdaptiveSteps > 4) {
+                set_error("ALREADY REDUCED TIME STEP MORE THAN 3 TIMES, REDUCE INITIAL TIME STEP!!!");
+                return IPIC_ERR_STOP;
+            }
+            if (c.RF_bool) RC(set_rf_voltage(c, timeCurrent + currDel_t));
+            RC(solve_div_ampere_anderson(c, currDel_t));
+        }
+        remainDel_t = remainDel_t - currDel_t;
+    }
+    return IPIC_OK;
+}
+
+}  // namespace ipic
+
+using namespace ipic;
+
+extern "C" {
+
+const char *ipic_version(void) { return "ipic1d_b200 0.1 (sm_100a)"; }
+const char *ipic_last_error(void) { return g_err.c_str(); }
+int ipic_device_count(int *n) { IPIC_CUDA(cudaGetDeviceCount(n)); return IPIC_OK; }
+
+int ipic_create(ipic_handle *out, int scheme, int32_t Nx, const double *grid, const double *dx_dl, const int32_t *bc, int smooth, int device) {
+    if (!out || !grid || !dx_dl || !bc || Nx < 3 || (scheme != IPIC_SCHEME_NGP && scheme != IPIC_SCHEME_CIC)) { set_error("ipic_create: bad argument"); return IPIC_ERR_ARG; }
+    IPIC_CUDA(cudaSetDevice(device));
+    Ctx *c = new Ctx();
+    c->scheme = scheme; c->Nx = Nx; c->device = device; c->smooth = smooth ? 1 : 0;
+    c->Nh = (scheme == IPIC_SCHEME_NGP) ? Nx - 1 : Nx + 1;
+    c->nbc = (scheme == IPIC_SCHEME_NGP) ? Nx : c->Nh;
+    c->ndx = (scheme == IPIC_SCHEME_NGP) ? c->Nh : Nx;
+    if (c->Nh > MAX_GRID_SMEM || Nx > MAX_GRID_SMEM) { delete c; set_error("grid larger than the shared-memory accumulator supports"); return IPIC_ERR_UNSUPPORTED; }
+    c->h_grid.assign(grid, grid + Nx); c->h_dx.assign(dx_dl, dx_dl + c->ndx); c->h_bc.assign(bc, bc + c->nbc);
+    cudaDeviceProp prop; IPIC_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    IPIC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    const size_t NM = (size_t)std::max(Nx, c->Nh) + 2;
+    auto dalloc = [&](double **p, size_t n) -> int { IPIC_CUDA(cudaMalloc(p, n * sizeof(double))); IPIC_CUDA(cudaMemset(*p, 0, n * sizeof(double))); return IPIC_OK; };
+    RC(dalloc(&c->d_grid, NM)); RC(dalloc(&c->d_dx, NM));
+    IPIC_CUDA(cudaMalloc(&c->d_bc, (NM + 2) * sizeof(int))); IPIC_CUDA(cudaMemset(c->d_bc, 0, (NM + 2) * sizeof(int)));
+    IPIC_CUDA(cudaMemcpy(c->d_grid, grid, Nx * sizeof(double), cudaMemcpyHostToDevice));
+    IPIC_CUDA(cudaMemcpy(c->d_dx, dx_dl, c->ndx * sizeof(double), cudaMemcpyHostToDevice));
+    IPIC_CUDA(cudaMemcpy(c->d_bc, bc, c->nbc * sizeof(int), cudaMemcpyHostToDevice));
+    RC(dalloc(&c->d_phi, NM)); RC(dalloc(&c->d_phi_f, NM)); RC(dalloc(&c->d_rho, NM)); RC(dalloc(&c->d_J, NM)); RC(dalloc(&c->d_E, NM));
+    RC(dalloc(&c->d_a, NM)); RC(dalloc(&c->d_b, NM)); RC(dalloc(&c->d_c, NM)); RC(dalloc(&c->d_cp, NM)); RC(dalloc(&c->d_m, NM));
+    RC(dalloc(&c->d_work, std::max<size_t>(8 * NM, 8192))); RC(dalloc(&c->d_rho_i, NM)); RC(dalloc(&c->d_scal, 64));
+    IPIC_CUDA(cudaMalloc(&c->d_acc, NSP_MAX * NM * sizeof(unsigned long long)));
+    IPIC_CUDA(cudaMemset(c->d_acc, 0, NSP_MAX * NM * sizeof(unsigned long long)));
+    const size_t tabsz = std::max(sizeof(CellTabNGP), sizeof(CellTabCIC));
+    IPIC_CUDA(cudaMalloc(&c->d_tab, NSP_MAX * NM * tabsz)); IPIC_CUDA(cudaMemset(c->d_tab, 0, NSP_MAX * NM * tabsz));
+    IPIC_CUDA(cudaMalloc(&c->d_counters, NSP_MAX * 8 * sizeof(unsigned long long)));
+    IPIC_CUDA(cudaMemset(c->d_counters, 0, NSP_MAX * 8 * sizeof(unsigned long long)));
+    IPIC_CUDA(cudaMallocHost(&c->h_scal, 64 * sizeof(double)));
+    IPIC_CUDA(cudaEventCreate(&c->ev0)); IPIC_CUDA(cudaEventCreate(&c->ev1));
+    *out = reinterpret_cast<ipic_handle>(c);
+    return IPIC_OK;
+}
+
+int ipic_destroy(ipic_handle h) {
+    CTX(h);
+    cudaStreamSynchronize(c->stream);
+    resolve_timing(*c);
+    for (auto &e : g_pool[c]) cudaEventDestroy(e);
+    g_pool.erase(c); g_pending.erase(c);
+    if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
+    for (auto &s : c->sp) { if (s.l) cudaFree(s.l); if (s.l2) cudaFree(s.l2); }
+    double *dp[] = {c->d_grid, c->d_dx, c->d_phi, c->d_phi_f, c->d_rho, c->d_J, c->d_E, c->d_a, c->d_b, c->d_c, c->d_cp, c->d_m, c->d_pcr, c->d_work,
+                    c->d_rho_i, c->d_scal, c->d_phi_k, c->d_res_k, c->d_norms, c->d_loss};
+    for (double *p : dp) if (p) cudaFree(p);
+    if (c->d_bc) cudaFree(c->d_bc);
+    if (c->d_acc) cudaFree(c->d_acc);
+    if (c->d_tab) cudaFree(c->d_tab);
+    if (c->d_counters) cudaFree(c->d_counters);
+    if (c->d_tileCount) cudaFree(c->d_tileCount);
+    if (c->d_tileOffset) cudaFree(c->d_tileOffset);
+    if (c->d_total) cudaFree(c->d_total);
+    if (c->d_slab) cudaFree(c->d_slab);
+    if (c->h_scal) cudaFreeHost(c->h_scal);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return IPIC_OK;
+}
+
+// potentialSolver_constructor: NGP mod_potentialSolver.f90:50-86 ; CIC :49-90
+int ipic_init_solver(ipic_handle h, double leftVoltage, double rightVoltage, double RF_frequency, double timeCurrent) {
+    CTX(h);
+    const int Nx = c->Nx, Nh = c->Nh;
+    const double pi = 4.0 * std::atan(1.0);
+    std::vector<double> phi(Nx, 0.0);
+    c->rho_const = 0.0; c->RF_half_amplitude = 0.0;
+    c->RF_rad_frequency = 2.0 * pi * RF_frequency;
+    c->boundPhi[0] = c->boundPhi[1] = 0.0; c->sourceTermVals[0] = c->sourceTermVals[1] = 0.0; c->RF_voltage = 0.0; c->RF_indx = 0;
+    if (c->scheme == IPIC_SCHEME_NGP) {
+        const int bl = c->h_bc[0], br = c->h_bc[Nx - 1];
+        if (bl == 1) phi[0] = leftVoltage;
+        if (bl == 4) { c->RF_half_amplitude = leftVoltage; phi[0] = c->RF_half_amplitude * std::sin(timeCurrent * c->RF_rad_frequency); }
+        if (br == 1) phi[Nx - 1] = rightVoltage;
+        if (br == 4) {
+            if (c->RF_half_amplitude != 0) { set_error("Half amplitude voltage for RF already set, have two RF boundaries!"); return IPIC_ERR_STOP; }
+            c->RF_half_amplitude = rightVoltage;
+            phi[Nx - 1] = c->RF_half_amplitude * std::sin(timeCurrent * c->RF_rad_frequency);
+        }
+        if (bl == 3) { phi[0] = leftVoltage; phi[Nx - 1] = leftVoltage; }
+        c->RF_bool = c->RF_rad_frequency > 0 && c->RF_half_amplitude > 0 && (bl == 4 || br == 4);
+    } else {
+        const int bl = c->h_bc[0], br = c->h_bc[Nh - 1];
+        if (bl == 1) { c->boundPhi[0] = leftVoltage; c->sourceTermVals[0] = -c->boundPhi[0] * 2.0 / c->h_dx[0]; }
+        else if (bl == 4) { c->RF_half_amplitude = leftVoltage; c->RF_voltage = c->RF_half_amplitude * std::sin(timeCurrent * c->RF_rad_frequency); c->RF_indx = 1; }
+        if (br == 1) { c->boundPhi[1] = rightVoltage; c->sourceTermVals[1] = -c->boundPhi[1] * 2.0 / c->h_dx[Nx - 1]; }
+        else if (br == 4) { c->RF_half_amplitude = rightVoltage; c->RF_voltage = c->RF_half_amplitude * std::sin(timeCurrent * c->RF_rad_frequency); c->RF_indx = 2; }
+        c->RF_bool = c->RF_rad_frequency > 0 && c->RF_half_amplitude > 0 && (bl == 4 || br == 4);
+    }
+    IPIC_CUDA(cudaMemcpy(c->d_phi, phi.data(), Nx * sizeof(double), cudaMemcpyHostToDevice));
+    IPIC_CUDA(cudaMemcpy(c->d_phi_f, phi.data(), Nx * sizeof(double), cudaMemcpyHostToDevice));
+    IPIC_CUDA(cudaMemset(c->d_rho, 0, Nx * sizeof(double)));
+    IPIC_CUDA(cudaMemset(c->d_J, 0, Nh * sizeof(double)));
+    IPIC_CUDA(cudaMemset(c->d_E, 0, Nh * sizeof(double)));
+    RC(field_setup(*c));
+    c->solver_ready = true;
+    return IPIC_OK;
+}
+
+int ipic_set_tridiag_mode(ipic_handle h, int mode) {
+    CTX(h);
+    if (mode != IPIC_TRIDIAG_PCR && mode != IPIC_TRIDIAG_THOMAS) return IPIC_ERR_ARG;
+    c->tridiag_mode = mode;
+    return IPIC_OK;
+}
+
+int ipic_add_species(ipic_handle h, double mass, double q, double w_p, int32_t *species) {
+    CTX(h);
+    if ((int)c->sp.size() >= NSP_MAX) { set_error("too many species"); return IPIC_ERR_ARG; }
+    SpeciesDev s;
+    s.mass = mass; s.q = q; s.w_p = w_p; s.q_over_m = q / mass; s.q_times_wp = q * w_p;
+    c->sp.push_back(s);
+    if (species) *species = (int32_t)c->sp.size() - 1;
+    return IPIC_OK;
+}
+#define SPECIES(sp) if ((sp) < 0 || (sp) >= (int)c->sp.size()) { set_error("bad species index"); return IPIC_ERR_ARG; }
+
+int ipic_set_weight(ipic_handle h, int32_t sp, double w_p) {
+    CTX(h); SPECIES(sp);
+    c->sp[sp].w_p = w_p; c->sp[sp].q_times_wp = c->sp[sp].q * w_p;
+    return IPIC_OK;
+}
+int ipic_upload_particles(ipic_handle h, int32_t sp, const double *ps, const int32_t *N_p, int32_t T, int32_t finalIdx) {
+    CTX(h); SPECIES(sp);
+    if (!ps || !N_p || T < 1 || finalIdx < 0) return IPIC_ERR_ARG;
+    Timed t(*c, "upload");
+    return upload_species(*c, sp, ps, N_p, T, finalIdx);
+}
+int ipic_download_particles(ipic_handle h, int32_t sp, double *ps, int32_t *N_p, int32_t T, int32_t finalIdx) {
+    CTX(h); SPECIES(sp);
+    if (!ps || !N_p || T < 1) return IPIC_ERR_ARG;
+    Timed t(*c, "download");
+    return download_species(*c, sp, ps, N_p, T, finalIdx);
+}
+int ipic_particle_count(ipic_handle h, int32_t sp, int64_t *n) { CTX(h); SPECIES(sp); *n = c->sp[sp].n; return IPIC_OK; }
+int ipic_generate_particles(ipic_handle h, int32_t sp, int64_t n, double T_eV, double v_drift, uint64_t seed) {
+    CTX(h); SPECIES(sp);
+    return generate_species(*c, sp, n, T_eV, v_drift, seed);
+}
+int ipic_sort_particles(ipic_handle h, int32_t sp) { CTX(h); SPECIES(sp); Timed t(*c, "sort"); return sort_species(*c, sp); }
+
+static double *field_ptr(Ctx *c, int which, int *n) {
+    switch (which) {
+    case IPIC_F_PHI: *n = c->Nx; return c->d_phi;
+    case IPIC_F_PHI_F: *n = c->Nx; return c->d_phi_f;
+    case IPIC_F_J: *n = c->Nh; return c->d_J;
+    case IPIC_F_RHO: *n = c->Nx; return c->d_rho;
+    case IPIC_F_EFIELD: *n = c->Nh; return c->d_E;
+    case IPIC_F_A_TRI: *n = c->Nx - 1; return c->d_a;
+    case IPIC_F_B_TRI: *n = c->Nx; return c->d_b;
+    case IPIC_F_C_TRI: *n = c->Nx - 1; return c->d_c;
+    }
+    *n = 0; return nullptr;
+}
+int ipic_get_field(ipic_handle h, int which, double *out, int32_t n) {
+    CTX(h);
+    int len; double *p = field_ptr(c, which, &len);
+    if (!p || !out || n < len) { set_error("ipic_get_field: bad selector or short buffer"); return IPIC_ERR_ARG; }
+    IPIC_CUDA(cudaMemcpyAsync(out, p, len * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    IPIC_CUDA(cudaStreamSynchronize(c->stream));
+    return IPIC_OK;
+}
+int ipic_set_field(ipic_handle h, int which, const double *in, int32_t n) {
+    CTX(h);
+    int len; double *p = field_ptr(c, which, &len);
+    if (!p || !in || n < len) { set_error("ipic_set_field: bad selector or short buffer"); return IPIC_ERR_ARG; }
+    IPIC_CUDA(cudaMemcpyAsync(p, in, len * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    IPIC_CUDA(cudaStreamSynchronize(c->stream));
+    return IPIC_OK;
+}
+
+#define NEED_SOLVER if (!c->solver_ready) { set_error("ipic_init_solver has not been called"); return IPIC_ERR_ARG; }
+
+int ipic_deposit_rho(ipic_handle h) {
+    CTX(h); NEED_SOLVER;
+    { Timed t(*c, "depositRho_kernels"); for (int s = 0; s < (int)c->sp.size(); ++s) RC(launch_deposit_rho(*c, s)); }
+    RC(allreduce_acc(*c));
+    return field_finalize_rho(*c);
+}
+int ipic_solve_tridiag_poisson(ipic_handle h, double t) { CTX(h); NEED_SOLVER; return field_poisson(*c, t); }
+int ipic_solve_initial_potential(ipic_handle h, double t) {
+    RC(ipic_deposit_rho(h));
+    return ipic_solve_tridiag_poisson(h, t);
+}
+int ipic_make_const_source_term(ipic_handle h) { CTX(h); NEED_SOLVER; return field_const_source(*c); }
+int ipic_make_half_time_efield(ipic_handle h) { CTX(h); NEED_SOLVER; return field_half_time_E(*c); }
+int ipic_solve_tridiag_ampere(ipic_handle h, double del_t) { CTX(h); NEED_SOLVER; Timed t(*c, "field_kernels"); return field_ampere(*c, del_t); }
+int ipic_set_rf_voltage(ipic_handle h, double t) { CTX(h); NEED_SOLVER; return set_rf_voltage(*c, t); }
+int ipic_reset_voltage(ipic_handle h) { CTX(h); NEED_SOLVER; return reset_voltage(*c); }
+
+int ipic_deposit_J(ipic_handle h, double del_t) {
+    CTX(h); NEED_SOLVER;
+    RC(field_half_time_E(*c));
+    RC(zero_counters(*c));
+    RC(sweep_deposit(*c, del_t));
+    RC(field_finalize_J(*c, del_t));
+    unsigned long long cnt[NSP_MAX * 8];
+    RC(read_counters(*c, cnt));
+    for (int s = 0; s < (int)c->sp.size(); ++s) c->sp[s].depositSubsteps = (long long)cnt[s * 8];
+    return IPIC_OK;
+}
+
+int ipic_move_particles(ipic_handle h, double del_t) {
+    CTX(h); NEED_SOLVER;
+    RC(field_half_time_E(*c));
+    return move_all(*c, del_t);
+}
+
+int ipic_get_move_stats(ipic_handle h, int32_t sp, ipic_move_stats *out) { CTX(h); SPECIES(sp); *out = c->sp[sp].stats; return IPIC_OK; }
+int ipic_get_deposit_substeps(ipic_handle h, int32_t sp, int64_t *n) { CTX(h); SPECIES(sp); *n = c->sp[sp].depositSubsteps; return IPIC_OK; }
+
+// initializeSolver  mod_nonLinSolvers.f90:41-81
+int ipic_initialize_solver(ipic_handle h, double eps_a, double eps_r, int solverType, int m_Anderson, double Beta_k, int maxIter) {
+    CTX(h);
+    if (solverType != 0 && solverType != 1) { set_error("Solver type incorrect!"); return IPIC_ERR_STOP; }
+    if (m_Anderson < 1 || m_Anderson > 31) { set_error("m_Anderson must be in 1..31"); return IPIC_ERR_ARG; }
+    c->eps_a = eps_a; c->eps_r = eps_r; c->solverType = solverType; c->m_Anderson = m_Anderson; c->Beta_k = Beta_k; c->maxIter = maxIter;
+    if (c->d_phi_k) { cudaFree(c->d_phi_k); cudaFree(c->d_res_k); cudaFree(c->d_norms); }
+    const size_t n = (size_t)c->Nx * (m_Anderson + 1);
+    IPIC_CUDA(cudaMalloc(&c->d_phi_k, n * sizeof(double))); IPIC_CUDA(cudaMemset(c->d_phi_k, 0, n * sizeof(double)));
+    IPIC_CUDA(cudaMalloc(&c->d_res_k, n * sizeof(double))); IPIC_CUDA(cudaMemset(c->d_res_k, 0, n * sizeof(double)));
+    IPIC_CUDA(cudaMalloc(&c->d_norms, (m_Anderson + 2) * sizeof(double)));
+    return IPIC_OK;
+}
+
+int ipic_solve_div_ampere_anderson(ipic_handle h, double del_t) {
+    CTX(h); NEED_SOLVER;
+    if (!c->d_phi_k) { set_error("ipic_initialize_solver has not been called"); return IPIC_ERR_ARG; }
+    RC(zero_counters(*c));
+    return solve_div_ampere_anderson(*c, del_t);
+}
+
+// solvePotential  mod_nonLinSolvers.f90:198-215
+int ipic_solve_potential(ipic_handle h, double del_t, double *remainDel_t, double *currDel_t, double timeCurrent) {
+    CTX(h); NEED_SOLVER;
+    if (!c->d_phi_k || !remainDel_t || !currDel_t) { set_error("ipic_solve_potential: solver not initialised / null argument"); return IPIC_ERR_ARG; }
+    c->sweeps = 0; c->substeps = 0;
+    RC(zero_counters(*c));
+    RC(reset_voltage(*c));
+    if (c->solverType != 0) { set_error("solverType 1 (JFNK): drive NITSOL on the host with ipic_func_nitsol as the residual callback"); return IPIC_ERR_UNSUPPORTED; }
+    // deposit sub-steps accumulate in device counter slot 0 over all sweeps; harvested after the step
+    int rc = adaptive_anderson(*c, del_t, *remainDel_t, *currDel_t, timeCurrent);
+    if (rc) return rc;
+    unsigned long long cnt[NSP_MAX * 8];
+    RC(read_counters(*c, cnt));
+    for (int s = 0; s < (int)c->sp.size(); ++s) c->substeps += (long long)cnt[s * 8];
+    return IPIC_OK;
+}
+
+// funcNitsol  mod_nonLinSolvers.f90:218-239 : phi_f <- xcur ; depositJ ; solve_tridiag_Ampere ; fcur = xcur - phi_f
+int ipic_func_nitsol(ipic_handle h, int32_t n, const double *xcur, double *fcur, double del_t) {
+    CTX(h); NEED_SOLVER;
+    if (n != c->Nx || !xcur || !fcur) return IPIC_ERR_ARG;
+    double *d_x = c->d_work, *d_f = c->d_work + (c->Nx + 2);
+    IPIC_CUDA(cudaMemcpyAsync(d_x, xcur, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    IPIC_CUDA(cudaMemcpyAsync(c->d_phi_f, d_x, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    RC(field_half_time_E(*c));
+    RC(sweep_deposit(*c, del_t));
+    RC(field_finalize_J(*c, del_t));
+    RC(field_ampere(*c, del_t));
+    RC(field_residual(*c, d_x, d_f));
+    IPIC_CUDA(cudaMemcpyAsync(fcur, d_f, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    IPIC_CUDA(cudaStreamSynchronize(c->stream));
+    return IPIC_OK;
+}
+
+int ipic_get_solver_stats(ipic_handle h, ipic_solver_stats *out) {
+    CTX(h);
+    resolve_timing(*c);
+    out->iterNumPicard = c->iterNumPicard; out->iterNumAdaptiveSteps = c->iterNumAdaptiveSteps; out->amountTimeSplits = c->amountTimeSplits;
+    out->sweeps = c->sweeps; out->substeps = c->substeps;
+    out->moverSeconds = (c->timing["depositJ_kernels"].ms + c->timing["moveParticles_kernels"].ms + c->timing["compaction"].ms) * 1e-3;
+    out->potSeconds = c->timing["field_kernels"].ms * 1e-3;
+    out->lastResidualNorm = c->lastNorm;
+    return IPIC_OK;
+}
+int ipic_get_norm_history(ipic_handle h, double *out, int32_t nmax, int32_t *n) {
+    CTX(h);
+    *n = (int32_t)c->normHist.size();
+    for (int i = 0; i < *n && i < nmax; ++i) out[i] = c->normHist[i];
+    return IPIC_OK;
+}
+
+int ipic_get_total_PE(ipic_handle h, int future, double *out) { CTX(h); NEED_SOLVER; return field_diag(*c, future ? 1 : 0, 0.0, out); }
+int ipic_get_JdotE(ipic_handle h, double del_t, double *out) { CTX(h); NEED_SOLVER; return field_diag(*c, 2, del_t, out); }
+int ipic_get_energy_from_boundary(ipic_handle h, double del_t, double *out) { CTX(h); NEED_SOLVER; return field_diag(*c, 3, del_t, out); }
+int ipic_get_error_tridiag_poisson(ipic_handle h, double *out) { CTX(h); NEED_SOLVER; return field_diag(*c, 4, 0.0, out); }
+int ipic_get_charge_continuity_error(ipic_handle h, const double *rho_i, double del_t, double *out) {
+    CTX(h); NEED_SOLVER;
+    IPIC_CUDA(cudaMemcpyAsync(c->d_rho_i, rho_i, c->Nx * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    return field_diag(*c, 5, del_t, out);
+}
+int ipic_get_total_KE(ipic_handle h, int32_t sp, double *out) {
+    CTX(h); SPECIES(sp);
+    double m4[4]; RC(particle_moments(*c, sp, m4));
+    *out = m4[0] * c->sp[sp].mass * 0.5 * c->sp[sp].w_p;   // mod_particle.f90:228
+    return IPIC_OK;
+}
+int ipic_get_total_momentum(ipic_handle h, int32_t sp, double *out3) {
+    CTX(h); SPECIES(sp);
+    double m4[4]; RC(particle_moments(*c, sp, m4));
+    for (int k = 0; k < 3; ++k) out3[k] = m4[k + 1] * c->sp[sp].w_p * c->sp[sp].mass;   // :215
+    return IPIC_OK;
+}
+
+int ipic_nccl_unique_id(void *out128) {
+    RC(nccl_load());
+    int rc = g_nccl.GetUniqueId(out128);
+    if (rc) { set_error("ncclGetUniqueId failed"); return IPIC_ERR_NCCL; }
+    return IPIC_OK;
+}
+int ipic_comm_init(ipic_handle h, int32_t nranks, int32_t rank, const void *uid) {
+    CTX(h);
+    if (nranks < 1 || rank < 0 || rank >= nranks) return IPIC_ERR_ARG;
+    c->nranks = nranks; c->rank = rank;
+    if (nranks == 1) return IPIC_OK;
+    RC(nccl_load());
+    NcclUid id; std::memcpy(id.b, uid, 128);
+    int rc = g_nccl.CommInitRank(&c->nccl_comm, nranks, id, rank);
+    if (rc) { set_error(std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?")); return IPIC_ERR_NCCL; }
+    return IPIC_OK;
+}
+
+int ipic_set_option(ipic_handle h, const char *name, double value) {
+    CTX(h);
+    const std::string k(name ? name : "");
+    if (k == "refill_min") c->refill_min = (int)value;
+    else if (k == "push_blocks") c->push_blocks = (int)value;
+    else if (k == "timing") c->timing_on = value != 0.0;
+    else if (k == "lazy_compaction") c->lazy_compaction = (int)value;
+    else { set_error("unknown option " + k); return IPIC_ERR_ARG; }
+    return IPIC_OK;
+}
+int ipic_get_timing(ipic_handle h, const char *name, double *ms, int64_t *launches) {
+    CTX(h);
+    resolve_timing(*c);
+    auto it = c->timing.find(name ? name : "");
+    if (it == c->timing.end()) { *ms = 0.0; *launches = 0; return IPIC_OK; }
+    *ms = it->second.ms; *launches = it->second.launches;
+    return IPIC_OK;
+}
+int ipic_reset_timing(ipic_handle h) { CTX(h); resolve_timing(*c); c->timing.clear(); return IPIC_OK; }
+int ipic_synchronize(ipic_handle h) { CTX(h); IPIC_CUDA(cudaStreamSynchronize(c->stream)); return IPIC_OK; }
+
+}  // extern "C"

@@ -1,0 +1,787 @@
+// Grid-sized ("field") work of the implicit step as single-CTA kernels: everything between two particle
+// sweeps stays on the device -- J/rho finalisation, half-time E + per-cell push tables, the tridiagonal
+// solves (parallel cyclic reduction with cached level coefficients, or a Thomas sweep in the reference's
+// operation order), the Anderson history / mixing and the conservation diagnostics.
+//
+// Reference semantics restated here (never copied): OpenMP/NGP/src/mod_potentialSolver.f90,
+// OpenMP/CIC/src/mod_potentialSolver.f90, OpenMP/{NGP,CIC}/src/mod_domain.f90 (smoothField),
+// OpenMP/SharedModules/src/mod_nonLinSolvers.f90:85-160, mod_BasicFunctions.f90:218-265.
+#include "ipic_common.cuh"
+#include <cmath>
+#include <algorithm>
+
+namespace ipic {
+
+constexpr int FT = 1024;   // threads of the field CTA
+
+enum : unsigned {
+    OP_FINALIZE_RHO = 1u << 0,
+    OP_POISSON = 1u << 1,
+    OP_CONST_SOURCE = 1u << 2,
+    OP_FINALIZE_J = 1u << 3,
+    OP_AMPERE = 1u << 4,
+    OP_AND_STORE0 = 1u << 5,   // phi_k(:,1) = phi_f
+    OP_AND_FIRST = 1u << 6,    // phi_k(:,2) = phi_f ; R(:,1) = phi_k2 - phi_k1 ; norm
+    OP_AND_RESID = 1u << 7,    // R(:,index) = phi_f - phi_k(:,index) ; norm
+    OP_AND_MIX = 1u << 8,      // normal equations + next iterate -> phi_f
+    OP_HALF_E = 1u << 9,       // EField + push tables
+    OP_DIAG = 1u << 10,
+    OP_RESID_F = 1u << 11,     // f = x - phi_f  (funcNitsol)
+};
+
+struct FieldArgs {
+    int scheme, Nx, Nh, smooth, nsp, tridiag_mode, pcr_levels, acc_stride, tab_cells;
+    const double *grid, *dx;
+    const int *bc;
+    double *phi, *phi_f, *rho, *J, *E, *a, *b, *c, *cp, *m, *pcr, *work, *scal, *rho_i;
+    unsigned long long *acc;
+    void *tab;
+    double qw[NSP_MAX], qm[NSP_MAX];
+    double del_t, rho_const, RF_voltage, bound1, bound2, src1, src2, poisson_rf_value;
+    double *phi_k, *res_k, *norms;
+    int and_i, and_m;          // loop index i and m_Anderson
+    double beta;
+    int diag_which;
+    const double *xin; double *fout;
+};
+
+// 1-based accessors so that every stencil reads like the reference line it restates
+#define GRID(i) A.grid[(i)-1]
+#define DX(i) A.dx[(i)-1]
+#define BC(i) A.bc[(i)-1]
+#define PHI(i) A.phi[(i)-1]
+#define PHIF(i) A.phi_f[(i)-1]
+#define RHO(i) A.rho[(i)-1]
+#define JJ(i) A.J[(i)-1]
+#define EF(i) A.E[(i)-1]
+
+__device__ __forceinline__ int fmodulo(int a, int p) { int r = a % p; return r < 0 ? r + p : r; }
+
+// deterministic block sum (fixed tree); result valid in every thread
+__device__ double block_sum(double x) {
+    __shared__ double sh[FT / 32];
+    __shared__ double tot;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    __syncthreads();
+    if (lane == 0) sh[warp] = x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < FT / 32; ++w) s += sh[w];
+        tot = s;
+    }
+    __syncthreads();
+    return tot;
+}
+
+// smoothField: NGP mod_domain.f90:298-324 ; CIC mod_domain.f90:289-312.  raw/out are 1-based via (i)-1.
+__device__ void dev_smooth(const FieldArgs &A, const double *raw, double *out) {
+    const int Nh = A.Nh, Nx = A.Nx;
+#define RAW(i) raw[(i)-1]
+    if (A.scheme == 0) {
+        for (int i = 1 + threadIdx.x; i <= Nh; i += FT) {
+            const int bv = BC(i + 1) - BC(i);
+            double r = 0.0;
+            switch (bv) {
+            case 0: r = 0.25 * (RAW(i - 1) + 2.0 * RAW(i) + RAW(i + 1)); break;
+            case -1: case -4: r = 0.25 * (3.0 * RAW(1) + RAW(2)); break;
+            case 1: case 4: r = 0.25 * (3.0 * RAW(Nh) + RAW(Nh - 1)); break;
+            case -2: r = 0.25 * (RAW(1) + RAW(2)); break;
+            case 2: r = 0.25 * (RAW(Nh) + RAW(Nh - 1)); break;
+            case -3: r = 0.25 * (RAW(Nh) + 2.0 * RAW(1) + RAW(2)); break;
+            case 3: r = 0.25 * (RAW(Nh - 1) + 2.0 * RAW(Nh) + RAW(1)); break;
+            default: r = out[i - 1]; break;
+            }
+            out[i - 1] = r;
+        }
+    } else {
+        for (int i = 1 + threadIdx.x; i <= Nh; i += FT) {
+            double r = 0.0;
+            if (i == 1) {
+                switch (BC(1)) {
+                case 1: case 4: r = 0.25 * (2.0 * RAW(1) + 2.0 * RAW(2)); break;
+                case 2: r = 0.0; break;
+                case 3: r = 0.25 * (RAW(Nh - 1) + 2.0 * RAW(1) + RAW(2)); break;
+                }
+            } else if (i == Nh) {
+                switch (BC(Nh)) {
+                case 1: case 4: r = 0.25 * (2.0 * RAW(Nh) + 2.0 * RAW(Nh - 1)); break;
+                case 2: r = 0.0; break;
+                case 3: r = 0.25 * (RAW(Nh - 1) + 2.0 * RAW(1) + RAW(2)); break;   // newField(N_h) = newField(1)
+                }
+            } else {
+                r = 0.25 * (RAW(i - 1) + 2.0 * RAW(i) + RAW(i + 1));
+            }
+            out[i - 1] = r;
+        }
+    }
+#undef RAW
+}
+
+// Sum the per-species int64 grids (species order, scaled by q*w_p) into dst[0..n-1]; zero the grids.
+__device__ void dev_collect(const FieldArgs &A, double *dst, int n) {
+    for (int i = threadIdx.x; i < n; i += FT) {
+        double acc = 0.0;
+        for (int s = 0; s < A.nsp; ++s) {
+            unsigned long long *p = A.acc + (size_t)s * A.acc_stride + (i + 1);
+            const double v = (double)(long long)(*p) * FX_INV;
+            *p = 0ull;
+            if (s == 0) acc = v * A.qw[0];
+            else acc = acc + v * A.qw[s];
+        }
+        dst[i] = acc;
+    }
+}
+
+// tridiagonal solve of (a,b,c) x = d, d in shared memory (1-based via (i)-1), result left in d.
+__device__ void dev_tridiag(const FieldArgs &A, double *d, double *tmp) {
+    const int n = A.Nx;
+    if (A.tridiag_mode == IPIC_TRIDIAG_THOMAS) {
+        // Thomas sweep in the reference's operation order (no FMA contraction): NGP :308-328 / CIC :282-299
+        if (threadIdx.x == 0) {
+            d[0] = __ddiv_rn(d[0], A.b[0]);
+            for (int i = 2; i <= n; ++i)
+                d[i - 1] = __ddiv_rn(__dsub_rn(d[i - 1], __dmul_rn(d[i - 2], A.a[i - 2])), A.m[i - 1]);
+            for (int i = n - 1; i >= 1; --i) d[i - 1] = __dsub_rn(d[i - 1], __dmul_rn(A.cp[i - 1], d[i]));
+        }
+        __syncthreads();
+        return;
+    }
+    // parallel cyclic reduction; the matrix is constant, so alpha/gamma of every level are precomputed
+    double *src = d, *dst = tmp;
+    int stride = 1;
+    for (int lev = 0; lev < A.pcr_levels; ++lev) {
+        const double *al = A.pcr + (size_t)lev * 2 * n, *ga = al + n;
+        for (int i = threadIdx.x; i < n; i += FT) {
+            double v = src[i];
+            if (i - stride >= 0) v = fma(al[i], src[i - stride], v);
+            if (i + stride < n) v = fma(ga[i], src[i + stride], v);
+            dst[i] = v;
+        }
+        __syncthreads();
+        double *t = src; src = dst; dst = t;
+        stride <<= 1;
+    }
+    const double *inv = A.pcr + (size_t)A.pcr_levels * 2 * n;
+    for (int i = threadIdx.x; i < n; i += FT) d[i] = src[i] * inv[i];
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsigned ops) {
+    extern __shared__ __align__(16) double sm[];
+    const int Nx = A.Nx, Nh = A.Nh;
+    const int NM = max(Nx, Nh) + 2;
+    double *s0 = sm, *s1 = sm + NM;   // two shared work vectors
+
+    // ---------------- depositRho epilogue: NGP :150-187 ; CIC :146-172 ----------------
+    if (ops & OP_FINALIZE_RHO) {
+        dev_collect(A, s0, Nx);
+        __syncthreads();
+#define D(i) s0[(i)-1]
+        if (A.scheme == 0) {
+            if (threadIdx.x == 0) {
+                switch (BC(1)) {
+                case 1: case 4: D(1) = 0.0; break;
+                case 2: D(1) = 2.0 * D(1); break;
+                case 3: D(1) = D(1) + D(Nx); break;
+                }
+                switch (BC(Nx)) {
+                case 1: case 4: D(Nx) = 0.0; break;
+                case 2: D(Nx) = 2.0 * D(Nx); break;
+                case 3: D(Nx) = D(1); break;
+                }
+            }
+            __syncthreads();
+            for (int i = 1 + threadIdx.x; i <= Nx; i += FT) {
+                double r = D(i);
+                if (A.smooth) {
+                    switch (BC(i)) {
+                    case 0: r = 0.25 * (D(i - 1) + 2.0 * D(i) + D(i + 1)); break;
+                    case 1: case 4: r = 0.0; break;
+                    case 2: r = (i == 1) ? 0.25 * (2.0 * D(1) + 2.0 * D(2)) : 0.25 * (2.0 * D(Nx) + 2.0 * D(Nh)); break;
+                    case 3: r = 0.25 * (D(Nh) + 2.0 * D(1) + D(2)); break;
+                    }
+                }
+                RHO(i) = r;
+            }
+        } else {
+            for (int i = 1 + threadIdx.x; i <= Nx; i += FT) {
+                double r = D(i);
+                if (A.smooth) {
+                    switch (BC(i + 1) - BC(i)) {
+                    case 0: r = 0.25 * (D(i - 1) + 2.0 * D(i) + D(i + 1)); break;
+                    case -1: case -4: r = 0.25 * (D(1) + D(2)); break;
+                    case 1: case 4: r = 0.25 * (D(Nx) + D(Nx - 1)); break;
+                    case -2: r = 0.25 * (3.0 * D(1) + D(2)); break;
+                    case 2: r = 0.25 * (3.0 * D(Nx) + D(Nx - 1)); break;
+                    case -3: r = 0.25 * (D(Nx) + 2.0 * D(1) + D(2)); break;
+                    case 3: r = 0.25 * (D(1) + 2.0 * D(Nx) + D(Nx - 1)); break;
+                    }
+                }
+                RHO(i) = r;
+            }
+        }
+#undef D
+        __syncthreads();
+    }
+
+    // ---------------- solve_tridiag_Poisson: NGP :190-226 ; CIC :175-218 ----------------
+    if (ops & OP_POISSON) {
+        for (int i = 1 + threadIdx.x; i <= Nx; i += FT) {
+            double d = 0.0;
+            if (A.scheme == 0) {
+                switch (BC(i)) {
+                case 0: case 2: d = (-RHO(i) - A.rho_const) / eps_0; break;
+                case 1: case 3: d = PHI(i); break;
+                case 4: d = A.poisson_rf_value; break;
+                }
+            } else {
+                d = (-RHO(i) - A.rho_const) / eps_0;
+                if (i == 1) d = d + A.src1;
+                if (i == Nx) d = d + A.src2;
+            }
+            s0[i - 1] = d;
+        }
+        __syncthreads();
+        dev_tridiag(A, s0, s1);
+        for (int i = threadIdx.x; i < Nx; i += FT) { A.phi[i] = s0[i]; A.phi_f[i] = s0[i]; }
+        __syncthreads();
+    }
+
+    // ---------------- makeConstSourceTerm: NGP :267-286 ; CIC :246-270 ----------------
+    if (ops & OP_CONST_SOURCE) {
+        for (int i = 1 + threadIdx.x; i <= Nx; i += FT) {
+            double r = RHO(i);
+            if (A.scheme == 0) {
+                switch (BC(i)) {
+                case 0: r = -(PHI(i) - PHI(i - 1)) / DX(i - 1) + (PHI(i + 1) - PHI(i)) / DX(i); break;
+                case 1: case 3: case 4: r = PHIF(i); break;
+                case 2:
+                    if (i == 1) r = -2.0 * (PHI(i) - PHI(i + 1)) / DX(i);
+                    else if (i == Nx) r = -2.0 * (PHI(i) - PHI(i - 1)) / DX(i - 1);
+                    break;
+                }
+            } else {
+                switch (BC(i + 1) - BC(i)) {
+                case 0: r = -(PHI(i) - PHI(i + 1)) / (GRID(i + 1) - GRID(i)) + (PHI(i - 1) - PHI(i)) / (GRID(i) - GRID(i - 1)); break;
+                case -1: case -4: r = -(PHI(i) - PHI(i + 1)) / (GRID(i + 1) - GRID(i)) + 2.0 * (A.bound1 - PHI(1)) / DX(1) + A.src1; break;
+                case 1: case 4: r = -2.0 * (PHI(Nx) - A.bound2) / DX(Nx) + (PHI(i - 1) - PHI(i)) / (GRID(i) - GRID(i - 1)) + A.src2; break;
+                case -2: r = -(PHI(i) - PHI(i + 1)) / (GRID(i + 1) - GRID(i)); break;
+                case 2: r = (PHI(i - 1) - PHI(i)) / (GRID(i) - GRID(i - 1)); break;
+                case -3: r = -(PHI(i) - PHI(i + 1)) / (GRID(i + 1) - GRID(i)) + 2.0 * (PHI(Nx) - PHI(1)) / (DX(1) + DX(Nx)); break;
+                case 3: r = -2.0 * (PHI(Nx) - PHI(1)) / (DX(1) + DX(Nx)) + (PHI(i - 1) - PHI(i)) / (GRID(i) - GRID(i - 1)); break;
+                }
+            }
+            RHO(i) = r;
+        }
+        __syncthreads();
+    }
+
+    // ---------------- depositJ epilogue: NGP mod_particleMover.f90:145-156 ; CIC mod_particleMoverPicard.f90:165-194 ----------------
+    if (ops & OP_FINALIZE_J) {
+        dev_collect(A, s0, Nh);
+        __syncthreads();
+        if (A.scheme == 1 && threadIdx.x == 0) {
+#define W(i) s0[(i)-1]
+            switch (BC(1)) {
+            case 1: case 4: W(1) = 2.0 * W(1); break;
+            case 2: W(1) = 0.0; break;
+            case 3: W(1) = W(1) + W(Nh); break;
+            }
+            switch (BC(Nh)) {
+            case 1: case 4: W(Nh) = 2.0 * W(Nh); break;
+            case 2: W(Nh) = 0.0; break;
+            case 3: W(Nh) = W(1); break;
+            }
+#undef W
+        }
+        __syncthreads();
+        if (A.smooth) {
+            dev_smooth(A, s0, s1);
+            __syncthreads();
+            for (int i = threadIdx.x; i < Nh; i += FT) A.J[i] = s1[i] / A.del_t;
+        } else {
+            for (int i = threadIdx.x; i < Nh; i += FT) A.J[i] = s0[i] / A.del_t;
+        }
+        __syncthreads();
+    }
+
+    // ---------------- solve_tridiag_Ampere: NGP :288-330 ; CIC :272-301 ----------------
+    if (ops & OP_AMPERE) {
+        for (int i = 1 + threadIdx.x; i <= Nx; i += FT) {
+            double d = 0.0;
+            if (A.scheme == 0) {
+                switch (BC(i)) {
+                case 0: d = (JJ(i) - JJ(i - 1)) * A.del_t / eps_0; break;
+                case 1: case 3: case 4: d = 0.0; break;
+                case 2:
+                    if (i == 1) d = 2.0 * (A.del_t * JJ(i) / eps_0);
+                    else if (i == Nx) d = 2.0 * (-A.del_t * JJ(i - 1) / eps_0);
+                    break;
+                }
+                d = d + RHO(i);
+            } else {
+                d = (JJ(i + 1) - JJ(i)) * A.del_t / eps_0 + RHO(i);
+            }
+            s0[i - 1] = d;
+        }
+        __syncthreads();
+        dev_tridiag(A, s0, s1);
+        for (int i = threadIdx.x; i < Nx; i += FT) A.phi_f[i] = s0[i];
+        __syncthreads();
+    }
+
+    // ---------------- Anderson bookkeeping: mod_nonLinSolvers.f90:98-157 ----------------
+    const int M1 = A.and_m + 1;
+#define PK(i, c) A.phi_k[(size_t)((c)-1) * Nx + (i)-1]
+#define RK(i, c) A.res_k[(size_t)((c)-1) * Nx + (i)-1]
+    if (ops & OP_AND_STORE0) {
+        for (int i = 1 + threadIdx.x; i <= Nx; i += FT) PK(i, 1) = PHIF(i);
+        __syncthreads();
+    }
+    if (ops & (OP_AND_FIRST | OP_AND_RESID)) {
+        const int index = (ops & OP_AND_FIRST) ? 1 : fmodulo(A.and_i, M1) + 1;
+        double part = 0.0;
+        for (int i = 1 + threadIdx.x; i <= Nx; i += FT) {
+            double r;
+            if (ops & OP_AND_FIRST) { PK(i, 2) = PHIF(i); r = PHIF(i) - PK(i, 1); }
+            else r = PHIF(i) - PK(i, index);
+            RK(i, index) = r;
+            part += r * r;
+        }
+        const double nrm = sqrt(block_sum(part));
+        if (threadIdx.x == 0) { A.norms[index - 1] = nrm; A.scal[0] = nrm; }
+        __syncthreads();
+    }
+    if (ops & OP_AND_MIX) {
+        const int i = A.and_i, m = A.and_m;
+        const int index = fmodulo(i, M1) + 1;
+        const int m_k = min(i, m);
+        // normal equations A^T A alpha = A^T r with columns fitMat(:,j+1) = r_index - r_{col(i-m_k+j)}
+        double *An = s0;                 // m_k x m_k column-major
+        double *bn = s0 + 32 * 32;       // m_k
+        double *alpha = bn + 64;         // m_k + 1
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int npairs = m_k * m_k + m_k;
+        for (int p = warp; p < npairs; p += FT / 32) {
+            int j, k;
+            if (p < m_k * m_k) { j = p % m_k; k = p / m_k; } else { j = p - m_k * m_k; k = -1; }
+            const int cj = fmodulo(i - m_k + j, M1) + 1;
+            const int ck = (k >= 0) ? fmodulo(i - m_k + k, M1) + 1 : 0;
+            double acc = 0.0;
+            for (int r = 1 + lane; r <= Nx; r += 32) {
+                const double ri = RK(r, index);
+                const double fj = ri - RK(r, cj);
+                const double fk = (k >= 0) ? (ri - RK(r, ck)) : ri;
+                acc += fj * fk;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+            if (lane == 0) { if (k >= 0) An[j + m_k * k] = acc; else bn[j] = acc; }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            // solveGaussElimination, no pivoting (mod_BasicFunctions.f90:218-254)
+            const int n = m_k;
+#define AA(r, c) An[((r)-1) + n * ((c)-1)]
+            for (int k = 1; k <= n - 1; ++k) {
+                const double k1 = AA(k, k);
+                for (int r = k + 1; r <= n; ++r) AA(r, k) = AA(r, k) / k1;
+                for (int j = k + 1; j <= n; ++j) {
+                    const double k2 = AA(k, j);
+                    for (int r = k + 1; r <= n; ++r) AA(r, j) = AA(r, j) - AA(r, k) * k2;
+                }
+            }
+            for (int r = 1; r <= n; ++r) for (int j = 1; j <= r - 1; ++j) bn[r - 1] = bn[r - 1] - AA(r, j) * bn[j - 1];
+            for (int r = n; r >= 1; --r) {
+                for (int j = r + 1; j <= n; ++j) bn[r - 1] = bn[r - 1] - AA(r, j) * bn[j - 1];
+                bn[r - 1] = bn[r - 1] / AA(r, r);
+            }
+#undef AA
+            double sa = 0.0;
+            for (int j = 0; j < n; ++j) { alpha[j] = bn[j]; sa += bn[j]; }
+            alpha[n] = 1.0 - sa;
+        }
+        __syncthreads();
+        const int cn = fmodulo(i + 1, M1) + 1, c0 = fmodulo(i - m_k, M1) + 1;
+        for (int r = 1 + threadIdx.x; r <= Nx; r += FT) {
+            double x = alpha[0] * (A.beta * RK(r, c0) + PK(r, c0));
+            for (int j = 1; j <= m_k; ++j) {
+                const int cj = fmodulo(i - m_k + j, M1) + 1;
+                x = x + alpha[j] * (A.beta * RK(r, cj) + PK(r, cj));
+            }
+            PK(r, cn) = x;
+            PHIF(r) = x;
+        }
+        __syncthreads();
+    }
+#undef PK
+#undef RK
+
+    if (ops & OP_RESID_F) {   // funcNitsol: fcur = xcur - phi_f   (mod_nonLinSolvers.f90:236)
+        for (int i = threadIdx.x; i < Nx; i += FT) A.fout[i] = A.xin[i] - A.phi_f[i];
+        __syncthreads();
+    }
+
+    // ---------------- makeHalfTimeEField (+ push tables): NGP :392-406 ; CIC :333-366, Picard :92-94 ----------------
+    if (ops & OP_HALF_E) {
+        if (A.scheme == 0) {
+            for (int i = 1 + threadIdx.x; i <= Nh; i += FT) s0[i - 1] = 0.5 * (PHIF(i) + PHI(i) - PHIF(i + 1) - PHI(i + 1));
+            __syncthreads();
+            if (A.smooth) {
+                dev_smooth(A, s0, s1);
+                __syncthreads();
+                for (int i = 1 + threadIdx.x; i <= Nh; i += FT) EF(i) = s1[i - 1] / DX(i);
+            } else {
+                for (int i = 1 + threadIdx.x; i <= Nh; i += FT) EF(i) = s0[i - 1] / DX(i);
+            }
+            __syncthreads();
+            for (int s = 0; s < A.nsp; ++s) {
+                CellTabNGP *T = reinterpret_cast<CellTabNGP *>(A.tab) + (size_t)s * A.tab_cells;
+                for (int cI = 1 + threadIdx.x; cI <= Nh; cI += FT) {
+                    const double a = A.qm[s] * EF(cI), dx = DX(cI);
+                    CellTabNGP t;
+                    t.a = a; t.inv_dx = 1.0 / dx; t.two_a_dx = 2.0 * a * dx; t.inv_a = 1.0 / a;
+                    T[cI] = t;
+                }
+            }
+        } else {
+            for (int i = 1 + threadIdx.x; i <= Nh; i += FT) {
+                double w;
+                if (i == 1) {
+                    switch (BC(1)) {
+                    case 1: w = (2.0 * A.bound1 - PHI(1) - PHIF(1)); break;
+                    case 2: w = 0.0; break;
+                    case 3: w = 0.5 * (PHI(Nx) + PHIF(Nx) - PHI(1) - PHIF(1)); break;
+                    default: w = (A.bound1 + A.RF_voltage - PHI(1) - PHIF(1)); break;   // 4
+                    }
+                } else if (i == Nh) {
+                    switch (BC(Nh)) {
+                    case 1: w = PHI(Nx) + PHIF(Nx) - 2.0 * A.bound2; break;
+                    case 2: w = 0.0; break;
+                    case 3: w = 0.5 * (PHI(Nx) + PHIF(Nx) - PHI(1) - PHIF(1)); break;   // workArray(N_h) = workArray(1)
+                    default: w = PHI(Nx) + PHIF(Nx) - A.bound2 - A.RF_voltage; break;   // 4
+                    }
+                } else {
+                    w = 0.5 * (PHIF(i - 1) + PHI(i - 1) - PHIF(i) - PHI(i));
+                }
+                s0[i - 1] = w;
+            }
+            __syncthreads();
+            if (A.smooth) {
+                dev_smooth(A, s0, A.E);
+            } else {
+                for (int i = threadIdx.x; i < Nh; i += FT) A.E[i] = s0[i];
+            }
+            __syncthreads();
+            for (int s = 0; s < A.nsp; ++s) {
+                CellTabCIC *T = reinterpret_cast<CellTabCIC *>(A.tab) + (size_t)s * A.tab_cells;
+                for (int cI = 1 + threadIdx.x; cI <= Nx; cI += FT) {
+                    const double dx = DX(cI), el = EF(cI), er = EF(cI + 1);
+                    CellTabCIC t;
+                    t.A0 = A.qm[s] * el; t.A1 = A.qm[s] * (er - el); t.inv_dx = 1.0 / dx; t.dx = dx;
+                    t.cap = 0.1 * dx / sqrt(fabs(A.qm[s] * (el - er)));
+                    t.pad[0] = t.pad[1] = t.pad[2] = 0.0;
+                    T[cI] = t;
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---------------- conservation diagnostics ----------------
+    if (ops & OP_DIAG) {
+        const int wch = A.diag_which;
+        double part = 0.0, res = 0.0;
+        if (wch == 0 || wch == 1) {   // getTotalPE(future = wch): NGP :408-420 ; CIC :369-413
+            const double *ph = wch ? A.phi_f : A.phi;
+            if (A.scheme == 0) {
+                for (int i = 1 + threadIdx.x; i <= Nh; i += FT) { const double dphi = ph[i] - ph[i - 1]; part += dphi * dphi / DX(i); }
+                res = 0.5 * eps_0 * block_sum(part);
+            } else {
+                for (int i = 1 + threadIdx.x; i <= Nx - 1; i += FT) { const double dphi = ph[i] - ph[i - 1]; part += dphi * dphi / (GRID(i + 1) - GRID(i)); }
+                res = 0.5 * eps_0 * block_sum(part);
+                const double p1 = ph[0], pN = ph[Nx - 1];
+                if (wch) {
+                    switch (BC(1)) {
+                    case 1: res += eps_0 * (A.bound1 - p1) * (A.bound1 - p1) / DX(1); break;
+                    case 3: res += eps_0 * (pN - p1) * (pN - p1) / (DX(1) + DX(Nx)); break;
+                    case 4: res += eps_0 * (A.RF_voltage - p1) * (A.RF_voltage - p1) / DX(1); break;
+                    }
+                    switch (BC(Nh)) {
+                    case 1: res += eps_0 * (A.bound2 - pN) * (A.bound2 - pN) / DX(Nx); break;
+                    case 4: res += eps_0 * (A.RF_voltage - pN) * (A.RF_voltage - pN) / DX(Nx); break;
+                    }
+                } else {
+                    switch (BC(1)) {
+                    case 1: case 4: res += eps_0 * (A.bound1 - p1) * (A.bound1 - p1) / DX(1); break;
+                    case 3: res += eps_0 * (pN - p1) * (pN - p1) / (DX(1) + DX(Nx)); break;
+                    }
+                    switch (BC(Nh)) {
+                    case 1: case 4: res += eps_0 * (A.bound2 - pN) * (A.bound2 - pN) / DX(Nx); break;
+                    }
+                }
+            }
+        } else if (wch == 2) {   // getJdotE: NGP :422-430 ; CIC :415-426
+            if (A.scheme == 0) {
+                for (int i = 1 + threadIdx.x; i <= Nh; i += FT) part += EF(i) * DX(i) * JJ(i);
+                res = block_sum(part) * A.del_t;
+            } else {
+                for (int i = 2 + threadIdx.x; i <= Nx; i += FT) part += JJ(i) * EF(i);
+                res = block_sum(part);
+                res = res + 0.5 * JJ(1) * EF(1) + JJ(Nh) * EF(Nh) * 0.5;
+                res = res * A.del_t;
+            }
+        } else if (wch == 3) {   // getEnergyFromBoundary: NGP :432-442 ; CIC :428-456
+            if (A.scheme == 0) {
+                res = A.del_t * JJ(1);
+                res = res + eps_0 * ((PHIF(1) - PHIF(2)) - (PHI(1) - PHI(2))) / DX(1);
+                res = res * (PHIF(1) + PHI(1) - PHIF(Nx) - PHI(Nx)) * 0.5;
+            } else {
+                double lA = 0.0, rA = 0.0;
+                switch (BC(1)) { case 1: lA = A.bound1; break; case 4: lA = 0.5 * (A.RF_voltage + A.bound1); break; }
+                switch (BC(Nh)) { case 1: rA = A.bound2; break; case 4: rA = 0.5 * (A.RF_voltage + A.bound2); break; }
+                res = A.del_t * JJ(2) + eps_0 * ((PHIF(1) - PHIF(2)) - (PHI(1) - PHI(2))) / (GRID(2) - GRID(1));
+                res = res * (lA - rA);
+            }
+        } else if (wch == 4) {   // getError_tridiag_Poisson: NGP :240-265 ; CIC :232-244
+            for (int i = 1 + threadIdx.x; i <= Nx; i += FT) {
+                double Ax = PHIF(i) * A.b[i - 1];
+                if (i > 1) Ax += PHIF(i - 1) * A.a[i - 2];
+                if (i < Nx) Ax += PHIF(i + 1) * A.c[i - 1];
+                if (A.scheme == 0) {
+                    const int b = BC(i);
+                    if (b == 0 || b == 2) {
+                        if (RHO(i) + A.rho_const != 0) { const double v = Ax * eps_0 / (-RHO(i) - A.rho_const) - 1.0; part += v * v; }
+                        else { const double v = Ax * eps_0; part += v * v; }
+                    } else {
+                        if (PHIF(i) != 0) { const double v = Ax / PHIF(i) - 1.0; part += v * v; }
+                        else part += Ax * Ax;
+                    }
+                } else {
+                    double d = (-RHO(i) - A.rho_const) / eps_0;
+                    if (i == 1) d += A.src1;
+                    if (i == Nx) d += A.src2;
+                    const double v = 1.0 - Ax / d;
+                    part += v * v;
+                }
+            }
+            res = sqrt(block_sum(part) / Nx);
+        } else if (wch == 5) {   // getChargeContinuityError: NGP :358-390 ; CIC :315-331
+            double cnt = 0.0;
+            for (int i = 1 + threadIdx.x; i <= Nx; i += FT) {
+                const double dR = RHO(i) - A.rho_i[i - 1];
+                if (dR != 0) {
+                    if (A.scheme == 0) {
+                        switch (BC(i)) {
+                        case 0: { const double v = 1.0 + A.del_t * (JJ(i) - JJ(i - 1)) / dR; part += v * v; cnt += 1.0; break; }
+                        case 2: {
+                            const double v = (i == 1) ? 1.0 + 2.0 * A.del_t * JJ(1) / dR : 1.0 - 2.0 * A.del_t * JJ(Nh) / dR;
+                            part += v * v; cnt += 1.0; break; }
+                        case 3: if (i == 1) { const double v = 1.0 + A.del_t * (JJ(1) - JJ(Nh)) / dR; part += v * v; } break;
+                        }
+                    } else {
+                        const double v = 1.0 + A.del_t * (JJ(i + 1) - JJ(i)) / dR; part += v * v; cnt += 1.0;
+                    }
+                }
+            }
+            const double tot = block_sum(part);
+            const double k = block_sum(cnt);
+            res = sqrt(tot / k);
+        }
+        if (threadIdx.x == 0) A.scal[1] = res;
+    }
+}
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+static FieldArgs make_args(Ctx &c) {
+    FieldArgs A{};
+    A.scheme = c.scheme; A.Nx = c.Nx; A.Nh = c.Nh; A.smooth = c.smooth; A.nsp = (int)c.sp.size();
+    A.tridiag_mode = c.tridiag_mode; A.pcr_levels = c.pcr_levels;
+    A.acc_stride = std::max(c.Nx, c.Nh) + 2;
+    A.tab_cells = ((c.scheme == IPIC_SCHEME_NGP) ? c.Nh : c.Nx) + 2;
+    A.grid = c.d_grid; A.dx = c.d_dx; A.bc = c.d_bc;
+    A.phi = c.d_phi; A.phi_f = c.d_phi_f; A.rho = c.d_rho; A.J = c.d_J; A.E = c.d_E;
+    A.a = c.d_a; A.b = c.d_b; A.c = c.d_c; A.cp = c.d_cp; A.m = c.d_m; A.pcr = c.d_pcr;
+    A.work = c.d_work; A.scal = c.d_scal; A.rho_i = c.d_rho_i; A.acc = c.d_acc; A.tab = c.d_tab;
+    for (int s = 0; s < A.nsp && s < NSP_MAX; ++s) { A.qw[s] = c.sp[s].q_times_wp; A.qm[s] = c.sp[s].q_over_m; }
+    A.rho_const = c.rho_const; A.RF_voltage = c.RF_voltage;
+    A.bound1 = c.boundPhi[0]; A.bound2 = c.boundPhi[1]; A.src1 = c.sourceTermVals[0]; A.src2 = c.sourceTermVals[1];
+    A.phi_k = c.d_phi_k; A.res_k = c.d_res_k; A.norms = c.d_norms;
+    A.and_m = c.m_Anderson; A.beta = c.Beta_k;
+    return A;
+}
+
+static int run_field(Ctx &c, const FieldArgs &A, unsigned ops) {
+    const size_t smem = (size_t)2 * (std::max(c.Nx, c.Nh) + 2) * sizeof(double) + 4096 * sizeof(double);
+    static size_t configured = 0;
+    if (smem > configured) {
+        IPIC_CUDA(cudaFuncSetAttribute(k_field, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    k_field<<<1, FT, smem, c.stream>>>(A, ops);
+    IPIC_CUDA(cudaGetLastError());
+    return IPIC_OK;
+}
+
+// construct_diagMatrix (NGP :88-128 ; CIC :92-126) + constant-matrix factor tables
+int field_setup(Ctx &c) {
+    const int Nx = c.Nx;
+    std::vector<double> a(Nx + 2, 0.0), b(Nx + 2, 0.0), cc(Nx + 2, 0.0);   // 1-based
+    auto DXh = [&](int i) -> double { return (i >= 1 && i <= c.ndx) ? c.h_dx[i - 1] : 1.0; };
+    auto BCh = [&](int i) -> int { return c.h_bc[i - 1]; };
+    if (c.scheme == IPIC_SCHEME_NGP) {
+        for (int i = 1; i <= Nx; ++i) {
+            switch (BCh(i)) {
+            case 0:
+                if (i < Nx) cc[i] = 1.0 / DXh(i);
+                if (i > 1) a[i - 1] = 1.0 / DXh(i - 1);
+                b[i] = -(1.0 / DXh(i - 1) + 1.0 / DXh(i));
+                break;
+            case 1: case 4: b[i] = 1.0; break;
+            case 2:
+                if (i == 1) { cc[i] = 2.0 / DXh(i); b[i] = -(2.0 / DXh(i)); }
+                else if (i == Nx) { a[i - 1] = 2.0 / DXh(i - 1); b[i] = -(2.0 / DXh(i - 1)); }
+                else { set_error("Neumann boundary not on left or right most index!"); return IPIC_ERR_STOP; }
+                break;
+            case 3: b[i] = 1.0; break;
+            default: break;
+            }
+        }
+    } else {
+        for (int i = 1; i <= Nx; ++i) {
+            switch (BCh(i + 1) - BCh(i)) {
+            case 0:
+                b[i] = -2.0 * (1.0 / (DXh(i - 1) + DXh(i)) + 1.0 / (DXh(i + 1) + DXh(i)));
+                a[i - 1] = 2.0 / (DXh(i - 1) + DXh(i));
+                cc[i] = 2.0 / (DXh(i) + DXh(i + 1));
+                break;
+            case -1: case -4: case -3:
+                b[i] = -2.0 * (1.0 / (DXh(i + 1) + DXh(i)) + 1.0 / DXh(i));
+                cc[i] = 2.0 / (DXh(i + 1) + DXh(i));
+                c.sourceTermVals[0] = -c.boundPhi[0] * 2.0 / DXh(1);
+                break;
+            case 1: case 4: case 3:
+                b[i] = -2.0 * (1.0 / (DXh(i - 1) + DXh(i)) + 1.0 / DXh(i));
+                a[i - 1] = 2.0 / (DXh(i - 1) + DXh(i));
+                c.sourceTermVals[1] = -c.boundPhi[1] * 2.0 / DXh(Nx);
+                break;
+            case -2:
+                b[i] = -2.0 / (DXh(i + 1) + DXh(i));
+                cc[i] = 2.0 / (DXh(i + 1) + DXh(i));
+                break;
+            case 2:
+                b[i] = -2.0 / (DXh(i - 1) + DXh(i));
+                a[i - 1] = 2.0 / (DXh(i - 1) + DXh(i));
+                break;
+            }
+        }
+    }
+    // Thomas: c'_i and pivots m_i exactly as the reference recomputes them on every call
+    std::vector<double> cp(Nx + 2, 0.0), mm(Nx + 2, 0.0);
+    cp[1] = cc[1] / b[1]; mm[1] = b[1];
+    for (int i = 2; i <= Nx - 1; ++i) { mm[i] = b[i] - cp[i - 1] * a[i - 1]; cp[i] = cc[i] / mm[i]; }
+    mm[Nx] = b[Nx] - cp[Nx - 1] * a[Nx - 1];
+    // PCR level coefficients on the constant matrix
+    int levels = 0; while ((1 << levels) < Nx) ++levels;
+    std::vector<double> pcr((size_t)(levels * 2 + 1) * Nx, 0.0);
+    {
+        std::vector<double> la(Nx), lb(Nx), lc(Nx), na(Nx), nb(Nx), nc(Nx);   // 0-based rows
+        for (int i = 0; i < Nx; ++i) { la[i] = (i > 0) ? a[i] : 0.0; lb[i] = b[i + 1]; lc[i] = (i < Nx - 1) ? cc[i + 1] : 0.0; }
+        int stride = 1;
+        for (int lev = 0; lev < levels; ++lev) {
+            double *al = &pcr[(size_t)lev * 2 * Nx], *ga = al + Nx;
+            for (int i = 0; i < Nx; ++i) {
+                double alpha = 0.0, gamma = 0.0, aa = 0.0, cq = 0.0, bb = lb[i];
+                if (i - stride >= 0) { alpha = -la[i] / lb[i - stride]; aa = alpha * la[i - stride]; bb += alpha * lc[i - stride]; }
+                if (i + stride < Nx) { gamma = -lc[i] / lb[i + stride]; cq = gamma * lc[i + stride]; bb += gamma * la[i + stride]; }
+                al[i] = alpha; ga[i] = gamma; na[i] = aa; nb[i] = bb; nc[i] = cq;
+            }
+            la.swap(na); lb.swap(nb); lc.swap(nc);
+            stride <<= 1;
+        }
+        double *inv = &pcr[(size_t)levels * 2 * Nx];
+        for (int i = 0; i < Nx; ++i) inv[i] = 1.0 / lb[i];
+    }
+    c.pcr_levels = levels;
+    if (c.d_pcr) cudaFree(c.d_pcr);
+    IPIC_CUDA(cudaMalloc(&c.d_pcr, pcr.size() * sizeof(double)));
+    IPIC_CUDA(cudaMemcpy(c.d_pcr, pcr.data(), pcr.size() * sizeof(double), cudaMemcpyHostToDevice));
+    IPIC_CUDA(cudaMemcpy(c.d_a, &a[1], (Nx - 1) * sizeof(double), cudaMemcpyHostToDevice));
+    IPIC_CUDA(cudaMemcpy(c.d_b, &b[1], Nx * sizeof(double), cudaMemcpyHostToDevice));
+    IPIC_CUDA(cudaMemcpy(c.d_c, &cc[1], (Nx - 1) * sizeof(double), cudaMemcpyHostToDevice));
+    IPIC_CUDA(cudaMemcpy(c.d_cp, &cp[1], Nx * sizeof(double), cudaMemcpyHostToDevice));
+    IPIC_CUDA(cudaMemcpy(c.d_m, &mm[1], Nx * sizeof(double), cudaMemcpyHostToDevice));
+    return IPIC_OK;
+}
+
+int field_finalize_rho(Ctx &c) { FieldArgs A = make_args(c); return run_field(c, A, OP_FINALIZE_RHO); }
+
+int field_poisson(Ctx &c, double timeCurrent) {
+    // CIC: RF wall value refreshed first (:181-189)
+    if (c.scheme == IPIC_SCHEME_CIC && c.RF_bool) {
+        const double v = c.RF_half_amplitude * std::sin(c.RF_rad_frequency * timeCurrent);
+        if (c.RF_indx == 1) { c.boundPhi[0] = v; c.sourceTermVals[0] = -v * 2.0 / c.h_dx[0]; }
+        else { c.boundPhi[1] = v; c.sourceTermVals[1] = -v * 2.0 / c.h_dx[c.Nx - 1]; }
+    }
+    FieldArgs A = make_args(c);
+    A.poisson_rf_value = c.RF_half_amplitude * std::sin(c.RF_rad_frequency * timeCurrent);
+    return run_field(c, A, OP_POISSON);
+}
+
+int field_const_source(Ctx &c) { FieldArgs A = make_args(c); return run_field(c, A, OP_CONST_SOURCE); }
+int field_half_time_E(Ctx &c) { FieldArgs A = make_args(c); return run_field(c, A, OP_HALF_E); }
+int field_finalize_J(Ctx &c, double del_t) { FieldArgs A = make_args(c); A.del_t = del_t; return run_field(c, A, OP_FINALIZE_J); }
+int field_ampere(Ctx &c, double del_t) { FieldArgs A = make_args(c); A.del_t = del_t; return run_field(c, A, OP_AMPERE); }
+
+int field_diag(Ctx &c, int which, double del_t, double *out) {
+    FieldArgs A = make_args(c);
+    A.del_t = del_t; A.diag_which = which;
+    int rc = run_field(c, A, OP_DIAG);
+    if (rc) return rc;
+    IPIC_CUDA(cudaMemcpyAsync(c.h_scal, c.d_scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    IPIC_CUDA(cudaStreamSynchronize(c.stream));
+    *out = c.h_scal[1];
+    return IPIC_OK;
+}
+
+int field_anderson_begin(Ctx &c) {
+    FieldArgs A = make_args(c);
+    return run_field(c, A, OP_CONST_SOURCE | OP_AND_STORE0 | OP_HALF_E);
+}
+
+// phase 0: after the first sweep   : finalize J, Ampere, column 2 + R1 + norm
+// phase 1: after sweep i           : finalize J, Ampere, R_index + norm
+// phase 2: mixing for iteration i  : next iterate into phi_f, then E + tables for the next sweep
+// phase 3: E + tables only (converged: the mover uses the freshly solved phi_f)
+int field_anderson_step(Ctx &c, int i, int phase, double del_t, int *status, double *norm) {
+    FieldArgs A = make_args(c);
+    A.del_t = del_t; A.and_i = i;
+    unsigned ops = 0;
+    if (phase == 0) ops = OP_FINALIZE_J | OP_AMPERE | OP_AND_FIRST | OP_HALF_E;
+    else if (phase == 1) ops = OP_FINALIZE_J | OP_AMPERE | OP_AND_RESID;
+    else if (phase == 2) ops = OP_AND_MIX | OP_HALF_E;
+    else ops = OP_HALF_E;
+    int rc = run_field(c, A, ops);
+    if (rc) return rc;
+    if (phase <= 1) {
+        IPIC_CUDA(cudaMemcpyAsync(c.h_scal, c.d_scal, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        IPIC_CUDA(cudaStreamSynchronize(c.stream));
+        *norm = c.h_scal[0];
+    }
+    if (status) *status = 0;
+    return IPIC_OK;
+}
+
+// funcNitsol tail: phi_f already holds G(x); f = x - phi_f
+int field_residual(Ctx &c, const double *d_x, double *d_f) {
+    FieldArgs A = make_args(c);
+    A.xin = d_x; A.fout = d_f;
+    return run_field(c, A, OP_RESID_F);
+}
+
+}  // namespace ipic

@@ -1,0 +1,198 @@
+// Shared declarations of the B200 implicit-PIC library: context, device tables, PTX wrappers.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include <map>
+#include "../../include/ipic1d_b200.h"
+
+namespace ipic {
+
+// constants.f90:7-15
+constexpr double eps_0 = 8.8541878128e-12;
+constexpr double e_c = 1.602176634e-19;
+
+// ---- fixed-point deposition ---------------------------------------------------------------------
+// Every deposited weight x (|x| <= 2) is rounded to a multiple of 2^-FX_BITS and accumulated as a
+// 64-bit integer, so sums are order-independent: bit-identical run to run, for any particle order,
+// block count or GPU count.  x + FX_MAGIC puts round(x * 2^FX_BITS) into the low mantissa bits.
+constexpr int FX_BITS = 44;
+constexpr double FX_MAGIC = 384.0;                                  // 1.5 * 2^(52 - FX_BITS)
+constexpr double FX_INV = 1.0 / 17592186044416.0;                   // 2^-44
+
+__device__ __forceinline__ long long fx_from_double(double x) {
+    return __double_as_longlong(x + FX_MAGIC) - __double_as_longlong(FX_MAGIC);
+}
+
+// Per-cell, per-species lookup tables rebuilt from (phi, phi_f) before every sweep.
+struct CellTabNGP {   // OpenMP/NGP/src/mod_particleMover.f90:21-63 operands
+    double a;          // q/m * E_c
+    double inv_dx;     // 1 / dx_dl(c)
+    double two_a_dx;   // 2 a dx_dl(c)
+    double inv_a;      // 1 / a
+};
+struct CellTabCIC {   // OpenMP/CIC/src/mod_particleMoverPicard.f90:17-65,92-94 operands
+    double A0;         // q/m * E_left
+    double A1;         // q/m * (E_right - E_left)
+    double inv_dx;     // 1 / dx_dl(c)
+    double dx;         // dx_dl(c)
+    double cap;        // particleTimeStep(c, species)
+    double pad[3];
+};
+
+// streaming geometry of the push kernels
+constexpr int PUSH_THREADS = 1024;
+constexpr int PUSH_WARPS = PUSH_THREADS / 32;
+constexpr int CHUNK = 64;          // particles per staged chunk (per warp)
+constexpr int STAGES = 3;          // chunks in flight per warp
+constexpr int MAX_GRID_SMEM = 8192;   // largest N_h the shared-memory limb grid supports (12 B per cell)
+
+struct PushArgs {
+    const double *l, *vx;      // inputs (SoA)
+    double *l_out, *vx_out;    // MOVE: in-place outputs
+    long long n;               // particles in the arrays (alive or marked dead)
+    const void *tab;           // CellTabNGP* / CellTabCIC* for this species
+    const int *bc;             // boundaryConditions
+    unsigned long long *acc;   // !MOVE: int64 fixed-point grid [Nh] for this species
+    unsigned long long *counters;  // [0] deposit substeps, [1] func evals, [2] absorbed left, [3] absorbed right, [4] first reflections, [5] move substeps
+    int Nh;                    // grid entries to deposit on
+    int NB;                    // wall index on the right: N_x (NGP) or N_h (CIC)
+    double del_t, f_tol;
+    int refill_min;            // refill a warp when at least this many lanes are idle (32 = lock-step)
+};
+
+// ---- device context -------------------------------------------------------------------------------
+struct SpeciesDev {
+    double mass = 0, q = 0, w_p = 1, q_over_m = 0, q_times_wp = 0;
+    long long n = 0, cap = 0;
+    double *l = nullptr, *vx = nullptr, *vy = nullptr, *vz = nullptr;
+    double *l2 = nullptr, *vx2 = nullptr, *vy2 = nullptr, *vz2 = nullptr;
+    long long cap2 = 0;
+    std::vector<long long> slab_off;       // numThread+1 offsets of the reference's thread slabs
+    ipic_move_stats stats{};
+    long long depositSubsteps = 0;
+};
+
+struct Timing { double ms = 0; long long launches = 0; };
+
+struct Ctx {
+    int scheme = 0, Nx = 0, Nh = 0, nbc = 0, ndx = 0, smooth = 0, device = 0;
+    cudaStream_t stream = nullptr;
+    // device tables
+    double *d_grid = nullptr, *d_dx = nullptr;
+    int *d_bc = nullptr;
+    std::vector<double> h_grid, h_dx;
+    std::vector<int> h_bc;
+    // field vectors (device)
+    double *d_phi = nullptr, *d_phi_f = nullptr, *d_rho = nullptr, *d_J = nullptr, *d_E = nullptr;
+    double *d_a = nullptr, *d_b = nullptr, *d_c = nullptr;       // tridiagonal
+    double *d_cp = nullptr, *d_m = nullptr;                       // Thomas: c' and pivots m_i (constant matrix)
+    double *d_pcr = nullptr; int pcr_levels = 0;                  // PCR level coefficients [levels][2][Nx] + inv diag [Nx]
+    double *d_work = nullptr;                                     // scratch (4 * max(Nx,Nh))
+    double *d_rho_i = nullptr;
+    unsigned long long *d_acc = nullptr;                          // [nsp_max][max(Nx,Nh)] int64 accumulators
+    void *d_tab = nullptr;                                        // [nsp_max][cells] CellTab*
+    unsigned long long *d_counters = nullptr;                     // [nsp_max][8]
+    double *d_scal = nullptr;                                     // small device scalar outputs (64 doubles)
+    double *h_scal = nullptr;                                     // pinned mirror
+    // Anderson
+    double *d_phi_k = nullptr, *d_res_k = nullptr;                // [m+1][Nx]
+    double *d_norms = nullptr;
+    int tridiag_mode = IPIC_TRIDIAG_PCR;
+    // solver scalars (host mirror; NGP mod_potentialSolver.f90:17-22, CIC :17-23)
+    double rho_const = 0, RF_rad_frequency = 0, RF_half_amplitude = 0, RF_voltage = 0;
+    double boundPhi[2] = {0, 0}, sourceTermVals[2] = {0, 0};
+    int RF_indx = 0; bool RF_bool = false;
+    bool solver_ready = false;
+    // nonlinear solver (mod_nonLinSolvers.f90:29-35)
+    int iterNumPicard = 0, iterNumAdaptiveSteps = 0, amountTimeSplits = 0;
+    int maxIter = 100, solverType = 0, m_Anderson = 10;
+    double Beta_k = 0.5, eps_r = 0, eps_a = 1e-8;
+    long long sweeps = 0, substeps = 0;
+    std::vector<double> normHist;
+    double lastNorm = 0;
+    std::vector<SpeciesDev> sp;
+    // options
+    int refill_min = 8;
+    int push_blocks = 0;          // 0 = one CTA per SM
+    int lazy_compaction = 0;
+    // multi-GPU
+    void *nccl_comm = nullptr; int nranks = 1, rank = 0;
+    // timing
+    std::map<std::string, Timing> timing;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timing_on = true;
+    int num_sms = 148;
+    // compaction scratch
+    unsigned *d_tileCount = nullptr; long long *d_tileOffset = nullptr; double *d_loss = nullptr;
+    long long cap_tiles = 0; long long *d_total = nullptr; long long *d_slab = nullptr; int cap_slab = 0;
+};
+
+static constexpr int NSP_MAX = 8;
+
+void set_error(const std::string &s);
+#define IPIC_CUDA(call)                                                                             \
+    do {                                                                                            \
+        cudaError_t _e = (call);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            ::ipic::set_error(std::string(#call) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + std::to_string(__LINE__)); \
+            return IPIC_ERR_CUDA;                                                                   \
+        }                                                                                           \
+    } while (0)
+
+// ---- launchers implemented in particles.cu ---------------------------------------------------------
+int launch_deposit(Ctx &c, int sp, double del_t);
+int launch_move(Ctx &c, int sp, double del_t);
+int launch_deposit_rho(Ctx &c, int sp);
+int compact_species(Ctx &c, int sp);
+int particle_moments(Ctx &c, int sp, double out4[4]);      // sum v^2, sum vx, vy, vz
+int upload_species(Ctx &c, int sp, const double *ps, const int32_t *N_p, int T, int finalIdx);
+int download_species(Ctx &c, int sp, double *ps, int32_t *N_p, int T, int finalIdx);
+int generate_species(Ctx &c, int sp, long long n, double T_eV, double v_drift, unsigned long long seed);
+int sort_species(Ctx &c, int sp);
+int ensure_capacity(Ctx &c, int sp, long long n);
+
+// ---- launchers implemented in field.cu --------------------------------------------------------------
+int field_setup(Ctx &c);                                   // construct_diagMatrix + Thomas/PCR factor tables
+int field_finalize_rho(Ctx &c);
+int field_poisson(Ctx &c, double timeCurrent);
+int field_const_source(Ctx &c);
+int field_half_time_E(Ctx &c);                             // EField + per-species cell tables
+int field_finalize_J(Ctx &c, double del_t);
+int field_ampere(Ctx &c, double del_t);
+int field_diag(Ctx &c, int which, double del_t, double *out);
+int field_anderson_begin(Ctx &c);
+int field_anderson_step(Ctx &c, int i, int phase, double eps_tol, int *status, double *norm);
+int field_residual(Ctx &c, const double *d_x, double *d_f);
+
+// ---- PTX wrappers: mbarrier + bulk async copy (TMA 1-D) ----------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+                 "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+
+}  // namespace ipic

@@ -1,0 +1,925 @@
+// Particle kernels of the B200 implicit-PIC library: the sub-stepping push (depositJ / moveParticles),
+// rho deposition, moments, stable compaction, AoS<->SoA transposition, synthetic loader and cell sort.
+//
+// Reference semantics restated here (never copied): OpenMP/NGP/src/mod_particleMover.f90:21-270 and
+// OpenMP/CIC/src/mod_particleMoverPicard.f90:17-317.
+#include "ipic_common.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <algorithm>
+
+namespace ipic {
+
+#define FULL 0xffffffffu
+
+// =====================================================================================================
+// Shared-memory fixed-point grid: each cell is three 32-bit limbs (16/16/32-bit digits of the int64 sum)
+// so that deposits are native 32-bit shared atomics (ATOMS.ADD) fed by native warp reductions (REDUX).
+// Limb counters carry into the next limb when they pass 2^31, so capacity is unbounded.
+// =====================================================================================================
+struct LimbGrid {
+    unsigned *g0, *g1;
+    int *g2;
+    unsigned long long *gacc;   // global int64 grid, receives top-limb spills and the final flush
+};
+
+__device__ __forceinline__ void limb2_add(const LimbGrid &g, int c, int r2) {
+    int o = atomicAdd(&g.g2[c], r2);
+    int nv = o + r2;
+    if (nv >= (1 << 30) && o < (1 << 30)) {
+        atomicSub(&g.g2[c], 1 << 30);
+        atomicAdd(&g.gacc[c], (unsigned long long)(1ull << 62));
+    } else if (nv <= -(1 << 30) && o > -(1 << 30)) {
+        atomicAdd(&g.g2[c], 1 << 30);
+        atomicAdd(&g.gacc[c], (unsigned long long)(0ull - (1ull << 62)));
+    }
+}
+__device__ __forceinline__ void limb1_add(const LimbGrid &g, int c, unsigned r1) {
+    unsigned o = atomicAdd(&g.g1[c], r1);
+    if (o < 0x80000000u && o + r1 >= 0x80000000u) {
+        atomicSub(&g.g1[c], 0x80000000u);
+        limb2_add(g, c, 1 << 15);
+    }
+}
+__device__ __forceinline__ void limb0_add(const LimbGrid &g, int c, unsigned r0) {
+    unsigned o = atomicAdd(&g.g0[c], r0);
+    if (o < 0x80000000u && o + r0 >= 0x80000000u) {
+        atomicSub(&g.g0[c], 0x80000000u);
+        limb1_add(g, c, 1u << 15);
+    }
+}
+__device__ __forceinline__ void limb_add(const LimbGrid &g, int c, unsigned r0, unsigned r1, int r2) {
+    limb0_add(g, c, r0);
+    limb1_add(g, c, r1);
+    limb2_add(g, c, r2);
+}
+
+// Warp-aggregated deposit of one fixed-point value per lane.  Must be called by all 32 lanes.
+// Lanes that share the leader's cell are summed with REDUX and written once; after MAXPASS groups the
+// remaining lanes fall back to their own atomics.
+template <int MAXPASS>
+__device__ __forceinline__ void warp_deposit(const LimbGrid &g, bool has, int cell, long long q, int lane) {
+    unsigned pend = __ballot_sync(FULL, has);
+    if (!pend) return;
+    const unsigned u0 = (unsigned)q & 0xFFFFu, u1 = (unsigned)(q >> 16) & 0xFFFFu;
+    const int s2 = (int)(q >> 32);
+#pragma unroll
+    for (int pass = 0; pass < MAXPASS; ++pass) {
+        const int leader = __ffs(pend) - 1;
+        const int key = __shfl_sync(FULL, cell, leader);
+        const bool mine = has && (cell == key);
+        const unsigned grp = __ballot_sync(FULL, mine);
+        if (mine) {
+            const unsigned r0 = __reduce_add_sync(grp, u0);
+            const unsigned r1 = __reduce_add_sync(grp, u1);
+            const int r2 = __reduce_add_sync(grp, s2);
+            if (lane == leader) limb_add(g, key, r0, r1, r2);
+        }
+        has = has && !mine;
+        pend &= ~grp;
+        if (!pend) return;
+    }
+    if (has) limb_add(g, cell, u0, u1, s2);
+}
+
+// Two-point variant: qa goes to `cell`, qb to `cell + 1` (CIC current, NGP charge).
+template <int MAXPASS>
+__device__ __forceinline__ void warp_deposit2(const LimbGrid &g, bool has, int cell, long long qa, long long qb, int lane) {
+    unsigned pend = __ballot_sync(FULL, has);
+    if (!pend) return;
+    const unsigned a0 = (unsigned)qa & 0xFFFFu, a1 = (unsigned)(qa >> 16) & 0xFFFFu;
+    const int a2 = (int)(qa >> 32);
+    const unsigned b0 = (unsigned)qb & 0xFFFFu, b1 = (unsigned)(qb >> 16) & 0xFFFFu;
+    const int b2 = (int)(qb >> 32);
+#pragma unroll
+    for (int pass = 0; pass < MAXPASS; ++pass) {
+        const int leader = __ffs(pend) - 1;
+        const int key = __shfl_sync(FULL, cell, leader);
+        const bool mine = has && (cell == key);
+        const unsigned grp = __ballot_sync(FULL, mine);
+        if (mine) {
+            const unsigned ra0 = __reduce_add_sync(grp, a0), ra1 = __reduce_add_sync(grp, a1);
+            const int ra2 = __reduce_add_sync(grp, a2);
+            const unsigned rb0 = __reduce_add_sync(grp, b0), rb1 = __reduce_add_sync(grp, b1);
+            const int rb2 = __reduce_add_sync(grp, b2);
+            if (lane == leader) {
+                limb_add(g, key, ra0, ra1, ra2);
+                limb_add(g, key + 1, rb0, rb1, rb2);
+            }
+        }
+        has = has && !mine;
+        pend &= ~grp;
+        if (!pend) return;
+    }
+    if (has) {
+        limb_add(g, cell, a0, a1, a2);
+        limb_add(g, cell + 1, b0, b1, b2);
+    }
+}
+
+__device__ __forceinline__ void limb_grid_zero(const LimbGrid &g, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { g.g0[i] = 0u; g.g1[i] = 0u; g.g2[i] = 0; }
+}
+// flush entries [1..n] (1-based cells) to the global int64 grid
+__device__ __forceinline__ void limb_grid_flush(const LimbGrid &g, int n) {
+    for (int i = threadIdx.x + 1; i <= n; i += blockDim.x) {
+        unsigned long long v = (unsigned long long)g.g0[i] + ((unsigned long long)g.g1[i] << 16) +
+                               ((unsigned long long)(long long)g.g2[i] << 32);
+        if (v) atomicAdd(&g.gacc[i], v);
+    }
+}
+
+// =====================================================================================================
+// The push kernel.  One CTA per SM; every warp streams its own chunks of (l, v_x) through a private
+// 3-stage shared-memory ring filled by 1-D bulk async copies (TMA) signalled on warp-private mbarriers,
+// so no inter-warp synchronisation exists in the streaming loop.  Lanes execute exactly one sub-step
+// per loop trip; finished lanes are refilled from the ring once `refill_min` lanes are idle, which
+// bounds warp divergence from the data-dependent sub-step count.
+//   SCHEME 0: NGP constant-field sub-step   (mod_particleMover.f90:21-63)
+//   SCHEME 1: CIC Picard sub-step           (mod_particleMoverPicard.f90:17-65)
+//   MOVE false: depositJ sweep (no particle writes, J accumulated)   true: moveParticles (write back)
+// =====================================================================================================
+template <int SCHEME, bool MOVE>
+__global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // layout: [ring: WARPS x STAGES x 2 x CHUNK doubles][mbar: WARPS x STAGES u64][limb grid]
+    double *ring = reinterpret_cast<double *>(smem_raw);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(ring + (size_t)PUSH_WARPS * STAGES * 2 * CHUNK);
+    LimbGrid G;
+    if (!MOVE) {
+        const int ng = A.Nh + 2;
+        G.g0 = reinterpret_cast<unsigned *>(bars + PUSH_WARPS * STAGES);
+        G.g1 = G.g0 + ng;
+        G.g2 = reinterpret_cast<int *>(G.g1 + ng);
+        G.gacc = A.acc;
+        limb_grid_zero(G, ng);
+    }
+    double *my_ring = ring + (size_t)warp * STAGES * 2 * CHUNK;
+    const unsigned my_bar0 = smem_u32(bars + warp * STAGES);
+    if (lane == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(my_bar0 + 8u * s, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    const long long GW = (long long)gridDim.x * PUSH_WARPS;
+    const long long gw = (long long)blockIdx.x * PUSH_WARPS + warp;
+    const long long nchunks = (A.n + CHUNK - 1) / CHUNK;
+    constexpr unsigned CH_BYTES = CHUNK * sizeof(double);
+
+    // prologue: put STAGES chunks in flight
+    if (lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            const long long ck = gw + (long long)s * GW;
+            if (ck < nchunks) {
+                const unsigned bar = my_bar0 + 8u * s;
+                mbar_expect_tx(bar, 2 * CH_BYTES);
+                bulk_g2s(smem_u32(my_ring + (size_t)s * 2 * CHUNK), A.l + ck * CHUNK, CH_BYTES, bar);
+                bulk_g2s(smem_u32(my_ring + (size_t)s * 2 * CHUNK + CHUNK), A.vx + ck * CHUNK, CH_BYTES, bar);
+            }
+        }
+    }
+    __syncwarp();
+
+    long long kc = 0;          // ordinal of the chunk currently being consumed
+    int pos = 0;               // consumed entries of that chunk
+    bool have_more = gw < nchunks;
+
+    bool active = false, refl = false;
+    double l = 0.0, v = 0.0, tp = 0.0;
+    int cell = 0;
+    long long idx = 0;
+    unsigned nsub = 0, nfev = 0, nabsL = 0, nabsR = 0, nrefl = 0;
+    const double del_t = A.del_t, f_tol = A.f_tol;
+
+    while (true) {
+        // ---------------- refill idle lanes from the ring ----------------
+        const unsigned idle = __ballot_sync(FULL, !active);
+        if (have_more && __popc(idle) >= A.refill_min) {
+            const int stage = (int)(kc % STAGES);
+            mbar_wait(my_bar0 + 8u * stage, (unsigned)((kc / STAGES) & 1));
+            const int take = min(__popc(idle), CHUNK - pos);
+            const int rank = __popc(idle & ((1u << lane) - 1u));
+            if (!active && rank < take) {
+                const int slot = pos + rank;
+                const double *st = my_ring + (size_t)stage * 2 * CHUNK;
+                const double ll = st[slot], vv = st[CHUNK + slot];
+                const long long id = (gw + kc * GW) * CHUNK + slot;
+                if (id < A.n && ll >= 0.0) {   // l < 0 marks a particle absorbed earlier and not yet compacted
+                    l = ll; v = vv; tp = 0.0; idx = id; refl = false;
+                    // l_cell = INT(l_sub + SIGN(1.d-12, v_sub))
+                    cell = (int)(ll + copysign(1.e-12, vv));
+                    active = true;
+                }
+            }
+            pos += take;
+            if (pos == CHUNK) {   // chunk consumed: reuse its stage for the chunk STAGES ahead
+                __syncwarp();
+                if (lane == 0) {
+                    const long long ck = gw + (kc + STAGES) * GW;
+                    if (ck < nchunks) {
+                        fence_proxy_async();
+                        const unsigned bar = my_bar0 + 8u * stage;
+                        mbar_expect_tx(bar, 2 * CH_BYTES);
+                        bulk_g2s(smem_u32(my_ring + (size_t)stage * 2 * CHUNK), A.l + ck * CHUNK, CH_BYTES, bar);
+                        bulk_g2s(smem_u32(my_ring + (size_t)stage * 2 * CHUNK + CHUNK), A.vx + ck * CHUNK, CH_BYTES, bar);
+                    }
+                }
+                kc += 1; pos = 0;
+                have_more = (gw + kc * GW) < nchunks;
+            }
+        }
+        const unsigned act = __ballot_sync(FULL, active);
+        if (act == 0u) {
+            if (!have_more) break;
+            continue;
+        }
+
+        // ---------------- one sub-step for every active lane ----------------
+        bool dep = false;
+        int dcell = 0;
+        long long qa = 0, qb = 0;
+        if (active) {
+            nsub += 1;
+            double l_f, v_f, dtau = del_t - tp;
+            bool atB;
+            int lb = 0;
+            if (SCHEME == 0) {
+                const double2 *tp2 = reinterpret_cast<const double2 *>(reinterpret_cast<const CellTabNGP *>(A.tab) + cell);
+                const double2 t0 = __ldg(tp2), t1 = __ldg(tp2 + 1);
+                const double a = t0.x, inv_dx = t0.y, two_a_dx = t1.x, inv_a = t1.y;
+                v_f = fma(a, dtau, v);
+                l_f = l + 0.5 * (v + v_f) * dtau * inv_dx;
+                const bool inCell = ((int)l_f == cell);
+                const bool eqSign = ((v > 0.0) == (v_f > 0.0));
+                atB = (!inCell) || (!eqSign);
+                if (atB) {
+                    lb = (v > 0.0) ? cell + 1 : cell;
+                    double diff_PE = two_a_dx * ((double)lb - l);
+                    const double v2 = v * v;
+                    if (diff_PE > -v2) {
+                        l_f = (double)lb;
+                        v_f = copysign(sqrt(diff_PE + v2), v);
+                        dtau = (v_f - v) * inv_a;
+                    } else if (!inCell) {
+                        lb = 2 * cell + 1 - lb;
+                        l_f = (double)lb;
+                        diff_PE = two_a_dx * (l_f - l);
+                        v_f = -copysign(sqrt(diff_PE + v2), v);
+                        dtau = (v_f - v) * inv_a;
+                    } else {
+                        atB = false;
+                    }
+                }
+                if (!MOVE) { dep = true; dcell = cell; qa = fx_from_double(l_f - l); }
+            } else {
+                const double2 *tp2 = reinterpret_cast<const double2 *>(reinterpret_cast<const CellTabCIC *>(A.tab) + cell);
+                const double2 t0 = __ldg(tp2), t1 = __ldg(tp2 + 1);
+                const double cap = __ldg(reinterpret_cast<const double *>(tp2 + 2));
+                const double A0 = t0.x, A1 = t0.y, inv_dx = t1.x, dx = t1.y;
+                dtau = fmin(dtau, cap);
+                const double ls = l - (double)cell;
+                const double r = dtau * inv_dx;
+                double l_prev = ls, lf = ls, d_half = ls, accel = 0.0, v_half = v;
+                int it;
+                atB = false;
+                for (it = 1; it <= 50; ++it) {
+                    d_half = (ls + l_prev) * 0.5;
+                    accel = fma(A1, d_half, A0);
+                    v_half = fma(0.5 * accel, r, v);
+                    lf = fma(v_half, r, ls);
+                    atB = (lf <= 0.0) || (lf >= 1.0);
+                    if (atB) lf = (v_half < 0.0) ? 0.0 : 1.0;
+                    if (fabs(lf - l_prev) < 1.e-10) break;
+                    l_prev = lf;
+                }
+                int numIter = it;   // 51 after an exhausted loop, as the Fortran loop variable
+                if (!atB) {
+                    v_f = 2.0 * v_half - v;
+                } else {
+                    if (lf != ls) {
+                        v_f = copysign(sqrt(2.0 * accel * (lf - ls) + v * v), v_half);
+                        dtau = (lf - ls) * dx / v_half;
+                        numIter += 1;
+                    } else {
+                        dtau = -2.0 * v * dx / accel;
+                        v_f = -v;
+                    }
+                    lb = (int)lf + cell;
+                }
+                l_f = lf + (double)cell;
+                if (MOVE) nfev += (unsigned)numIter;
+                if (!MOVE) {
+                    const double Jp = l_f - l;
+                    dep = true; dcell = cell;
+                    qa = fx_from_double((1.0 - d_half) * Jp);
+                    qb = fx_from_double(Jp * d_half);
+                }
+            }
+            bool absorbed = false;
+            if (atB) {
+                const int b = __ldg(A.bc + lb);
+                if (b == 0) {
+                    cell += signbit(v_f) ? -1 : 1;
+                } else if (b == 1 || b == 4) {
+                    absorbed = true;
+                } else if (b == 2) {
+                    if (lb == A.NB) { if (v_f > 0.0) v_f = -v_f; }
+                    else { if (v_f < 0.0) v_f = -v_f; }
+                    if (MOVE && !refl) { refl = true; nrefl += 1; }
+                } else if (b == 3) {
+                    l_f = (double)abs(lb - A.NB - 1);
+                    cell = abs(cell - A.NB);
+                }
+            }
+            tp += dtau;
+            const double rem = del_t - tp;
+            if (absorbed) {
+                active = false;
+                if (MOVE) {
+                    // mark for the compaction pass; the wall side is recoverable from the marker
+                    const bool left = (lb == 1);
+                    if (left) nabsL += 1; else nabsR += 1;
+                    A.l_out[idx] = left ? -1.0 : -2.0;
+                    A.vx_out[idx] = v_f;
+                }
+            } else if (!(rem > f_tol)) {
+                active = false;
+                if (MOVE) { A.l_out[idx] = l_f; A.vx_out[idx] = v_f; }
+            } else {
+                l = l_f; v = v_f;
+            }
+        }
+        if (!MOVE) {
+            if (SCHEME == 0) warp_deposit<2>(G, dep, dcell, qa, lane);
+            else warp_deposit2<2>(G, dep, dcell, qa, qb, lane);
+        }
+    }
+
+    // ---------------- epilogue: counters, flush ----------------
+    {
+        const unsigned s0 = __reduce_add_sync(FULL, nsub);
+        if (lane == 0 && s0) atomicAdd(&A.counters[MOVE ? 5 : 0], (unsigned long long)s0);
+        if (MOVE) {
+            const unsigned s1 = __reduce_add_sync(FULL, nfev), s2 = __reduce_add_sync(FULL, nabsL), s3 = __reduce_add_sync(FULL, nabsR),
+                           s4 = __reduce_add_sync(FULL, nrefl);
+            if (lane == 0) {
+                if (s1) atomicAdd(&A.counters[1], (unsigned long long)s1);
+                if (s2) atomicAdd(&A.counters[2], (unsigned long long)s2);
+                if (s3) atomicAdd(&A.counters[3], (unsigned long long)s3);
+                if (s4) atomicAdd(&A.counters[4], (unsigned long long)s4);
+            }
+        }
+    }
+    if (!MOVE) {
+        __syncthreads();
+        limb_grid_flush(G, A.Nh);
+    }
+}
+
+static size_t push_smem_bytes(bool move, int Nh) {
+    size_t s = (size_t)PUSH_WARPS * STAGES * 2 * CHUNK * sizeof(double) + (size_t)PUSH_WARPS * STAGES * 8;
+    if (!move) s += (size_t)3 * (Nh + 2) * 4;
+    return s;
+}
+
+template <int SCHEME, bool MOVE>
+static int launch_push_t(Ctx &c, const PushArgs &A) {
+    const size_t smem = push_smem_bytes(MOVE, A.Nh);
+    static size_t configured = 0;
+    if (smem > configured) {
+        IPIC_CUDA(cudaFuncSetAttribute(k_push<SCHEME, MOVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int blocks = c.push_blocks > 0 ? c.push_blocks : c.num_sms;
+    k_push<SCHEME, MOVE><<<blocks, PUSH_THREADS, smem, c.stream>>>(A);
+    IPIC_CUDA(cudaGetLastError());
+    return IPIC_OK;
+}
+
+static PushArgs make_push_args(Ctx &c, int sp, double del_t) {
+    SpeciesDev &s = c.sp[sp];
+    PushArgs A{};
+    A.l = s.l; A.vx = s.vx; A.l_out = s.l; A.vx_out = s.vx;
+    A.n = s.n;
+    const int cells = (c.scheme == IPIC_SCHEME_NGP) ? c.Nh : c.Nx;
+    const size_t tab_stride = (c.scheme == IPIC_SCHEME_NGP) ? sizeof(CellTabNGP) : sizeof(CellTabCIC);
+    A.tab = (const char *)c.d_tab + (size_t)sp * (cells + 2) * tab_stride;
+    A.bc = c.d_bc;
+    A.acc = c.d_acc + (size_t)sp * (std::max(c.Nx, c.Nh) + 2);
+    A.counters = c.d_counters + (size_t)sp * 8;
+    A.Nh = c.Nh;
+    A.NB = (c.scheme == IPIC_SCHEME_NGP) ? c.Nx : c.Nh;
+    A.del_t = del_t;
+    A.f_tol = del_t * ((c.scheme == IPIC_SCHEME_NGP) ? 1.e-15 : 1.e-10);   // NGP :79,172 ; CIC :90,208
+    A.refill_min = std::min(32, std::max(1, c.refill_min));
+    return A;
+}
+
+int launch_deposit(Ctx &c, int sp, double del_t) {
+    if (c.Nh > MAX_GRID_SMEM) { set_error("N_h exceeds the shared-memory grid limit"); return IPIC_ERR_UNSUPPORTED; }
+    PushArgs A = make_push_args(c, sp, del_t);
+    if (A.n == 0) return IPIC_OK;
+    if (c.scheme == IPIC_SCHEME_NGP) return launch_push_t<0, false>(c, A);
+    return launch_push_t<1, false>(c, A);
+}
+
+int launch_move(Ctx &c, int sp, double del_t) {
+    PushArgs A = make_push_args(c, sp, del_t);
+    if (A.n == 0) return IPIC_OK;
+    if (c.scheme == IPIC_SCHEME_NGP) return launch_push_t<0, true>(c, A);
+    return launch_push_t<1, true>(c, A);
+}
+
+// =====================================================================================================
+// rho deposition (interpolateParticleToNodes: NGP mod_Scheme.f90:50-65, CIC mod_Scheme.f90:21-66)
+// =====================================================================================================
+template <int SCHEME>
+__global__ void __launch_bounds__(1024, 1) k_deposit_rho(const double *__restrict__ lpos, long long n, const int *__restrict__ bc, int Nx,
+                                                         unsigned long long *acc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    LimbGrid G;
+    const int ng = Nx + 2;
+    G.g0 = reinterpret_cast<unsigned *>(smem_raw);
+    G.g1 = G.g0 + ng;
+    G.g2 = reinterpret_cast<int *>(G.g1 + ng);
+    G.gacc = acc;
+    limb_grid_zero(G, ng);
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long nround = ((n + stride - 1) / stride) * stride;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+        bool has = false;
+        double l = 0.0;
+        if (i < n) { l = lpos[i]; has = (l >= 0.0); }
+        const int lc = (int)l;
+        const double d = l - (double)lc;
+        if (SCHEME == 0) {
+            warp_deposit2<2>(G, has, lc, fx_from_double(1.0 - d), fx_from_double(d), lane);
+        } else {
+            // quadratic-spline weights with wall folding
+            double wc = -d * d + d + 0.5, wl = 0.5 * (1.0 - d) * (1.0 - d), wr = 0.5 * d * d;
+            int il = lc - 1, ir = lc + 1;
+            bool hl = has, hr = has;
+            if (has) {
+                const int bv = bc[lc + 1] - bc[lc];
+                switch (bv) {
+                case 0: break;
+                case -1: case -4: wc -= wl; hl = false; break;                 // Dirichlet to the left
+                case 1: case 4: wc -= wr; hr = false; break;                   // Dirichlet to the right
+                case -2: wc += wl; hl = false; break;                          // Neumann to the left
+                case 2: wc += wr; hr = false; break;                           // Neumann to the right
+                case -3: il = Nx; break;                                        // periodic to the left
+                case 3: ir = 1; break;                                          // periodic to the right
+                }
+            }
+            warp_deposit<2>(G, has, lc, fx_from_double(wc), lane);
+            warp_deposit<2>(G, hl, il, fx_from_double(wl), lane);
+            warp_deposit<2>(G, hr, ir, fx_from_double(wr), lane);
+        }
+    }
+    __syncthreads();
+    limb_grid_flush(G, Nx);
+}
+
+int launch_deposit_rho(Ctx &c, int sp) {
+    SpeciesDev &s = c.sp[sp];
+    if (s.n == 0) return IPIC_OK;
+    if (c.Nx > MAX_GRID_SMEM) return IPIC_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)3 * (c.Nx + 2) * 4;
+    unsigned long long *acc = c.d_acc + (size_t)sp * (std::max(c.Nx, c.Nh) + 2);
+    static bool cfg0 = false, cfg1 = false;
+    if (c.scheme == IPIC_SCHEME_NGP) {
+        if (!cfg0) { IPIC_CUDA(cudaFuncSetAttribute(k_deposit_rho<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (MAX_GRID_SMEM + 2) * 4)); cfg0 = true; }
+        k_deposit_rho<0><<<c.num_sms, 1024, smem, c.stream>>>(s.l, s.n, c.d_bc, c.Nx, acc);
+    } else {
+        if (!cfg1) { IPIC_CUDA(cudaFuncSetAttribute(k_deposit_rho<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (MAX_GRID_SMEM + 2) * 4)); cfg1 = true; }
+        k_deposit_rho<1><<<c.num_sms, 1024, smem, c.stream>>>(s.l, s.n, c.d_bc, c.Nx, acc);
+    }
+    IPIC_CUDA(cudaGetLastError());
+    return IPIC_OK;
+}
+
+// =====================================================================================================
+// Deterministic particle reductions: fixed grid, fixed tree, fixed final order.
+// =====================================================================================================
+constexpr int RED_BLOCKS = 592, RED_THREADS = 256;
+
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double (&v)[NV], double *out /* [NV] per block */) {
+    __shared__ double sh[NV][RED_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(FULL, x, o);
+        if (lane == 0) sh[k][warp] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double x = 0.0;
+        for (int w = 0; w < RED_THREADS / 32; ++w) x += sh[threadIdx.x][w];
+        out[threadIdx.x] = x;
+    }
+}
+
+// sum(vx^2+vy^2+vz^2), sum vx, sum vy, sum vz over alive particles (mod_particle.f90:206-230)
+__global__ void __launch_bounds__(RED_THREADS) k_moments(const double *__restrict__ l, const double *__restrict__ vx, const double *__restrict__ vy,
+                                                         const double *__restrict__ vz, long long n, double *partial) {
+    double a[4] = {0, 0, 0, 0};
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (l[i] < 0.0) continue;
+        const double x = vx[i], y = vy[i], z = vz[i];
+        a[0] += x * x + y * y + z * z;
+        a[1] += x; a[2] += y; a[3] += z;
+    }
+    block_reduce_store<4>(a, partial + (size_t)blockIdx.x * 4);
+}
+template <int NV>
+__global__ void k_final_sum(const double *partial, int nblocks, double *out) {
+    if (threadIdx.x < NV) {
+        double x = 0.0;
+        for (int b = 0; b < nblocks; ++b) x += partial[(size_t)b * NV + threadIdx.x];
+        out[threadIdx.x] = x;
+    }
+}
+
+int particle_moments(Ctx &c, int sp, double out4[4]) {
+    SpeciesDev &s = c.sp[sp];
+    double *partial = c.d_work;   // needs RED_BLOCKS*4 doubles: allocated with slack in ipic_create
+    k_moments<<<RED_BLOCKS, RED_THREADS, 0, c.stream>>>(s.l, s.vx, s.vy, s.vz, s.n, partial);
+    k_final_sum<4><<<1, 32, 0, c.stream>>>(partial, RED_BLOCKS, c.d_scal);
+    IPIC_CUDA(cudaGetLastError());
+    IPIC_CUDA(cudaMemcpyAsync(c.h_scal, c.d_scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    IPIC_CUDA(cudaStreamSynchronize(c.stream));
+    for (int k = 0; k < 4; ++k) out4[k] = c.h_scal[k];
+    return IPIC_OK;
+}
+
+// =====================================================================================================
+// Stable compaction after moveParticles (mod_particleMover.f90:252-256: survivors keep their order).
+// Pass 1: per-tile survivor counts + wall-loss partial sums.  Pass 2: scan.  Pass 3: stable scatter.
+// =====================================================================================================
+constexpr int CT_THREADS = 256, CT_ITEMS = 16, CT_TILE = CT_THREADS * CT_ITEMS;
+
+__global__ void __launch_bounds__(CT_THREADS) k_compact_count(const double *__restrict__ l, const double *__restrict__ vx, const double *__restrict__ vy,
+                                                              const double *__restrict__ vz, long long n, unsigned *tileCount, double *lossPartial) {
+    const long long base = (long long)blockIdx.x * CT_TILE;
+    unsigned cnt = 0;
+    double a[4] = {0, 0, 0, 0};   // energy L, energy R, momentum L, momentum R
+    for (int k = 0; k < CT_ITEMS; ++k) {
+        const long long i = base + (long long)k * CT_THREADS + threadIdx.x;
+        if (i < n) {
+            const double ll = l[i];
+            if (ll >= 0.0) cnt += 1;
+            else {
+                // energyLoss += v_f**2 + SUM(v_y**2 + v_z**2) ; momentumLoss += v_f   (mod_particleMover.f90:206-215)
+                const double vf = vx[i], y = vy[i], z = vz[i];
+                const double en = vf * vf + (y * y + z * z);
+                if (ll == -1.0) { a[0] += en; a[2] += vf; } else { a[1] += en; a[3] += vf; }
+            }
+        }
+    }
+    __shared__ unsigned shc[CT_THREADS / 32];
+    const unsigned wc = __reduce_add_sync(FULL, cnt);
+    if ((threadIdx.x & 31) == 0) shc[threadIdx.x >> 5] = wc;
+    block_reduce_store<4>(a, lossPartial + (size_t)blockIdx.x * 4);   // has a __syncthreads inside
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+        for (int w = 0; w < CT_THREADS / 32; ++w) t += shc[w];
+        tileCount[blockIdx.x] = t;
+    }
+}
+
+// exclusive scan of tile counts (single block), total to out[0]
+__global__ void __launch_bounds__(1024) k_scan_tiles(const unsigned *tileCount, long long ntiles, long long *tileOffset, long long *total) {
+    __shared__ long long sh[1024];
+    const long long per = (ntiles + 1023) / 1024;
+    const long long b = (long long)threadIdx.x * per, e = min(b + per, ntiles);
+    long long s = 0;
+    for (long long i = b; i < e; ++i) s += tileCount[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long run = 0;
+        for (int t = 0; t < 1024; ++t) { const long long x = sh[t]; sh[t] = run; run += x; }
+        *total = run;
+    }
+    __syncthreads();
+    long long run = sh[threadIdx.x];
+    for (long long i = b; i < e; ++i) { tileOffset[i] = run; run += tileCount[i]; }
+}
+
+__global__ void __launch_bounds__(CT_THREADS) k_compact_scatter(const double *__restrict__ l, const double *__restrict__ vx,
+                                                                const double *__restrict__ vy, const double *__restrict__ vz, long long n,
+                                                                const long long *__restrict__ tileOffset, double *lo, double *vxo, double *vyo,
+                                                                double *vzo) {
+    __shared__ unsigned warpBase[CT_THREADS / 32];
+    __shared__ unsigned running;
+    const long long base = (long long)blockIdx.x * CT_TILE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    const long long off = tileOffset[blockIdx.x];
+    for (int k = 0; k < CT_ITEMS; ++k) {
+        const long long i = base + (long long)k * CT_THREADS + threadIdx.x;
+        double ll = -1.0;
+        if (i < n) ll = l[i];
+        const bool alive = ll >= 0.0;
+        const unsigned m = __ballot_sync(FULL, alive);
+        if (lane == 0) warpBase[warp] = __popc(m);
+        __syncthreads();
+        unsigned wb = 0, tot = 0;
+        for (int w = 0; w < CT_THREADS / 32; ++w) { const unsigned x = warpBase[w]; if (w < warp) wb += x; tot += x; }
+        const unsigned run = running;
+        if (alive) {
+            const long long dst = off + run + wb + __popc(m & ((1u << lane) - 1u));
+            lo[dst] = ll; vxo[dst] = vx[i]; vyo[dst] = vy[i]; vzo[dst] = vz[i];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) running = run + tot;
+        __syncthreads();
+    }
+}
+
+// survivors before each slab boundary -> new slab offsets
+__global__ void k_slab_offsets(const double *__restrict__ l, const long long *__restrict__ tileOffset, const long long *oldOff, long long *newOff, int nb,
+                               long long n) {
+    const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (k >= nb) return;
+    const long long o = oldOff[k];
+    const long long tile = o / CT_TILE;
+    const long long b = tile * CT_TILE;
+    unsigned cnt = 0;
+    for (long long i = b + lane; i < o; i += 32) if (i < n && l[i] >= 0.0) cnt += 1;
+    cnt = __reduce_add_sync(FULL, cnt);
+    if (lane == 0) {
+        const long long ntiles = (n + CT_TILE - 1) / CT_TILE;
+        newOff[k] = (tile < ntiles ? tileOffset[tile] : 0) + cnt;
+    }
+}
+
+int ensure_capacity(Ctx &c, int sp, long long n) {
+    SpeciesDev &s = c.sp[sp];
+    // padded so that whole CHUNKs / tiles may be read past n
+    const long long need = ((n + CT_TILE - 1) / CT_TILE + 1) * CT_TILE;
+    if (need <= s.cap) return IPIC_OK;
+    double *bankA = nullptr, *bankB = nullptr;
+    IPIC_CUDA(cudaMalloc(&bankA, (size_t)need * 4 * sizeof(double)));
+    IPIC_CUDA(cudaMalloc(&bankB, (size_t)need * 4 * sizeof(double)));
+    IPIC_CUDA(cudaMemsetAsync(bankA, 0, (size_t)need * 4 * sizeof(double), c.stream));
+    IPIC_CUDA(cudaMemsetAsync(bankB, 0, (size_t)need * 4 * sizeof(double), c.stream));
+    if (s.l) {
+        if (s.n > 0) {
+            IPIC_CUDA(cudaMemcpyAsync(bankA, s.l, s.n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+            IPIC_CUDA(cudaMemcpyAsync(bankA + need, s.vx, s.n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+            IPIC_CUDA(cudaMemcpyAsync(bankA + 2 * need, s.vy, s.n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+            IPIC_CUDA(cudaMemcpyAsync(bankA + 3 * need, s.vz, s.n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+        }
+        IPIC_CUDA(cudaStreamSynchronize(c.stream));
+        // each bank is one allocation whose base is its l pointer
+        cudaFree(s.l);
+        cudaFree(s.l2);
+    }
+    s.l = bankA; s.vx = bankA + need; s.vy = bankA + 2 * need; s.vz = bankA + 3 * need;
+    s.l2 = bankB; s.vx2 = bankB + need; s.vy2 = bankB + 2 * need; s.vz2 = bankB + 3 * need;
+    s.cap = need; s.cap2 = need;
+    return IPIC_OK;
+}
+
+static void swap_banks(SpeciesDev &s) {
+    std::swap(s.l, s.l2); std::swap(s.vx, s.vx2); std::swap(s.vy, s.vy2); std::swap(s.vz, s.vz2);
+}
+
+// Runs after the move kernel.  Fills wallLoss/energyLoss/momentumLoss and removes absorbed particles.
+int compact_species(Ctx &c, int sp) {
+    SpeciesDev &s = c.sp[sp];
+    const long long n = s.n;
+    if (n == 0) return IPIC_OK;
+    const long long ntiles = (n + CT_TILE - 1) / CT_TILE;
+    if (ntiles > c.cap_tiles) {
+        if (c.d_tileCount) { cudaFree(c.d_tileCount); cudaFree(c.d_tileOffset); cudaFree(c.d_loss); }
+        c.cap_tiles = ntiles + ntiles / 4 + 16;
+        IPIC_CUDA(cudaMalloc(&c.d_tileCount, c.cap_tiles * sizeof(unsigned)));
+        IPIC_CUDA(cudaMalloc(&c.d_tileOffset, c.cap_tiles * sizeof(long long)));
+        IPIC_CUDA(cudaMalloc(&c.d_loss, c.cap_tiles * 4 * sizeof(double)));
+    }
+    if (!c.d_total) IPIC_CUDA(cudaMalloc(&c.d_total, 8 * sizeof(long long)));
+    const int nb = (int)s.slab_off.size();
+    if (nb > c.cap_slab) {
+        if (c.d_slab) cudaFree(c.d_slab);
+        c.cap_slab = nb + 64;
+        IPIC_CUDA(cudaMalloc(&c.d_slab, (size_t)2 * c.cap_slab * sizeof(long long)));
+    }
+    unsigned *d_tileCount = c.d_tileCount; long long *d_tileOffset = c.d_tileOffset; double *d_loss = c.d_loss;
+    long long *d_total = c.d_total; long long *d_slab = c.d_slab; const int cap_slab = c.cap_slab;
+    k_compact_count<<<(unsigned)ntiles, CT_THREADS, 0, c.stream>>>(s.l, s.vx, s.vy, s.vz, n, d_tileCount, d_loss);
+    k_scan_tiles<<<1, 1024, 0, c.stream>>>(d_tileCount, ntiles, d_tileOffset, d_total);
+    k_final_sum<4><<<1, 32, 0, c.stream>>>(d_loss, (int)ntiles, c.d_scal);
+    IPIC_CUDA(cudaGetLastError());
+    long long total = 0;
+    IPIC_CUDA(cudaMemcpyAsync(&total, d_total, sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
+    IPIC_CUDA(cudaMemcpyAsync(c.h_scal, c.d_scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    IPIC_CUDA(cudaStreamSynchronize(c.stream));
+    s.stats.energyLoss[0] = c.h_scal[0]; s.stats.energyLoss[1] = c.h_scal[1];
+    s.stats.momentumLoss[0] += c.h_scal[2]; s.stats.momentumLoss[1] += c.h_scal[3];
+    if (total == n) return IPIC_OK;   // nothing absorbed: arrays already compact
+    if (nb > 0) {
+        IPIC_CUDA(cudaMemcpyAsync(d_slab, s.slab_off.data(), nb * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
+        k_slab_offsets<<<(nb + 7) / 8, 256, 0, c.stream>>>(s.l, d_tileOffset, d_slab, d_slab + cap_slab, nb, n);
+    }
+    k_compact_scatter<<<(unsigned)ntiles, CT_THREADS, 0, c.stream>>>(s.l, s.vx, s.vy, s.vz, n, d_tileOffset, s.l2, s.vx2, s.vy2, s.vz2);
+    IPIC_CUDA(cudaGetLastError());
+    if (nb > 0) IPIC_CUDA(cudaMemcpyAsync(s.slab_off.data(), d_slab + cap_slab, nb * sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
+    IPIC_CUDA(cudaStreamSynchronize(c.stream));
+    if (nb > 0) s.slab_off[nb - 1] = total;
+    swap_banks(s);
+    s.n = total;
+    return IPIC_OK;
+}
+
+// =====================================================================================================
+// AoS slab <-> SoA transposition (reference layout phaseSpace(4, finalIdx, T), mod_particle.f90:23,65)
+// =====================================================================================================
+__global__ void k_aos_to_soa(const double4 *__restrict__ aos, long long n, double *l, double *vx, double *vy, double *vz) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double4 p = aos[i];
+        l[i] = p.x; vx[i] = p.y; vy[i] = p.z; vz[i] = p.w;
+    }
+}
+__global__ void k_soa_to_aos(double4 *aos, long long n, const double *__restrict__ l, const double *__restrict__ vx, const double *__restrict__ vy,
+                             const double *__restrict__ vz) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) aos[i] = make_double4(l[i], vx[i], vy[i], vz[i]);
+}
+
+int upload_species(Ctx &c, int sp, const double *ps, const int32_t *N_p, int T, int finalIdx) {
+    SpeciesDev &s = c.sp[sp];
+    long long n = 0;
+    for (int t = 0; t < T; ++t) {
+        if (N_p[t] < 0 || N_p[t] > finalIdx) { set_error("N_p out of range"); return IPIC_ERR_ARG; }
+        n += N_p[t];
+    }
+    int rc = ensure_capacity(c, sp, n);
+    if (rc) return rc;
+    s.slab_off.assign(T + 1, 0);
+    double *stage = s.l2;   // bank B as flat AoS staging (4*cap doubles)
+    long long off = 0;
+    for (int t = 0; t < T; ++t) {
+        s.slab_off[t] = off;
+        if (N_p[t] > 0)
+            IPIC_CUDA(cudaMemcpyAsync(stage + 4 * off, ps + (size_t)4 * finalIdx * t, (size_t)N_p[t] * 4 * sizeof(double), cudaMemcpyHostToDevice,
+                                      c.stream));
+        off += N_p[t];
+    }
+    s.slab_off[T] = off;
+    s.n = n;
+    if (n > 0) {
+        k_aos_to_soa<<<c.num_sms * 4, 256, 0, c.stream>>>(reinterpret_cast<const double4 *>(stage), n, s.l, s.vx, s.vy, s.vz);
+        IPIC_CUDA(cudaGetLastError());
+    }
+    IPIC_CUDA(cudaStreamSynchronize(c.stream));
+    return IPIC_OK;
+}
+
+int download_species(Ctx &c, int sp, double *ps, int32_t *N_p, int T, int finalIdx) {
+    SpeciesDev &s = c.sp[sp];
+    if ((int)s.slab_off.size() != T + 1) {
+        // particles did not come from slabs (device loader / sorted): split evenly, as the reference loader does
+        s.slab_off.assign(T + 1, 0);
+        for (int t = 0; t <= T; ++t) s.slab_off[t] = s.n * t / T;
+    }
+    double *stage = s.l2;
+    if (s.n > 0) {
+        k_soa_to_aos<<<c.num_sms * 4, 256, 0, c.stream>>>(reinterpret_cast<double4 *>(stage), s.n, s.l, s.vx, s.vy, s.vz);
+        IPIC_CUDA(cudaGetLastError());
+    }
+    for (int t = 0; t < T; ++t) {
+        const long long cnt = s.slab_off[t + 1] - s.slab_off[t];
+        if (cnt > finalIdx) { set_error("slab larger than finalIdx"); return IPIC_ERR_ARG; }
+        N_p[t] = (int32_t)cnt;
+        if (cnt > 0)
+            IPIC_CUDA(cudaMemcpyAsync(ps + (size_t)4 * finalIdx * t, stage + 4 * s.slab_off[t], (size_t)cnt * 4 * sizeof(double),
+                                      cudaMemcpyDeviceToHost, c.stream));
+    }
+    IPIC_CUDA(cudaStreamSynchronize(c.stream));
+    return IPIC_OK;
+}
+
+// =====================================================================================================
+// Device synthetic loader: uniform x -> l = getLFromX(x), 3-D Maxwellian by Box-Muller
+// (mod_particle.f90:84-97, 156-191) from a counter-based PCG32 stream (one short stream per particle).
+// =====================================================================================================
+__device__ __forceinline__ unsigned pcg32_next(unsigned long long &state, unsigned long long inc) {
+    const unsigned long long old = state;
+    state = old * 6364136223846793005ULL + inc;
+    const unsigned xorshifted = (unsigned)(((old >> 18u) ^ old) >> 27u);
+    const unsigned rot = (unsigned)(old >> 59u);
+    return (xorshifted >> rot) | (xorshifted << ((0u - rot) & 31u));
+}
+__device__ __forceinline__ double pcg_uniform(unsigned long long &state, unsigned long long inc) {
+    // (res + 1) / (2^32 + 1): in (0,1), the mapping of PIC1D/SharedModules/src/PCG_func.c:9-20
+    return ((double)pcg32_next(state, inc) + 1.0) / 4294967297.0;
+}
+
+__global__ void k_generate(double *l, double *vx, double *vy, double *vz, long long n, long long first_index, const double *__restrict__ grid,
+                           const double *__restrict__ dx, int Nx, int scheme, double startX, double L_domain, double v_therm, double v_drift,
+                           unsigned long long seed) {
+    const double two_pi = 6.283185307179586476925286766559;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long gid = (unsigned long long)(first_index + i);
+        unsigned long long inc = ((seed ^ (gid * 0x9E3779B97F4A7C15ULL)) << 1u) | 1u;
+        unsigned long long state = 0ULL;
+        pcg32_next(state, inc);
+        state += seed + gid;
+        pcg32_next(state, inc);
+        const double U0 = pcg_uniform(state, inc), U1 = pcg_uniform(state, inc), U2 = pcg_uniform(state, inc), U3 = pcg_uniform(state, inc),
+                     U4 = pcg_uniform(state, inc);
+        const double x = U0 * L_domain + startX;
+        int lo = 1, hi = Nx;   // grid arrays here are 0-based: grid[k-1] = grid(k)
+        double lpos;
+        if (scheme == 0) {
+            while (lo != hi - 1) { const int mid = (lo + hi) / 2; if (grid[mid - 1] <= x) lo = mid; else hi = mid; }
+            lpos = lo + (x - grid[lo - 1]) / dx[lo - 1];
+        } else {
+            while (lo != hi - 1) { const int mid = (lo + hi) / 2; if (grid[mid - 1] - 0.5 * dx[mid - 1] <= x) lo = mid; else hi = mid; }
+            if (grid[lo - 1] + 0.5 * dx[lo - 1] <= x) lo = hi;
+            lpos = lo + 0.5 + (x - grid[lo - 1]) / dx[lo - 1];
+        }
+        l[i] = lpos;
+        const double r1 = v_therm * sqrt(-2.0 * log(U1)), r3 = v_therm * sqrt(-2.0 * log(U3));
+        vx[i] = r1 * cos(two_pi * U2) + v_drift;
+        vy[i] = r1 * sin(two_pi * U2);
+        vz[i] = r3 * sin(two_pi * U4);
+    }
+}
+
+int generate_species(Ctx &c, int sp, long long n, double T_eV, double v_drift, unsigned long long seed) {
+    SpeciesDev &s = c.sp[sp];
+    int rc = ensure_capacity(c, sp, n);
+    if (rc) return rc;
+    double startX, L;
+    if (c.scheme == IPIC_SCHEME_NGP) { startX = c.h_grid[0]; L = c.h_grid[c.Nx - 1] - c.h_grid[0]; }
+    else { startX = c.h_grid[0] - 0.5 * c.h_dx[0]; L = c.h_grid[c.Nx - 1] + 0.5 * c.h_dx[c.Nx - 1] - startX; }
+    const double v_therm = sqrt(T_eV * e_c / s.mass);
+    const long long first = (long long)c.rank * n;   // ranks draw disjoint index ranges of one global stream
+    k_generate<<<c.num_sms * 8, 256, 0, c.stream>>>(s.l, s.vx, s.vy, s.vz, n, first, c.d_grid, c.d_dx, c.Nx, c.scheme, startX, L, v_therm, v_drift,
+                                                     seed + 0x1000003ULL * (unsigned long long)sp);
+    IPIC_CUDA(cudaGetLastError());
+    s.n = n;
+    s.slab_off.clear();
+    IPIC_CUDA(cudaStreamSynchronize(c.stream));
+    return IPIC_OK;
+}
+
+// =====================================================================================================
+// Cell sort: stable LSD radix sort of (cell key, index) + gather.  Maintenance op, not on the hot path.
+// =====================================================================================================
+__global__ void k_sort_keys(const double *__restrict__ l, long long n, unsigned *keys, unsigned *vals) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double ll = l[i];
+        keys[i] = ll >= 0.0 ? (unsigned)(int)ll : 0xFFFFu;   // dead particles sort to the end
+        vals[i] = (unsigned)i;
+    }
+}
+__global__ void k_gather4(const unsigned *__restrict__ perm, long long n, const double *__restrict__ l, const double *__restrict__ vx,
+                          const double *__restrict__ vy, const double *__restrict__ vz, double *lo, double *vxo, double *vyo, double *vzo) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned j = perm[i];
+        lo[i] = l[j]; vxo[i] = vx[j]; vyo[i] = vy[j]; vzo[i] = vz[j];
+    }
+}
+
+int sort_species(Ctx &c, int sp) {
+    SpeciesDev &s = c.sp[sp];
+    const long long n = s.n;
+    if (n <= 1) return IPIC_OK;
+    if (n >= (1ll << 32)) { set_error("sort: more than 2^32 particles per GPU"); return IPIC_ERR_UNSUPPORTED; }
+    unsigned *keys = nullptr, *keys2 = nullptr, *vals = nullptr, *vals2 = nullptr;
+    void *tmp = nullptr; size_t tmp_bytes = 0;
+    IPIC_CUDA(cudaMalloc(&keys, n * 4)); IPIC_CUDA(cudaMalloc(&keys2, n * 4));
+    IPIC_CUDA(cudaMalloc(&vals, n * 4)); IPIC_CUDA(cudaMalloc(&vals2, n * 4));
+    k_sort_keys<<<c.num_sms * 8, 256, 0, c.stream>>>(s.l, n, keys, vals);
+    int bits = 1; while ((1 << bits) <= std::max(c.Nx, c.Nh) + 1) ++bits;
+    bits = std::max(bits, 16);
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, vals, vals2, (int)n, 0, bits, c.stream);
+    IPIC_CUDA(cudaMalloc(&tmp, tmp_bytes));
+    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, vals2, (int)n, 0, bits, c.stream);
+    k_gather4<<<c.num_sms * 8, 256, 0, c.stream>>>(vals2, n, s.l, s.vx, s.vy, s.vz, s.l2, s.vx2, s.vy2, s.vz2);
+    IPIC_CUDA(cudaGetLastError());
+    IPIC_CUDA(cudaStreamSynchronize(c.stream));
+    cudaFree(keys); cudaFree(keys2); cudaFree(vals); cudaFree(vals2); cudaFree(tmp);
+    swap_banks(s);
+    s.slab_off.clear();   // slab identity is not preserved by a sort
+    return IPIC_OK;
+}
+
+}  // namespace ipic

@@ -1,0 +1,91 @@
+"""Host-side `type(Particle)` (OpenMP/SharedModules/src/mod_particle.f90:15-74).
+
+Holds the species scalars and, optionally, a host copy of phaseSpace in the reference's slab layout
+(numThread, finalIdx, 4) == Fortran phaseSpace(4, finalIdx, numThread).  The live particles are device
+resident; `upload`/`download` move them through the C ABI."""
+import ctypes as C
+import numpy as np
+from . import _lib
+
+
+class Particle:
+    def __init__(self, mass, q, w_p, N_p, finalIdx, particleName, numThread):
+        """particle_constructor (mod_particle.f90:46-74); N_p is particles per thread slab."""
+        self.name = particleName
+        self.mass, self.q, self.w_p = float(mass), float(q), float(w_p)
+        self.q_over_m = self.q / self.mass
+        self.q_times_wp = self.q * self.w_p
+        self.finalIdx, self.numThread = int(finalIdx), int(numThread)
+        self.N_p = np.full(self.numThread, int(N_p), dtype=np.int32)
+        self.phaseSpace = None            # host copy, allocated on demand
+        self.delIdx = 0
+        self.refIdx = 0
+        self.wallLoss = np.zeros(2)
+        self.energyLoss = np.zeros(2)
+        self.momentumLoss = np.zeros(2)
+        self.accumEnergyLoss = np.zeros(2)
+        self.accumWallLoss = np.zeros(2, dtype=np.int64)
+        self.numSubStepsAve = 0.0
+        self.numFuncEvalAve = 0.0
+        self._solver = None
+        self._index = -1
+
+    def initialize_n_ave(self, n_ave, L_domain):
+        """mod_particle.f90:76-82"""
+        self.w_p = n_ave * L_domain / float(np.sum(self.N_p))
+        self.q_times_wp = self.q * self.w_p
+        if self._solver is not None:
+            _lib.check(_lib.load().ipic_set_weight(self._solver._h, self._index, self.w_p))
+
+    def set_phase_space(self, phaseSpace, N_p):
+        ps = np.ascontiguousarray(phaseSpace, dtype=np.float64)
+        if ps.shape != (self.numThread, self.finalIdx, 4):
+            raise ValueError("phaseSpace must have shape (numThread, finalIdx, 4)")
+        self.phaseSpace = ps
+        self.N_p = np.ascontiguousarray(N_p, dtype=np.int32).copy()
+
+    # ---- device residency
+    def upload(self):
+        if self._solver is None:
+            raise RuntimeError("particle is not bound to a potentialSolver")
+        L = _lib.load()
+        _lib.check(L.ipic_upload_particles(self._solver._h, self._index, self.phaseSpace.ctypes.data_as(_lib._dp),
+                                           self.N_p.ctypes.data_as(_lib._ip), self.numThread, self.finalIdx))
+
+    def download(self):
+        if self.phaseSpace is None:
+            self.phaseSpace = np.zeros((self.numThread, self.finalIdx, 4))
+        L = _lib.load()
+        _lib.check(L.ipic_download_particles(self._solver._h, self._index, self.phaseSpace.ctypes.data_as(_lib._dp),
+                                             self.N_p.ctypes.data_as(_lib._ip), self.numThread, self.finalIdx))
+        return self.phaseSpace
+
+    def count(self):
+        n = C.c_int64()
+        _lib.check(_lib.load().ipic_particle_count(self._solver._h, self._index, C.byref(n)))
+        return n.value
+
+    # ---- mod_particle.f90:206-230
+    def getTotalKE(self):
+        out = C.c_double()
+        _lib.check(_lib.load().ipic_get_total_KE(self._solver._h, self._index, C.byref(out)))
+        return out.value
+
+    def getTotalMomentum(self):
+        out = np.zeros(3)
+        _lib.check(_lib.load().ipic_get_total_momentum(self._solver._h, self._index, out.ctypes.data_as(_lib._dp)))
+        return out
+
+    def _refresh_stats(self):
+        st = _lib.MoveStats()
+        _lib.check(_lib.load().ipic_get_move_stats(self._solver._h, self._index, C.byref(st)))
+        self.delIdx, self.refIdx = st.delIdx, st.refIdx
+        self.wallLoss = np.array(st.wallLoss[:])
+        self.energyLoss = np.array(st.energyLoss[:])
+        self.momentumLoss = np.array(st.momentumLoss[:])
+        self.accumEnergyLoss = np.array(st.accumEnergyLoss[:])
+        self.accumWallLoss = np.array(st.accumWallLoss[:], dtype=np.int64)
+        self.numSubStepsAve, self.numFuncEvalAve = st.numSubStepsAve, st.numFuncEvalAve
+        self.numSubSteps, self.numFuncEvals = st.numSubSteps, st.numFuncEvals
+        self.N_p_total = st.N_p
+        return st

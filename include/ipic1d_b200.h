@@ -1,0 +1,190 @@
+/* =============================================================================
+ * ipic1d_b200.h -- C ABI of the B200-native implicit-PIC inner loop
+ *
+ * Drop-in boundary for the hot path of nsavard01/ImplicitPic1D (trees
+ * OpenMP/NGP and OpenMP/CIC): particle mover, J/rho deposition, field solve
+ * and the nonlinear (Anderson / JFNK-residual) iteration.  The reference has
+ * no FFI boundary of its own: callers reach the path through Fortran module
+ * procedures.  Every entry point below names the module procedure it replaces
+ * (file:line under /root/reference/OpenMP); fortran/ipic_b200_shim.f90 shows
+ * the iso_c_binding interface a maintainer adds.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types; every call returns an int
+ *     status (0 = ok); no exceptions cross the boundary.  The Fortran shim maps
+ *     nonzero to `print *, ...; stop`, the reference's only error behaviour.
+ *   - arrays are 0-based C arrays holding the reference's 1-based arrays in
+ *     the same order (element k here = Fortran element k+1).
+ *   - all floating point is IEEE fp64, indices are int32, as in the reference.
+ *   - one host thread per context; all kernels of a context run on one CUDA
+ *     stream; calls that return host data are synchronous.
+ *   - particles live on the device between calls (per-species SoA l, v_x, v_y,
+ *     v_z).  Host copies move only through ipic_upload_particles /
+ *     ipic_download_particles.
+ * ========================================================================== */
+#ifndef IPIC1D_B200_H
+#define IPIC1D_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ipic_ctx *ipic_handle;
+
+/* scheme = which reference tree's semantics are used */
+#define IPIC_SCHEME_NGP 0 /* OpenMP/NGP : phi on N_x nodes, J/E on N_h = N_x-1 cells */
+#define IPIC_SCHEME_CIC 1 /* OpenMP/CIC : phi on N_x centres, J/E on N_h = N_x+1 faces */
+
+/* status codes */
+#define IPIC_OK 0
+#define IPIC_ERR_ARG 1         /* bad argument */
+#define IPIC_ERR_CUDA 2        /* CUDA runtime error (see ipic_last_error) */
+#define IPIC_ERR_STOP 3        /* a condition on which the reference executes `stop` */
+#define IPIC_ERR_NOT_CONVERGED 4
+#define IPIC_ERR_UNSUPPORTED 5
+#define IPIC_ERR_NCCL 6
+
+/* field selectors for ipic_get_field / ipic_set_field */
+#define IPIC_F_PHI 0    /* solver%phi    (N_x) */
+#define IPIC_F_PHI_F 1  /* solver%phi_f  (N_x) */
+#define IPIC_F_J 2      /* solver%J      (N_h) */
+#define IPIC_F_RHO 3    /* solver%rho    (N_x) */
+#define IPIC_F_EFIELD 4 /* solver%EField (N_h) */
+#define IPIC_F_A_TRI 5  /* solver%a_tri  (N_x-1) */
+#define IPIC_F_B_TRI 6  /* solver%b_tri  (N_x) */
+#define IPIC_F_C_TRI 7  /* solver%c_tri  (N_x-1) */
+
+/* linear-solve modes for the tridiagonal Ampere/Poisson systems */
+#define IPIC_TRIDIAG_PCR 0    /* single-block parallel cyclic reduction, cached level coefficients (default) */
+#define IPIC_TRIDIAG_THOMAS 1 /* sequential Thomas sweep in the reference's operation order (parity mode) */
+
+const char *ipic_version(void);
+const char *ipic_last_error(void);
+int ipic_device_count(int *n);
+
+/* ---- world + solver construction -------------------------------------------
+ * replaces: type(Domain) contents built by readWorld        NGP/src/mod_domain.f90:347-391, CIC/src/mod_domain.f90:332-376
+ *           potentialSolver_constructor + construct_diagMatrix
+ *                                                           NGP/src/mod_potentialSolver.f90:50-128, CIC/src/mod_potentialSolver.f90:49-126
+ * grid: N_x doubles; dx_dl: N_h (NGP) or N_x (CIC) doubles; boundaryConditions: N_x (NGP) or N_h (CIC) int32.
+ * The caller (Fortran host) keeps owning its Domain; this copies the tables to the device. */
+int ipic_create(ipic_handle *out, int scheme, int32_t NumberXNodes, const double *grid, const double *dx_dl,
+                const int32_t *boundaryConditions, int gridSmoothBool, int device);
+int ipic_destroy(ipic_handle h);
+int ipic_init_solver(ipic_handle h, double leftVoltage, double rightVoltage, double RF_frequency, double timeCurrent);
+int ipic_set_tridiag_mode(ipic_handle h, int mode);
+
+/* ---- particle container ----------------------------------------------------
+ * replaces: type(Particle)                                   SharedModules/src/mod_particle.f90:15-74
+ * mass [kg], q [C], w_p [1/m^2].  Returns the species index through *species. */
+int ipic_add_species(ipic_handle h, double mass, double q, double w_p, int32_t *species);
+int ipic_set_weight(ipic_handle h, int32_t species, double w_p);
+/* phaseSpace(4, finalIdx, numThread) real64 AoS slabs + N_p(numThread), exactly the reference's arrays
+ * (mod_particle.f90:23,65); transposed to device SoA, slab order preserved. */
+int ipic_upload_particles(ipic_handle h, int32_t species, const double *phaseSpace, const int32_t *N_p, int32_t numThread,
+                          int32_t finalIdx);
+int ipic_download_particles(ipic_handle h, int32_t species, double *phaseSpace, int32_t *N_p, int32_t numThread, int32_t finalIdx);
+int ipic_particle_count(ipic_handle h, int32_t species, int64_t *n);
+/* device-side synthetic loader for loads too large to stage through the host (bench): uniform positions,
+ * Maxwellian velocities (mod_particle.f90:84-97,156-191 rules) from a counter-based PCG32 stream. */
+int ipic_generate_particles(ipic_handle h, int32_t species, int64_t n, double T_eV, double v_drift, uint64_t seed);
+/* periodic cell sort (counting sort on INT(l)); does not change any deposited quantity. */
+int ipic_sort_particles(ipic_handle h, int32_t species);
+
+/* ---- field state -----------------------------------------------------------*/
+int ipic_get_field(ipic_handle h, int which, double *out, int32_t n);
+int ipic_set_field(ipic_handle h, int which, const double *in, int32_t n);
+
+/* ---- the path ---------------------------------------------------------------
+ * depositRho            NGP/src/mod_potentialSolver.f90:130-188   CIC/src/mod_potentialSolver.f90:128-173
+ * solve_tridiag_Poisson NGP :190-226                              CIC :175-218
+ * solveInitialPotential NGP :228-238                              CIC :220-230
+ * makeConstSourceTerm   NGP :267-286                              CIC :246-270
+ * makeHalfTimeEField    NGP :392-406                              CIC :333-366
+ * solve_tridiag_Ampere  NGP :288-330                              CIC :272-301
+ * setRFVoltage          NGP :444-453                              CIC :458-470
+ * resetVoltage          NGP :455-459                              CIC :472-478
+ * depositJ              NGP/src/mod_particleMover.f90:67-157      CIC/src/mod_particleMoverPicard.f90:77-195
+ * moveParticles         NGP/src/mod_particleMover.f90:162-270     CIC/src/mod_particleMoverPicard.f90:198-317 */
+int ipic_deposit_rho(ipic_handle h);
+int ipic_solve_tridiag_poisson(ipic_handle h, double timeCurrent);
+int ipic_solve_initial_potential(ipic_handle h, double timeCurrent);
+int ipic_make_const_source_term(ipic_handle h);
+int ipic_make_half_time_efield(ipic_handle h);
+int ipic_solve_tridiag_ampere(ipic_handle h, double del_t);
+int ipic_set_rf_voltage(ipic_handle h, double timeFuture);
+int ipic_reset_voltage(ipic_handle h);
+int ipic_deposit_J(ipic_handle h, double del_t);
+int ipic_move_particles(ipic_handle h, double del_t);
+
+/* per-species outputs of moveParticles (mod_particle.f90:18-27): totals over the reference's thread slabs.
+ * wallLoss/energyLoss/momentumLoss are [left,right]; energyLoss is the raw sum of v^2 as in the reference. */
+typedef struct {
+    int64_t N_p;            /* SUM(N_p) after the move */
+    int64_t delIdx;         /* SUM(delIdx): absorbed at Dirichlet/RF walls */
+    int64_t refIdx;         /* SUM(refIdx): first reflections at Neumann walls */
+    int64_t numSubSteps;    /* executed do-while trips (numerator of numSubStepsAve) */
+    int64_t numFuncEvals;   /* CIC Picard iterations (numerator of numFuncEvalAve) */
+    double numSubStepsAve;  /* mod_particleMover.f90:265 (single-precision division, as the reference) */
+    double numFuncEvalAve;  /* :266 */
+    double wallLoss[2];
+    double energyLoss[2];
+    double momentumLoss[2]; /* accumulates across steps, as the reference (never reset) */
+    double accumEnergyLoss[2];
+    int64_t accumWallLoss[2];
+} ipic_move_stats;
+int ipic_get_move_stats(ipic_handle h, int32_t species, ipic_move_stats *out);
+/* executed sub-steps of the last depositJ sweep for a species (instrumentation for the throughput metric) */
+int ipic_get_deposit_substeps(ipic_handle h, int32_t species, int64_t *n);
+
+/* ---- nonlinear solvers -------------------------------------------------------
+ * initializeSolver               SharedModules/src/mod_nonLinSolvers.f90:41-81
+ * solveDivAmpereAnderson         :85-160
+ * adaptiveSolveDivAmpereAnderson :162-196
+ * solvePotential                 :198-215
+ * funcNitsol                     :218-239  (residual callback F(x) = x - G(x) for NITSOL's JFNK) */
+int ipic_initialize_solver(ipic_handle h, double eps_a, double eps_r, int solverType, int m_Anderson, double Beta_k, int maxIter);
+int ipic_solve_div_ampere_anderson(ipic_handle h, double del_t);
+int ipic_solve_potential(ipic_handle h, double del_t, double *remainDel_t, double *currDel_t, double timeCurrent);
+int ipic_func_nitsol(ipic_handle h, int32_t n, const double *xcur, double *fcur, double del_t);
+
+typedef struct {
+    int32_t iterNumPicard, iterNumAdaptiveSteps, amountTimeSplits; /* mod_nonLinSolvers.f90:29 */
+    int64_t sweeps;        /* depositJ calls in the last solvePotential */
+    int64_t substeps;      /* executed sub-steps in the last solvePotential (all sweeps + final move, all species) */
+    double moverSeconds;   /* device time in depositJ/moveParticles kernels (moverTimer analogue) */
+    double potSeconds;     /* device time in the field kernels (potTimer analogue) */
+    double lastResidualNorm;
+} ipic_solver_stats;
+int ipic_get_solver_stats(ipic_handle h, ipic_solver_stats *out);
+int ipic_get_norm_history(ipic_handle h, double *out, int32_t nmax, int32_t *n);
+
+/* ---- conservation diagnostics (main.f90:58-114) -------------------------------
+ * getTotalPE NGP :408-420 CIC :369-413 | getJdotE NGP :422-430 CIC :415-426 | getEnergyFromBoundary NGP :432-442 CIC :428-456
+ * getError_tridiag_Poisson NGP :240-265 CIC :232-244 | getChargeContinuityError NGP :358-390 CIC :315-331
+ * getTotalKE / getTotalMomentum mod_particle.f90:206-230 */
+int ipic_get_total_PE(ipic_handle h, int future, double *out);
+int ipic_get_JdotE(ipic_handle h, double del_t, double *out);
+int ipic_get_energy_from_boundary(ipic_handle h, double del_t, double *out);
+int ipic_get_error_tridiag_poisson(ipic_handle h, double *out);
+int ipic_get_charge_continuity_error(ipic_handle h, const double *rho_i, double del_t, double *out);
+int ipic_get_total_KE(ipic_handle h, int32_t species, double *out);
+int ipic_get_total_momentum(ipic_handle h, int32_t species, double *out3);
+
+/* ---- multi-GPU: particles sharded over ranks, one all-reduce of the fixed-point J/rho grid per deposit ------
+ * (pattern of PIC1D/ExplicitPIC_Cpp/src/potential_solver.cpp:142).  unique_id is the 128-byte ncclUniqueId. */
+int ipic_nccl_unique_id(void *out128);
+int ipic_comm_init(ipic_handle h, int32_t nranks, int32_t rank, const void *unique_id128);
+
+/* ---- tuning / introspection ----------------------------------------------------*/
+int ipic_set_option(ipic_handle h, const char *name, double value);
+int ipic_get_timing(ipic_handle h, const char *name, double *ms, int64_t *launches);
+int ipic_reset_timing(ipic_handle h);
+int ipic_synchronize(ipic_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPIC1D_B200_H */

@@ -1,0 +1,279 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical particle sets.
+
+Tolerances (from BASELINE.json north_star): J / rho within 1e-12 relative to max|.|; identical nonlinear
+iteration counts; energy conservation no worse than the oracle.  Integer quantities are compared exactly."""
+import numpy as np
+import pytest
+import implicitpic1d_b200 as ip
+from implicitpic1d_b200 import _lib
+from implicitpic1d_b200.particle_mover import depositSubsteps
+from common import DECKS, build_oracle, build_cuda_from_oracle, deck_del_t, relerr
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+TOL_GRID = 1e-12      # J, rho: relative to max |.|
+ALL = sorted(DECKS)
+
+
+@pytest.fixture(params=ALL)
+def pair(request):
+    d = DECKS[request.param]
+    o = build_oracle(d)
+    world, solver, plist = build_cuda_from_oracle(d, o, tridiag_mode=_lib.TRIDIAG_THOMAS)
+    yield d, o, world, solver, plist
+    solver.close()
+
+
+def test_deposit_rho_and_initial_potential(pair):
+    d, o, world, solver, plist = pair
+    assert relerr(solver.rho, o.get("rho")) < TOL_GRID
+    # Thomas mode reproduces the reference's operation order; the remaining difference is the 1e-16-level rho difference
+    assert relerr(solver.phi, o.get("phi")) < 1e-10
+    assert relerr(solver.phi_f, o.get("phi_f")) < 1e-10
+    for name in ("a_tri", "b_tri", "c_tri"):
+        assert relerr(getattr(solver, name), o.get(name)) < 1e-15
+
+
+def test_pcr_matches_thomas(pair):
+    d, o, world, solver, plist = pair
+    phi_t = solver.phi
+    solver.set_tridiag_mode(_lib.TRIDIAG_PCR)
+    solver.solve_tridiag_Poisson(world, 0.0)
+    assert relerr(solver.phi, phi_t) < 1e-9
+    solver.set_tridiag_mode(_lib.TRIDIAG_THOMAS)
+
+
+def _sync_fields(o, solver):
+    """put the oracle's phi / phi_f on the device so that the particle kernels see identical fields"""
+    solver.phi = o.get("phi")
+    solver.phi_f = o.get("phi_f")
+    solver.rho = o.get("rho")
+
+
+def test_half_time_efield(pair):
+    d, o, world, solver, plist = pair
+    _sync_fields(o, solver)
+    o.makeHalfTimeEField()
+    solver.makeHalfTimeEField()
+    assert relerr(solver.EField, o.get("EField")) < 1e-14
+
+
+def test_depositJ(pair):
+    d, o, world, solver, plist = pair
+    _sync_fields(o, solver)
+    del_t = deck_del_t(d)
+    o.depositJ(del_t)
+    ip.depositJ(solver, plist, world, del_t)
+    Jo, Jg = o.get("J"), solver.J
+    assert relerr(Jg, Jo) < TOL_GRID, relerr(Jg, Jo)
+    for sp, p in enumerate(plist):
+        assert depositSubsteps(solver, p) == o.move_stats(sp)["substepsDeposit"]
+    # deterministic: bit-identical on repeat, for any refill threshold, and after a cell sort
+    ip.depositJ(solver, plist, world, del_t)
+    assert np.array_equal(solver.J, Jg)
+    for rm in (1, 32):
+        solver.set_option("refill_min", rm)
+        ip.depositJ(solver, plist, world, del_t)
+        assert np.array_equal(solver.J, Jg)
+    solver.set_option("refill_min", 8)
+
+
+def test_ampere_solve(pair):
+    d, o, world, solver, plist = pair
+    _sync_fields(o, solver)
+    del_t = deck_del_t(d)
+    o.makeConstSourceTerm()
+    solver.makeConstSourceTerm()
+    assert relerr(solver.rho, o.get("rho")) < 1e-13
+    o.depositJ(del_t)
+    o.solve_tridiag_Ampere(del_t)
+    solver.J = o.get("J")
+    solver.solve_tridiag_Ampere(world, del_t)
+    assert relerr(solver.phi_f, o.get("phi_f")) < 1e-13       # same J, same operation order
+    solver.set_tridiag_mode(_lib.TRIDIAG_PCR)
+    solver.phi_f = o.get("phi")
+    solver.solve_tridiag_Ampere(world, del_t)
+    assert relerr(solver.phi_f, o.get("phi_f")) < 1e-8
+    solver.set_tridiag_mode(_lib.TRIDIAG_THOMAS)
+
+
+def test_moveParticles(pair):
+    d, o, world, solver, plist = pair
+    _sync_fields(o, solver)
+    del_t = deck_del_t(d)
+    o.moveParticles(del_t)
+    ip.moveParticles(solver, plist, world, del_t)
+    for sp, p in enumerate(plist):
+        c = o.counters(sp)
+        ms = o.move_stats(sp)
+        assert p.delIdx == int(c["delIdx"].sum())
+        assert p.refIdx == int(c["refIdx"].sum())
+        assert np.array_equal(p.wallLoss, c["wallLoss"].sum(axis=0))
+        assert p.numSubSteps == ms["substepsMove"]
+        assert p.numFuncEvals == ms["funcEvalsMove"]
+        assert p.numSubStepsAve == ms["numSubStepsAve"]
+        el = c["energyLoss"].sum(axis=0)
+        np.testing.assert_allclose(p.energyLoss, el, rtol=1e-12, atol=0)
+        np.testing.assert_allclose(p.momentumLoss, c["momentumLoss"].sum(axis=0), rtol=1e-11, atol=1e-9)
+        ps_g = p.download()
+        ps_o = o.phase_space(sp)
+        assert np.array_equal(p.N_p, o.N_p(sp))            # per-slab survivor counts: stable compaction
+        for t in range(d["T"]):
+            n = p.N_p[t]
+            lo, lg = ps_o[t, :n, 0], ps_g[t, :n, 0]
+            assert np.max(np.abs(lg - lo)) < 1e-9, (sp, t, np.max(np.abs(lg - lo)))
+            np.testing.assert_allclose(ps_g[t, :n, 1], ps_o[t, :n, 1], rtol=1e-9, atol=1e-6)
+            assert np.array_equal(ps_g[t, :n, 2:], ps_o[t, :n, 2:])   # v_y, v_z are carried bit-for-bit
+        assert abs(p.getTotalKE() - o.getTotalKE(sp)) < 1e-12 * abs(o.getTotalKE(sp))
+        np.testing.assert_allclose(p.getTotalMomentum(), o.getTotalMomentum(sp), rtol=1e-9, atol=1e-30)
+
+
+def _one_step(d, o, world, solver, plist):
+    del_t = deck_del_t(d)
+    rho_i_o, rho_i_g = o.get("rho"), solver.rho
+    KE_i_o = sum(o.getTotalKE(s) for s in range(2))
+    KE_i_g = sum(p.getTotalKE() for p in plist)
+    ro, co = o.solvePotential(del_t, del_t, del_t, 0.0)
+    rg, cg = ip.solvePotential(solver, plist, world, del_t, del_t, del_t, 0.0)
+    so, sg = o.solver_stats(), ip.SolverState(solver)
+    # energy bookkeeping of main.f90:75-93
+    PE_i_o, PE_i_g = o.getTotalPE(False), solver.getTotalPE(world, False)
+    KE_f_o = KE_f_g = 0.0
+    for s, p in enumerate(plist):
+        sc = o.species_scalars(s)
+        KE_f_o += o.getTotalKE(s) + o.lostEnergySum(s) * sc["mass"] * sc["w_p"] * 0.5
+        KE_f_g += p.getTotalKE() + p.energyLoss.sum() * p.mass * p.w_p * 0.5
+    PE_f_o = o.getTotalPE(True) - o.getEnergyFromBoundary(co)
+    PE_f_g = solver.getTotalPE(world, True) - solver.getEnergyFromBoundary(world, cg)
+    e_o = abs((PE_i_o + KE_i_o - PE_f_o - KE_f_o) / (PE_i_o + KE_i_o))
+    e_g = abs((PE_i_g + KE_i_g - PE_f_g - KE_f_g) / (PE_i_g + KE_i_g))
+    return dict(ro=ro, co=co, rg=rg, cg=cg, so=so, sg=sg, e_o=e_o, e_g=e_g, rho_i_o=rho_i_o, rho_i_g=rho_i_g)
+
+
+def test_solvePotential_iteration_parity(pair):
+    """config 2 of BASELINE.json: same nonlinear iteration counts, energy conservation no worse than the reference path."""
+    d, o, world, solver, plist = pair
+    r = _one_step(d, o, world, solver, plist)
+    so, sg = r["so"], r["sg"]
+    assert (r["rg"], r["cg"]) == (r["ro"], r["co"])
+    assert sg.iterNumPicard == so["iterNumPicard"], (sg.normHistory, o.norm_history())
+    assert sg.sweeps == so["sweeps"]
+    assert sg.amountTimeSplits == so["amountTimeSplits"]
+    assert sg.substeps == so["substeps"]
+    nh_o, nh_g = o.norm_history(), sg.normHistory
+    assert len(nh_o) == len(nh_g)
+    # the residual history agrees until it reaches the round-off floor of the fixed point
+    floor = 1e-9 * nh_o[0]
+    for a, b in zip(nh_g, nh_o):
+        assert abs(a - b) <= 1e-6 * b + floor
+    assert relerr(solver.phi_f, o.get("phi_f")) < 1e-9
+    assert relerr(solver.J, o.get("J")) < 1e-8
+    assert r["e_g"] <= max(2.0 * r["e_o"], 1e-12), (r["e_g"], r["e_o"])
+    for sp, p in enumerate(plist):
+        assert p.count() == int(o.N_p(sp).sum())
+    # charge continuity and Gauss law after the step (main.f90:102-114)
+    o.depositRho()
+    solver.depositRho(plist, world)
+    assert relerr(solver.rho, o.get("rho")) < 1e-11
+    ce_o = o.getChargeContinuityError(r["rho_i_o"], r["co"])
+    ce_g = solver.getChargeContinuityError(r["rho_i_g"], world, r["cg"])
+    assert ce_g < max(10 * ce_o, 1e-9), (ce_g, ce_o)
+    assert abs(solver.getError_tridiag_Poisson(world) - o.getError_tridiag_Poisson()) <= 1e-6 * o.getError_tridiag_Poisson() + 1e-12
+    assert abs(solver.getJdotE(world, r["cg"]) - o.getJdotE(r["co"])) <= 1e-8 * abs(o.getJdotE(r["co"])) + 1e-30
+
+
+@pytest.mark.parametrize("name", ["ngp_rf", "cic_rf"])
+def test_solvePotential_pcr_mode(name):
+    """production mode (PCR field solve): same iteration count as the oracle on the default decks"""
+    d = DECKS[name]
+    o = build_oracle(d)
+    world, solver, plist = build_cuda_from_oracle(d, o, tridiag_mode=_lib.TRIDIAG_PCR)
+    try:
+        r = _one_step(d, o, world, solver, plist)
+        assert r["sg"].iterNumPicard == r["so"]["iterNumPicard"]
+        assert r["e_g"] <= max(2.0 * r["e_o"], 1e-12)
+        assert relerr(solver.phi_f, o.get("phi_f")) < 1e-7
+    finally:
+        solver.close()
+
+
+@pytest.mark.parametrize("name", ["ngp_rf", "cic_rf"])
+def test_funcNitsol_residual(name):
+    """JFNK residual callback F(x) = x - G(x) (mod_nonLinSolvers.f90:218-239) against the oracle's pieces"""
+    d = DECKS[name]
+    o = build_oracle(d)
+    world, solver, plist = build_cuda_from_oracle(d, o, tridiag_mode=_lib.TRIDIAG_THOMAS)
+    try:
+        del_t = deck_del_t(d)
+        _sync_fields(o, solver)
+        o.makeConstSourceTerm()
+        solver.makeConstSourceTerm()
+        x = o.get("phi_f") * (1.0 + 1e-3 * np.sin(np.arange(d["Nx"])))
+        o.set("phi_f", x)
+        o.depositJ(del_t)
+        o.solve_tridiag_Ampere(del_t)
+        f_o = x - o.get("phi_f")
+        f_g = ip.funcNitsol(solver, plist, x, del_t)
+        assert relerr(f_g, f_o) < 1e-9
+    finally:
+        solver.close()
+
+
+def test_sort_keeps_J_bitwise_and_sorts():
+    d = DECKS["ngp_rf"]
+    o = build_oracle(d)
+    world, solver, plist = build_cuda_from_oracle(d, o)
+    try:
+        del_t = deck_del_t(d)
+        ip.depositJ(solver, plist, world, del_t)
+        J0 = solver.J
+        L = ip.load_library()
+        for p in plist:
+            _lib.check(L.ipic_sort_particles(solver._h, p._index))
+        ip.depositJ(solver, plist, world, del_t)
+        assert np.array_equal(solver.J, J0)
+        ps = plist[0].download()
+        l = np.concatenate([ps[t, :plist[0].N_p[t], 0] for t in range(d["T"])])
+        assert np.all(np.diff(np.floor(l)) >= 0)
+        assert l.size == int(o.N_p(0).sum())
+    finally:
+        solver.close()
+
+
+def test_large_load_properties():
+    """size-independent properties at a device-generated load: charge continuity, energy conservation, determinism"""
+    import ctypes as C
+    from implicitpic1d_b200.domain import readWorld
+    from implicitpic1d_b200 import constants as K
+    n_ave, T_e, Nx, L_dom = 1e16, 4.0, 1025, 0.05
+    world = readWorld(0, Nx, L_dom, 0, 0.0, 1, 1, 1, T_e, n_ave)
+    solver = ip.potentialSolver(world, 0.0, 0.0, 0.0, 0.0)
+    try:
+        N = 2_000_000
+        L = ip.load_library()
+        m_ion = 4.002602 * K.m_amu - K.m_e
+        e = ip.Particle(K.m_e, -K.e, n_ave * world.L_domain / N, 0, 0, "e", 1)
+        ion = ip.Particle(m_ion, K.e, n_ave * world.L_domain / N, 0, 0, "He+", 1)
+        plist = [e, ion]
+        solver._bind(plist)
+        _lib.check(L.ipic_generate_particles(solver._h, 0, N, T_e, 0.0, 1234))
+        _lib.check(L.ipic_generate_particles(solver._h, 1, N, 0.025, 0.0, 1234))
+        for p in plist:
+            _lib.check(L.ipic_sort_particles(solver._h, p._index))
+        ip.initializeSolver(solver, 1e-8, 0.0, 0, 10, 0.5, 100)
+        solver.solveInitialPotential(plist, world, 0.0)
+        rho_i = solver.rho
+        del_t = K.del_t_from_deck(n_ave, 1.0, 1.0)
+        KE_i = sum(p.getTotalKE() for p in plist)
+        r, c = ip.solvePotential(solver, plist, world, del_t, del_t, del_t, 0.0)
+        st = ip.SolverState(solver)
+        assert st.iterNumPicard < 100
+        PE_i = solver.getTotalPE(world, False)
+        KE_f = sum(p.getTotalKE() + p.energyLoss.sum() * p.mass * p.w_p * 0.5 for p in plist)
+        PE_f = solver.getTotalPE(world, True) - solver.getEnergyFromBoundary(world, c)
+        assert abs((PE_i + KE_i - PE_f - KE_f) / (PE_i + KE_i)) < 1e-9
+        solver.depositRho(plist, world)
+        assert solver.getChargeContinuityError(rho_i, world, c) < 1e-6
+        assert sum(p.count() + p.delIdx for p in plist) == 2 * N
+    finally:
+        solver.close()

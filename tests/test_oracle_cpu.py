@@ -1,0 +1,175 @@
+"""CPU tests: the oracle against analytic known answers and the reference's own acceptance invariants
+(main.f90:93-114), the host-side Domain against the oracle's, and the C-ABI export list."""
+import os
+import re
+import subprocess
+import numpy as np
+import pytest
+from oracle import oracle_py as op
+import implicitpic1d_b200 as ip
+from implicitpic1d_b200.domain import readWorld, Domain
+from common import DECKS, build_oracle, deck_del_t
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_ran2_known_answer():
+    # Park-Miller minimal standard: seed 1 -> 16807, and the 10000th value is 1043618065 (Park & Miller 1988)
+    import ctypes as C
+    L = op.lib()
+    s = C.c_int32(1)
+    r = L.orc_ran2(C.byref(s))
+    assert s.value == 16807 and abs(r - 16807 / 2147483647.0) < 1e-18
+    for _ in range(9999):
+        L.orc_ran2(C.byref(s))
+    assert s.value == 1043618065
+
+
+def test_pcg_matches_reference_c_function():
+    # randPCG (mod_BasicFunctions.f90:76-96) uses the PCG32 XSH-RR step of PIC1D/SharedModules/src/PCG_func.c
+    import ctypes as C
+    L = op.lib()
+    st = C.c_uint64(42)
+    state = 42
+    for _ in range(100):
+        old = state
+        state = (old * 6364136223846793005 + 1442695040888963407) & ((1 << 64) - 1)
+        xs = (((old >> 18) ^ old) >> 27) & 0xFFFFFFFF
+        rot = old >> 59
+        rn = ((xs >> rot) | (xs << ((-rot) & 31))) & 0xFFFFFFFF
+        sgn = rn - (1 << 32) if rn >= (1 << 31) else rn
+        expect = (float(sgn) + 2147483648.0) / 4294967296.0
+        got = L.orc_randPCG(C.byref(st))
+        assert st.value == state and got == expect
+
+
+@pytest.mark.parametrize("scheme,gridType", [(0, 0), (0, 1), (0, 2), (0, 3), (0, 5), (1, 0), (1, 1), (1, 2), (1, 5)])
+def test_domain_matches_oracle(scheme, gridType):
+    Nx, L, dx_min = 65, 0.05, 2e-4
+    bcl = 1
+    o = op.Oracle(scheme, Nx, L, gridType, dx_min, bcl, 1, False, 2)
+    g, dx, bc = o.grid()
+    w = Domain(scheme, Nx, bcl, 1).constructGrid(dx_min, L, gridType)
+    np.testing.assert_allclose(w.grid, g, rtol=0, atol=1e-15 * L)
+    np.testing.assert_allclose(w.dx_dl, dx, rtol=1e-12, atol=1e-18)
+    assert np.array_equal(w.boundaryConditions, bc)
+    assert abs(w.L_domain - o.L_domain) < 1e-15
+    rng = np.random.default_rng(1)
+    for x in rng.uniform(w.startX, w.endX, 50):
+        l = w.getLFromX(x)
+        assert abs(l - o.getLFromX(x)) < 1e-12
+        assert abs(w.getXFromL(l) - x) < 1e-12 * L + 1e-18
+
+
+def test_poisson_analytic_parabola():
+    # TestCombination.f90's check: uniform rho between grounded walls -> phi(x) = rho x (L - x) / (2 eps0)
+    Nx, L = 129, 0.02
+    o = op.Oracle(op.NGP, Nx, L, 0, 0.0, 1, 1, False, 1)
+    o.init_solver(0.0, 0.0)
+    o.add_species(op.m_e, -op.e, 10, 1)
+    g, dx, bc = o.grid()
+    rho_phys = 1e-6                                    # C/m^3
+    rho_logical = rho_phys * np.r_[0.0, 0.5 * (dx[:-1] + dx[1:]), 0.0]   # the solver's rho is charge per node
+    o.set("rho", rho_logical)
+    o.solve_tridiag_Poisson(0.0)
+    phi = o.get("phi")
+    exact = rho_phys * g * (L - g) / (2 * op.eps_0)
+    assert np.max(np.abs(phi - exact)) < 1e-10 * np.max(exact)
+
+
+def test_normal_equation_solves_least_squares():
+    rng = np.random.default_rng(0)
+    m, n = 200, 6
+    A = rng.normal(size=(m, n))
+    b = rng.normal(size=m)
+    out = np.zeros(n)
+    Af = np.asfortranarray(A)
+    op.lib().orc_solve_normal_equation(Af.ctypes.data_as(op.C.POINTER(op.C.c_double)), b.ctypes.data_as(op.C.POINTER(op.C.c_double)), m, n,
+                                       out.ctypes.data_as(op.C.POINTER(op.C.c_double)))
+    ref = np.linalg.lstsq(A, b, rcond=None)[0]
+    np.testing.assert_allclose(out, ref, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", sorted(DECKS))
+def test_reference_invariants_one_step(name):
+    """main.f90:58-114: energy error ~ solver tolerance, charge/Gauss error ~ round-off after one implicit step."""
+    d = DECKS[name]
+    o = build_oracle(d)
+    del_t = deck_del_t(d)
+    rho_i = o.get("rho")
+    KE_i = sum(o.getTotalKE(s) for s in range(2))
+    remain, curr = o.solvePotential(del_t, del_t, del_t, 0.0)
+    PE_i = o.getTotalPE(False)
+    KE_f = 0.0
+    for s in range(2):
+        sc = o.species_scalars(s)
+        KE_f += o.getTotalKE(s) + o.lostEnergySum(s) * sc["mass"] * sc["w_p"] * 0.5
+    PE_f = o.getTotalPE(True) - o.getEnergyFromBoundary(curr)
+    st = o.solver_stats()
+    assert st["iterNumPicard"] < d["maxIter"]
+    energy_err = abs((PE_i + KE_i - PE_f - KE_f) / (PE_i + KE_i))
+    assert energy_err < 1e-6, energy_err
+    o.depositRho()
+    gauss = o.getError_tridiag_Poisson()
+    charge = o.getChargeContinuityError(rho_i, curr)
+    assert charge < 1e-6, charge
+    assert gauss < 1e-3, gauss
+    nh = o.norm_history()
+    assert nh[-1] < nh[0]
+
+
+def test_mover_edge_cases_cpu():
+    """absorbed particles still deposit their last partial displacement; Neumann wall reflects; sub-step counts."""
+    o = op.Oracle(op.NGP, 11, 1.0, 0, 0.0, 1, 2, False, 1)
+    o.init_solver(0.0, 0.0)
+    sp = o.add_species(op.m_e, -op.e, 3, 1)
+    o.set_weight(sp, 1.0)
+    ps = o.phase_space(sp)
+    # zero field everywhere is the reference's NaN edge case -> use a tiny uniform field instead
+    phi = np.linspace(0.0, 1e-15, 11)
+    o.set("phi", phi)
+    o.set("phi_f", phi)
+    dt = 1e-3
+    ps[0, 0] = [1.5, -100.0, 1.0, 2.0]      # hits the Dirichlet wall at l = 1 -> absorbed
+    ps[0, 1] = [10.5, 100.0, 0.0, 0.0]      # hits the Neumann wall at l = 11 -> reflected
+    ps[0, 2] = [5.25, 1.0, 0.0, 0.0]        # stays in its cell
+    o.depositJ(dt)
+    J = o.get("J")
+    assert abs(J[0] * dt / (-op.e) - (-0.5)) < 1e-9          # absorbed one deposited 1.5 -> 1.0
+    o.moveParticles(dt)
+    c = o.counters(sp)
+    assert c["delIdx"][0] == 1 and c["wallLoss"][0, 0] == 1 and c["refIdx"][0] == 1
+    assert abs(c["energyLoss"][0, 0] - (100.0 ** 2 + 1 + 4)) < 1e-3
+    assert o.N_p(sp)[0] == 2
+    assert ps[0, 0, 1] < 0 and 10.0 < ps[0, 0, 0] < 11.0     # reflected particle moved to slot 1 (stable compaction), v flipped
+
+
+def test_c_abi_exports_every_header_symbol():
+    hdr = open(os.path.join(ROOT, "include", "ipic1d_b200.h")).read()
+    declared = set(re.findall(r"\b(ipic_[a-z_A-Z0-9]+)\s*\(", hdr))
+    declared.discard("ipic_ctx")
+    L = ip.load_library()
+    from implicitpic1d_b200 import _lib
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(L, name), name
+    out = subprocess.check_output(["nm", "-D", "--defined-only", ip.LIB_PATH]).decode()
+    exported = set(re.findall(r" T (ipic_[a-zA-Z0-9_]+)", out))
+    assert declared <= exported
+
+
+def test_library_is_sm100a_and_has_tma():
+    out = subprocess.run(["cuobjdump", "-lelf", ip.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4ipic6k_pushILi0ELb0EEEvNS_8PushArgsE", ip.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass            # cp.async.bulk (TMA 1-D)
+    assert "REDUX" in sass             # warp-aggregated deposits
+    assert "ATOMS" in sass and "SYNCS" in sass
+
+
+def test_no_gpu_means_loud_failure(gpu_available):
+    if gpu_available:
+        pytest.skip("GPU present")
+    w = readWorld(0, 33, 0.01, 0, 0.0, 1, 1, 0, 2.0, 1e15)
+    with pytest.raises(ip.IpicError):
+        ip.potentialSolver(w, 0.0, 0.0, 0.0, 0.0)
