@@ -264,7 +264,7 @@ int ipic_create(ipic_handle *out, int scheme, int32_t Nx, const double *grid, co
     IPIC_CUDA(cudaMalloc(&c->d_bc, (NM + 2) * sizeof(int))); IPIC_CUDA(cudaMemset(c->d_bc, 0, (NM + 2) * sizeof(int)));
     IPIC_CUDA(cudaMemcpy(c->d_grid, grid, Nx * sizeof(double), cudaMemcpyHostToDevice));
     IPIC_CUDA(cudaMemcpy(c->d_dx, dx_dl, c->ndx * sizeof(double), cudaMemcpyHostToDevice));
-    IPIC_CUDA(cudaMemcpy(c->d_bc, bc, c->nbc * sizeof(int), cudaMemcpyHostToDevice));
+    IPIC_CUDA(cudaMemcpy(c->d_bc + 1, bc, c->nbc * sizeof(int), cudaMemcpyHostToDevice));   // d_bc is indexed 1-based (element 0 is padding)
     RC(dalloc(&c->d_phi, NM)); RC(dalloc(&c->d_phi_f, NM)); RC(dalloc(&c->d_rho, NM)); RC(dalloc(&c->d_J, NM)); RC(dalloc(&c->d_E, NM));
     RC(dalloc(&c->d_a, NM)); RC(dalloc(&c->d_b, NM)); RC(dalloc(&c->d_c, NM)); RC(dalloc(&c->d_cp, NM)); RC(dalloc(&c->d_m, NM));
     RC(dalloc(&c->d_work, std::max<size_t>(8 * NM, 8192))); RC(dalloc(&c->d_rho_i, NM)); RC(dalloc(&c->d_scal, 64));

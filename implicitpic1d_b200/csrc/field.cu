@@ -48,7 +48,7 @@ struct FieldArgs {
 // 1-based accessors so that every stencil reads like the reference line it restates
 #define GRID(i) A.grid[(i)-1]
 #define DX(i) A.dx[(i)-1]
-#define BC(i) A.bc[(i)-1]
+#define BC(i) A.bc[(i)]   /* device bc table is stored 1-based */
 #define PHI(i) A.phi[(i)-1]
 #define PHIF(i) A.phi_f[(i)-1]
 #define RHO(i) A.rho[(i)-1]

@@ -82,7 +82,7 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     // device tables
     double *d_grid = nullptr, *d_dx = nullptr;
-    int *d_bc = nullptr;
+    int *d_bc = nullptr;                                          // boundaryConditions, 1-based (d_bc[k] = bc(k))
     std::vector<double> h_grid, h_dx;
     std::vector<int> h_bc;
     // field vectors (device)

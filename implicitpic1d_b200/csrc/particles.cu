@@ -129,82 +129,110 @@ __device__ __forceinline__ void limb_grid_flush(const LimbGrid &g, int n) {
 }
 
 // =====================================================================================================
-// The push kernel.  One CTA per SM; every warp streams its own chunks of (l, v_x) through a private
-// 3-stage shared-memory ring filled by 1-D bulk async copies (TMA) signalled on warp-private mbarriers,
-// so no inter-warp synchronisation exists in the streaming loop.  Lanes execute exactly one sub-step
-// per loop trip; finished lanes are refilled from the ring once `refill_min` lanes are idle, which
-// bounds warp divergence from the data-dependent sub-step count.
+// The push kernel.  One CTA per SM; every warp owns a CONTIGUOUS range of particles and streams it
+// through a private 3-stage shared-memory ring filled by 1-D bulk async copies (TMA) signalled on
+// warp-private mbarriers, so no inter-warp synchronisation exists in the streaming loop.  Lanes execute
+// exactly one sub-step per loop trip; finished lanes are refilled from the ring once `refill_min` lanes
+// are idle, which bounds warp divergence from the data-dependent sub-step count.
+//
+// Deposition (MOVE == false): every lane owns a private window of WIN int64 fixed-point accumulators in
+// shared memory (cells base-WLO .. base-WLO+WIN-1, `base` warp-uniform = cell of the warp's newest
+// particles; conflict-free layout [k][lane]).  A deposit is a plain 64-bit read-modify-write -- no
+// atomics, no cross-lane traffic -- because cell-sorted particles keep a warp inside a few cells.
+// Deposits outside the window, and the windows themselves when `base` moves on, go to the global int64
+// grid with native RED.ADD.64.  Integer sums make the result independent of all of this bookkeeping.
 //   SCHEME 0: NGP constant-field sub-step   (mod_particleMover.f90:21-63)
 //   SCHEME 1: CIC Picard sub-step           (mod_particleMoverPicard.f90:17-65)
 //   MOVE false: depositJ sweep (no particle writes, J accumulated)   true: moveParticles (write back)
 // =====================================================================================================
+constexpr int WIN = 8, WLO = 3;   // window covers cells base-3 .. base+4
+
+__device__ __forceinline__ void window_flush(unsigned long long *win, int lane, int base, unsigned &dirty, unsigned long long *gacc) {
+    while (dirty) {
+        const int k = __ffs(dirty) - 1;
+        dirty &= dirty - 1;
+        unsigned long long *p = win + k * 32 + lane;
+        const unsigned long long v = *p;
+        *p = 0ull;
+        if (v) atomicAdd(gacc + (base - WLO + k), v);
+    }
+}
+__device__ __forceinline__ void window_add(unsigned long long *win, int lane, int base, unsigned &dirty, unsigned long long *gacc, int cell,
+                                           long long q) {
+    const unsigned k = (unsigned)(cell - base + WLO);
+    if (k < (unsigned)WIN) {
+        unsigned long long *p = win + k * 32 + lane;
+        *p += (unsigned long long)q;
+        dirty |= 1u << k;
+    } else {
+        atomicAdd(gacc + cell, (unsigned long long)q);
+    }
+}
+
 template <int SCHEME, bool MOVE>
 __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // layout: [ring: WARPS x STAGES x 2 x CHUNK doubles][mbar: WARPS x STAGES u64][limb grid]
+    // layout: [ring: WARPS x STAGES x 2 x CHUNK doubles][mbar: WARPS x STAGES u64][windows: WARPS x WIN x 32 u64]
     double *ring = reinterpret_cast<double *>(smem_raw);
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(ring + (size_t)PUSH_WARPS * STAGES * 2 * CHUNK);
-    LimbGrid G;
-    if (!MOVE) {
-        const int ng = A.Nh + 2;
-        G.g0 = reinterpret_cast<unsigned *>(bars + PUSH_WARPS * STAGES);
-        G.g1 = G.g0 + ng;
-        G.g2 = reinterpret_cast<int *>(G.g1 + ng);
-        G.gacc = A.acc;
-        limb_grid_zero(G, ng);
-    }
+    unsigned long long *win = bars + PUSH_WARPS * STAGES + (size_t)warp * WIN * 32;
     double *my_ring = ring + (size_t)warp * STAGES * 2 * CHUNK;
     const unsigned my_bar0 = smem_u32(bars + warp * STAGES);
     if (lane == 0) {
         for (int s = 0; s < STAGES; ++s) mbar_init(my_bar0 + 8u * s, 1);
         fence_barrier_init();
     }
-    __syncthreads();
+    if (!MOVE) {
+#pragma unroll
+        for (int k = 0; k < WIN; ++k) win[k * 32 + lane] = 0ull;
+    }
+    __syncwarp();
 
+    // contiguous chunk range of this warp
     const long long GW = (long long)gridDim.x * PUSH_WARPS;
     const long long gw = (long long)blockIdx.x * PUSH_WARPS + warp;
     const long long nchunks = (A.n + CHUNK - 1) / CHUNK;
+    const long long per = (nchunks + GW - 1) / GW;
+    const long long c_beg = min(gw * per, nchunks), c_end = min(c_beg + per, nchunks);
     constexpr unsigned CH_BYTES = CHUNK * sizeof(double);
 
-    // prologue: put STAGES chunks in flight
+    long long c_issue = c_beg;   // next chunk to put in flight (lane 0 only uses it)
     if (lane == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            const long long ck = gw + (long long)s * GW;
-            if (ck < nchunks) {
-                const unsigned bar = my_bar0 + 8u * s;
-                mbar_expect_tx(bar, 2 * CH_BYTES);
-                bulk_g2s(smem_u32(my_ring + (size_t)s * 2 * CHUNK), A.l + ck * CHUNK, CH_BYTES, bar);
-                bulk_g2s(smem_u32(my_ring + (size_t)s * 2 * CHUNK + CHUNK), A.vx + ck * CHUNK, CH_BYTES, bar);
-            }
+        for (int s = 0; s < STAGES && c_issue < c_end; ++s, ++c_issue) {
+            const unsigned bar = my_bar0 + 8u * s;
+            mbar_expect_tx(bar, 2 * CH_BYTES);
+            bulk_g2s(smem_u32(my_ring + (size_t)s * 2 * CHUNK), A.l + c_issue * CHUNK, CH_BYTES, bar);
+            bulk_g2s(smem_u32(my_ring + (size_t)s * 2 * CHUNK + CHUNK), A.vx + c_issue * CHUNK, CH_BYTES, bar);
         }
     }
     __syncwarp();
 
-    long long kc = 0;          // ordinal of the chunk currently being consumed
-    int pos = 0;               // consumed entries of that chunk
-    bool have_more = gw < nchunks;
+    long long c_cur = c_beg;               // chunk being consumed
+    long long id0 = c_beg * CHUNK;         // global index of its first particle
+    int pos = 0, stage = 0;
+    unsigned parity = 0;
 
     bool active = false, refl = false;
     double l = 0.0, v = 0.0, tp = 0.0;
     int cell = 0;
     long long idx = 0;
-    unsigned nsub = 0, nfev = 0, nabsL = 0, nabsR = 0, nrefl = 0;
+    unsigned nsub = 0, nfev = 0, nabsL = 0, nabsR = 0, nrefl = 0, dirty = 0;
+    int base = 0;
     const double del_t = A.del_t, f_tol = A.f_tol;
 
     while (true) {
         // ---------------- refill idle lanes from the ring ----------------
-        const unsigned idle = __ballot_sync(FULL, !active);
-        if (have_more && __popc(idle) >= A.refill_min) {
-            const int stage = (int)(kc % STAGES);
-            mbar_wait(my_bar0 + 8u * stage, (unsigned)((kc / STAGES) & 1));
+        unsigned idle = __ballot_sync(FULL, !active);
+        if (c_cur < c_end && __popc(idle) >= A.refill_min) {
+            if (pos == 0) mbar_wait(my_bar0 + 8u * stage, parity);
             const int take = min(__popc(idle), CHUNK - pos);
             const int rank = __popc(idle & ((1u << lane) - 1u));
             if (!active && rank < take) {
                 const int slot = pos + rank;
-                const double *st = my_ring + (size_t)stage * 2 * CHUNK;
+                const double *st = my_ring + stage * (2 * CHUNK);
                 const double ll = st[slot], vv = st[CHUNK + slot];
-                const long long id = (gw + kc * GW) * CHUNK + slot;
+                const long long id = id0 + slot;
                 if (id < A.n && ll >= 0.0) {   // l < 0 marks a particle absorbed earlier and not yet compacted
                     l = ll; v = vv; tp = 0.0; idx = id; refl = false;
                     // l_cell = INT(l_sub + SIGN(1.d-12, v_sub))
@@ -213,32 +241,35 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
                 }
             }
             pos += take;
-            if (pos == CHUNK) {   // chunk consumed: reuse its stage for the chunk STAGES ahead
-                __syncwarp();
-                if (lane == 0) {
-                    const long long ck = gw + (kc + STAGES) * GW;
-                    if (ck < nchunks) {
-                        fence_proxy_async();
-                        const unsigned bar = my_bar0 + 8u * stage;
-                        mbar_expect_tx(bar, 2 * CH_BYTES);
-                        bulk_g2s(smem_u32(my_ring + (size_t)stage * 2 * CHUNK), A.l + ck * CHUNK, CH_BYTES, bar);
-                        bulk_g2s(smem_u32(my_ring + (size_t)stage * 2 * CHUNK + CHUNK), A.vx + ck * CHUNK, CH_BYTES, bar);
-                    }
+            if (!MOVE) {
+                // follow the stream: the window is re-centred on the cell of the first particle just loaded
+                const int nb = __shfl_sync(FULL, cell, __ffs(idle) - 1);
+                if (nb != base && nb > 0) {
+                    window_flush(win, lane, base, dirty, A.acc);
+                    base = nb;
                 }
-                kc += 1; pos = 0;
-                have_more = (gw + kc * GW) < nchunks;
             }
+            if (pos == CHUNK) {   // chunk consumed: its stage is refilled with the next chunk of the range
+                __syncwarp();
+                if (lane == 0 && c_issue < c_end) {
+                    fence_proxy_async();
+                    const unsigned bar = my_bar0 + 8u * stage;
+                    mbar_expect_tx(bar, 2 * CH_BYTES);
+                    bulk_g2s(smem_u32(my_ring + stage * (2 * CHUNK)), A.l + c_issue * CHUNK, CH_BYTES, bar);
+                    bulk_g2s(smem_u32(my_ring + stage * (2 * CHUNK) + CHUNK), A.vx + c_issue * CHUNK, CH_BYTES, bar);
+                    ++c_issue;
+                }
+                c_cur += 1; id0 += CHUNK; pos = 0;
+                if (++stage == STAGES) { stage = 0; parity ^= 1u; }
+            }
+            idle = __ballot_sync(FULL, !active);
         }
-        const unsigned act = __ballot_sync(FULL, active);
-        if (act == 0u) {
-            if (!have_more) break;
+        if (idle == FULL) {
+            if (c_cur >= c_end) break;
             continue;
         }
 
         // ---------------- one sub-step for every active lane ----------------
-        bool dep = false;
-        int dcell = 0;
-        long long qa = 0, qb = 0;
         if (active) {
             nsub += 1;
             double l_f, v_f, dtau = del_t - tp;
@@ -249,7 +280,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
                 const double2 t0 = __ldg(tp2), t1 = __ldg(tp2 + 1);
                 const double a = t0.x, inv_dx = t0.y, two_a_dx = t1.x, inv_a = t1.y;
                 v_f = fma(a, dtau, v);
-                l_f = l + 0.5 * (v + v_f) * dtau * inv_dx;
+                l_f = fma(0.5 * (v + v_f) * dtau, inv_dx, l);
                 const bool inCell = ((int)l_f == cell);
                 const bool eqSign = ((v > 0.0) == (v_f > 0.0));
                 atB = (!inCell) || (!eqSign);
@@ -271,7 +302,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
                         atB = false;
                     }
                 }
-                if (!MOVE) { dep = true; dcell = cell; qa = fx_from_double(l_f - l); }
+                if (!MOVE) window_add(win, lane, base, dirty, A.acc, cell, fx_from_double(l_f - l));
             } else {
                 const double2 *tp2 = reinterpret_cast<const double2 *>(reinterpret_cast<const CellTabCIC *>(A.tab) + cell);
                 const double2 t0 = __ldg(tp2), t1 = __ldg(tp2 + 1);
@@ -311,9 +342,8 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
                 if (MOVE) nfev += (unsigned)numIter;
                 if (!MOVE) {
                     const double Jp = l_f - l;
-                    dep = true; dcell = cell;
-                    qa = fx_from_double((1.0 - d_half) * Jp);
-                    qb = fx_from_double(Jp * d_half);
+                    window_add(win, lane, base, dirty, A.acc, cell, fx_from_double((1.0 - d_half) * Jp));
+                    window_add(win, lane, base, dirty, A.acc, cell + 1, fx_from_double(Jp * d_half));
                 }
             }
             bool absorbed = false;
@@ -350,13 +380,10 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
                 l = l_f; v = v_f;
             }
         }
-        if (!MOVE) {
-            if (SCHEME == 0) warp_deposit<2>(G, dep, dcell, qa, lane);
-            else warp_deposit2<2>(G, dep, dcell, qa, qb, lane);
-        }
     }
 
-    // ---------------- epilogue: counters, flush ----------------
+    // ---------------- epilogue: windows, counters ----------------
+    if (!MOVE) window_flush(win, lane, base, dirty, A.acc);
     {
         const unsigned s0 = __reduce_add_sync(FULL, nsub);
         if (lane == 0 && s0) atomicAdd(&A.counters[MOVE ? 5 : 0], (unsigned long long)s0);
@@ -371,15 +398,12 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
             }
         }
     }
-    if (!MOVE) {
-        __syncthreads();
-        limb_grid_flush(G, A.Nh);
-    }
 }
 
 static size_t push_smem_bytes(bool move, int Nh) {
+    (void)Nh;
     size_t s = (size_t)PUSH_WARPS * STAGES * 2 * CHUNK * sizeof(double) + (size_t)PUSH_WARPS * STAGES * 8;
-    if (!move) s += (size_t)3 * (Nh + 2) * 4;
+    if (!move) s += (size_t)PUSH_WARPS * WIN * 32 * 8;
     return s;
 }
 

@@ -41,9 +41,11 @@ elif stage == "perf":
     Nx = int(sys.argv[2]) if len(sys.argv) > 2 else 4097
     N = int(float(sys.argv[3])) if len(sys.argv) > 3 else 20_000_000
     scheme = int(sys.argv[4]) if len(sys.argv) > 4 else 0
-    n_ave, T_e, L_dom = 1.6e16, 4.0, 0.067
-    world = readWorld(scheme, Nx, L_dom, 0, 0.0, 1, 1, 1, T_e, n_ave)
-    solver = ip.potentialSolver(world, 0.0, 0.0, 0.0, 0.0)
+    # default NGP deck (OpenMP/NGP/InputData) with the cell size kept: L = 0.067 m * (Nx-1)/1000
+    n_ave, T_e = 1.6e18, 4.0
+    L_dom = 0.067 * (Nx - 1) / 1000.0
+    world = readWorld(scheme, Nx, L_dom, 0, 0.0, 1, 4, 1, T_e, n_ave)
+    solver = ip.potentialSolver(world, 0.0, 2000.0, 200e6, 0.0)
     L = ip.load_library()
     m_ion = 4.002602 * K.m_amu - K.m_e
     plist = [ip.Particle(K.m_e, -K.e, n_ave * world.L_domain / N, 0, 0, "e", 1), ip.Particle(m_ion, K.e, n_ave * world.L_domain / N, 0, 0, "He+", 1)]
@@ -52,7 +54,7 @@ elif stage == "perf":
     _lib.check(L.ipic_generate_particles(solver._h, 1, N, 0.025, 0.0, 1234))
     ip.initializeSolver(solver, 1e-8, 0.0, 0, 10, 0.5, 100)
     solver.solveInitialPotential(plist, world, 0.0)
-    del_t = K.del_t_from_deck(n_ave, float(sys.argv[5]) if len(sys.argv) > 5 else 1.0, 1.0)
+    del_t = K.del_t_from_deck(n_ave, 10.0, float(sys.argv[5]) if len(sys.argv) > 5 else 2.5e-11)
     print("del_t", del_t, "N per species", N, "Nx", Nx, "scheme", scheme, flush=True)
 
     def timeit(label, reps=5):
@@ -66,7 +68,7 @@ elif stage == "perf":
             t = ms / max(n, 1)
             print("  %-22s %-14s %8.3f ms  %7.1f GB/s  substeps/particle %.3f  %.3e substeps/s" % (label, k, t, N * 16 / t / 1e6, sub / N, sub / t * 1e3), flush=True)
 
-    for rm in (32, 16, 8, 4, 1):
+    for rm in (32, 8):
         solver.set_option("refill_min", rm)
         timeit("unsorted refill_min=%d" % rm)
     t0 = time.time()
@@ -74,7 +76,7 @@ elif stage == "perf":
         _lib.check(L.ipic_sort_particles(solver._h, p._index))
     solver.synchronize()
     print("sort wall s", time.time() - t0, flush=True)
-    for rm in (32, 16, 8, 4, 1):
+    for rm in (32, 16, 8, 4):
         solver.set_option("refill_min", rm)
         timeit("sorted refill_min=%d" % rm)
     solver.set_option("refill_min", 8)
