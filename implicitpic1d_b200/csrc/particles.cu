@@ -130,39 +130,51 @@ __device__ __forceinline__ void limb_grid_flush(const LimbGrid &g, int n) {
 
 // =====================================================================================================
 // The push kernel.  One CTA per SM; every warp owns a CONTIGUOUS range of particles and streams it
-// through a private 3-stage shared-memory ring filled by 1-D bulk async copies (TMA) signalled on
-// warp-private mbarriers, so no inter-warp synchronisation exists in the streaming loop.  Lanes execute
-// exactly one sub-step per loop trip; finished lanes are refilled from the ring once `refill_min` lanes
-// are idle, which bounds warp divergence from the data-dependent sub-step count.
+// through a private shared-memory ring filled by 1-D bulk async copies (TMA) signalled on warp-private
+// mbarriers, so no inter-warp synchronisation exists in the streaming loop.
+//
+// Divergence control: a batch is 32 particles, one per lane, and executes exactly ONE sub-step.  Fresh
+// batches come straight from the ring (lane = slot).  Lanes whose particle must continue (it reached a
+// cell face with time left) push their state into a per-warp shared-memory queue; as soon as the queue
+// holds 32 continuations they are popped and executed as a full batch.  So every sub-step runs with all
+// lanes active, whatever the per-particle sub-step count, and the common single-sub-step particle costs
+// no bookkeeping at all.
 //
 // Deposition (MOVE == false): every lane owns a private window of WIN int64 fixed-point accumulators in
-// shared memory (cells base-WLO .. base-WLO+WIN-1, `base` warp-uniform = cell of the warp's newest
-// particles; conflict-free layout [k][lane]).  A deposit is a plain 64-bit read-modify-write -- no
-// atomics, no cross-lane traffic -- because cell-sorted particles keep a warp inside a few cells.
-// Deposits outside the window, and the windows themselves when `base` moves on, go to the global int64
-// grid with native RED.ADD.64.  Integer sums make the result independent of all of this bookkeeping.
+// shared memory (cells base-WLO .. base-WLO+WIN-1, `base` warp-uniform = cell of the newest fresh batch;
+// conflict-free layout [k][lane]).  A deposit is a plain 64-bit read-modify-write -- no atomics, no
+// cross-lane traffic -- because cell-sorted particles keep a warp inside a few cells.  Deposits outside
+// the window, and the windows themselves when `base` moves on, go to the global int64 grid with native
+// RED.ADD.64.  Integer sums make the result independent of all of this bookkeeping.
 //   SCHEME 0: NGP constant-field sub-step   (mod_particleMover.f90:21-63)
 //   SCHEME 1: CIC Picard sub-step           (mod_particleMoverPicard.f90:17-65)
 //   MOVE false: depositJ sweep (no particle writes, J accumulated)   true: moveParticles (write back)
 // =====================================================================================================
-constexpr int WIN = 8, WLO = 3;   // window covers cells base-3 .. base+4
+constexpr int WIN = 6, WLO = 2;   // window covers cells base-2 .. base+3
+constexpr int QCAP = 64;          // continuation queue entries per warp
 
-__device__ __forceinline__ void window_flush(unsigned long long *win, int lane, int base, unsigned &dirty, unsigned long long *gacc) {
+struct alignas(128) WarpSmem {    // per-warp shared memory (6.6 KB, TMA destinations 128-byte aligned)
+    double ring[STAGES][2][CHUNK];
+    unsigned long long win[WIN][32];
+    double ql[QCAP], qv[QCAP], qt[QCAP];
+    int qcell[QCAP];
+    unsigned qidx[QCAP];          // particle index relative to the warp's range; bit 31 = already reflected
+    unsigned long long bar[STAGES];
+};
+
+__device__ __forceinline__ void window_flush(WarpSmem &W, int lane, int base, unsigned &dirty, unsigned long long *gacc) {
     while (dirty) {
         const int k = __ffs(dirty) - 1;
         dirty &= dirty - 1;
-        unsigned long long *p = win + k * 32 + lane;
-        const unsigned long long v = *p;
-        *p = 0ull;
+        const unsigned long long v = W.win[k][lane];
+        W.win[k][lane] = 0ull;
         if (v) atomicAdd(gacc + (base - WLO + k), v);
     }
 }
-__device__ __forceinline__ void window_add(unsigned long long *win, int lane, int base, unsigned &dirty, unsigned long long *gacc, int cell,
-                                           long long q) {
+__device__ __forceinline__ void window_add(WarpSmem &W, int lane, int base, unsigned &dirty, unsigned long long *gacc, int cell, long long q) {
     const unsigned k = (unsigned)(cell - base + WLO);
     if (k < (unsigned)WIN) {
-        unsigned long long *p = win + k * 32 + lane;
-        *p += (unsigned long long)q;
+        W.win[k][lane] += (unsigned long long)q;
         dirty |= 1u << k;
     } else {
         atomicAdd(gacc + cell, (unsigned long long)q);
@@ -173,19 +185,15 @@ template <int SCHEME, bool MOVE>
 __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // layout: [ring: WARPS x STAGES x 2 x CHUNK doubles][mbar: WARPS x STAGES u64][windows: WARPS x WIN x 32 u64]
-    double *ring = reinterpret_cast<double *>(smem_raw);
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(ring + (size_t)PUSH_WARPS * STAGES * 2 * CHUNK);
-    unsigned long long *win = bars + PUSH_WARPS * STAGES + (size_t)warp * WIN * 32;
-    double *my_ring = ring + (size_t)warp * STAGES * 2 * CHUNK;
-    const unsigned my_bar0 = smem_u32(bars + warp * STAGES);
+    WarpSmem &W = reinterpret_cast<WarpSmem *>(smem_raw)[warp];
+    const unsigned bar0 = smem_u32(&W.bar[0]);
     if (lane == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(my_bar0 + 8u * s, 1);
+        for (int s = 0; s < STAGES; ++s) mbar_init(bar0 + 8u * s, 1);
         fence_barrier_init();
     }
     if (!MOVE) {
 #pragma unroll
-        for (int k = 0; k < WIN; ++k) win[k * 32 + lane] = 0ull;
+        for (int k = 0; k < WIN; ++k) W.win[k][lane] = 0ull;
     }
     __syncwarp();
 
@@ -197,55 +205,55 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
     const long long c_beg = min(gw * per, nchunks), c_end = min(c_beg + per, nchunks);
     constexpr unsigned CH_BYTES = CHUNK * sizeof(double);
 
-    long long c_issue = c_beg;   // next chunk to put in flight (lane 0 only uses it)
+    long long c_issue = c_beg;   // next chunk to put in flight (only lane 0 uses it)
     if (lane == 0) {
         for (int s = 0; s < STAGES && c_issue < c_end; ++s, ++c_issue) {
-            const unsigned bar = my_bar0 + 8u * s;
+            const unsigned bar = bar0 + 8u * s;
             mbar_expect_tx(bar, 2 * CH_BYTES);
-            bulk_g2s(smem_u32(my_ring + (size_t)s * 2 * CHUNK), A.l + c_issue * CHUNK, CH_BYTES, bar);
-            bulk_g2s(smem_u32(my_ring + (size_t)s * 2 * CHUNK + CHUNK), A.vx + c_issue * CHUNK, CH_BYTES, bar);
+            bulk_g2s(smem_u32(&W.ring[s][0][0]), A.l + c_issue * CHUNK, CH_BYTES, bar);
+            bulk_g2s(smem_u32(&W.ring[s][1][0]), A.vx + c_issue * CHUNK, CH_BYTES, bar);
         }
     }
     __syncwarp();
 
-    long long c_cur = c_beg;               // chunk being consumed
-    long long id0 = c_beg * CHUNK;         // global index of its first particle
-    int pos = 0, stage = 0;
-    unsigned parity = 0;
-
-    bool active = false, refl = false;
-    double l = 0.0, v = 0.0, tp = 0.0;
-    int cell = 0;
-    long long idx = 0;
-    unsigned nsub = 0, nfev = 0, nabsL = 0, nabsR = 0, nrefl = 0, dirty = 0;
-    int base = 0;
+    const long long range0 = c_beg * CHUNK;             // first particle of the warp's range
+    const unsigned n_rel = (unsigned)min((long long)0x7fffffff, max(0ll, A.n - range0));   // particles at or after range0
+    unsigned rel0 = 0;                                   // range-relative index of the current chunk's first particle
+    long long c_cur = c_beg;
+    int pos = 0, stage = 0, qcount = 0, base = 0;
+    unsigned parity = 0, dirty = 0;
+    unsigned nsub = 0, nfev = 0, nabsL = 0, nabsR = 0, nrefl = 0;
     const double del_t = A.del_t, f_tol = A.f_tol;
 
-    while (true) {
-        // ---------------- refill idle lanes from the ring ----------------
-        unsigned idle = __ballot_sync(FULL, !active);
-        if (c_cur < c_end && __popc(idle) >= A.refill_min) {
-            if (pos == 0) mbar_wait(my_bar0 + 8u * stage, parity);
-            const int take = min(__popc(idle), CHUNK - pos);
-            const int rank = __popc(idle & ((1u << lane) - 1u));
-            if (!active && rank < take) {
-                const int slot = pos + rank;
-                const double *st = my_ring + stage * (2 * CHUNK);
-                const double ll = st[slot], vv = st[CHUNK + slot];
-                const long long id = id0 + slot;
-                if (id < A.n && ll >= 0.0) {   // l < 0 marks a particle absorbed earlier and not yet compacted
-                    l = ll; v = vv; tp = 0.0; idx = id; refl = false;
-                    // l_cell = INT(l_sub + SIGN(1.d-12, v_sub))
-                    cell = (int)(ll + copysign(1.e-12, vv));
-                    active = true;
-                }
-            }
-            pos += take;
+    bool fresh_left = c_cur < c_end;
+    while (fresh_left || qcount > 0) {
+        // ---------------- assemble one batch: queued continuations first (when full), else fresh ----------------
+        bool valid;
+        double l, v, tp;
+        int cell;
+        unsigned idx;     // range-relative particle index, bit 31 = reflected before
+        if (qcount >= 32 || !fresh_left) {
+            const int take = min(qcount, 32);
+            qcount -= take;
+            valid = lane < take;
+            const int q = qcount + (valid ? lane : 0);
+            l = W.ql[q]; v = W.qv[q]; tp = W.qt[q]; cell = W.qcell[q]; idx = W.qidx[q];
+            __syncwarp();
+        } else {
+            if (pos == 0) mbar_wait(bar0 + 8u * stage, parity);
+            l = W.ring[stage][0][pos + lane];
+            v = W.ring[stage][1][pos + lane];
+            idx = rel0 + pos + lane;
+            tp = 0.0;
+            valid = (idx < n_rel) && (l >= 0.0);        // l < 0 marks a particle absorbed earlier and not yet compacted
+            // l_cell = INT(l_sub + SIGN(1.d-12, v_sub))
+            cell = (int)(l + copysign(1.e-12, v));
+            pos += 32;
             if (!MOVE) {
-                // follow the stream: the window is re-centred on the cell of the first particle just loaded
-                const int nb = __shfl_sync(FULL, cell, __ffs(idle) - 1);
+                // follow the stream: re-centre the window on the cell of the batch's first particle
+                const int nb = __shfl_sync(FULL, cell, 0);
                 if (nb != base && nb > 0) {
-                    window_flush(win, lane, base, dirty, A.acc);
+                    window_flush(W, lane, base, dirty, A.acc);
                     base = nb;
                 }
             }
@@ -253,26 +261,24 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
                 __syncwarp();
                 if (lane == 0 && c_issue < c_end) {
                     fence_proxy_async();
-                    const unsigned bar = my_bar0 + 8u * stage;
+                    const unsigned bar = bar0 + 8u * stage;
                     mbar_expect_tx(bar, 2 * CH_BYTES);
-                    bulk_g2s(smem_u32(my_ring + stage * (2 * CHUNK)), A.l + c_issue * CHUNK, CH_BYTES, bar);
-                    bulk_g2s(smem_u32(my_ring + stage * (2 * CHUNK) + CHUNK), A.vx + c_issue * CHUNK, CH_BYTES, bar);
+                    bulk_g2s(smem_u32(&W.ring[stage][0][0]), A.l + c_issue * CHUNK, CH_BYTES, bar);
+                    bulk_g2s(smem_u32(&W.ring[stage][1][0]), A.vx + c_issue * CHUNK, CH_BYTES, bar);
                     ++c_issue;
                 }
-                c_cur += 1; id0 += CHUNK; pos = 0;
+                c_cur += 1; rel0 += CHUNK; pos = 0;
                 if (++stage == STAGES) { stage = 0; parity ^= 1u; }
+                fresh_left = c_cur < c_end;
             }
-            idle = __ballot_sync(FULL, !active);
-        }
-        if (idle == FULL) {
-            if (c_cur >= c_end) break;
-            continue;
         }
 
-        // ---------------- one sub-step for every active lane ----------------
-        if (active) {
+        // ---------------- one sub-step for every valid lane ----------------
+        bool cont = false;
+        double l_f = 0.0, v_f = 0.0;
+        if (valid) {
             nsub += 1;
-            double l_f, v_f, dtau = del_t - tp;
+            double dtau = del_t - tp;
             bool atB;
             int lb = 0;
             if (SCHEME == 0) {
@@ -302,7 +308,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
                         atB = false;
                     }
                 }
-                if (!MOVE) window_add(win, lane, base, dirty, A.acc, cell, fx_from_double(l_f - l));
+                if (!MOVE) window_add(W, lane, base, dirty, A.acc, cell, fx_from_double(l_f - l));
             } else {
                 const double2 *tp2 = reinterpret_cast<const double2 *>(reinterpret_cast<const CellTabCIC *>(A.tab) + cell);
                 const double2 t0 = __ldg(tp2), t1 = __ldg(tp2 + 1);
@@ -342,8 +348,8 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
                 if (MOVE) nfev += (unsigned)numIter;
                 if (!MOVE) {
                     const double Jp = l_f - l;
-                    window_add(win, lane, base, dirty, A.acc, cell, fx_from_double((1.0 - d_half) * Jp));
-                    window_add(win, lane, base, dirty, A.acc, cell + 1, fx_from_double(Jp * d_half));
+                    window_add(W, lane, base, dirty, A.acc, cell, fx_from_double((1.0 - d_half) * Jp));
+                    window_add(W, lane, base, dirty, A.acc, cell + 1, fx_from_double(Jp * d_half));
                 }
             }
             bool absorbed = false;
@@ -356,7 +362,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
                 } else if (b == 2) {
                     if (lb == A.NB) { if (v_f > 0.0) v_f = -v_f; }
                     else { if (v_f < 0.0) v_f = -v_f; }
-                    if (MOVE && !refl) { refl = true; nrefl += 1; }
+                    if (MOVE && !(idx >> 31)) { idx |= 0x80000000u; nrefl += 1; }
                 } else if (b == 3) {
                     l_f = (double)abs(lb - A.NB - 1);
                     cell = abs(cell - A.NB);
@@ -365,25 +371,38 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
             tp += dtau;
             const double rem = del_t - tp;
             if (absorbed) {
-                active = false;
                 if (MOVE) {
                     // mark for the compaction pass; the wall side is recoverable from the marker
                     const bool left = (lb == 1);
                     if (left) nabsL += 1; else nabsR += 1;
-                    A.l_out[idx] = left ? -1.0 : -2.0;
-                    A.vx_out[idx] = v_f;
+                    const long long gi = range0 + (idx & 0x7fffffffu);
+                    A.l_out[gi] = left ? -1.0 : -2.0;
+                    A.vx_out[gi] = v_f;
                 }
             } else if (!(rem > f_tol)) {
-                active = false;
-                if (MOVE) { A.l_out[idx] = l_f; A.vx_out[idx] = v_f; }
+                if (MOVE) {
+                    const long long gi = range0 + (idx & 0x7fffffffu);
+                    A.l_out[gi] = l_f;
+                    A.vx_out[gi] = v_f;
+                }
             } else {
-                l = l_f; v = v_f;
+                cont = true;
             }
+        }
+        // ---------------- lanes with time left queue their state ----------------
+        const unsigned cm = __ballot_sync(FULL, cont);
+        if (cm) {
+            if (cont) {
+                const int q = qcount + __popc(cm & ((1u << lane) - 1u));
+                W.ql[q] = l_f; W.qv[q] = v_f; W.qt[q] = tp; W.qcell[q] = cell; W.qidx[q] = idx;
+            }
+            qcount += __popc(cm);
+            __syncwarp();
         }
     }
 
     // ---------------- epilogue: windows, counters ----------------
-    if (!MOVE) window_flush(win, lane, base, dirty, A.acc);
+    if (!MOVE) window_flush(W, lane, base, dirty, A.acc);
     {
         const unsigned s0 = __reduce_add_sync(FULL, nsub);
         if (lane == 0 && s0) atomicAdd(&A.counters[MOVE ? 5 : 0], (unsigned long long)s0);
@@ -401,10 +420,8 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
 }
 
 static size_t push_smem_bytes(bool move, int Nh) {
-    (void)Nh;
-    size_t s = (size_t)PUSH_WARPS * STAGES * 2 * CHUNK * sizeof(double) + (size_t)PUSH_WARPS * STAGES * 8;
-    if (!move) s += (size_t)PUSH_WARPS * WIN * 32 * 8;
-    return s;
+    (void)move; (void)Nh;
+    return (size_t)PUSH_WARPS * sizeof(WarpSmem);
 }
 
 template <int SCHEME, bool MOVE>

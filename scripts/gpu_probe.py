@@ -37,7 +37,7 @@ if stage == "parity":
         solver.close()
     print("PARITY PROBE DONE", flush=True)
 
-elif stage == "perf":
+elif stage in ("perf", "prof"):
     Nx = int(sys.argv[2]) if len(sys.argv) > 2 else 4097
     N = int(float(sys.argv[3])) if len(sys.argv) > 3 else 20_000_000
     scheme = int(sys.argv[4]) if len(sys.argv) > 4 else 0
@@ -68,6 +68,14 @@ elif stage == "perf":
             t = ms / max(n, 1)
             print("  %-22s %-14s %8.3f ms  %7.1f GB/s  substeps/particle %.3f  %.3e substeps/s" % (label, k, t, N * 16 / t / 1e6, sub / N, sub / t * 1e3), flush=True)
 
+    if stage == "prof":
+        for pp in plist:
+            _lib.check(L.ipic_sort_particles(solver._h, pp._index))
+        solver.set_option("refill_min", int(sys.argv[6]) if len(sys.argv) > 6 else 32)
+        for _ in range(3):
+            ip.depositJ(solver, plist, world, del_t)
+        solver.synchronize()
+        print("PROF DONE"); sys.exit(0)
     for rm in (32, 8):
         solver.set_option("refill_min", rm)
         timeit("unsorted refill_min=%d" % rm)

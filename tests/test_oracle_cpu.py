@@ -163,7 +163,7 @@ def test_library_is_sm100a_and_has_tma():
     assert "sm_100a" in out
     sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN4ipic6k_pushILi0ELb0EEEvNS_8PushArgsE", ip.LIB_PATH], capture_output=True, text=True).stdout
     assert "UBLKCP" in sass            # cp.async.bulk (TMA 1-D)
-    assert "REDUX" in sass             # warp-aggregated deposits
+    assert "RED.E.ADD.64" in sass      # int64 fixed-point spill to the global grid
     assert "ATOMS" in sass and "SYNCS" in sass
 
 
