@@ -575,6 +575,7 @@ int ipic_set_option(ipic_handle h, const char *name, double value) {
     if (k == "refill_min") c->refill_min = (int)value;
     else if (k == "push_blocks") c->push_blocks = (int)value;
     else if (k == "timing") c->timing_on = value != 0.0;
+    else if (k == "use_tma") c->use_tma = value != 0.0;
     else if (k == "lazy_compaction") c->lazy_compaction = (int)value;
     else { set_error("unknown option " + k); return IPIC_ERR_ARG; }
     return IPIC_OK;

@@ -118,6 +118,7 @@ struct Ctx {
     int refill_min = 8;
     int push_blocks = 0;          // 0 = one CTA per SM
     int lazy_compaction = 0;
+    int use_tma = 1;              // particle streaming: 1 = TMA bulk copies into a per-warp ring, 0 = register-prefetched LDG
     // multi-GPU
     void *nccl_comm = nullptr; int nranks = 1, rank = 0;
     // timing

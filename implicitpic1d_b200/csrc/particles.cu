@@ -181,13 +181,13 @@ __device__ __forceinline__ void window_add(WarpSmem &W, int lane, int base, unsi
     }
 }
 
-template <int SCHEME, bool MOVE>
+template <int SCHEME, bool MOVE, bool TMA>
 __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpSmem &W = reinterpret_cast<WarpSmem *>(smem_raw)[warp];
     const unsigned bar0 = smem_u32(&W.bar[0]);
-    if (lane == 0) {
+    if (TMA && lane == 0) {
         for (int s = 0; s < STAGES; ++s) mbar_init(bar0 + 8u * s, 1);
         fence_barrier_init();
     }
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
     constexpr unsigned CH_BYTES = CHUNK * sizeof(double);
 
     long long c_issue = c_beg;   // next chunk to put in flight (only lane 0 uses it)
-    if (lane == 0) {
+    if (TMA && lane == 0) {
         for (int s = 0; s < STAGES && c_issue < c_end; ++s, ++c_issue) {
             const unsigned bar = bar0 + 8u * s;
             mbar_expect_tx(bar, 2 * CH_BYTES);
@@ -218,14 +218,30 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
 
     const long long range0 = c_beg * CHUNK;             // first particle of the warp's range
     const unsigned n_rel = (unsigned)min((long long)0x7fffffff, max(0ll, A.n - range0));   // particles at or after range0
-    unsigned rel0 = 0;                                   // range-relative index of the current chunk's first particle
+    const unsigned n_rng = (unsigned)((c_end - c_beg) * CHUNK);                              // slots in the warp's range
+    unsigned rel0 = 0;                                   // TMA: range-relative index of the current chunk's first particle
     long long c_cur = c_beg;
     int pos = 0, stage = 0, qcount = 0, base = 0;
     unsigned parity = 0, dirty = 0;
     unsigned nsub = 0, nfev = 0, nabsL = 0, nabsR = 0, nrefl = 0;
     const double del_t = A.del_t, f_tol = A.f_tol;
 
-    bool fresh_left = c_cur < c_end;
+    // !TMA: register-prefetched streaming loads, PF batches ahead (coalesced 256 B per array per warp)
+    constexpr int PF = 3;
+    const double *gl = A.l + range0 + lane, *gv = A.vx + range0 + lane;
+    double pl[PF], pv[PF];
+    unsigned cur = 0;                                    // !TMA: range-relative index of the current batch
+    if (!TMA) {
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            const unsigned o = (unsigned)k * 32u;
+            const bool in = o < n_rng;
+            pl[k] = in ? __ldcs(gl + o) : -1.0;
+            pv[k] = in ? __ldcs(gv + o) : 0.0;
+        }
+    }
+
+    bool fresh_left = TMA ? (c_cur < c_end) : (n_rng > 0);
     while (fresh_left || qcount > 0) {
         // ---------------- assemble one batch: queued continuations first (when full), else fresh ----------------
         bool valid;
@@ -240,15 +256,28 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
             l = W.ql[q]; v = W.qv[q]; tp = W.qt[q]; cell = W.qcell[q]; idx = W.qidx[q];
             __syncwarp();
         } else {
-            if (pos == 0) mbar_wait(bar0 + 8u * stage, parity);
-            l = W.ring[stage][0][pos + lane];
-            v = W.ring[stage][1][pos + lane];
-            idx = rel0 + pos + lane;
+            if (TMA) {
+                if (pos == 0) mbar_wait(bar0 + 8u * stage, parity);
+                l = W.ring[stage][0][pos + lane];
+                v = W.ring[stage][1][pos + lane];
+                idx = rel0 + pos + lane;
+                pos += 32;
+            } else {
+                l = pl[0]; v = pv[0];
+                idx = cur + lane;
+#pragma unroll
+                for (int k = 0; k + 1 < PF; ++k) { pl[k] = pl[k + 1]; pv[k] = pv[k + 1]; }
+                const unsigned o = cur + (unsigned)PF * 32u;
+                const bool in = o < n_rng;
+                pl[PF - 1] = in ? __ldcs(gl + o) : -1.0;
+                pv[PF - 1] = in ? __ldcs(gv + o) : 0.0;
+                cur += 32u;
+                fresh_left = cur < n_rng;
+            }
             tp = 0.0;
             valid = (idx < n_rel) && (l >= 0.0);        // l < 0 marks a particle absorbed earlier and not yet compacted
             // l_cell = INT(l_sub + SIGN(1.d-12, v_sub))
             cell = (int)(l + copysign(1.e-12, v));
-            pos += 32;
             if (!MOVE) {
                 // follow the stream: re-centre the window on the cell of the batch's first particle
                 const int nb = __shfl_sync(FULL, cell, 0);
@@ -257,7 +286,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
                     base = nb;
                 }
             }
-            if (pos == CHUNK) {   // chunk consumed: its stage is refilled with the next chunk of the range
+            if (TMA && pos == CHUNK) {   // chunk consumed: its stage is refilled with the next chunk of the range
                 __syncwarp();
                 if (lane == 0 && c_issue < c_end) {
                     fence_proxy_async();
@@ -424,18 +453,22 @@ static size_t push_smem_bytes(bool move, int Nh) {
     return (size_t)PUSH_WARPS * sizeof(WarpSmem);
 }
 
-template <int SCHEME, bool MOVE>
-static int launch_push_t(Ctx &c, const PushArgs &A) {
+template <int SCHEME, bool MOVE, bool TMA>
+static int launch_push_v(Ctx &c, const PushArgs &A) {
     const size_t smem = push_smem_bytes(MOVE, A.Nh);
-    static size_t configured = 0;
-    if (smem > configured) {
-        IPIC_CUDA(cudaFuncSetAttribute(k_push<SCHEME, MOVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    static bool configured = false;
+    if (!configured) {
+        IPIC_CUDA(cudaFuncSetAttribute(k_push<SCHEME, MOVE, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
     }
     const int blocks = c.push_blocks > 0 ? c.push_blocks : c.num_sms;
-    k_push<SCHEME, MOVE><<<blocks, PUSH_THREADS, smem, c.stream>>>(A);
+    k_push<SCHEME, MOVE, TMA><<<blocks, PUSH_THREADS, smem, c.stream>>>(A);
     IPIC_CUDA(cudaGetLastError());
     return IPIC_OK;
+}
+template <int SCHEME, bool MOVE>
+static int launch_push_t(Ctx &c, const PushArgs &A) {
+    return c.use_tma ? launch_push_v<SCHEME, MOVE, true>(c, A) : launch_push_v<SCHEME, MOVE, false>(c, A);
 }
 
 static PushArgs make_push_args(Ctx &c, int sp, double del_t) {

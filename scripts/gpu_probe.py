@@ -68,29 +68,35 @@ elif stage in ("perf", "prof"):
             t = ms / max(n, 1)
             print("  %-22s %-14s %8.3f ms  %7.1f GB/s  substeps/particle %.3f  %.3e substeps/s" % (label, k, t, N * 16 / t / 1e6, sub / N, sub / t * 1e3), flush=True)
 
+    for pp in plist:
+        _lib.check(L.ipic_sort_particles(solver._h, pp._index))
+    # relax the violent random start: a few implicit steps, then re-sort (steady-state operating point)
+    nwarm = int(sys.argv[7]) if len(sys.argv) > 7 else 3
+    tcur, remain, curr = 0.0, del_t, del_t
+    for k in range(nwarm):
+        remain, curr = ip.solvePotential(solver, plist, world, del_t, remain, curr, tcur)
+        tcur += curr
+        st = ip.SolverState(solver)
+        print("warm step", k, "iters", st.iterNumPicard, "substeps/particle/sweep %.3f" % (st.substeps / (st.sweeps + 1) / (2 * N)), "norm0 %.3e" % st.normHistory[0], flush=True)
+    for pp in plist:
+        _lib.check(L.ipic_sort_particles(solver._h, pp._index))
     if stage == "prof":
-        for pp in plist:
-            _lib.check(L.ipic_sort_particles(solver._h, pp._index))
-        solver.set_option("refill_min", int(sys.argv[6]) if len(sys.argv) > 6 else 32)
-        for _ in range(3):
-            ip.depositJ(solver, plist, world, del_t)
+        solver.set_option("use_tma", int(sys.argv[6]) if len(sys.argv) > 6 else 1)
+        ip.depositJ(solver, plist, world, del_t)
         solver.synchronize()
+        cu = C.CDLL("libcuda.so.1")
+        cu.cuProfilerStart()            # run ncu with --profile-from-start off
+        ip.depositJ(solver, plist, world, del_t)
+        solver.synchronize()
+        cu.cuProfilerStop()
         print("PROF DONE"); sys.exit(0)
-    for rm in (32, 8):
-        solver.set_option("refill_min", rm)
-        timeit("unsorted refill_min=%d" % rm)
-    t0 = time.time()
-    for p in plist:
-        _lib.check(L.ipic_sort_particles(solver._h, p._index))
-    solver.synchronize()
-    print("sort wall s", time.time() - t0, flush=True)
-    for rm in (32, 16, 8, 4):
-        solver.set_option("refill_min", rm)
-        timeit("sorted refill_min=%d" % rm)
-    solver.set_option("refill_min", 8)
+    for tma in (1, 0):
+        solver.set_option("use_tma", tma)
+        timeit("sorted use_tma=%d" % tma)
+    solver.set_option("use_tma", int(sys.argv[6]) if len(sys.argv) > 6 else 1)
     solver.reset_timing()
     t0 = time.time()
-    r, c = ip.solvePotential(solver, plist, world, del_t, del_t, del_t, 0.0)
+    r, c = ip.solvePotential(solver, plist, world, del_t, remain, curr, tcur)
     solver.synchronize()
     wall = time.time() - t0
     st = ip.SolverState(solver)
