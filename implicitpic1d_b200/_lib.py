@@ -80,6 +80,10 @@ SIGNATURES = {
     "ipic_nccl_unique_id": (_i, [_p]),
     "ipic_comm_init": (_i, [_p, _i32, _i32, _p]),
     "ipic_set_option": (_i, [_p, C.c_char_p, _d]),
+    "ipic_set_stream": (_i, [_p, _p]),
+    "ipic_get_launch_count": (_i, [_p, C.POINTER(_i64)]),
+    "ipic_host_alloc": (_i, [C.POINTER(_p), C.c_uint64]),
+    "ipic_host_free": (_i, [_p]),
     "ipic_get_timing": (_i, [_p, C.c_char_p, _dp, C.POINTER(_i64)]),
     "ipic_reset_timing": (_i, [_p]),
     "ipic_synchronize": (_i, [_p]),

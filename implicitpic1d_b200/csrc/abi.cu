@@ -257,7 +257,8 @@ int ipic_create(ipic_handle *out, int scheme, int32_t Nx, const double *grid, co
     c->h_grid.assign(grid, grid + Nx); c->h_dx.assign(dx_dl, dx_dl + c->ndx); c->h_bc.assign(bc, bc + c->nbc);
     cudaDeviceProp prop; IPIC_CUDA(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
-    IPIC_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    IPIC_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
     const size_t NM = (size_t)std::max(Nx, c->Nh) + 2;
     auto dalloc = [&](double **p, size_t n) -> int { IPIC_CUDA(cudaMalloc(p, n * sizeof(double))); IPIC_CUDA(cudaMemset(*p, 0, n * sizeof(double))); return IPIC_OK; };
     RC(dalloc(&c->d_grid, NM)); RC(dalloc(&c->d_dx, NM));
@@ -301,7 +302,7 @@ int ipic_destroy(ipic_handle h) {
     if (c->d_slab) cudaFree(c->d_slab);
     if (c->h_scal) cudaFreeHost(c->h_scal);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
-    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->own_stream);
     delete c;
     return IPIC_OK;
 }
@@ -580,6 +581,20 @@ int ipic_set_option(ipic_handle h, const char *name, double value) {
     else { set_error("unknown option " + k); return IPIC_ERR_ARG; }
     return IPIC_OK;
 }
+int ipic_set_stream(ipic_handle h, void *cuda_stream) {
+    CTX(h);
+    IPIC_CUDA(cudaStreamSynchronize(c->stream));
+    resolve_timing(*c);
+    c->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    return IPIC_OK;
+}
+int ipic_get_launch_count(ipic_handle h, int64_t *n) { CTX(h); if (!n) return IPIC_ERR_ARG; *n = c->launches; return IPIC_OK; }
+int ipic_host_alloc(void **out, uint64_t bytes) {
+    if (!out) return IPIC_ERR_ARG;
+    IPIC_CUDA(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable));
+    return IPIC_OK;
+}
+int ipic_host_free(void *p) { if (p) IPIC_CUDA(cudaFreeHost(p)); return IPIC_OK; }
 int ipic_get_timing(ipic_handle h, const char *name, double *ms, int64_t *launches) {
     CTX(h);
     resolve_timing(*c);

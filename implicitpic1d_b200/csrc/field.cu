@@ -623,7 +623,7 @@ static int run_field(Ctx &c, const FieldArgs &A, unsigned ops) {
         IPIC_CUDA(cudaFuncSetAttribute(k_field, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    k_field<<<1, FT, smem, c.stream>>>(A, ops);
+    c.launches += 1; k_field<<<1, FT, smem, c.stream>>>(A, ops);
     IPIC_CUDA(cudaGetLastError());
     return IPIC_OK;
 }

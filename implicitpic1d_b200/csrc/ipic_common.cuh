@@ -79,7 +79,8 @@ struct Timing { double ms = 0; long long launches = 0; };
 
 struct Ctx {
     int scheme = 0, Nx = 0, Nh = 0, nbc = 0, ndx = 0, smooth = 0, device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    long long launches = 0;                                       // kernels launched by this context
     // device tables
     double *d_grid = nullptr, *d_dx = nullptr;
     int *d_bc = nullptr;                                          // boundaryConditions, 1-based (d_bc[k] = bc(k))

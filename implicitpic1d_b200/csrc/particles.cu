@@ -462,7 +462,7 @@ static int launch_push_v(Ctx &c, const PushArgs &A) {
         configured = true;
     }
     const int blocks = c.push_blocks > 0 ? c.push_blocks : c.num_sms;
-    k_push<SCHEME, MOVE, TMA><<<blocks, PUSH_THREADS, smem, c.stream>>>(A);
+    c.launches += 1; k_push<SCHEME, MOVE, TMA><<<blocks, PUSH_THREADS, smem, c.stream>>>(A);
     IPIC_CUDA(cudaGetLastError());
     return IPIC_OK;
 }
@@ -566,10 +566,10 @@ int launch_deposit_rho(Ctx &c, int sp) {
     static bool cfg0 = false, cfg1 = false;
     if (c.scheme == IPIC_SCHEME_NGP) {
         if (!cfg0) { IPIC_CUDA(cudaFuncSetAttribute(k_deposit_rho<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (MAX_GRID_SMEM + 2) * 4)); cfg0 = true; }
-        k_deposit_rho<0><<<c.num_sms, 1024, smem, c.stream>>>(s.l, s.n, c.d_bc, c.Nx, acc);
+        c.launches += 1; k_deposit_rho<0><<<c.num_sms, 1024, smem, c.stream>>>(s.l, s.n, c.d_bc, c.Nx, acc);
     } else {
         if (!cfg1) { IPIC_CUDA(cudaFuncSetAttribute(k_deposit_rho<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (MAX_GRID_SMEM + 2) * 4)); cfg1 = true; }
-        k_deposit_rho<1><<<c.num_sms, 1024, smem, c.stream>>>(s.l, s.n, c.d_bc, c.Nx, acc);
+        c.launches += 1; k_deposit_rho<1><<<c.num_sms, 1024, smem, c.stream>>>(s.l, s.n, c.d_bc, c.Nx, acc);
     }
     IPIC_CUDA(cudaGetLastError());
     return IPIC_OK;
@@ -624,8 +624,8 @@ __global__ void k_final_sum(const double *partial, int nblocks, double *out) {
 int particle_moments(Ctx &c, int sp, double out4[4]) {
     SpeciesDev &s = c.sp[sp];
     double *partial = c.d_work;   // needs RED_BLOCKS*4 doubles: allocated with slack in ipic_create
-    k_moments<<<RED_BLOCKS, RED_THREADS, 0, c.stream>>>(s.l, s.vx, s.vy, s.vz, s.n, partial);
-    k_final_sum<4><<<1, 32, 0, c.stream>>>(partial, RED_BLOCKS, c.d_scal);
+    c.launches += 1; k_moments<<<RED_BLOCKS, RED_THREADS, 0, c.stream>>>(s.l, s.vx, s.vy, s.vz, s.n, partial);
+    c.launches += 1; k_final_sum<4><<<1, 32, 0, c.stream>>>(partial, RED_BLOCKS, c.d_scal);
     IPIC_CUDA(cudaGetLastError());
     IPIC_CUDA(cudaMemcpyAsync(c.h_scal, c.d_scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     IPIC_CUDA(cudaStreamSynchronize(c.stream));
@@ -791,9 +791,9 @@ int compact_species(Ctx &c, int sp) {
     }
     unsigned *d_tileCount = c.d_tileCount; long long *d_tileOffset = c.d_tileOffset; double *d_loss = c.d_loss;
     long long *d_total = c.d_total; long long *d_slab = c.d_slab; const int cap_slab = c.cap_slab;
-    k_compact_count<<<(unsigned)ntiles, CT_THREADS, 0, c.stream>>>(s.l, s.vx, s.vy, s.vz, n, d_tileCount, d_loss);
-    k_scan_tiles<<<1, 1024, 0, c.stream>>>(d_tileCount, ntiles, d_tileOffset, d_total);
-    k_final_sum<4><<<1, 32, 0, c.stream>>>(d_loss, (int)ntiles, c.d_scal);
+    c.launches += 1; k_compact_count<<<(unsigned)ntiles, CT_THREADS, 0, c.stream>>>(s.l, s.vx, s.vy, s.vz, n, d_tileCount, d_loss);
+    c.launches += 1; k_scan_tiles<<<1, 1024, 0, c.stream>>>(d_tileCount, ntiles, d_tileOffset, d_total);
+    c.launches += 1; k_final_sum<4><<<1, 32, 0, c.stream>>>(d_loss, (int)ntiles, c.d_scal);
     IPIC_CUDA(cudaGetLastError());
     long long total = 0;
     IPIC_CUDA(cudaMemcpyAsync(&total, d_total, sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
@@ -804,9 +804,9 @@ int compact_species(Ctx &c, int sp) {
     if (total == n) return IPIC_OK;   // nothing absorbed: arrays already compact
     if (nb > 0) {
         IPIC_CUDA(cudaMemcpyAsync(d_slab, s.slab_off.data(), nb * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
-        k_slab_offsets<<<(nb + 7) / 8, 256, 0, c.stream>>>(s.l, d_tileOffset, d_slab, d_slab + cap_slab, nb, n);
+        c.launches += 1; k_slab_offsets<<<(nb + 7) / 8, 256, 0, c.stream>>>(s.l, d_tileOffset, d_slab, d_slab + cap_slab, nb, n);
     }
-    k_compact_scatter<<<(unsigned)ntiles, CT_THREADS, 0, c.stream>>>(s.l, s.vx, s.vy, s.vz, n, d_tileOffset, s.l2, s.vx2, s.vy2, s.vz2);
+    c.launches += 1; k_compact_scatter<<<(unsigned)ntiles, CT_THREADS, 0, c.stream>>>(s.l, s.vx, s.vy, s.vz, n, d_tileOffset, s.l2, s.vx2, s.vy2, s.vz2);
     IPIC_CUDA(cudaGetLastError());
     if (nb > 0) IPIC_CUDA(cudaMemcpyAsync(s.slab_off.data(), d_slab + cap_slab, nb * sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
     IPIC_CUDA(cudaStreamSynchronize(c.stream));
@@ -854,7 +854,7 @@ int upload_species(Ctx &c, int sp, const double *ps, const int32_t *N_p, int T, 
     s.slab_off[T] = off;
     s.n = n;
     if (n > 0) {
-        k_aos_to_soa<<<c.num_sms * 4, 256, 0, c.stream>>>(reinterpret_cast<const double4 *>(stage), n, s.l, s.vx, s.vy, s.vz);
+        c.launches += 1; k_aos_to_soa<<<c.num_sms * 4, 256, 0, c.stream>>>(reinterpret_cast<const double4 *>(stage), n, s.l, s.vx, s.vy, s.vz);
         IPIC_CUDA(cudaGetLastError());
     }
     IPIC_CUDA(cudaStreamSynchronize(c.stream));
@@ -870,7 +870,7 @@ int download_species(Ctx &c, int sp, double *ps, int32_t *N_p, int T, int finalI
     }
     double *stage = s.l2;
     if (s.n > 0) {
-        k_soa_to_aos<<<c.num_sms * 4, 256, 0, c.stream>>>(reinterpret_cast<double4 *>(stage), s.n, s.l, s.vx, s.vy, s.vz);
+        c.launches += 1; k_soa_to_aos<<<c.num_sms * 4, 256, 0, c.stream>>>(reinterpret_cast<double4 *>(stage), s.n, s.l, s.vx, s.vy, s.vz);
         IPIC_CUDA(cudaGetLastError());
     }
     for (int t = 0; t < T; ++t) {
@@ -943,7 +943,7 @@ int generate_species(Ctx &c, int sp, long long n, double T_eV, double v_drift, u
     else { startX = c.h_grid[0] - 0.5 * c.h_dx[0]; L = c.h_grid[c.Nx - 1] + 0.5 * c.h_dx[c.Nx - 1] - startX; }
     const double v_therm = sqrt(T_eV * e_c / s.mass);
     const long long first = (long long)c.rank * n;   // ranks draw disjoint index ranges of one global stream
-    k_generate<<<c.num_sms * 8, 256, 0, c.stream>>>(s.l, s.vx, s.vy, s.vz, n, first, c.d_grid, c.d_dx, c.Nx, c.scheme, startX, L, v_therm, v_drift,
+    c.launches += 1; k_generate<<<c.num_sms * 8, 256, 0, c.stream>>>(s.l, s.vx, s.vy, s.vz, n, first, c.d_grid, c.d_dx, c.Nx, c.scheme, startX, L, v_therm, v_drift,
                                                      seed + 0x1000003ULL * (unsigned long long)sp);
     IPIC_CUDA(cudaGetLastError());
     s.n = n;
@@ -981,13 +981,13 @@ int sort_species(Ctx &c, int sp) {
     void *tmp = nullptr; size_t tmp_bytes = 0;
     IPIC_CUDA(cudaMalloc(&keys, n * 4)); IPIC_CUDA(cudaMalloc(&keys2, n * 4));
     IPIC_CUDA(cudaMalloc(&vals, n * 4)); IPIC_CUDA(cudaMalloc(&vals2, n * 4));
-    k_sort_keys<<<c.num_sms * 8, 256, 0, c.stream>>>(s.l, n, keys, vals);
+    c.launches += 1; k_sort_keys<<<c.num_sms * 8, 256, 0, c.stream>>>(s.l, n, keys, vals);
     int bits = 1; while ((1 << bits) <= std::max(c.Nx, c.Nh) + 1) ++bits;
     bits = std::max(bits, 16);
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, vals, vals2, (int)n, 0, bits, c.stream);
     IPIC_CUDA(cudaMalloc(&tmp, tmp_bytes));
-    cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, vals2, (int)n, 0, bits, c.stream);
-    k_gather4<<<c.num_sms * 8, 256, 0, c.stream>>>(vals2, n, s.l, s.vx, s.vy, s.vz, s.l2, s.vx2, s.vy2, s.vz2);
+    c.launches += 1; cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, vals2, (int)n, 0, bits, c.stream);
+    c.launches += 1; k_gather4<<<c.num_sms * 8, 256, 0, c.stream>>>(vals2, n, s.l, s.vx, s.vy, s.vz, s.l2, s.vx2, s.vy2, s.vz2);
     IPIC_CUDA(cudaGetLastError());
     IPIC_CUDA(cudaStreamSynchronize(c.stream));
     cudaFree(keys); cudaFree(keys2); cudaFree(vals); cudaFree(vals2); cudaFree(tmp);

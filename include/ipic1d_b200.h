@@ -180,6 +180,15 @@ int ipic_comm_init(ipic_handle h, int32_t nranks, int32_t rank, const void *uniq
 
 /* ---- tuning / introspection ----------------------------------------------------*/
 int ipic_set_option(ipic_handle h, const char *name, double value);
+/* run all kernels of this context on a caller-owned CUDA stream (cudaStream_t passed as void*), e.g. the
+ * host program's / torch's current stream; NULL restores the context's own stream. */
+int ipic_set_stream(ipic_handle h, void *cuda_stream);
+/* kernels launched by this context since creation (cub sort passes count as one each) */
+int ipic_get_launch_count(ipic_handle h, int64_t *n);
+/* page-locked host buffers for phaseSpace so that upload/download run at full PCIe rate; a Fortran host
+ * maps them with c_f_pointer.  Plain (pageable) memory works too, only slower. */
+int ipic_host_alloc(void **out, uint64_t bytes);
+int ipic_host_free(void *p);
 int ipic_get_timing(ipic_handle h, const char *name, double *ms, int64_t *launches);
 int ipic_reset_timing(ipic_handle h);
 int ipic_synchronize(ipic_handle h);
