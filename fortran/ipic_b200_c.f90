@@ -1,0 +1,212 @@
+! =============================================================================
+! ipic_b200_c.f90 -- ISO_C_BINDING interface to libipic1d_b200.so (include/ipic1d_b200.h)
+!
+! Reference-side binding a maintainer of nsavard01/ImplicitPic1D adds to
+! OpenMP/SharedModules/src/ (listed before mod_particleMover.o in the Makefile) and links with
+!     -L<repo>/implicitpic1d_b200/lib -lipic1d_b200 -Wl,-rpath,<repo>/implicitpic1d_b200/lib
+! Precedent in the reference for Fortran -> C calls: pcg32_random_r, bind(c)
+! (PIC1D/SharedModules/src/mod_BasicFunctions.f90:13-19).
+!
+! NOTE: this container has no Fortran compiler (SURVEY.md section 0), so this file is exercised
+! only through its C twin: tests/test_c_abi_host.py drives the same entry points in the same
+! order from C (tests/c_host/host_driver.c).
+! =============================================================================
+module ipic_b200_c
+    use iso_c_binding
+    implicit none
+    public
+
+    integer(c_int), parameter :: IPIC_SCHEME_NGP = 0, IPIC_SCHEME_CIC = 1, IPIC_SCHEME_NGP_PERIODIC = 2
+    integer(c_int), parameter :: IPIC_F_PHI = 0, IPIC_F_PHI_F = 1, IPIC_F_J = 2, IPIC_F_RHO = 3, IPIC_F_EFIELD = 4
+    integer(c_int), parameter :: IPIC_TRIDIAG_PCR = 0, IPIC_TRIDIAG_THOMAS = 1
+
+    type, bind(c) :: ipic_move_stats
+        integer(c_int64_t) :: N_p, delIdx, refIdx, numSubSteps, numFuncEvals
+        real(c_double) :: numSubStepsAve, numFuncEvalAve
+        real(c_double) :: wallLoss(2), energyLoss(2), momentumLoss(2), accumEnergyLoss(2)
+        integer(c_int64_t) :: accumWallLoss(2)
+    end type ipic_move_stats
+
+    type, bind(c) :: ipic_solver_stats
+        integer(c_int32_t) :: iterNumPicard, iterNumAdaptiveSteps, amountTimeSplits
+        integer(c_int64_t) :: sweeps, substeps
+        real(c_double) :: moverSeconds, potSeconds, lastResidualNorm
+    end type ipic_solver_stats
+
+    interface
+        function ipic_last_error() bind(c, name="ipic_last_error") result(msg)
+            import :: c_ptr
+            type(c_ptr) :: msg
+        end function
+        function ipic_create(handle, scheme, NumberXNodes, grid, dx_dl, boundaryConditions, gridSmoothBool, device) &
+                bind(c, name="ipic_create") result(rc)
+            import :: c_ptr, c_int, c_int32_t, c_double
+            type(c_ptr), intent(out) :: handle
+            integer(c_int), value :: scheme, gridSmoothBool, device
+            integer(c_int32_t), value :: NumberXNodes
+            real(c_double), intent(in) :: grid(*), dx_dl(*)
+            integer(c_int32_t), intent(in) :: boundaryConditions(*)
+            integer(c_int) :: rc
+        end function
+        function ipic_destroy(handle) bind(c, name="ipic_destroy") result(rc)
+            import :: c_ptr, c_int
+            type(c_ptr), value :: handle
+            integer(c_int) :: rc
+        end function
+        function ipic_init_solver(handle, leftVoltage, rightVoltage, RF_frequency, timeCurrent) bind(c, name="ipic_init_solver") result(rc)
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value :: handle
+            real(c_double), value :: leftVoltage, rightVoltage, RF_frequency, timeCurrent
+            integer(c_int) :: rc
+        end function
+        function ipic_set_tridiag_mode(handle, mode) bind(c, name="ipic_set_tridiag_mode") result(rc)
+            import :: c_ptr, c_int
+            type(c_ptr), value :: handle
+            integer(c_int), value :: mode
+            integer(c_int) :: rc
+        end function
+        function ipic_add_species(handle, mass, q, w_p, species) bind(c, name="ipic_add_species") result(rc)
+            import :: c_ptr, c_int, c_int32_t, c_double
+            type(c_ptr), value :: handle
+            real(c_double), value :: mass, q, w_p
+            integer(c_int32_t), intent(out) :: species
+            integer(c_int) :: rc
+        end function
+        function ipic_set_weight(handle, species, w_p) bind(c, name="ipic_set_weight") result(rc)
+            import :: c_ptr, c_int, c_int32_t, c_double
+            type(c_ptr), value :: handle
+            integer(c_int32_t), value :: species
+            real(c_double), value :: w_p
+            integer(c_int) :: rc
+        end function
+        function ipic_upload_particles(handle, species, phaseSpace, N_p, numThread, finalIdx) bind(c, name="ipic_upload_particles") result(rc)
+            import :: c_ptr, c_int, c_int32_t, c_double
+            type(c_ptr), value :: handle
+            integer(c_int32_t), value :: species, numThread, finalIdx
+            real(c_double), intent(in) :: phaseSpace(4, finalIdx, numThread)
+            integer(c_int32_t), intent(in) :: N_p(numThread)
+            integer(c_int) :: rc
+        end function
+        function ipic_download_particles(handle, species, phaseSpace, N_p, numThread, finalIdx) bind(c, name="ipic_download_particles") result(rc)
+            import :: c_ptr, c_int, c_int32_t, c_double
+            type(c_ptr), value :: handle
+            integer(c_int32_t), value :: species, numThread, finalIdx
+            real(c_double), intent(in out) :: phaseSpace(4, finalIdx, numThread)
+            integer(c_int32_t), intent(out) :: N_p(numThread)
+            integer(c_int) :: rc
+        end function
+        function ipic_get_field(handle, which, out, n) bind(c, name="ipic_get_field") result(rc)
+            import :: c_ptr, c_int, c_int32_t, c_double
+            type(c_ptr), value :: handle
+            integer(c_int), value :: which
+            integer(c_int32_t), value :: n
+            real(c_double), intent(out) :: out(*)
+            integer(c_int) :: rc
+        end function
+        function ipic_set_field(handle, which, vals, n) bind(c, name="ipic_set_field") result(rc)
+            import :: c_ptr, c_int, c_int32_t, c_double
+            type(c_ptr), value :: handle
+            integer(c_int), value :: which
+            integer(c_int32_t), value :: n
+            real(c_double), intent(in) :: vals(*)
+            integer(c_int) :: rc
+        end function
+        function ipic_deposit_rho(handle) bind(c, name="ipic_deposit_rho") result(rc)
+            import :: c_ptr, c_int
+            type(c_ptr), value :: handle
+            integer(c_int) :: rc
+        end function
+        function ipic_solve_tridiag_poisson(handle, timeCurrent) bind(c, name="ipic_solve_tridiag_poisson") result(rc)
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value :: handle
+            real(c_double), value :: timeCurrent
+            integer(c_int) :: rc
+        end function
+        function ipic_make_const_source_term(handle) bind(c, name="ipic_make_const_source_term") result(rc)
+            import :: c_ptr, c_int
+            type(c_ptr), value :: handle
+            integer(c_int) :: rc
+        end function
+        function ipic_solve_tridiag_ampere(handle, del_t) bind(c, name="ipic_solve_tridiag_ampere") result(rc)
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value :: handle
+            real(c_double), value :: del_t
+            integer(c_int) :: rc
+        end function
+        function ipic_set_rf_voltage(handle, timeFuture) bind(c, name="ipic_set_rf_voltage") result(rc)
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value :: handle
+            real(c_double), value :: timeFuture
+            integer(c_int) :: rc
+        end function
+        function ipic_deposit_J(handle, del_t) bind(c, name="ipic_deposit_J") result(rc)
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value :: handle
+            real(c_double), value :: del_t
+            integer(c_int) :: rc
+        end function
+        function ipic_move_particles(handle, del_t) bind(c, name="ipic_move_particles") result(rc)
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value :: handle
+            real(c_double), value :: del_t
+            integer(c_int) :: rc
+        end function
+        function ipic_get_move_stats(handle, species, stats) bind(c, name="ipic_get_move_stats") result(rc)
+            import :: c_ptr, c_int, c_int32_t, ipic_move_stats
+            type(c_ptr), value :: handle
+            integer(c_int32_t), value :: species
+            type(ipic_move_stats), intent(out) :: stats
+            integer(c_int) :: rc
+        end function
+        function ipic_initialize_solver(handle, eps_a, eps_r, solverType, m_Anderson, Beta_k, maxIter) &
+                bind(c, name="ipic_initialize_solver") result(rc)
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value :: handle
+            real(c_double), value :: eps_a, eps_r, Beta_k
+            integer(c_int), value :: solverType, m_Anderson, maxIter
+            integer(c_int) :: rc
+        end function
+        function ipic_solve_potential(handle, del_t, remainDel_t, currDel_t, timeCurrent) bind(c, name="ipic_solve_potential") result(rc)
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value :: handle
+            real(c_double), value :: del_t, timeCurrent
+            real(c_double), intent(in out) :: remainDel_t, currDel_t
+            integer(c_int) :: rc
+        end function
+        function ipic_func_nitsol(handle, n, xcur, fcur, del_t) bind(c, name="ipic_func_nitsol") result(rc)
+            import :: c_ptr, c_int, c_int32_t, c_double
+            type(c_ptr), value :: handle
+            integer(c_int32_t), value :: n
+            real(c_double), intent(in) :: xcur(n)
+            real(c_double), intent(out) :: fcur(n)
+            real(c_double), value :: del_t
+            integer(c_int) :: rc
+        end function
+        function ipic_get_solver_stats(handle, stats) bind(c, name="ipic_get_solver_stats") result(rc)
+            import :: c_ptr, c_int, ipic_solver_stats
+            type(c_ptr), value :: handle
+            type(ipic_solver_stats), intent(out) :: stats
+            integer(c_int) :: rc
+        end function
+    end interface
+
+contains
+
+    subroutine ipic_check(rc, where)
+        ! the reference's only error behaviour is `print *, ...; stop` (e.g. mod_nonLinSolvers.f90:186)
+        integer(c_int), intent(in) :: rc
+        character(len=*), intent(in) :: where
+        character(kind=c_char), pointer :: cmsg(:)
+        integer :: k
+        if (rc /= 0) then
+            print *, 'ipic1d_b200 error ', rc, ' in ', where
+            call c_f_pointer(ipic_last_error(), cmsg, [512])
+            do k = 1, 512
+                if (cmsg(k) == c_null_char) exit
+            end do
+            print *, cmsg(1:k-1)
+            stop
+        end if
+    end subroutine ipic_check
+
+end module ipic_b200_c

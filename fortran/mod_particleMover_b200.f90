@@ -1,0 +1,112 @@
+! =============================================================================
+! mod_particleMover_b200.f90 -- drop-in replacement of
+!     OpenMP/NGP/src/mod_particleMover.f90           (scheme 0)
+!     OpenMP/CIC/src/mod_particleMoverPicard.f90     (scheme 1; the file the CIC Makefile compiles as mod_particleMover.o)
+! Same module name, same public procedures and argument lists (NGP :17,67-74,162-167 ; CIC :67-70,77-84,198-203), so
+! mod_nonLinSolvers / mod_simulation / main keep compiling unchanged.  The bodies call the C ABI (include/ipic1d_b200.h).
+!
+! Residency protocol (level-1 integration, see INTEGRATION.md): the host keeps owning particleList and solver.  Particles are
+! uploaded at the first depositJ after the host may have touched them (start of a step: collisions / injection happen on the
+! host between steps) and downloaded by moveParticles; phi, phi_f and rho (8 B x N_x each) go up and J (and phi_f) come back on
+! every call.  Build with -DIPIC_SCHEME=0 (NGP tree) or 1 (CIC tree).
+! =============================================================================
+module mod_particleMover
+    use iso_fortran_env, only: int32, real64
+    use iso_c_binding
+    use constants
+    use mod_particle
+    use mod_domain
+    use mod_potentialSolver
+    use ipic_b200_c
+    implicit none
+#ifndef IPIC_SCHEME
+#define IPIC_SCHEME 0
+#endif
+    type(c_ptr), private :: ipic_h = c_null_ptr
+    logical, private :: particlesOnDevice = .false.
+
+contains
+
+    subroutine allocateParticleMoverData()
+        ! NGP: no-op (:17-19).  CIC allocated particleTimeStep here (:67-70); the per-cell cap table now lives on the device.
+    end subroutine allocateParticleMoverData
+
+    subroutine ipic_attach(solver, particleList, world)
+        class(potentialSolver), intent(in) :: solver
+        type(Domain), intent(in) :: world
+        type(Particle), intent(in) :: particleList(:)
+        integer(c_int32_t) :: sp
+        integer :: j
+        if (c_associated(ipic_h)) return
+        call ipic_check(ipic_create(ipic_h, IPIC_SCHEME, NumberXNodes, world%grid, world%dx_dl, world%boundaryConditions, &
+            merge(1_c_int, 0_c_int, world%gridSmoothBool), 0_c_int), 'ipic_create')
+        ! voltages are carried by phi / phi_f (NGP) and set again by the host through setRFVoltage; 0 here
+        call ipic_check(ipic_init_solver(ipic_h, 0.0_c_double, 0.0_c_double, solver%RF_rad_frequency / (2.0d0 * pi), 0.0_c_double), 'ipic_init_solver')
+        do j = 1, size(particleList)
+            call ipic_check(ipic_add_species(ipic_h, particleList(j)%mass, particleList(j)%q, particleList(j)%w_p, sp), 'ipic_add_species')
+        end do
+    end subroutine ipic_attach
+
+    subroutine ipic_push_state(solver, particleList)
+        class(potentialSolver), intent(in) :: solver
+        type(Particle), intent(in) :: particleList(:)
+        integer :: j
+        call ipic_check(ipic_set_field(ipic_h, IPIC_F_PHI, solver%phi, NumberXNodes), 'set phi')
+        call ipic_check(ipic_set_field(ipic_h, IPIC_F_PHI_F, solver%phi_f, NumberXNodes), 'set phi_f')
+        if (.not. particlesOnDevice) then
+            do j = 1, size(particleList)
+                call ipic_check(ipic_set_weight(ipic_h, j - 1, particleList(j)%w_p), 'ipic_set_weight')
+                call ipic_check(ipic_upload_particles(ipic_h, j - 1, particleList(j)%phaseSpace, particleList(j)%N_p, numThread, &
+                    particleList(j)%finalIdx), 'ipic_upload_particles')
+            end do
+            particlesOnDevice = .true.
+        end if
+    end subroutine ipic_push_state
+
+    subroutine depositJ(solver, particleList, world, del_t)
+        class(potentialSolver), intent(in out), target :: solver
+        type(Domain), intent(in) :: world
+        type(Particle), intent(in out) :: particleList(:)
+        real(real64), intent(in) :: del_t
+        call ipic_attach(solver, particleList, world)
+        call ipic_push_state(solver, particleList)
+        call ipic_check(ipic_deposit_J(ipic_h, del_t), 'ipic_deposit_J')
+        call ipic_check(ipic_get_field(ipic_h, IPIC_F_J, solver%J, NumberXHalfNodes), 'get J')
+        call ipic_check(ipic_get_field(ipic_h, IPIC_F_EFIELD, solver%EField, NumberXHalfNodes), 'get EField')
+    end subroutine depositJ
+
+    subroutine moveParticles(solver, particleList, world, del_t)
+        class(potentialSolver), intent(in out) :: solver
+        type(Domain), intent(in) :: world
+        type(Particle), intent(in out) :: particleList(:)
+        real(real64), intent(in) :: del_t
+        type(ipic_move_stats) :: st
+        integer :: j
+        call ipic_attach(solver, particleList, world)
+        call ipic_push_state(solver, particleList)
+        call ipic_check(ipic_move_particles(ipic_h, del_t), 'ipic_move_particles')
+        do j = 1, size(particleList)
+            call ipic_check(ipic_download_particles(ipic_h, j - 1, particleList(j)%phaseSpace, particleList(j)%N_p, numThread, &
+                particleList(j)%finalIdx), 'ipic_download_particles')
+            call ipic_check(ipic_get_move_stats(ipic_h, j - 1, st), 'ipic_get_move_stats')
+            ! totals are reported in slab 1; callers only ever use SUM(...) over the thread dimension
+            ! (main.f90:79-84, mod_simulation.f90:171-200)
+            particleList(j)%delIdx = 0
+            particleList(j)%delIdx(1) = int(st%delIdx, int32)
+            particleList(j)%refIdx = 0
+            particleList(j)%refIdx(1) = int(st%refIdx, int32)
+            particleList(j)%wallLoss = 0
+            particleList(j)%wallLoss(:, 1) = st%wallLoss
+            particleList(j)%energyLoss = 0.0d0
+            particleList(j)%energyLoss(:, 1) = st%energyLoss
+            particleList(j)%momentumLoss(:, 1) = st%momentumLoss
+            particleList(j)%numToCollide = particleList(j)%N_p
+            particleList(j)%numSubStepsAve = st%numSubStepsAve
+            particleList(j)%numFuncEvalAve = st%numFuncEvalAve
+            particleList(j)%accumEnergyLoss = particleList(j)%accumEnergyLoss + st%energyLoss
+            particleList(j)%accumWallLoss = particleList(j)%accumWallLoss + int(st%wallLoss, int32)
+        end do
+        particlesOnDevice = .false.     ! collisions / injection run on the host before the next step
+    end subroutine moveParticles
+
+end module mod_particleMover

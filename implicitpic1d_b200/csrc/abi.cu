@@ -44,7 +44,7 @@ constexpr int kNcclUint64 = 5, kNcclSum = 0;
 
 static int allreduce_acc(Ctx &c) {
     if (c.nranks <= 1 || !c.nccl_comm) return IPIC_OK;
-    const size_t count = (size_t)c.sp.size() * (std::max(c.Nx, c.Nh) + 2);
+    const size_t count = (size_t)c.sp.size() * 2 * (std::max(c.Nx, c.Nh) + 2);
     int rc = g_nccl.AllReduce(c.d_acc, c.d_acc, count, kNcclUint64, kNcclSum, c.nccl_comm, c.stream);
     if (rc != 0) { set_error(std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?")); return IPIC_ERR_NCCL; }
     return IPIC_OK;
@@ -269,8 +269,8 @@ int ipic_create(ipic_handle *out, int scheme, int32_t Nx, const double *grid, co
     RC(dalloc(&c->d_phi, NM)); RC(dalloc(&c->d_phi_f, NM)); RC(dalloc(&c->d_rho, NM)); RC(dalloc(&c->d_J, NM)); RC(dalloc(&c->d_E, NM));
     RC(dalloc(&c->d_a, NM)); RC(dalloc(&c->d_b, NM)); RC(dalloc(&c->d_c, NM)); RC(dalloc(&c->d_cp, NM)); RC(dalloc(&c->d_m, NM));
     RC(dalloc(&c->d_work, std::max<size_t>(8 * NM, 8192))); RC(dalloc(&c->d_rho_i, NM)); RC(dalloc(&c->d_scal, 64));
-    IPIC_CUDA(cudaMalloc(&c->d_acc, NSP_MAX * NM * sizeof(unsigned long long)));
-    IPIC_CUDA(cudaMemset(c->d_acc, 0, NSP_MAX * NM * sizeof(unsigned long long)));
+    IPIC_CUDA(cudaMalloc(&c->d_acc, NSP_MAX * 2 * NM * sizeof(unsigned long long)));
+    IPIC_CUDA(cudaMemset(c->d_acc, 0, NSP_MAX * 2 * NM * sizeof(unsigned long long)));
     const size_t tabsz = std::max(sizeof(CellTabNGP), sizeof(CellTabCIC));
     IPIC_CUDA(cudaMalloc(&c->d_tab, NSP_MAX * NM * tabsz)); IPIC_CUDA(cudaMemset(c->d_tab, 0, NSP_MAX * NM * tabsz));
     IPIC_CUDA(cudaMalloc(&c->d_counters, NSP_MAX * 8 * sizeof(unsigned long long)));
@@ -573,10 +573,11 @@ int ipic_comm_init(ipic_handle h, int32_t nranks, int32_t rank, const void *uid)
 int ipic_set_option(ipic_handle h, const char *name, double value) {
     CTX(h);
     const std::string k(name ? name : "");
-    if (k == "refill_min") c->refill_min = (int)value;
+    if (k == "stay_min" || k == "refill_min") c->stay_min = (int)value;
     else if (k == "push_blocks") c->push_blocks = (int)value;
+    else if (k == "tile_order") c->tile_order = (int)value;
     else if (k == "timing") c->timing_on = value != 0.0;
-    else if (k == "use_tma") c->use_tma = value != 0.0;
+    else if (k == "use_tma") { /* accepted for compatibility: the streaming path is register-prefetched */ }
     else if (k == "lazy_compaction") c->lazy_compaction = (int)value;
     else { set_error("unknown option " + k); return IPIC_ERR_ARG; }
     return IPIC_OK;

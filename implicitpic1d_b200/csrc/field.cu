@@ -120,18 +120,49 @@ __device__ void dev_smooth(const FieldArgs &A, const double *raw, double *out) {
 #undef RAW
 }
 
+// in-place inclusive prefix sum of n int64 values in shared memory (fixed order; integer, so exact)
+__device__ void block_scan_i64(long long *x, int n) {
+    __shared__ long long wtot[FT / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per = (n + FT - 1) / FT;
+    const int b = min(threadIdx.x * per, n), e = min(b + per, n);
+    long long run = 0;
+    for (int i = b; i < e; ++i) { run += x[i]; x[i] = run; }
+    long long inc = run;                                  // inclusive scan of the per-thread totals
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    long long off = inc - run;                            // exclusive within the warp
+    for (int w = 0; w < warp; ++w) off += wtot[w];
+    for (int i = b; i < e; ++i) x[i] += off;
+    __syncthreads();
+}
+
 // Sum the per-species int64 grids (species order, scaled by q*w_p) into dst[0..n-1]; zero the grids.
-__device__ void dev_collect(const FieldArgs &A, double *dst, int n) {
-    for (int i = threadIdx.x; i < n; i += FT) {
-        double acc = 0.0;
-        for (int s = 0; s < A.nsp; ++s) {
-            unsigned long long *p = A.acc + (size_t)s * A.acc_stride + (i + 1);
-            const double v = (double)(long long)(*p) * FX_INV;
-            *p = 0ull;
-            if (s == 0) acc = v * A.qw[0];
-            else acc = acc + v * A.qw[s];
+// with_runs: add the prefix sum of the species' difference grid (runs of fully traversed cells, see k_push).
+__device__ void dev_collect(const FieldArgs &A, double *dst, int n, bool with_runs, long long *scratch) {
+    for (int s = 0; s < A.nsp; ++s) {
+        unsigned long long *g = A.acc + (size_t)s * A.acc_stride;
+        if (with_runs) {
+            unsigned long long *d = g + A.acc_stride / 2;
+            for (int i = threadIdx.x; i < n; i += FT) { scratch[i] = (long long)d[i + 1]; d[i + 1] = 0ull; }
+            if (threadIdx.x == 0) d[n + 1] = 0ull;        // closing entry of a run that ends on the last cell
+            __syncthreads();
+            block_scan_i64(scratch, n);
         }
-        dst[i] = acc;
+        for (int i = threadIdx.x; i < n; i += FT) {
+            long long q = (long long)g[i + 1];
+            g[i + 1] = 0ull;
+            if (with_runs) q += scratch[i];
+            const double v = (double)q * FX_INV;
+            if (s == 0) dst[i] = v * A.qw[0];
+            else dst[i] = dst[i] + v * A.qw[s];
+        }
+        __syncthreads();
     }
 }
 
@@ -177,7 +208,7 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
 
     // ---------------- depositRho epilogue: NGP :150-187 ; CIC :146-172 ----------------
     if (ops & OP_FINALIZE_RHO) {
-        dev_collect(A, s0, Nx);
+        dev_collect(A, s0, Nx, false, reinterpret_cast<long long *>(s1));
         __syncthreads();
 #define D(i) s0[(i)-1]
         if (A.scheme == 0) {
@@ -281,7 +312,7 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
 
     // ---------------- depositJ epilogue: NGP mod_particleMover.f90:145-156 ; CIC mod_particleMoverPicard.f90:165-194 ----------------
     if (ops & OP_FINALIZE_J) {
-        dev_collect(A, s0, Nh);
+        dev_collect(A, s0, Nh, A.scheme == 0, reinterpret_cast<long long *>(s1));
         __syncthreads();
         if (A.scheme == 1 && threadIdx.x == 0) {
 #define W(i) s0[(i)-1]
@@ -443,7 +474,7 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
                 for (int cI = 1 + threadIdx.x; cI <= Nh; cI += FT) {
                     const double a = A.qm[s] * EF(cI), dx = DX(cI);
                     CellTabNGP t;
-                    t.a = a; t.inv_dx = 1.0 / dx; t.two_a_dx = 2.0 * a * dx; t.inv_a = 1.0 / a;
+                    t.a = a; t.hinv = 0.5 / dx; t.two_a_dx = 2.0 * a * dx; t.inv_a = 1.0 / a;
                     T[cI] = t;
                 }
             }
@@ -602,7 +633,7 @@ static FieldArgs make_args(Ctx &c) {
     FieldArgs A{};
     A.scheme = c.scheme; A.Nx = c.Nx; A.Nh = c.Nh; A.smooth = c.smooth; A.nsp = (int)c.sp.size();
     A.tridiag_mode = c.tridiag_mode; A.pcr_levels = c.pcr_levels;
-    A.acc_stride = std::max(c.Nx, c.Nh) + 2;
+    A.acc_stride = 2 * (std::max(c.Nx, c.Nh) + 2);
     A.tab_cells = ((c.scheme == IPIC_SCHEME_NGP) ? c.Nh : c.Nx) + 2;
     A.grid = c.d_grid; A.dx = c.d_dx; A.bc = c.d_bc;
     A.phi = c.d_phi; A.phi_f = c.d_phi_f; A.rho = c.d_rho; A.J = c.d_J; A.E = c.d_E;

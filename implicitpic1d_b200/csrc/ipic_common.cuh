@@ -29,7 +29,7 @@ __device__ __forceinline__ long long fx_from_double(double x) {
 // Per-cell, per-species lookup tables rebuilt from (phi, phi_f) before every sweep.
 struct CellTabNGP {   // OpenMP/NGP/src/mod_particleMover.f90:21-63 operands
     double a;          // q/m * E_c
-    double inv_dx;     // 1 / dx_dl(c)
+    double hinv;       // 0.5 / dx_dl(c)
     double two_a_dx;   // 2 a dx_dl(c)
     double inv_a;      // 1 / a
 };
@@ -45,8 +45,6 @@ struct CellTabCIC {   // OpenMP/CIC/src/mod_particleMoverPicard.f90:17-65,92-94 
 // streaming geometry of the push kernels
 constexpr int PUSH_THREADS = 1024;
 constexpr int PUSH_WARPS = PUSH_THREADS / 32;
-constexpr int CHUNK = 64;          // particles per staged chunk (per warp)
-constexpr int STAGES = 3;          // chunks in flight per warp
 constexpr int MAX_GRID_SMEM = 8192;   // largest N_h the shared-memory limb grid supports (12 B per cell)
 
 struct PushArgs {
@@ -54,13 +52,16 @@ struct PushArgs {
     double *l_out, *vx_out;    // MOVE: in-place outputs
     long long n;               // particles in the arrays (alive or marked dead)
     const void *tab;           // CellTabNGP* / CellTabCIC* for this species
-    const int *bc;             // boundaryConditions
+    int bcL, bcR;              // boundaryConditions at the two walls (zero everywhere else)
+    unsigned *tile_counter;    // dynamic tile scheduler (zeroed before the launch)
     unsigned long long *acc;   // !MOVE: int64 fixed-point grid [Nh] for this species
+    unsigned long long *dacc;  // !MOVE: difference grid of the runs of fully traversed cells (prefix-summed by the field kernel)
+    unsigned tile_stride;      // stride permutation of the tile order
     unsigned long long *counters;  // [0] deposit substeps, [1] func evals, [2] absorbed left, [3] absorbed right, [4] first reflections, [5] move substeps
     int Nh;                    // grid entries to deposit on
     int NB;                    // wall index on the right: N_x (NGP) or N_h (CIC)
     double del_t, f_tol;
-    int refill_min;            // refill a warp when at least this many lanes are idle (32 = lock-step)
+    int stay_min;              // a queued batch keeps looping in registers while at least this many lanes continue
 };
 
 // ---- device context -------------------------------------------------------------------------------
@@ -93,7 +94,7 @@ struct Ctx {
     double *d_pcr = nullptr; int pcr_levels = 0;                  // PCR level coefficients [levels][2][Nx] + inv diag [Nx]
     double *d_work = nullptr;                                     // scratch (4 * max(Nx,Nh))
     double *d_rho_i = nullptr;
-    unsigned long long *d_acc = nullptr;                          // [nsp_max][max(Nx,Nh)] int64 accumulators
+    unsigned long long *d_acc = nullptr;                          // [nsp_max][2][max(Nx,Nh)+2] int64 accumulators: grid, difference grid
     void *d_tab = nullptr;                                        // [nsp_max][cells] CellTab*
     unsigned long long *d_counters = nullptr;                     // [nsp_max][8]
     double *d_scal = nullptr;                                     // small device scalar outputs (64 doubles)
@@ -116,10 +117,10 @@ struct Ctx {
     double lastNorm = 0;
     std::vector<SpeciesDev> sp;
     // options
-    int refill_min = 8;
+    int stay_min = 20;
+    int tile_order = 1;           // 1 = stride-permuted tile order, 0 = in array order
     int push_blocks = 0;          // 0 = one CTA per SM
     int lazy_compaction = 0;
-    int use_tma = 1;              // particle streaming: 1 = TMA bulk copies into a per-warp ring, 0 = register-prefetched LDG
     // multi-GPU
     void *nccl_comm = nullptr; int nranks = 1, rank = 0;
     // timing

@@ -129,309 +129,441 @@ __device__ __forceinline__ void limb_grid_flush(const LimbGrid &g, int n) {
 }
 
 // =====================================================================================================
-// The push kernel.  One CTA per SM; every warp owns a CONTIGUOUS range of particles and streams it
-// through a private shared-memory ring filled by 1-D bulk async copies (TMA) signalled on warp-private
-// mbarriers, so no inter-warp synchronisation exists in the streaming loop.
+// The push kernel (depositJ sweep / moveParticles).  Persistent CTAs, one per SM, 32 warps each.
 //
-// Divergence control: a batch is 32 particles, one per lane, and executes exactly ONE sub-step.  Fresh
-// batches come straight from the ring (lane = slot).  Lanes whose particle must continue (it reached a
-// cell face with time left) push their state into a per-warp shared-memory queue; as soon as the queue
-// holds 32 continuations they are popped and executed as a full batch.  So every sub-step runs with all
-// lanes active, whatever the per-particle sub-step count, and the common single-sub-step particle costs
-// no bookkeeping at all.
+// Work distribution: the particle array is cut into TILEs of 512 particles that warps claim from a global
+// counter (one atomic per tile).  Cell-sorted particles make the cost of a tile depend on where it lies
+// (sheath electrons take tens of sub-steps, bulk ions one), so a static partition would leave most of the
+// GPU waiting for the few warps that drew the sheath; dynamic tiles keep every warp busy to the end.
 //
-// Deposition (MOVE == false): every lane owns a private window of WIN int64 fixed-point accumulators in
-// shared memory (cells base-WLO .. base-WLO+WIN-1, `base` warp-uniform = cell of the newest fresh batch;
-// conflict-free layout [k][lane]).  A deposit is a plain 64-bit read-modify-write -- no atomics, no
-// cross-lane traffic -- because cell-sorted particles keep a warp inside a few cells.  Deposits outside
-// the window, and the windows themselves when `base` moves on, go to the global int64 grid with native
-// RED.ADD.64.  Integer sums make the result independent of all of this bookkeeping.
+// Streaming: when a warp claims a tile it prefetches the tile's 2 x 4 KB into L2 (one prefetch instruction
+// per array: 32 lanes x one 128-byte line); it then reads the tile in sub-tiles of 32*SUB particles with
+// coalesced, L1-bypassing loads issued one sub-tile ahead into registers, so the loop body never waits
+// on HBM and the shared memory stays small enough to leave most of the 256 KB to L1 (per-cell tables).
+//
+// Divergence control: a batch is 32 particles, one per lane, and executes exactly ONE sub-step.
+//   fresh batch : the cheap first part of the sub-step only (no square root, no divide).  A particle that
+//                 stays in its cell for the whole del_t -- every ion, most bulk electrons at small del_t --
+//                 is finished here.  One that reaches a cell face is pushed, unchanged, to the warp's
+//                 continuation queue in shared memory.
+//   queued batch: as soon as the queue holds 32 entries they are popped and run through the general
+//                 sub-step with all lanes active.  Lanes with time left go back to the queue -- unless
+//                 at least `stay_min` lanes continue, in which case the batch simply loops in registers
+//                 (sheath electrons: tens of consecutive sub-steps without any queue traffic).
+//
+// Deposition (MOVE == false): deposits are 64-bit fixed-point integers (see ipic_common.cuh), so the sum
+// is exact and independent of order, of the tile schedule and of the GPU count.  Every lane keeps
+// register accumulators for the warp's current cell `base` and base+1 and a private shared-memory window
+// [WIN][lane] for base-WLO .. base-WLO+WIN-1 (conflict-free, no atomics); anything further away goes
+// straight to the global int64 grid with RED.64.  When `base` moves on (sorted input: about once per tile)
+// the accumulators are summed across the warp with integer REDUX on 21-bit limbs and flushed with one
+// RED.64 per cell.
+//
+// Runs of fully traversed cells (NGP): a fast electron that crosses k whole cells deposits exactly +-1.0
+// (= +-2^44 in fixed point) in each of them.  Instead of k deposits the particle carries the first cell of
+// the run; when the run ends, [a, b] += s is recorded as two entries of a difference grid, D[a] += s,
+// D[b+1] -= s, whose integer prefix sum the field kernel adds back (exactly the same integers, so the
+// result is bit-identical to depositing cell by cell).  A sheath electron therefore costs ~4 deposits
+// per sweep, not one per sub-step.
 //   SCHEME 0: NGP constant-field sub-step   (mod_particleMover.f90:21-63)
 //   SCHEME 1: CIC Picard sub-step           (mod_particleMoverPicard.f90:17-65)
 //   MOVE false: depositJ sweep (no particle writes, J accumulated)   true: moveParticles (write back)
 // =====================================================================================================
-constexpr int WIN = 6, WLO = 2;   // window covers cells base-2 .. base+3
-constexpr int QCAP = 64;          // continuation queue entries per warp
+constexpr int SUB = 2;                       // batches per register-staged sub-tile
+constexpr int SUBTILE = 32 * SUB;            // 64 particles
+constexpr int TILE_SUBS = 8;
+constexpr int TILE = SUBTILE * TILE_SUBS;    // 512 particles per scheduled tile = one 4 KB L2 prefetch per array
+constexpr int WIN = 4, WLO = 2;              // window slots hold cells base-2, base-1, base+2, base+3 (base, base+1 live in registers)
+constexpr int QCAP = 32 * (SUB + 1);         // continuation queue entries per warp: at most 31 + 32*SUB live
 
-struct alignas(128) WarpSmem {    // per-warp shared memory (6.6 KB, TMA destinations 128-byte aligned)
-    double ring[STAGES][2][CHUNK];
+struct alignas(16) WarpSmem {                // per-warp shared memory: 4.4 KB
     unsigned long long win[WIN][32];
     double ql[QCAP], qv[QCAP], qt[QCAP];
     int qcell[QCAP];
-    unsigned qidx[QCAP];          // particle index relative to the warp's range; bit 31 = already reflected
-    unsigned long long bar[STAGES];
+    int qpend[QCAP];                         // pending run of fully traversed cells: +first cell (moving right), -first cell (moving left)
+    unsigned qidx[QCAP];                     // global particle index; bit 31 = already reflected (MOVE)
 };
 
-__device__ __forceinline__ void window_flush(WarpSmem &W, int lane, int base, unsigned &dirty, unsigned long long *gacc) {
-    while (dirty) {
-        const int k = __ffs(dirty) - 1;
-        dirty &= dirty - 1;
-        const unsigned long long v = W.win[k][lane];
-        W.win[k][lane] = 0ull;
-        if (v) atomicAdd(gacc + (base - WLO + k), v);
+// exact warp sum of one int64 per lane, one RED.64 to *dst.  Called by all 32 lanes.
+__device__ __forceinline__ void warp_flush_value(unsigned long long v, unsigned long long *dst, int lane) {
+    if (!__any_sync(FULL, v != 0ull)) return;
+    const unsigned lo = __reduce_add_sync(FULL, (unsigned)v & 0x1FFFFFu);
+    const unsigned mid = __reduce_add_sync(FULL, (unsigned)(v >> 21) & 0x1FFFFFu);
+    const int hi = __reduce_add_sync(FULL, (int)((long long)v >> 42));
+    if (lane == 0) {
+        const unsigned long long t = (unsigned long long)lo + ((unsigned long long)mid << 21) + ((unsigned long long)(long long)hi << 42);
+        if (t) atomicAdd(dst, t);
     }
 }
-__device__ __forceinline__ void window_add(WarpSmem &W, int lane, int base, unsigned &dirty, unsigned long long *gacc, int cell, long long q) {
-    const unsigned k = (unsigned)(cell - base + WLO);
-    if (k < (unsigned)WIN) {
-        W.win[k][lane] += (unsigned long long)q;
-        dirty |= 1u << k;
+
+struct DepositState {
+    unsigned long long r0 = 0ull, r1 = 0ull;   // accumulators for cells base, base+1
+    unsigned dirty = 0u;
+    int base = 0;
+};
+
+__device__ __forceinline__ void deposit_flush(WarpSmem &W, DepositState &D, int lane, unsigned long long *gacc) {
+    if (D.base > 0) {
+        warp_flush_value(D.r0, gacc + D.base, lane);
+        warp_flush_value(D.r1, gacc + D.base + 1, lane);
+    }
+    D.r0 = 0ull; D.r1 = 0ull;
+    unsigned d = __reduce_or_sync(FULL, D.dirty);
+    while (d) {
+        const int k = __ffs(d) - 1;
+        d &= d - 1;
+        unsigned long long v = 0ull;
+        if ((D.dirty >> k) & 1u) { v = W.win[k][lane]; W.win[k][lane] = 0ull; }
+        warp_flush_value(v, gacc + (D.base - WLO + k), lane);
+    }
+    D.dirty = 0u;
+}
+
+__device__ __forceinline__ void deposit_add(WarpSmem &W, DepositState &D, int lane, unsigned long long *gacc, int cell, long long q) {
+    const int k = cell - D.base;
+    if (k == 0) D.r0 += (unsigned long long)q;
+    else if (k == 1) D.r1 += (unsigned long long)q;
+    else if ((unsigned)(k + WLO) < (unsigned)WIN) {
+        W.win[k + WLO][lane] += (unsigned long long)q;
+        D.dirty |= 1u << (k + WLO);
     } else {
         atomicAdd(gacc + cell, (unsigned long long)q);
     }
 }
 
-template <int SCHEME, bool MOVE, bool TMA>
+constexpr long long FX_ONE = 1ll << FX_BITS;
+
+// ends a run of fully traversed cells; `cend` is the cell the particle is in now (not part of the run)
+__device__ __forceinline__ void close_run(WarpSmem &W, DepositState &D, int lane, const PushArgs &A, int pend, int cend) {
+    if (pend > 0) {                                          // moving right: cells pend .. cend-1 got +1 each
+        if (cend - pend == 1) deposit_add(W, D, lane, A.acc, pend, FX_ONE);
+        else {
+            atomicAdd(A.dacc + pend, (unsigned long long)FX_ONE);
+            atomicAdd(A.dacc + cend, (unsigned long long)(-FX_ONE));
+        }
+    } else {                                                 // moving left: cells cend+1 .. -pend got -1 each
+        const int start = -pend;
+        if (start - cend == 1) deposit_add(W, D, lane, A.acc, start, -FX_ONE);
+        else {
+            atomicAdd(A.dacc + cend + 1, (unsigned long long)(-FX_ONE));
+            atomicAdd(A.dacc + start + 1, (unsigned long long)FX_ONE);
+        }
+    }
+}
+
+template <int SCHEME, bool MOVE>
 __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpSmem &W = reinterpret_cast<WarpSmem *>(smem_raw)[warp];
-    const unsigned bar0 = smem_u32(&W.bar[0]);
-    if (TMA && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(bar0 + 8u * s, 1);
-        fence_barrier_init();
-    }
+    DepositState D;
     if (!MOVE) {
 #pragma unroll
         for (int k = 0; k < WIN; ++k) W.win[k][lane] = 0ull;
     }
     __syncwarp();
 
-    // contiguous chunk range of this warp
-    const long long GW = (long long)gridDim.x * PUSH_WARPS;
-    const long long gw = (long long)blockIdx.x * PUSH_WARPS + warp;
-    const long long nchunks = (A.n + CHUNK - 1) / CHUNK;
-    const long long per = (nchunks + GW - 1) / GW;
-    const long long c_beg = min(gw * per, nchunks), c_end = min(c_beg + per, nchunks);
-    constexpr unsigned CH_BYTES = CHUNK * sizeof(double);
-
-    long long c_issue = c_beg;   // next chunk to put in flight (only lane 0 uses it)
-    if (TMA && lane == 0) {
-        for (int s = 0; s < STAGES && c_issue < c_end; ++s, ++c_issue) {
-            const unsigned bar = bar0 + 8u * s;
-            mbar_expect_tx(bar, 2 * CH_BYTES);
-            bulk_g2s(smem_u32(&W.ring[s][0][0]), A.l + c_issue * CHUNK, CH_BYTES, bar);
-            bulk_g2s(smem_u32(&W.ring[s][1][0]), A.vx + c_issue * CHUNK, CH_BYTES, bar);
-        }
-    }
-    __syncwarp();
-
-    const long long range0 = c_beg * CHUNK;             // first particle of the warp's range
-    const unsigned n_rel = (unsigned)min((long long)0x7fffffff, max(0ll, A.n - range0));   // particles at or after range0
-    const unsigned n_rng = (unsigned)((c_end - c_beg) * CHUNK);                              // slots in the warp's range
-    unsigned rel0 = 0;                                   // TMA: range-relative index of the current chunk's first particle
-    long long c_cur = c_beg;
-    int pos = 0, stage = 0, qcount = 0, base = 0;
-    unsigned parity = 0, dirty = 0;
-    unsigned nsub = 0, nfev = 0, nabsL = 0, nabsR = 0, nrefl = 0;
+    const unsigned n = (unsigned)A.n;                       // n < 2^31 (checked on the host)
+    const unsigned ntiles = (n + TILE - 1) / TILE;
     const double del_t = A.del_t, f_tol = A.f_tol;
+    const int stay_min = A.stay_min;
+    int qcount = 0;
+    unsigned nsub = 0, nfev = 0, nabsL = 0, nabsR = 0, nrefl = 0;
 
-    // !TMA: register-prefetched streaming loads, PF batches ahead (coalesced 256 B per array per warp)
-    constexpr int PF = 3;
-    const double *gl = A.l + range0 + lane, *gv = A.vx + range0 + lane;
-    double pl[PF], pv[PF];
-    unsigned cur = 0;                                    // !TMA: range-relative index of the current batch
-    if (!TMA) {
-#pragma unroll
-        for (int k = 0; k < PF; ++k) {
-            const unsigned o = (unsigned)k * 32u;
-            const bool in = o < n_rng;
-            pl[k] = in ? __ldcs(gl + o) : -1.0;
-            pv[k] = in ? __ldcs(gv + o) : 0.0;
+    // tile claims run one ahead so that the atomic's latency is never exposed
+    auto claim = [&]() -> unsigned {
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(A.tile_counter, 1u);
+        t = __shfl_sync(FULL, t, 0);
+        // claims are mapped through a stride permutation so that the tiles in flight are spread over the whole
+        // domain: expensive regions are met throughout the kernel and concurrent warps deposit to different cells
+        t = (t < ntiles) ? (unsigned)(((unsigned long long)t * A.tile_stride) % ntiles) : ntiles;
+        if (t < ntiles) {                                    // pull the tile into L2: 32 lanes x 128 B = 4 KB per array
+            const size_t off = (size_t)t * TILE + 16u * lane;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(A.l + off));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(A.vx + off));
         }
-    }
+        return t;
+    };
+    unsigned tile = claim();
+    unsigned tile_next = (tile < ntiles) ? claim() : ntiles;
+    int sub = 0;
+    double nl[SUB], nv[SUB];                                // next sub-tile, in flight
+    unsigned next_g0 = tile * (unsigned)TILE;               // global index of its first particle
+    bool next_ok = tile < ntiles;
+    auto issue_loads = [&]() {
+#pragma unroll
+        for (int b = 0; b < SUB; ++b) {
+            const unsigned gi = next_g0 + 32u * b + lane;   // arrays are padded past n (ensure_capacity)
+            nl[b] = __ldcs(A.l + gi);
+            nv[b] = __ldcs(A.vx + gi);
+        }
+    };
+    if (next_ok) issue_loads();
 
-    bool fresh_left = TMA ? (c_cur < c_end) : (n_rng > 0);
-    while (fresh_left || qcount > 0) {
-        // ---------------- assemble one batch: queued continuations first (when full), else fresh ----------------
-        bool valid;
-        double l, v, tp;
-        int cell;
-        unsigned idx;     // range-relative particle index, bit 31 = reflected before
-        if (qcount >= 32 || !fresh_left) {
+    // ---------------- the general sub-step: runs batches popped from the queue ----------------
+    bool drain_all = !next_ok;
+    for (;;) {
+        while (qcount >= 32 || (drain_all && qcount > 0)) {
             const int take = min(qcount, 32);
             qcount -= take;
-            valid = lane < take;
+            bool valid = lane < take;
             const int q = qcount + (valid ? lane : 0);
-            l = W.ql[q]; v = W.qv[q]; tp = W.qt[q]; cell = W.qcell[q]; idx = W.qidx[q];
+            double l = W.ql[q], v = W.qv[q], tp = W.qt[q];
+            int cell = W.qcell[q];
+            int pend = W.qpend[q];
+            unsigned idx = W.qidx[q];
             __syncwarp();
-        } else {
-            if (TMA) {
-                if (pos == 0) mbar_wait(bar0 + 8u * stage, parity);
-                l = W.ring[stage][0][pos + lane];
-                v = W.ring[stage][1][pos + lane];
-                idx = rel0 + pos + lane;
-                pos += 32;
-            } else {
-                l = pl[0]; v = pv[0];
-                idx = cur + lane;
-#pragma unroll
-                for (int k = 0; k + 1 < PF; ++k) { pl[k] = pl[k + 1]; pv[k] = pv[k + 1]; }
-                const unsigned o = cur + (unsigned)PF * 32u;
-                const bool in = o < n_rng;
-                pl[PF - 1] = in ? __ldcs(gl + o) : -1.0;
-                pv[PF - 1] = in ? __ldcs(gv + o) : 0.0;
-                cur += 32u;
-                fresh_left = cur < n_rng;
-            }
-            tp = 0.0;
-            valid = (idx < n_rel) && (l >= 0.0);        // l < 0 marks a particle absorbed earlier and not yet compacted
-            // l_cell = INT(l_sub + SIGN(1.d-12, v_sub))
-            cell = (int)(l + copysign(1.e-12, v));
-            if (!MOVE) {
-                // follow the stream: re-centre the window on the cell of the batch's first particle
-                const int nb = __shfl_sync(FULL, cell, 0);
-                if (nb != base && nb > 0) {
-                    window_flush(W, lane, base, dirty, A.acc);
-                    base = nb;
-                }
-            }
-            if (TMA && pos == CHUNK) {   // chunk consumed: its stage is refilled with the next chunk of the range
-                __syncwarp();
-                if (lane == 0 && c_issue < c_end) {
-                    fence_proxy_async();
-                    const unsigned bar = bar0 + 8u * stage;
-                    mbar_expect_tx(bar, 2 * CH_BYTES);
-                    bulk_g2s(smem_u32(&W.ring[stage][0][0]), A.l + c_issue * CHUNK, CH_BYTES, bar);
-                    bulk_g2s(smem_u32(&W.ring[stage][1][0]), A.vx + c_issue * CHUNK, CH_BYTES, bar);
-                    ++c_issue;
-                }
-                c_cur += 1; rel0 += CHUNK; pos = 0;
-                if (++stage == STAGES) { stage = 0; parity ^= 1u; }
-                fresh_left = c_cur < c_end;
-            }
-        }
-
-        // ---------------- one sub-step for every valid lane ----------------
-        bool cont = false;
-        double l_f = 0.0, v_f = 0.0;
-        if (valid) {
-            nsub += 1;
-            double dtau = del_t - tp;
-            bool atB;
-            int lb = 0;
-            if (SCHEME == 0) {
-                const double2 *tp2 = reinterpret_cast<const double2 *>(reinterpret_cast<const CellTabNGP *>(A.tab) + cell);
-                const double2 t0 = __ldg(tp2), t1 = __ldg(tp2 + 1);
-                const double a = t0.x, inv_dx = t0.y, two_a_dx = t1.x, inv_a = t1.y;
-                v_f = fma(a, dtau, v);
-                l_f = fma(0.5 * (v + v_f) * dtau, inv_dx, l);
-                const bool inCell = ((int)l_f == cell);
-                const bool eqSign = ((v > 0.0) == (v_f > 0.0));
-                atB = (!inCell) || (!eqSign);
-                if (atB) {
-                    lb = (v > 0.0) ? cell + 1 : cell;
-                    double diff_PE = two_a_dx * ((double)lb - l);
-                    const double v2 = v * v;
-                    if (diff_PE > -v2) {
-                        l_f = (double)lb;
-                        v_f = copysign(sqrt(diff_PE + v2), v);
-                        dtau = (v_f - v) * inv_a;
-                    } else if (!inCell) {
-                        lb = 2 * cell + 1 - lb;
-                        l_f = (double)lb;
-                        diff_PE = two_a_dx * (l_f - l);
-                        v_f = -copysign(sqrt(diff_PE + v2), v);
-                        dtau = (v_f - v) * inv_a;
+            for (;;) {
+                bool cont = false;
+                double l_f = l, v_f = v;
+                if (valid) {
+                    nsub += 1;
+                    double dtau = del_t - tp;
+                    bool atB;
+                    int lb = 0;
+                    if (SCHEME == 0) {
+                        // particleSubStepNoBField (mod_particleMover.f90:21-63), written flat: the three outcomes
+                        // (reaches the face ahead / leaves through the face behind / stays in the cell) are selected,
+                        // not branched on, so the common face-to-face transit runs without divergence.
+                        const double2 *tp2 = reinterpret_cast<const double2 *>(reinterpret_cast<const CellTabNGP *>(A.tab) + cell);
+                        const double2 t0 = __ldg(tp2), t1 = __ldg(tp2 + 1);
+                        const double a = t0.x, hinv = t0.y, two_a_dx = t1.x, inv_a = t1.y;
+                        const double v_f0 = fma(a, dtau, v);
+                        const double l_f0 = fma((v + v_f0) * dtau, hinv, l);
+                        const bool inCell = ((int)l_f0 == cell);
+                        const bool vpos = v > 0.0;
+                        const bool eqSign = (vpos == (v_f0 > 0.0));
+                        const double v2 = v * v;
+                        lb = cell + (vpos ? 1 : 0);
+                        double diff_PE = two_a_dx * ((double)lb - l);
+                        const bool maybeB = !(inCell && eqSign);
+                        const bool fwd = maybeB && (diff_PE > -v2);
+                        const bool bwd = maybeB && !fwd && !inCell;
+                        atB = fwd || bwd;
+                        double sgn = v;
+                        if (bwd) {
+                            lb = 2 * cell + 1 - lb;
+                            diff_PE = two_a_dx * ((double)lb - l);
+                            sgn = -v;
+                        }
+                        v_f = v_f0; l_f = l_f0;
+                        if (atB) {
+                            l_f = (double)lb;
+                            v_f = copysign(sqrt(diff_PE + v2), sgn);
+                            dtau = (v_f - v) * inv_a;
+                        }
+                        if (!MOVE) {
+                            const double dl = l_f - l;
+                            const bool full = (fabs(dl) == 1.0);
+                            const bool right = dl > 0.0;
+                            if (pend != 0 && !(full && ((pend > 0) == right))) { close_run(W, D, lane, A, pend, cell); pend = 0; }
+                            if (full) pend = (pend != 0) ? pend : (right ? cell : -cell);
+                            else deposit_add(W, D, lane, A.acc, cell, fx_from_double(dl));
+                        }
                     } else {
+                        const double2 *tp2 = reinterpret_cast<const double2 *>(reinterpret_cast<const CellTabCIC *>(A.tab) + cell);
+                        const double2 t0 = __ldg(tp2), t1 = __ldg(tp2 + 1);
+                        const double cap = __ldg(reinterpret_cast<const double *>(tp2 + 2));
+                        const double A0 = t0.x, A1 = t0.y, inv_dx = t1.x, dx = t1.y;
+                        dtau = fmin(dtau, cap);
+                        const double ls = l - (double)cell;
+                        const double r = dtau * inv_dx;
+                        double l_prev = ls, lf = ls, d_half = ls, accel = 0.0, v_half = v;
+                        int it;
                         atB = false;
+                        for (it = 1; it <= 50; ++it) {
+                            d_half = (ls + l_prev) * 0.5;
+                            accel = fma(A1, d_half, A0);
+                            v_half = fma(0.5 * accel, r, v);
+                            lf = fma(v_half, r, ls);
+                            atB = (lf <= 0.0) || (lf >= 1.0);
+                            if (atB) lf = (v_half < 0.0) ? 0.0 : 1.0;
+                            if (fabs(lf - l_prev) < 1.e-10) break;
+                            l_prev = lf;
+                        }
+                        int numIter = it;   // 51 after an exhausted loop, as the Fortran loop variable
+                        if (!atB) {
+                            v_f = 2.0 * v_half - v;
+                        } else {
+                            if (lf != ls) {
+                                v_f = copysign(sqrt(2.0 * accel * (lf - ls) + v * v), v_half);
+                                dtau = (lf - ls) * dx / v_half;
+                                numIter += 1;
+                            } else {
+                                dtau = -2.0 * v * dx / accel;
+                                v_f = -v;
+                            }
+                            lb = (int)lf + cell;
+                        }
+                        l_f = lf + (double)cell;
+                        if (MOVE) nfev += (unsigned)numIter;
+                        if (!MOVE) {
+                            const double Jp = l_f - l;
+                            deposit_add(W, D, lane, A.acc, cell, fx_from_double((1.0 - d_half) * Jp));
+                            deposit_add(W, D, lane, A.acc, cell + 1, fx_from_double(Jp * d_half));
+                        }
                     }
-                }
-                if (!MOVE) window_add(W, lane, base, dirty, A.acc, cell, fx_from_double(l_f - l));
-            } else {
-                const double2 *tp2 = reinterpret_cast<const double2 *>(reinterpret_cast<const CellTabCIC *>(A.tab) + cell);
-                const double2 t0 = __ldg(tp2), t1 = __ldg(tp2 + 1);
-                const double cap = __ldg(reinterpret_cast<const double *>(tp2 + 2));
-                const double A0 = t0.x, A1 = t0.y, inv_dx = t1.x, dx = t1.y;
-                dtau = fmin(dtau, cap);
-                const double ls = l - (double)cell;
-                const double r = dtau * inv_dx;
-                double l_prev = ls, lf = ls, d_half = ls, accel = 0.0, v_half = v;
-                int it;
-                atB = false;
-                for (it = 1; it <= 50; ++it) {
-                    d_half = (ls + l_prev) * 0.5;
-                    accel = fma(A1, d_half, A0);
-                    v_half = fma(0.5 * accel, r, v);
-                    lf = fma(v_half, r, ls);
-                    atB = (lf <= 0.0) || (lf >= 1.0);
-                    if (atB) lf = (v_half < 0.0) ? 0.0 : 1.0;
-                    if (fabs(lf - l_prev) < 1.e-10) break;
-                    l_prev = lf;
-                }
-                int numIter = it;   // 51 after an exhausted loop, as the Fortran loop variable
-                if (!atB) {
-                    v_f = 2.0 * v_half - v;
-                } else {
-                    if (lf != ls) {
-                        v_f = copysign(sqrt(2.0 * accel * (lf - ls) + v * v), v_half);
-                        dtau = (lf - ls) * dx / v_half;
-                        numIter += 1;
+                    bool absorbed = false;
+                    if (atB) {
+                        // boundaryConditions is zero except at the two walls (mod_domain.f90: walls only at index 1 and N)
+                        if (lb != 1 && lb != A.NB) {
+                            cell += signbit(v_f) ? -1 : 1;
+                        } else {
+                            const int b = (lb == 1) ? A.bcL : A.bcR;
+                            if (!MOVE && SCHEME == 0 && b != 0 && pend != 0) {
+                                // a run that ends on a wall includes the wall cell: the particle does not move on to a new cell
+                                close_run(W, D, lane, A, pend, cell + (pend > 0 ? 1 : -1));
+                                pend = 0;
+                            }
+                            if (b == 0) {
+                                cell += signbit(v_f) ? -1 : 1;
+                            } else if (b == 1 || b == 4) {
+                                absorbed = true;
+                            } else if (b == 2) {
+                                if (lb == A.NB) { if (v_f > 0.0) v_f = -v_f; }
+                                else { if (v_f < 0.0) v_f = -v_f; }
+                                if (MOVE && !(idx >> 31)) { idx |= 0x80000000u; nrefl += 1; }
+                            } else if (b == 3) {
+                                l_f = (double)abs(lb - A.NB - 1);
+                                cell = abs(cell - A.NB);
+                            }
+                        }
+                    }
+                    tp += dtau;
+                    const double rem = del_t - tp;
+                    if (absorbed) {
+                        if (MOVE) {
+                            // mark for the compaction pass; the wall side is recoverable from the marker
+                            const bool left = (lb == 1);
+                            if (left) nabsL += 1; else nabsR += 1;
+                            const unsigned gi = idx & 0x7fffffffu;
+                            A.l_out[gi] = left ? -1.0 : -2.0;
+                            A.vx_out[gi] = v_f;
+                        }
+                    } else if (!(rem > f_tol)) {
+                        if (MOVE) {
+                            const unsigned gi = idx & 0x7fffffffu;
+                            A.l_out[gi] = l_f;
+                            A.vx_out[gi] = v_f;
+                        }
+                        if (!MOVE && SCHEME == 0 && pend != 0) close_run(W, D, lane, A, pend, cell);
                     } else {
-                        dtau = -2.0 * v * dx / accel;
-                        v_f = -v;
+                        cont = true;
                     }
-                    lb = (int)lf + cell;
                 }
-                l_f = lf + (double)cell;
-                if (MOVE) nfev += (unsigned)numIter;
-                if (!MOVE) {
-                    const double Jp = l_f - l;
-                    window_add(W, lane, base, dirty, A.acc, cell, fx_from_double((1.0 - d_half) * Jp));
-                    window_add(W, lane, base, dirty, A.acc, cell + 1, fx_from_double(Jp * d_half));
+                const unsigned cm = __ballot_sync(FULL, cont);
+                if (!cm) break;
+                if (__popc(cm) >= stay_min) {       // most of the batch goes on: loop in registers
+                    valid = cont; l = l_f; v = v_f;
+                    continue;
                 }
-            }
-            bool absorbed = false;
-            if (atB) {
-                const int b = __ldg(A.bc + lb);
-                if (b == 0) {
-                    cell += signbit(v_f) ? -1 : 1;
-                } else if (b == 1 || b == 4) {
-                    absorbed = true;
-                } else if (b == 2) {
-                    if (lb == A.NB) { if (v_f > 0.0) v_f = -v_f; }
-                    else { if (v_f < 0.0) v_f = -v_f; }
-                    if (MOVE && !(idx >> 31)) { idx |= 0x80000000u; nrefl += 1; }
-                } else if (b == 3) {
-                    l_f = (double)abs(lb - A.NB - 1);
-                    cell = abs(cell - A.NB);
+                if (cont) {
+                    const int qq = qcount + __popc(cm & ((1u << lane) - 1u));
+                    W.ql[qq] = l_f; W.qv[qq] = v_f; W.qt[qq] = tp; W.qcell[qq] = cell; W.qpend[qq] = pend; W.qidx[qq] = idx;
                 }
-            }
-            tp += dtau;
-            const double rem = del_t - tp;
-            if (absorbed) {
-                if (MOVE) {
-                    // mark for the compaction pass; the wall side is recoverable from the marker
-                    const bool left = (lb == 1);
-                    if (left) nabsL += 1; else nabsR += 1;
-                    const long long gi = range0 + (idx & 0x7fffffffu);
-                    A.l_out[gi] = left ? -1.0 : -2.0;
-                    A.vx_out[gi] = v_f;
-                }
-            } else if (!(rem > f_tol)) {
-                if (MOVE) {
-                    const long long gi = range0 + (idx & 0x7fffffffu);
-                    A.l_out[gi] = l_f;
-                    A.vx_out[gi] = v_f;
-                }
-            } else {
-                cont = true;
+                qcount += __popc(cm);
+                __syncwarp();
+                break;
             }
         }
-        // ---------------- lanes with time left queue their state ----------------
-        const unsigned cm = __ballot_sync(FULL, cont);
-        if (cm) {
-            if (cont) {
-                const int q = qcount + __popc(cm & ((1u << lane) - 1u));
-                W.ql[q] = l_f; W.qv[q] = v_f; W.qt[q] = tp; W.qcell[q] = cell; W.qidx[q] = idx;
-            }
-            qcount += __popc(cm);
-            __syncwarp();
+        if (drain_all) break;
+
+        // ---------------- fresh batches of the next sub-tile ----------------
+        // rotate the staged sub-tile into the working registers and put the following one in flight
+        double cl[SUB], cv[SUB];
+#pragma unroll
+        for (int b = 0; b < SUB; ++b) { cl[b] = nl[b]; cv[b] = nv[b]; }
+        const unsigned g0 = next_g0;
+        if (++sub == TILE_SUBS) {
+            sub = 0;
+            tile = tile_next;
+            if (tile < ntiles) tile_next = claim();
         }
+        next_ok = tile < ntiles;
+        next_g0 = tile * (unsigned)TILE + (unsigned)sub * SUBTILE;
+        if (next_ok) issue_loads();
+
+#pragma unroll
+        for (int b = 0; b < SUB; ++b) {
+            const double l = cl[b], v = cv[b];
+            const unsigned gi = g0 + 32u * b + lane;
+            const bool valid = (gi < n) && (l >= 0.0);      // l < 0 marks a particle absorbed earlier and not yet compacted
+            // l_cell = INT(l_sub + SIGN(1.d-12, v_sub))
+            const int cell = (int)(l + copysign(1.e-12, v));
+            if (!MOVE && b == 0) {
+                // follow the stream: re-centre the accumulators on the cell of the sub-tile's first particle
+                const int nb = __shfl_sync(FULL, cell, 0);
+                if (nb != D.base && nb > 0) {
+                    deposit_flush(W, D, lane, A.acc);
+                    D.base = nb;
+                }
+            }
+            bool cont = false;
+            if (valid) {
+                bool done;
+                if (SCHEME == 0) {
+                    const double2 t0 = __ldg(reinterpret_cast<const double2 *>(reinterpret_cast<const CellTabNGP *>(A.tab) + cell));
+                    const double v_f = fma(t0.x, del_t, v);
+                    const double l_f = fma((v + v_f) * del_t, t0.y, l);
+                    done = ((int)l_f == cell) && ((v > 0.0) == (v_f > 0.0));
+                    if (done) {
+                        if (!MOVE) deposit_add(W, D, lane, A.acc, cell, fx_from_double(l_f - l));
+                        else { A.l_out[gi] = l_f; A.vx_out[gi] = v_f; }
+                    }
+                } else {
+                    const double2 *tp2 = reinterpret_cast<const double2 *>(reinterpret_cast<const CellTabCIC *>(A.tab) + cell);
+                    const double2 t0 = __ldg(tp2), t1 = __ldg(tp2 + 1);
+                    const double cap = __ldg(reinterpret_cast<const double *>(tp2 + 2));
+                    done = false;
+                    if (cap >= del_t) {                      // otherwise the sub-step cap splits the step: general path
+                        const double ls = l - (double)cell;
+                        const double r = del_t * t1.x;
+                        double l_prev = ls, lf = ls, d_half = ls, v_half = v;
+                        bool atB = false;
+                        int it;
+                        for (it = 1; it <= 50; ++it) {
+                            d_half = (ls + l_prev) * 0.5;
+                            const double accel = fma(t0.y, d_half, t0.x);
+                            v_half = fma(0.5 * accel, r, v);
+                            lf = fma(v_half, r, ls);
+                            atB = (lf <= 0.0) || (lf >= 1.0);
+                            if (atB) break;                  // reaches a face: the general path redoes this sub-step
+                            if (fabs(lf - l_prev) < 1.e-10) break;
+                            l_prev = lf;
+                        }
+                        if (!atB) {
+                            done = true;
+                            const double l_f = lf + (double)cell;
+                            if (MOVE) {
+                                nfev += (unsigned)it;
+                                A.l_out[gi] = l_f; A.vx_out[gi] = 2.0 * v_half - v;
+                            } else {
+                                const double Jp = l_f - l;
+                                deposit_add(W, D, lane, A.acc, cell, fx_from_double((1.0 - d_half) * Jp));
+                                deposit_add(W, D, lane, A.acc, cell + 1, fx_from_double(Jp * d_half));
+                            }
+                        }
+                    }
+                }
+                if (done) nsub += 1;
+                cont = !done;
+            }
+            const unsigned cm = __ballot_sync(FULL, cont);
+            if (cm) {
+                if (cont) {
+                    const int qq = qcount + __popc(cm & ((1u << lane) - 1u));
+                    W.ql[qq] = l; W.qv[qq] = v; W.qt[qq] = 0.0; W.qcell[qq] = cell; W.qpend[qq] = 0; W.qidx[qq] = gi;
+                }
+                qcount += __popc(cm);
+                __syncwarp();
+            }
+        }
+        drain_all = !next_ok;
     }
 
-    // ---------------- epilogue: windows, counters ----------------
-    if (!MOVE) window_flush(W, lane, base, dirty, A.acc);
+    // ---------------- epilogue: accumulators, counters ----------------
+    if (!MOVE) deposit_flush(W, D, lane, A.acc);
     {
         const unsigned s0 = __reduce_add_sync(FULL, nsub);
         if (lane == 0 && s0) atomicAdd(&A.counters[MOVE ? 5 : 0], (unsigned long long)s0);
@@ -448,61 +580,70 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
     }
 }
 
-static size_t push_smem_bytes(bool move, int Nh) {
-    (void)move; (void)Nh;
-    return (size_t)PUSH_WARPS * sizeof(WarpSmem);
-}
-
-template <int SCHEME, bool MOVE, bool TMA>
+template <int SCHEME, bool MOVE>
 static int launch_push_v(Ctx &c, const PushArgs &A) {
-    const size_t smem = push_smem_bytes(MOVE, A.Nh);
+    const size_t smem = (size_t)PUSH_WARPS * sizeof(WarpSmem);
     static bool configured = false;
     if (!configured) {
-        IPIC_CUDA(cudaFuncSetAttribute(k_push<SCHEME, MOVE, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IPIC_CUDA(cudaFuncSetAttribute(k_push<SCHEME, MOVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // leave the rest of the 256 KB to L1: the per-cell tables are gathered through it
+        IPIC_CUDA(cudaFuncSetAttribute(k_push<SCHEME, MOVE>, cudaFuncAttributePreferredSharedMemoryCarveout, 52));
         configured = true;
     }
+    IPIC_CUDA(cudaMemsetAsync(A.tile_counter, 0, sizeof(unsigned), c.stream));
     const int blocks = c.push_blocks > 0 ? c.push_blocks : c.num_sms;
-    c.launches += 1; k_push<SCHEME, MOVE, TMA><<<blocks, PUSH_THREADS, smem, c.stream>>>(A);
+    c.launches += 1; k_push<SCHEME, MOVE><<<blocks, PUSH_THREADS, smem, c.stream>>>(A);
     IPIC_CUDA(cudaGetLastError());
     return IPIC_OK;
 }
-template <int SCHEME, bool MOVE>
-static int launch_push_t(Ctx &c, const PushArgs &A) {
-    return c.use_tma ? launch_push_v<SCHEME, MOVE, true>(c, A) : launch_push_v<SCHEME, MOVE, false>(c, A);
-}
 
-static PushArgs make_push_args(Ctx &c, int sp, double del_t) {
+static int make_push_args(Ctx &c, int sp, double del_t, PushArgs &A) {
     SpeciesDev &s = c.sp[sp];
-    PushArgs A{};
+    if (s.n >= (1ll << 31)) { set_error("more than 2^31-1 particles of one species on one GPU"); return IPIC_ERR_UNSUPPORTED; }
+    A = PushArgs{};
     A.l = s.l; A.vx = s.vx; A.l_out = s.l; A.vx_out = s.vx;
     A.n = s.n;
     const int cells = (c.scheme == IPIC_SCHEME_NGP) ? c.Nh : c.Nx;
     const size_t tab_stride = (c.scheme == IPIC_SCHEME_NGP) ? sizeof(CellTabNGP) : sizeof(CellTabCIC);
     A.tab = (const char *)c.d_tab + (size_t)sp * (cells + 2) * tab_stride;
-    A.bc = c.d_bc;
-    A.acc = c.d_acc + (size_t)sp * (std::max(c.Nx, c.Nh) + 2);
+    const size_t NM = (size_t)std::max(c.Nx, c.Nh) + 2;
+    A.acc = c.d_acc + (size_t)sp * 2 * NM;
+    A.dacc = A.acc + NM;
+    {   // stride permutation of the tile order: an odd multiplier near the golden ratio, coprime with the tile count
+        const unsigned long long ntiles = ((unsigned long long)s.n + TILE - 1) / TILE;
+        unsigned long long st = (unsigned long long)(0.6180339887498949 * (double)ntiles) | 1ull;
+        auto gcd = [](unsigned long long a, unsigned long long b) { while (b) { unsigned long long t = a % b; a = b; b = t; } return a; };
+        while (ntiles > 1 && gcd(st, ntiles) != 1) st += 2;
+        A.tile_stride = (unsigned)(ntiles > 1 ? st % ntiles : 1);
+        if (c.tile_order == 0 || A.tile_stride == 0) A.tile_stride = 1;
+    }
     A.counters = c.d_counters + (size_t)sp * 8;
+    A.tile_counter = reinterpret_cast<unsigned *>(c.d_counters + (size_t)sp * 8 + 6);
     A.Nh = c.Nh;
     A.NB = (c.scheme == IPIC_SCHEME_NGP) ? c.Nx : c.Nh;
+    A.bcL = c.h_bc[0]; A.bcR = c.h_bc[c.nbc - 1];
     A.del_t = del_t;
     A.f_tol = del_t * ((c.scheme == IPIC_SCHEME_NGP) ? 1.e-15 : 1.e-10);   // NGP :79,172 ; CIC :90,208
-    A.refill_min = std::min(32, std::max(1, c.refill_min));
-    return A;
+    A.stay_min = std::min(32, std::max(1, c.stay_min));
+    return IPIC_OK;
 }
 
 int launch_deposit(Ctx &c, int sp, double del_t) {
-    if (c.Nh > MAX_GRID_SMEM) { set_error("N_h exceeds the shared-memory grid limit"); return IPIC_ERR_UNSUPPORTED; }
-    PushArgs A = make_push_args(c, sp, del_t);
+    PushArgs A;
+    int rc = make_push_args(c, sp, del_t, A);
+    if (rc) return rc;
     if (A.n == 0) return IPIC_OK;
-    if (c.scheme == IPIC_SCHEME_NGP) return launch_push_t<0, false>(c, A);
-    return launch_push_t<1, false>(c, A);
+    if (c.scheme == IPIC_SCHEME_NGP) return launch_push_v<0, false>(c, A);
+    return launch_push_v<1, false>(c, A);
 }
 
 int launch_move(Ctx &c, int sp, double del_t) {
-    PushArgs A = make_push_args(c, sp, del_t);
+    PushArgs A;
+    int rc = make_push_args(c, sp, del_t, A);
+    if (rc) return rc;
     if (A.n == 0) return IPIC_OK;
-    if (c.scheme == IPIC_SCHEME_NGP) return launch_push_t<0, true>(c, A);
-    return launch_push_t<1, true>(c, A);
+    if (c.scheme == IPIC_SCHEME_NGP) return launch_push_v<0, true>(c, A);
+    return launch_push_v<1, true>(c, A);
 }
 
 // =====================================================================================================
@@ -562,7 +703,7 @@ int launch_deposit_rho(Ctx &c, int sp) {
     if (s.n == 0) return IPIC_OK;
     if (c.Nx > MAX_GRID_SMEM) return IPIC_ERR_UNSUPPORTED;
     const size_t smem = (size_t)3 * (c.Nx + 2) * 4;
-    unsigned long long *acc = c.d_acc + (size_t)sp * (std::max(c.Nx, c.Nh) + 2);
+    unsigned long long *acc = c.d_acc + (size_t)sp * 2 * ((size_t)std::max(c.Nx, c.Nh) + 2);
     static bool cfg0 = false, cfg1 = false;
     if (c.scheme == IPIC_SCHEME_NGP) {
         if (!cfg0) { IPIC_CUDA(cudaFuncSetAttribute(k_deposit_rho<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (MAX_GRID_SMEM + 2) * 4)); cfg0 = true; }

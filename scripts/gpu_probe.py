@@ -90,7 +90,7 @@ elif stage in ("perf", "prof"):
         solver.synchronize()
         cu.cuProfilerStop()
         print("PROF DONE"); sys.exit(0)
-    for tma in (1, 0):
+    for tma in (1,):
         solver.set_option("use_tma", tma)
         timeit("sorted use_tma=%d" % tma)
     solver.set_option("use_tma", int(sys.argv[6]) if len(sys.argv) > 6 else 1)

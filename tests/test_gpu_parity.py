@@ -68,14 +68,16 @@ def test_depositJ(pair):
     assert relerr(Jg, Jo) < TOL_GRID, relerr(Jg, Jo)
     for sp, p in enumerate(plist):
         assert depositSubsteps(solver, p) == o.move_stats(sp)["substepsDeposit"]
-    # deterministic: bit-identical on repeat, for any refill threshold, and after a cell sort
+    # deterministic: bit-identical on repeat, for any scheduling of the sub-steps (register-loop threshold, tile order,
+    # grid size): the deposits are exact integers
     ip.depositJ(solver, plist, world, del_t)
     assert np.array_equal(solver.J, Jg)
-    for rm in (1, 32):
-        solver.set_option("refill_min", rm)
-        ip.depositJ(solver, plist, world, del_t)
-        assert np.array_equal(solver.J, Jg)
-    solver.set_option("refill_min", 8)
+    for name, vals, default in (("stay_min", (1, 32), 20), ("tile_order", (0,), 1), ("push_blocks", (1, 7), 0)):
+        for v in vals:
+            solver.set_option(name, v)
+            ip.depositJ(solver, plist, world, del_t)
+            assert np.array_equal(solver.J, Jg), (name, v)
+        solver.set_option(name, default)
 
 
 def test_ampere_solve(pair):
