@@ -753,20 +753,24 @@ __global__ void __launch_bounds__(RED_THREADS) k_moments(const double *__restric
     }
     block_reduce_store<4>(a, partial + (size_t)blockIdx.x * 4);
 }
+// fixed-order sum of per-block partials: each thread sums a strided subset, then a fixed tree over the block
 template <int NV>
-__global__ void k_final_sum(const double *partial, int nblocks, double *out) {
-    if (threadIdx.x < NV) {
-        double x = 0.0;
-        for (int b = 0; b < nblocks; ++b) x += partial[(size_t)b * NV + threadIdx.x];
-        out[threadIdx.x] = x;
+__global__ void __launch_bounds__(RED_THREADS) k_final_sum(const double *partial, int nblocks, double *out) {
+    double a[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) a[k] = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += RED_THREADS) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) a[k] += partial[(size_t)b * NV + k];
     }
+    block_reduce_store<NV>(a, out);
 }
 
 int particle_moments(Ctx &c, int sp, double out4[4]) {
     SpeciesDev &s = c.sp[sp];
     double *partial = c.d_work;   // needs RED_BLOCKS*4 doubles: allocated with slack in ipic_create
     c.launches += 1; k_moments<<<RED_BLOCKS, RED_THREADS, 0, c.stream>>>(s.l, s.vx, s.vy, s.vz, s.n, partial);
-    c.launches += 1; k_final_sum<4><<<1, 32, 0, c.stream>>>(partial, RED_BLOCKS, c.d_scal);
+    c.launches += 1; k_final_sum<4><<<1, RED_THREADS, 0, c.stream>>>(partial, RED_BLOCKS, c.d_scal);
     IPIC_CUDA(cudaGetLastError());
     IPIC_CUDA(cudaMemcpyAsync(c.h_scal, c.d_scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     IPIC_CUDA(cudaStreamSynchronize(c.stream));
@@ -934,7 +938,7 @@ int compact_species(Ctx &c, int sp) {
     long long *d_total = c.d_total; long long *d_slab = c.d_slab; const int cap_slab = c.cap_slab;
     c.launches += 1; k_compact_count<<<(unsigned)ntiles, CT_THREADS, 0, c.stream>>>(s.l, s.vx, s.vy, s.vz, n, d_tileCount, d_loss);
     c.launches += 1; k_scan_tiles<<<1, 1024, 0, c.stream>>>(d_tileCount, ntiles, d_tileOffset, d_total);
-    c.launches += 1; k_final_sum<4><<<1, 32, 0, c.stream>>>(d_loss, (int)ntiles, c.d_scal);
+    c.launches += 1; k_final_sum<4><<<1, RED_THREADS, 0, c.stream>>>(d_loss, (int)ntiles, c.d_scal);
     IPIC_CUDA(cudaGetLastError());
     long long total = 0;
     IPIC_CUDA(cudaMemcpyAsync(&total, d_total, sizeof(long long), cudaMemcpyDeviceToHost, c.stream));

@@ -280,3 +280,16 @@ def test_large_load_properties():
         assert sum(p.count() + p.delIdx for p in plist) == 2 * N
     finally:
         solver.close()
+
+
+def test_two_gpu_sharded_step_is_bitwise_single_gpu():
+    """needs >= 2 GPUs on the box: launches tests/multi_gpu_check.py under torchrun"""
+    import ctypes as C, os, subprocess, sys
+    n = C.c_int(0)
+    _lib.check(_lib.load().ipic_device_count(C.byref(n)))
+    if n.value < 2:
+        pytest.skip("one GPU on this box")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29517", os.path.join(root, "tests", "multi_gpu_check.py")], capture_output=True, text=True, timeout=280)
+    assert r.returncode == 0 and "MULTI-GPU CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
