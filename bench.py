@@ -200,6 +200,8 @@ def run_cuda_arm(args, w):
     torch.cuda.set_device(local_rank)
     dist = None
     if world_size > 1:
+        # stdout carries exactly one JSON line: whatever NCCL_DEBUG level the environment sets goes to a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/ipic_bench_nccl_%h_%p.log")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 

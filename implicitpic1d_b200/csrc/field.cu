@@ -649,7 +649,8 @@ static FieldArgs make_args(Ctx &c) {
 
 static int run_field(Ctx &c, const FieldArgs &A, unsigned ops) {
     const size_t smem = (size_t)2 * (std::max(c.Nx, c.Nh) + 2) * sizeof(double) + 4096 * sizeof(double);
-    static size_t configured = 0;
+    static size_t configured_dev[64] = {};    // function attributes are per device
+    size_t &configured = configured_dev[c.device & 63];
     if (smem > configured) {
         IPIC_CUDA(cudaFuncSetAttribute(k_field, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;

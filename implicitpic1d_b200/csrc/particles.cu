@@ -583,12 +583,12 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
 template <int SCHEME, bool MOVE>
 static int launch_push_v(Ctx &c, const PushArgs &A) {
     const size_t smem = (size_t)PUSH_WARPS * sizeof(WarpSmem);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};          // function attributes are per device
+    if (!configured[c.device & 63]) {
         IPIC_CUDA(cudaFuncSetAttribute(k_push<SCHEME, MOVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // leave the rest of the 256 KB to L1: the per-cell tables are gathered through it
         IPIC_CUDA(cudaFuncSetAttribute(k_push<SCHEME, MOVE>, cudaFuncAttributePreferredSharedMemoryCarveout, 52));
-        configured = true;
+        configured[c.device & 63] = true;
     }
     IPIC_CUDA(cudaMemsetAsync(A.tile_counter, 0, sizeof(unsigned), c.stream));
     const int blocks = c.push_blocks > 0 ? c.push_blocks : c.num_sms;
@@ -704,7 +704,8 @@ int launch_deposit_rho(Ctx &c, int sp) {
     if (c.Nx > MAX_GRID_SMEM) return IPIC_ERR_UNSUPPORTED;
     const size_t smem = (size_t)3 * (c.Nx + 2) * 4;
     unsigned long long *acc = c.d_acc + (size_t)sp * 2 * ((size_t)std::max(c.Nx, c.Nh) + 2);
-    static bool cfg0 = false, cfg1 = false;
+    static bool cfg0s[64] = {}, cfg1s[64] = {};   // function attributes are per device
+    bool &cfg0 = cfg0s[c.device & 63], &cfg1 = cfg1s[c.device & 63];
     if (c.scheme == IPIC_SCHEME_NGP) {
         if (!cfg0) { IPIC_CUDA(cudaFuncSetAttribute(k_deposit_rho<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (MAX_GRID_SMEM + 2) * 4)); cfg0 = true; }
         c.launches += 1; k_deposit_rho<0><<<c.num_sms, 1024, smem, c.stream>>>(s.l, s.n, c.d_bc, c.Nx, acc);

@@ -39,11 +39,11 @@ def build_oracle(d, factor=1):
                              factor=factor)
 
 
-def build_cuda_from_oracle(d, o, tridiag_mode=None):
+def build_cuda_from_oracle(d, o, tridiag_mode=None, device=0):
     """CUDA-side program state (main.f90:25-40) on the oracle's particle set."""
     world = readWorld(d["scheme"], d["Nx"], d["L"], d.get("gridType", 0), d.get("del_x", 0.0), d["bcL"], d["bcR"], int(d["smooth"]),
                       d["T_e"], d["n_ave"])
-    solver = ip.potentialSolver(world, d["Vl"], d["Vr"], d["rf"], 0.0)
+    solver = ip.potentialSolver(world, d["Vl"], d["Vr"], d["rf"], 0.0, device=device)
     if tridiag_mode is not None:
         solver.set_tridiag_mode(tridiag_mode)
     plist = []

@@ -26,7 +26,7 @@ def main():
         o = build_oracle(d)
         del_t = deck_del_t(d)
         # single-GPU result on this rank's GPU (no communicator)
-        w1, s1, p1 = build_cuda_from_oracle(d, o, tridiag_mode=_lib.TRIDIAG_THOMAS)
+        w1, s1, p1 = build_cuda_from_oracle(d, o, tridiag_mode=_lib.TRIDIAG_THOMAS, device=local)
         ip.depositJ(s1, p1, w1, del_t)
         J_single = s1.J
         r1 = ip.solvePotential(s1, p1, w1, del_t, del_t, del_t, 0.0)
