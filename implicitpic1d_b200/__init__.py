@@ -15,8 +15,8 @@ from .domain import Domain
 from .particle import Particle
 from .potential_solver import potentialSolver
 from .particle_mover import depositJ, moveParticles, allocateParticleMoverData
-from .nonlin_solvers import initializeSolver, solvePotential, solveDivAmpereAnderson, funcNitsol, SolverState
+from .nonlin_solvers import initializeSolver, solvePotential, solveDivAmpereAnderson, funcNitsol, SolverState, solveJFNK, nitsol, NitsolInfo
 from ._lib import IpicError, load as load_library, LIB_PATH
 
 __all__ = ["constants", "Domain", "Particle", "potentialSolver", "depositJ", "moveParticles", "allocateParticleMoverData",
-           "initializeSolver", "solvePotential", "solveDivAmpereAnderson", "funcNitsol", "SolverState", "IpicError", "load_library", "LIB_PATH"]
+           "initializeSolver", "solvePotential", "solveDivAmpereAnderson", "funcNitsol", "SolverState", "solveJFNK", "nitsol", "NitsolInfo", "IpicError", "load_library", "LIB_PATH"]

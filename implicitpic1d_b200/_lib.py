@@ -68,6 +68,9 @@ SIGNATURES = {
     "ipic_solve_div_ampere_anderson": (_i, [_p, _d]),
     "ipic_solve_potential": (_i, [_p, _d, _dp, _dp, _d]),
     "ipic_func_nitsol": (_i, [_p, _i32, _dp, _dp, _d]),
+    "ipic_solve_jfnk": (_i, [_p, _d]),
+    "ipic_get_nitsol_info": (_i, [_p, _ip]),
+    "ipic_nitsol_host": (_i, [_i32, _dp, C.CFUNCTYPE(C.c_int, C.c_int32, _dp, _dp, C.c_void_p), C.c_void_p, _d, _d, _d, _i32, _i32, _ip, _ip]),
     "ipic_get_solver_stats": (_i, [_p, C.POINTER(SolverStats)]),
     "ipic_get_norm_history": (_i, [_p, _dp, _i32, _ip]),
     "ipic_get_total_PE": (_i, [_p, _i, _dp]),

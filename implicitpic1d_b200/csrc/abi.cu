@@ -4,6 +4,7 @@
 // Reference semantics restated here (never copied): OpenMP/SharedModules/src/mod_nonLinSolvers.f90:41-215,
 // OpenMP/{NGP,CIC}/src/mod_potentialSolver.f90 (constructor, setRFVoltage, resetVoltage).
 #include "ipic_common.cuh"
+#include "nitsol.hpp"
 #include <cmath>
 #include <cstring>
 #include <dlfcn.h>
@@ -210,8 +211,65 @@ static int solve_div_ampere_anderson(Ctx &c, double del_t) {
     return IPIC_OK;   // loop exhausted: iterNumPicard left untouched, as in the reference
 }
 
-// adaptiveSolveDivAmpereAnderson  mod_nonLinSolvers.f90:162-196
+// funcNitsol  mod_nonLinSolvers.f90:218-239 : phi_f <- xcur ; depositJ ; solve_tridiag_Ampere ; fcur = xcur - phi_f
+// (host vectors in, host vectors out; phi_f is left holding G(xcur), as in the reference)
+static int residual_device(Ctx &c, double del_t, int n, const double *xcur, double *fcur) {
+    double *d_x = c.d_work, *d_f = c.d_work + (c.Nx + 2);
+    IPIC_CUDA(cudaMemcpyAsync(d_x, xcur, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    IPIC_CUDA(cudaMemcpyAsync(c.d_phi_f, d_x, n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+    { Timed t(c, "field_kernels"); RC(field_half_time_E(c)); }
+    RC(sweep_deposit(c, del_t));
+    {
+        Timed t(c, "field_kernels");
+        RC(field_finalize_J(c, del_t));
+        RC(field_ampere(c, del_t));
+        RC(field_residual(c, d_x, d_f));
+    }
+    IPIC_CUDA(cudaMemcpyAsync(fcur, d_f, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    IPIC_CUDA(cudaStreamSynchronize(c.stream));
+    return IPIC_OK;
+}
+
+// solveJFNK  mod_nonLinSolvers.f90:255-282
+static int solve_jfnk(Ctx &c, double del_t) {
+    auto *nit = static_cast<nitsol::Solver *>(c.nitsol_state);
+    if (!nit) { set_error("JFNK solver not initialised"); return IPIC_ERR_ARG; }
+    const int n = c.Nx;
+    RC(field_const_source(c));
+    std::vector<double> x(n);
+    IPIC_CUDA(cudaMemcpyAsync(x.data(), c.d_phi_f, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    IPIC_CUDA(cudaStreamSynchronize(c.stream));
+    int rc_dev = IPIC_OK;
+    c.normHist.clear();
+    nitsol::Residual f = [&](int nn, const double *xc, double *fc) -> int {
+        rc_dev = residual_device(c, del_t, nn, xc, fc);
+        return rc_dev == IPIC_OK ? 0 : 1;
+    };
+    nitsol::Info info;
+    const int iterm = nit->solve(n, x.data(), f, c.eps_a, c.eps_r, 1.e-12, info);
+    if (rc_dev != IPIC_OK) return rc_dev;
+    c.nitsol_info[0] = info.nfe; c.nitsol_info[1] = info.njve; c.nitsol_info[2] = info.nrpre;
+    c.nitsol_info[3] = info.nli; c.nitsol_info[4] = info.nni; c.nitsol_info[5] = info.nbt; c.nitsol_info[6] = iterm;
+    c.lastNorm = nit->fcurnrm;
+    switch (iterm) {
+    case 0:
+        c.iterNumPicard = info.nfe;
+        { Timed t(c, "field_kernels"); RC(field_half_time_E(c)); }
+        RC(move_all(c, del_t));
+        break;
+    case 1: case 5: case 6:
+        c.iterNumPicard = c.maxIter;
+        break;
+    default:
+        set_error("Nitsol error with iterm == " + std::to_string(iterm));
+        return IPIC_ERR_STOP;
+    }
+    return IPIC_OK;
+}
+
+// adaptiveSolveDivAmpereAnderson / adaptiveSolveDivAmpereJFNK  mod_nonLinSolvers.f90:162-196, 284-314
 static int adaptive_anderson(Ctx &c, double del_t, double &remainDel_t, double &currDel_t, double timeCurrent) {
+    auto solve_div_ampere_anderson = [](Ctx &cc, double dt) -> int { return cc.solverType == 0 ? ipic::solve_div_ampere_anderson(cc, dt) : solve_jfnk(cc, dt); };
     currDel_t = remainDel_t;
     if (c.RF_bool) RC(set_rf_voltage(c, timeCurrent + remainDel_t));
     RC(solve_div_ampere_anderson(c, remainDel_t));
@@ -288,6 +346,7 @@ int ipic_destroy(ipic_handle h) {
     for (auto &e : g_pool[c]) cudaEventDestroy(e);
     g_pool.erase(c); g_pending.erase(c);
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
+    delete static_cast<nitsol::Solver *>(c->nitsol_state);
     for (auto &s : c->sp) { if (s.l) cudaFree(s.l); if (s.l2) cudaFree(s.l2); }
     double *dp[] = {c->d_grid, c->d_dx, c->d_phi, c->d_phi_f, c->d_rho, c->d_J, c->d_E, c->d_a, c->d_b, c->d_c, c->d_cp, c->d_m, c->d_pcr, c->d_work,
                     c->d_rho_i, c->d_scal, c->d_phi_k, c->d_res_k, c->d_norms, c->d_loss};
@@ -469,6 +528,14 @@ int ipic_initialize_solver(ipic_handle h, double eps_a, double eps_r, int solver
     IPIC_CUDA(cudaMalloc(&c->d_phi_k, n * sizeof(double))); IPIC_CUDA(cudaMemset(c->d_phi_k, 0, n * sizeof(double)));
     IPIC_CUDA(cudaMalloc(&c->d_res_k, n * sizeof(double))); IPIC_CUDA(cudaMemset(c->d_res_k, 0, n * sizeof(double)));
     IPIC_CUDA(cudaMalloc(&c->d_norms, (m_Anderson + 2) * sizeof(double)));
+    // initializeNitsol(maxIter, m_Anderson, NumberXNodes)  mod_nonLinSolvers.f90:63-65
+    delete static_cast<nitsol::Solver *>(c->nitsol_state);
+    c->nitsol_state = nullptr;
+    if (solverType == 1) {
+        auto *nit = new nitsol::Solver();
+        nit->initialize(maxIter, m_Anderson, c->Nx);
+        c->nitsol_state = nit;
+    }
     return IPIC_OK;
 }
 
@@ -486,7 +553,6 @@ int ipic_solve_potential(ipic_handle h, double del_t, double *remainDel_t, doubl
     c->sweeps = 0; c->substeps = 0;
     RC(zero_counters(*c));
     RC(reset_voltage(*c));
-    if (c->solverType != 0) { set_error("solverType 1 (JFNK): drive NITSOL on the host with ipic_func_nitsol as the residual callback"); return IPIC_ERR_UNSUPPORTED; }
     // deposit sub-steps accumulate in device counter slot 0 over all sweeps; harvested after the step
     int rc = adaptive_anderson(*c, del_t, *remainDel_t, *currDel_t, timeCurrent);
     if (rc) return rc;
@@ -500,16 +566,32 @@ int ipic_solve_potential(ipic_handle h, double del_t, double *remainDel_t, doubl
 int ipic_func_nitsol(ipic_handle h, int32_t n, const double *xcur, double *fcur, double del_t) {
     CTX(h); NEED_SOLVER;
     if (n != c->Nx || !xcur || !fcur) return IPIC_ERR_ARG;
-    double *d_x = c->d_work, *d_f = c->d_work + (c->Nx + 2);
-    IPIC_CUDA(cudaMemcpyAsync(d_x, xcur, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    IPIC_CUDA(cudaMemcpyAsync(c->d_phi_f, d_x, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-    RC(field_half_time_E(*c));
-    RC(sweep_deposit(*c, del_t));
-    RC(field_finalize_J(*c, del_t));
-    RC(field_ampere(*c, del_t));
-    RC(field_residual(*c, d_x, d_f));
-    IPIC_CUDA(cudaMemcpyAsync(fcur, d_f, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    IPIC_CUDA(cudaStreamSynchronize(c->stream));
+    return residual_device(*c, del_t, n, xcur, fcur);
+}
+
+// solveJFNK  mod_nonLinSolvers.f90:255-282 (one Newton-Krylov solve at a fixed del_t, without the step halving)
+int ipic_solve_jfnk(ipic_handle h, double del_t) {
+    CTX(h); NEED_SOLVER;
+    RC(zero_counters(*c));
+    return solve_jfnk(*c, del_t);
+}
+int ipic_get_nitsol_info(ipic_handle h, int32_t *info7) {
+    CTX(h);
+    if (!info7) return IPIC_ERR_ARG;
+    for (int k = 0; k < 7; ++k) info7[k] = c->nitsol_info[k];
+    return IPIC_OK;
+}
+
+// nitsol  mod_nitsol.f90:2964-3443 on a host callback: the library's Newton-GMRES-backtracking driver for any F(x) = 0
+int ipic_nitsol_host(int32_t n, double *x, ipic_residual_fn f, void *user, double abstol, double reltol, double stptol, int32_t maxIter,
+                     int32_t kdmax, int32_t *info6, int32_t *iterm) {
+    if (n < 1 || !x || !f || !info6 || !iterm) { set_error("ipic_nitsol_host: bad argument"); return IPIC_ERR_ARG; }
+    nitsol::Solver nit;
+    nit.initialize(maxIter, kdmax, n);
+    nitsol::Info info;
+    nitsol::Residual fn = [&](int nn, const double *xc, double *fc) -> int { return f(nn, xc, fc, user); };
+    *iterm = nit.solve(n, x, fn, abstol, reltol, stptol, info);
+    info6[0] = info.nfe; info6[1] = info.njve; info6[2] = info.nrpre; info6[3] = info.nli; info6[4] = info.nni; info6[5] = info.nbt;
     return IPIC_OK;
 }
 

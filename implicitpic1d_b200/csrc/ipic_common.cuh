@@ -114,6 +114,8 @@ struct Ctx {
     double Beta_k = 0.5, eps_r = 0, eps_a = 1e-8;
     long long sweeps = 0, substeps = 0;
     std::vector<double> normHist;
+    void *nitsol_state = nullptr;                                 // nitsol::Solver (solverType 1)
+    int nitsol_info[7] = {0, 0, 0, 0, 0, 0, 0};                   // nfe, njve, nrpre, nli, nni, nbt, iterm of the last JFNK solve
     double lastNorm = 0;
     std::vector<SpeciesDev> sp;
     // options

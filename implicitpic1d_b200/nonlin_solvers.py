@@ -55,3 +55,47 @@ def funcNitsol(solver, particleList, xcur, del_t):
     f = np.zeros_like(x)
     _lib.check(_lib.load().ipic_func_nitsol(solver._h, x.size, x.ctypes.data_as(_lib._dp), f.ctypes.data_as(_lib._dp), del_t))
     return f
+
+
+class NitsolInfo:
+    """info(1:6) of nitsol (mod_nitsol.f90:3430-3435) + iterm"""
+
+    def __init__(self, v):
+        self.nfe, self.njve, self.nrpre, self.nli, self.nni, self.nbt, self.iterm = [int(x) for x in v]
+
+    def __repr__(self):
+        return "NitsolInfo(nfe=%d, njve=%d, nrpre=%d, nli=%d, nni=%d, nbt=%d, iterm=%d)" % (
+            self.nfe, self.njve, self.nrpre, self.nli, self.nni, self.nbt, self.iterm)
+
+
+def solveJFNK(solver, particleList, world, del_t):
+    """solveJFNK (mod_nonLinSolvers.f90:255-282): NITSOL on F(phi_f) = phi_f - G(phi_f), then moveParticles on success.
+    Needs initializeSolver(..., solverType=1, ...)."""
+    solver._bind(particleList)
+    _lib.check(_lib.load().ipic_solve_jfnk(solver._h, del_t))
+    for p in particleList:
+        p._refresh_stats()
+    v = np.zeros(7, dtype=np.int32)
+    _lib.check(_lib.load().ipic_get_nitsol_info(solver._h, v.ctypes.data_as(_lib._ip)))
+    return NitsolInfo(v)
+
+
+def nitsol(f, x0, abstol, reltol, stptol=1.e-12, maxIter=100, kdmax=10):
+    """The library's NITSOL driver on a host callback f(x) -> F(x) (numpy arrays); returns (x, NitsolInfo)."""
+    x = np.array(x0, dtype=np.float64)
+    n = x.size
+    CB = C.CFUNCTYPE(C.c_int, C.c_int32, _lib._dp, _lib._dp, C.c_void_p)
+
+    def cb(nn, px, pf, user):
+        try:
+            xv = np.ctypeslib.as_array(px, shape=(nn,))
+            fv = np.ctypeslib.as_array(pf, shape=(nn,))
+            fv[:] = f(xv.copy())
+            return 0
+        except Exception:
+            return 1
+    info = np.zeros(6, dtype=np.int32)
+    iterm = C.c_int32()
+    _lib.check(_lib.load().ipic_nitsol_host(n, x.ctypes.data_as(_lib._dp), CB(cb), None, abstol, reltol, stptol, maxIter, kdmax,
+                                            info.ctypes.data_as(_lib._ip), C.byref(iterm)))
+    return x, NitsolInfo(list(info) + [iterm.value])

@@ -149,6 +149,16 @@ int ipic_initialize_solver(ipic_handle h, double eps_a, double eps_r, int solver
 int ipic_solve_div_ampere_anderson(ipic_handle h, double del_t);
 int ipic_solve_potential(ipic_handle h, double del_t, double *remainDel_t, double *currDel_t, double timeCurrent);
 int ipic_func_nitsol(ipic_handle h, int32_t n, const double *xcur, double *fcur, double del_t);
+/* solveJFNK :255-282 (solverType 1; ipic_solve_potential adds the adaptive step halving of :284-314).
+ * info7 = nfe, njve, nrpre, nli, nni, nbt (mod_nitsol.f90:3430-3435) and iterm of the last solve. */
+int ipic_solve_jfnk(ipic_handle h, double del_t);
+int ipic_get_nitsol_info(ipic_handle h, int32_t *info7);
+/* nitsol (SharedModules/src/mod_nitsol.f90:2964-3443) with the settings of initializeNitsol (:128-140) on a HOST residual
+ * callback f(n, xcur, fcur, user) -> itrmf: the driver the JFNK path uses, exposed for hosts that want to keep their own
+ * residual (and for CPU tests of the solver logic).  maxIter -> input(1), kdmax -> input(4), input(6) = 2*kdmax. */
+typedef int (*ipic_residual_fn)(int32_t n, const double *xcur, double *fcur, void *user);
+int ipic_nitsol_host(int32_t n, double *x, ipic_residual_fn f, void *user, double abstol, double reltol, double stptol, int32_t maxIter,
+                     int32_t kdmax, int32_t *info6, int32_t *iterm);
 
 typedef struct {
     int32_t iterNumPicard, iterNumAdaptiveSteps, amountTimeSplits; /* mod_nonLinSolvers.f90:29 */

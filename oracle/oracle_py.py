@@ -265,6 +265,28 @@ class Oracle:
         n = self.L.orc_get_norm_history(self.h, _dp(o), 1024)
         return o[:n].copy()
 
+    # ---- JFNK (mod_nonLinSolvers.f90:218-282) with the numpy NITSOL restatement (oracle/nitsol_np.py)
+    def funcNitsol(self, xcur, del_t):
+        """fcur = xcur - G(xcur); leaves phi_f = G(xcur) like the reference (:226-236)"""
+        self.set("phi_f", xcur)
+        self.depositJ(del_t)
+        self.solve_tridiag_Ampere(del_t)
+        return np.asarray(xcur) - self.get("phi_f")
+
+    def solveJFNK(self, del_t, eps_a, eps_r, maxIter, m_Anderson):
+        from . import nitsol_np
+        self.makeConstSourceTerm()
+        nit = nitsol_np.Nitsol(maxIter, m_Anderson)
+        self.jfnk_substeps = 0
+        def f(x):
+            r = self.funcNitsol(x, del_t)
+            self.jfnk_substeps += sum(self.move_stats(sp)["substepsDeposit"] for sp in range(self.n_species))
+            return r
+        x, iterm = nit.solve(f, self.get("phi_f"), eps_a, eps_r, 1.e-12)
+        if iterm == 0:
+            self.moveParticles(del_t)
+        return dict(nit.info, iterm=iterm, fnorms=list(nit.fnorms))
+
     # ---- diagnostics (main.f90:58-114)
     def getTotalPE(self, future): return self.L.orc_total_PE(self.h, int(future))
     def getTotalKE(self, sp): return self.L.orc_total_KE(self.h, sp)
