@@ -7,8 +7,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libipic1d_b200.so")
 
 OK, ERR_ARG, ERR_CUDA, ERR_STOP, ERR_NOT_CONVERGED, ERR_UNSUPPORTED, ERR_NCCL = range(7)
-SCHEME_NGP, SCHEME_CIC = 0, 1
-F_PHI, F_PHI_F, F_J, F_RHO, F_EFIELD, F_A_TRI, F_B_TRI, F_C_TRI = range(8)
+SCHEME_NGP, SCHEME_CIC, SCHEME_NGP_PERIODIC = 0, 1, 2
+F_PHI, F_PHI_F, F_J, F_RHO, F_EFIELD, F_A_TRI, F_B_TRI, F_C_TRI, F_EFIELD_F, F_EFIELD_HALF = range(10)
 TRIDIAG_PCR, TRIDIAG_THOMAS = 0, 1
 
 

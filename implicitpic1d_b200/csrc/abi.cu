@@ -148,6 +148,7 @@ static int move_all(Ctx &c, double del_t) {
 
 // setRFVoltage: NGP mod_potentialSolver.f90:444-453 ; CIC :458-470
 static int set_rf_voltage(Ctx &c, double timeFuture) {
+    if (c.scheme == IPIC_SCHEME_NGP_PERIODIC) return IPIC_OK;    // empty routine in that tree (mod_potentialSolver.f90:244-248)
     const double v = c.RF_half_amplitude * std::sin(c.RF_rad_frequency * timeFuture);
     if (c.scheme == IPIC_SCHEME_NGP) {
         const int idx = (c.h_bc[0] == 4) ? 0 : c.Nx - 1;
@@ -164,6 +165,10 @@ static int set_rf_voltage(Ctx &c, double timeFuture) {
 
 // resetVoltage: NGP :455-459 ; CIC :472-478
 static int reset_voltage(Ctx &c) {
+    if (c.scheme == IPIC_SCHEME_NGP_PERIODIC) {                   // EField = EField_f (:283-286)
+        IPIC_CUDA(cudaMemcpyAsync(c.d_E, c.d_Ef, c.Nh * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+        return IPIC_OK;
+    }
     IPIC_CUDA(cudaMemcpyAsync(c.d_phi, c.d_phi_f, c.Nx * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
     if (c.scheme == IPIC_SCHEME_CIC && c.RF_bool) c.boundPhi[c.RF_indx - 1] = c.RF_voltage;
     return IPIC_OK;
@@ -181,8 +186,9 @@ static int solve_div_ampere_anderson(Ctx &c, double del_t) {
     { Timed t(c, "field_kernels"); RC(field_anderson_step(c, 0, 0, del_t, &status, &norm)); }
     normResidual[1] = norm;
     c.normHist.push_back(norm);
-    // eps_a * SQRT(real(NumberXNodes)): single-precision square root in the reference (:111)
-    const double eps_tol = c.eps_r * normResidual[1] + c.eps_a * (double)std::sqrt((float)c.Nx);
+    // eps_a * SQRT(real(NumberXNodes)): single-precision square root in the reference (:111); NGP_Periodic: N_h (:102)
+    const bool ef = (c.scheme == IPIC_SCHEME_NGP_PERIODIC);
+    const double eps_tol = c.eps_r * normResidual[1] + c.eps_a * (double)std::sqrt((float)(ef ? c.Nh : c.Nx));
     for (int i = 1; i <= c.maxIter; ++i) {
         const int index = fmodulo(i, M1) + 1;
         RC(sweep_deposit(c, del_t));
@@ -193,12 +199,15 @@ static int solve_div_ampere_anderson(Ctx &c, double del_t) {
         if (norm < eps_tol) {
             { Timed t(c, "field_kernels"); RC(field_anderson_step(c, i, 3, del_t, &status, &norm)); }
             RC(move_all(c, del_t));
-            c.iterNumPicard = i + 1;
+            c.iterNumPicard = ef ? i : i + 1;                     // NGP_Periodic :113
             return IPIC_OK;
         }
         if (i > m) {
             double sumPast;
-            if (m > 3) {
+            if (ef) {                                             // NGP_Periodic :116-123: mean of the last two
+                if (m > 1) sumPast = (normResidual[fmodulo(i - 1, M1) + 1] + normResidual[fmodulo(i - 2, M1) + 1]) / 2.0;
+                else sumPast = normResidual[fmodulo(i - 1, M1) + 1];
+            } else if (m > 3) {
                 sumPast = normResidual[fmodulo(i - 1, M1) + 1] + normResidual[fmodulo(i - 2, M1) + 1] + normResidual[fmodulo(i - 3, M1) + 1];
                 sumPast = sumPast / 3.0;
             } else {
@@ -216,7 +225,7 @@ static int solve_div_ampere_anderson(Ctx &c, double del_t) {
 static int residual_device(Ctx &c, double del_t, int n, const double *xcur, double *fcur) {
     double *d_x = c.d_work, *d_f = c.d_work + (c.Nx + 2);
     IPIC_CUDA(cudaMemcpyAsync(d_x, xcur, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
-    IPIC_CUDA(cudaMemcpyAsync(c.d_phi_f, d_x, n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+    IPIC_CUDA(cudaMemcpyAsync(c.scheme == IPIC_SCHEME_NGP_PERIODIC ? c.d_Ef : c.d_phi_f, d_x, n * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
     { Timed t(c, "field_kernels"); RC(field_half_time_E(c)); }
     RC(sweep_deposit(c, del_t));
     {
@@ -234,10 +243,11 @@ static int residual_device(Ctx &c, double del_t, int n, const double *xcur, doub
 static int solve_jfnk(Ctx &c, double del_t) {
     auto *nit = static_cast<nitsol::Solver *>(c.nitsol_state);
     if (!nit) { set_error("JFNK solver not initialised"); return IPIC_ERR_ARG; }
-    const int n = c.Nx;
+    const bool ef = (c.scheme == IPIC_SCHEME_NGP_PERIODIC);
+    const int n = ef ? c.Nh : c.Nx;
     RC(field_const_source(c));
     std::vector<double> x(n);
-    IPIC_CUDA(cudaMemcpyAsync(x.data(), c.d_phi_f, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    IPIC_CUDA(cudaMemcpyAsync(x.data(), ef ? c.d_Ef : c.d_phi_f, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     IPIC_CUDA(cudaStreamSynchronize(c.stream));
     int rc_dev = IPIC_OK;
     c.normHist.clear();
@@ -253,8 +263,13 @@ static int solve_jfnk(Ctx &c, double del_t) {
     c.lastNorm = nit->fcurnrm;
     switch (iterm) {
     case 0:
-        c.iterNumPicard = info.nfe;
+        c.iterNumPicard = ef ? info.nli : info.nfe;               // info(4) in NGP_Periodic (:251), info(1) otherwise (:271)
         { Timed t(c, "field_kernels"); RC(field_half_time_E(c)); }
+        if (ef) {                                                  // NGP_Periodic re-deposits J before the move (:252)
+            RC(sweep_deposit(c, del_t));
+            Timed t(c, "field_kernels");
+            RC(field_finalize_J(c, del_t));
+        }
         RC(move_all(c, del_t));
         break;
     case 1: case 5: case 6:
@@ -304,15 +319,20 @@ const char *ipic_last_error(void) { return g_err.c_str(); }
 int ipic_device_count(int *n) { IPIC_CUDA(cudaGetDeviceCount(n)); return IPIC_OK; }
 
 int ipic_create(ipic_handle *out, int scheme, int32_t Nx, const double *grid, const double *dx_dl, const int32_t *bc, int smooth, int device) {
-    if (!out || !grid || !dx_dl || !bc || Nx < 3 || (scheme != IPIC_SCHEME_NGP && scheme != IPIC_SCHEME_CIC)) { set_error("ipic_create: bad argument"); return IPIC_ERR_ARG; }
+    if (!out || !grid || !dx_dl || !bc || Nx < 3 || (scheme != IPIC_SCHEME_NGP && scheme != IPIC_SCHEME_CIC && scheme != IPIC_SCHEME_NGP_PERIODIC)) {
+        set_error("ipic_create: bad argument"); return IPIC_ERR_ARG;
+    }
     IPIC_CUDA(cudaSetDevice(device));
     Ctx *c = new Ctx();
     c->scheme = scheme; c->Nx = Nx; c->device = device; c->smooth = smooth ? 1 : 0;
-    c->Nh = (scheme == IPIC_SCHEME_NGP) ? Nx - 1 : Nx + 1;
-    c->nbc = (scheme == IPIC_SCHEME_NGP) ? Nx : c->Nh;
-    c->ndx = (scheme == IPIC_SCHEME_NGP) ? c->Nh : Nx;
+    const bool ngp_grid = (scheme != IPIC_SCHEME_CIC);
+    if (scheme == IPIC_SCHEME_NGP_PERIODIC) c->smooth = 0;   // that tree has no smoothing (mod_domain.f90 there has no smoothField)
+    c->Nh = ngp_grid ? Nx - 1 : Nx + 1;
+    c->nbc = ngp_grid ? Nx : c->Nh;
+    c->ndx = ngp_grid ? c->Nh : Nx;
     if (c->Nh > MAX_GRID_SMEM || Nx > MAX_GRID_SMEM) { delete c; set_error("grid larger than the shared-memory accumulator supports"); return IPIC_ERR_UNSUPPORTED; }
     c->h_grid.assign(grid, grid + Nx); c->h_dx.assign(dx_dl, dx_dl + c->ndx); c->h_bc.assign(bc, bc + c->nbc);
+    c->L_domain = ngp_grid ? grid[Nx - 1] - grid[0] : (grid[Nx - 1] + 0.5 * dx_dl[Nx - 1]) - (grid[0] - 0.5 * dx_dl[0]);
     cudaDeviceProp prop; IPIC_CUDA(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
     IPIC_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
@@ -325,6 +345,7 @@ int ipic_create(ipic_handle *out, int scheme, int32_t Nx, const double *grid, co
     IPIC_CUDA(cudaMemcpy(c->d_dx, dx_dl, c->ndx * sizeof(double), cudaMemcpyHostToDevice));
     IPIC_CUDA(cudaMemcpy(c->d_bc + 1, bc, c->nbc * sizeof(int), cudaMemcpyHostToDevice));   // d_bc is indexed 1-based (element 0 is padding)
     RC(dalloc(&c->d_phi, NM)); RC(dalloc(&c->d_phi_f, NM)); RC(dalloc(&c->d_rho, NM)); RC(dalloc(&c->d_J, NM)); RC(dalloc(&c->d_E, NM));
+    RC(dalloc(&c->d_Ef, NM)); RC(dalloc(&c->d_Eh, NM));
     RC(dalloc(&c->d_a, NM)); RC(dalloc(&c->d_b, NM)); RC(dalloc(&c->d_c, NM)); RC(dalloc(&c->d_cp, NM)); RC(dalloc(&c->d_m, NM));
     RC(dalloc(&c->d_work, std::max<size_t>(8 * NM, 8192))); RC(dalloc(&c->d_rho_i, NM)); RC(dalloc(&c->d_scal, 64));
     IPIC_CUDA(cudaMalloc(&c->d_acc, NSP_MAX * 2 * NM * sizeof(unsigned long long)));
@@ -349,7 +370,7 @@ int ipic_destroy(ipic_handle h) {
     delete static_cast<nitsol::Solver *>(c->nitsol_state);
     for (auto &s : c->sp) { if (s.l) cudaFree(s.l); if (s.l2) cudaFree(s.l2); }
     double *dp[] = {c->d_grid, c->d_dx, c->d_phi, c->d_phi_f, c->d_rho, c->d_J, c->d_E, c->d_a, c->d_b, c->d_c, c->d_cp, c->d_m, c->d_pcr, c->d_work,
-                    c->d_rho_i, c->d_scal, c->d_phi_k, c->d_res_k, c->d_norms, c->d_loss};
+                    c->d_rho_i, c->d_scal, c->d_phi_k, c->d_res_k, c->d_norms, c->d_loss, c->d_Ef, c->d_Eh};
     for (double *p : dp) if (p) cudaFree(p);
     if (c->d_bc) cudaFree(c->d_bc);
     if (c->d_acc) cudaFree(c->d_acc);
@@ -375,7 +396,21 @@ int ipic_init_solver(ipic_handle h, double leftVoltage, double rightVoltage, dou
     c->rho_const = 0.0; c->RF_half_amplitude = 0.0;
     c->RF_rad_frequency = 2.0 * pi * RF_frequency;
     c->boundPhi[0] = c->boundPhi[1] = 0.0; c->sourceTermVals[0] = c->sourceTermVals[1] = 0.0; c->RF_voltage = 0.0; c->RF_indx = 0;
-    if (c->scheme == IPIC_SCHEME_NGP) {
+    if (c->scheme == IPIC_SCHEME_NGP_PERIODIC) {
+        // potentialSolver_constructor  NGP_Periodic/src/mod_potentialSolver.f90:33-86
+        const int bl = c->h_bc[0], br = c->h_bc[Nx - 1];
+        if (bl == 1) phi[0] = leftVoltage;
+        if (bl == 4) c->RF_half_amplitude = leftVoltage;
+        if (br == 1) phi[Nx - 1] = rightVoltage;
+        if (br == 4) {
+            if (c->RF_half_amplitude != 0) { set_error("Half amplitude voltage for RF already set, have two RF boundaries!"); return IPIC_ERR_STOP; }
+            c->RF_half_amplitude = rightVoltage;
+        }
+        if (bl == 3) { phi[0] = leftVoltage; phi[Nx - 1] = leftVoltage; }
+        c->RF_bool = c->RF_rad_frequency > 0 && c->RF_half_amplitude > 0 && (bl == 4 || br == 4);
+        IPIC_CUDA(cudaMemset(c->d_Ef, 0, Nh * sizeof(double)));
+        IPIC_CUDA(cudaMemset(c->d_Eh, 0, Nh * sizeof(double)));
+    } else if (c->scheme == IPIC_SCHEME_NGP) {
         const int bl = c->h_bc[0], br = c->h_bc[Nx - 1];
         if (bl == 1) phi[0] = leftVoltage;
         if (bl == 4) { c->RF_half_amplitude = leftVoltage; phi[0] = c->RF_half_amplitude * std::sin(timeCurrent * c->RF_rad_frequency); }
@@ -457,6 +492,8 @@ static double *field_ptr(Ctx *c, int which, int *n) {
     case IPIC_F_A_TRI: *n = c->Nx - 1; return c->d_a;
     case IPIC_F_B_TRI: *n = c->Nx; return c->d_b;
     case IPIC_F_C_TRI: *n = c->Nx - 1; return c->d_c;
+    case IPIC_F_EFIELD_F: *n = c->Nh; return c->d_Ef;
+    case IPIC_F_EFIELD_HALF: *n = c->Nh; return c->d_Eh;
     }
     *n = 0; return nullptr;
 }
@@ -524,7 +561,7 @@ int ipic_initialize_solver(ipic_handle h, double eps_a, double eps_r, int solver
     if (m_Anderson < 1 || m_Anderson > 31) { set_error("m_Anderson must be in 1..31"); return IPIC_ERR_ARG; }
     c->eps_a = eps_a; c->eps_r = eps_r; c->solverType = solverType; c->m_Anderson = m_Anderson; c->Beta_k = Beta_k; c->maxIter = maxIter;
     if (c->d_phi_k) { cudaFree(c->d_phi_k); cudaFree(c->d_res_k); cudaFree(c->d_norms); }
-    const size_t n = (size_t)c->Nx * (m_Anderson + 1);
+    const size_t n = (size_t)(std::max(c->Nx, c->Nh) + 2) * (m_Anderson + 1);
     IPIC_CUDA(cudaMalloc(&c->d_phi_k, n * sizeof(double))); IPIC_CUDA(cudaMemset(c->d_phi_k, 0, n * sizeof(double)));
     IPIC_CUDA(cudaMalloc(&c->d_res_k, n * sizeof(double))); IPIC_CUDA(cudaMemset(c->d_res_k, 0, n * sizeof(double)));
     IPIC_CUDA(cudaMalloc(&c->d_norms, (m_Anderson + 2) * sizeof(double)));
@@ -533,7 +570,7 @@ int ipic_initialize_solver(ipic_handle h, double eps_a, double eps_r, int solver
     c->nitsol_state = nullptr;
     if (solverType == 1) {
         auto *nit = new nitsol::Solver();
-        nit->initialize(maxIter, m_Anderson, c->Nx);
+        nit->initialize(maxIter, m_Anderson, c->scheme == IPIC_SCHEME_NGP_PERIODIC ? c->Nh : c->Nx);
         c->nitsol_state = nit;
     }
     return IPIC_OK;
@@ -565,7 +602,7 @@ int ipic_solve_potential(ipic_handle h, double del_t, double *remainDel_t, doubl
 // funcNitsol  mod_nonLinSolvers.f90:218-239 : phi_f <- xcur ; depositJ ; solve_tridiag_Ampere ; fcur = xcur - phi_f
 int ipic_func_nitsol(ipic_handle h, int32_t n, const double *xcur, double *fcur, double del_t) {
     CTX(h); NEED_SOLVER;
-    if (n != c->Nx || !xcur || !fcur) return IPIC_ERR_ARG;
+    if (n != (c->scheme == IPIC_SCHEME_NGP_PERIODIC ? c->Nh : c->Nx) || !xcur || !fcur) return IPIC_ERR_ARG;
     return residual_device(*c, del_t, n, xcur, fcur);
 }
 

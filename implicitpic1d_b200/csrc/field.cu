@@ -26,7 +26,13 @@ enum : unsigned {
     OP_AND_MIX = 1u << 8,      // normal equations + next iterate -> phi_f
     OP_HALF_E = 1u << 9,       // EField + push tables
     OP_DIAG = 1u << 10,
-    OP_RESID_F = 1u << 11,     // f = x - phi_f  (funcNitsol)
+    OP_RESID_F = 1u << 11,     // f = x - unknown  (funcNitsol)
+    // NGP_Periodic (E-field form), OpenMP/NGP_Periodic/src/mod_potentialSolver.f90 / mod_Scheme.f90
+    OP_P_RHO = 1u << 12,       // depositRho epilogue: raw sums, no wall fix-ups, no smoothing
+    OP_P_POISSON = 1u << 13,   // solve_tridiag_Poisson + EField = -grad phi, EField_f = EField
+    OP_P_FINALIZE_J = 1u << 14,
+    OP_P_AMPERE = 1u << 15,    // EField_f = (<J> - J) del_t / eps_0 + EField
+    OP_P_HALF_E = 1u << 16,    // EField_half + push tables
 };
 
 struct FieldArgs {
@@ -38,6 +44,9 @@ struct FieldArgs {
     void *tab;
     double qw[NSP_MAX], qm[NSP_MAX];
     double del_t, rho_const, RF_voltage, bound1, bound2, src1, src2, poisson_rf_value;
+    double *Ef, *Eh;           // NGP_Periodic (E-field form): EField_f, EField_half
+    double *unk; int nunk;     // unknown of the nonlinear solve: phi_f (N_x) or EField_f (N_h)
+    double L_domain; int globJ;
     double *phi_k, *res_k, *norms;
     int and_i, and_m;          // loop index i and m_Anderson
     double beta;
@@ -364,21 +373,70 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
         __syncthreads();
     }
 
+
+    // ================= NGP_Periodic (E-field form) =================
+    // depositRho: NGP_Periodic/src/mod_Scheme.f90:57-70
+    if (ops & OP_P_RHO) {
+        dev_collect(A, s0, Nx, false, reinterpret_cast<long long *>(s1));
+        for (int i = threadIdx.x; i < Nx; i += FT) A.rho[i] = s0[i];
+        __syncthreads();
+    }
+    // solve_tridiag_Poisson: NGP_Periodic/src/mod_potentialSolver.f90:127-158
+    if (ops & OP_P_POISSON) {
+        for (int i = 1 + threadIdx.x; i <= Nx; i += FT) {
+            double d = 0.0;
+            switch (BC(i)) {
+            case 0: case 2: d = (-RHO(i) - A.rho_const) / eps_0; break;
+            case 1: case 3: d = PHI(i); break;
+            case 4: d = A.poisson_rf_value; break;
+            }
+            s0[i - 1] = d;
+        }
+        __syncthreads();
+        dev_tridiag(A, s0, s1);
+        for (int i = threadIdx.x; i < Nx; i += FT) { A.phi[i] = s0[i]; A.phi_f[i] = s0[i]; }
+        for (int i = 1 + threadIdx.x; i <= Nh; i += FT) {
+            const double e = (s0[i - 1] - s0[i]) / DX(i);
+            EF(i) = e; A.Ef[i - 1] = e;
+        }
+        __syncthreads();
+    }
+    // depositJ epilogue: NGP_Periodic/src/mod_particleMover.f90:131-134 (no smoothing)
+    if (ops & OP_P_FINALIZE_J) {
+        dev_collect(A, s0, Nh, true, reinterpret_cast<long long *>(s1));
+        for (int i = threadIdx.x; i < Nh; i += FT) A.J[i] = s0[i] / A.del_t;
+        __syncthreads();
+    }
+    // solve_tridiag_Ampere: :170-176
+    if (ops & OP_P_AMPERE) {
+        double aveJ = A.scal[2];
+        if (!A.globJ) {
+            double part = 0.0;
+            for (int i = 1 + threadIdx.x; i <= Nh; i += FT) part += JJ(i) * DX(i);
+            aveJ = block_sum(part) / A.L_domain;
+            if (threadIdx.x == 0) A.scal[2] = aveJ;
+        }
+        for (int i = 1 + threadIdx.x; i <= Nh; i += FT) A.Ef[i - 1] = (aveJ - JJ(i)) * A.del_t / eps_0 + EF(i);
+        __syncthreads();
+    }
+
     // ---------------- Anderson bookkeeping: mod_nonLinSolvers.f90:98-157 ----------------
     const int M1 = A.and_m + 1;
-#define PK(i, c) A.phi_k[(size_t)((c)-1) * Nx + (i)-1]
-#define RK(i, c) A.res_k[(size_t)((c)-1) * Nx + (i)-1]
+    const int NU = A.nunk;                 // N_x (phi_f) or N_h (EField_f)
+#define PK(i, c) A.phi_k[(size_t)((c)-1) * NU + (i)-1]
+#define RK(i, c) A.res_k[(size_t)((c)-1) * NU + (i)-1]
+#define UNK(i) A.unk[(i)-1]
     if (ops & OP_AND_STORE0) {
-        for (int i = 1 + threadIdx.x; i <= Nx; i += FT) PK(i, 1) = PHIF(i);
+        for (int i = 1 + threadIdx.x; i <= NU; i += FT) PK(i, 1) = UNK(i);
         __syncthreads();
     }
     if (ops & (OP_AND_FIRST | OP_AND_RESID)) {
         const int index = (ops & OP_AND_FIRST) ? 1 : fmodulo(A.and_i, M1) + 1;
         double part = 0.0;
-        for (int i = 1 + threadIdx.x; i <= Nx; i += FT) {
+        for (int i = 1 + threadIdx.x; i <= NU; i += FT) {
             double r;
-            if (ops & OP_AND_FIRST) { PK(i, 2) = PHIF(i); r = PHIF(i) - PK(i, 1); }
-            else r = PHIF(i) - PK(i, index);
+            if (ops & OP_AND_FIRST) { PK(i, 2) = UNK(i); r = UNK(i) - PK(i, 1); }
+            else r = UNK(i) - PK(i, index);
             RK(i, index) = r;
             part += r * r;
         }
@@ -402,7 +460,7 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
             const int cj = fmodulo(i - m_k + j, M1) + 1;
             const int ck = (k >= 0) ? fmodulo(i - m_k + k, M1) + 1 : 0;
             double acc = 0.0;
-            for (int r = 1 + lane; r <= Nx; r += 32) {
+            for (int r = 1 + lane; r <= NU; r += 32) {
                 const double ri = RK(r, index);
                 const double fj = ri - RK(r, cj);
                 const double fk = (k >= 0) ? (ri - RK(r, ck)) : ri;
@@ -437,22 +495,23 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
         }
         __syncthreads();
         const int cn = fmodulo(i + 1, M1) + 1, c0 = fmodulo(i - m_k, M1) + 1;
-        for (int r = 1 + threadIdx.x; r <= Nx; r += FT) {
+        for (int r = 1 + threadIdx.x; r <= NU; r += FT) {
             double x = alpha[0] * (A.beta * RK(r, c0) + PK(r, c0));
             for (int j = 1; j <= m_k; ++j) {
                 const int cj = fmodulo(i - m_k + j, M1) + 1;
                 x = x + alpha[j] * (A.beta * RK(r, cj) + PK(r, cj));
             }
             PK(r, cn) = x;
-            PHIF(r) = x;
+            UNK(r) = x;
         }
         __syncthreads();
     }
 #undef PK
 #undef RK
+#undef UNK
 
-    if (ops & OP_RESID_F) {   // funcNitsol: fcur = xcur - phi_f   (mod_nonLinSolvers.f90:236)
-        for (int i = threadIdx.x; i < Nx; i += FT) A.fout[i] = A.xin[i] - A.phi_f[i];
+    if (ops & OP_RESID_F) {   // funcNitsol: fcur = xcur - unknown   (mod_nonLinSolvers.f90:236 ; NGP_Periodic :219)
+        for (int i = threadIdx.x; i < NU; i += FT) A.fout[i] = A.xin[i] - A.unk[i];
         __syncthreads();
     }
 
@@ -522,11 +581,61 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
         __syncthreads();
     }
 
+
+    // EField_half = 0.5 (EField + EField_f) (NGP_Periodic/src/mod_particleMover.f90:72) + push tables
+    if (ops & OP_P_HALF_E) {
+        for (int i = threadIdx.x; i < Nh; i += FT) A.Eh[i] = 0.5 * (A.E[i] + A.Ef[i]);
+        __syncthreads();
+        for (int s = 0; s < A.nsp; ++s) {
+            CellTabNGP *T = reinterpret_cast<CellTabNGP *>(A.tab) + (size_t)s * A.tab_cells;
+            for (int cI = 1 + threadIdx.x; cI <= Nh; cI += FT) {
+                const double a = A.qm[s] * A.Eh[cI - 1], dx = DX(cI);
+                CellTabNGP t;
+                t.a = a; t.hinv = 0.5 / dx; t.two_a_dx = 2.0 * a * dx; t.inv_a = 1.0 / a;
+                T[cI] = t;
+            }
+        }
+        __syncthreads();
+    }
+
     // ---------------- conservation diagnostics ----------------
     if (ops & OP_DIAG) {
         const int wch = A.diag_which;
         double part = 0.0, res = 0.0;
-        if (wch == 0 || wch == 1) {   // getTotalPE(future = wch): NGP :408-420 ; CIC :369-413
+        if ((wch == 0 || wch == 1) && A.scheme == 2) {   // getTotalPE: NGP_Periodic :226-236
+            const double *Ev = wch ? A.Ef : A.E;
+            for (int i = 1 + threadIdx.x; i <= Nh; i += FT) part += Ev[i - 1] * Ev[i - 1] * DX(i);
+            res = 0.5 * eps_0 * block_sum(part);
+        } else if (wch == 4 && A.scheme == 2) {          // getError_tridiag_Poisson: NGP_Periodic :159-169
+            for (int i = 1 + threadIdx.x; i <= Nh; i += FT) {
+                double r;
+                if (i == 1) r = eps_0 * (A.Ef[0] - A.Ef[Nh - 1]) / (RHO(1) + RHO(Nx)) - 1.0;
+                else r = eps_0 * (A.Ef[i - 1] - A.Ef[i - 2]) / RHO(i) - 1.0;
+                part += r * r;
+            }
+            res = sqrt(block_sum(part) / Nh);
+        } else if (wch == 5 && A.scheme == 2) {          // getChargeContinuityError: NGP_Periodic :187-225
+            double cnt = 0.0;
+            for (int i = 1 + threadIdx.x; i <= Nx; i += FT) {
+                double dR = RHO(i) - A.rho_i[i - 1];
+                if (dR != 0) {
+                    switch (BC(i)) {
+                    case 0: { const double v = 1.0 + A.del_t * (JJ(i) - JJ(i - 1)) / dR; part += v * v; cnt += 1.0; break; }
+                    case 2: {
+                        const double v = (i == 1) ? 1.0 + A.del_t * JJ(1) / dR : 1.0 - A.del_t * JJ(Nh) / dR;
+                        part += v * v; cnt += 1.0; break; }
+                    case 3:
+                        if (i == 1) { dR = dR + RHO(Nx) - A.rho_i[Nx - 1]; const double v = 1.0 + A.del_t * (JJ(1) - JJ(Nh)) / dR; part += v * v; }
+                        break;
+                    }
+                }
+            }
+            const double tot = block_sum(part);
+            const double k = block_sum(cnt);
+            res = sqrt(tot / k);
+        } else if (wch == 3 && A.scheme == 2) {          // getEnergyFromBoundary: NGP_Periodic :237-243
+            res = 0.0;
+        } else if (wch == 0 || wch == 1) {   // getTotalPE(future = wch): NGP :408-420 ; CIC :369-413
             const double *ph = wch ? A.phi_f : A.phi;
             if (A.scheme == 0) {
                 for (int i = 1 + threadIdx.x; i <= Nh; i += FT) { const double dphi = ph[i] - ph[i - 1]; part += dphi * dphi / DX(i); }
@@ -634,7 +743,7 @@ static FieldArgs make_args(Ctx &c) {
     A.scheme = c.scheme; A.Nx = c.Nx; A.Nh = c.Nh; A.smooth = c.smooth; A.nsp = (int)c.sp.size();
     A.tridiag_mode = c.tridiag_mode; A.pcr_levels = c.pcr_levels;
     A.acc_stride = 2 * (std::max(c.Nx, c.Nh) + 2);
-    A.tab_cells = ((c.scheme == IPIC_SCHEME_NGP) ? c.Nh : c.Nx) + 2;
+    A.tab_cells = ((c.scheme == IPIC_SCHEME_CIC) ? c.Nx : c.Nh) + 2;
     A.grid = c.d_grid; A.dx = c.d_dx; A.bc = c.d_bc;
     A.phi = c.d_phi; A.phi_f = c.d_phi_f; A.rho = c.d_rho; A.J = c.d_J; A.E = c.d_E;
     A.a = c.d_a; A.b = c.d_b; A.c = c.d_c; A.cp = c.d_cp; A.m = c.d_m; A.pcr = c.d_pcr;
@@ -642,6 +751,10 @@ static FieldArgs make_args(Ctx &c) {
     for (int s = 0; s < A.nsp && s < NSP_MAX; ++s) { A.qw[s] = c.sp[s].q_times_wp; A.qm[s] = c.sp[s].q_over_m; }
     A.rho_const = c.rho_const; A.RF_voltage = c.RF_voltage;
     A.bound1 = c.boundPhi[0]; A.bound2 = c.boundPhi[1]; A.src1 = c.sourceTermVals[0]; A.src2 = c.sourceTermVals[1];
+    A.Ef = c.d_Ef; A.Eh = c.d_Eh;
+    A.unk = (c.scheme == IPIC_SCHEME_NGP_PERIODIC) ? c.d_Ef : c.d_phi_f;
+    A.nunk = (c.scheme == IPIC_SCHEME_NGP_PERIODIC) ? c.Nh : c.Nx;
+    A.L_domain = c.L_domain; A.globJ = 0;
     A.phi_k = c.d_phi_k; A.res_k = c.d_res_k; A.norms = c.d_norms;
     A.and_m = c.m_Anderson; A.beta = c.Beta_k;
     return A;
@@ -666,7 +779,9 @@ int field_setup(Ctx &c) {
     std::vector<double> a(Nx + 2, 0.0), b(Nx + 2, 0.0), cc(Nx + 2, 0.0);   // 1-based
     auto DXh = [&](int i) -> double { return (i >= 1 && i <= c.ndx) ? c.h_dx[i - 1] : 1.0; };
     auto BCh = [&](int i) -> int { return c.h_bc[i - 1]; };
-    if (c.scheme == IPIC_SCHEME_NGP) {
+    if (c.scheme == IPIC_SCHEME_NGP || c.scheme == IPIC_SCHEME_NGP_PERIODIC) {
+        // NGP_Periodic/src/mod_potentialSolver.f90:88-126 differs only in the Neumann rows (factor 1 instead of 2)
+        const double nf = (c.scheme == IPIC_SCHEME_NGP) ? 2.0 : 1.0;
         for (int i = 1; i <= Nx; ++i) {
             switch (BCh(i)) {
             case 0:
@@ -676,8 +791,8 @@ int field_setup(Ctx &c) {
                 break;
             case 1: case 4: b[i] = 1.0; break;
             case 2:
-                if (i == 1) { cc[i] = 2.0 / DXh(i); b[i] = -(2.0 / DXh(i)); }
-                else if (i == Nx) { a[i - 1] = 2.0 / DXh(i - 1); b[i] = -(2.0 / DXh(i - 1)); }
+                if (i == 1) { cc[i] = nf / DXh(i); b[i] = -(nf / DXh(i)); }
+                else if (i == Nx) { a[i - 1] = nf / DXh(i - 1); b[i] = -(nf / DXh(i - 1)); }
                 else { set_error("Neumann boundary not on left or right most index!"); return IPIC_ERR_STOP; }
                 break;
             case 3: b[i] = 1.0; break;
@@ -751,7 +866,8 @@ int field_setup(Ctx &c) {
     return IPIC_OK;
 }
 
-int field_finalize_rho(Ctx &c) { FieldArgs A = make_args(c); return run_field(c, A, OP_FINALIZE_RHO); }
+static bool eform(const Ctx &c) { return c.scheme == IPIC_SCHEME_NGP_PERIODIC; }
+int field_finalize_rho(Ctx &c) { FieldArgs A = make_args(c); return run_field(c, A, eform(c) ? OP_P_RHO : OP_FINALIZE_RHO); }
 
 int field_poisson(Ctx &c, double timeCurrent) {
     // CIC: RF wall value refreshed first (:181-189)
@@ -762,13 +878,13 @@ int field_poisson(Ctx &c, double timeCurrent) {
     }
     FieldArgs A = make_args(c);
     A.poisson_rf_value = c.RF_half_amplitude * std::sin(c.RF_rad_frequency * timeCurrent);
-    return run_field(c, A, OP_POISSON);
+    return run_field(c, A, eform(c) ? OP_P_POISSON : OP_POISSON);
 }
 
-int field_const_source(Ctx &c) { FieldArgs A = make_args(c); return run_field(c, A, OP_CONST_SOURCE); }
-int field_half_time_E(Ctx &c) { FieldArgs A = make_args(c); return run_field(c, A, OP_HALF_E); }
-int field_finalize_J(Ctx &c, double del_t) { FieldArgs A = make_args(c); A.del_t = del_t; return run_field(c, A, OP_FINALIZE_J); }
-int field_ampere(Ctx &c, double del_t) { FieldArgs A = make_args(c); A.del_t = del_t; return run_field(c, A, OP_AMPERE); }
+int field_const_source(Ctx &c) { if (eform(c)) return IPIC_OK; FieldArgs A = make_args(c); return run_field(c, A, OP_CONST_SOURCE); }
+int field_half_time_E(Ctx &c) { FieldArgs A = make_args(c); return run_field(c, A, eform(c) ? OP_P_HALF_E : OP_HALF_E); }
+int field_finalize_J(Ctx &c, double del_t) { FieldArgs A = make_args(c); A.del_t = del_t; return run_field(c, A, eform(c) ? OP_P_FINALIZE_J : OP_FINALIZE_J); }
+int field_ampere(Ctx &c, double del_t) { FieldArgs A = make_args(c); A.del_t = del_t; return run_field(c, A, eform(c) ? OP_P_AMPERE : OP_AMPERE); }
 
 int field_diag(Ctx &c, int which, double del_t, double *out) {
     FieldArgs A = make_args(c);
@@ -783,6 +899,7 @@ int field_diag(Ctx &c, int which, double del_t, double *out) {
 
 int field_anderson_begin(Ctx &c) {
     FieldArgs A = make_args(c);
+    if (eform(c)) return run_field(c, A, OP_AND_STORE0 | OP_P_HALF_E);
     return run_field(c, A, OP_CONST_SOURCE | OP_AND_STORE0 | OP_HALF_E);
 }
 
@@ -794,10 +911,11 @@ int field_anderson_step(Ctx &c, int i, int phase, double del_t, int *status, dou
     FieldArgs A = make_args(c);
     A.del_t = del_t; A.and_i = i;
     unsigned ops = 0;
-    if (phase == 0) ops = OP_FINALIZE_J | OP_AMPERE | OP_AND_FIRST | OP_HALF_E;
-    else if (phase == 1) ops = OP_FINALIZE_J | OP_AMPERE | OP_AND_RESID;
-    else if (phase == 2) ops = OP_AND_MIX | OP_HALF_E;
-    else ops = OP_HALF_E;
+    const unsigned fj = eform(c) ? OP_P_FINALIZE_J : OP_FINALIZE_J, am = eform(c) ? OP_P_AMPERE : OP_AMPERE, he = eform(c) ? OP_P_HALF_E : OP_HALF_E;
+    if (phase == 0) ops = fj | am | OP_AND_FIRST | he;
+    else if (phase == 1) ops = fj | am | OP_AND_RESID;
+    else if (phase == 2) ops = OP_AND_MIX | he;
+    else ops = he;
     int rc = run_field(c, A, ops);
     if (rc) return rc;
     if (phase <= 1) {

@@ -89,6 +89,8 @@ struct Ctx {
     std::vector<int> h_bc;
     // field vectors (device)
     double *d_phi = nullptr, *d_phi_f = nullptr, *d_rho = nullptr, *d_J = nullptr, *d_E = nullptr;
+    double *d_Ef = nullptr, *d_Eh = nullptr;                      // NGP_Periodic: EField_f, EField_half
+    double L_domain = 0.0;
     double *d_a = nullptr, *d_b = nullptr, *d_c = nullptr;       // tridiagonal
     double *d_cp = nullptr, *d_m = nullptr;                       // Thomas: c' and pivots m_i (constant matrix)
     double *d_pcr = nullptr; int pcr_levels = 0;                  // PCR level coefficients [levels][2][Nx] + inv diag [Nx]

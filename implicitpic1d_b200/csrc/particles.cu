@@ -322,21 +322,24 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
                     double dtau = del_t - tp;
                     bool atB;
                     int lb = 0;
-                    if (SCHEME == 0) {
-                        // particleSubStepNoBField (mod_particleMover.f90:21-63), written flat: the three outcomes
-                        // (reaches the face ahead / leaves through the face behind / stays in the cell) are selected,
-                        // not branched on, so the common face-to-face transit runs without divergence.
+                    if (SCHEME != 1) {
+                        // particleSubStepNoBField (mod_particleMover.f90:21-63 ; NGP_Periodic/src/mod_particleMover.f90:18-59),
+                        // written flat: the three outcomes (reaches the face ahead / leaves through the face behind / stays in
+                        // the cell) are selected, not branched on, so the common face-to-face transit runs without divergence.
+                        // SCHEME 2 works in cell-local coordinates (l - l_cell in [0,1]) exactly as that tree does.
                         const double2 *tp2 = reinterpret_cast<const double2 *>(reinterpret_cast<const CellTabNGP *>(A.tab) + cell);
                         const double2 t0 = __ldg(tp2), t1 = __ldg(tp2 + 1);
                         const double a = t0.x, hinv = t0.y, two_a_dx = t1.x, inv_a = t1.y;
+                        const double lc = (SCHEME == 2) ? (double)cell : 0.0;       // origin of the working coordinate
+                        const double lw = l - lc;
                         const double v_f0 = fma(a, dtau, v);
-                        const double l_f0 = fma((v + v_f0) * dtau, hinv, l);
-                        const bool inCell = ((int)l_f0 == cell);
+                        const double l_f0 = fma((v + v_f0) * dtau, hinv, lw);
+                        const bool inCell = (SCHEME == 2) ? ((int)(l_f0 + 1.0) == 1) : ((int)l_f0 == cell);
                         const bool vpos = v > 0.0;
                         const bool eqSign = (vpos == (v_f0 > 0.0));
                         const double v2 = v * v;
                         lb = cell + (vpos ? 1 : 0);
-                        double diff_PE = two_a_dx * ((double)lb - l);
+                        double diff_PE = two_a_dx * (((double)lb - lc) - lw);
                         const bool maybeB = !(inCell && eqSign);
                         const bool fwd = maybeB && (diff_PE > -v2);
                         const bool bwd = maybeB && !fwd && !inCell;
@@ -344,17 +347,19 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
                         double sgn = v;
                         if (bwd) {
                             lb = 2 * cell + 1 - lb;
-                            diff_PE = two_a_dx * ((double)lb - l);
+                            diff_PE = two_a_dx * (((double)lb - lc) - lw);
                             sgn = -v;
                         }
-                        v_f = v_f0; l_f = l_f0;
+                        v_f = v_f0;
+                        double l_fw = l_f0;
                         if (atB) {
-                            l_f = (double)lb;
+                            l_fw = (double)lb - lc;
                             v_f = copysign(sqrt(diff_PE + v2), sgn);
                             dtau = (v_f - v) * inv_a;
                         }
+                        l_f = l_fw + lc;
                         if (!MOVE) {
-                            const double dl = l_f - l;
+                            const double dl = l_fw - lw;
                             const bool full = (fabs(dl) == 1.0);
                             const bool right = dl > 0.0;
                             if (pend != 0 && !(full && ((pend > 0) == right))) { close_run(W, D, lane, A, pend, cell); pend = 0; }
@@ -411,7 +416,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
                             cell += signbit(v_f) ? -1 : 1;
                         } else {
                             const int b = (lb == 1) ? A.bcL : A.bcR;
-                            if (!MOVE && SCHEME == 0 && b != 0 && pend != 0) {
+                            if (!MOVE && SCHEME != 1 && b != 0 && pend != 0) {
                                 // a run that ends on a wall includes the wall cell: the particle does not move on to a new cell
                                 close_run(W, D, lane, A, pend, cell + (pend > 0 ? 1 : -1));
                                 pend = 0;
@@ -447,7 +452,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
                             A.l_out[gi] = l_f;
                             A.vx_out[gi] = v_f;
                         }
-                        if (!MOVE && SCHEME == 0 && pend != 0) close_run(W, D, lane, A, pend, cell);
+                        if (!MOVE && SCHEME != 1 && pend != 0) close_run(W, D, lane, A, pend, cell);
                     } else {
                         cont = true;
                     }
@@ -489,8 +494,11 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
             const double l = cl[b], v = cv[b];
             const unsigned gi = g0 + 32u * b + lane;
             const bool valid = (gi < n) && (l >= 0.0);      // l < 0 marks a particle absorbed earlier and not yet compacted
-            // l_cell = INT(l_sub + SIGN(1.d-12, v_sub))
-            const int cell = (int)(l + copysign(1.e-12, v));
+            // l_cell = INT(l_sub + SIGN(1.d-12, v_sub)) ; NGP_Periodic: INT(l_sub), minus one for a left-mover sitting exactly on a
+            // face (mod_particleMover.f90:84,91-95 there)
+            int cell;
+            if (SCHEME == 2) { cell = (int)l; if ((double)cell == l && signbit(v)) cell -= 1; }
+            else cell = (int)(l + copysign(1.e-12, v));
             if (!MOVE && b == 0) {
                 // follow the stream: re-centre the accumulators on the cell of the sub-tile's first particle
                 const int nb = __shfl_sync(FULL, cell, 0);
@@ -502,14 +510,16 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
             bool cont = false;
             if (valid) {
                 bool done;
-                if (SCHEME == 0) {
+                if (SCHEME != 1) {
                     const double2 t0 = __ldg(reinterpret_cast<const double2 *>(reinterpret_cast<const CellTabNGP *>(A.tab) + cell));
+                    const double lc = (SCHEME == 2) ? (double)cell : 0.0;
+                    const double lw = l - lc;
                     const double v_f = fma(t0.x, del_t, v);
-                    const double l_f = fma((v + v_f) * del_t, t0.y, l);
-                    done = ((int)l_f == cell) && ((v > 0.0) == (v_f > 0.0));
+                    const double l_fw = fma((v + v_f) * del_t, t0.y, lw);
+                    done = ((SCHEME == 2) ? ((int)(l_fw + 1.0) == 1) : ((int)l_fw == cell)) && ((v > 0.0) == (v_f > 0.0));
                     if (done) {
-                        if (!MOVE) deposit_add(W, D, lane, A.acc, cell, fx_from_double(l_f - l));
-                        else { A.l_out[gi] = l_f; A.vx_out[gi] = v_f; }
+                        if (!MOVE) deposit_add(W, D, lane, A.acc, cell, fx_from_double(l_fw - lw));
+                        else { A.l_out[gi] = l_fw + lc; A.vx_out[gi] = v_f; }
                     }
                 } else {
                     const double2 *tp2 = reinterpret_cast<const double2 *>(reinterpret_cast<const CellTabCIC *>(A.tab) + cell);
@@ -603,8 +613,8 @@ static int make_push_args(Ctx &c, int sp, double del_t, PushArgs &A) {
     A = PushArgs{};
     A.l = s.l; A.vx = s.vx; A.l_out = s.l; A.vx_out = s.vx;
     A.n = s.n;
-    const int cells = (c.scheme == IPIC_SCHEME_NGP) ? c.Nh : c.Nx;
-    const size_t tab_stride = (c.scheme == IPIC_SCHEME_NGP) ? sizeof(CellTabNGP) : sizeof(CellTabCIC);
+    const int cells = (c.scheme == IPIC_SCHEME_CIC) ? c.Nx : c.Nh;
+    const size_t tab_stride = (c.scheme == IPIC_SCHEME_CIC) ? sizeof(CellTabCIC) : sizeof(CellTabNGP);
     A.tab = (const char *)c.d_tab + (size_t)sp * (cells + 2) * tab_stride;
     const size_t NM = (size_t)std::max(c.Nx, c.Nh) + 2;
     A.acc = c.d_acc + (size_t)sp * 2 * NM;
@@ -620,10 +630,11 @@ static int make_push_args(Ctx &c, int sp, double del_t, PushArgs &A) {
     A.counters = c.d_counters + (size_t)sp * 8;
     A.tile_counter = reinterpret_cast<unsigned *>(c.d_counters + (size_t)sp * 8 + 6);
     A.Nh = c.Nh;
-    A.NB = (c.scheme == IPIC_SCHEME_NGP) ? c.Nx : c.Nh;
+    A.NB = (c.scheme == IPIC_SCHEME_CIC) ? c.Nh : c.Nx;
     A.bcL = c.h_bc[0]; A.bcR = c.h_bc[c.nbc - 1];
     A.del_t = del_t;
-    A.f_tol = del_t * ((c.scheme == IPIC_SCHEME_NGP) ? 1.e-15 : 1.e-10);   // NGP :79,172 ; CIC :90,208
+    // NGP :79,172 ; CIC :90,208 ; NGP_Periodic :75,150 (`del_t * 1e-12` with a default-real literal)
+    A.f_tol = del_t * ((c.scheme == IPIC_SCHEME_NGP) ? 1.e-15 : (c.scheme == IPIC_SCHEME_CIC) ? 1.e-10 : (double)1e-12f);
     A.stay_min = std::min(32, std::max(1, c.stay_min));
     return IPIC_OK;
 }
@@ -634,6 +645,7 @@ int launch_deposit(Ctx &c, int sp, double del_t) {
     if (rc) return rc;
     if (A.n == 0) return IPIC_OK;
     if (c.scheme == IPIC_SCHEME_NGP) return launch_push_v<0, false>(c, A);
+    if (c.scheme == IPIC_SCHEME_NGP_PERIODIC) return launch_push_v<2, false>(c, A);
     return launch_push_v<1, false>(c, A);
 }
 
@@ -643,6 +655,7 @@ int launch_move(Ctx &c, int sp, double del_t) {
     if (rc) return rc;
     if (A.n == 0) return IPIC_OK;
     if (c.scheme == IPIC_SCHEME_NGP) return launch_push_v<0, true>(c, A);
+    if (c.scheme == IPIC_SCHEME_NGP_PERIODIC) return launch_push_v<2, true>(c, A);
     return launch_push_v<1, true>(c, A);
 }
 
@@ -706,7 +719,7 @@ int launch_deposit_rho(Ctx &c, int sp) {
     unsigned long long *acc = c.d_acc + (size_t)sp * 2 * ((size_t)std::max(c.Nx, c.Nh) + 2);
     static bool cfg0s[64] = {}, cfg1s[64] = {};   // function attributes are per device
     bool &cfg0 = cfg0s[c.device & 63], &cfg1 = cfg1s[c.device & 63];
-    if (c.scheme == IPIC_SCHEME_NGP) {
+    if (c.scheme != IPIC_SCHEME_CIC) {
         if (!cfg0) { IPIC_CUDA(cudaFuncSetAttribute(k_deposit_rho<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (MAX_GRID_SMEM + 2) * 4)); cfg0 = true; }
         c.launches += 1; k_deposit_rho<0><<<c.num_sms, 1024, smem, c.stream>>>(s.l, s.n, c.d_bc, c.Nx, acc);
     } else {
@@ -1085,11 +1098,11 @@ int generate_species(Ctx &c, int sp, long long n, double T_eV, double v_drift, u
     int rc = ensure_capacity(c, sp, n);
     if (rc) return rc;
     double startX, L;
-    if (c.scheme == IPIC_SCHEME_NGP) { startX = c.h_grid[0]; L = c.h_grid[c.Nx - 1] - c.h_grid[0]; }
+    if (c.scheme != IPIC_SCHEME_CIC) { startX = c.h_grid[0]; L = c.h_grid[c.Nx - 1] - c.h_grid[0]; }
     else { startX = c.h_grid[0] - 0.5 * c.h_dx[0]; L = c.h_grid[c.Nx - 1] + 0.5 * c.h_dx[c.Nx - 1] - startX; }
     const double v_therm = sqrt(T_eV * e_c / s.mass);
     const long long first = (long long)c.rank * n;   // ranks draw disjoint index ranges of one global stream
-    c.launches += 1; k_generate<<<c.num_sms * 8, 256, 0, c.stream>>>(s.l, s.vx, s.vy, s.vz, n, first, c.d_grid, c.d_dx, c.Nx, c.scheme, startX, L, v_therm, v_drift,
+    c.launches += 1; k_generate<<<c.num_sms * 8, 256, 0, c.stream>>>(s.l, s.vx, s.vy, s.vz, n, first, c.d_grid, c.d_dx, c.Nx, c.scheme == IPIC_SCHEME_CIC ? 1 : 0, startX, L, v_therm, v_drift,
                                                      seed + 0x1000003ULL * (unsigned long long)sp);
     IPIC_CUDA(cudaGetLastError());
     s.n = n;

@@ -7,20 +7,21 @@ import math
 import numpy as np
 from . import constants as K
 
-NGP, CIC = 0, 1
+NGP, CIC, NGP_PERIODIC = 0, 1, 2
 
 
 class Domain:
     def __init__(self, scheme, NumberXNodes, leftBoundary, rightBoundary):
-        if scheme not in (NGP, CIC):
-            raise ValueError("scheme must be 0 (NGP) or 1 (CIC)")
+        if scheme not in (NGP, CIC, NGP_PERIODIC):
+            raise ValueError("scheme must be 0 (NGP), 1 (CIC) or 2 (NGP_Periodic, E-field form)")
         self.scheme = scheme
+        self._ngp = scheme != CIC          # NGP_Periodic uses the NGP grid (OpenMP/NGP_Periodic/src/mod_domain.f90)
         self.NumberXNodes = int(NumberXNodes)
-        self.NumberXHalfNodes = self.NumberXNodes - 1 if scheme == NGP else self.NumberXNodes + 1
+        self.NumberXHalfNodes = self.NumberXNodes - 1 if scheme != CIC else self.NumberXNodes + 1
         Nx, Nh = self.NumberXNodes, self.NumberXHalfNodes
-        nb = Nx if scheme == NGP else Nh
+        nb = Nx if scheme != CIC else Nh
         self.grid = np.arange(1, Nx + 1, dtype=np.float64)
-        self.dx_dl = np.ones(Nh if scheme == NGP else Nx)
+        self.dx_dl = np.ones(Nh if scheme != CIC else Nx)
         self.boundaryConditions = np.zeros(nb, dtype=np.int32)
         self.boundaryConditions[0] = leftBoundary
         self.boundaryConditions[-1] = rightBoundary
@@ -35,7 +36,7 @@ class Domain:
     def constructGrid(self, del_x, L_domain, gridType):
         Nx, Nh = self.NumberXNodes, self.NumberXHalfNodes
         pi = K.pi
-        if self.scheme == NGP:
+        if self._ngp:
             g = np.zeros(Nx)
             g[Nx - 1] = L_domain
             i = np.arange(2, Nh + 1, dtype=np.float64)     # Fortran index of interior nodes
@@ -111,7 +112,7 @@ class Domain:
     def getLFromX(self, x):
         lo, hi = 1, self.NumberXNodes
         g, dx = self.grid, self.dx_dl
-        if self.scheme == NGP:
+        if self._ngp:
             if x < g[0] or x > g[-1]:
                 raise ValueError("x value outside of grid range in getLFromX!")
             while lo != hi - 1:
@@ -136,7 +137,7 @@ class Domain:
     # ---- getXFromL: NGP :267-273 ; CIC :281-287
     def getXFromL(self, l):
         il = int(l)
-        if self.scheme == NGP:
+        if self._ngp:
             return self.grid[il - 1] + self.dx_dl[il - 1] * (l - il)
         return self.grid[il - 1] + self.dx_dl[il - 1] * (l - il - 0.5)
 

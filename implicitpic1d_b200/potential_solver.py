@@ -62,6 +62,8 @@ class potentialSolver:
     J = property(lambda s: s._get(_lib.F_J, s.world.NumberXHalfNodes), lambda s, v: s._set(_lib.F_J, v))
     rho = property(lambda s: s._get(_lib.F_RHO, s.world.NumberXNodes), lambda s, v: s._set(_lib.F_RHO, v))
     EField = property(lambda s: s._get(_lib.F_EFIELD, s.world.NumberXHalfNodes), lambda s, v: s._set(_lib.F_EFIELD, v))
+    EField_f = property(lambda s: s._get(_lib.F_EFIELD_F, s.world.NumberXHalfNodes), lambda s, v: s._set(_lib.F_EFIELD_F, v))
+    EField_half = property(lambda s: s._get(_lib.F_EFIELD_HALF, s.world.NumberXHalfNodes))
     a_tri = property(lambda s: s._get(_lib.F_A_TRI, s.world.NumberXNodes - 1))
     b_tri = property(lambda s: s._get(_lib.F_B_TRI, s.world.NumberXNodes))
     c_tri = property(lambda s: s._get(_lib.F_C_TRI, s.world.NumberXNodes - 1))

@@ -36,6 +36,8 @@ typedef struct ipic_ctx *ipic_handle;
 /* scheme = which reference tree's semantics are used */
 #define IPIC_SCHEME_NGP 0 /* OpenMP/NGP : phi on N_x nodes, J/E on N_h = N_x-1 cells */
 #define IPIC_SCHEME_CIC 1 /* OpenMP/CIC : phi on N_x centres, J/E on N_h = N_x+1 faces */
+#define IPIC_SCHEME_NGP_PERIODIC 2 /* OpenMP/NGP_Periodic : E-field form; the nonlinear unknown is EField_f (N_h), explicit Ampere update,
+                                      cell-local mover arithmetic (mod_particleMover.f90:18-238, mod_potentialSolver.f90:127-176) */
 
 /* status codes */
 #define IPIC_OK 0
@@ -55,6 +57,8 @@ typedef struct ipic_ctx *ipic_handle;
 #define IPIC_F_A_TRI 5  /* solver%a_tri  (N_x-1) */
 #define IPIC_F_B_TRI 6  /* solver%b_tri  (N_x) */
 #define IPIC_F_C_TRI 7  /* solver%c_tri  (N_x-1) */
+#define IPIC_F_EFIELD_F 8    /* solver%EField_f    (N_h)  NGP_Periodic */
+#define IPIC_F_EFIELD_HALF 9 /* solver%EField_half (N_h)  NGP_Periodic */
 
 /* linear-solve modes for the tridiagonal Ampere/Poisson systems */
 #define IPIC_TRIDIAG_PCR 0    /* single-block parallel cyclic reduction, cached level coefficients (default) */

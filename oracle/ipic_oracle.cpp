@@ -285,6 +285,10 @@ struct Solver {   // NGP mod_potentialSolver.f90:17-22 ; CIC :17-23
     double RF_voltage = 0, boundPhi[3] = {0, 0, 0}, sourceTermVals[3] = {0, 0, 0};  // CIC only, 1-based
     int RF_indx = 0;
     bool RF_bool = false;
+    // NGP_Periodic (E-field form): OpenMP/NGP_Periodic/src/mod_potentialSolver.f90:10-13
+    dvec EField_f, EField_half;
+    double aveJ = 0.0;
+    bool eform = false, globJBool = false;
 };
 
 struct NonLin {   // mod_nonLinSolvers.f90:29-35
@@ -1263,6 +1267,373 @@ static int solvePotential(Oracle &o, double del_t, double &remainDel_t, double &
     return 2;   // JFNK: not restated in this file
 }
 
+
+// =============================================================================
+// NGP_Periodic tree (E-field form): the unknown of the nonlinear solve is EField_f (N_h), the field update is the
+// explicit Ampere law, positions are advanced in cell-local coordinates.
+//   OpenMP/NGP_Periodic/src/mod_particleMover.f90, mod_potentialSolver.f90, mod_nonLinSolvers.f90, mod_Scheme.f90
+// The grid (mod_domain.f90) is the NGP grid without smoothing; world.scheme stays 0.
+// =============================================================================
+
+// construct_diagMatrix  NGP_Periodic/src/mod_potentialSolver.f90:88-126 (Neumann rows carry factor 1, not 2)
+static int P_construct_diagMatrix(Oracle &o) {
+    Domain &w = o.world; Solver &s = o.solver;
+    const int Nx = w.Nx;
+    std::fill(s.a_tri.begin(), s.a_tri.end(), 0.0); std::fill(s.b_tri.begin(), s.b_tri.end(), 0.0); std::fill(s.c_tri.begin(), s.c_tri.end(), 0.0);
+    for (int i = 1; i <= Nx; ++i) {
+        switch (w.bc[i]) {
+        case 0:
+            if (i < Nx) s.c_tri[i] = 1.0 / w.dx_dl[i];
+            if (i > 1) s.a_tri[i - 1] = 1.0 / w.dx_dl[i - 1];
+            s.b_tri[i] = -(1.0 / w.dx_dl[i - 1] + 1.0 / w.dx_dl[i]);
+            break;
+        case 1: case 4: s.b_tri[i] = 1.0; break;
+        case 2:
+            if (i == 1) { s.c_tri[i] = 1.0 / w.dx_dl[i]; s.b_tri[i] = -(1.0 / w.dx_dl[i]); }
+            else if (i == Nx) { s.a_tri[i - 1] = 1.0 / w.dx_dl[i - 1]; s.b_tri[i] = -(1.0 / w.dx_dl[i - 1]); }
+            else return 1;
+            break;
+        case 3: s.b_tri[i] = 1.0; break;
+        default: break;
+        }
+    }
+    return 0;
+}
+
+// potentialSolver_constructor  :33-86
+static int P_solver_init(Oracle &o, double leftV, double rightV, double RF_frequency) {
+    Domain &w = o.world; Solver &s = o.solver;
+    const int Nx = w.Nx, Nh = w.Nh;
+    s.eform = true;
+    s.phi.assign(Nx + 2, 0.0); s.phi_f.assign(Nx + 2, 0.0); s.rho.assign(Nx + 2, 0.0); s.J.assign(Nh + 2, 0.0);
+    s.EField.assign(Nh + 2, 0.0); s.EField_f.assign(Nh + 2, 0.0); s.EField_half.assign(Nh + 2, 0.0);
+    s.a_tri.assign(Nx + 2, 0.0); s.b_tri.assign(Nx + 2, 0.0); s.c_tri.assign(Nx + 2, 0.0);
+    if (P_construct_diagMatrix(o)) return 1;
+    s.rho_const = 0.0; s.RF_half_amplitude = 0.0;
+    if (w.bc[1] == 1) s.phi[1] = leftV;
+    if (w.bc[1] == 4) s.RF_half_amplitude = leftV;
+    if (w.bc[Nx] == 1) s.phi[Nx] = rightV;
+    if (w.bc[Nx] == 4) { if (s.RF_half_amplitude != 0) return 2; s.RF_half_amplitude = rightV; }
+    if (w.bc[1] == 3) { s.phi[1] = leftV; s.phi[Nx] = leftV; }
+    s.RF_rad_frequency = 2.0 * pi * RF_frequency;
+    s.RF_bool = s.RF_rad_frequency > 0 && s.RF_half_amplitude > 0 && (w.bc[1] == 4 || w.bc[Nx] == 4);
+    s.aveJ = 0.0; s.globJBool = false;
+    return 0;
+}
+
+// addThreadedDomainArray  NGP_Periodic/src/mod_domain.f90:261-273: array(slice) += SUM_t x(slice,t) * const, species by species
+template <class GET>
+static void P_add_threaded(Oracle &o, double *arr /*1-based*/, int nSlices, const ivec &L, const ivec &R, GET get) {
+    const int T = o.world.T;
+    for (auto &p : o.plist) {
+#pragma omp parallel for schedule(static, 1)
+        for (int it = 1; it <= T; ++it) {
+            if (it <= nSlices) {
+                for (int i = L[it]; i <= R[it]; ++i) {
+                    double sm = 0.0;
+                    for (int t = 1; t <= T; ++t) sm += get(p, i, t);
+                    arr[i] = arr[i] + sm * p.q_times_wp;
+                }
+            }
+        }
+    }
+}
+
+// depositRho  NGP_Periodic/src/mod_Scheme.f90:57-70 (interpolateParticleToNodes :25-37): raw linear weights, no wall fix-ups
+static void P_depositRho(Oracle &o) {
+    Domain &w = o.world; Solver &s = o.solver;
+    const int Nx = w.Nx, T = w.T;
+    for (int i = 1; i <= Nx; ++i) s.rho[i] = 0.0;
+#pragma omp parallel for schedule(static, 1)
+    for (int it = 1; it <= T; ++it) {
+        for (auto &p : o.plist) {
+            for (int i = 0; i <= Nx + 1; ++i) p.DN(i, it) = 0.0;
+            for (int j = 1; j <= p.N_p[it]; ++j) {
+                const int l_left = (int)p.P(1, j, it);
+                const double d = p.P(1, j, it) - (double)l_left;
+                p.DN(l_left, it) = p.DN(l_left, it) + (1.0 - d);
+                p.DN(l_left + 1, it) = p.DN(l_left + 1, it) + d;
+            }
+        }
+    }
+    P_add_threaded(o, s.rho.data(), w.nTN, w.tnL, w.tnR, [](Species &p, int i, int t) -> double & { return p.DN(i, t); });
+}
+
+// solve_tridiag_Poisson  :127-158 (also sets EField and EField_f)
+static void P_solve_tridiag_Poisson(Oracle &o, double timeCurrent) {
+    Domain &w = o.world; Solver &s = o.solver;
+    const int Nx = w.Nx, Nh = w.Nh;
+    dvec d(Nx + 2, 0.0), cp(Nh + 2, 0.0), dp(Nx + 2, 0.0);
+    for (int i = 1; i <= Nx; ++i) {
+        switch (w.bc[i]) {
+        case 0: case 2: d[i] = (-s.rho[i] - s.rho_const) / eps_0; break;
+        case 1: case 3: d[i] = s.phi[i]; break;
+        case 4: d[i] = s.RF_half_amplitude * std::sin(s.RF_rad_frequency * timeCurrent); break;
+        }
+    }
+    cp[1] = s.c_tri[1] / s.b_tri[1];
+    dp[1] = d[1] / s.b_tri[1];
+    for (int i = 2; i <= Nh; ++i) {
+        const double m = s.b_tri[i] - cp[i - 1] * s.a_tri[i - 1];
+        cp[i] = s.c_tri[i] / m;
+        dp[i] = (d[i] - dp[i - 1] * s.a_tri[i - 1]) / m;
+    }
+    {
+        const double m = s.b_tri[Nx] - cp[Nh] * s.a_tri[Nh];
+        dp[Nx] = (d[Nx] - dp[Nh] * s.a_tri[Nh]) / m;
+    }
+    for (int i = 1; i <= Nx; ++i) s.phi[i] = dp[i];
+    for (int i = Nh; i >= 1; --i) s.phi[i] = dp[i] - cp[i] * s.phi[i + 1];
+    for (int i = 1; i <= Nh; ++i) { s.EField[i] = (s.phi[i] - s.phi[i + 1]) / w.dx_dl[i]; s.EField_f[i] = s.EField[i]; }
+    for (int i = 1; i <= Nx; ++i) s.phi_f[i] = s.phi[i];
+}
+
+// solve_tridiag_Ampere  :170-176: explicit Ampere update of EField_f
+static void P_solve_tridiag_Ampere(Oracle &o, double del_t) {
+    Domain &w = o.world; Solver &s = o.solver;
+    const int Nh = w.Nh;
+    if (!s.globJBool) {
+        double sm = 0.0;
+        for (int i = 1; i <= Nh; ++i) sm += s.J[i] * w.dx_dl[i];
+        s.aveJ = sm / w.L_domain;
+    }
+    for (int i = 1; i <= Nh; ++i) s.EField_f[i] = (s.aveJ - s.J[i]) * del_t / eps_0 + s.EField[i];
+}
+
+// particleSubStepNoBField  NGP_Periodic/src/mod_particleMover.f90:18-59 (cell-local l in [0,1])
+static inline void P_subStep(double l_sub, double v_sub, double &l_f, double &v_f, double &del_tau, double E_x, double q_over_m, double dx_dl,
+                             bool &atB, int &l_boundary) {
+    const double a = q_over_m * E_x;
+    v_f = v_sub + a * del_tau;
+    l_f = l_sub + 0.5 * (v_sub + v_f) * del_tau / dx_dl;
+    const bool inCell = ((int)(l_f + 1.0) == 1);
+    const bool eqSign = ((v_sub > 0) == (v_f > 0));
+    atB = (!inCell) || (!eqSign);
+    if (atB) {
+        l_boundary = (v_sub > 0) ? 1 : 0;
+        double diff_PE = 2.0 * a * ((double)l_boundary - l_sub) * dx_dl;
+        const double v_i_sqr = v_sub * v_sub;
+        atB = (diff_PE > -v_i_sqr);
+        if (atB) {
+            l_f = (double)l_boundary;
+            v_f = fsign(1.0, v_sub) * std::sqrt(diff_PE + v_i_sqr);
+            del_tau = (v_f - v_sub) / a;
+        } else if (!inCell) {
+            atB = true;
+            l_boundary = 1 - l_boundary;
+            l_f = (double)l_boundary;
+            diff_PE = 2.0 * a * (l_f - l_sub) * dx_dl;
+            v_f = -fsign(1.0, v_sub) * std::sqrt(diff_PE + v_i_sqr);
+            del_tau = (v_f - v_sub) / a;
+        }
+    }
+}
+
+// depositJ :60-135 / moveParticles :136-238 share this sweep (MOVE selects the bookkeeping)
+template <bool MOVE>
+static void P_sweep(Oracle &o, double del_t) {
+    Domain &w = o.world; Solver &s = o.solver;
+    const int Nx = w.Nx, Nh = w.Nh, T = w.T, nS = (int)o.plist.size();
+    for (int i = 1; i <= Nh; ++i) s.EField_half[i] = 0.5 * (s.EField[i] + s.EField_f[i]);
+    if (!MOVE) for (int i = 1; i <= Nh; ++i) s.J[i] = 0.0;
+    const double f_tol = del_t * (double)1e-12f;                  // `del_t * 1e-12`: default-real literal (:75,:150)
+    std::vector<long long> numSubStepAve(nS, 0);
+    if (!MOVE) for (auto &p : o.plist) p.substepsDeposit = 0;
+#pragma omp parallel for schedule(static, 1)
+    for (int iThread = 1; iThread <= T; ++iThread) {
+        for (int j = 0; j < nS; ++j) {
+            Species &p = o.plist[j];
+            long long trips = 0;
+            int delIdx = 0, refIdx = 0;
+            if (MOVE) { p.WL(1, iThread) = 0; p.WL(2, iThread) = 0; p.EL(1, iThread) = 0.0; p.EL(2, iThread) = 0.0; }
+            else for (int i = 1; i <= Nh; ++i) p.WS(i, iThread) = 0.0;
+            const int N_p = p.N_p[iThread];
+            for (int i = 1; i <= N_p; ++i) {
+                double v_sub = p.P(2, i, iThread), l_sub = p.P(1, i, iThread);
+                double timePassed = 0.0, l_f = 0, v_f = 0, del_tau;
+                bool refluxedBool = false, futB = false, absorbed = false;
+                bool atBoundary = (std::fmod(l_sub, 1.0) == 0.0);
+                bool timeNotConverged = true;
+                int l_cell, l_boundary = 0;
+                while (timeNotConverged) {
+                    ++trips;
+                    if (!atBoundary) l_cell = (int)l_sub;
+                    else l_cell = (int)l_sub + ((int)fsign(1.0, v_sub) - 1) / 2;
+                    const double E_x = s.EField_half[l_cell], dx = w.dx_dl[l_cell];
+                    del_tau = del_t - timePassed;
+                    l_sub = l_sub - (double)l_cell;
+                    P_subStep(l_sub, v_sub, l_f, v_f, del_tau, E_x, p.q_over_m, dx, futB, l_boundary);
+                    if (!MOVE) p.WS(l_cell, iThread) = p.WS(l_cell, iThread) + l_f - l_sub;
+                    l_f = l_f + (double)l_cell;
+                    if (futB) {
+                        l_boundary = l_boundary + l_cell;
+                        const int b = w.bc[l_boundary];
+                        if (b == 1 || b == 4) {
+                            if (MOVE) {
+                                delIdx = delIdx + 1;
+                                const double e_perp = p.P(3, i, iThread) * p.P(3, i, iThread) + p.P(4, i, iThread) * p.P(4, i, iThread);
+                                if (l_boundary == 1) { p.EL(1, iThread) = p.EL(1, iThread) + v_f * v_f + e_perp; p.WL(1, iThread) = p.WL(1, iThread) + 1; }
+                                else if (l_boundary == Nx) { p.EL(2, iThread) = p.EL(2, iThread) + v_f * v_f + e_perp; p.WL(2, iThread) = p.WL(2, iThread) + 1; }
+                            }
+                            absorbed = true;
+                            break;
+                        } else if (b == 2) {
+                            if (l_boundary == Nx) { if (v_f > 0) v_f = -v_f; }
+                            else { if (v_f < 0) v_f = -v_f; }
+                            if (MOVE && !refluxedBool) {
+                                refIdx = refIdx + 1;
+                                if (refIdx <= p.refRecLen) p.refRecordIdx[(size_t)refIdx + (size_t)(p.refRecLen + 1) * iThread] = i - delIdx;
+                                refluxedBool = true;
+                            }
+                        } else if (b == 3) {
+                            l_f = (double)std::abs(l_boundary - Nx - 1);
+                        }
+                    }
+                    timePassed = timePassed + del_tau;
+                    timeNotConverged = (del_t - timePassed > f_tol);
+                    l_sub = l_f; v_sub = v_f;
+                    atBoundary = futB;
+                }
+                if (MOVE && !absorbed) {
+                    const double vy = p.P(3, i, iThread), vz = p.P(4, i, iThread);
+                    p.P(1, i - delIdx, iThread) = l_f; p.P(2, i - delIdx, iThread) = v_f;
+                    p.P(3, i - delIdx, iThread) = vy; p.P(4, i - delIdx, iThread) = vz;
+                }
+            }
+            if (MOVE) { p.N_p[iThread] = N_p - delIdx; p.delIdx[iThread] = delIdx; p.refIdx[iThread] = refIdx; }
+#pragma omp critical
+            { if (MOVE) numSubStepAve[j] += trips; else p.substepsDeposit += trips; }
+        }
+    }
+    if (!MOVE) {
+        P_add_threaded(o, s.J.data(), w.nTH, w.thL, w.thR, [](Species &p, int i, int t) -> double & { return p.WS(i, t); });
+        for (int i = 1; i <= Nh; ++i) s.J[i] = s.J[i] / del_t;
+        o.nl.sweeps += 1;
+        for (auto &p : o.plist) o.nl.substeps += p.substepsDeposit;
+    } else {
+        for (int j = 0; j < nS; ++j) {
+            Species &p = o.plist[j];
+            for (int t = 1; t <= T; ++t) p.numToCollide[t] = p.N_p[t];
+            const float denom = (float)(int)(p.sumNp() + p.sumDel());
+            p.numSubStepsAve = (double)((float)(int)numSubStepAve[j] / denom);
+            p.numFuncEvalAve = 0.0;
+            for (int sd = 1; sd <= 2; ++sd) {
+                double se = 0.0, sw = 0.0;
+                for (int t = 1; t <= T; ++t) { se += p.EL(sd, t); sw += p.WL(sd, t); }
+                p.accumEnergyLoss[sd - 1] += se;
+                p.accumWallLoss[sd - 1] += (int)sw;
+            }
+            p.substepsMove = numSubStepAve[j]; p.funcEvalsMove = 0;
+            o.nl.substeps += numSubStepAve[j];
+        }
+    }
+}
+
+// solveDivAmpereAnderson  NGP_Periodic/src/mod_nonLinSolvers.f90:85-141: Anderson on EField_f (N_h); iterNumPicard = i
+static void P_solveDivAmpereAnderson(Oracle &o, double del_t) {
+    Solver &s = o.solver; NonLin &nl = o.nl;
+    const int N = o.world.Nh, m = nl.m_Anderson, M1 = m + 1;
+    if ((int)nl.phi_k.size() < N * M1) { nl.phi_k.assign((size_t)N * M1, 0.0); nl.Residual_k.assign((size_t)N * M1, 0.0); nl.fitMat.assign((size_t)N * m, 0.0); }
+    auto EK = [&](int i, int c) -> double & { return nl.phi_k[(size_t)(i - 1) + (size_t)N * (c - 1)]; };
+    auto RK = [&](int i, int c) -> double & { return nl.Residual_k[(size_t)(i - 1) + (size_t)N * (c - 1)]; };
+    dvec normResidual(M1 + 1, 0.0), alpha(M1 + 1, 0.0);
+    nl.normHist.clear();
+    for (int i = 1; i <= N; ++i) EK(i, 1) = s.EField_f[i];
+    P_sweep<false>(o, del_t);
+    P_solve_tridiag_Ampere(o, del_t);
+    for (int i = 1; i <= N; ++i) { EK(i, 2) = s.EField_f[i]; RK(i, 1) = EK(i, 2) - EK(i, 1); }
+    { double sm = 0.0; for (int i = 1; i <= N; ++i) sm += RK(i, 1) * RK(i, 1); normResidual[1] = std::sqrt(sm); }
+    nl.normHist.push_back(normResidual[1]);
+    const double eps_tol = nl.eps_r * normResidual[1] + nl.eps_a * (double)std::sqrt((float)N);
+    for (int i = 1; i <= nl.maxIter; ++i) {
+        const int index = fmodulo(i, M1) + 1, m_k = std::min(i, m);
+        P_sweep<false>(o, del_t);
+        P_solve_tridiag_Ampere(o, del_t);
+        for (int k = 1; k <= N; ++k) RK(k, index) = s.EField_f[k] - EK(k, index);
+        { double sm = 0.0; for (int k = 1; k <= N; ++k) sm += RK(k, index) * RK(k, index); normResidual[index] = std::sqrt(sm); }
+        nl.normHist.push_back(normResidual[index]);
+        if (normResidual[index] < eps_tol) { P_sweep<true>(o, del_t); nl.iterNumPicard = i; return; }
+        if (i > m) {
+            double sumPast;
+            if (m > 1) sumPast = (normResidual[fmodulo(i - 1, M1) + 1] + normResidual[fmodulo(i - 2, M1) + 1]) / 2.0;
+            else sumPast = normResidual[fmodulo(i - 1, M1) + 1];
+            if (normResidual[index] > sumPast) { nl.iterNumPicard = nl.maxIter; return; }
+        }
+        for (int j = 0; j <= m_k - 1; ++j) {
+            const int cj = fmodulo(i - m_k + j, M1) + 1;
+            for (int k = 1; k <= N; ++k) nl.fitMat[(size_t)(k - 1) + (size_t)N * j] = RK(k, index) - RK(k, cj);
+        }
+        solveNormalEquation(nl.fitMat.data(), &RK(1, index), N, m_k, &alpha[1]);
+        { double sa = 0.0; for (int j = 1; j <= m_k; ++j) sa += alpha[j]; alpha[m_k + 1] = 1.0 - sa; }
+        const int cn = fmodulo(i + 1, M1) + 1, c0 = fmodulo(i - m_k, M1) + 1;
+        for (int k = 1; k <= N; ++k) EK(k, cn) = alpha[1] * (nl.Beta_k * RK(k, c0) + EK(k, c0));
+        for (int j = 1; j <= m_k; ++j) {
+            const int cj = fmodulo(i - m_k + j, M1) + 1;
+            for (int k = 1; k <= N; ++k) EK(k, cn) = EK(k, cn) + alpha[j + 1] * (nl.Beta_k * RK(k, cj) + EK(k, cj));
+        }
+        for (int k = 1; k <= N; ++k) s.EField_f[k] = EK(k, cn);
+    }
+}
+
+// adaptiveSolveDivAmpereAnderson :142-172 (setRFVoltage is an empty routine in this tree) ; solvePotential :173-189
+static int P_solvePotential(Oracle &o, double del_t, double &remainDel_t, double &currDel_t) {
+    NonLin &nl = o.nl; Solver &s = o.solver;
+    nl.sweeps = 0; nl.substeps = 0;
+    for (int i = 1; i <= o.world.Nh; ++i) s.EField[i] = s.EField_f[i];      // resetVoltage :283-286
+    if (nl.solverType != 0) return 2;
+    currDel_t = remainDel_t;
+    P_solveDivAmpereAnderson(o, remainDel_t);
+    if (nl.iterNumPicard < nl.maxIter) { remainDel_t = del_t; return 0; }
+    nl.amountTimeSplits += 1;
+    nl.iterNumAdaptiveSteps = 0;
+    while (nl.iterNumPicard == nl.maxIter) {
+        currDel_t = currDel_t / 2.0;
+        nl.iterNumAdaptiveSteps += 1;
+        if (nl.iterNumAdaptiveSteps > 4) return 1;
+        P_solveDivAmpereAnderson(o, currDel_t);
+    }
+    remainDel_t = remainDel_t - currDel_t;
+    return 0;
+}
+
+// getTotalPE :226-236 ; getError_tridiag_Poisson :159-169 ; getChargeContinuityError :187-225
+static double P_getTotalPE(Oracle &o, bool future) {
+    Domain &w = o.world; Solver &s = o.solver;
+    const dvec &E = future ? s.EField_f : s.EField;
+    double sm = 0.0;
+    for (int i = 1; i <= w.Nh; ++i) sm += E[i] * E[i] * w.dx_dl[i];
+    return 0.5 * eps_0 * sm;
+}
+static double P_gaussError(Oracle &o) {
+    Domain &w = o.world; Solver &s = o.solver;
+    const int Nh = w.Nh, Nx = w.Nx;
+    double r = eps_0 * (s.EField_f[1] - s.EField_f[Nh]) / (s.rho[1] + s.rho[Nx]) - 1.0;
+    double res = r * r;
+    for (int i = 2; i <= Nh; ++i) { r = eps_0 * (s.EField_f[i] - s.EField_f[i - 1]) / s.rho[i] - 1.0; res = res + r * r; }
+    return std::sqrt(res / Nh);
+}
+static double P_chargeError(Oracle &o, const double *rho_i /*1-based*/, double del_t) {
+    Domain &w = o.world; Solver &s = o.solver;
+    const int Nx = w.Nx, Nh = w.Nh;
+    double err = 0.0; int k = 0;
+    for (int i = 1; i <= Nx; ++i) {
+        double dR = s.rho[i] - rho_i[i];
+        if (dR != 0) {
+            switch (w.bc[i]) {
+            case 0: { const double v = 1.0 + del_t * (s.J[i] - s.J[i - 1]) / dR; err += v * v; k += 1; break; }
+            case 2: {
+                const double v = (i == 1) ? 1.0 + del_t * s.J[1] / dR : 1.0 - del_t * s.J[Nh] / dR;
+                err += v * v; k += 1; break; }
+            case 3:
+                if (i == 1) { dR = dR + s.rho[Nx] - rho_i[Nx]; const double v = 1.0 + del_t * (s.J[1] - s.J[Nh]) / dR; err += v * v; }
+                break;
+            default: break;
+            }
+        }
+    }
+    return std::sqrt(err / k);
+}
+
 }  // namespace
 
 // =============================================================================
@@ -1393,6 +1764,8 @@ static dvec *field_ptr(Oracle *o, int which, int *n) {
     case 5: *n = Nx - 1; return &s.a_tri;
     case 6: *n = Nx; return &s.b_tri;
     case 7: *n = Nx - 1; return &s.c_tri;
+    case 8: *n = Nh; return &s.EField_f;
+    case 9: *n = Nh; return &s.EField_half;
     }
     *n = 0; return nullptr;
 }
@@ -1466,4 +1839,25 @@ int orc_max_threads() {
 #endif
 }
 
+
+// ---- NGP_Periodic (E-field form) ----
+int orc_p_init_solver(void *h, double leftV, double rightV, double RF_frequency) { return P_solver_init(*(Oracle *)h, leftV, rightV, RF_frequency); }
+void orc_p_deposit_rho(void *h) { P_depositRho(*(Oracle *)h); }
+void orc_p_solve_tridiag_poisson(void *h, double t) { P_solve_tridiag_Poisson(*(Oracle *)h, t); }
+void orc_p_deposit_J(void *h, double del_t) { P_sweep<false>(*(Oracle *)h, del_t); }
+void orc_p_move_particles(void *h, double del_t) { P_sweep<true>(*(Oracle *)h, del_t); }
+void orc_p_solve_tridiag_ampere(void *h, double del_t) { P_solve_tridiag_Ampere(*(Oracle *)h, del_t); }
+void orc_p_reset_voltage(void *h) { Oracle *o = (Oracle *)h; for (int i = 1; i <= o->world.Nh; ++i) o->solver.EField[i] = o->solver.EField_f[i]; }
+int orc_p_solve_potential(void *h, double del_t, double *remainDel_t, double *currDel_t) { return P_solvePotential(*(Oracle *)h, del_t, *remainDel_t, *currDel_t); }
+void orc_p_solve_div_ampere_anderson(void *h, double del_t) { P_solveDivAmpereAnderson(*(Oracle *)h, del_t); }
+double orc_p_total_PE(void *h, int future) { return P_getTotalPE(*(Oracle *)h, future != 0); }
+double orc_p_gauss_error(void *h) { return P_gaussError(*(Oracle *)h); }
+double orc_p_charge_error(void *h, const double *rho_i, double del_t) {
+    Oracle *o = (Oracle *)h;
+    dvec r(o->world.Nx + 2, 0.0);
+    for (int i = 1; i <= o->world.Nx; ++i) r[i] = rho_i[i - 1];
+    return P_chargeError(*o, r.data(), del_t);
+}
+double orc_p_aveJ(void *h) { return ((Oracle *)h)->solver.aveJ; }
+void orc_reset_sweep_counters(void *h) { Oracle *o = (Oracle *)h; o->nl.sweeps = 0; o->nl.substeps = 0; }
 }  // extern "C"

@@ -79,6 +79,13 @@ def lib(native=False):
         "orc_ran2": (d, [C.POINTER(C.c_int32)]), "orc_randPCG": (d, [C.POINTER(C.c_uint64)]),
         "orc_species_scalars": (None, [p, i, dp]),
         "orc_max_threads": (i, []),
+        "orc_p_init_solver": (i, [p, d, d, d]),
+        "orc_p_deposit_rho": (None, [p]), "orc_p_solve_tridiag_poisson": (None, [p, d]),
+        "orc_p_deposit_J": (None, [p, d]), "orc_p_move_particles": (None, [p, d]),
+        "orc_p_solve_tridiag_ampere": (None, [p, d]), "orc_p_reset_voltage": (None, [p]),
+        "orc_p_solve_potential": (i, [p, d, dp, dp]), "orc_p_solve_div_ampere_anderson": (None, [p, d]),
+        "orc_p_total_PE": (d, [p, i]), "orc_p_gauss_error": (d, [p]), "orc_p_charge_error": (d, [p, dp, d]),
+        "orc_p_aveJ": (d, [p]), "orc_reset_sweep_counters": (None, [p]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -96,8 +103,8 @@ def _ip(a):
     return a.ctypes.data_as(C.POINTER(C.c_int))
 
 
-FIELDS = {"phi": 0, "phi_f": 1, "J": 2, "rho": 3, "EField": 4, "a_tri": 5, "b_tri": 6, "c_tri": 7}
-NGP, CIC = 0, 1
+FIELDS = {"phi": 0, "phi_f": 1, "J": 2, "rho": 3, "EField": 4, "a_tri": 5, "b_tri": 6, "c_tri": 7, "EField_f": 8, "EField_half": 9}
+NGP, CIC, NGP_PERIODIC = 0, 1, 2
 
 
 def default_seeds(T):
@@ -110,6 +117,10 @@ class Oracle:
 
     def __init__(self, scheme, Nx, L_domain, gridType=0, del_x=0.0, bcL=1, bcR=1, smooth=False, T=1, native=False):
         self.L = lib(native)
+        # NGP_PERIODIC (E-field form, OpenMP/NGP_Periodic): the NGP grid without smoothing + the E-form solver/mover routines
+        self.eform = scheme == NGP_PERIODIC
+        if self.eform:
+            scheme, smooth = NGP, False
         self.h = self.L.orc_create(scheme, Nx, L_domain, gridType, del_x, bcL, bcR, int(smooth), T)
         if not self.h:
             raise ValueError("oracle: grid construction failed (the reference would stop)")
@@ -147,7 +158,10 @@ class Oracle:
 
     # ---- solver
     def init_solver(self, leftV, rightV, RF_frequency=0.0, t0=0.0):
-        rc = self.L.orc_init_solver(self.h, leftV, rightV, RF_frequency, t0)
+        if self.eform:
+            rc = self.L.orc_p_init_solver(self.h, leftV, rightV, RF_frequency)
+        else:
+            rc = self.L.orc_init_solver(self.h, leftV, rightV, RF_frequency, t0)
         if rc:
             raise ValueError("oracle: potentialSolver constructor would stop (%d)" % rc)
 
@@ -232,22 +246,36 @@ class Oracle:
         self.L.orc_get_particle_time_step(self.h, sp, _dp(o))
         return o
 
-    # ---- the path
-    def depositRho(self): self.L.orc_deposit_rho(self.h)
-    def solve_tridiag_Poisson(self, t=0.0): self.L.orc_solve_tridiag_poisson(self.h, t)
-    def solveInitialPotential(self, t=0.0): self.L.orc_solve_initial_potential(self.h, t)
-    def makeConstSourceTerm(self): self.L.orc_make_const_source_term(self.h)
+    # ---- the path (E-form routines when self.eform)
+    def depositRho(self): (self.L.orc_p_deposit_rho if self.eform else self.L.orc_deposit_rho)(self.h)
+    def solve_tridiag_Poisson(self, t=0.0): (self.L.orc_p_solve_tridiag_poisson if self.eform else self.L.orc_solve_tridiag_poisson)(self.h, t)
+
+    def solveInitialPotential(self, t=0.0):
+        if self.eform:
+            self.depositRho(); self.solve_tridiag_Poisson(t)
+        else:
+            self.L.orc_solve_initial_potential(self.h, t)
+
+    def makeConstSourceTerm(self):
+        if not self.eform:
+            self.L.orc_make_const_source_term(self.h)
+
     def makeHalfTimeEField(self): self.L.orc_make_half_time_efield(self.h)
-    def depositJ(self, del_t): self.L.orc_deposit_J(self.h, del_t)
-    def solve_tridiag_Ampere(self, del_t): self.L.orc_solve_tridiag_ampere(self.h, del_t)
-    def moveParticles(self, del_t): self.L.orc_move_particles(self.h, del_t)
-    def resetVoltage(self): self.L.orc_reset_voltage(self.h)
-    def setRFVoltage(self, t): self.L.orc_set_rf_voltage(self.h, t)
-    def solveDivAmpereAnderson(self, del_t): self.L.orc_solve_div_ampere_anderson(self.h, del_t)
+    def depositJ(self, del_t): (self.L.orc_p_deposit_J if self.eform else self.L.orc_deposit_J)(self.h, del_t)
+    def solve_tridiag_Ampere(self, del_t): (self.L.orc_p_solve_tridiag_ampere if self.eform else self.L.orc_solve_tridiag_ampere)(self.h, del_t)
+    def moveParticles(self, del_t): (self.L.orc_p_move_particles if self.eform else self.L.orc_move_particles)(self.h, del_t)
+    def resetVoltage(self): (self.L.orc_p_reset_voltage if self.eform else self.L.orc_reset_voltage)(self.h)
+    def setRFVoltage(self, t):
+        if not self.eform:
+            self.L.orc_set_rf_voltage(self.h, t)
+    def solveDivAmpereAnderson(self, del_t): (self.L.orc_p_solve_div_ampere_anderson if self.eform else self.L.orc_solve_div_ampere_anderson)(self.h, del_t)
 
     def solvePotential(self, del_t, remainDel_t, currDel_t, timeCurrent):
         r, c = C.c_double(remainDel_t), C.c_double(currDel_t)
-        rc = self.L.orc_solve_potential(self.h, del_t, C.byref(r), C.byref(c), timeCurrent)
+        if self.eform:
+            rc = self.L.orc_p_solve_potential(self.h, del_t, C.byref(r), C.byref(c))
+        else:
+            rc = self.L.orc_solve_potential(self.h, del_t, C.byref(r), C.byref(c), timeCurrent)
         if rc:
             raise RuntimeError("oracle: solvePotential would stop (%d)" % rc)
         return r.value, c.value
@@ -267,11 +295,13 @@ class Oracle:
 
     # ---- JFNK (mod_nonLinSolvers.f90:218-282) with the numpy NITSOL restatement (oracle/nitsol_np.py)
     def funcNitsol(self, xcur, del_t):
-        """fcur = xcur - G(xcur); leaves phi_f = G(xcur) like the reference (:226-236)"""
-        self.set("phi_f", xcur)
+        """fcur = xcur - G(xcur); leaves phi_f (E-form: EField_f) = G(xcur) like the reference
+        (mod_nonLinSolvers.f90:226-236 ; NGP_Periodic/src/mod_nonLinSolvers.f90:209-221)"""
+        unk = "EField_f" if self.eform else "phi_f"
+        self.set(unk, xcur)
         self.depositJ(del_t)
         self.solve_tridiag_Ampere(del_t)
-        return np.asarray(xcur) - self.get("phi_f")
+        return np.asarray(xcur) - self.get(unk)
 
     def solveJFNK(self, del_t, eps_a, eps_r, maxIter, m_Anderson):
         from . import nitsol_np
@@ -282,18 +312,21 @@ class Oracle:
             r = self.funcNitsol(x, del_t)
             self.jfnk_substeps += sum(self.move_stats(sp)["substepsDeposit"] for sp in range(self.n_species))
             return r
-        x, iterm = nit.solve(f, self.get("phi_f"), eps_a, eps_r, 1.e-12)
+        x, iterm = nit.solve(f, self.get("EField_f" if self.eform else "phi_f"), eps_a, eps_r, 1.e-12)
         if iterm == 0:
+            if self.eform:                       # NGP_Periodic solveJFNK re-deposits J before the move (:251-254)
+                self.depositJ(del_t)
             self.moveParticles(del_t)
         return dict(nit.info, iterm=iterm, fnorms=list(nit.fnorms))
 
     # ---- diagnostics (main.f90:58-114)
-    def getTotalPE(self, future): return self.L.orc_total_PE(self.h, int(future))
+    def getTotalPE(self, future): return (self.L.orc_p_total_PE if self.eform else self.L.orc_total_PE)(self.h, int(future))
     def getTotalKE(self, sp): return self.L.orc_total_KE(self.h, sp)
     def getKEAve(self, sp): return self.L.orc_KE_ave(self.h, sp)
     def getJdotE(self, del_t): return self.L.orc_JdotE(self.h, del_t)
-    def getEnergyFromBoundary(self, del_t): return self.L.orc_energy_from_boundary(self.h, del_t)
-    def getError_tridiag_Poisson(self): return self.L.orc_gauss_error(self.h)
+    def getEnergyFromBoundary(self, del_t): return 0.0 if self.eform else self.L.orc_energy_from_boundary(self.h, del_t)
+    def getError_tridiag_Poisson(self): return (self.L.orc_p_gauss_error if self.eform else self.L.orc_gauss_error)(self.h)
+    def aveJ(self): return self.L.orc_p_aveJ(self.h)
     def lostEnergySum(self, sp): return self.L.orc_lost_energy_sum(self.h, sp)
 
     def getTotalMomentum(self, sp):
@@ -303,7 +336,7 @@ class Oracle:
 
     def getChargeContinuityError(self, rho_i, del_t):
         r = np.ascontiguousarray(rho_i, dtype=np.float64)
-        return self.L.orc_charge_error(self.h, _dp(r), del_t)
+        return (self.L.orc_p_charge_error if self.eform else self.L.orc_charge_error)(self.h, _dp(r), del_t)
 
 
 def plasma_del_t(n_ave, fractionFreq, del_t_deck):
@@ -319,7 +352,7 @@ def debye_length(T_e, n_e):
 
 def make_deck_case(scheme, Nx, L_domain, n_ave, T_e, T_i, ppt, T, bcL, bcR, Vl, Vr, RF_freq, smooth, ion_amu=4.002602,
                    gridType=0, del_x=0.0, eps_a=1e-8, eps_r=0.0, m_Anderson=10, Beta_k=0.5, maxIter=100, t0=0.0, factor=1,
-                   seeds=None, native=False, ion_charge=1.0):
+                   seeds=None, native=False, ion_charge=1.0, alpha=0.0, distType=0, v_drift=0.0, solverType=0):
     """Builds the program state exactly as main.f90:25-40 does from a deck (electrons + one ion species),
     with the deterministic seeds of mod_BasicFunctions.f90:119."""
     del_x = max(0.1 * debye_length(T_e, n_ave), del_x)     # mod_domain.f90:371
@@ -328,11 +361,11 @@ def make_deck_case(scheme, Nx, L_domain, n_ave, T_e, T_i, ppt, T, bcL, bcR, Vl, 
     seeds = default_seeds(T) if seeds is None else seeds.copy()
     sp_e = o.add_species(m_e, -1.0 * e, ppt, factor)
     o.initialize_n_ave(sp_e, n_ave)
-    o.load_particles(sp_e, seeds, T_e)
+    o.load_particles(sp_e, seeds, T_e, alpha, distType, v_drift)
     m_ion = ion_amu * m_amu - ion_charge * m_e              # mod_particle.f90:334
     sp_i = o.add_species(m_ion, ion_charge * e, ppt, factor)
     o.initialize_n_ave(sp_i, n_ave)
-    o.load_particles(sp_i, seeds, T_i)
-    o.config_solver(eps_a, eps_r, 0, m_Anderson, Beta_k, maxIter)
+    o.load_particles(sp_i, seeds, T_i, alpha, distType, v_drift)
+    o.config_solver(eps_a, eps_r, solverType, m_Anderson, Beta_k, maxIter)
     o.solveInitialPotential(t0)
     return o

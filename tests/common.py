@@ -28,6 +28,19 @@ DECKS = {
 }
 
 
+# NGP_Periodic (E-field form) decks: OpenMP/NGP_Periodic/InputData (ion-acoustic shock wave of Chacon 2013: sine-perturbed
+# density, drifting Maxwellians, mass ratio 1e4, periodic walls, JFNK eps_r = 1e-8, m = 20), scaled down
+PERIODIC_DECKS = {
+    "ngpp_iasw": dict(scheme=2, Nx=65, L=0.33245599281881233 / 8, n_ave=1e14, T_e=5.0, T_i=0.01, ppt=4000, T=2, bcL=3, bcR=3, Vl=0.0, Vr=0.0,
+                      rf=0.0, smooth=False, frac=1.0, dt_deck=1.0, eps_a=0.0, eps_r=1e-8, m=20, beta=0.5, maxIter=100,
+                      ion_amu=5.48634767053312, alpha=0.4, distType=2, v_drift=-9372.932223215392),
+    # bounded variant of the same tree: Dirichlet / Neumann walls exercise absorption and reflection in cell-local coordinates
+    "ngpp_walls": dict(scheme=2, Nx=97, L=0.02, n_ave=5e14, T_e=3.0, T_i=0.05, ppt=3000, T=3, bcL=2, bcR=1, Vl=0.0, Vr=10.0,
+                       rf=0.0, smooth=False, frac=1.0, dt_deck=1.0, eps_a=0.0, eps_r=1e-8, m=10, beta=0.5, maxIter=100,
+                       ion_amu=4.002602),
+}
+
+
 def deck_del_t(d):
     return K.del_t_from_deck(d["n_ave"], d["frac"], d["dt_deck"])
 
@@ -35,8 +48,9 @@ def deck_del_t(d):
 def build_oracle(d, factor=1):
     return op.make_deck_case(d["scheme"], d["Nx"], d["L"], d["n_ave"], d["T_e"], d["T_i"], d["ppt"], d["T"], d["bcL"], d["bcR"],
                              d["Vl"], d["Vr"], d["rf"], d["smooth"], ion_amu=d["ion_amu"], gridType=d.get("gridType", 0),
-                             del_x=d.get("del_x", 0.0), eps_a=d["eps_a"], m_Anderson=d["m"], Beta_k=d["beta"], maxIter=d["maxIter"],
-                             factor=factor)
+                             del_x=d.get("del_x", 0.0), eps_a=d["eps_a"], eps_r=d.get("eps_r", 0.0), m_Anderson=d["m"], Beta_k=d["beta"],
+                             maxIter=d["maxIter"], factor=factor, alpha=d.get("alpha", 0.0), distType=d.get("distType", 0),
+                             v_drift=d.get("v_drift", 0.0))
 
 
 def build_cuda_from_oracle(d, o, tridiag_mode=None, device=0):
@@ -53,7 +67,7 @@ def build_cuda_from_oracle(d, o, tridiag_mode=None, device=0):
         p = ip.Particle(sc["mass"], sc["q"], sc["w_p"], 0, ps.shape[1], "e" if sp == 0 else "ion", d["T"])
         p.set_phase_space(ps.copy(), o.N_p(sp))
         plist.append(p)
-    ip.initializeSolver(solver, d["eps_a"], 0.0, 0, d["m"], d["beta"], d["maxIter"])
+    ip.initializeSolver(solver, d["eps_a"], d.get("eps_r", 0.0), 0, d["m"], d["beta"], d["maxIter"])
     solver.solveInitialPotential(plist, world, 0.0)
     return world, solver, plist
 

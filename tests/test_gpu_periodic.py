@@ -1,0 +1,122 @@
+"""GPU parity for the NGP_Periodic tree (IPIC_SCHEME_NGP_PERIODIC: E-field form, explicit Ampere update, cell-local mover,
+Anderson on EField_f, JFNK through NITSOL) against the oracle's restatement of OpenMP/NGP_Periodic/src/*.f90."""
+import numpy as np
+import pytest
+import implicitpic1d_b200 as ip
+from implicitpic1d_b200 import _lib
+from implicitpic1d_b200.particle_mover import depositSubsteps
+from common import PERIODIC_DECKS, build_oracle, build_cuda_from_oracle, deck_del_t, relerr
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+
+@pytest.fixture(params=sorted(PERIODIC_DECKS))
+def pair(request):
+    d = PERIODIC_DECKS[request.param]
+    o = build_oracle(d)
+    world, solver, plist = build_cuda_from_oracle(d, o, tridiag_mode=_lib.TRIDIAG_THOMAS)
+    yield d, o, world, solver, plist
+    solver.close()
+
+
+def test_rho_poisson_and_fields(pair):
+    d, o, world, solver, plist = pair
+    assert relerr(solver.rho, o.get("rho")) < 1e-12
+    assert relerr(solver.phi, o.get("phi")) < 1e-10
+    assert relerr(solver.EField, o.get("EField")) < 1e-9
+    assert np.array_equal(solver.EField_f, solver.EField)
+    for name in ("a_tri", "b_tri", "c_tri"):
+        assert relerr(getattr(solver, name), o.get(name)) < 1e-15
+
+
+def _sync(o, solver):
+    solver.EField = o.get("EField")
+    solver.EField_f = o.get("EField_f")
+
+
+def test_depositJ_and_ampere(pair):
+    d, o, world, solver, plist = pair
+    _sync(o, solver)
+    del_t = deck_del_t(d)
+    o.depositJ(del_t)
+    ip.depositJ(solver, plist, world, del_t)
+    assert relerr(solver.EField_half, o.get("EField_half")) < 1e-15
+    assert relerr(solver.J, o.get("J")) < 1e-12
+    for sp, p in enumerate(plist):
+        assert depositSubsteps(solver, p) == o.move_stats(sp)["substepsDeposit"]
+    o.solve_tridiag_Ampere(del_t)
+    solver.J = o.get("J")
+    solver.solve_tridiag_Ampere(world, del_t)
+    assert relerr(solver.EField_f, o.get("EField_f")) < 1e-13
+
+
+def test_moveParticles(pair):
+    d, o, world, solver, plist = pair
+    _sync(o, solver)
+    del_t = deck_del_t(d)
+    o.moveParticles(del_t)
+    ip.moveParticles(solver, plist, world, del_t)
+    for sp, p in enumerate(plist):
+        c, ms = o.counters(sp), o.move_stats(sp)
+        assert p.delIdx == int(c["delIdx"].sum()) and p.refIdx == int(c["refIdx"].sum())
+        assert np.array_equal(p.wallLoss, c["wallLoss"].sum(axis=0))
+        assert p.numSubSteps == ms["substepsMove"]
+        np.testing.assert_allclose(p.energyLoss, c["energyLoss"].sum(axis=0), rtol=1e-12, atol=0)
+        ps_g, ps_o = p.download(), o.phase_space(sp)
+        assert np.array_equal(p.N_p, o.N_p(sp))
+        for t in range(d["T"]):
+            n = p.N_p[t]
+            assert np.max(np.abs(ps_g[t, :n, 0] - ps_o[t, :n, 0])) < 1e-9
+            np.testing.assert_allclose(ps_g[t, :n, 1], ps_o[t, :n, 1], rtol=1e-9, atol=1e-6)
+            assert np.array_equal(ps_g[t, :n, 2:], ps_o[t, :n, 2:])
+
+
+def _energy(o, solver, plist, KE_i_o, KE_i_g):
+    PE_i_o, PE_i_g = o.getTotalPE(False), solver.getTotalPE(None, False)
+    KE_f_o = sum(o.getTotalKE(s) + o.lostEnergySum(s) * o.species_scalars(s)["mass"] * o.species_scalars(s)["w_p"] * 0.5 for s in range(2))
+    KE_f_g = sum(p.getTotalKE() + p.energyLoss.sum() * p.mass * p.w_p * 0.5 for p in plist)
+    PE_f_o, PE_f_g = o.getTotalPE(True), solver.getTotalPE(None, True)
+    return abs((PE_i_o + KE_i_o - PE_f_o - KE_f_o) / (PE_i_o + KE_i_o)), abs((PE_i_g + KE_i_g - PE_f_g - KE_f_g) / (PE_i_g + KE_i_g))
+
+
+def test_anderson_step(pair):
+    """main program of that tree (BoundPlasmaExample.f90:41-108) with solverType 0"""
+    d, o, world, solver, plist = pair
+    del_t = deck_del_t(d)
+    rho_i = o.get("rho")
+    KE_i_o, KE_i_g = sum(o.getTotalKE(s) for s in range(2)), sum(p.getTotalKE() for p in plist)
+    ro, co = o.solvePotential(del_t, del_t, del_t, 0.0)
+    rg, cg = ip.solvePotential(solver, plist, world, del_t, del_t, del_t, 0.0)
+    so, sg = o.solver_stats(), ip.SolverState(solver)
+    assert (rg, cg) == (ro, co)
+    assert sg.iterNumPicard == so["iterNumPicard"] and sg.amountTimeSplits == so["amountTimeSplits"]
+    assert sg.sweeps == so["sweeps"] and sg.substeps == so["substeps"]
+    assert relerr(solver.EField_f, o.get("EField_f")) < 1e-8
+    e_o, e_g = _energy(o, solver, plist, KE_i_o, KE_i_g)
+    assert e_g < max(2.0 * e_o, 1e-11), (e_g, e_o)
+    # Gauss and charge-continuity errors after re-depositing rho (BoundPlasmaExample.f90:105-107)
+    o.depositRho(); solver.depositRho(plist)
+    go, gg = o.getError_tridiag_Poisson(), solver.getError_tridiag_Poisson()
+    assert abs(gg - go) <= 1e-6 * max(go, 1e-12) + 1e-12
+    co_, cg_ = o.getChargeContinuityError(rho_i, co), solver.getChargeContinuityError(rho_i, None, cg)
+    assert abs(cg_ - co_) <= 1e-3 * max(co_, 1e-12) + 1e-10
+
+
+def test_jfnk_step(pair):
+    """solverType 1 (the deck's setting): NITSOL on F(E_f) = E_f - G(E_f) with n = N_h; iterNumPicard = nli; J is re-deposited
+    before the move (NGP_Periodic/src/mod_nonLinSolvers.f90:240-262)"""
+    d, o, world, solver, plist = pair
+    ip.initializeSolver(solver, d["eps_a"], d["eps_r"], 1, d["m"], d["beta"], d["maxIter"])
+    del_t = deck_del_t(d)
+    KE_i_o, KE_i_g = sum(o.getTotalKE(s) for s in range(2)), sum(p.getTotalKE() for p in plist)
+    o.resetVoltage(); solver.resetVoltage()
+    io = o.solveJFNK(del_t, d["eps_a"], d["eps_r"], d["maxIter"], d["m"])
+    ig = ip.solveJFNK(solver, plist, world, del_t)
+    assert ig.iterm == io["iterm"] == 0, (ig, io)
+    assert (ig.nfe, ig.njve, ig.nli, ig.nni, ig.nbt) == (io["nfe"], io["njve"], io["nli"], io["nni"], io["nbt"]), (ig, io)
+    assert ip.SolverState(solver).iterNumPicard == io["nli"]
+    assert relerr(solver.EField_f, o.get("EField_f")) < 1e-7
+    e_o, e_g = _energy(o, solver, plist, KE_i_o, KE_i_g)
+    assert e_g < max(2.0 * e_o, 1e-9), (e_g, e_o)
+    for sp, p in enumerate(plist):
+        assert p.N_p_total == int(o.N_p(sp).sum())
