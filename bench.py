@@ -42,6 +42,12 @@ WORKLOADS = {
                scheme=1, Nx=256, L=0.067, n_ave=5.12e14, T_e=2.59, T_i=0.025, bcL=1, bcR=4, Vl=0.0, Vr=200.0, rf=13.56e6,
                smooth=1, frac=1.5, dt_deck=9.218289085545723e-11, eps_a=1e-6, eps_r=0.0, m=10, beta=0.5, maxIter=100, ion_amu=4.002602,
                per_species_per_gpu=5_000_000),
+    # configs[2]: NGP_Periodic (E-field form), 2048 cells, 1e8 particles, JFNK (deck template OpenMP/NGP_Periodic/InputData:
+    # ion-acoustic shock wave, sine-perturbed drifting Maxwellians, eps_r = 1e-8, m = 20), cell size of the deck kept
+    "c3": dict(name="C3: NGP_Periodic (E-form) ion-acoustic load, 2048 cells, 1e8 particles (2 species), JFNK (NITSOL) eps_r=1e-8 m=20",
+               scheme=2, Nx=2049, L=0.33245599281881233 * 2048 / 512, n_ave=1e14, T_e=5.0, T_i=0.01, bcL=3, bcR=3, Vl=0.0, Vr=0.0, rf=0.0,
+               smooth=0, frac=10.0, dt_deck=1.0, eps_a=0.0, eps_r=1e-8, m=20, beta=0.5, maxIter=100, ion_amu=5.48634767053312,
+               alpha=0.4, distType=2, v_drift=-9372.932223215392, solver_type=1, per_species_per_gpu=50_000_000),
     # configs[0]: the default NGP deck itself (CPU-runnable case)
     "c1": dict(name="C1: default NGP deck, 1000 cells, 1.536e6 particles (2 species)",
                scheme=0, Nx=1001, L=0.067, n_ave=1.6e18, T_e=4.0, T_i=0.025, bcL=1, bcR=4, Vl=0.0, Vr=2000.0, rf=200.0e6,
@@ -132,18 +138,32 @@ def cpu_reference_run(w, steps, warmup, budget_s):
     def make(ppt):
         return op.make_deck_case(w["scheme"], w["Nx"], w["L"], w["n_ave"], w["T_e"], w["T_i"], ppt, T, w["bcL"], w["bcR"], w["Vl"], w["Vr"],
                                  w["rf"], bool(w["smooth"]), ion_amu=w["ion_amu"], eps_a=w["eps_a"], eps_r=w["eps_r"], m_Anderson=w["m"],
-                                 Beta_k=w["beta"], maxIter=w["maxIter"], native=True)
+                                 Beta_k=w["beta"], maxIter=w["maxIter"], native=True, alpha=w.get("alpha", 0.0), distType=w.get("distType", 0),
+                                 v_drift=w.get("v_drift", 0.0))
 
     def run_steps(o, n, tcur, remain, curr):
         sub, secs, iters = 0, 0.0, []
         for _ in range(n):
             t0 = time.perf_counter()
-            remain, curr = o.solvePotential(del_t, remain, curr, tcur)
+            if w.get("solver_type", 0) == 1:
+                # solvePotential with solverType 1: resetVoltage + adaptiveSolveDivAmpereJFNK (step halving on NITSOL failure)
+                o.L.orc_reset_sweep_counters(o.h)
+                o.resetVoltage()
+                curr, halvings = remain, 0
+                info = o.solveJFNK(curr, w["eps_a"], w["eps_r"], w["maxIter"], w["m"])
+                while info["iterm"] != 0 and halvings < 4:
+                    curr, halvings = curr / 2.0, halvings + 1
+                    info = o.solveJFNK(curr, w["eps_a"], w["eps_r"], w["maxIter"], w["m"])
+                remain = del_t if halvings == 0 else remain - curr
+                its = info["nli"]
+            else:
+                remain, curr = o.solvePotential(del_t, remain, curr, tcur)
+                its = None
             secs += time.perf_counter() - t0
             tcur += curr
             st = o.solver_stats()
             sub += st["substeps"]
-            iters.append(st["iterNumPicard"])
+            iters.append(st["iterNumPicard"] if its is None else its)
         return sub, secs, iters, tcur, remain, curr
 
     # calibrate on a small load, then size the sample so that (warmup + steps) fit the budget
@@ -227,11 +247,11 @@ def run_cuda_arm(args, w):
         _lib.check(L.ipic_comm_init(solver._h, world_size, rank, C.c_char_p(raw)))
     w_p = w["n_ave"] * world.L_domain / N_total_per_species                 # mod_particle.f90:76-82 with SUM(N_p) over all ranks
     m_ion = w["ion_amu"] * K.m_amu - K.m_e                                   # mod_particle.f90:334
-    plist = [ip.Particle(K.m_e, -K.e, w_p, 0, 0, "e", 1), ip.Particle(m_ion, K.e, w_p, 0, 0, "He+", 1)]
+    plist = [ip.Particle(K.m_e, -K.e, w_p, 0, 0, "e", 1), ip.Particle(m_ion, K.e, w_p, 0, 0, "ion", 1)]
     solver._bind(plist)
-    _lib.check(L.ipic_generate_particles(solver._h, 0, n_sp, w["T_e"], 0.0, SEED))
-    _lib.check(L.ipic_generate_particles(solver._h, 1, n_sp, w["T_i"], 0.0, SEED))
-    ip.initializeSolver(solver, w["eps_a"], w["eps_r"], 0, w["m"], w["beta"], w["maxIter"])
+    _lib.check(L.ipic_generate_particles_dist(solver._h, 0, n_sp, w["T_e"], w.get("v_drift", 0.0), w.get("alpha", 0.0), w.get("distType", 0), SEED))
+    _lib.check(L.ipic_generate_particles_dist(solver._h, 1, n_sp, w["T_i"], w.get("v_drift", 0.0), w.get("alpha", 0.0), w.get("distType", 0), SEED))
+    ip.initializeSolver(solver, w["eps_a"], w["eps_r"], w.get("solver_type", 0), w["m"], w["beta"], w["maxIter"])
     if args.thomas:
         solver.set_tridiag_mode(_lib.TRIDIAG_THOMAS)
     for k, v in (args.option or []):
@@ -325,7 +345,8 @@ def run_cuda_arm(args, w):
             p.phaseSpace = arr
             p.download()                                             # host copy of the current state
             host.append(ptr)
-        phi_h = solver.phi_f
+        unk = "EField_f" if w["scheme"] == 2 else "phi_f"
+        phi_h = getattr(solver, unk)
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -335,14 +356,14 @@ def run_cuda_arm(args, w):
             for p in plist:                                          # host -> device: phaseSpace + N_p of every species, phi_f
                 p.upload()
                 h2d += int(p.N_p.sum()) * 32
-            solver.phi_f = phi_h
+            setattr(solver, unk, phi_h)
             h2d += phi_h.nbytes
             st = one_step()
             sub2 += st.substeps
             for p in plist:                                          # device -> host: moved particles, counters, new potential
                 p.download()
                 d2h += int(p.N_p.sum()) * 32
-            phi_h = solver.phi_f
+            phi_h = getattr(solver, unk)
             d2h += phi_h.nbytes
         f1.record(stream)
         barrier()
@@ -370,7 +391,7 @@ def run_cuda_arm(args, w):
     alg_bytes_total = 16.0 * (n_dep0 * n_e + n_dep1 * n_i)          # particle counts change by <0.1% per step (wall losses)
     achieved = alg_bytes_total / max(dep_ms * 1e-3, 1e-12) / 1e9
     roofline = {"bound": "hbm", "kernel": "k_push<NGP,deposit> (depositJ sweep, one launch per species)" if w["scheme"] == 0
-                else "k_push<CIC,deposit> (depositJ sweep, one launch per species)",
+                else ("k_push<CIC,deposit>" if w["scheme"] == 1 else "k_push<NGP_Periodic,deposit>") + " (depositJ sweep, one launch per species)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": (args.traffic_bytes_per_particle * (n_e + n_i) / 2.0) if args.traffic_bytes_per_particle else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": 16.0 * (n_e + n_i) / 2.0, "avg_launch_ms": dep_ms / max(dep_launches, 1),
@@ -414,7 +435,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS), help="c5 (default, the bench line) | c1 | c2 | c3: the other BASELINE configs")
     ap.add_argument("--particles-per-species", type=int, default=0, help="override particles per species per GPU (debug)")
     ap.add_argument("--sort-every", type=int, default=5, help="cell-sort the particles every this many steps inside the timed region (0 = never)")
     ap.add_argument("--thomas", action="store_true", help="sequential Thomas solve (bit-parity mode) instead of PCR")

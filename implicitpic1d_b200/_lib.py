@@ -49,6 +49,7 @@ SIGNATURES = {
     "ipic_download_particles": (_i, [_p, _i32, _dp, _ip, _i32, _i32]),
     "ipic_particle_count": (_i, [_p, _i32, C.POINTER(_i64)]),
     "ipic_generate_particles": (_i, [_p, _i32, _i64, _d, _d, C.c_uint64]),
+    "ipic_generate_particles_dist": (_i, [_p, _i32, _i64, _d, _d, _d, _i, C.c_uint64]),
     "ipic_sort_particles": (_i, [_p, _i32]),
     "ipic_get_field": (_i, [_p, _i, _dp, _i32]),
     "ipic_set_field": (_i, [_p, _i, _dp, _i32]),

@@ -478,7 +478,12 @@ int ipic_download_particles(ipic_handle h, int32_t sp, double *ps, int32_t *N_p,
 int ipic_particle_count(ipic_handle h, int32_t sp, int64_t *n) { CTX(h); SPECIES(sp); *n = c->sp[sp].n; return IPIC_OK; }
 int ipic_generate_particles(ipic_handle h, int32_t sp, int64_t n, double T_eV, double v_drift, uint64_t seed) {
     CTX(h); SPECIES(sp);
-    return generate_species(*c, sp, n, T_eV, v_drift, seed);
+    return generate_species(*c, sp, n, T_eV, v_drift, seed, 0.0, 0);
+}
+int ipic_generate_particles_dist(ipic_handle h, int32_t sp, int64_t n, double T_eV, double v_drift, double alpha, int distType, uint64_t seed) {
+    CTX(h); SPECIES(sp);
+    if (distType < 0 || distType > 2) { set_error("distType must be 0 (uniform), 1 (cosine) or 2 (sine)"); return IPIC_ERR_ARG; }
+    return generate_species(*c, sp, n, T_eV, v_drift, seed, alpha, distType);
 }
 int ipic_sort_particles(ipic_handle h, int32_t sp) { CTX(h); SPECIES(sp); Timed t(*c, "sort"); return sort_species(*c, sp); }
 

@@ -157,7 +157,7 @@ int compact_species(Ctx &c, int sp);
 int particle_moments(Ctx &c, int sp, double out4[4]);      // sum v^2, sum vx, vy, vz
 int upload_species(Ctx &c, int sp, const double *ps, const int32_t *N_p, int T, int finalIdx);
 int download_species(Ctx &c, int sp, double *ps, int32_t *N_p, int T, int finalIdx);
-int generate_species(Ctx &c, int sp, long long n, double T_eV, double v_drift, unsigned long long seed);
+int generate_species(Ctx &c, int sp, long long n, double T_eV, double v_drift, unsigned long long seed, double alpha, int distType);
 int sort_species(Ctx &c, int sp);
 int ensure_capacity(Ctx &c, int sp, long long n);
 

@@ -1062,7 +1062,7 @@ __device__ __forceinline__ double pcg_uniform(unsigned long long &state, unsigne
 
 __global__ void k_generate(double *l, double *vx, double *vy, double *vz, long long n, long long first_index, const double *__restrict__ grid,
                            const double *__restrict__ dx, int Nx, int scheme, double startX, double L_domain, double v_therm, double v_drift,
-                           unsigned long long seed) {
+                           unsigned long long seed, double alpha, int distType) {
     const double two_pi = 6.283185307179586476925286766559;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -1072,8 +1072,18 @@ __global__ void k_generate(double *l, double *vx, double *vy, double *vz, long l
         pcg32_next(state, inc);
         state += seed + gid;
         pcg32_next(state, inc);
-        const double U0 = pcg_uniform(state, inc), U1 = pcg_uniform(state, inc), U2 = pcg_uniform(state, inc), U3 = pcg_uniform(state, inc),
-                     U4 = pcg_uniform(state, inc);
+        double U0 = pcg_uniform(state, inc);
+        if (distType != 0) {
+            // initializeRandCosine / initializeRandSine (mod_particle.f90:99-151): rejection on (1 + alpha f(2 pi R2)) / (1 + alpha)
+            double R1 = U0, R2 = pcg_uniform(state, inc);
+            for (int guard = 0; guard < 4096; ++guard) {
+                const double tr = (distType == 1) ? cos(two_pi * R2) : sin(two_pi * R2);
+                if (!(R1 > (1.0 + alpha * tr) / (1.0 + alpha))) break;
+                R1 = pcg_uniform(state, inc); R2 = pcg_uniform(state, inc);
+            }
+            U0 = R2;
+        }
+        const double U1 = pcg_uniform(state, inc), U2 = pcg_uniform(state, inc), U3 = pcg_uniform(state, inc), U4 = pcg_uniform(state, inc);
         const double x = U0 * L_domain + startX;
         int lo = 1, hi = Nx;   // grid arrays here are 0-based: grid[k-1] = grid(k)
         double lpos;
@@ -1087,13 +1097,17 @@ __global__ void k_generate(double *l, double *vx, double *vy, double *vz, long l
         }
         l[i] = lpos;
         const double r1 = v_therm * sqrt(-2.0 * log(U1)), r3 = v_therm * sqrt(-2.0 * log(U3));
-        vx[i] = r1 * cos(two_pi * U2) + v_drift;
+        // generate3DMaxwellian :172-181: position-dependent drift for the perturbed loads
+        double v_extra = v_drift;
+        if (distType == 1) v_extra = v_drift * (1.0 + alpha * cos(two_pi * (x / L_domain)));
+        else if (distType == 2) v_extra = v_drift * (1.0 - alpha * sin(two_pi * (x / L_domain)));
+        vx[i] = r1 * cos(two_pi * U2) + v_extra;
         vy[i] = r1 * sin(two_pi * U2);
         vz[i] = r3 * sin(two_pi * U4);
     }
 }
 
-int generate_species(Ctx &c, int sp, long long n, double T_eV, double v_drift, unsigned long long seed) {
+int generate_species(Ctx &c, int sp, long long n, double T_eV, double v_drift, unsigned long long seed, double alpha, int distType) {
     SpeciesDev &s = c.sp[sp];
     int rc = ensure_capacity(c, sp, n);
     if (rc) return rc;
@@ -1103,7 +1117,7 @@ int generate_species(Ctx &c, int sp, long long n, double T_eV, double v_drift, u
     const double v_therm = sqrt(T_eV * e_c / s.mass);
     const long long first = (long long)c.rank * n;   // ranks draw disjoint index ranges of one global stream
     c.launches += 1; k_generate<<<c.num_sms * 8, 256, 0, c.stream>>>(s.l, s.vx, s.vy, s.vz, n, first, c.d_grid, c.d_dx, c.Nx, c.scheme == IPIC_SCHEME_CIC ? 1 : 0, startX, L, v_therm, v_drift,
-                                                     seed + 0x1000003ULL * (unsigned long long)sp);
+                                                     seed + 0x1000003ULL * (unsigned long long)sp, alpha, distType);
     IPIC_CUDA(cudaGetLastError());
     s.n = n;
     s.slab_off.clear();

@@ -94,6 +94,10 @@ int ipic_particle_count(ipic_handle h, int32_t species, int64_t *n);
 /* device-side synthetic loader for loads too large to stage through the host (bench): uniform positions,
  * Maxwellian velocities (mod_particle.f90:84-97,156-191 rules) from a counter-based PCG32 stream. */
 int ipic_generate_particles(ipic_handle h, int32_t species, int64_t n, double T_eV, double v_drift, uint64_t seed);
+/* same with the perturbed loads of readChargedParticleInputs (mod_particle.f90:99-151,172-181): distType 0 uniform, 1 cosine, 2 sine
+ * density perturbation of amplitude alpha (rejection sampling) and the matching position-dependent drift. */
+int ipic_generate_particles_dist(ipic_handle h, int32_t species, int64_t n, double T_eV, double v_drift, double alpha, int distType,
+                                 uint64_t seed);
 /* periodic cell sort (counting sort on INT(l)); does not change any deposited quantity. */
 int ipic_sort_particles(ipic_handle h, int32_t species);
 
