@@ -380,6 +380,8 @@ int ipic_destroy(ipic_handle h) {
     if (c->d_tileOffset) cudaFree(c->d_tileOffset);
     if (c->d_total) cudaFree(c->d_total);
     if (c->d_slab) cudaFree(c->d_slab);
+    if (c->d_sort) cudaFree(c->d_sort);
+    if (c->d_sort_tmp) cudaFree(c->d_sort_tmp);
     if (c->h_scal) cudaFreeHost(c->h_scal);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->own_stream);
@@ -699,6 +701,7 @@ int ipic_set_option(ipic_handle h, const char *name, double value) {
     const std::string k(name ? name : "");
     if (k == "stay_min" || k == "refill_min") c->stay_min = (int)value;
     else if (k == "push_blocks") c->push_blocks = (int)value;
+    else if (k == "transit_min") c->transit_min = (int)value;
     else if (k == "tile_order") c->tile_order = (int)value;
     else if (k == "timing") c->timing_on = value != 0.0;
     else if (k == "use_tma") { /* accepted for compatibility: the streaming path is register-prefetched */ }

@@ -43,7 +43,10 @@ struct CellTabCIC {   // OpenMP/CIC/src/mod_particleMoverPicard.f90:17-65,92-94 
 };
 
 // streaming geometry of the push kernels
-constexpr int PUSH_THREADS = 1024;
+#ifndef IPIC_PUSH_THREADS
+#define IPIC_PUSH_THREADS 1024
+#endif
+constexpr int PUSH_THREADS = IPIC_PUSH_THREADS;
 constexpr int PUSH_WARPS = PUSH_THREADS / 32;
 constexpr int MAX_GRID_SMEM = 8192;   // largest N_h the shared-memory limb grid supports (12 B per cell)
 
@@ -62,6 +65,7 @@ struct PushArgs {
     int NB;                    // wall index on the right: N_x (NGP) or N_h (CIC)
     double del_t, f_tol;
     int stay_min;              // a queued batch keeps looping in registers while at least this many lanes continue
+    int transit_min;           // the lean face-to-face loop runs while at least this many lanes are in transit
 };
 
 // ---- device context -------------------------------------------------------------------------------
@@ -122,6 +126,7 @@ struct Ctx {
     std::vector<SpeciesDev> sp;
     // options
     int stay_min = 20;
+    int transit_min = 12;
     int tile_order = 1;           // 1 = stride-permuted tile order, 0 = in array order
     int push_blocks = 0;          // 0 = one CTA per SM
     int lazy_compaction = 0;
@@ -135,6 +140,8 @@ struct Ctx {
     // compaction scratch
     unsigned *d_tileCount = nullptr; long long *d_tileOffset = nullptr; double *d_loss = nullptr;
     long long cap_tiles = 0; long long *d_total = nullptr; long long *d_slab = nullptr; int cap_slab = 0;
+    // cell-sort scratch (kept between sorts: cudaMalloc/cudaFree of GB-sized buffers costs more than the sort)
+    unsigned *d_sort = nullptr; long long cap_sort = 0; void *d_sort_tmp = nullptr; size_t cap_sort_tmp = 0;
 };
 
 static constexpr int NSP_MAX = 8;
