@@ -38,6 +38,7 @@ constexpr double eps_0 = 8.8541878128e-12;
 constexpr double m_amu = 1.66053906660e-27;
 constexpr double m_e   = 9.1093837015e-31;
 constexpr double e_c   = 1.602176634e-19;
+constexpr double k_B   = 1.380649e-23;
 const double pi = 4.0 * std::atan(1.0);
 
 inline double fsign(double a, double b) { return std::signbit(b) ? -std::fabs(a) : std::fabs(a); }  // Fortran SIGN(a,b)
@@ -302,12 +303,34 @@ struct NonLin {   // mod_nonLinSolvers.f90:29-35
     dvec normHist;                // residual norms of the last solveDivAmpereAnderson
 };
 
+// ---- mod_targetParticle.f90:13-37  type targetParticle -------------------------
+struct TargetParticle { double mass = 0, density = 0, temperature = 0, v_therm = 0; };
+
+// ---- mod_NullCollision.f90:18-33  type nullCollision ----------------------------
+struct NullCollision {
+    int numberCollisions = 0, lengthArrays = 0;
+    int primary = 0, target = 0;       // reactantsIndx(1), reactantsIndx(2), 1-based
+    dvec energyArray;                  // (lengthArrays), 1-based
+    dvec sigmaArray;                   // (lengthArrays, numberCollisions), 1-based via SA()
+    dvec energyThreshold;              // 1-based
+    ivec collisionType, numberProducts, productsIndx;   // productsIndx(3, numberCollisions) 1-based species numbers
+    double sigmaVMax = 0, reducedMass = 0, minEnergy = 0, maxEnergy = 0, sumMass = 0, reducedMassIonization = 0;
+    std::vector<long long> totalAmountCollisions;
+    dvec totalIncidentEnergy, totalEnergyLoss;
+    long long totalNumberCollidableParticles = 0;
+    double P_null_last = 0;
+    inline double &SA(int j, int i) { return sigmaArray[(size_t)j + (size_t)(lengthArrays + 1) * (size_t)(i - 1)]; }
+    inline int &PI(int k, int i) { return productsIndx[(size_t)k + 4 * (size_t)(i - 1)]; }
+};
+
 struct Oracle {
     Domain world;
     Solver solver;
     std::vector<Species> plist;
     NonLin nl;
     dvec particleTimeStep;        // CIC (Nx, nSpecies)
+    std::vector<TargetParticle> targets;   // targetParticleList
+    std::vector<NullCollision> colls;       // nullCollisionList
     int err = 0;
 };
 
@@ -1634,6 +1657,264 @@ static double P_chargeError(Oracle &o, const double *rho_i /*1-based*/, double d
     return std::sqrt(err / k);
 }
 
+
+// =============================================================================
+// Null-collision Monte-Carlo collisions
+//   OpenMP/SharedModules/src/mod_NullCollision.f90 (constructor :44-108, generateCollision :110-237,
+//   ionizationCollisionIsotropic :359-444, elasticExcitCollisionIsotropic :511-562, scatterVector :634-661)
+//   OpenMP/SharedModules/src/mod_targetParticle.f90:42-56 (generate3DMaxwellianVelocity)
+// Pinned on the reference's own known-answer test OpenMP-BField/TestMCC/MCCExample.f90:13,97-98 (electron swarm in He at
+// 25 Td against the BOLSIG collision frequency) in tests/test_mcc_cpu.py.
+// =============================================================================
+
+// indexSortArray  mod_BasicFunctions.f90:316-403 (Numerical Recipes indexx).  For n < 7 the routine is the straight insertion
+// of :336-345 (stable, ascending); larger inputs take its quicksort, whose result differs from a stable sort only in the order
+// of equal keys -- which no caller depends on (equal energies are removed, equal sigma_v maxima do not occur).
+static void indexSortArray(int n, const double *arr /*1-based*/, int *indx /*1-based*/) {
+    for (int j = 1; j <= n; ++j) indx[j] = j;
+    if (n < 8) {
+        for (int j = 2; j <= n; ++j) {
+            const int indxt = indx[j];
+            const double a = arr[indxt];
+            int i = j - 1;
+            for (; i >= 1; --i) {
+                if (arr[indx[i]] <= a) break;
+                indx[i + 1] = indx[i];
+            }
+            indx[i + 1] = indxt;
+        }
+    } else {
+        std::stable_sort(indx + 1, indx + n + 1, [&](int a, int b) { return arr[a] < arr[b]; });
+    }
+}
+
+// nullCollision_constructor :44-108.  sigma (lengthArrays, numberCollisions) column-major 0-based storage at this interface.
+static void nullCollision_init(NullCollision &nc, int numberCollisions, int lengthArrays, double red_mass, double sumMass,
+                               double redMassTripleProducts, const double *energyArray, const double *sigmaArray, const double *energyThreshold,
+                               const int *collisionType, int primary, int target, const int *numberProducts, const int *productsIndx /*(3,nc)*/) {
+    nc.numberCollisions = numberCollisions; nc.lengthArrays = lengthArrays;
+    nc.sumMass = sumMass; nc.reducedMass = red_mass; nc.reducedMassIonization = redMassTripleProducts;
+    nc.primary = primary; nc.target = target;
+    auto SIG = [&](int j, int i) { return sigmaArray[(size_t)(j - 1) + (size_t)lengthArrays * (size_t)(i - 1)]; };
+    // order collisions by maximum sigma_v in each collision (:55-70)
+    dvec sigma_v_max(numberCollisions + 1, 0.0);
+    ivec indxOrder(numberCollisions + 1, 0);
+    for (int i = 1; i <= numberCollisions; ++i) {
+        sigma_v_max[i] = 0;
+        for (int j = 1; j <= lengthArrays; ++j) {
+            const double v_r = std::sqrt(2.0 * energyArray[j - 1] * e_c / nc.reducedMass);
+            sigma_v_max[i] = std::max(sigma_v_max[i], SIG(j, i) * v_r);
+        }
+    }
+    indexSortArray(numberCollisions, sigma_v_max.data(), indxOrder.data());
+    for (int i = 1; i <= numberCollisions / 2; ++i) std::swap(indxOrder[i], indxOrder[numberCollisions - i + 1]);
+    nc.energyArray.assign(lengthArrays + 1, 0.0);
+    nc.sigmaArray.assign((size_t)(lengthArrays + 1) * numberCollisions + 1, 0.0);
+    nc.energyThreshold.assign(numberCollisions + 1, 0.0);
+    nc.collisionType.assign(numberCollisions + 1, 0); nc.numberProducts.assign(numberCollisions + 1, 0);
+    nc.productsIndx.assign((size_t)4 * numberCollisions + 4, 0);
+    for (int j = 1; j <= lengthArrays; ++j) nc.energyArray[j] = energyArray[j - 1];
+    for (int i = 1; i <= numberCollisions; ++i) {
+        const int j = indxOrder[i];
+        for (int k = 1; k <= lengthArrays; ++k) nc.SA(k, i) = SIG(k, j);
+        nc.energyThreshold[i] = energyThreshold[j - 1];
+        nc.collisionType[i] = collisionType[j - 1];
+        nc.numberProducts[i] = numberProducts[j - 1];
+        for (int k = 1; k <= 3; ++k) nc.PI(k, i) = productsIndx[(k - 1) + 3 * (j - 1)];
+    }
+    // sigma_v_max total along the energy array (:88-98)
+    nc.sigmaVMax = 0.0;
+    for (int i = 1; i <= lengthArrays; ++i) {
+        double sum_sigma = 0;
+        const double v_r = std::sqrt(2.0 * energyArray[i - 1] * e_c / nc.reducedMass);
+        for (int j = 1; j <= numberCollisions; ++j) sum_sigma = sum_sigma + SIG(i, j);
+        nc.sigmaVMax = std::max(nc.sigmaVMax, sum_sigma * v_r);
+    }
+    nc.totalAmountCollisions.assign(numberCollisions + 1, 0);
+    nc.totalIncidentEnergy.assign(numberCollisions + 1, 0.0);
+    nc.totalEnergyLoss.assign(numberCollisions + 1, 0.0);
+    nc.totalNumberCollidableParticles = 0;
+    nc.minEnergy = *std::min_element(energyArray, energyArray + lengthArrays);
+    nc.maxEnergy = *std::max_element(energyArray, energyArray + lengthArrays);
+}
+
+// generate3DMaxwellianVelocity  mod_targetParticle.f90:42-56
+static inline void targetMaxwellian(const TargetParticle &tp, int32_t &irand, double res[3]) {
+    const double U1 = ran2(irand), U2 = ran2(irand), U3 = ran2(irand), U4 = ran2(irand);
+    res[0] = tp.v_therm * std::sqrt(-2 * std::log(U1)) * std::cos(2 * pi * U2);
+    res[1] = tp.v_therm * std::sqrt(-2 * std::log(U1)) * std::sin(2 * pi * U2);
+    res[2] = tp.v_therm * std::sqrt(-2 * std::log(U3)) * std::sin(2 * pi * U4);
+}
+
+// scatterVector :634-661
+static inline void scatterVector(double u[3], const double ev[3], double costheta, double phi) {
+    const double sintheta = std::sqrt(1.0 - costheta * costheta), sinphi = std::sin(phi), cosphi = std::cos(phi);
+    if (std::fabs(ev[1]) > std::fabs(ev[2])) {
+        const double vv = std::sqrt(ev[0] * ev[0] + ev[1] * ev[1]);
+        u[0] = ev[0] * costheta + (ev[1] * sinphi + ev[0] * ev[2] * cosphi) / vv * sintheta;
+        u[1] = ev[1] * costheta + (-ev[0] * sinphi + ev[1] * ev[2] * cosphi) / vv * sintheta;
+        u[2] = ev[2] * costheta - vv * cosphi * sintheta;
+    } else {
+        const double vv = std::sqrt(ev[0] * ev[0] + ev[2] * ev[2]);
+        u[0] = ev[0] * costheta + (ev[2] * sinphi - ev[1] * ev[0] * cosphi) / vv * sintheta;
+        u[1] = ev[1] * costheta + vv * cosphi * sintheta;
+        u[2] = ev[2] * costheta - (ev[0] * sinphi + ev[1] * ev[2] * cosphi) / vv * sintheta;
+    }
+}
+
+// elasticExcitCollisionIsotropic :511-562
+static inline void elasticExcitCollisionIsotropic(const NullCollision &nc, double primary_mass, double target_mass, int32_t &irand, double energyCM,
+                                                  double E_thres, double incidentVelocity[3], double targetVelocity[3]) {
+    const double delE = (energyCM - E_thres) * e_c;
+    double P_beginning[3], V_cm[3], e_vector[3];
+    for (int k = 0; k < 3; ++k) { P_beginning[k] = primary_mass * incidentVelocity[k] + target_mass * targetVelocity[k]; V_cm[k] = P_beginning[k] / nc.sumMass; }
+    const double cos_theta = 1.0 - 2.0 * ran2(irand);
+    const double phi = ran2(irand) * 2.0 * pi;
+    const double sin_theta = std::sqrt(1.0 - cos_theta * cos_theta);
+    const double cos_phi = std::cos(phi), sin_phi = std::sin(phi);
+    e_vector[0] = cos_theta; e_vector[1] = sin_phi * sin_theta; e_vector[2] = cos_phi * sin_theta;
+    const double speedPerParticle = std::sqrt(2.0 * delE * nc.reducedMass / (primary_mass * primary_mass));
+    for (int k = 0; k < 3; ++k) incidentVelocity[k] = e_vector[k] * speedPerParticle + V_cm[k];
+    for (int k = 0; k < 3; ++k) targetVelocity[k] = (P_beginning[k] - primary_mass * incidentVelocity[k]) / target_mass;
+}
+
+// ionizationCollisionIsotropic :359-444 (active statements only)
+static inline void ionizationCollisionIsotropic(const NullCollision &nc, double primary_mass, double ion_mass, double target_mass, int32_t &irand,
+                                                double energyCM, double E_thres, double incidentVelocity[3], double targetVelocity[3],
+                                                double velocityCM[3]) {
+    const double delE = (energyCM - E_thres) * e_c;
+    double P_beginning[3], V_cm[3], e_vector[3], u_vector[3];
+    for (int k = 0; k < 3; ++k) { P_beginning[k] = primary_mass * incidentVelocity[k] + target_mass * targetVelocity[k]; V_cm[k] = P_beginning[k] / nc.sumMass; }
+    double cos_theta = 1.0 - 2.0 * ran2(irand);
+    double phi = ran2(irand) * 2.0 * pi;
+    const double sin_theta = std::sqrt(1.0 - cos_theta * cos_theta);
+    const double cos_phi = std::cos(phi), sin_phi = std::sin(phi);
+    e_vector[0] = cos_theta; e_vector[1] = sin_phi * sin_theta; e_vector[2] = cos_phi * sin_theta;
+    double speedPerParticle = std::sqrt(2.0 * delE * nc.reducedMassIonization / (primary_mass * primary_mass));
+    for (int k = 0; k < 3; ++k) incidentVelocity[k] = e_vector[k] * speedPerParticle + V_cm[k];
+    // second electron: 120 degrees from the first in the centre-of-mass frame
+    cos_theta = std::cos(2.0 * pi / 3.0);
+    phi = ran2(irand) * 2.0 * pi;
+    scatterVector(u_vector, e_vector, cos_theta, phi);
+    speedPerParticle = std::sqrt(2.0 * delE * nc.reducedMassIonization / (m_e * m_e));
+    for (int k = 0; k < 3; ++k) velocityCM[k] = u_vector[k] * speedPerParticle + V_cm[k];
+    for (int k = 0; k < 3; ++k) targetVelocity[k] = (P_beginning[k] - primary_mass * incidentVelocity[k] - m_e * velocityCM[k]) / ion_mass;
+}
+
+// generateCollision :110-237.  irand: T seeds (1-based).  Returns nonzero where the reference `stop`s (P_null > 0.5) or a slab would
+// overflow finalIdx (the reference would write out of bounds).
+static int generateCollision(Oracle &o, NullCollision &nc, int32_t *irand, double del_t) {
+    Species &prim = o.plist[nc.primary - 1];
+    const TargetParticle &tg = o.targets[nc.target - 1];
+    const int T = o.world.T, nC = nc.numberCollisions;
+    const double P_null = 1.0 - std::exp(-nc.sigmaVMax * tg.density * del_t);
+    nc.P_null_last = P_null;
+    if (P_null > 0.5) return 1;
+    const double primary_mass = prim.mass, target_mass = tg.mass;
+    { long long s = 0; for (int t = 1; t <= T; ++t) s += prim.numToCollide[t]; nc.totalNumberCollidableParticles += s; }
+    // OpenMP reduction(+) arrays: per-thread copies added in thread order here
+    std::vector<dvec> energyLossT(T + 1, dvec(nC + 1, 0.0)), totIncT(T + 1, dvec(nC + 1, 0.0));
+    std::vector<std::vector<long long>> totalCollT(T + 1, std::vector<long long>(nC + 1, 0));
+    int overflow = 0;
+#pragma omp parallel for schedule(static, 1) reduction(| : overflow)
+    for (int iThread = 1; iThread <= T; ++iThread) {
+        int32_t irand_thread = irand[iThread];
+        int numberTotalParticles = prim.numToCollide[iThread];
+        const double numberSelectedReal = P_null * (double)numberTotalParticles;   // real(...) of an int32 is exact in single only below 2^24; the product is real64
+        int numberSelected = (int)numberSelectedReal;
+        double Rand = ran2(irand_thread);
+        if (Rand < (numberSelectedReal - numberSelected)) numberSelected = numberSelected + 1;
+        dvec &energyLoss = energyLossT[iThread], &totIncidentEnergy = totIncT[iThread];
+        std::vector<long long> &totalCollisions = totalCollT[iThread];
+        for (int i = 1; i <= numberSelected; ++i) {
+            Rand = ran2(irand_thread);
+            const int particleIndx = (int)((numberTotalParticles)*Rand) + 1;
+            const double particleLocation = prim.P(1, particleIndx, iThread);
+            double incidentVelocity[3] = {prim.P(2, particleIndx, iThread), prim.P(3, particleIndx, iThread), prim.P(4, particleIndx, iThread)};
+            double targetVelocity[3], velocity_CM[3];
+            targetMaxwellian(tg, irand_thread, targetVelocity);
+            for (int k = 0; k < 3; ++k) velocity_CM[k] = incidentVelocity[k] - targetVelocity[k];
+            const double vcm2 = velocity_CM[0] * velocity_CM[0] + velocity_CM[1] * velocity_CM[1] + velocity_CM[2] * velocity_CM[2];
+            const double speedCM = std::sqrt(vcm2);
+            const double energyCM = vcm2 * 0.5 * nc.reducedMass / e_c;   // eV
+            int indxLow = 1, indxHigh = nc.lengthArrays;
+            double d_value;
+            if (energyCM < nc.minEnergy) {
+                d_value = 0.0;
+            } else if (energyCM > nc.maxEnergy) {
+                indxLow = indxHigh - 1;
+                d_value = 1.0;
+            } else {
+                while (indxLow != indxHigh - 1) {
+                    const int indxMiddle = (indxLow + indxHigh) / 2;
+                    if (nc.energyArray[indxMiddle] < energyCM) indxLow = indxMiddle;
+                    else if (nc.energyArray[indxMiddle] > energyCM) indxHigh = indxMiddle;
+                    else { indxLow = indxMiddle; indxHigh = indxLow + 1; }
+                }
+                d_value = (energyCM - nc.energyArray[indxLow]) / (nc.energyArray[indxHigh] - nc.energyArray[indxLow]);
+            }
+            Rand = ran2(irand_thread);
+            double sigma_v_low = 0.0;
+            for (int collIdx = 1; collIdx <= nC; ++collIdx) {
+                if (energyCM > nc.energyThreshold[collIdx]) {
+                    const double sigma_v = (nc.SA(indxLow, collIdx) * (1.0 - d_value) + nc.SA(indxHigh, collIdx) * d_value) * speedCM + sigma_v_low;
+                    const bool collisionBool = (Rand <= sigma_v / nc.sigmaVMax);
+                    if (collisionBool) {
+                        totalCollisions[collIdx] += 1;
+                        const double IncidentEnergy = incidentVelocity[0] * incidentVelocity[0] + incidentVelocity[1] * incidentVelocity[1] +
+                                                      incidentVelocity[2] * incidentVelocity[2];
+                        totIncidentEnergy[collIdx] += IncidentEnergy;
+                        switch (nc.collisionType[collIdx]) {
+                        case 1: case 3:
+                            elasticExcitCollisionIsotropic(nc, primary_mass, target_mass, irand_thread, energyCM, nc.energyThreshold[collIdx],
+                                                           incidentVelocity, targetVelocity);
+                            break;
+                        case 2: {
+                            Species &ion = o.plist[nc.PI(2, collIdx) - 1];
+                            ionizationCollisionIsotropic(nc, primary_mass, ion.mass, target_mass, irand_thread, energyCM, nc.energyThreshold[collIdx],
+                                                         incidentVelocity, targetVelocity, velocity_CM);
+                            if (prim.N_p[iThread] + 1 > prim.finalIdx || ion.N_p[iThread] + 1 > ion.finalIdx) { overflow |= 1; break; }
+                            prim.N_p[iThread] += 1;
+                            ion.N_p[iThread] += 1;
+                            const int ne = prim.N_p[iThread], ni = ion.N_p[iThread];
+                            for (int k = 0; k < 3; ++k) prim.P(2 + k, ne, iThread) = velocity_CM[k];
+                            prim.P(1, ne, iThread) = particleLocation;
+                            for (int k = 0; k < 3; ++k) ion.P(2 + k, ni, iThread) = targetVelocity[k];
+                            ion.P(1, ni, iThread) = particleLocation;
+                            energyLoss[collIdx] = energyLoss[collIdx] -
+                                                  (targetVelocity[0] * targetVelocity[0] + targetVelocity[1] * targetVelocity[1] + targetVelocity[2] * targetVelocity[2]) * target_mass -
+                                                  (velocity_CM[0] * velocity_CM[0] + velocity_CM[1] * velocity_CM[1] + velocity_CM[2] * velocity_CM[2]) * primary_mass;
+                            break; }
+                        case 4:
+                            for (int k = 0; k < 3; ++k) incidentVelocity[k] = targetVelocity[k];
+                            break;
+                        default: break;   // 5: dissociation, nothing happens
+                        }
+                        energyLoss[collIdx] = energyLoss[collIdx] + primary_mass * (IncidentEnergy - (incidentVelocity[0] * incidentVelocity[0] +
+                                              incidentVelocity[1] * incidentVelocity[1] + incidentVelocity[2] * incidentVelocity[2]));
+                        break;
+                    }
+                    sigma_v_low = sigma_v;
+                }
+            }
+            // swap with the last collidable particle so that there are no repeats (:222-227)
+            for (int k = 1; k <= 4; ++k) prim.P(k, particleIndx, iThread) = prim.P(k, numberTotalParticles, iThread);
+            for (int k = 0; k < 3; ++k) prim.P(2 + k, numberTotalParticles, iThread) = incidentVelocity[k];
+            prim.P(1, numberTotalParticles, iThread) = particleLocation;
+            numberTotalParticles = numberTotalParticles - 1;
+        }
+        irand[iThread] = irand_thread;
+        prim.numToCollide[iThread] = numberTotalParticles;
+    }
+    for (int t = 1; t <= T; ++t)
+        for (int c = 1; c <= nC; ++c) {
+            nc.totalAmountCollisions[c] += totalCollT[t][c];
+            nc.totalEnergyLoss[c] += energyLossT[t][c];
+            nc.totalIncidentEnergy[c] += totIncT[t][c];
+        }
+    return overflow ? 2 : 0;
+}
+
 }  // namespace
 
 // =============================================================================
@@ -1825,6 +2106,74 @@ int orc_get_norm_history(void *h, double *out, int nmax) {
     return n;
 }
 void orc_solve_normal_equation(const double *A, const double *b, int m, int n, double *out) { solveNormalEquation(A, b, m, n, out); }
+// ---- null-collision MCC ------------------------------------------------------------------------------------------
+// targetParticle_constructor mod_targetParticle.f90:27-37 (mass in kg)
+int orc_add_target(void *h, double mass, double density, double temperature) {
+    Oracle *o = (Oracle *)h;
+    TargetParticle t; t.mass = mass; t.density = density; t.temperature = temperature;
+    t.v_therm = std::sqrt(t.temperature * k_B / t.mass);
+    o->targets.push_back(t);
+    return (int)o->targets.size() - 1;
+}
+// one reactant pair = one nullCollision (readNullCollisionInputs :821-905 tail: masses -> red_mass, sumMass; constructor).
+// sp/target are 0-based here; productsIndx (3, nc) holds 1-based species numbers as the reference (0 = unused / neutral slot).
+int orc_add_null_collision(void *h, int sp, int target, int numberCollisions, int lengthArrays, const double *energyArray, const double *sigmaArray,
+                           const double *energyThreshold, const int *collisionType, const int *numberProducts, const int *productsIndx,
+                           double redMassTripleProducts) {
+    Oracle *o = (Oracle *)h;
+    const double m1 = o->plist[sp].mass, m2 = o->targets[target].mass;
+    const double red_mass = m1 * m2 / (m1 + m2), sumMass = (m1 + m2);
+    o->colls.emplace_back();
+    nullCollision_init(o->colls.back(), numberCollisions, lengthArrays, red_mass, sumMass, redMassTripleProducts, energyArray, sigmaArray, energyThreshold,
+                       collisionType, sp + 1, target + 1, numberProducts, productsIndx);
+    return (int)o->colls.size() - 1;
+}
+int orc_generate_collision(void *h, int set, int32_t *irand, double del_t) {
+    Oracle *o = (Oracle *)h;
+    std::vector<int32_t> ir(o->world.T + 1);
+    for (int t = 1; t <= o->world.T; ++t) ir[t] = irand[t - 1];
+    const int rc = generateCollision(*o, o->colls[set], ir.data(), del_t);
+    for (int t = 1; t <= o->world.T; ++t) irand[t - 1] = ir[t];
+    return rc;
+}
+// scalars7 = sigmaVMax, reducedMass, sumMass, reducedMassIonization, minEnergy, maxEnergy, P_null of the last call
+void orc_get_collision_scalars(void *h, int set, double *scalars7) {
+    NullCollision &nc = ((Oracle *)h)->colls[set];
+    scalars7[0] = nc.sigmaVMax; scalars7[1] = nc.reducedMass; scalars7[2] = nc.sumMass; scalars7[3] = nc.reducedMassIonization;
+    scalars7[4] = nc.minEnergy; scalars7[5] = nc.maxEnergy; scalars7[6] = nc.P_null_last;
+}
+// the collision tables in the constructor's (sorted) order; sigma as (lengthArrays, numberCollisions) column-major
+void orc_get_collision_tables(void *h, int set, double *energyThreshold, int *collisionType, double *sigmaArray) {
+    NullCollision &nc = ((Oracle *)h)->colls[set];
+    for (int i = 1; i <= nc.numberCollisions; ++i) {
+        energyThreshold[i - 1] = nc.energyThreshold[i]; collisionType[i - 1] = nc.collisionType[i];
+        for (int j = 1; j <= nc.lengthArrays; ++j) sigmaArray[(size_t)(j - 1) + (size_t)nc.lengthArrays * (i - 1)] = nc.SA(j, i);
+    }
+}
+void orc_get_collision_totals(void *h, int set, long long *totalAmountCollisions, double *totalEnergyLoss, double *totalIncidentEnergy,
+                              long long *totalNumberCollidableParticles) {
+    NullCollision &nc = ((Oracle *)h)->colls[set];
+    for (int i = 1; i <= nc.numberCollisions; ++i) {
+        totalAmountCollisions[i - 1] = nc.totalAmountCollisions[i]; totalEnergyLoss[i - 1] = nc.totalEnergyLoss[i];
+        totalIncidentEnergy[i - 1] = nc.totalIncidentEnergy[i];
+    }
+    *totalNumberCollidableParticles = nc.totalNumberCollidableParticles;
+}
+void orc_reset_collision_totals(void *h, int set) {
+    NullCollision &nc = ((Oracle *)h)->colls[set];
+    std::fill(nc.totalAmountCollisions.begin(), nc.totalAmountCollisions.end(), 0LL);
+    std::fill(nc.totalEnergyLoss.begin(), nc.totalEnergyLoss.end(), 0.0);
+    std::fill(nc.totalIncidentEnergy.begin(), nc.totalIncidentEnergy.end(), 0.0);
+    nc.totalNumberCollidableParticles = 0;
+}
+// numToCollide = N_p, the epilogue of moveParticles (mod_particleMover.f90:263), for callers that collide without moving
+void orc_set_num_to_collide(void *h, int sp) { Species &s = ((Oracle *)h)->plist[sp]; for (int t = 1; t <= s.T; ++t) s.numToCollide[t] = s.N_p[t]; }
+void orc_index_sort(int n, const double *arr, int *indx) {   // 0-based in/out wrapper of indexSortArray
+    dvec a(n + 1); ivec ix(n + 1);
+    for (int i = 0; i < n; ++i) a[i + 1] = arr[i];
+    indexSortArray(n, a.data(), ix.data());
+    for (int i = 0; i < n; ++i) indx[i] = ix[i + 1] - 1;
+}
 double orc_ran2(int32_t *irand) { return ran2(*irand); }
 double orc_randPCG(uint64_t *state) { return randPCG(*state); }
 void orc_species_scalars(void *h, int sp, double *out5) {
