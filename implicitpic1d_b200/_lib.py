@@ -25,6 +25,18 @@ class SolverStats(C.Structure):
                 ("lastResidualNorm", C.c_double)]
 
 
+MAX_COLLISIONS = 16
+
+
+class CollisionStats(C.Structure):
+    _fields_ = [("numberCollisions", C.c_int32), ("lengthArrays", C.c_int32), ("collisionType", C.c_int32 * MAX_COLLISIONS),
+                ("energyThreshold", C.c_double * MAX_COLLISIONS), ("sigmaVMax", C.c_double), ("reducedMass", C.c_double),
+                ("sumMass", C.c_double), ("reducedMassIonization", C.c_double), ("minEnergy", C.c_double), ("maxEnergy", C.c_double),
+                ("P_null", C.c_double), ("numberSelected", C.c_int64), ("ionizations", C.c_int64),
+                ("totalAmountCollisions", C.c_int64 * MAX_COLLISIONS), ("totalEnergyLoss", C.c_double * MAX_COLLISIONS),
+                ("totalIncidentEnergy", C.c_double * MAX_COLLISIONS), ("totalNumberCollidableParticles", C.c_int64)]
+
+
 class IpicError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("ipic1d_b200 error %d: %s" % (code, msg))
@@ -48,6 +60,7 @@ SIGNATURES = {
     "ipic_upload_particles": (_i, [_p, _i32, _dp, _ip, _i32, _i32]),
     "ipic_download_particles": (_i, [_p, _i32, _dp, _ip, _i32, _i32]),
     "ipic_particle_count": (_i, [_p, _i32, C.POINTER(_i64)]),
+    "ipic_particle_device_pointers": (_i, [_p, _i32, C.POINTER(_dp), C.POINTER(_dp), C.POINTER(_dp), C.POINTER(_dp), C.POINTER(_i64)]),
     "ipic_generate_particles": (_i, [_p, _i32, _i64, _d, _d, C.c_uint64]),
     "ipic_generate_particles_dist": (_i, [_p, _i32, _i64, _d, _d, _d, _i, C.c_uint64]),
     "ipic_sort_particles": (_i, [_p, _i32]),
@@ -81,6 +94,13 @@ SIGNATURES = {
     "ipic_get_charge_continuity_error": (_i, [_p, _dp, _d, _dp]),
     "ipic_get_total_KE": (_i, [_p, _i32, _dp]),
     "ipic_get_total_momentum": (_i, [_p, _i32, _dp]),
+    "ipic_add_target_particle": (_i, [_p, _d, _d, _d, _ip]),
+    "ipic_null_collision_create": (_i, [_p, _i32, _i32, _d, _d, _d, _dp, _dp, _dp, _ip, _ip, _ip, _ip, C.c_uint64, _ip]),
+    "ipic_generate_collision": (_i, [_p, _i32, _d]),
+    "ipic_get_collision_stats": (_i, [_p, _i32, C.POINTER(CollisionStats)]),
+    "ipic_reset_collision_stats": (_i, [_p, _i32]),
+    "ipic_set_num_to_collide": (_i, [_p, _i32, _i64]),
+    "ipic_mcc_permutation": (_i, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
     "ipic_nccl_unique_id": (_i, [_p]),
     "ipic_comm_init": (_i, [_p, _i32, _i32, _p]),
     "ipic_set_option": (_i, [_p, C.c_char_p, _d]),

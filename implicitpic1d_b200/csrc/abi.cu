@@ -133,6 +133,7 @@ static int move_all(Ctx &c, double del_t) {
             st.energyLoss[0] = st.energyLoss[1] = 0.0;
             if (st.delIdx > 0) RC(compact_species(c, s));
             st.N_p = S.n;
+            S.n_collide = S.n;                            // numToCollide = N_p (mod_particleMover.f90:263)
             if (c.nranks > 1) { /* per-rank statistics; callers all-reduce the scalars they need */ }
             // real(int)/real(int): single-precision division as in mod_particleMover.f90:265-266
             const float denom = (float)(int)(st.N_p + st.delIdx);
@@ -368,6 +369,7 @@ int ipic_destroy(ipic_handle h) {
     g_pool.erase(c); g_pending.erase(c);
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
     delete static_cast<nitsol::Solver *>(c->nitsol_state);
+    collisions_free(*c);
     for (auto &s : c->sp) { if (s.l) cudaFree(s.l); if (s.l2) cudaFree(s.l2); }
     double *dp[] = {c->d_grid, c->d_dx, c->d_phi, c->d_phi_f, c->d_rho, c->d_J, c->d_E, c->d_a, c->d_b, c->d_c, c->d_cp, c->d_m, c->d_pcr, c->d_work,
                     c->d_rho_i, c->d_scal, c->d_phi_k, c->d_res_k, c->d_norms, c->d_loss, c->d_Ef, c->d_Eh};
@@ -478,6 +480,12 @@ int ipic_download_particles(ipic_handle h, int32_t sp, double *ps, int32_t *N_p,
     return download_species(*c, sp, ps, N_p, T, finalIdx);
 }
 int ipic_particle_count(ipic_handle h, int32_t sp, int64_t *n) { CTX(h); SPECIES(sp); *n = c->sp[sp].n; return IPIC_OK; }
+int ipic_particle_device_pointers(ipic_handle h, int32_t sp, double **l, double **vx, double **vy, double **vz, int64_t *n) {
+    CTX(h); SPECIES(sp);
+    SpeciesDev &s = c->sp[sp];
+    if (l) *l = s.l; if (vx) *vx = s.vx; if (vy) *vy = s.vy; if (vz) *vz = s.vz; if (n) *n = s.n;
+    return IPIC_OK;
+}
 int ipic_generate_particles(ipic_handle h, int32_t sp, int64_t n, double T_eV, double v_drift, uint64_t seed) {
     CTX(h); SPECIES(sp);
     return generate_species(*c, sp, n, T_eV, v_drift, seed, 0.0, 0);
@@ -675,6 +683,56 @@ int ipic_get_total_momentum(ipic_handle h, int32_t sp, double *out3) {
     CTX(h); SPECIES(sp);
     double m4[4]; RC(particle_moments(*c, sp, m4));
     for (int k = 0; k < 3; ++k) out3[k] = m4[k + 1] * c->sp[sp].w_p * c->sp[sp].mass;   // :215
+    return IPIC_OK;
+}
+
+// ---- null-collision MCC (collisions.cu) ---------------------------------------------------------------------
+int ipic_add_target_particle(ipic_handle h, double mass, double density, double temperature, int32_t *target) {
+    CTX(h);
+    if (!(mass > 0.0) || density < 0.0 || temperature < 0.0) { set_error("target particle: mass > 0, density >= 0, temperature >= 0"); return IPIC_ERR_ARG; }
+    TargetDev t; t.mass = mass; t.density = density; t.temperature = temperature;
+    t.v_therm = std::sqrt(temperature * 1.380649e-23 / mass);      // mod_targetParticle.f90:36
+    c->targets.push_back(t);
+    if (target) *target = (int32_t)c->targets.size() - 1;
+    return IPIC_OK;
+}
+int ipic_null_collision_create(ipic_handle h, int32_t numberCollisions, int32_t lengthArrays, double red_mass, double sumMass, double redMassTripleProducts,
+                               const double *energyArray, const double *sigmaArray, const double *energyThreshold, const int32_t *collisionType,
+                               const int32_t *reactantsIndx, const int32_t *numberProducts, const int32_t *productsIndx, uint64_t seed,
+                               int32_t *collision_set) {
+    CTX(h);
+    (void)numberProducts;
+    if (!energyArray || !sigmaArray || !energyThreshold || !collisionType || !reactantsIndx || !productsIndx || !collision_set) return IPIC_ERR_ARG;
+    int out = -1;
+    RC(collision_set_create(*c, numberCollisions, lengthArrays, red_mass, sumMass, redMassTripleProducts, energyArray, sigmaArray, energyThreshold,
+                            collisionType, reactantsIndx, productsIndx, seed, &out));
+    *collision_set = out;
+    return IPIC_OK;
+}
+#define COLLSET(s) if ((s) < 0 || (s) >= (int)c->colls.size()) { set_error("bad collision set index"); return IPIC_ERR_ARG; }
+int ipic_generate_collision(ipic_handle h, int32_t set, double del_t) {
+    CTX(h); COLLSET(set);
+    Timed t(*c, "collisions");
+    return generate_collision(*c, set, del_t);
+}
+int ipic_get_collision_stats(ipic_handle h, int32_t set, ipic_collision_stats *out) {
+    CTX(h); COLLSET(set);
+    if (!out) return IPIC_ERR_ARG;
+    *out = c->colls[set].stats;
+    return IPIC_OK;
+}
+int ipic_reset_collision_stats(ipic_handle h, int32_t set) {
+    CTX(h); COLLSET(set);
+    ipic_collision_stats &st = c->colls[set].stats;
+    for (int i = 0; i < IPIC_MAX_COLLISIONS; ++i) { st.totalAmountCollisions[i] = 0; st.totalEnergyLoss[i] = 0.0; st.totalIncidentEnergy[i] = 0.0; }
+    st.totalNumberCollidableParticles = 0;
+    return IPIC_OK;
+}
+int ipic_set_num_to_collide(ipic_handle h, int32_t sp, int64_t n) { CTX(h); SPECIES(sp); c->sp[sp].n_collide = n; return IPIC_OK; }
+int ipic_mcc_permutation(uint64_t n, uint64_t key, uint64_t j0, uint64_t count, uint64_t *out) {
+    if (!out || n == 0 || j0 + count > n) { set_error("mcc permutation: need j0 + count <= n"); return IPIC_ERR_ARG; }
+    const int bits = mcc_bits_hd(n);
+    for (uint64_t k = 0; k < count; ++k) out[k] = mcc_permute_hd(j0 + k, n, bits, key);
     return IPIC_OK;
 }
 

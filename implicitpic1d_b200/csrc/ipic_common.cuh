@@ -78,6 +78,20 @@ struct SpeciesDev {
     std::vector<long long> slab_off;       // numThread+1 offsets of the reference's thread slabs
     ipic_move_stats stats{};
     long long depositSubsteps = 0;
+    long long n_collide = -1;              // numToCollide (mod_particle.f90:17); < 0 = all
+};
+
+// ---- null-collision MCC (collisions.cu) -------------------------------------------------------------
+struct TargetDev { double mass = 0, density = 0, temperature = 0, v_therm = 0; };
+struct CollSet {
+    int nC = 0, nE = 0, primary = 0, target = 0;
+    int type[IPIC_MAX_COLLISIONS] = {}; int ionSpecies[IPIC_MAX_COLLISIONS] = {};
+    double thr[IPIC_MAX_COLLISIONS] = {};
+    double sigmaVMax = 0, reducedMass = 0, sumMass = 0, redMassIon = 0, minE = 0, maxE = 0;
+    double *d_energy = nullptr, *d_sigma = nullptr;      // [nE], [nC][nE]
+    unsigned long long seed = 0, calls = 0;
+    bool has_ionization = false;
+    ipic_collision_stats stats{};
 };
 
 struct Timing { double ms = 0; long long launches = 0; };
@@ -124,6 +138,10 @@ struct Ctx {
     int nitsol_info[7] = {0, 0, 0, 0, 0, 0, 0};                   // nfe, njve, nrpre, nli, nni, nbt, iterm of the last JFNK solve
     double lastNorm = 0;
     std::vector<SpeciesDev> sp;
+    std::vector<TargetDev> targets;
+    std::vector<CollSet> colls;
+    // MCC scratch
+    double *d_mcc = nullptr; long long cap_mcc = 0; void *d_mcc_tmp = nullptr; size_t cap_mcc_tmp = 0;
     // options
     int stay_min = 20;
     int transit_min = 12;
@@ -168,6 +186,13 @@ int generate_species(Ctx &c, int sp, long long n, double T_eV, double v_drift, u
 int sort_species(Ctx &c, int sp);
 int ensure_capacity(Ctx &c, int sp, long long n);
 
+// ---- collisions.cu -----------------------------------------------------------------------------------
+int collision_set_create(Ctx &c, int nC, int nE, double red_mass, double sumMass, double redMassTriple, const double *energyArray, const double *sigmaArray,
+                         const double *energyThreshold, const int32_t *collisionType, const int32_t *reactantsIndx, const int32_t *productsIndx,
+                         unsigned long long seed, int *out);
+int generate_collision(Ctx &c, int set, double del_t);
+void collisions_free(Ctx &c);
+
 // ---- launchers implemented in field.cu --------------------------------------------------------------
 int field_setup(Ctx &c);                                   // construct_diagMatrix + Thomas/PCR factor tables
 int field_finalize_rho(Ctx &c);
@@ -180,6 +205,59 @@ int field_diag(Ctx &c, int which, double del_t, double *out);
 int field_anderson_begin(Ctx &c);
 int field_anderson_step(Ctx &c, int i, int phase, double eps_tol, int *status, double *norm);
 int field_residual(Ctx &c, const double *d_x, double *d_f);
+
+// ---- counter-based PCG32 (one short stream per work item) ------------------------------------------------
+__host__ __device__ __forceinline__ unsigned pcg32_next(unsigned long long &state, unsigned long long inc) {
+    const unsigned long long old = state;
+    state = old * 6364136223846793005ULL + inc;
+    const unsigned xorshifted = (unsigned)(((old >> 18u) ^ old) >> 27u);
+    const unsigned rot = (unsigned)(old >> 59u);
+    return (xorshifted >> rot) | (xorshifted << ((0u - rot) & 31u));
+}
+__host__ __device__ __forceinline__ double pcg_uniform(unsigned long long &state, unsigned long long inc) {
+    // (res + 1) / (2^32 + 1): in (0,1), the mapping of PIC1D/SharedModules/src/PCG_func.c:9-20
+    return ((double)pcg32_next(state, inc) + 1.0) / 4294967297.0;
+}
+// stream `gid` of generator `seed`
+__host__ __device__ __forceinline__ void pcg_seed(unsigned long long &state, unsigned long long &inc, unsigned long long seed, unsigned long long gid) {
+    inc = ((seed ^ (gid * 0x9E3779B97F4A7C15ULL)) << 1u) | 1u;
+    state = 0ULL;
+    pcg32_next(state, inc);
+    state += seed + gid;
+    pcg32_next(state, inc);
+}
+
+// ---- keyed bijection of [0, n): how the MCC draws its collision candidates without replacement -------------
+// Four rounds of (add round key, xorshift, odd multiply) on `bits`-bit integers -- each step is invertible modulo 2^bits, so
+// the composition is a permutation of [0, 2^bits); values >= n are walked through the permutation again (cycle walking,
+// < 2 trips on average since 2^bits < 2n).
+__host__ __device__ __forceinline__ int mcc_bits_hd(unsigned long long n) {
+    int b = 1;
+    while (b < 63 && (1ull << b) < n) ++b;
+    return b;
+}
+__host__ __device__ __forceinline__ unsigned long long mcc_permute_hd(unsigned long long x, unsigned long long n, int bits, unsigned long long key) {
+    const unsigned long long mask = (1ull << bits) - 1ull;
+    const int s1 = (bits + 1) / 2, s2 = (bits + 2) / 3;
+    do {
+        unsigned long long z = key;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            z += 0x9E3779B97F4A7C15ULL;                                  // splitmix64 round keys
+            unsigned long long k = z;
+            k = (k ^ (k >> 30)) * 0xBF58476D1CE4E5B9ULL;
+            k = (k ^ (k >> 27)) * 0x94D049BB133111EBULL;
+            k ^= k >> 31;
+            x = (x + k) & mask;
+            x ^= x >> s1;
+            x = (x * 0xD6E8FEB86659FD93ULL) & mask;
+            x ^= x >> s2;
+            x = (x * 0xCA5A826395121157ULL) & mask;
+            x ^= x >> s1;
+        }
+    } while (x >= n);
+    return x;
+}
 
 // ---- PTX wrappers: mbarrier + bulk async copy (TMA 1-D) ----------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }

@@ -1065,6 +1065,7 @@ int upload_species(Ctx &c, int sp, const double *ps, const int32_t *N_p, int T, 
     }
     s.slab_off[T] = off;
     s.n = n;
+    s.n_collide = n;
     if (n > 0) {
         c.launches += 1; k_aos_to_soa<<<c.num_sms * 4, 256, 0, c.stream>>>(reinterpret_cast<const double4 *>(stage), n, s.l, s.vx, s.vy, s.vz);
         IPIC_CUDA(cudaGetLastError());
@@ -1075,7 +1076,10 @@ int upload_species(Ctx &c, int sp, const double *ps, const int32_t *N_p, int T, 
 
 int download_species(Ctx &c, int sp, double *ps, int32_t *N_p, int T, int finalIdx) {
     SpeciesDev &s = c.sp[sp];
-    if ((int)s.slab_off.size() != T + 1) {
+    bool resplit = (int)s.slab_off.size() != T + 1;
+    if (!resplit)   // a slab outgrew the host's finalIdx (ionization appends to the last slab): rebalance if the total fits
+        for (int t = 0; t < T; ++t) if (s.slab_off[t + 1] - s.slab_off[t] > finalIdx && s.n <= (long long)T * finalIdx) resplit = true;
+    if (resplit) {
         // particles did not come from slabs (device loader / sorted): split evenly, as the reference loader does
         s.slab_off.assign(T + 1, 0);
         for (int t = 0; t <= T; ++t) s.slab_off[t] = s.n * t / T;
@@ -1101,18 +1105,6 @@ int download_species(Ctx &c, int sp, double *ps, int32_t *N_p, int T, int finalI
 // Device synthetic loader: uniform x -> l = getLFromX(x), 3-D Maxwellian by Box-Muller
 // (mod_particle.f90:84-97, 156-191) from a counter-based PCG32 stream (one short stream per particle).
 // =====================================================================================================
-__device__ __forceinline__ unsigned pcg32_next(unsigned long long &state, unsigned long long inc) {
-    const unsigned long long old = state;
-    state = old * 6364136223846793005ULL + inc;
-    const unsigned xorshifted = (unsigned)(((old >> 18u) ^ old) >> 27u);
-    const unsigned rot = (unsigned)(old >> 59u);
-    return (xorshifted >> rot) | (xorshifted << ((0u - rot) & 31u));
-}
-__device__ __forceinline__ double pcg_uniform(unsigned long long &state, unsigned long long inc) {
-    // (res + 1) / (2^32 + 1): in (0,1), the mapping of PIC1D/SharedModules/src/PCG_func.c:9-20
-    return ((double)pcg32_next(state, inc) + 1.0) / 4294967297.0;
-}
-
 __global__ void k_generate(double *l, double *vx, double *vy, double *vz, long long n, long long first_index, const double *__restrict__ grid,
                            const double *__restrict__ dx, int Nx, int scheme, double startX, double L_domain, double v_therm, double v_drift,
                            unsigned long long seed, double alpha, int distType) {
@@ -1173,6 +1165,7 @@ int generate_species(Ctx &c, int sp, long long n, double T_eV, double v_drift, u
                                                      seed + 0x1000003ULL * (unsigned long long)sp, alpha, distType);
     IPIC_CUDA(cudaGetLastError());
     s.n = n;
+    s.n_collide = n;
     s.slab_off.clear();
     IPIC_CUDA(cudaStreamSynchronize(c.stream));
     return IPIC_OK;

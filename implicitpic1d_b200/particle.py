@@ -65,6 +65,20 @@ class Particle:
         _lib.check(_lib.load().ipic_particle_count(self._solver._h, self._index, C.byref(n)))
         return n.value
 
+    def device_arrays(self):
+        """zero-copy torch views (l, v_x, v_y, v_z) of the device-resident arrays; valid until the next call that moves, sorts,
+        compacts, uploads or grows the species"""
+        import torch
+        ptr = [_lib._dp() for _ in range(4)]
+        n = C.c_int64()
+        _lib.check(_lib.load().ipic_particle_device_pointers(self._solver._h, self._index, *[C.byref(p) for p in ptr], C.byref(n)))
+
+        class _View:
+            def __init__(self, addr, count):
+                self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (addr, False), "version": 2}
+        dev = torch.device("cuda", self._solver.device)
+        return tuple(torch.as_tensor(_View(C.cast(p, C.c_void_p).value, n.value), device=dev) for p in ptr)
+
     # ---- mod_particle.f90:206-230
     def getTotalKE(self):
         out = C.c_double()

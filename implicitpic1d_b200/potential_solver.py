@@ -12,6 +12,7 @@ class potentialSolver:
     def __init__(self, world: Domain, leftVoltage, rightVoltage, RF_frequency, timeCurrent, device=0):
         L = _lib.load()
         self.world = world
+        self.device = int(device)
         self._h = C.c_void_p()
         g = np.ascontiguousarray(world.grid, dtype=np.float64)
         dx = np.ascontiguousarray(world.dx_dl, dtype=np.float64)

@@ -91,6 +91,9 @@ int ipic_upload_particles(ipic_handle h, int32_t species, const double *phaseSpa
                           int32_t finalIdx);
 int ipic_download_particles(ipic_handle h, int32_t species, double *phaseSpace, int32_t *N_p, int32_t numThread, int32_t finalIdx);
 int ipic_particle_count(ipic_handle h, int32_t species, int64_t *n);
+/* zero-copy view of the device-resident SoA arrays (valid until the next call that moves, sorts, compacts, uploads or grows
+ * the species); for hosts that run their own kernels on the particles (e.g. through __cuda_array_interface__). */
+int ipic_particle_device_pointers(ipic_handle h, int32_t species, double **l, double **v_x, double **v_y, double **v_z, int64_t *n);
 /* device-side synthetic loader for loads too large to stage through the host (bench): uniform positions,
  * Maxwellian velocities (mod_particle.f90:84-97,156-191 rules) from a counter-based PCG32 stream. */
 int ipic_generate_particles(ipic_handle h, int32_t species, int64_t n, double T_eV, double v_drift, uint64_t seed);
@@ -190,6 +193,48 @@ int ipic_get_error_tridiag_poisson(ipic_handle h, double *out);
 int ipic_get_charge_continuity_error(ipic_handle h, const double *rho_i, double del_t, double *out);
 int ipic_get_total_KE(ipic_handle h, int32_t species, double *out);
 int ipic_get_total_momentum(ipic_handle h, int32_t species, double *out3);
+
+/* ---- null-collision Monte-Carlo collisions ---------------------------------------------------------
+ * replaces: type(targetParticle) + constructor          SharedModules/src/mod_targetParticle.f90:13-37
+ *           type(nullCollision) + constructor           SharedModules/src/mod_NullCollision.f90:18-108
+ *           generateCollision                           :110-237  (called once per set per step, mod_simulation.f90:166-168)
+ *           elasticExcitCollisionIsotropic :511-562, ionizationCollisionIsotropic :359-444, scatterVector :634-661
+ * The arguments of ipic_null_collision_create are those of nullCollision_constructor (:44), arrays in the reference's
+ * order: sigmaArray(lengthArrays, numberCollisions) column-major; reactantsIndx = (charged species, target particle) and
+ * productsIndx(3, numberCollisions) hold the reference's 1-based numbers (species k here = ipic_add_species index k-1).
+ * collisionType: 1 elastic, 2 ionization, 3 excitation, 4 charge exchange, 5 dissociation (:783-792).
+ * Random numbers: a counter-based PCG32 stream per (seed, rank, call, collision candidate) instead of the reference's
+ * per-thread ran2 states, and the `numberSelected` collision candidates are drawn without replacement through a keyed
+ * bijection of [0, numToCollide) instead of the swap-to-end loop (:222-227) -- the same uniform subset statistically,
+ * with no serial dependence.  Particles keep their array positions; products of ionization are appended in candidate order,
+ * so a run is bit-reproducible for a given seed.  Results agree with the reference statistically (moments), not bit-wise. */
+#define IPIC_MAX_COLLISIONS 16
+int ipic_add_target_particle(ipic_handle h, double mass, double density, double temperature, int32_t *target);
+int ipic_null_collision_create(ipic_handle h, int32_t numberCollisions, int32_t lengthArrays, double red_mass, double sumMass,
+                               double redMassTripleProducts, const double *energyArray, const double *sigmaArray, const double *energyThreshold,
+                               const int32_t *collisionType, const int32_t *reactantsIndx, const int32_t *numberProducts,
+                               const int32_t *productsIndx, uint64_t seed, int32_t *collision_set);
+int ipic_generate_collision(ipic_handle h, int32_t collision_set, double del_t);
+typedef struct {
+    int32_t numberCollisions, lengthArrays;
+    int32_t collisionType[IPIC_MAX_COLLISIONS];     /* in the constructor's order (descending max sigma*v, :55-86) */
+    double energyThreshold[IPIC_MAX_COLLISIONS];
+    double sigmaVMax, reducedMass, sumMass, reducedMassIonization, minEnergy, maxEnergy;
+    double P_null;                                  /* of the last call */
+    int64_t numberSelected;                         /* collision candidates of the last call */
+    int64_t ionizations;                            /* particle pairs appended by the last call */
+    int64_t totalAmountCollisions[IPIC_MAX_COLLISIONS];
+    double totalEnergyLoss[IPIC_MAX_COLLISIONS];    /* raw sums in the reference's units (mass * v^2), :216 */
+    double totalIncidentEnergy[IPIC_MAX_COLLISIONS];
+    int64_t totalNumberCollidableParticles;
+} ipic_collision_stats;
+int ipic_get_collision_stats(ipic_handle h, int32_t collision_set, ipic_collision_stats *out);
+int ipic_reset_collision_stats(ipic_handle h, int32_t collision_set);
+/* numToCollide (mod_particle.f90:17): set to N_p by moveParticles (mod_particleMover.f90:263) and by upload; this sets it
+ * explicitly (n < 0: all particles). */
+int ipic_set_num_to_collide(ipic_handle h, int32_t species, int64_t n);
+/* the keyed bijection used to draw collision candidates: out[k] = image of j0 + k in [0, n).  Host function (no GPU needed). */
+int ipic_mcc_permutation(uint64_t n, uint64_t key, uint64_t j0, uint64_t count, uint64_t *out);
 
 /* ---- multi-GPU: particles sharded over ranks, one all-reduce of the fixed-point J/rho grid per deposit ------
  * (pattern of PIC1D/ExplicitPIC_Cpp/src/potential_solver.cpp:142).  unique_id is the 128-byte ncclUniqueId. */

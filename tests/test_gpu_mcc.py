@@ -1,0 +1,210 @@
+"""GPU parity tests of the null-collision MCC (csrc/collisions.cu through the C ABI) against the CPU oracle
+(mod_NullCollision.f90 restated in oracle/ipic_oracle.cpp).  The random streams differ by design (counter-based PCG32 per
+candidate vs per-thread ran2), so the comparison is statistical, on counts and moments, with the tolerances written below;
+what does not depend on the stream (conservation, bookkeeping, reproducibility for a seed) is checked exactly."""
+import os
+import numpy as np
+import pytest
+from oracle import oracle_py as op, mcc_py as mp
+import implicitpic1d_b200 as ip
+from implicitpic1d_b200 import _lib
+from implicitpic1d_b200.domain import readWorld
+
+pytestmark = pytest.mark.gpu
+
+DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "collision_data")
+M_HE = 4.002602 * op.m_amu
+M_AR = 39.948 * op.m_amu
+
+
+def ar_states(T=4, ppt=50000, T_e=20.0, seed=1234):
+    """the same hot argon plasma on both sides: oracle state and CUDA state built from the oracle's particles"""
+    o = op.Oracle(op.NGP, 33, 0.05, T=T)
+    e = o.add_species(op.m_e, -op.e, ppt, 2)
+    o.set_weight(e, 1.0)
+    seeds = op.default_seeds(T)
+    o.load_particles(e, seeds, T_e)
+    ion = o.add_species(M_AR - op.m_e, op.e, ppt, 2)
+    o.set_weight(ion, 1.0)
+    o.load_particles(ion, seeds, 0.05)
+    mp.add_target(o, M_AR, 2.4e21, 300.0)
+    specs = mp.read_null_collision_inputs([os.path.join(DATA, "Ar_electron_table.dat")], [("e", op.m_e), ("Ar+", M_AR - op.m_e)], [("Ar", M_AR)])
+    ncs_o = [mp.NullCollisionOracle(o, s) for s in specs]
+
+    world = readWorld(0, 33, 0.05, 0, 0.0, 1, 1, 0, T_e, 1e15)
+    solver = ip.potentialSolver(world, 0.0, 0.0, 0.0, 0.0)
+    plist = []
+    for sp, nm in ((e, "e"), (ion, "Ar+")):
+        sc = o.species_scalars(sp)
+        ps = o.phase_space(sp)
+        p = ip.Particle(sc["mass"], sc["q"], sc["w_p"], 0, ps.shape[1], nm, T)
+        p.set_phase_space(ps.copy(), o.N_p(sp))
+        plist.append(p)
+    solver._bind(plist)
+    tl = [ip.targetParticle("Ar", M_AR, 2.4e21, 300.0)]
+    ncs_g = ip.readNullCollisionInputs(["Ar_electron_table.dat"], plist, tl, collision_dir=DATA, seed=seed)
+    return o, (e, ion), seeds, ncs_o, solver, plist, tl, ncs_g
+
+
+def alive(p):
+    ps = p.download()
+    return np.concatenate([ps[t, :p.N_p[t]] for t in range(p.numThread)])
+
+
+def test_tables_sorted_like_the_reference_constructor():
+    o, _, _, ncs_o, solver, plist, tl, ncs_g = ar_states(ppt=100)
+    for g, r in zip(ncs_g, ncs_o):
+        for t in tl:
+            t._bind(solver)
+        g._bind(solver)
+        tb, sc = r.tables(), r.scalars()
+        assert np.array_equal(g.collisionType, tb["collisionType"]) and np.array_equal(g.energyThreshold, tb["energyThreshold"])
+        assert abs(g.sigmaVMax - sc["sigmaVMax"]) <= 1e-15 * sc["sigmaVMax"]
+        assert g.minEnergy == sc["minEnergy"] and g.maxEnergy == sc["maxEnergy"]
+    solver.close()
+
+
+def test_counts_and_energy_loss_match_oracle_statistically():
+    """20 collision calls on the same plasma.  Counts per collision type: |N_gpu - N_oracle| < 5 sqrt(N_gpu + N_oracle) (both are
+    sums of independent draws); mean energy loss per collision within 2 % (+ 5 sigma of the mean for rare types); mean electron
+    energy after the calls within 0.5 %."""
+    o, (e, ion), seeds, ncs_o, solver, plist, tl, ncs_g = ar_states()
+    del_t = 1e-10
+    for _ in range(20):
+        for s in (e, ion):
+            mp.set_num_to_collide(o, s)
+        for r in ncs_o:
+            r.generateCollision(seeds, del_t)
+        for p in plist:
+            _lib.check(_lib.load().ipic_set_num_to_collide(solver._h, p._index, -1))
+        for g in ncs_g:
+            g.generateCollision(plist, tl, del_t=del_t)
+    for g, r, mass in zip(ncs_g, ncs_o, (op.m_e, M_AR - op.m_e)):
+        to = r.totals()
+        assert g.totalNumberCollidableParticles == to["totalNumberCollidableParticles"] or \
+            abs(g.totalNumberCollidableParticles - to["totalNumberCollidableParticles"]) < 1e-3 * to["totalNumberCollidableParticles"]
+        assert abs(g.P_null - r.scalars()["P_null"]) < 1e-15
+        for c in range(g.numberCollisions):
+            ng, no = int(g.totalAmountCollisions[c]), int(to["totalAmountCollisions"][c])
+            assert abs(ng - no) < 5.0 * np.sqrt(ng + no + 1), (c, ng, no)
+            if min(ng, no) > 200:
+                lg, lo = g.totalEnergyLoss[c] / ng, to["totalEnergyLoss"][c] / no
+                ig, io = g.totalIncidentEnergy[c] / ng, to["totalIncidentEnergy"][c] / no
+                assert abs(ig - io) < (0.02 + 5.0 / np.sqrt(min(ng, no))) * abs(io), (c, ig, io)
+                # per-collision losses scatter by up to ~ mass * incident v^2 (elastic recoil, charge exchange): 5 sigma of the mean
+                assert abs(lg - lo) < 0.02 * abs(lo) + 5.0 * mass * io / np.sqrt(min(ng, no)), (c, lg, lo)
+    # moments after the calls
+    ke_g = plist[0].getTotalKE() / plist[0].count()
+    ke_o = o.getTotalKE(e) / o.N_p(e).sum()
+    assert abs(ke_g - ke_o) < 5e-3 * ke_o
+    assert abs(plist[0].count() - o.N_p(e).sum()) < 5.0 * np.sqrt(2.0 * (o.N_p(e).sum() - 4 * 50000) + 1)
+    assert plist[0].count() - 4 * 50000 == plist[1].count() - 4 * 50000 > 0
+    solver.close()
+
+
+def test_bookkeeping_is_exact():
+    """what one call changes: exactly the collided particles' velocities, positions never; tallies equal the actual change of
+    sum m v^2; each ionization appends one electron and one ion at the parent's position, in candidate order"""
+    o, (e, ion), seeds, ncs_o, solver, plist, tl, ncs_g = ar_states(ppt=40000)
+    before = [alive(p) for p in plist]
+    g = ncs_g[0]
+    g.generateCollision(plist, tl, del_t=2e-10)
+    after = [alive(p) for p in plist]
+    n0 = before[0].shape[0]
+    nion = int(g.ionizations)
+    ncoll = int(g.totalAmountCollisions.sum())
+    assert nion == int(g.totalAmountCollisions[g.collisionType == 2].sum()) > 5
+    assert after[0].shape[0] == n0 + nion and after[1].shape[0] == before[1].shape[0] + nion
+    assert g.numberSelected in (int(g.P_null * n0), int(g.P_null * n0) + 1)
+    old = after[0][:n0]
+    assert np.array_equal(old[:, 0], before[0][:, 0])                       # nobody moved
+    changed = np.any(old[:, 1:] != before[0][:, 1:], axis=1)
+    assert changed.sum() == ncoll <= g.numberSelected                       # distinct candidates: one change per collision
+    assert np.array_equal(after[1][:before[1].shape[0]], before[1])         # existing ions untouched by the electron set
+    new_e, new_i = after[0][n0:], after[1][before[1].shape[0]:]
+    assert np.array_equal(new_e[:, 0], new_i[:, 0])
+    parents = set(before[0][changed, 0].tolist())
+    assert all(x in parents for x in new_e[:, 0].tolist())
+    # energy tallies (:208,216) against the particles
+    sumv2 = lambda a: (a[:, 1:] ** 2).sum()
+    expect = op.m_e * (sumv2(before[0]) - sumv2(old)) - op.m_e * sumv2(new_e) - M_AR * sumv2(new_i)
+    assert abs(g.totalEnergyLoss.sum() - expect) <= 1e-9 * abs(expect)
+    inc = (before[0][changed, 1:] ** 2).sum()
+    assert abs(g.totalIncidentEnergy.sum() - inc) <= 1e-12 * inc
+    # momentum: ionization conserves m_e v + M v_target = m_e v1 + m_e v2 + m_ion v_ion; the ion's velocity stays thermal-sized
+    assert np.sqrt((new_i[:, 1:] ** 2).sum(axis=1)).max() < 1e4
+    # charge exchange on the ion set: the ion takes a thermal neutral's velocity, counts only
+    gi = ncs_g[1]
+    gi.generateCollision(plist, tl, del_t=2e-8)
+    assert gi.totalAmountCollisions.sum() > 100 and gi.ionizations == 0
+    assert plist[1].count() == after[1].shape[0]
+    solver.close()
+
+
+def test_reproducible_for_a_seed_and_different_otherwise():
+    res = []
+    for seed in (77, 77, 78):
+        o, _, _, _, solver, plist, tl, ncs_g = ar_states(ppt=20000, seed=seed)
+        for _ in range(3):
+            for g in ncs_g:
+                g.generateCollision(plist, tl, del_t=2e-10)
+        res.append([alive(p) for p in plist] + [ncs_g[0].totalEnergyLoss.copy()])
+        solver.close()
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a, b)
+    assert res[0][0].shape != res[2][0].shape or not np.array_equal(res[0][0], res[2][0])
+
+
+def test_p_null_above_one_half_stops():
+    o, _, _, _, solver, plist, tl, ncs_g = ar_states(ppt=100)
+    with pytest.raises(_lib.IpicError) as ei:
+        ncs_g[0].generateCollision(plist, tl, del_t=1e-6)                   # P_null ~ 1: the reference prints and stops (:126-129)
+    assert ei.value.code == _lib.ERR_STOP
+    solver.close()
+
+
+def test_num_to_collide_excludes_particles_born_this_step():
+    """numToCollide is the count after the mover (mod_particleMover.f90:263): products of ionization are not collided again
+    within the step, by either set"""
+    o, _, _, _, solver, plist, tl, ncs_g = ar_states(ppt=20000)
+    n_e, n_i = plist[0].count(), plist[1].count()
+    ncs_g[0].generateCollision(plist, tl, del_t=2e-10)
+    assert plist[0].count() > n_e
+    ncs_g[1].generateCollision(plist, tl, del_t=2e-8)
+    assert ncs_g[1].totalNumberCollidableParticles == n_i
+    ncs_g[0].generateCollision(plist, tl, del_t=2e-10)
+    assert ncs_g[0].totalNumberCollidableParticles == 2 * n_e
+    solver.close()
+
+
+def test_gpu_swarm_reproduces_bolsig_collision_frequency():
+    """The reference's known-answer test on the device (OpenMP-BField/TestMCC/MCCExample.f90): He, 25 Td, nu*dt = 0.02,
+    2 x 25 000 steps on 2e5 electrons; collision frequency within 2 % of BOLSIG after the (1 - exp(-x))/x null-collision factor."""
+    import torch
+    world = readWorld(0, 33, 1.0, 0, 0.0, 1, 1, 0, 1.5, 1e15)
+    solver = ip.potentialSolver(world, 0.0, 0.0, 0.0, 0.0)
+    plist = [ip.Particle(op.m_e, -op.e, 1.0, 0, 0, "e", 1), ip.Particle(M_HE - op.m_e, op.e, 1.0, 0, 0, "He+", 1)]
+    solver._bind(plist)
+    L = _lib.load()
+    _lib.check(L.ipic_generate_particles(solver._h, 0, 200000, 2.25 * 2.0 / 3.0, 0.0, 4242))
+    tl = [ip.targetParticle("He", M_HE, 1e21, 300.0)]
+    nc = ip.readNullCollisionInputs(["turner_benchmark_he_electron_table_noIonization.dat"], plist, tl, collision_dir=DATA, seed=99)[0]
+    bolsig, n_gas = 0.7733e-13, 1e21
+    del_t = 2e-2 / (bolsig * n_gas)
+    accel = -op.e * (25.0 * 1e-21 * n_gas) * del_t / op.m_e
+    _, vx, _, _ = plist[0].device_arrays()
+    steps = 25000
+    for phase in range(2):
+        if phase:
+            nc.reset_totals()
+        for _ in range(steps):
+            vx += accel
+            torch.cuda.synchronize()
+            nc.generateCollision(plist, tl, del_t=del_t)
+    freq = nc.totalAmountCollisions.sum() / steps / del_t / plist[0].count()
+    x = nc.sigmaVMax * n_gas * del_t
+    corrected = freq * x / (1 - np.exp(-x))
+    assert abs(corrected / (bolsig * n_gas) - 1.0) < 0.02, (freq, corrected)
+    ke = plist[0].getTotalKE() / plist[0].count() / op.e          # w_p = 1: joules per particle -> eV
+    assert 6.5 < ke < 9.0
+    solver.close()
