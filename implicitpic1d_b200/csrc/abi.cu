@@ -353,6 +353,7 @@ int ipic_create(ipic_handle *out, int scheme, int32_t Nx, const double *grid, co
     IPIC_CUDA(cudaMemset(c->d_acc, 0, NSP_MAX * 2 * NM * sizeof(unsigned long long)));
     const size_t tabsz = std::max(sizeof(CellTabNGP), sizeof(CellTabCIC));
     IPIC_CUDA(cudaMalloc(&c->d_tab, NSP_MAX * NM * tabsz)); IPIC_CUDA(cudaMemset(c->d_tab, 0, NSP_MAX * NM * tabsz));
+    IPIC_CUDA(cudaMalloc(&c->d_ttab, NSP_MAX * NM * sizeof(double2))); IPIC_CUDA(cudaMemset(c->d_ttab, 0, NSP_MAX * NM * sizeof(double2)));
     IPIC_CUDA(cudaMalloc(&c->d_counters, NSP_MAX * 8 * sizeof(unsigned long long)));
     IPIC_CUDA(cudaMemset(c->d_counters, 0, NSP_MAX * 8 * sizeof(unsigned long long)));
     IPIC_CUDA(cudaMallocHost(&c->h_scal, 64 * sizeof(double)));
@@ -377,6 +378,7 @@ int ipic_destroy(ipic_handle h) {
     if (c->d_bc) cudaFree(c->d_bc);
     if (c->d_acc) cudaFree(c->d_acc);
     if (c->d_tab) cudaFree(c->d_tab);
+    if (c->d_ttab) cudaFree(c->d_ttab);
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->d_tileCount) cudaFree(c->d_tileCount);
     if (c->d_tileOffset) cudaFree(c->d_tileOffset);

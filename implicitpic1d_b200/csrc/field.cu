@@ -42,6 +42,7 @@ struct FieldArgs {
     double *phi, *phi_f, *rho, *J, *E, *a, *b, *c, *cp, *m, *pcr, *work, *scal, *rho_i;
     unsigned long long *acc;
     void *tab;
+    double2 *ttab;
     double qw[NSP_MAX], qm[NSP_MAX];
     double del_t, rho_const, RF_voltage, bound1, bound2, src1, src2, poisson_rf_value;
     double *Ef, *Eh;           // NGP_Periodic (E-field form): EField_f, EField_half
@@ -530,11 +531,13 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
             __syncthreads();
             for (int s = 0; s < A.nsp; ++s) {
                 CellTabNGP *T = reinterpret_cast<CellTabNGP *>(A.tab) + (size_t)s * A.tab_cells;
+                double2 *TT = A.ttab + (size_t)s * A.tab_cells;
                 for (int cI = 1 + threadIdx.x; cI <= Nh; cI += FT) {
                     const double a = A.qm[s] * EF(cI), dx = DX(cI);
                     CellTabNGP t;
                     t.a = a; t.hinv = 0.5 / dx; t.two_a_dx = 2.0 * a * dx; t.inv_a = 1.0 / a;
                     T[cI] = t;
+                    TT[cI] = make_double2(t.two_a_dx, t.inv_a);
                 }
             }
         } else {
@@ -588,11 +591,13 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
         __syncthreads();
         for (int s = 0; s < A.nsp; ++s) {
             CellTabNGP *T = reinterpret_cast<CellTabNGP *>(A.tab) + (size_t)s * A.tab_cells;
+            double2 *TT = A.ttab + (size_t)s * A.tab_cells;
             for (int cI = 1 + threadIdx.x; cI <= Nh; cI += FT) {
                 const double a = A.qm[s] * A.Eh[cI - 1], dx = DX(cI);
                 CellTabNGP t;
                 t.a = a; t.hinv = 0.5 / dx; t.two_a_dx = 2.0 * a * dx; t.inv_a = 1.0 / a;
                 T[cI] = t;
+                TT[cI] = make_double2(t.two_a_dx, t.inv_a);
             }
         }
         __syncthreads();
@@ -747,7 +752,7 @@ static FieldArgs make_args(Ctx &c) {
     A.grid = c.d_grid; A.dx = c.d_dx; A.bc = c.d_bc;
     A.phi = c.d_phi; A.phi_f = c.d_phi_f; A.rho = c.d_rho; A.J = c.d_J; A.E = c.d_E;
     A.a = c.d_a; A.b = c.d_b; A.c = c.d_c; A.cp = c.d_cp; A.m = c.d_m; A.pcr = c.d_pcr;
-    A.work = c.d_work; A.scal = c.d_scal; A.rho_i = c.d_rho_i; A.acc = c.d_acc; A.tab = c.d_tab;
+    A.work = c.d_work; A.scal = c.d_scal; A.rho_i = c.d_rho_i; A.acc = c.d_acc; A.tab = c.d_tab; A.ttab = c.d_ttab;
     for (int s = 0; s < A.nsp && s < NSP_MAX; ++s) { A.qw[s] = c.sp[s].q_times_wp; A.qm[s] = c.sp[s].q_over_m; }
     A.rho_const = c.rho_const; A.RF_voltage = c.RF_voltage;
     A.bound1 = c.boundPhi[0]; A.bound2 = c.boundPhi[1]; A.src1 = c.sourceTermVals[0]; A.src2 = c.sourceTermVals[1];

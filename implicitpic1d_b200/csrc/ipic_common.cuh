@@ -55,6 +55,7 @@ struct PushArgs {
     double *l_out, *vx_out;    // MOVE: in-place outputs
     long long n;               // particles in the arrays (alive or marked dead)
     const void *tab;           // CellTabNGP* / CellTabCIC* for this species
+    const double2 *ttab;       // NGP: compact transit table {2 a dx, 1/a} per cell for this species (16 B: the lean loop's only gather)
     int bcL, bcR;              // boundaryConditions at the two walls (zero everywhere else)
     unsigned *tile_counter;    // dynamic tile scheduler (zeroed before the launch)
     unsigned long long *acc;   // !MOVE: int64 fixed-point grid [Nh] for this species
@@ -64,6 +65,7 @@ struct PushArgs {
     int Nh;                    // grid entries to deposit on
     int NB;                    // wall index on the right: N_x (NGP) or N_h (CIC)
     double del_t, f_tol;
+    double t_lim;              // smallest double t with !(del_t - t > f_tol): `t < t_lim` is the reference's `del_t - t > f_tol`
     int stay_min;              // a queued batch keeps looping in registers while at least this many lanes continue
     int transit_min;           // the lean face-to-face loop runs while at least this many lanes are in transit
 };
@@ -115,6 +117,7 @@ struct Ctx {
     double *d_work = nullptr;                                     // scratch (4 * max(Nx,Nh))
     double *d_rho_i = nullptr;
     unsigned long long *d_acc = nullptr;                          // [nsp_max][2][max(Nx,Nh)+2] int64 accumulators: grid, difference grid
+    double2 *d_ttab = nullptr;                                    // [nsp_max][cells] NGP transit table
     void *d_tab = nullptr;                                        // [nsp_max][cells] CellTab*
     unsigned long long *d_counters = nullptr;                     // [nsp_max][8]
     double *d_scal = nullptr;                                     // small device scalar outputs (64 doubles)

@@ -251,6 +251,47 @@ __device__ __forceinline__ void close_run(WarpSmem &W, DepositState &D, int lane
     }
 }
 
+// One face-to-face crossing of an interior cell in the lean transit loop (NGP sub-step, mod_particleMover.f90:36-60, for a particle
+// that sits on the entry face): s = u^2 +- 2 a dx, u_f = sqrt(s), t_f = t +- (u_f - u)/a, committed when t_f < t_lim.  Same operations and
+// roundings as the general sub-step (the +-1 multipliers are exact, so the two fma are a plain add/sub), written in PTX to pin the
+// instruction sequence: 13 FP64 arithmetic instructions + 1 compare, everything unconditional except the two result writes (predicated
+// on `alive`), no branches.  The square root is the sequence CUDA's own sqrt(double) executes for normal operands (MUFU.RSQ64H seed,
+// one third-order refinement of 1/sqrt, one residual correction of the root: correctly rounded), without its special-operand slow path:
+// s <= 0 (the particle turns around inside the cell) gives NaN or Inf*0, the compare fails and the lane is left to the general sub-step.
+__device__ __forceinline__ int transit_crossing(double u_in, double t_in, double2 tt, double sgn, double t_lim, bool alive, double &u_out, double &t_out) {
+    int ok;
+    asm("{\n\t"
+        ".reg .pred pa, pk;\n\t"
+        ".reg .f64 uu, s, y, t, nt, e, c, p, g, ng, h, r, d;\n\t"
+        ".reg .b32 lo, hi;\n\t"
+        "setp.ne.s32 pa, %8, 0;\n\t"
+        "mul.rn.f64 uu, %3, %3;\n\t"
+        "fma.rn.f64 s, %7, %5, uu;\n\t"
+        "rsqrt.approx.ftz.f64 y, s;\n\t"
+        "mul.rn.f64 t, y, y;\n\t"
+        "neg.f64 nt, t;\n\t"
+        "fma.rn.f64 e, s, nt, 0d3FF0000000000000;\n\t"
+        "fma.rn.f64 c, e, 0d3FD8000000000000, 0d3FE0000000000000;\n\t"
+        "mul.rn.f64 p, y, e;\n\t"
+        "fma.rn.f64 y, c, p, y;\n\t"
+        "mul.rn.f64 g, s, y;\n\t"
+        "mov.b64 {lo, hi}, y;\n\t"
+        "add.s32 hi, hi, -1048576;\n\t"
+        "mov.b64 h, {lo, hi};\n\t"
+        "neg.f64 ng, g;\n\t"
+        "fma.rn.f64 r, g, ng, s;\n\t"
+        "@pa fma.rn.f64 %0, r, h, g;\n\t"
+        "sub.rn.f64 d, %0, %3;\n\t"
+        "mul.rn.f64 d, d, %6;\n\t"
+        "@pa fma.rn.f64 %1, %7, d, %4;\n\t"
+        "setp.lt.and.f64 pk, %1, %9, pa;\n\t"
+        "selp.s32 %2, 1, 0, pk;\n\t"
+        "}"
+        : "+d"(u_out), "+d"(t_out), "=r"(ok)
+        : "d"(u_in), "d"(t_in), "d"(tt.x), "d"(tt.y), "d"(sgn), "r"((int)alive), "d"(t_lim));
+    return ok;
+}
+
 template <int SCHEME, bool MOVE>
 __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -329,31 +370,30 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
                 // decision except within the rounding of that formula itself.  ~2x fewer instructions than the general sub-step.
                 if (SCHEME != 1) {
                     const bool vpos = v > 0.0;
-                    bool tr = valid && (v != 0.0) && (l == (double)(cell + (vpos ? 0 : 1)));
+                    const unsigned tr_span = (unsigned)max(A.NB - 3, 0);          // interior cells 2 .. N_cells-1
+                    bool tr = valid && (v != 0.0) && (l == (double)(cell + (vpos ? 0 : 1))) && ((unsigned)(cell - 2) < tr_span);
                     if (!MOVE) tr = tr && (pend == 0 || ((pend > 0) == vpos));
                     if (__popc(__ballot_sync(FULL, tr)) >= A.transit_min) {
-                        const unsigned tr_span = (unsigned)max(A.NB - 3, 0);      // interior cells 2 .. N_cells-1
-                        const int sflip = vpos ? 0 : (int)0x80000000;
                         const int step = vpos ? 1 : -1;
+                        const int cell_end = vpos ? A.NB - 1 : 1;                // first cell past the interior, along the motion
+                        const double sgn = vpos ? 1.0 : -1.0;
                         const int cell0 = cell;
-                        double u = fabs(v);
+                        // two register copies of (|v|, t): a crossing reads one and writes the other, so committing costs no moves;
+                        // after k committed crossings the valid copy is A (k even) or B (k odd)
+                        double uA = fabs(v), tA = tp, uB = uA, tB = tp;
                         do {
-                            if (tr) {
-                                tr = (unsigned)(cell - 2) < tr_span;
-                                if (tr) {
-                                    const double2 t1 = __ldg(reinterpret_cast<const double2 *>(reinterpret_cast<const CellTabNGP *>(A.tab) + cell) + 1);
-                                    // (two_a_dx, 1/a) seen along the direction of motion
-                                    const double dpe = __hiloint2double(__double2hiint(t1.x) ^ sflip, __double2loint(t1.x));
-                                    const double ia = __hiloint2double(__double2hiint(t1.y) ^ sflip, __double2loint(t1.y));
-                                    const double s = __dadd_rn(dpe, __dmul_rn(u, u));
-                                    const double u_f = sqrt(s);
-                                    const double tpn = __dadd_rn(tp, __dmul_rn(__dsub_rn(u_f, u), ia));
-                                    tr = (s > 0.0) && (del_t - tpn > f_tol);
-                                    if (tr) { tp = tpn; u = u_f; cell += step; nsub += 1; }
-                                }
-                            }
+                            int ok = transit_crossing(uA, tA, __ldg(A.ttab + cell), sgn, A.t_lim, tr, uB, tB);
+                            cell += ok ? step : 0;
+                            tr = ok && (cell != cell_end);
+                            ok = transit_crossing(uB, tB, __ldg(A.ttab + cell), sgn, A.t_lim, tr, uA, tA);
+                            cell += ok ? step : 0;
+                            tr = ok && (cell != cell_end);
                         } while (__popc(__ballot_sync(FULL, tr)) >= A.transit_min);
                         if (cell != cell0) {
+                            const int k = (cell - cell0) * step;
+                            const double u = (k & 1) ? uB : uA;
+                            tp = (k & 1) ? tB : tA;
+                            nsub += (unsigned)k;
                             v = vpos ? u : -u;
                             l = (double)(cell + (vpos ? 0 : 1));
                             if (!MOVE && pend == 0) pend = vpos ? cell0 : -cell0;
@@ -681,6 +721,15 @@ static int make_push_args(Ctx &c, int sp, double del_t, PushArgs &A) {
     A.del_t = del_t;
     // NGP :79,172 ; CIC :90,208 ; NGP_Periodic :75,150 (`del_t * 1e-12` with a default-real literal)
     A.f_tol = del_t * ((c.scheme == IPIC_SCHEME_NGP) ? 1.e-15 : (c.scheme == IPIC_SCHEME_CIC) ? 1.e-10 : (double)1e-12f);
+    {   // `t < t_lim` <=> `del_t - t > f_tol` for every double t: the difference is monotone in t, so the first t that fails the
+        // reference's test (mod_particleMover.f90:89,183) splits the number line exactly
+        double t = A.del_t - A.f_tol;
+        if (!(A.del_t > 0.0) || !std::isfinite(A.del_t)) { set_error("del_t must be positive and finite"); return IPIC_ERR_ARG; }
+        while (A.del_t - t > A.f_tol) t = std::nextafter(t, INFINITY);
+        while (!(A.del_t - std::nextafter(t, -INFINITY) > A.f_tol)) t = std::nextafter(t, -INFINITY);
+        A.t_lim = t;
+    }
+    A.ttab = c.d_ttab + (size_t)sp * (cells + 2);
     A.stay_min = std::min(32, std::max(1, c.stay_min));
     A.transit_min = std::min(33, std::max(1, c.transit_min));   // 33 disables the transit loop
     return IPIC_OK;

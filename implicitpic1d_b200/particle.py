@@ -44,6 +44,41 @@ class Particle:
         self.phaseSpace = ps
         self.N_p = np.ascontiguousarray(N_p, dtype=np.int32).copy()
 
+    # ---- restart files (the reference's particle interchange format)
+    def _thread_file(self, dirName, iThread):
+        # file name of mod_particle.f90:243 / :375 (write(char_i,'(I3)') + trim(adjustl()) -> plain decimal thread number, 1-based)
+        import os
+        return os.path.join(dirName, "PhaseSpace", "phaseSpace_%s_thread%d.dat" % (self.name, iThread))
+
+    def writePhaseSpace(self, dirName, download=True):
+        """writePhaseSpace (mod_particle.f90:234-249): one unformatted stream file per thread slab holding phaseSpace(:, 1:N_p(t), t),
+        i.e. N_p(t) records of (l, v_x, v_y, v_z) as raw little-endian float64.  Pulls the particles from the device first."""
+        import os
+        if download and self._solver is not None:
+            self.download()
+        os.makedirs(os.path.join(dirName, "PhaseSpace"), exist_ok=True)
+        for t in range(self.numThread):
+            np.ascontiguousarray(self.phaseSpace[t, :int(self.N_p[t]), :], dtype="<f8").tofile(self._thread_file(dirName, t + 1))
+
+    def readPhaseSpace(self, restartDirectory, upload=True):
+        """The restart branch of readChargedParticleInputs (mod_particle.f90:371-390): every thread reads its own file until end of file;
+        N_p(t) = number of complete 4-double records.  A missing file stops the reference ('Does not exist'); here it raises."""
+        import os
+        if self.phaseSpace is None:
+            self.phaseSpace = np.zeros((self.numThread, self.finalIdx, 4))
+        for t in range(self.numThread):
+            fn = self._thread_file(restartDirectory, t + 1)
+            if not os.path.exists(fn):
+                raise FileNotFoundError(fn + " Does not exist")
+            raw = np.fromfile(fn, dtype="<f8")
+            n = raw.size // 4
+            if n > self.finalIdx:
+                raise ValueError("%s holds %d particles, more than finalIdx = %d" % (fn, n, self.finalIdx))
+            self.phaseSpace[t, :n, :] = raw[:4 * n].reshape(n, 4)
+            self.N_p[t] = n
+        if upload and self._solver is not None:
+            self.upload()
+
     # ---- device residency
     def upload(self):
         if self._solver is None:

@@ -1205,58 +1205,72 @@ static double wtime() {
 #endif
 }
 
-// solveDivAmpereAnderson  mod_nonLinSolvers.f90:85-160
-static void solveDivAmpereAnderson(Oracle &o, double del_t) {
-    Solver &s = o.solver; NonLin &nl = o.nl;
-    const int Nx = o.world.Nx, m = nl.m_Anderson, M1 = m + 1;
-    auto PK = [&](int i, int c) -> double & { return nl.phi_k[(size_t)(i - 1) + (size_t)Nx * (c - 1)]; };
-    auto RK = [&](int i, int c) -> double & { return nl.Residual_k[(size_t)(i - 1) + (size_t)Nx * (c - 1)]; };
+// The Anderson(m) fixed-point loop of solveDivAmpereAnderson (mod_nonLinSolvers.f90:96-158; NGP_Periodic twin :93-140), written once
+// over the map x <- G(x): `G()` overwrites x[1..N] with G(x), `onConverged()` is what the reference does when the norm test passes
+// (moveParticles).  The two trees differ only in the stagnation window (`nAvg` past norms, used when m > mMin) and in the value
+// stored in iterNumPicard on convergence (`iterAdd`).  Also driven stand-alone (orc_anderson_fixed_point) on the reference's own
+// Anderson test problem (Serial/TestAndersonAcceleration/main.f90).
+template <class GFun, class DoneFun>
+static void andersonLoop(NonLin &nl, int N, double *x /* 1-based */, int nAvg, int mMin, int iterAdd, GFun G, DoneFun onConverged) {
+    const int m = nl.m_Anderson, M1 = m + 1;
+    if ((int)nl.phi_k.size() < N * M1) { nl.phi_k.assign((size_t)N * M1, 0.0); nl.Residual_k.assign((size_t)N * M1, 0.0); nl.fitMat.assign((size_t)N * m, 0.0); }
+    auto PK = [&](int i, int c) -> double & { return nl.phi_k[(size_t)(i - 1) + (size_t)N * (c - 1)]; };
+    auto RK = [&](int i, int c) -> double & { return nl.Residual_k[(size_t)(i - 1) + (size_t)N * (c - 1)]; };
     dvec normResidual(M1 + 1, 0.0), alpha(M1 + 1, 0.0);
     nl.normHist.clear();
-    makeConstSourceTerm(o);
-    for (int i = 1; i <= Nx; ++i) PK(i, 1) = s.phi_f[i];
-    double t0 = wtime(); depositJ(o, del_t); nl.moverSeconds += wtime() - t0;
-    t0 = wtime(); solve_tridiag_Ampere(o, del_t); nl.potSeconds += wtime() - t0;
-    for (int i = 1; i <= Nx; ++i) { PK(i, 2) = s.phi_f[i]; RK(i, 1) = PK(i, 2) - PK(i, 1); }
-    { double sm = 0.0; for (int i = 1; i <= Nx; ++i) sm += RK(i, 1) * RK(i, 1); normResidual[1] = std::sqrt(sm); }
+    for (int i = 1; i <= N; ++i) PK(i, 1) = x[i];
+    G();
+    for (int i = 1; i <= N; ++i) { PK(i, 2) = x[i]; RK(i, 1) = PK(i, 2) - PK(i, 1); }
+    { double sm = 0.0; for (int i = 1; i <= N; ++i) sm += RK(i, 1) * RK(i, 1); normResidual[1] = std::sqrt(sm); }
     nl.normHist.push_back(normResidual[1]);
-    double eps_tol = nl.eps_r * normResidual[1] + nl.eps_a * (double)std::sqrt((float)Nx)   /* SQRT(real(N)) is single precision */;
+    const double eps_tol = nl.eps_r * normResidual[1] + nl.eps_a * (double)std::sqrt((float)N)   /* SQRT(real(N)) is single precision */;
     for (int i = 1; i <= nl.maxIter; ++i) {
-        int index = fmodulo(i, M1) + 1;
-        int m_k = std::min(i, m);
-        t0 = wtime(); depositJ(o, del_t); nl.moverSeconds += wtime() - t0;
-        t0 = wtime(); solve_tridiag_Ampere(o, del_t); nl.potSeconds += wtime() - t0;
-        for (int k = 1; k <= Nx; ++k) RK(k, index) = s.phi_f[k] - PK(k, index);
-        { double sm = 0.0; for (int k = 1; k <= Nx; ++k) sm += RK(k, index) * RK(k, index); normResidual[index] = std::sqrt(sm); }
+        const int index = fmodulo(i, M1) + 1, m_k = std::min(i, m);
+        G();
+        for (int k = 1; k <= N; ++k) RK(k, index) = x[k] - PK(k, index);
+        { double sm = 0.0; for (int k = 1; k <= N; ++k) sm += RK(k, index) * RK(k, index); normResidual[index] = std::sqrt(sm); }
         nl.normHist.push_back(normResidual[index]);
         if (normResidual[index] < eps_tol) {
-            t0 = wtime(); moveParticles(o, del_t); nl.moverSeconds += wtime() - t0;
-            nl.iterNumPicard = i + 1;
+            onConverged();
+            nl.iterNumPicard = i + iterAdd;
             return;
         }
         if (i > m) {
             double sumPast;
-            if (m > 3) {
-                sumPast = normResidual[fmodulo(i - 1, M1) + 1] + normResidual[fmodulo(i - 2, M1) + 1] + normResidual[fmodulo(i - 3, M1) + 1];
-                sumPast = sumPast / 3.0;
+            if (m > mMin) {
+                sumPast = 0.0;
+                for (int k = 1; k <= nAvg; ++k) sumPast += normResidual[fmodulo(i - k, M1) + 1];   // same left-to-right order as the source
+                sumPast = sumPast / (double)nAvg;
             } else sumPast = normResidual[fmodulo(i - 1, M1) + 1];
             if (normResidual[index] > sumPast) { nl.iterNumPicard = nl.maxIter; return; }
         }
         for (int j = 0; j <= m_k - 1; ++j) {
-            int cj = fmodulo(i - m_k + j, M1) + 1;
-            for (int k = 1; k <= Nx; ++k) nl.fitMat[(size_t)(k - 1) + (size_t)Nx * j] = RK(k, index) - RK(k, cj);
+            const int cj = fmodulo(i - m_k + j, M1) + 1;
+            for (int k = 1; k <= N; ++k) nl.fitMat[(size_t)(k - 1) + (size_t)N * j] = RK(k, index) - RK(k, cj);
         }
-        solveNormalEquation(nl.fitMat.data(), &RK(1, index), Nx, m_k, &alpha[1]);
+        solveNormalEquation(nl.fitMat.data(), &RK(1, index), N, m_k, &alpha[1]);
         { double sa = 0.0; for (int j = 1; j <= m_k; ++j) sa += alpha[j]; alpha[m_k + 1] = 1.0 - sa; }
-        int cn = fmodulo(i + 1, M1) + 1, c0 = fmodulo(i - m_k, M1) + 1;
-        for (int k = 1; k <= Nx; ++k) PK(k, cn) = alpha[1] * (nl.Beta_k * RK(k, c0) + PK(k, c0));
+        const int cn = fmodulo(i + 1, M1) + 1, c0 = fmodulo(i - m_k, M1) + 1;
+        for (int k = 1; k <= N; ++k) PK(k, cn) = alpha[1] * (nl.Beta_k * RK(k, c0) + PK(k, c0));
         for (int j = 1; j <= m_k; ++j) {
-            int cj = fmodulo(i - m_k + j, M1) + 1;
-            for (int k = 1; k <= Nx; ++k) PK(k, cn) = PK(k, cn) + alpha[j + 1] * (nl.Beta_k * RK(k, cj) + PK(k, cj));
+            const int cj = fmodulo(i - m_k + j, M1) + 1;
+            for (int k = 1; k <= N; ++k) PK(k, cn) = PK(k, cn) + alpha[j + 1] * (nl.Beta_k * RK(k, cj) + PK(k, cj));
         }
-        for (int k = 1; k <= Nx; ++k) s.phi_f[k] = PK(k, cn);
+        for (int k = 1; k <= N; ++k) x[k] = PK(k, cn);
     }
     // loop exhausted: the reference leaves iterNumPicard untouched (:112-158)
+}
+
+// solveDivAmpereAnderson  mod_nonLinSolvers.f90:85-160 (stagnation: mean of the last three norms when m > 3, :120-126)
+static void solveDivAmpereAnderson(Oracle &o, double del_t) {
+    Solver &s = o.solver; NonLin &nl = o.nl;
+    makeConstSourceTerm(o);
+    andersonLoop(nl, o.world.Nx, s.phi_f.data(), 3, 3, 1,
+        [&]() {
+            double t0 = wtime(); depositJ(o, del_t); nl.moverSeconds += wtime() - t0;
+            t0 = wtime(); solve_tridiag_Ampere(o, del_t); nl.potSeconds += wtime() - t0;
+        },
+        [&]() { double t0 = wtime(); moveParticles(o, del_t); nl.moverSeconds += wtime() - t0; });
 }
 
 // adaptiveSolveDivAmpereAnderson  mod_nonLinSolvers.f90:162-196 ; returns nonzero where the reference `stop`s
@@ -1552,50 +1566,13 @@ static void P_sweep(Oracle &o, double del_t) {
     }
 }
 
-// solveDivAmpereAnderson  NGP_Periodic/src/mod_nonLinSolvers.f90:85-141: Anderson on EField_f (N_h); iterNumPicard = i
+// solveDivAmpereAnderson  NGP_Periodic/src/mod_nonLinSolvers.f90:85-141: Anderson on EField_f (N_h); iterNumPicard = i;
+// stagnation: mean of the last two norms when m > 1
 static void P_solveDivAmpereAnderson(Oracle &o, double del_t) {
     Solver &s = o.solver; NonLin &nl = o.nl;
-    const int N = o.world.Nh, m = nl.m_Anderson, M1 = m + 1;
-    if ((int)nl.phi_k.size() < N * M1) { nl.phi_k.assign((size_t)N * M1, 0.0); nl.Residual_k.assign((size_t)N * M1, 0.0); nl.fitMat.assign((size_t)N * m, 0.0); }
-    auto EK = [&](int i, int c) -> double & { return nl.phi_k[(size_t)(i - 1) + (size_t)N * (c - 1)]; };
-    auto RK = [&](int i, int c) -> double & { return nl.Residual_k[(size_t)(i - 1) + (size_t)N * (c - 1)]; };
-    dvec normResidual(M1 + 1, 0.0), alpha(M1 + 1, 0.0);
-    nl.normHist.clear();
-    for (int i = 1; i <= N; ++i) EK(i, 1) = s.EField_f[i];
-    P_sweep<false>(o, del_t);
-    P_solve_tridiag_Ampere(o, del_t);
-    for (int i = 1; i <= N; ++i) { EK(i, 2) = s.EField_f[i]; RK(i, 1) = EK(i, 2) - EK(i, 1); }
-    { double sm = 0.0; for (int i = 1; i <= N; ++i) sm += RK(i, 1) * RK(i, 1); normResidual[1] = std::sqrt(sm); }
-    nl.normHist.push_back(normResidual[1]);
-    const double eps_tol = nl.eps_r * normResidual[1] + nl.eps_a * (double)std::sqrt((float)N);
-    for (int i = 1; i <= nl.maxIter; ++i) {
-        const int index = fmodulo(i, M1) + 1, m_k = std::min(i, m);
-        P_sweep<false>(o, del_t);
-        P_solve_tridiag_Ampere(o, del_t);
-        for (int k = 1; k <= N; ++k) RK(k, index) = s.EField_f[k] - EK(k, index);
-        { double sm = 0.0; for (int k = 1; k <= N; ++k) sm += RK(k, index) * RK(k, index); normResidual[index] = std::sqrt(sm); }
-        nl.normHist.push_back(normResidual[index]);
-        if (normResidual[index] < eps_tol) { P_sweep<true>(o, del_t); nl.iterNumPicard = i; return; }
-        if (i > m) {
-            double sumPast;
-            if (m > 1) sumPast = (normResidual[fmodulo(i - 1, M1) + 1] + normResidual[fmodulo(i - 2, M1) + 1]) / 2.0;
-            else sumPast = normResidual[fmodulo(i - 1, M1) + 1];
-            if (normResidual[index] > sumPast) { nl.iterNumPicard = nl.maxIter; return; }
-        }
-        for (int j = 0; j <= m_k - 1; ++j) {
-            const int cj = fmodulo(i - m_k + j, M1) + 1;
-            for (int k = 1; k <= N; ++k) nl.fitMat[(size_t)(k - 1) + (size_t)N * j] = RK(k, index) - RK(k, cj);
-        }
-        solveNormalEquation(nl.fitMat.data(), &RK(1, index), N, m_k, &alpha[1]);
-        { double sa = 0.0; for (int j = 1; j <= m_k; ++j) sa += alpha[j]; alpha[m_k + 1] = 1.0 - sa; }
-        const int cn = fmodulo(i + 1, M1) + 1, c0 = fmodulo(i - m_k, M1) + 1;
-        for (int k = 1; k <= N; ++k) EK(k, cn) = alpha[1] * (nl.Beta_k * RK(k, c0) + EK(k, c0));
-        for (int j = 1; j <= m_k; ++j) {
-            const int cj = fmodulo(i - m_k + j, M1) + 1;
-            for (int k = 1; k <= N; ++k) EK(k, cn) = EK(k, cn) + alpha[j + 1] * (nl.Beta_k * RK(k, cj) + EK(k, cj));
-        }
-        for (int k = 1; k <= N; ++k) s.EField_f[k] = EK(k, cn);
-    }
+    andersonLoop(nl, o.world.Nh, s.EField_f.data(), 2, 1, 0,
+        [&]() { P_sweep<false>(o, del_t); P_solve_tridiag_Ampere(o, del_t); },
+        [&]() { P_sweep<true>(o, del_t); });
 }
 
 // adaptiveSolveDivAmpereAnderson :142-172 (setRFVoltage is an empty routine in this tree) ; solvePotential :173-189
@@ -2209,4 +2186,22 @@ double orc_p_charge_error(void *h, const double *rho_i, double del_t) {
 }
 double orc_p_aveJ(void *h) { return ((Oracle *)h)->solver.aveJ; }
 void orc_reset_sweep_counters(void *h) { Oracle *o = (Oracle *)h; o->nl.sweeps = 0; o->nl.substeps = 0; }
+
+// The Anderson loop of solveDivAmpereAnderson on a caller-supplied map x <- G(x) (known-answer tests: the reference's own
+// Serial/TestAndersonAcceleration/main.f90 problem).  Returns iterNumPicard as the reference would store it (maxIter on stagnation,
+// 0 when the loop is exhausted); the residual norms go to normHist.
+int orc_anderson_fixed_point(void (*G)(int n, const double *x, double *gx, void *user), void *user, int n, double *x, int m_Anderson, double Beta_k,
+                             double eps_a, double eps_r, int maxIter, int periodicTree, double *normHist, int histCap, int *nHist) {
+    NonLin nl;
+    nl.m_Anderson = m_Anderson; nl.Beta_k = Beta_k; nl.eps_a = eps_a; nl.eps_r = eps_r; nl.maxIter = maxIter; nl.iterNumPicard = 0;
+    dvec xv(n + 1, 0.0), gx(n);
+    for (int i = 0; i < n; ++i) xv[i + 1] = x[i];
+    auto map = [&]() { G(n, xv.data() + 1, gx.data(), user); for (int i = 0; i < n; ++i) xv[i + 1] = gx[i]; };
+    if (periodicTree) andersonLoop(nl, n, xv.data(), 2, 1, 0, map, []() {});
+    else andersonLoop(nl, n, xv.data(), 3, 3, 1, map, []() {});
+    for (int i = 0; i < n; ++i) x[i] = xv[i + 1];
+    if (nHist) *nHist = (int)nl.normHist.size();
+    for (int i = 0; i < (int)nl.normHist.size() && i < histCap; ++i) normHist[i] = nl.normHist[i];
+    return nl.iterNumPicard;
+}
 }  // extern "C"

@@ -80,6 +80,17 @@ elif stage in ("perf", "prof"):
         print("warm step", k, "iters", st.iterNumPicard, "substeps/particle/sweep %.3f" % (st.substeps / (st.sweeps + 1) / (2 * N)), "norm0 %.3e" % st.normHistory[0], flush=True)
     for pp in plist:
         _lib.check(L.ipic_sort_particles(solver._h, pp._index))
+    if os.environ.get("IPIC_PROF_STEP"):
+        # profile one whole implicit step at the operating point reached after `nwarm` steps (run ncu with --profile-from-start off)
+        cu = C.CDLL("libcuda.so.1")
+        solver.synchronize()
+        cu.cuProfilerStart()
+        remain, curr = ip.solvePotential(solver, plist, world, del_t, remain, curr, tcur)
+        solver.synchronize()
+        cu.cuProfilerStop()
+        st = ip.SolverState(solver)
+        print("profiled step: iters", st.iterNumPicard, "sweeps", st.sweeps, "substeps/particle/sweep %.3f" % (st.substeps / (st.sweeps + 1) / (2 * N)), flush=True)
+        print("PROF STEP DONE"); sys.exit(0)
     if stage == "prof":
         solver.set_option("use_tma", int(sys.argv[6]) if len(sys.argv) > 6 else 1)
         ip.depositJ(solver, plist, world, del_t)

@@ -90,6 +90,53 @@ def test_normal_equation_solves_least_squares():
     np.testing.assert_allclose(out, ref, rtol=1e-9, atol=1e-12)
 
 
+def test_anderson_loop_on_reference_test_problem():
+    """Serial/TestAndersonAcceleration/main.f90: 64-node Poisson (62 unknowns) written as the Jacobi fixed point phi = A phi - b, m = 3, mixing 1,
+    relative tolerance 1e-8.  The reference prints the Picard and Anderson iteration counts and phi; the known answer is the direct solve.  The
+    oracle's Anderson loop (the one solveDivAmpereAnderson runs, normal equations and all) must reach it, far faster than Picard."""
+    n, L = 62, 0.1
+    delx = L / 63.0
+    rho = op.e * 1.0e12
+    b = np.full(n, -rho * delx ** 2 / op.eps_0 / 2.0)
+    A = np.zeros((n, n))
+    A[np.arange(n - 1), np.arange(1, n)] = 0.5
+    A[np.arange(1, n), np.arange(n - 1)] = 0.5
+    exact = np.linalg.solve(np.eye(n) - A, -b)
+    # Picard, as main.f90:32-39
+    phi = np.zeros(n)
+    r0 = np.linalg.norm(A @ phi - b - phi)
+    picard = None
+    for i in range(1, 50001):
+        phi = A @ phi - b
+        if np.linalg.norm(A @ phi - b - phi) < r0 * 1e-8:
+            picard = i
+            break
+    assert picard is not None and picard > 2000
+    calls = [0]
+    CB = op.C.CFUNCTYPE(None, op.C.c_int, op.C.POINTER(op.C.c_double), op.C.POINTER(op.C.c_double), op.C.c_void_p)
+
+    def G(nn, px, pg, user):
+        x = np.ctypeslib.as_array(px, shape=(nn,))
+        g = np.ctypeslib.as_array(pg, shape=(nn,))
+        g[:] = A @ x - b
+        calls[0] += 1
+    cb = CB(G)
+    L_ = op.lib()
+    L_.orc_anderson_fixed_point.restype = op.C.c_int
+    for periodic_tree in (0, 1):
+        x = np.zeros(n)
+        hist = np.zeros(4096)
+        nh = op.C.c_int()
+        calls[0] = 0
+        it = L_.orc_anderson_fixed_point(cb, None, n, x.ctypes.data_as(op.C.POINTER(op.C.c_double)), 3, op.C.c_double(1.0), op.C.c_double(0.0),
+                                         op.C.c_double(1e-8), 10000, periodic_tree, hist.ctypes.data_as(op.C.POINTER(op.C.c_double)), 4096, op.C.byref(nh))
+        assert 0 < it < 10000 and it < picard // 4, (it, picard)
+        # iterNumPicard is i + 1 in the bounded tree (mod_nonLinSolvers.f90:134), i in the periodic tree (:121); G ran 1 + i times
+        assert calls[0] == nh.value == it + periodic_tree
+        assert hist[nh.value - 1] < 1e-8 * hist[0]
+        assert np.max(np.abs(x - exact)) < 1e-6 * np.max(np.abs(exact))
+
+
 @pytest.mark.parametrize("name", sorted(DECKS))
 def test_reference_invariants_one_step(name):
     """main.f90:58-114: energy error ~ solver tolerance, charge/Gauss error ~ round-off after one implicit step."""
@@ -175,3 +222,29 @@ def test_no_gpu_means_loud_failure(gpu_available):
     w = readWorld(0, 33, 0.01, 0, 0.0, 1, 1, 0, 2.0, 1e15)
     with pytest.raises(ip.IpicError):
         ip.potentialSolver(w, 0.0, 0.0, 0.0, 0.0)
+
+
+def test_restart_phase_space_files_round_trip(tmp_path):
+    """writePhaseSpace (mod_particle.f90:234-249) / restart read (:371-390): one raw float64 stream per thread slab, N_p from the file length."""
+    import implicitpic1d_b200 as ip
+    rng = np.random.default_rng(3)
+    T, finalIdx = 3, 50
+    p = ip.Particle(op.m_e, -op.e, 1.0, 0, finalIdx, "e", T)
+    ps = rng.normal(size=(T, finalIdx, 4))
+    N_p = np.array([17, 0, 50], dtype=np.int32)
+    p.set_phase_space(ps, N_p)
+    p.writePhaseSpace(str(tmp_path), download=False)
+    for t in range(T):
+        fn = tmp_path / "PhaseSpace" / ("phaseSpace_e_thread%d.dat" % (t + 1))
+        assert fn.stat().st_size == 32 * N_p[t]
+    # Fortran stream order: phaseSpace(1:4, i, t) for i = 1..N_p -> l, v_x, v_y, v_z of particle 1, then particle 2, ...
+    first = np.fromfile(tmp_path / "PhaseSpace" / "phaseSpace_e_thread1.dat", dtype="<f8", count=8)
+    assert np.array_equal(first, ps[0, :2, :].ravel())
+    q = ip.Particle(op.m_e, -op.e, 1.0, 0, finalIdx, "e", T)
+    q.readPhaseSpace(str(tmp_path), upload=False)
+    assert np.array_equal(q.N_p, N_p)
+    for t in range(T):
+        assert np.array_equal(q.phaseSpace[t, :N_p[t]], ps[t, :N_p[t]])
+    (tmp_path / "PhaseSpace" / "phaseSpace_e_thread2.dat").unlink()
+    with pytest.raises(FileNotFoundError):
+        q.readPhaseSpace(str(tmp_path), upload=False)
