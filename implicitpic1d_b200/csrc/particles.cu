@@ -292,6 +292,73 @@ __device__ __forceinline__ int transit_crossing(double u_in, double t_in, double
     return ok;
 }
 
+// Software-pipelined form of the same crossing: the time update and test of crossing j (t_j = t_{j-1} +- (u_j - u_{j-1})/a_j, t_j < t_lim)
+// is issued between the square-root chain of crossing j+1 (candidate speed from u_j and the next cell's 2 a dx), so that the in-order
+// issue of one warp always has two independent dependency chains to draw from.  `u_cur` was committed under `alive` (crossing j is
+// attempted by this lane); a lane whose test fails keeps (u_prev, t_prev) as its state.  Returns ok_j; the candidate u_{j+1} is
+// returned raw in `u_cand` and committed by the caller once the lane is known to attempt crossing j+1.
+__device__ __forceinline__ int transit_step(double u_prev, double u_cur, double t_prev, double &t_cur, double inv_a, double dpe_next, double sgn,
+                                            double t_lim, bool alive, double &u_cand) {
+    int ok;
+    asm("{\n\t"
+        ".reg .pred pa, pk;\n\t"
+        ".reg .f64 uu, s, y, t, nt, e, c, p, g, ng, h, r, d;\n\t"
+        ".reg .b32 lo, hi;\n\t"
+        "setp.ne.s32 pa, %10, 0;\n\t"
+        "mul.rn.f64 uu, %4, %4;\n\t"
+        "sub.rn.f64 d, %4, %3;\n\t"
+        "fma.rn.f64 s, %8, %7, uu;\n\t"
+        "mul.rn.f64 d, d, %6;\n\t"
+        "rsqrt.approx.ftz.f64 y, s;\n\t"
+        "@pa fma.rn.f64 %0, %8, d, %5;\n\t"
+        "mul.rn.f64 t, y, y;\n\t"
+        "neg.f64 nt, t;\n\t"
+        "setp.lt.and.f64 pk, %0, %9, pa;\n\t"
+        "fma.rn.f64 e, s, nt, 0d3FF0000000000000;\n\t"
+        "selp.s32 %2, 1, 0, pk;\n\t"
+        "fma.rn.f64 c, e, 0d3FD8000000000000, 0d3FE0000000000000;\n\t"
+        "mul.rn.f64 p, y, e;\n\t"
+        "fma.rn.f64 y, c, p, y;\n\t"
+        "mul.rn.f64 g, s, y;\n\t"
+        "mov.b64 {lo, hi}, y;\n\t"
+        "add.s32 hi, hi, -1048576;\n\t"
+        "mov.b64 h, {lo, hi};\n\t"
+        "neg.f64 ng, g;\n\t"
+        "fma.rn.f64 r, g, ng, s;\n\t"
+        "fma.rn.f64 %1, r, h, g;\n\t"
+        "}"
+        : "+d"(t_cur), "=d"(u_cand), "=r"(ok)
+        : "d"(u_prev), "d"(u_cur), "d"(t_prev), "d"(inv_a), "d"(dpe_next), "d"(sgn), "d"(t_lim), "r"((int)alive));
+    return ok;
+}
+
+// candidate speed after crossing a cell: sqrt(u^2 +- 2 a dx), the same instruction sequence as in transit_step
+__device__ __forceinline__ double transit_speed(double u, double dpe, double sgn) {
+    double uf;
+    asm("{\n\t"
+        ".reg .f64 uu, s, y, t, nt, e, c, p, g, ng, h, r;\n\t"
+        ".reg .b32 lo, hi;\n\t"
+        "mul.rn.f64 uu, %1, %1;\n\t"
+        "fma.rn.f64 s, %3, %2, uu;\n\t"
+        "rsqrt.approx.ftz.f64 y, s;\n\t"
+        "mul.rn.f64 t, y, y;\n\t"
+        "neg.f64 nt, t;\n\t"
+        "fma.rn.f64 e, s, nt, 0d3FF0000000000000;\n\t"
+        "fma.rn.f64 c, e, 0d3FD8000000000000, 0d3FE0000000000000;\n\t"
+        "mul.rn.f64 p, y, e;\n\t"
+        "fma.rn.f64 y, c, p, y;\n\t"
+        "mul.rn.f64 g, s, y;\n\t"
+        "mov.b64 {lo, hi}, y;\n\t"
+        "add.s32 hi, hi, -1048576;\n\t"
+        "mov.b64 h, {lo, hi};\n\t"
+        "neg.f64 ng, g;\n\t"
+        "fma.rn.f64 r, g, ng, s;\n\t"
+        "fma.rn.f64 %0, r, h, g;\n\t"
+        "}"
+        : "=d"(uf) : "d"(u), "d"(dpe), "d"(sgn));
+    return uf;
+}
+
 template <int SCHEME, bool MOVE>
 __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -380,14 +447,29 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
                         const int cell0 = cell;
                         // two register copies of (|v|, t): a crossing reads one and writes the other, so committing costs no moves;
                         // after k committed crossings the valid copy is A (k even) or B (k odd)
-                        double uA = fabs(v), tA = tp, uB = uA, tB = tp;
+                        // Crossing j reads state j-1 and writes state j into the other register copy (no commit moves).  Pipelined: the
+                        // speed after crossing j is committed as soon as the lane is known to attempt crossing j, its time test runs
+                        // one stage later, interleaved with the square root of crossing j+1.
+                        double uA = fabs(v), tA = tp, uB, tB = tp;
+                        double2 ttB = __ldg(A.ttab + cell), ttA = __ldg(A.ttab + (cell + step));
+                        {   // stage 0: speed of crossing 1
+                            const double c0 = transit_speed(uA, ttB.x, sgn);
+                            uB = tr ? c0 : uA;
+                        }
                         do {
-                            int ok = transit_crossing(uA, tA, __ldg(A.ttab + cell), sgn, A.t_lim, tr, uB, tB);
+                            // crossing j (state A -> B): time test; candidate for crossing j+1 from uB and the next cell
+                            double cand;
+                            int ok = transit_step(uA, uB, tA, tB, ttB.y, ttA.x, sgn, A.t_lim, tr, cand);
                             cell += ok ? step : 0;
                             tr = ok && (cell != cell_end);
-                            ok = transit_crossing(uB, tB, __ldg(A.ttab + cell), sgn, A.t_lim, tr, uA, tA);
+                            ttB = __ldg(A.ttab + (cell + step));
+                            uA = tr ? cand : uA;
+                            // crossing j+1 (state B -> A)
+                            ok = transit_step(uB, uA, tB, tA, ttA.y, ttB.x, sgn, A.t_lim, tr, cand);
                             cell += ok ? step : 0;
                             tr = ok && (cell != cell_end);
+                            ttA = __ldg(A.ttab + (cell + step));
+                            uB = tr ? cand : uB;
                         } while (__popc(__ballot_sync(FULL, tr)) >= A.transit_min);
                         if (cell != cell0) {
                             const int k = (cell - cell0) * step;
@@ -723,10 +805,14 @@ static int make_push_args(Ctx &c, int sp, double del_t, PushArgs &A) {
     A.f_tol = del_t * ((c.scheme == IPIC_SCHEME_NGP) ? 1.e-15 : (c.scheme == IPIC_SCHEME_CIC) ? 1.e-10 : (double)1e-12f);
     {   // `t < t_lim` <=> `del_t - t > f_tol` for every double t: the difference is monotone in t, so the first t that fails the
         // reference's test (mod_particleMover.f90:89,183) splits the number line exactly
-        double t = A.del_t - A.f_tol;
-        if (!(A.del_t > 0.0) || !std::isfinite(A.del_t)) { set_error("del_t must be positive and finite"); return IPIC_ERR_ARG; }
-        while (A.del_t - t > A.f_tol) t = std::nextafter(t, INFINITY);
-        while (!(A.del_t - std::nextafter(t, -INFINITY) > A.f_tol)) t = std::nextafter(t, -INFINITY);
+        // (del_t = 0 is reachable through the reference's own step halving -- a converged JFNK solve whose linear-iteration count
+        // exceeds maxIter leaves remainDel_t = 0, mod_nonLinSolvers.f90:297-313 -- so it must stay a valid, empty, sweep)
+        double t = -INFINITY;
+        if (A.del_t > 0.0 && std::isfinite(A.del_t)) {
+            t = A.del_t - A.f_tol;
+            while (A.del_t - t > A.f_tol) t = std::nextafter(t, INFINITY);
+            while (!(A.del_t - std::nextafter(t, -INFINITY) > A.f_tol)) t = std::nextafter(t, -INFINITY);
+        }
         A.t_lim = t;
     }
     A.ttab = c.d_ttab + (size_t)sp * (cells + 2);
