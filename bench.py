@@ -48,6 +48,14 @@ WORKLOADS = {
                scheme=2, Nx=2049, L=0.33245599281881233 * 2048 / 512, n_ave=1e14, T_e=5.0, T_i=0.01, bcL=3, bcR=3, Vl=0.0, Vr=0.0, rf=0.0,
                smooth=0, frac=10.0, dt_deck=1.0, eps_a=0.0, eps_r=1e-8, m=20, beta=0.5, maxIter=100, ion_amu=5.48634767053312,
                alpha=0.4, distType=2, v_drift=-9372.932223215392, solver_type=1, per_species_per_gpu=50_000_000),
+    # configs[3]: bounded argon plasma with null-collision MCC (OpenMP/NGP/InputDataSets/NGP_VassBenchmark_Ar_10xParticles: 257 nodes, 2.5 cm,
+    # RF 250 V 13.56 MHz, n = 1e16, eps_a = 1e-4, Ar 300 K 2.4e21 m^-3, table Ar_electron_table.dat), 1e8 particles over 2 GPUs = 5e7 per GPU;
+    # a step = solvePotential + generateCollision of every reactant pair (mod_simulation.f90:157-160)
+    "c4": dict(name="C4: NGP bounded Ar RF plasma with MCC (Ar_electron_table.dat), 256 cells, 5e7 particles/GPU (2 species), Vass benchmark deck, "
+                    "Anderson m=10 eps_a=1e-4",
+               scheme=0, Nx=257, L=0.025, n_ave=1.0e16, T_e=2.59, T_i=0.025, bcL=1, bcR=4, Vl=0.0, Vr=250.0, rf=13.56e6,
+               smooth=1, frac=1.5, dt_deck=7.845352413230403e-12, eps_a=1e-4, eps_r=0.0, m=10, beta=0.5, maxIter=100, ion_amu=39.948,
+               per_species_per_gpu=25_000_000, mcc=dict(table="Ar_electron_table.dat", neutral=("Ar", 39.948, 2.4e21, 300.0), ion_name="Ar+")),
     # configs[0]: the default NGP deck itself (CPU-runnable case)
     "c1": dict(name="C1: default NGP deck, 1000 cells, 1.536e6 particles (2 species)",
                scheme=0, Nx=1001, L=0.067, n_ave=1.6e18, T_e=4.0, T_i=0.025, bcL=1, bcR=4, Vl=0.0, Vr=2000.0, rf=200.0e6,
@@ -139,7 +147,21 @@ def cpu_reference_run(w, steps, warmup, budget_s):
         return op.make_deck_case(w["scheme"], w["Nx"], w["L"], w["n_ave"], w["T_e"], w["T_i"], ppt, T, w["bcL"], w["bcR"], w["Vl"], w["Vr"],
                                  w["rf"], bool(w["smooth"]), ion_amu=w["ion_amu"], eps_a=w["eps_a"], eps_r=w["eps_r"], m_Anderson=w["m"],
                                  Beta_k=w["beta"], maxIter=w["maxIter"], native=True, alpha=w.get("alpha", 0.0), distType=w.get("distType", 0),
-                                 v_drift=w.get("v_drift", 0.0))
+                                 v_drift=w.get("v_drift", 0.0), factor=2 if w.get("mcc") else 1)   # ionisation appends need head-room
+
+    mcc = w.get("mcc")
+    COLL = os.path.join(ROOT, "tests", "golden", "collision_data")
+
+    def add_mcc(o):
+        # readNullCollisionInputs + the neutral background, on the oracle side (mod_NullCollision.f90:666-939)
+        from oracle import mcc_py as mp
+        nm, amu, dens, temp = mcc["neutral"]
+        mp.add_target(o, amu * op.m_amu, dens, temp)
+        specs = mp.read_null_collision_inputs([os.path.join(COLL, mcc["table"])], [("e", op.m_e), (mcc["ion_name"], w["ion_amu"] * op.m_amu - op.m_e)],
+                                              [(nm, amu * op.m_amu)])
+        o._ncs = [mp.NullCollisionOracle(o, sp) for sp in specs]
+        o._seeds = op.default_seeds(T)
+        o._mp = mp
 
     def run_steps(o, n, tcur, remain, curr):
         sub, secs, iters = 0, 0.0, []
@@ -159,6 +181,11 @@ def cpu_reference_run(w, steps, warmup, budget_s):
             else:
                 remain, curr = o.solvePotential(del_t, remain, curr, tcur)
                 its = None
+            if mcc:
+                for sp in range(o.n_species):
+                    o._mp.set_num_to_collide(o, sp)
+                for nc in o._ncs:
+                    nc.generateCollision(o._seeds, curr)
             secs += time.perf_counter() - t0
             tcur += curr
             st = o.solver_stats()
@@ -169,6 +196,8 @@ def cpu_reference_run(w, steps, warmup, budget_s):
     # calibrate on a small load, then size the sample so that (warmup + steps) fit the budget
     ppt0 = max(2000, 200_000 // T)
     o = make(ppt0)
+    if mcc:
+        add_mcc(o)
     sub, secs, iters, *_ = run_steps(o, 1, 0.0, del_t, del_t)
     rate0 = sub / max(secs, 1e-9)
     per_particle_step = sub / (2.0 * ppt0 * T)                       # substeps per particle per implicit step
@@ -176,6 +205,8 @@ def cpu_reference_run(w, steps, warmup, budget_s):
     ppt = int(min(max(want / T, ppt0), 2_000_000))
     del o
     o = make(ppt)
+    if mcc:
+        add_mcc(o)
     tcur, remain, curr = 0.0, del_t, del_t
     _, _, _, tcur, remain, curr = run_steps(o, warmup, tcur, remain, curr)
     sub, secs, iters, *_ = run_steps(o, steps, tcur, remain, curr)
@@ -208,6 +239,7 @@ def run_cuda_arm(args, w):
     import implicitpic1d_b200 as ip
     from implicitpic1d_b200 import _lib, constants as K
     from implicitpic1d_b200.domain import readWorld
+    from implicitpic1d_b200.particle_mover import depositSubsteps
 
     rank = int(os.environ.get("RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
@@ -247,8 +279,16 @@ def run_cuda_arm(args, w):
         _lib.check(L.ipic_comm_init(solver._h, world_size, rank, C.c_char_p(raw)))
     w_p = w["n_ave"] * world.L_domain / N_total_per_species                 # mod_particle.f90:76-82 with SUM(N_p) over all ranks
     m_ion = w["ion_amu"] * K.m_amu - K.m_e                                   # mod_particle.f90:334
-    plist = [ip.Particle(K.m_e, -K.e, w_p, 0, 0, "e", 1), ip.Particle(m_ion, K.e, w_p, 0, 0, "ion", 1)]
+    mcc = w.get("mcc")
+    plist = [ip.Particle(K.m_e, -K.e, w_p, 0, 0, "e", 1), ip.Particle(m_ion, K.e, w_p, 0, 0, mcc["ion_name"] if mcc else "ion", 1)]
     solver._bind(plist)
+    targets, ncs = [], []
+    if mcc:
+        nm, amu, dens, temp = mcc["neutral"]
+        targets = [ip.targetParticle(nm, amu * K.m_amu, dens, temp)]
+        # every rank collides its own shard with its own counter-based stream
+        ncs = ip.readNullCollisionInputs([mcc["table"]], plist, targets, collision_dir=os.path.join(ROOT, "tests", "golden", "collision_data"),
+                                         seed=0x1D1C0111 + 7919 * rank)
     _lib.check(L.ipic_generate_particles_dist(solver._h, 0, n_sp, w["T_e"], w.get("v_drift", 0.0), w.get("alpha", 0.0), w.get("distType", 0), SEED))
     _lib.check(L.ipic_generate_particles_dist(solver._h, 1, n_sp, w["T_i"], w.get("v_drift", 0.0), w.get("alpha", 0.0), w.get("distType", 0), SEED))
     ip.initializeSolver(solver, w["eps_a"], w["eps_r"], w.get("solver_type", 0), w["m"], w["beta"], w["maxIter"])
@@ -267,7 +307,21 @@ def run_cuda_arm(args, w):
         if args.sort_every > 0 and state["nstep"] > 0 and state["nstep"] % args.sort_every == 0:
             for p in plist:
                 _lib.check(L.ipic_sort_particles(solver._h, p._index))
-        state["remain"], state["curr"] = ip.solvePotential(solver, plist, world, del_t, state["remain"], state["curr"], state["t"])
+        try:
+            state["remain"], state["curr"] = ip.solvePotential(solver, plist, world, del_t, state["remain"], state["curr"], state["t"])
+        except _lib.IpicError:
+            if w.get("solver_type", 0) == 1:                        # say what NITSOL saw before the reference's `stop`
+                v = np.zeros(7, dtype=np.int32)
+                L.ipic_get_nitsol_info(solver._h, v.ctypes.data_as(_lib._ip))
+                print("bench.py: step %d failed; last NITSOL solve: %r, norms %s" % (state["nstep"], ip.NitsolInfo(v), ip.SolverState(solver).normHistory[-6:]),
+                      file=sys.stderr)
+            raise
+        if ncs:
+            # mod_simulation.f90:157-160: numToCollide = N_p (set by the mover), then every reactant pair collides over the step just taken
+            for p in plist:
+                _lib.check(L.ipic_set_num_to_collide(solver._h, p._index, p.count()))
+            for nc in ncs:
+                nc.generateCollision(plist, targets, del_t=state["curr"])
         state["t"] += state["curr"]
         state["nstep"] += 1
         st = ip.SolverState(solver)
@@ -299,12 +353,13 @@ def run_cuda_arm(args, w):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = launches()
     e0.record(stream)
-    substeps, sweeps, iters, particle_sweeps = 0, 0, [], 0
+    substeps, sweeps, iters, particle_sweeps, dep_sub_e = 0, 0, [], 0, 0
     for _ in range(args.steps):
         n_before = sum(p.count() for p in plist)
         st = one_step()
         substeps += st.substeps
         sweeps += st.sweeps
+        dep_sub_e += depositSubsteps(solver, plist[0])
         iters.append(st.iterNumPicard)
         particle_sweeps += n_before * (st.sweeps + 1)
     e1.record(stream)
@@ -320,6 +375,7 @@ def run_cuda_arm(args, w):
     t_field, n_field = solver.timing("field_kernels")
     t_ar, _ = solver.timing("allreduce_J")
     t_sort, _ = solver.timing("sort")
+    t_coll, _ = solver.timing("collisions")
     n_e, n_i = plist[0].count(), plist[1].count()
 
     vals = torch.tensor([ms, float(substeps)], dtype=torch.float64, device="cuda")
@@ -397,6 +453,17 @@ def run_cuda_arm(args, w):
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": 16.0 * (n_e + n_i) / 2.0, "avg_launch_ms": dep_ms / max(dep_launches, 1),
                 "per_species_ms": {"electrons": t_dep0 / max(n_dep0, 1), "ions": t_dep1 / max(n_dep1, 1)},
                 "kernel_share_of_step": dep_ms / max(ms, 1e-9)}
+    # second bound of the same kernel: the sub-step loop of the electrons is FP64 work, not bytes.  One face-to-face crossing is 14 FP64 + 15 other
+    # instructions per warp; FP64 instructions issue every other cycle on sm_100 (scripts/micro/fp64_tput.cu), and the loop in isolation at 8 warps
+    # per sub-partition runs at 46.8 cycles per crossing (scripts/micro/transit_bench.cu) -- that is the floor quoted here.
+    if w["scheme"] != 1 and t_dep0 > 0:
+        props = torch.cuda.get_device_properties(torch.cuda.current_device())
+        sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
+        floor = props.multi_processor_count * 4 * sm_hz / 46.8 * 32.0
+        roofline["issue_bound"] = {"what": "electron sub-steps per second inside the depositJ sweeps vs the measured issue floor of the crossing loop",
+                                   "achieved": dep_sub_e / (t_dep0 * 1e-3), "peak": floor, "frac": dep_sub_e / (t_dep0 * 1e-3) / floor,
+                                   "unit": "sub-steps/s", "floor_cycles_per_crossing_per_sm_subpartition": 46.8,
+                                   "electron_substeps_per_particle_per_sweep": dep_sub_e / max(n_dep0 * n_e, 1)}
 
     line = None
     if rank == 0:
@@ -420,7 +487,7 @@ def run_cuda_arm(args, w):
                 "e2e": e2e, "gpu_launches": n_launch, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "breakdown_ms_per_step": {"depositJ_kernels": dep_ms / args.steps, "moveParticles_kernel": t_move / args.steps,
                                           "compaction": t_comp / args.steps, "field_kernels": t_field / args.steps,
-                                          "allreduce_J": t_ar / args.steps, "sort": t_sort / args.steps}}
+                                          "allreduce_J": t_ar / args.steps, "sort": t_sort / args.steps, "collisions": t_coll / args.steps}}
         print(json.dumps(line), flush=True)
     solver.close()
     if dist is not None:
@@ -435,7 +502,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS), help="c5 (default, the bench line) | c1 | c2 | c3: the other BASELINE configs")
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS), help="c5 (default, the bench line) | c1 | c2 | c3 | c4: the other BASELINE configs")
     ap.add_argument("--particles-per-species", type=int, default=0, help="override particles per species per GPU (debug)")
     ap.add_argument("--sort-every", type=int, default=5, help="cell-sort the particles every this many steps inside the timed region (0 = never)")
     ap.add_argument("--thomas", action="store_true", help="sequential Thomas solve (bit-parity mode) instead of PCR")

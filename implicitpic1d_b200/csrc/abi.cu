@@ -612,7 +612,7 @@ int ipic_solve_potential(ipic_handle h, double del_t, double *remainDel_t, doubl
     if (rc) return rc;
     unsigned long long cnt[NSP_MAX * 8];
     RC(read_counters(*c, cnt));
-    for (int s = 0; s < (int)c->sp.size(); ++s) c->substeps += (long long)cnt[s * 8];
+    for (int s = 0; s < (int)c->sp.size(); ++s) { c->substeps += (long long)cnt[s * 8]; c->sp[s].depositSubsteps = (long long)cnt[s * 8]; }
     return IPIC_OK;
 }
 

@@ -147,7 +147,8 @@ typedef struct {
     int64_t accumWallLoss[2];
 } ipic_move_stats;
 int ipic_get_move_stats(ipic_handle h, int32_t species, ipic_move_stats *out);
-/* executed sub-steps of the last depositJ sweep for a species (instrumentation for the throughput metric) */
+/* executed sub-steps of a species in the last depositJ sweep, or, after ipic_solve_potential, in all depositJ sweeps of that step
+ * (instrumentation for the throughput metric) */
 int ipic_get_deposit_substeps(ipic_handle h, int32_t species, int64_t *n);
 
 /* ---- nonlinear solvers -------------------------------------------------------

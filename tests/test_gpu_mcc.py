@@ -211,3 +211,63 @@ def test_gpu_swarm_reproduces_bolsig_collision_frequency():
     ke = plist[0].getTotalKE() / plist[0].count() / op.e          # w_p = 1: joules per particle -> eV
     assert 6.5 < ke < 9.0
     solver.close()
+
+
+def test_collisional_time_loop_moments_match_oracle():
+    """BASELINE configs[3] in small: the Vass argon deck (NGP_VassBenchmark_Ar_10xParticles: RF 250 V 13.56 MHz, n = 1e16, eps_a = 1e-4,
+    Ar 300 K 2.4e21 m^-3) on 64 cells, stepped as mod_simulation.f90:157-160 does -- solvePotential, then generateCollision of every
+    reactant pair over the step just taken -- on both sides from identical particles.  The collision streams differ by design, so
+    after 30 steps the comparison is on moments: collision counts |N_gpu - N_oracle| < 5 sqrt(N_gpu + N_oracle + 1) per type,
+    particle counts within 5 sigma of the ionisation/wall-loss counts, mean electron and ion energy within 1 %, wall losses
+    within 5 sigma, and the same number of nonlinear iterations to +-3 per step (the field sees the same plasma up to noise)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from common import build_oracle, build_cuda_from_oracle, deck_del_t
+    d = dict(scheme=0, Nx=65, L=0.025 / 4, n_ave=1.0e16, T_e=2.59, T_i=0.025, ppt=20000, T=4, bcL=1, bcR=4, Vl=0.0, Vr=250.0, rf=13.56e6,
+             smooth=True, frac=1.5, dt_deck=7.845352413230403e-12, eps_a=1e-4, m=10, beta=0.5, maxIter=100, ion_amu=39.948)
+    o = build_oracle(d, factor=2)
+    world, solver, plist = build_cuda_from_oracle(d, o)
+    plist[0].name, plist[1].name = "e", "Ar+"
+    mp.add_target(o, M_AR, 2.4e21, 300.0)
+    specs = mp.read_null_collision_inputs([os.path.join(DATA, "Ar_electron_table.dat")], [("e", op.m_e), ("Ar+", M_AR - op.m_e)], [("Ar", M_AR)])
+    ncs_o = [mp.NullCollisionOracle(o, s) for s in specs]
+    seeds = op.default_seeds(d["T"])
+    tl = [ip.targetParticle("Ar", M_AR, 2.4e21, 300.0)]
+    ncs_g = ip.readNullCollisionInputs(["Ar_electron_table.dat"], plist, tl, collision_dir=DATA, seed=2026)
+    del_t = deck_del_t(d)
+    n0 = [plist[s].count() for s in range(2)]
+    ro, co, rg, cg, to, tg = del_t, del_t, del_t, del_t, 0.0, 0.0
+    wall_o, wall_g = np.zeros(2), np.zeros(2)
+    for step in range(30):
+        ro, co = o.solvePotential(del_t, ro, co, to)
+        to += co
+        for s in range(2):
+            wall_o[s] += o.counters(s)["delIdx"].sum()
+            mp.set_num_to_collide(o, s)
+        for r in ncs_o:
+            r.generateCollision(seeds, co)
+        rg, cg = ip.solvePotential(solver, plist, world, del_t, rg, cg, tg)
+        tg += cg
+        assert abs(ip.SolverState(solver).iterNumPicard - o.solver_stats()["iterNumPicard"]) <= 3
+        for s in range(2):
+            plist[s]._refresh_stats()
+            wall_g[s] += plist[s].delIdx
+            _lib.check(_lib.load().ipic_set_num_to_collide(solver._h, plist[s]._index, plist[s].count()))
+        for g in ncs_g:
+            g.generateCollision(plist, tl, del_t=cg)
+    nion_g = nion_o = 0
+    for g, r in zip(ncs_g, ncs_o):
+        tot = r.totals()
+        for c in range(g.numberCollisions):
+            ng, no = int(g.totalAmountCollisions[c]), int(tot["totalAmountCollisions"][c])
+            assert abs(ng - no) < 5.0 * np.sqrt(ng + no + 1), (c, ng, no)
+            if g.collisionType[c] == 2:
+                nion_g += ng; nion_o += no
+    assert ncs_g[0].totalAmountCollisions.sum() > 2500          # the loop did collide
+    for s in range(2):
+        ng, no = plist[s].count(), int(o.N_p(s).sum())
+        assert ng == n0[s] + nion_g - int(wall_g[s]) and no == n0[s] + nion_o - int(wall_o[s])     # exact bookkeeping on both sides
+        assert abs(wall_g[s] - wall_o[s]) < 5.0 * np.sqrt(wall_g[s] + wall_o[s] + 1), (s, wall_g, wall_o)
+        ke_g, ke_o = plist[s].getTotalKE() / ng, o.getTotalKE(s) / no
+        assert abs(ke_g - ke_o) < 1e-2 * ke_o, (s, ke_g, ke_o)
+    solver.close()
