@@ -158,6 +158,15 @@ module ipic_b200_c
             type(ipic_move_stats), intent(out) :: stats
             integer(c_int) :: rc
         end function
+        function ipic_get_ref_record(handle, species, idx, cap, n) bind(c, name="ipic_get_ref_record") result(rc)
+            import :: c_ptr, c_int, c_int32_t, c_int64_t
+            type(c_ptr), value :: handle
+            integer(c_int32_t), value :: species
+            integer(c_int32_t), intent(out) :: idx(*)
+            integer(c_int64_t), value :: cap
+            integer(c_int64_t), intent(out) :: n
+            integer(c_int) :: rc
+        end function
         function ipic_initialize_solver(handle, eps_a, eps_r, solverType, m_Anderson, Beta_k, maxIter) &
                 bind(c, name="ipic_initialize_solver") result(rc)
             import :: c_ptr, c_int, c_double

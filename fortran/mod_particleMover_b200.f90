@@ -81,7 +81,9 @@ contains
         type(Particle), intent(in out) :: particleList(:)
         real(real64), intent(in) :: del_t
         type(ipic_move_stats) :: st
-        integer :: j
+        integer :: j, k, iThread
+        integer(c_int64_t) :: nRef, slabEnd
+        integer(c_int32_t), allocatable :: refGlobal(:)
         call ipic_attach(solver, particleList, world)
         call ipic_push_state(solver, particleList)
         call ipic_check(ipic_move_particles(ipic_h, del_t), 'ipic_move_particles')
@@ -93,8 +95,26 @@ contains
             ! (main.f90:79-84, mod_simulation.f90:171-200)
             particleList(j)%delIdx = 0
             particleList(j)%delIdx(1) = int(st%delIdx, int32)
+            ! refIdx(T), refRecordIdx(:, T) (mod_particleMover.f90:226-231): the library returns the reflected particles as ascending
+            ! 0-based indices into the downloaded order (slab after slab); split them back into 1-based per-slab indices
             particleList(j)%refIdx = 0
-            particleList(j)%refIdx(1) = int(st%refIdx, int32)
+            if (st%refIdx > 0) then
+                allocate(refGlobal(st%refIdx))
+                call ipic_check(ipic_get_ref_record(ipic_h, j - 1, refGlobal, int(st%refIdx, c_int64_t), nRef), 'ipic_get_ref_record')
+                iThread = 1
+                slabEnd = particleList(j)%N_p(1)
+                do k = 1, int(min(nRef, st%refIdx))
+                    do while (refGlobal(k) >= slabEnd .and. iThread < numThread)
+                        iThread = iThread + 1
+                        slabEnd = slabEnd + particleList(j)%N_p(iThread)
+                    end do
+                    particleList(j)%refIdx(iThread) = particleList(j)%refIdx(iThread) + 1
+                    if (particleList(j)%refIdx(iThread) <= size(particleList(j)%refRecordIdx, 1)) &
+                        particleList(j)%refRecordIdx(particleList(j)%refIdx(iThread), iThread) = &
+                            int(refGlobal(k) - (slabEnd - particleList(j)%N_p(iThread)) + 1, int32)
+                end do
+                deallocate(refGlobal)
+            end if
             particleList(j)%wallLoss = 0
             particleList(j)%wallLoss(:, 1) = st%wallLoss
             particleList(j)%energyLoss = 0.0d0

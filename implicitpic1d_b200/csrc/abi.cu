@@ -131,7 +131,9 @@ static int move_all(Ctx &c, double del_t) {
             st.wallLoss[0] = (double)k[2]; st.wallLoss[1] = (double)k[3];
             st.delIdx = (int64_t)(k[2] + k[3]); st.refIdx = (int64_t)k[4];
             st.energyLoss[0] = st.energyLoss[1] = 0.0;
+            if (st.refIdx > 0) RC(collect_reflected(c, s));
             if (st.delIdx > 0) RC(compact_species(c, s));
+            if (st.refIdx > 0) RC(map_reflected(c, s, st.delIdx > 0));
             st.N_p = S.n;
             S.n_collide = S.n;                            // numToCollide = N_p (mod_particleMover.f90:263)
             if (c.nranks > 1) { /* per-rank statistics; callers all-reduce the scalars they need */ }
@@ -371,7 +373,7 @@ int ipic_destroy(ipic_handle h) {
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
     delete static_cast<nitsol::Solver *>(c->nitsol_state);
     collisions_free(*c);
-    for (auto &s : c->sp) { if (s.l) cudaFree(s.l); if (s.l2) cudaFree(s.l2); }
+    for (auto &s : c->sp) { if (s.l) cudaFree(s.l); if (s.l2) cudaFree(s.l2); if (s.refl) cudaFree(s.refl); if (s.refList) cudaFree(s.refList); }
     double *dp[] = {c->d_grid, c->d_dx, c->d_phi, c->d_phi_f, c->d_rho, c->d_J, c->d_E, c->d_a, c->d_b, c->d_c, c->d_cp, c->d_m, c->d_pcr, c->d_work,
                     c->d_rho_i, c->d_scal, c->d_phi_k, c->d_res_k, c->d_norms, c->d_loss, c->d_Ef, c->d_Eh};
     for (double *p : dp) if (p) cudaFree(p);
@@ -569,6 +571,19 @@ int ipic_move_particles(ipic_handle h, double del_t) {
 }
 
 int ipic_get_move_stats(ipic_handle h, int32_t sp, ipic_move_stats *out) { CTX(h); SPECIES(sp); *out = c->sp[sp].stats; return IPIC_OK; }
+// refRecordIdx of the last moveParticles: ascending 0-based indices into the species' particle order after compaction
+int ipic_get_ref_record(ipic_handle h, int32_t sp, int32_t *idx, int64_t cap, int64_t *n) {
+    CTX(h); SPECIES(sp);
+    if (!n) return IPIC_ERR_ARG;
+    SpeciesDev &S = c->sp[sp];
+    *n = S.nRef;
+    const long long m = std::min<long long>(S.nRef, cap);
+    if (m > 0 && idx) {
+        IPIC_CUDA(cudaMemcpyAsync(idx, S.refList, (size_t)m * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+        IPIC_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return IPIC_OK;
+}
 int ipic_get_deposit_substeps(ipic_handle h, int32_t sp, int64_t *n) { CTX(h); SPECIES(sp); *n = c->sp[sp].depositSubsteps; return IPIC_OK; }
 
 // initializeSolver  mod_nonLinSolvers.f90:41-81

@@ -66,6 +66,7 @@ struct PushArgs {
     int NB;                    // wall index on the right: N_x (NGP) or N_h (CIC)
     double del_t, f_tol;
     double t_lim;              // smallest double t with !(del_t - t > f_tol): `t < t_lim` is the reference's `del_t - t > f_tol`
+    unsigned char *refl;       // MOVE, Neumann walls only: per-particle flag "reflected during this step" (refRecordIdx), else null
     int stay_min;              // a queued batch keeps looping in registers while at least this many lanes continue
     int transit_min;           // the lean face-to-face loop runs while at least this many lanes are in transit
 };
@@ -81,6 +82,10 @@ struct SpeciesDev {
     ipic_move_stats stats{};
     long long depositSubsteps = 0;
     long long n_collide = -1;              // numToCollide (mod_particle.f90:17); < 0 = all
+    // refRecordIdx (mod_particle.f90:19, mod_particleMover.f90:226-231): particles first reflected at a Neumann wall in the last move
+    unsigned char *refl = nullptr; long long refl_cap = 0;      // per-particle flags written by the move kernel
+    unsigned *refList = nullptr; long long refList_cap = 0;     // flagged indices, ascending; after the move: post-compaction indices
+    long long nRef = 0;
 };
 
 // ---- null-collision MCC (collisions.cu) -------------------------------------------------------------
@@ -182,6 +187,8 @@ int launch_deposit(Ctx &c, int sp, double del_t);
 int launch_move(Ctx &c, int sp, double del_t);
 int launch_deposit_rho(Ctx &c, int sp);
 int compact_species(Ctx &c, int sp);
+int collect_reflected(Ctx &c, int sp);                 // flagged pre-compaction indices -> refList
+int map_reflected(Ctx &c, int sp, bool compacted);     // -> post-compaction indices (absorbed ones dropped)
 int particle_moments(Ctx &c, int sp, double out4[4]);      // sum v^2, sum vx, vy, vz
 int upload_species(Ctx &c, int sp, const double *ps, const int32_t *N_p, int T, int finalIdx);
 int download_species(Ctx &c, int sp, double *ps, int32_t *N_p, int T, int finalIdx);

@@ -5,6 +5,9 @@
 // OpenMP/CIC/src/mod_particleMoverPicard.f90:17-317.
 #include "ipic_common.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include <vector>
 #include <algorithm>
 
 namespace ipic {
@@ -595,7 +598,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
                             } else if (b == 2) {
                                 if (lb == A.NB) { if (v_f > 0.0) v_f = -v_f; }
                                 else { if (v_f < 0.0) v_f = -v_f; }
-                                if (MOVE && !(idx >> 31)) { idx |= 0x80000000u; nrefl += 1; }
+                                if (MOVE && !(idx >> 31)) { idx |= 0x80000000u; nrefl += 1; if (A.refl) A.refl[idx & 0x7fffffffu] = 1; }
                             } else if (b == 3) {
                                 l_f = (double)abs(lb - A.NB - 1);
                                 cell = abs(cell - A.NB);
@@ -836,6 +839,17 @@ int launch_move(Ctx &c, int sp, double del_t) {
     int rc = make_push_args(c, sp, del_t, A);
     if (rc) return rc;
     if (A.n == 0) return IPIC_OK;
+    SpeciesDev &S = c.sp[sp];
+    S.nRef = 0;
+    if (A.bcL == 2 || A.bcR == 2) {          // Neumann wall: the mover records which particles it reflected (refRecordIdx)
+        if (S.refl_cap < S.cap) {
+            if (S.refl) cudaFree(S.refl);
+            IPIC_CUDA(cudaMalloc(&S.refl, (size_t)S.cap));
+            S.refl_cap = S.cap;
+        }
+        IPIC_CUDA(cudaMemsetAsync(S.refl, 0, (size_t)A.n, c.stream));
+        A.refl = S.refl;
+    }
     if (c.scheme == IPIC_SCHEME_NGP) return launch_push_v<0, true>(c, A);
     if (c.scheme == IPIC_SCHEME_NGP_PERIODIC) return launch_push_v<2, true>(c, A);
     return launch_push_v<1, true>(c, A);
@@ -1154,6 +1168,71 @@ int compact_species(Ctx &c, int sp) {
     if (nb > 0) s.slab_off[nb - 1] = total;
     swap_banks(s);
     s.n = total;
+    return IPIC_OK;
+}
+
+// refRecordIdx: the reference stores, per thread slab, the post-compaction index `i - delIdx` of every particle at its first
+// reflection in the step (mod_particleMover.f90:226-231), in particle order.  Here: the move kernel flags the particle, the flagged
+// (pre-compaction) indices are selected in ascending order, and after the stable compaction each is mapped to
+// tileOffset[tile] + (alive particles of the tile before it); a flagged particle that was absorbed later in the same step is dropped.
+__global__ void k_map_reflected(const unsigned *__restrict__ pre, long long nref, const double *__restrict__ l_old,
+                                const long long *__restrict__ tileOffset, unsigned *post) {
+    const int lane = threadIdx.x & 31;
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;    // one warp per entry
+    if (w >= nref) return;
+    const unsigned i = pre[w];
+    const long long tile = i / CT_TILE, base = tile * CT_TILE;
+    unsigned cnt = 0;
+    for (long long j = base + lane; j < (long long)i; j += 32) cnt += (l_old[j] >= 0.0) ? 1u : 0u;
+    cnt = __reduce_add_sync(FULL, cnt);
+    if (lane == 0) post[w] = (l_old[i] >= 0.0) ? (unsigned)(tileOffset[tile] + cnt) : 0xffffffffu;
+}
+
+int collect_reflected(Ctx &c, int sp) {
+    SpeciesDev &s = c.sp[sp];
+    s.nRef = 0;
+    if (!s.refl || s.n == 0) return IPIC_OK;
+    if (s.refList_cap < 2 * s.cap) {
+        if (s.refList) cudaFree(s.refList);
+        IPIC_CUDA(cudaMalloc(&s.refList, (size_t)2 * s.cap * sizeof(unsigned)));       // [0,cap): selected, [cap,2cap): mapped
+        s.refList_cap = 2 * s.cap;
+    }
+    if (!c.d_total) IPIC_CUDA(cudaMalloc(&c.d_total, 8 * sizeof(long long)));
+    int *d_num = reinterpret_cast<int *>(c.d_total + 4);
+    size_t tmp_bytes = 0;
+    cub::CountingInputIterator<unsigned> it(0u);
+    cub::DeviceSelect::Flagged(nullptr, tmp_bytes, it, s.refl, s.refList, d_num, (int)s.n, c.stream);
+    if (tmp_bytes > c.cap_sort_tmp) {
+        if (c.d_sort_tmp) cudaFree(c.d_sort_tmp);
+        c.cap_sort_tmp = tmp_bytes + tmp_bytes / 8;
+        IPIC_CUDA(cudaMalloc(&c.d_sort_tmp, c.cap_sort_tmp));
+    }
+    c.launches += 1; cub::DeviceSelect::Flagged(c.d_sort_tmp, tmp_bytes, it, s.refl, s.refList, d_num, (int)s.n, c.stream);
+    int h_num = 0;
+    IPIC_CUDA(cudaMemcpyAsync(&h_num, d_num, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    IPIC_CUDA(cudaStreamSynchronize(c.stream));
+    s.nRef = h_num;
+    return IPIC_OK;
+}
+
+int map_reflected(Ctx &c, int sp, bool compacted) {
+    SpeciesDev &s = c.sp[sp];
+    if (s.nRef == 0 || !compacted) return IPIC_OK;            // nothing absorbed: indices are already final
+    unsigned *post = s.refList + s.refList_cap / 2;
+    const long long warps_per_block = 8;
+    c.launches += 1;
+    k_map_reflected<<<(unsigned)((s.nRef + warps_per_block - 1) / warps_per_block), 256, 0, c.stream>>>(s.refList, s.nRef, s.l2 /* pre-compaction bank */,
+                                                                                                          c.d_tileOffset, post);
+    IPIC_CUDA(cudaGetLastError());
+    // drop the entries of particles absorbed after their reflection (0xffffffff), keep the order
+    std::vector<unsigned> h((size_t)s.nRef);
+    IPIC_CUDA(cudaMemcpyAsync(h.data(), post, (size_t)s.nRef * sizeof(unsigned), cudaMemcpyDeviceToHost, c.stream));
+    IPIC_CUDA(cudaStreamSynchronize(c.stream));
+    size_t k = 0;
+    for (size_t j = 0; j < h.size(); ++j) if (h[j] != 0xffffffffu) h[k++] = h[j];
+    s.nRef = (long long)k;
+    if (k) IPIC_CUDA(cudaMemcpyAsync(s.refList, h.data(), k * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
+    IPIC_CUDA(cudaStreamSynchronize(c.stream));
     return IPIC_OK;
 }
 

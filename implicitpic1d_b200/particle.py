@@ -125,6 +125,20 @@ class Particle:
         _lib.check(_lib.load().ipic_get_total_momentum(self._solver._h, self._index, out.ctypes.data_as(_lib._dp)))
         return out
 
+    def refRecord(self):
+        """refIdx(T), refRecordIdx(:, T) of the last moveParticles (mod_particle.f90:18-19; mod_particleMover.f90:226-231): per thread slab, the
+        1-based post-compaction indices of the particles first reflected at a Neumann wall in the step, in particle order.  The slabs are
+        those `download()` writes (N_p is refreshed by it); returns (refIdx per slab, list of int32 arrays)."""
+        L = _lib.load()
+        n = C.c_int64()
+        _lib.check(L.ipic_get_ref_record(self._solver._h, self._index, None, 0, C.byref(n)))
+        idx = np.zeros(max(n.value, 1), dtype=np.int32)
+        _lib.check(L.ipic_get_ref_record(self._solver._h, self._index, idx.ctypes.data_as(_lib._ip), n.value, C.byref(n)))
+        idx = idx[:n.value].astype(np.int64)
+        off = np.concatenate([[0], np.cumsum(self.N_p.astype(np.int64))])
+        rec = [(idx[(idx >= off[t]) & (idx < off[t + 1])] - off[t] + 1).astype(np.int32) for t in range(self.numThread)]
+        return np.array([r.size for r in rec], dtype=np.int32), rec
+
     def _refresh_stats(self):
         st = _lib.MoveStats()
         _lib.check(_lib.load().ipic_get_move_stats(self._solver._h, self._index, C.byref(st)))

@@ -147,6 +147,11 @@ typedef struct {
     int64_t accumWallLoss[2];
 } ipic_move_stats;
 int ipic_get_move_stats(ipic_handle h, int32_t species, ipic_move_stats *out);
+/* refRecordIdx (mod_particle.f90:19; written by moveParticles, NGP mod_particleMover.f90:226-231, CIC mod_particleMoverPicard.f90:276-281):
+ * the particles first reflected at a Neumann wall during the last ipic_move_particles / converged ipic_solve_potential, as ascending
+ * 0-based indices into the species' particle order after compaction (the order ipic_download_particles writes, slab after slab).
+ * *n receives the count; at most cap indices are written.  A particle reflected and then absorbed in the same step is not listed. */
+int ipic_get_ref_record(ipic_handle h, int32_t species, int32_t *idx, int64_t cap, int64_t *n);
 /* executed sub-steps of a species in the last depositJ sweep, or, after ipic_solve_potential, in all depositJ sweeps of that step
  * (instrumentation for the throughput metric) */
 int ipic_get_deposit_substeps(ipic_handle h, int32_t species, int64_t *n);

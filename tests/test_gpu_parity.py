@@ -316,3 +316,35 @@ def test_jfnk_step_matches_oracle(name):
         assert p.N_p_total == int(o.N_p(sp).sum())
     # the same step through solvePotential (adaptive wrapper :284-314) on a fresh pair gives the same counters
     solver.close()
+
+
+@pytest.mark.parametrize("name", ["ngp_neumann", "cic_neumann"])
+def test_refRecordIdx_matches_oracle(name):
+    """moveParticles at a Neumann wall records, per thread slab, the post-compaction index of every particle at its first reflection
+    (NGP mod_particleMover.f90:226-231, CIC mod_particleMoverPicard.f90:276-281); the other wall absorbs, so the compaction shifts them."""
+    d = DECKS[name]
+    o = build_oracle(d)
+    world, solver, plist = build_cuda_from_oracle(d, o, tridiag_mode=_lib.TRIDIAG_THOMAS)
+    del_t = deck_del_t(d) * 4.0                                  # enough wall traffic for a meaningful list
+    solver.phi, solver.phi_f, solver.rho = o.get("phi"), o.get("phi_f"), o.get("rho")
+    o.makeHalfTimeEField(); solver.makeHalfTimeEField()
+    for step in range(2):
+        o.moveParticles(del_t)
+        ip.moveParticles(solver, plist, world, del_t)
+        total = 0
+        for sp, p in enumerate(plist):
+            p.download()
+            cnt = o.counters(sp)
+            assert np.array_equal(p.N_p, o.N_p(sp))
+            refIdx, rec = p.refRecord()
+            assert np.array_equal(refIdx, cnt["refIdx"]), (sp, refIdx, cnt["refIdx"])
+            assert p.refIdx == int(cnt["refIdx"].sum())
+            cap = p.finalIdx // 10                                # refRecordIdx(finalIdx/10, T): the reference drops what does not fit
+            for t in range(d["T"]):
+                m = min(int(cnt["refIdx"][t]), cap)
+                assert np.array_equal(rec[t][:m], o.ref_record(sp, t + 1, m)), (sp, t)
+            total += int(refIdx.sum())
+            if sp == 0:
+                assert cnt["delIdx"].sum() > 0                    # the compaction did shift the electrons' indices
+        assert total > 20
+    solver.close()
