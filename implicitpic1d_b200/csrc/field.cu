@@ -537,7 +537,8 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
                     CellTabNGP t;
                     t.a = a; t.hinv = 0.5 / dx; t.two_a_dx = 2.0 * a * dx; t.inv_a = 1.0 / a;
                     T[cI] = t;
-                    TT[cI] = make_double2(t.two_a_dx, t.inv_a);
+                    // wall cells are not transited by the lean loop: NaN makes a lane that reaches one fail its next time test
+                    TT[cI] = (cI == 1 || cI == Nh) ? make_double2(__longlong_as_double(0x7ff8000000000000ll), 0.0) : make_double2(t.two_a_dx, t.inv_a);
                 }
             }
         } else {
@@ -597,7 +598,7 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
                 CellTabNGP t;
                 t.a = a; t.hinv = 0.5 / dx; t.two_a_dx = 2.0 * a * dx; t.inv_a = 1.0 / a;
                 T[cI] = t;
-                TT[cI] = make_double2(t.two_a_dx, t.inv_a);
+                TT[cI] = (cI == 1 || cI == Nh) ? make_double2(__longlong_as_double(0x7ff8000000000000ll), 0.0) : make_double2(t.two_a_dx, t.inv_a);
             }
         }
         __syncthreads();

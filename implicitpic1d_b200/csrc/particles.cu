@@ -265,7 +265,7 @@ __device__ __forceinline__ int transit_crossing(double u_in, double t_in, double
     int ok;
     asm("{\n\t"
         ".reg .pred pa, pk;\n\t"
-        ".reg .f64 uu, s, y, t, nt, e, c, p, g, ng, h, r, d;\n\t"
+        ".reg .f64 uu, s, y, y1, t, nt, e, c, p, g, ng, h, r, d;\n\t"
         ".reg .b32 lo, hi;\n\t"
         "setp.ne.s32 pa, %8, 0;\n\t"
         "mul.rn.f64 uu, %3, %3;\n\t"
@@ -276,9 +276,9 @@ __device__ __forceinline__ int transit_crossing(double u_in, double t_in, double
         "fma.rn.f64 e, s, nt, 0d3FF0000000000000;\n\t"
         "fma.rn.f64 c, e, 0d3FD8000000000000, 0d3FE0000000000000;\n\t"
         "mul.rn.f64 p, y, e;\n\t"
-        "fma.rn.f64 y, c, p, y;\n\t"
-        "mul.rn.f64 g, s, y;\n\t"
-        "mov.b64 {lo, hi}, y;\n\t"
+        "fma.rn.f64 y1, c, p, y;\n\t"
+        "mul.rn.f64 g, s, y1;\n\t"
+        "mov.b64 {lo, hi}, y1;\n\t"
         "add.s32 hi, hi, -1048576;\n\t"
         "mov.b64 h, {lo, hi};\n\t"
         "neg.f64 ng, g;\n\t"
@@ -305,7 +305,7 @@ __device__ __forceinline__ int transit_step(double u_prev, double u_cur, double 
     int ok;
     asm("{\n\t"
         ".reg .pred pa, pk;\n\t"
-        ".reg .f64 uu, s, y, t, nt, e, c, p, g, ng, h, r, d;\n\t"
+        ".reg .f64 uu, s, y, y1, t, nt, e, c, p, g, ng, h, r, d;\n\t"
         ".reg .b32 lo, hi;\n\t"
         "setp.ne.s32 pa, %10, 0;\n\t"
         "mul.rn.f64 uu, %4, %4;\n\t"
@@ -321,9 +321,9 @@ __device__ __forceinline__ int transit_step(double u_prev, double u_cur, double 
         "selp.s32 %2, 1, 0, pk;\n\t"
         "fma.rn.f64 c, e, 0d3FD8000000000000, 0d3FE0000000000000;\n\t"
         "mul.rn.f64 p, y, e;\n\t"
-        "fma.rn.f64 y, c, p, y;\n\t"
-        "mul.rn.f64 g, s, y;\n\t"
-        "mov.b64 {lo, hi}, y;\n\t"
+        "fma.rn.f64 y1, c, p, y;\n\t"
+        "mul.rn.f64 g, s, y1;\n\t"
+        "mov.b64 {lo, hi}, y1;\n\t"
         "add.s32 hi, hi, -1048576;\n\t"
         "mov.b64 h, {lo, hi};\n\t"
         "neg.f64 ng, g;\n\t"
@@ -339,7 +339,7 @@ __device__ __forceinline__ int transit_step(double u_prev, double u_cur, double 
 __device__ __forceinline__ double transit_speed(double u, double dpe, double sgn) {
     double uf;
     asm("{\n\t"
-        ".reg .f64 uu, s, y, t, nt, e, c, p, g, ng, h, r;\n\t"
+        ".reg .f64 uu, s, y, y1, t, nt, e, c, p, g, ng, h, r;\n\t"
         ".reg .b32 lo, hi;\n\t"
         "mul.rn.f64 uu, %1, %1;\n\t"
         "fma.rn.f64 s, %3, %2, uu;\n\t"
@@ -349,9 +349,9 @@ __device__ __forceinline__ double transit_speed(double u, double dpe, double sgn
         "fma.rn.f64 e, s, nt, 0d3FF0000000000000;\n\t"
         "fma.rn.f64 c, e, 0d3FD8000000000000, 0d3FE0000000000000;\n\t"
         "mul.rn.f64 p, y, e;\n\t"
-        "fma.rn.f64 y, c, p, y;\n\t"
-        "mul.rn.f64 g, s, y;\n\t"
-        "mov.b64 {lo, hi}, y;\n\t"
+        "fma.rn.f64 y1, c, p, y;\n\t"
+        "mul.rn.f64 g, s, y1;\n\t"
+        "mov.b64 {lo, hi}, y1;\n\t"
         "add.s32 hi, hi, -1048576;\n\t"
         "mov.b64 h, {lo, hi};\n\t"
         "neg.f64 ng, g;\n\t"
@@ -445,7 +445,6 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
                     if (!MOVE) tr = tr && (pend == 0 || ((pend > 0) == vpos));
                     if (__popc(__ballot_sync(FULL, tr)) >= A.transit_min) {
                         const int step = vpos ? 1 : -1;
-                        const int cell_end = vpos ? A.NB - 1 : 1;                // first cell past the interior, along the motion
                         const double sgn = vpos ? 1.0 : -1.0;
                         const int cell0 = cell;
                         // two register copies of (|v|, t): a crossing reads one and writes the other, so committing costs no moves;
@@ -459,20 +458,25 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
                             const double c0 = transit_speed(uA, ttB.x, sgn);
                             uB = tr ? c0 : uA;
                         }
+                        // The wall cells of the transit table hold NaN: a lane that reaches one fails its next test and is out, so the
+                        // loop needs no range check.  Two crossings per vote (four measured slower: more trips with few lanes left).
                         do {
-                            // crossing j (state A -> B): time test; candidate for crossing j+1 from uB and the next cell
-                            double cand;
-                            int ok = transit_step(uA, uB, tA, tB, ttB.y, ttA.x, sgn, A.t_lim, tr, cand);
-                            cell += ok ? step : 0;
-                            tr = ok && (cell != cell_end);
-                            ttB = __ldg(A.ttab + (cell + step));
-                            uA = tr ? cand : uA;
-                            // crossing j+1 (state B -> A)
-                            ok = transit_step(uB, uA, tB, tA, ttA.y, ttB.x, sgn, A.t_lim, tr, cand);
-                            cell += ok ? step : 0;
-                            tr = ok && (cell != cell_end);
-                            ttA = __ldg(A.ttab + (cell + step));
-                            uB = tr ? cand : uB;
+#pragma unroll
+                            for (int rep = 0; rep < 1; ++rep) {
+                                // crossing j (state A -> B): time test; candidate for crossing j+1 from uB and the next cell
+                                double cand;
+                                int ok = transit_step(uA, uB, tA, tB, ttB.y, ttA.x, sgn, A.t_lim, tr, cand);
+                                cell += ok ? step : 0;
+                                tr = ok;
+                                ttB = __ldg(A.ttab + (cell + step));
+                                uA = tr ? cand : uA;
+                                // crossing j+1 (state B -> A)
+                                ok = transit_step(uB, uA, tB, tA, ttA.y, ttB.x, sgn, A.t_lim, tr, cand);
+                                cell += ok ? step : 0;
+                                tr = ok;
+                                ttA = __ldg(A.ttab + (cell + step));
+                                uB = tr ? cand : uB;
+                            }
                         } while (__popc(__ballot_sync(FULL, tr)) >= A.transit_min);
                         if (cell != cell0) {
                             const int k = (cell - cell0) * step;
