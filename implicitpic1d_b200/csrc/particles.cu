@@ -257,45 +257,13 @@ __device__ __forceinline__ void close_run(WarpSmem &W, DepositState &D, int lane
 // One face-to-face crossing of an interior cell in the lean transit loop (NGP sub-step, mod_particleMover.f90:36-60, for a particle
 // that sits on the entry face): s = u^2 +- 2 a dx, u_f = sqrt(s), t_f = t +- (u_f - u)/a, committed when t_f < t_lim.  Same operations and
 // roundings as the general sub-step (the +-1 multipliers are exact, so the two fma are a plain add/sub), written in PTX to pin the
-// instruction sequence: 13 FP64 arithmetic instructions + 1 compare, everything unconditional except the two result writes (predicated
-// on `alive`), no branches.  The square root is the sequence CUDA's own sqrt(double) executes for normal operands (MUFU.RSQ64H seed,
-// one third-order refinement of 1/sqrt, one residual correction of the root: correctly rounded), without its special-operand slow path:
+// instruction sequence: 12 FP64 arithmetic instructions + 1 compare, everything unconditional except the two result writes (predicated
+// on `alive`), no branches.  The square root is CUDA's own sqrt(double) sequence for normal operands (MUFU.RSQ64H seed, one refinement
+// of 1/sqrt, one residual correction of the root) with the refinement taken to second instead of third order -- the residual
+// correction squares the remaining 2^-45 error, so the result is still the correctly rounded root: bit-identical to sqrt() on 5e9
+// random and near-square operands (scripts/micro/sqrt_check.cu) -- and without the special-operand slow path:
 // s <= 0 (the particle turns around inside the cell) gives NaN or Inf*0, the compare fails and the lane is left to the general sub-step.
-__device__ __forceinline__ int transit_crossing(double u_in, double t_in, double2 tt, double sgn, double t_lim, bool alive, double &u_out, double &t_out) {
-    int ok;
-    asm("{\n\t"
-        ".reg .pred pa, pk;\n\t"
-        ".reg .f64 uu, s, y, y1, t, nt, e, c, p, g, ng, h, r, d;\n\t"
-        ".reg .b32 lo, hi;\n\t"
-        "setp.ne.s32 pa, %8, 0;\n\t"
-        "mul.rn.f64 uu, %3, %3;\n\t"
-        "fma.rn.f64 s, %7, %5, uu;\n\t"
-        "rsqrt.approx.ftz.f64 y, s;\n\t"
-        "mul.rn.f64 t, y, y;\n\t"
-        "neg.f64 nt, t;\n\t"
-        "fma.rn.f64 e, s, nt, 0d3FF0000000000000;\n\t"
-        "fma.rn.f64 c, e, 0d3FD8000000000000, 0d3FE0000000000000;\n\t"
-        "mul.rn.f64 p, y, e;\n\t"
-        "fma.rn.f64 y1, c, p, y;\n\t"
-        "mul.rn.f64 g, s, y1;\n\t"
-        "mov.b64 {lo, hi}, y1;\n\t"
-        "add.s32 hi, hi, -1048576;\n\t"
-        "mov.b64 h, {lo, hi};\n\t"
-        "neg.f64 ng, g;\n\t"
-        "fma.rn.f64 r, g, ng, s;\n\t"
-        "@pa fma.rn.f64 %0, r, h, g;\n\t"
-        "sub.rn.f64 d, %0, %3;\n\t"
-        "mul.rn.f64 d, d, %6;\n\t"
-        "@pa fma.rn.f64 %1, %7, d, %4;\n\t"
-        "setp.lt.and.f64 pk, %1, %9, pa;\n\t"
-        "selp.s32 %2, 1, 0, pk;\n\t"
-        "}"
-        : "+d"(u_out), "+d"(t_out), "=r"(ok)
-        : "d"(u_in), "d"(t_in), "d"(tt.x), "d"(tt.y), "d"(sgn), "r"((int)alive), "d"(t_lim));
-    return ok;
-}
-
-// Software-pipelined form of the same crossing: the time update and test of crossing j (t_j = t_{j-1} +- (u_j - u_{j-1})/a_j, t_j < t_lim)
+// Software-pipelined form of that crossing (the one the kernel uses): the time update and test of crossing j (t_j = t_{j-1} +- (u_j - u_{j-1})/a_j, t_j < t_lim)
 // is issued between the square-root chain of crossing j+1 (candidate speed from u_j and the next cell's 2 a dx), so that the in-order
 // issue of one warp always has two independent dependency chains to draw from.  `u_cur` was committed under `alive` (crossing j is
 // attempted by this lane); a lane whose test fails keeps (u_prev, t_prev) as its state.  Returns ok_j; the candidate u_{j+1} is
@@ -319,9 +287,8 @@ __device__ __forceinline__ int transit_step(double u_prev, double u_cur, double 
         "setp.lt.and.f64 pk, %0, %9, pa;\n\t"
         "fma.rn.f64 e, s, nt, 0d3FF0000000000000;\n\t"
         "selp.s32 %2, 1, 0, pk;\n\t"
-        "fma.rn.f64 c, e, 0d3FD8000000000000, 0d3FE0000000000000;\n\t"
         "mul.rn.f64 p, y, e;\n\t"
-        "fma.rn.f64 y1, c, p, y;\n\t"
+        "fma.rn.f64 y1, p, 0d3FE0000000000000, y;\n\t"
         "mul.rn.f64 g, s, y1;\n\t"
         "mov.b64 {lo, hi}, y1;\n\t"
         "add.s32 hi, hi, -1048576;\n\t"
@@ -347,9 +314,8 @@ __device__ __forceinline__ double transit_speed(double u, double dpe, double sgn
         "mul.rn.f64 t, y, y;\n\t"
         "neg.f64 nt, t;\n\t"
         "fma.rn.f64 e, s, nt, 0d3FF0000000000000;\n\t"
-        "fma.rn.f64 c, e, 0d3FD8000000000000, 0d3FE0000000000000;\n\t"
         "mul.rn.f64 p, y, e;\n\t"
-        "fma.rn.f64 y1, c, p, y;\n\t"
+        "fma.rn.f64 y1, p, 0d3FE0000000000000, y;\n\t"
         "mul.rn.f64 g, s, y1;\n\t"
         "mov.b64 {lo, hi}, y1;\n\t"
         "add.s32 hi, hi, -1048576;\n\t"
