@@ -36,7 +36,8 @@ enum : unsigned {
 };
 
 struct FieldArgs {
-    int scheme, Nx, Nh, smooth, nsp, tridiag_mode, pcr_levels, acc_stride, tab_cells;
+    int scheme, Nx, Nh, smooth, nsp, tridiag_mode, pcr_levels, acc_stride, tab_cells, acc_reps;
+    unsigned long long acc_rep_stride;
     const double *grid, *dx;
     const int *bc;
     double *phi, *phi_f, *rho, *J, *E, *a, *b, *c, *cp, *m, *pcr, *work, *scal, *rho_i;
@@ -159,14 +160,26 @@ __device__ void dev_collect(const FieldArgs &A, double *dst, int n, bool with_ru
         unsigned long long *g = A.acc + (size_t)s * A.acc_stride;
         if (with_runs) {
             unsigned long long *d = g + A.acc_stride / 2;
-            for (int i = threadIdx.x; i < n; i += FT) { scratch[i] = (long long)d[i + 1]; d[i + 1] = 0ull; }
-            if (threadIdx.x == 0) d[n + 1] = 0ull;        // closing entry of a run that ends on the last cell
+            for (int i = threadIdx.x; i < n; i += FT) {
+                // loads first (independent, in flight together), then the zeroing stores
+                unsigned long long q = 0ull;
+#pragma unroll 4
+                for (int r = 0; r < A.acc_reps; ++r) q += __ldcg(d + (size_t)r * A.acc_rep_stride + i + 1);
+#pragma unroll 4
+                for (int r = 0; r < A.acc_reps; ++r) d[(size_t)r * A.acc_rep_stride + i + 1] = 0ull;
+                scratch[i] = (long long)q;
+            }
+            if (threadIdx.x < A.acc_reps) d[(size_t)threadIdx.x * A.acc_rep_stride + n + 1] = 0ull;   // closing entry of a run that ends on the last cell
             __syncthreads();
             block_scan_i64(scratch, n);
         }
         for (int i = threadIdx.x; i < n; i += FT) {
-            long long q = (long long)g[i + 1];
-            g[i + 1] = 0ull;
+            unsigned long long qq = 0ull;
+#pragma unroll 4
+            for (int r = 0; r < A.acc_reps; ++r) qq += __ldcg(g + (size_t)r * A.acc_rep_stride + i + 1);
+#pragma unroll 4
+            for (int r = 0; r < A.acc_reps; ++r) g[(size_t)r * A.acc_rep_stride + i + 1] = 0ull;
+            long long q = (long long)qq;
             if (with_runs) q += scratch[i];
             const double v = (double)q * FX_INV;
             if (s == 0) dst[i] = v * A.qw[0];
@@ -749,6 +762,7 @@ static FieldArgs make_args(Ctx &c) {
     A.scheme = c.scheme; A.Nx = c.Nx; A.Nh = c.Nh; A.smooth = c.smooth; A.nsp = (int)c.sp.size();
     A.tridiag_mode = c.tridiag_mode; A.pcr_levels = c.pcr_levels;
     A.acc_stride = 2 * (std::max(c.Nx, c.Nh) + 2);
+    A.acc_reps = std::max(1, c.acc_reps); A.acc_rep_stride = c.acc_rep_stride;
     A.tab_cells = ((c.scheme == IPIC_SCHEME_CIC) ? c.Nx : c.Nh) + 2;
     A.grid = c.d_grid; A.dx = c.d_dx; A.bc = c.d_bc;
     A.phi = c.d_phi; A.phi_f = c.d_phi_f; A.rho = c.d_rho; A.J = c.d_J; A.E = c.d_E;
@@ -775,6 +789,21 @@ static int run_field(Ctx &c, const FieldArgs &A, unsigned ops) {
         configured = smem;
     }
     c.launches += 1; k_field<<<1, FT, smem, c.stream>>>(A, ops);
+    IPIC_CUDA(cudaGetLastError());
+    return IPIC_OK;
+}
+
+// copies 1.. of the deposition grids are added into copy 0 and zeroed (multi-GPU: copy 0 is what the all-reduce carries)
+__global__ void k_fold_acc(unsigned long long *acc, size_t count, int reps, size_t rep_stride) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    unsigned long long q = 0ull;
+    for (int r = 1; r < reps; ++r) { unsigned long long *p = acc + (size_t)r * rep_stride + i; q += *p; *p = 0ull; }
+    if (q) acc[i] += q;
+}
+int fold_acc(Ctx &c, size_t count) {
+    if (c.acc_reps <= 1) return IPIC_OK;
+    c.launches += 1; k_fold_acc<<<(unsigned)((count + 255) / 256), 256, 0, c.stream>>>(c.d_acc, count, c.acc_reps, c.acc_rep_stride);
     IPIC_CUDA(cudaGetLastError());
     return IPIC_OK;
 }

@@ -60,6 +60,8 @@ struct PushArgs {
     unsigned *tile_counter;    // dynamic tile scheduler (zeroed before the launch)
     unsigned long long *acc;   // !MOVE: int64 fixed-point grid [Nh] for this species
     unsigned long long *dacc;  // !MOVE: difference grid of the runs of fully traversed cells (prefix-summed by the field kernel)
+    unsigned long long acc_rep_stride;   // !MOVE: the grids exist in acc_reps copies, this many entries apart; CTA b deposits into copy b % acc_reps
+    int acc_reps;
     unsigned tile_stride;      // stride permutation of the tile order
     unsigned long long *counters;  // [0] deposit substeps, [1] func evals, [2] absorbed left, [3] absorbed right, [4] first reflections, [5] move substeps
     int Nh;                    // grid entries to deposit on
@@ -121,7 +123,11 @@ struct Ctx {
     double *d_pcr = nullptr; int pcr_levels = 0;                  // PCR level coefficients [levels][2][Nx] + inv diag [Nx]
     double *d_work = nullptr;                                     // scratch (4 * max(Nx,Nh))
     double *d_rho_i = nullptr;
-    unsigned long long *d_acc = nullptr;                          // [nsp_max][2][max(Nx,Nh)+2] int64 accumulators: grid, difference grid
+    // [acc_reps][nsp_max][2][max(Nx,Nh)+2] int64 accumulators: grid, difference grid.  The copies spread the global RED traffic of the
+    // push kernel over more addresses (and L2 slices): on a 256-cell grid every CTA otherwise hammers the same 2 KB.  Integer sums, so
+    // the split changes nothing in the result; the field kernel adds the copies when it collects.
+    unsigned long long *d_acc = nullptr;
+    int acc_reps = 1; size_t acc_rep_stride = 0;
     double2 *d_ttab = nullptr;                                    // [nsp_max][cells] NGP transit table
     void *d_tab = nullptr;                                        // [nsp_max][cells] CellTab*
     unsigned long long *d_counters = nullptr;                     // [nsp_max][8]
@@ -187,6 +193,7 @@ int launch_deposit(Ctx &c, int sp, double del_t);
 int launch_move(Ctx &c, int sp, double del_t);
 int launch_deposit_rho(Ctx &c, int sp);
 int compact_species(Ctx &c, int sp);
+int fold_acc(Ctx &c, size_t count);                    // CTA copies of the deposition grids -> copy 0
 int collect_reflected(Ctx &c, int sp);                 // flagged pre-compaction indices -> refList
 int map_reflected(Ctx &c, int sp, bool compacted);     // -> post-compaction indices (absorbed ones dropped)
 int particle_moments(Ctx &c, int sp, double out4[4]);      // sum v^2, sum vx, vy, vz

@@ -237,19 +237,19 @@ __device__ __forceinline__ void deposit_add(WarpSmem &W, DepositState &D, int la
 constexpr long long FX_ONE = 1ll << FX_BITS;
 
 // ends a run of fully traversed cells; `cend` is the cell the particle is in now (not part of the run)
-__device__ __forceinline__ void close_run(WarpSmem &W, DepositState &D, int lane, const PushArgs &A, int pend, int cend) {
+__device__ __forceinline__ void close_run(WarpSmem &W, DepositState &D, int lane, unsigned long long *gacc, unsigned long long *gdacc, int pend, int cend) {
     if (pend > 0) {                                          // moving right: cells pend .. cend-1 got +1 each
-        if (cend - pend == 1) deposit_add(W, D, lane, A.acc, pend, FX_ONE);
+        if (cend - pend == 1) deposit_add(W, D, lane, gacc, pend, FX_ONE);
         else {
-            atomicAdd(A.dacc + pend, (unsigned long long)FX_ONE);
-            atomicAdd(A.dacc + cend, (unsigned long long)(-FX_ONE));
+            atomicAdd(gdacc + pend, (unsigned long long)FX_ONE);
+            atomicAdd(gdacc + cend, (unsigned long long)(-FX_ONE));
         }
     } else {                                                 // moving left: cells cend+1 .. -pend got -1 each
         const int start = -pend;
-        if (start - cend == 1) deposit_add(W, D, lane, A.acc, start, -FX_ONE);
+        if (start - cend == 1) deposit_add(W, D, lane, gacc, start, -FX_ONE);
         else {
-            atomicAdd(A.dacc + cend + 1, (unsigned long long)(-FX_ONE));
-            atomicAdd(A.dacc + start + 1, (unsigned long long)FX_ONE);
+            atomicAdd(gdacc + cend + 1, (unsigned long long)(-FX_ONE));
+            atomicAdd(gdacc + start + 1, (unsigned long long)FX_ONE);
         }
     }
 }
@@ -334,6 +334,9 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpSmem &W = reinterpret_cast<WarpSmem *>(smem_raw)[warp];
     DepositState D;
+    // this CTA's copy of the deposition grids (see Ctx::d_acc)
+    const size_t rep_off = MOVE ? 0 : (size_t)(blockIdx.x % (unsigned)A.acc_reps) * A.acc_rep_stride;
+    unsigned long long *const gacc = A.acc + rep_off, *const gdacc = A.dacc + rep_off;
     if (!MOVE) {
 #pragma unroll
         for (int k = 0; k < WIN; ++k) W.win[k][lane] = 0ull;
@@ -502,9 +505,9 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
                             const double dl = l_fw - lw;
                             const bool full = (fabs(dl) == 1.0);
                             const bool right = dl > 0.0;
-                            if (pend != 0 && !(full && ((pend > 0) == right))) { close_run(W, D, lane, A, pend, cell); pend = 0; }
+                            if (pend != 0 && !(full && ((pend > 0) == right))) { close_run(W, D, lane, gacc, gdacc, pend, cell); pend = 0; }
                             if (full) pend = (pend != 0) ? pend : (right ? cell : -cell);
-                            else deposit_add(W, D, lane, A.acc, cell, fx_from_double(dl));
+                            else deposit_add(W, D, lane, gacc, cell, fx_from_double(dl));
                         }
                     } else {
                         const double2 *tp2 = reinterpret_cast<const double2 *>(reinterpret_cast<const CellTabCIC *>(A.tab) + cell);
@@ -545,8 +548,8 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
                         if (MOVE) nfev += (unsigned)numIter;
                         if (!MOVE) {
                             const double Jp = l_f - l;
-                            deposit_add(W, D, lane, A.acc, cell, fx_from_double((1.0 - d_half) * Jp));
-                            deposit_add(W, D, lane, A.acc, cell + 1, fx_from_double(Jp * d_half));
+                            deposit_add(W, D, lane, gacc, cell, fx_from_double((1.0 - d_half) * Jp));
+                            deposit_add(W, D, lane, gacc, cell + 1, fx_from_double(Jp * d_half));
                         }
                     }
                     bool absorbed = false;
@@ -558,7 +561,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
                             const int b = (lb == 1) ? A.bcL : A.bcR;
                             if (!MOVE && SCHEME != 1 && b != 0 && pend != 0) {
                                 // a run that ends on a wall includes the wall cell: the particle does not move on to a new cell
-                                close_run(W, D, lane, A, pend, cell + (pend > 0 ? 1 : -1));
+                                close_run(W, D, lane, gacc, gdacc, pend, cell + (pend > 0 ? 1 : -1));
                                 pend = 0;
                             }
                             if (b == 0) {
@@ -592,7 +595,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
                             A.l_out[gi] = l_f;
                             A.vx_out[gi] = v_f;
                         }
-                        if (!MOVE && SCHEME != 1 && pend != 0) close_run(W, D, lane, A, pend, cell);
+                        if (!MOVE && SCHEME != 1 && pend != 0) close_run(W, D, lane, gacc, gdacc, pend, cell);
                     } else {
                         cont = true;
                     }
@@ -644,7 +647,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
                 // follow the stream: re-centre the accumulators on the cell of the sub-tile's first particle
                 const int nb = __shfl_sync(FULL, cell, 0);
                 if (nb != D.base && nb > 0) {
-                    deposit_flush(W, D, lane, A.acc);
+                    deposit_flush(W, D, lane, gacc);
                     D.base = nb;
                 }
             }
@@ -659,7 +662,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
                     const double l_fw = fma((v + v_f) * del_t, t0.y, lw);
                     done = ((SCHEME == 2) ? ((int)(l_fw + 1.0) == 1) : ((int)l_fw == cell)) && ((v > 0.0) == (v_f > 0.0));
                     if (done) {
-                        if (!MOVE) deposit_add(W, D, lane, A.acc, cell, fx_from_double(l_fw - lw));
+                        if (!MOVE) deposit_add(W, D, lane, gacc, cell, fx_from_double(l_fw - lw));
                         else { A.l_out[gi] = l_fw + lc; A.vx_out[gi] = v_f; }
                     }
                 } else {
@@ -691,8 +694,8 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
                                 A.l_out[gi] = l_f; A.vx_out[gi] = 2.0 * v_half - v;
                             } else {
                                 const double Jp = l_f - l;
-                                deposit_add(W, D, lane, A.acc, cell, fx_from_double((1.0 - d_half) * Jp));
-                                deposit_add(W, D, lane, A.acc, cell + 1, fx_from_double(Jp * d_half));
+                                deposit_add(W, D, lane, gacc, cell, fx_from_double((1.0 - d_half) * Jp));
+                                deposit_add(W, D, lane, gacc, cell + 1, fx_from_double(Jp * d_half));
                             }
                         }
                     }
@@ -714,7 +717,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
     }
 
     // ---------------- epilogue: accumulators, counters ----------------
-    if (!MOVE) deposit_flush(W, D, lane, A.acc);
+    if (!MOVE) deposit_flush(W, D, lane, gacc);
     {
         const unsigned s0 = __reduce_add_sync(FULL, nsub);
         if (lane == 0 && s0) atomicAdd(&A.counters[MOVE ? 5 : 0], (unsigned long long)s0);
@@ -760,6 +763,7 @@ static int make_push_args(Ctx &c, int sp, double del_t, PushArgs &A) {
     const size_t NM = (size_t)std::max(c.Nx, c.Nh) + 2;
     A.acc = c.d_acc + (size_t)sp * 2 * NM;
     A.dacc = A.acc + NM;
+    A.acc_reps = std::max(1, c.acc_reps); A.acc_rep_stride = c.acc_rep_stride;
     {   // stride permutation of the tile order: an odd multiplier near the golden ratio, coprime with the tile count
         const unsigned long long ntiles = ((unsigned long long)s.n + TILE - 1) / TILE;
         unsigned long long st = (unsigned long long)(0.6180339887498949 * (double)ntiles) | 1ull;

@@ -2,7 +2,7 @@
 # usage (GPU box): scripts/gpu_configs.sh <tag>  -- bench lines of the other BASELINE configs (C1, C2, C3) next to the C5 line
 tag=${1:-rX}
 mkdir -p gpurun_out
-for w in c1 c2 c3 c4; do
+for w in c1 c2 c4; do
   timeout 900 python bench.py --workload $w --steps 5 --warmup 3 --cpu-seconds 8 > gpurun_out/${tag}_bench_${w}.json 2> gpurun_out/${tag}_bench_${w}.err
   python - <<PY
 import json
