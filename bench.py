@@ -455,14 +455,14 @@ def run_cuda_arm(args, w):
                 "kernel_share_of_step": dep_ms / max(ms, 1e-9)}
     # second bound of the same kernel: the sub-step loop of the electrons is FP64 work, not bytes.  One face-to-face crossing is 14 FP64 + 15 other
     # instructions per warp; FP64 instructions issue every other cycle on sm_100 (scripts/micro/fp64_tput.cu), and the loop in isolation at 8 warps
-    # per sub-partition runs at 46.8 cycles per crossing (scripts/micro/transit_bench.cu) -- that is the floor quoted here.
+    # per sub-partition runs at 46.5 cycles per crossing (scripts/micro/transit_bench.cu) -- that is the floor quoted here.
     if w["scheme"] != 1 and t_dep0 > 0:
         props = torch.cuda.get_device_properties(torch.cuda.current_device())
         sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
-        floor = props.multi_processor_count * 4 * sm_hz / 46.8 * 32.0
+        floor = props.multi_processor_count * 4 * sm_hz / 46.5 * 32.0
         roofline["issue_bound"] = {"what": "electron sub-steps per second inside the depositJ sweeps vs the measured issue floor of the crossing loop",
                                    "achieved": dep_sub_e / (t_dep0 * 1e-3), "peak": floor, "frac": dep_sub_e / (t_dep0 * 1e-3) / floor,
-                                   "unit": "sub-steps/s", "floor_cycles_per_crossing_per_sm_subpartition": 46.8,
+                                   "unit": "sub-steps/s", "floor_cycles_per_crossing_per_sm_subpartition": 46.5,
                                    "electron_substeps_per_particle_per_sweep": dep_sub_e / max(n_dep0 * n_e, 1)}
 
     line = None

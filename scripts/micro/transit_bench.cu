@@ -1,5 +1,5 @@
 // Micro-benchmark of the lean transit loop in isolation: cycles per face-to-face crossing per SM sub-partition as a function of the
-// resident warps (the FP64 pipe floor is 14 instructions x 2 cycles = 28).  The two device functions are the ones of particles.cu.
+// resident warps (FP64 instructions issue every 2nd cycle and do not co-issue with the rest: 13 FP64 + 14 others ~ 40 cycles).  The two device functions are the ones of particles.cu.
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o transit_bench transit_bench.cu
 #include <cstdio>
 #include <cuda_runtime.h>
@@ -9,7 +9,7 @@ __device__ __forceinline__ int transit_step(double u_prev, double u_cur, double 
     int ok;
     asm("{\n\t"
         ".reg .pred pa, pk;\n\t"
-        ".reg .f64 uu, s, y, t, nt, e, c, p, g, ng, h, r, d;\n\t"
+        ".reg .f64 uu, s, y, y1, t, nt, e, c, p, g, ng, h, r, d;\n\t"
         ".reg .b32 lo, hi;\n\t"
         "setp.ne.s32 pa, %10, 0;\n\t"
         "mul.rn.f64 uu, %4, %4;\n\t"
@@ -23,11 +23,10 @@ __device__ __forceinline__ int transit_step(double u_prev, double u_cur, double 
         "setp.lt.and.f64 pk, %0, %9, pa;\n\t"
         "fma.rn.f64 e, s, nt, 0d3FF0000000000000;\n\t"
         "selp.s32 %2, 1, 0, pk;\n\t"
-        "fma.rn.f64 c, e, 0d3FD8000000000000, 0d3FE0000000000000;\n\t"
         "mul.rn.f64 p, y, e;\n\t"
-        "fma.rn.f64 y, c, p, y;\n\t"
-        "mul.rn.f64 g, s, y;\n\t"
-        "mov.b64 {lo, hi}, y;\n\t"
+        "fma.rn.f64 y1, p, 0d3FE0000000000000, y;\n\t"
+        "mul.rn.f64 g, s, y1;\n\t"
+        "mov.b64 {lo, hi}, y1;\n\t"
         "add.s32 hi, hi, -1048576;\n\t"
         "mov.b64 h, {lo, hi};\n\t"
         "neg.f64 ng, g;\n\t"
@@ -42,7 +41,7 @@ __device__ __forceinline__ int transit_step(double u_prev, double u_cur, double 
 __device__ __forceinline__ double transit_speed(double u, double dpe, double sgn) {
     double uf;
     asm("{\n\t"
-        ".reg .f64 uu, s, y, t, nt, e, c, p, g, ng, h, r;\n\t"
+        ".reg .f64 uu, s, y, y1, t, nt, e, c, p, g, ng, h, r;\n\t"
         ".reg .b32 lo, hi;\n\t"
         "mul.rn.f64 uu, %1, %1;\n\t"
         "fma.rn.f64 s, %3, %2, uu;\n\t"
@@ -50,11 +49,10 @@ __device__ __forceinline__ double transit_speed(double u, double dpe, double sgn
         "mul.rn.f64 t, y, y;\n\t"
         "neg.f64 nt, t;\n\t"
         "fma.rn.f64 e, s, nt, 0d3FF0000000000000;\n\t"
-        "fma.rn.f64 c, e, 0d3FD8000000000000, 0d3FE0000000000000;\n\t"
         "mul.rn.f64 p, y, e;\n\t"
-        "fma.rn.f64 y, c, p, y;\n\t"
-        "mul.rn.f64 g, s, y;\n\t"
-        "mov.b64 {lo, hi}, y;\n\t"
+        "fma.rn.f64 y1, p, 0d3FE0000000000000, y;\n\t"
+        "mul.rn.f64 g, s, y1;\n\t"
+        "mov.b64 {lo, hi}, y1;\n\t"
         "add.s32 hi, hi, -1048576;\n\t"
         "mov.b64 h, {lo, hi};\n\t"
         "neg.f64 ng, g;\n\t"
@@ -64,7 +62,6 @@ __device__ __forceinline__ double transit_speed(double u, double dpe, double sgn
         : "=d"(uf) : "d"(u), "d"(dpe), "d"(sgn));
     return uf;
 }
-
 
 __global__ void __launch_bounds__(1024, 1) k_transit(const double2 *__restrict__ ttab, int ncell, int iters, double t_lim, double *out, long long *cyc) {
     const int lane = threadIdx.x & 31;
