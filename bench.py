@@ -370,6 +370,7 @@ def run_cuda_arm(args, w):
     # per-kernel device time from the library's own CUDA events (recorded on the launching stream)
     t_dep0, n_dep0 = solver.timing("depositJ_sp0")
     t_dep1, n_dep1 = solver.timing("depositJ_sp1")
+    t_pair, n_pair = solver.timing("depositJ_pair")             # both species in one launch (the default for two-species plasmas)
     t_move, _ = solver.timing("moveParticles_kernels")
     t_comp, _ = solver.timing("compaction")
     t_field, n_field = solver.timing("field_kernels")
@@ -441,29 +442,34 @@ def run_cuda_arm(args, w):
 
     # ---- roofline of the dominant kernel (the depositJ push sweep) ----
     peak, peak_src = measured_peak_gbs()
-    dep_ms = t_dep0 + t_dep1
-    dep_launches = n_dep0 + n_dep1
-    # algorithmic bytes: 16 B (l, v_x) per particle per depositJ sweep; units per launch = particles of that species
-    alg_bytes_total = 16.0 * (n_dep0 * n_e + n_dep1 * n_i)          # particle counts change by <0.1% per step (wall losses)
+    paired = n_pair > 0
+    dep_ms = t_pair if paired else t_dep0 + t_dep1
+    dep_launches = n_pair if paired else n_dep0 + n_dep1
+    # algorithmic bytes: 16 B (l, v_x) per particle per depositJ sweep; units per launch = the particles the launch sweeps
+    # (both species when paired, one species otherwise); particle counts change by <0.1% per step (wall losses)
+    alg_bytes_total = 16.0 * (n_pair * (n_e + n_i) if paired else (n_dep0 * n_e + n_dep1 * n_i))
     achieved = alg_bytes_total / max(dep_ms * 1e-3, 1e-12) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_push<NGP,deposit> (depositJ sweep, one launch per species)" if w["scheme"] == 0
-                else ("k_push<CIC,deposit>" if w["scheme"] == 1 else "k_push<NGP_Periodic,deposit>") + " (depositJ sweep, one launch per species)",
+    units = (n_e + n_i) if paired else (n_e + n_i) / 2.0
+    kname = {0: "NGP", 1: "CIC", 2: "NGP_Periodic"}[w["scheme"]]
+    roofline = {"bound": "hbm", "kernel": ("k_push_pair<%s> (depositJ sweep, both species in one launch)" % kname) if paired
+                else ("k_push<%s,deposit> (depositJ sweep, one launch per species)" % kname),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": (args.traffic_bytes_per_particle * (n_e + n_i) / 2.0) if args.traffic_bytes_per_particle else None,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": 16.0 * (n_e + n_i) / 2.0, "avg_launch_ms": dep_ms / max(dep_launches, 1),
-                "per_species_ms": {"electrons": t_dep0 / max(n_dep0, 1), "ions": t_dep1 / max(n_dep1, 1)},
+                "traffic": (args.traffic_bytes_per_particle * units) if args.traffic_bytes_per_particle else None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": 16.0 * units, "avg_launch_ms": dep_ms / max(dep_launches, 1),
+                "per_species_ms": {"both": t_pair / max(n_pair, 1)} if paired else {"electrons": t_dep0 / max(n_dep0, 1), "ions": t_dep1 / max(n_dep1, 1)},
                 "kernel_share_of_step": dep_ms / max(ms, 1e-9)}
     # second bound of the same kernel: the sub-step loop of the electrons is FP64 work, not bytes.  One face-to-face crossing is 14 FP64 + 15 other
     # instructions per warp; FP64 instructions issue every other cycle on sm_100 (scripts/micro/fp64_tput.cu), and the loop in isolation at 8 warps
     # per sub-partition runs at 46.5 cycles per crossing (scripts/micro/transit_bench.cu) -- that is the floor quoted here.
-    if w["scheme"] != 1 and t_dep0 > 0:
+    t_e_sweeps, n_e_sweeps = (t_pair, n_pair) if paired else (t_dep0, n_dep0)     # paired: the electrons share the launch with the ions
+    if w["scheme"] != 1 and t_e_sweeps > 0:
         props = torch.cuda.get_device_properties(torch.cuda.current_device())
         sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
         floor = props.multi_processor_count * 4 * sm_hz / 46.5 * 32.0
         roofline["issue_bound"] = {"what": "electron sub-steps per second inside the depositJ sweeps vs the measured issue floor of the crossing loop",
-                                   "achieved": dep_sub_e / (t_dep0 * 1e-3), "peak": floor, "frac": dep_sub_e / (t_dep0 * 1e-3) / floor,
+                                   "achieved": dep_sub_e / (t_e_sweeps * 1e-3), "peak": floor, "frac": dep_sub_e / (t_e_sweeps * 1e-3) / floor,
                                    "unit": "sub-steps/s", "floor_cycles_per_crossing_per_sm_subpartition": 46.5,
-                                   "electron_substeps_per_particle_per_sweep": dep_sub_e / max(n_dep0 * n_e, 1)}
+                                   "electron_substeps_per_particle_per_sweep": dep_sub_e / max(n_e_sweeps * n_e, 1)}
 
     line = None
     if rank == 0:

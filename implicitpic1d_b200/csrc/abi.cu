@@ -102,9 +102,14 @@ static int read_counters(Ctx &c, unsigned long long *out /* NSP_MAX*8 */) {
 static int sweep_deposit(Ctx &c, double del_t) {
     {
         Timed t(c, "depositJ_kernels");
-        for (int s = 0; s < (int)c.sp.size(); ++s) {
-            Timed ts(c, s == 0 ? "depositJ_sp0" : (s == 1 ? "depositJ_sp1" : "depositJ_spN"));
-            RC(launch_deposit(c, s, del_t));
+        if (c.pair_species && c.sp.size() == 2) {
+            Timed ts(c, "depositJ_pair");
+            RC(launch_deposit_pair(c, 0, 1, del_t));
+        } else {
+            for (int s = 0; s < (int)c.sp.size(); ++s) {
+                Timed ts(c, s == 0 ? "depositJ_sp0" : (s == 1 ? "depositJ_sp1" : "depositJ_spN"));
+                RC(launch_deposit(c, s, del_t));
+            }
         }
     }
     if (c.nranks > 1) { Timed t(c, "allreduce_J"); RC(allreduce_acc(c)); }
@@ -780,6 +785,8 @@ int ipic_set_option(ipic_handle h, const char *name, double value) {
     if (k == "stay_min" || k == "refill_min") c->stay_min = (int)value;
     else if (k == "push_blocks") c->push_blocks = (int)value;
     else if (k == "transit_min") c->transit_min = (int)value;
+    else if (k == "pair_species") c->pair_species = (int)value;
+    else if (k == "pair_warps") c->pair_warps = (int)value;
     else if (k == "tile_order") c->tile_order = (int)value;
     else if (k == "timing") c->timing_on = value != 0.0;
     else if (k == "use_tma") { /* accepted for compatibility: the streaming path is register-prefetched */ }

@@ -159,6 +159,9 @@ struct Ctx {
     // options
     int stay_min = 20;
     int transit_min = 12;
+    int pair_species = 0;      // 1 = depositJ of a two-species plasma in one launch (k_push_pair).  Off: measured slower (C5: 2.34 ms per
+                               // sweep against 1.88 + 0.32 ms) -- both species' sweeps are issue-bound, so running them side by side frees nothing
+    int pair_warps = 4;        // warps per CTA (of 32) that start with the second species
     int tile_order = 1;           // 1 = stride-permuted tile order, 0 = in array order
     int push_blocks = 0;          // 0 = one CTA per SM
     int lazy_compaction = 0;
@@ -191,6 +194,7 @@ void set_error(const std::string &s);
 // ---- launchers implemented in particles.cu ---------------------------------------------------------
 int launch_deposit(Ctx &c, int sp, double del_t);
 int launch_move(Ctx &c, int sp, double del_t);
+int launch_deposit_pair(Ctx &c, int a, int b, double del_t);
 int launch_deposit_rho(Ctx &c, int sp);
 int compact_species(Ctx &c, int sp);
 int fold_acc(Ctx &c, size_t count);                    // CTA copies of the deposition grids -> copy 0

@@ -13,6 +13,7 @@
 namespace ipic {
 
 #define FULL 0xffffffffu
+#define RC_(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
 
 // =====================================================================================================
 // Shared-memory fixed-point grid: each cell is three 32-bit limbs (16/16/32-bit digits of the int64 sum)
@@ -328,11 +329,10 @@ __device__ __forceinline__ double transit_speed(double u, double dpe, double sgn
     return uf;
 }
 
+// The whole sweep of one species by one warp: claims tiles until the species has none left, drains its queue, flushes its deposits
+// and counters.  `A` is always a kernel parameter (constant bank), so the body can be instantiated for several species in one kernel.
 template <int SCHEME, bool MOVE>
-__global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpSmem &W = reinterpret_cast<WarpSmem *>(smem_raw)[warp];
+__device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const int lane) {
     DepositState D;
     // this CTA's copy of the deposition grids (see Ctx::d_acc)
     const size_t rep_off = MOVE ? 0 : (size_t)(blockIdx.x % (unsigned)A.acc_reps) * A.acc_rep_stride;
@@ -732,6 +732,53 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const PushArgs A) {
             }
         }
     }
+    __syncwarp();
+}
+
+template <int SCHEME, bool MOVE>
+__global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const __grid_constant__ PushArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    push_body<SCHEME, MOVE>(A, reinterpret_cast<WarpSmem *>(smem_raw)[warp], lane);
+}
+
+// depositJ sweep of TWO species in one launch.  Each warp works through one species' tiles and then through the other's; the first
+// `warps_b_first` warps of every CTA start with species B.  A memory-bound species (ions: one sub-step per particle, limited by load
+// latency) and an issue-bound one (electrons crossing many cells: FP64 work, HBM idle) then run side by side on every SM instead of one
+// after the other; whichever runs out of tiles first simply donates its warps to the other.  Results are unchanged: the species keep
+// their own grids, counters and tile counters, and deposition is order-independent integer arithmetic.
+// Kept as an option (`pair_species`), off by default: on B200 the ion sweep turned out to be issue-bound as well (65 % issue
+// utilisation), so the pairing only adds the two instruction streams -- measured 2.34 ms per sweep against 1.88 + 0.32 ms.
+template <int SCHEME>
+__global__ void __launch_bounds__(PUSH_THREADS, 1) k_push_pair(const __grid_constant__ PushArgs A, const __grid_constant__ PushArgs B, const int warps_b_first) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpSmem &W = reinterpret_cast<WarpSmem *>(smem_raw)[warp];
+    if (warp < warps_b_first) {
+        push_body<SCHEME, false>(B, W, lane);
+        push_body<SCHEME, false>(A, W, lane);
+    } else {
+        push_body<SCHEME, false>(A, W, lane);
+        push_body<SCHEME, false>(B, W, lane);
+    }
+}
+
+template <int SCHEME>
+static int launch_push_pair_v(Ctx &c, const PushArgs &A, const PushArgs &B) {
+    const size_t smem = (size_t)PUSH_WARPS * sizeof(WarpSmem);
+    static bool configured[64] = {};
+    if (!configured[c.device & 63]) {
+        IPIC_CUDA(cudaFuncSetAttribute(k_push_pair<SCHEME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IPIC_CUDA(cudaFuncSetAttribute(k_push_pair<SCHEME>, cudaFuncAttributePreferredSharedMemoryCarveout, 52));
+        configured[c.device & 63] = true;
+    }
+    IPIC_CUDA(cudaMemsetAsync(A.tile_counter, 0, sizeof(unsigned), c.stream));
+    IPIC_CUDA(cudaMemsetAsync(B.tile_counter, 0, sizeof(unsigned), c.stream));
+    const int blocks = c.push_blocks > 0 ? c.push_blocks : c.num_sms;
+    const int wb = std::min(PUSH_WARPS - 1, std::max(1, c.pair_warps));
+    c.launches += 1; k_push_pair<SCHEME><<<blocks, PUSH_THREADS, smem, c.stream>>>(A, B, wb);
+    IPIC_CUDA(cudaGetLastError());
+    return IPIC_OK;
 }
 
 template <int SCHEME, bool MOVE>
@@ -806,6 +853,23 @@ int launch_deposit(Ctx &c, int sp, double del_t) {
     if (c.scheme == IPIC_SCHEME_NGP) return launch_push_v<0, false>(c, A);
     if (c.scheme == IPIC_SCHEME_NGP_PERIODIC) return launch_push_v<2, false>(c, A);
     return launch_push_v<1, false>(c, A);
+}
+
+// both species of a two-species plasma in one launch (species `a` first for most warps, `b` first for c.pair_warps of them)
+int launch_deposit_pair(Ctx &c, int a, int b, double del_t) {
+    PushArgs A, B;
+    int rc = make_push_args(c, a, del_t, A);
+    if (rc) return rc;
+    rc = make_push_args(c, b, del_t, B);
+    if (rc) return rc;
+    if (A.n == 0 || B.n == 0) {
+        if (A.n) RC_(launch_deposit(c, a, del_t));
+        if (B.n) RC_(launch_deposit(c, b, del_t));
+        return IPIC_OK;
+    }
+    if (c.scheme == IPIC_SCHEME_NGP) return launch_push_pair_v<0>(c, A, B);
+    if (c.scheme == IPIC_SCHEME_NGP_PERIODIC) return launch_push_pair_v<2>(c, A, B);
+    return launch_push_pair_v<1>(c, A, B);
 }
 
 int launch_move(Ctx &c, int sp, double del_t) {
