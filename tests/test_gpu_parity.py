@@ -282,6 +282,75 @@ def test_large_load_properties():
         solver.close()
 
 
+FULL_SIZE = {
+    # BASELINE configs[1]: default CIC deck scaled to 1e7 particles (OpenMP/CIC/InputData)
+    "c2_cic_1e7": dict(scheme=1, Nx=256, L=0.067, n_ave=5.12e14, T_e=2.59, T_i=0.025, bcL=1, bcR=4, Vl=0.0, Vr=200.0, rf=13.56e6, smooth=1, frac=1.5,
+                       dt_deck=9.218289085545723e-11, eps_a=1e-6, m=10, N=5_000_000, e_tol=1e-7),
+    # BASELINE configs[4] per-GPU shard: default NGP deck, 4096 cells, 1.25e8 particles
+    "c5_ngp_shard": dict(scheme=0, Nx=4097, L=0.067 * 4096 / 1000.0, n_ave=1.6e18, T_e=4.0, T_i=0.025, bcL=1, bcR=4, Vl=0.0, Vr=2000.0, rf=200.0e6, smooth=1,
+                         frac=10.0, dt_deck=1.0, eps_a=1e-8, m=10, N=62_500_000, e_tol=1e-7),
+}
+
+
+@pytest.mark.parametrize("name", sorted(FULL_SIZE))
+def test_full_size_properties(name):
+    """BASELINE.json's own sizes, where the oracle is too slow to be the checker: the size-independent properties the scheme offers
+    (main.f90:93-114) -- total energy conserved to the nonlinear tolerance, charge continuity to round-off, every particle accounted
+    for -- plus determinism: J is bit-identical from sweep to sweep and for a different tile schedule / CTA count."""
+    import ctypes as C
+    from implicitpic1d_b200.domain import readWorld
+    from implicitpic1d_b200 import constants as K
+    w = FULL_SIZE[name]
+    world = readWorld(w["scheme"], w["Nx"], w["L"], 0, 0.0, w["bcL"], w["bcR"], w["smooth"], w["T_e"], w["n_ave"])
+    solver = ip.potentialSolver(world, w["Vl"], w["Vr"], w["rf"], 0.0)
+    try:
+        N = w["N"]
+        L = ip.load_library()
+        m_ion = 4.002602 * K.m_amu - K.m_e
+        plist = [ip.Particle(K.m_e, -K.e, w["n_ave"] * world.L_domain / N, 0, 0, "e", 1),
+                 ip.Particle(m_ion, K.e, w["n_ave"] * world.L_domain / N, 0, 0, "He+", 1)]
+        solver._bind(plist)
+        _lib.check(L.ipic_generate_particles(solver._h, 0, N, w["T_e"], 0.0, 2026))
+        _lib.check(L.ipic_generate_particles(solver._h, 1, N, w["T_i"], 0.0, 2026))
+        for p in plist:
+            _lib.check(L.ipic_sort_particles(solver._h, p._index))
+        ip.initializeSolver(solver, w["eps_a"], 0.0, 0, w["m"], 0.5, 100)
+        solver.solveInitialPotential(plist, world, 0.0)
+        del_t = K.del_t_from_deck(w["n_ave"], w["frac"], w["dt_deck"])
+        # determinism of the deposition
+        ip.depositJ(solver, plist, world, del_t)
+        J0 = solver.J.copy()
+        ip.depositJ(solver, plist, world, del_t)
+        assert np.array_equal(J0, solver.J)
+        solver.set_option("tile_order", 0)
+        solver.set_option("push_blocks", 97)
+        ip.depositJ(solver, plist, world, del_t)
+        assert np.array_equal(J0, solver.J)
+        solver.set_option("tile_order", 1)
+        solver.set_option("push_blocks", 0)
+        assert np.all(np.isfinite(J0)) and np.max(np.abs(J0)) > 0
+        # two implicit steps: conservation laws
+        tcur, remain, curr = 0.0, del_t, del_t
+        for step in range(2):
+            rho_i = solver.rho if step == 0 else rho_f
+            KE_i = sum(p.getTotalKE() for p in plist)
+            PE_i = solver.getTotalPE(world, False) if step == 0 else solver.getTotalPE(world, True)
+            n_before = sum(p.count() for p in plist)
+            remain, curr = ip.solvePotential(solver, plist, world, del_t, remain, curr, tcur)
+            tcur += curr
+            st = ip.SolverState(solver)
+            assert st.iterNumPicard < 100
+            KE_f = sum(p.getTotalKE() + p.energyLoss.sum() * p.mass * p.w_p * 0.5 for p in plist)
+            PE_f = solver.getTotalPE(world, True) - solver.getEnergyFromBoundary(world, curr)
+            assert abs((PE_i + KE_i - PE_f - KE_f) / (PE_i + KE_i)) < w["e_tol"], (step, PE_i, KE_i, PE_f, KE_f)
+            solver.depositRho(plist, world)
+            rho_f = solver.rho
+            assert solver.getChargeContinuityError(rho_i, world, curr) < 1e-6
+            assert sum(p.count() + p.delIdx for p in plist) == n_before
+    finally:
+        solver.close()
+
+
 def test_two_gpu_sharded_step_is_bitwise_single_gpu():
     """needs >= 2 GPUs on the box: launches tests/multi_gpu_check.py under torchrun"""
     import ctypes as C, os, subprocess, sys
