@@ -417,3 +417,42 @@ def test_refRecordIdx_matches_oracle(name):
                 assert cnt["delIdx"].sum() > 0                    # the compaction did shift the electrons' indices
         assert total > 20
     solver.close()
+
+
+@pytest.mark.parametrize("name", ["ngp_rf", "cic_rf"])
+def test_empty_and_ragged_slabs(name):
+    """edge cases of the container (mod_particle.f90:15-37: N_p(T) is per thread slab and may be anything up to finalIdx): an empty slab, a
+    one-particle slab, a full slab, and a species with no particles at all -- depositJ and moveParticles against the oracle on the same slabs"""
+    d = DECKS[name]
+    o = build_oracle(d)
+    world, solver, plist = build_cuda_from_oracle(d, o, tridiag_mode=_lib.TRIDIAG_THOMAS)
+    del_t = deck_del_t(d)
+    T, ppt = d["T"], d["ppt"]
+    ragged = [np.array([ppt, 0, 1, ppt // 3][:T], dtype=np.int32), np.zeros(T, dtype=np.int32)]    # electrons ragged, no ions at all
+    for sp, p in enumerate(plist):
+        o.set_N_p(sp, ragged[sp])
+        p.N_p = ragged[sp].copy()
+        p.upload()
+        assert p.count() == int(ragged[sp].sum())
+    solver.phi, solver.phi_f, solver.rho = o.get("phi"), o.get("phi_f"), o.get("rho")
+    o.makeHalfTimeEField(); solver.makeHalfTimeEField()
+    o.depositJ(del_t)
+    ip.depositJ(solver, plist, world, del_t)
+    assert relerr(solver.J, o.get("J")) < TOL_GRID
+    assert depositSubsteps(solver, plist[0]) == o.move_stats(0)["substepsDeposit"] and depositSubsteps(solver, plist[1]) == 0
+    o.moveParticles(del_t)
+    ip.moveParticles(solver, plist, world, del_t)
+    for sp, p in enumerate(plist):
+        ps_g, ps_o = p.download(), o.phase_space(sp)
+        assert np.array_equal(p.N_p, o.N_p(sp))
+        assert p.delIdx == int(o.counters(sp)["delIdx"].sum())
+        for t in range(T):
+            n = p.N_p[t]
+            assert np.max(np.abs(ps_g[t, :n, 0] - ps_o[t, :n, 0]), initial=0.0) < 1e-9
+            assert np.array_equal(ps_g[t, :n, 2:], ps_o[t, :n, 2:])
+    assert plist[1].count() == 0 and plist[1].getTotalKE() == 0.0
+    # rho of an empty species is zero; the solver still runs
+    solver.depositRho(plist, world)
+    o.depositRho()
+    assert relerr(solver.rho, o.get("rho")) < TOL_GRID
+    solver.close()
