@@ -139,6 +139,13 @@ module ipic_b200_c
             real(c_double), value :: timeFuture
             integer(c_int) :: rc
         end function
+        function ipic_set_cic_walls(handle, boundPhi, RF_voltage, sourceTermVals) bind(c, name="ipic_set_cic_walls") result(rc)
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value :: handle
+            real(c_double), intent(in) :: boundPhi(2), sourceTermVals(2)
+            real(c_double), value :: RF_voltage
+            integer(c_int) :: rc
+        end function
         function ipic_deposit_J(handle, del_t) bind(c, name="ipic_deposit_J") result(rc)
             import :: c_ptr, c_int, c_double
             type(c_ptr), value :: handle
@@ -180,6 +187,18 @@ module ipic_b200_c
             type(c_ptr), value :: handle
             real(c_double), value :: del_t, timeCurrent
             real(c_double), intent(in out) :: remainDel_t, currDel_t
+            integer(c_int) :: rc
+        end function
+        function ipic_solve_div_ampere_anderson(handle, del_t) bind(c, name="ipic_solve_div_ampere_anderson") result(rc)
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value :: handle
+            real(c_double), value :: del_t
+            integer(c_int) :: rc
+        end function
+        function ipic_solve_jfnk(handle, del_t) bind(c, name="ipic_solve_jfnk") result(rc)
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value :: handle
+            real(c_double), value :: del_t
             integer(c_int) :: rc
         end function
         function ipic_func_nitsol(handle, n, xcur, fcur, del_t) bind(c, name="ipic_func_nitsol") result(rc)

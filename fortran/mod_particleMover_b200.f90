@@ -22,8 +22,9 @@ module mod_particleMover
 #ifndef IPIC_SCHEME
 #define IPIC_SCHEME 0
 #endif
-    type(c_ptr), private :: ipic_h = c_null_ptr
-    logical, private :: particlesOnDevice = .false.
+    ! public: the level-2 shim (mod_nonLinSolvers_b200.f90) drives the same handle
+    type(c_ptr) :: ipic_h = c_null_ptr
+    logical :: particlesOnDevice = .false.
 
 contains
 
@@ -40,12 +41,34 @@ contains
         if (c_associated(ipic_h)) return
         call ipic_check(ipic_create(ipic_h, IPIC_SCHEME, NumberXNodes, world%grid, world%dx_dl, world%boundaryConditions, &
             merge(1_c_int, 0_c_int, world%gridSmoothBool), 0_c_int), 'ipic_create')
-        ! voltages are carried by phi / phi_f (NGP) and set again by the host through setRFVoltage; 0 here
-        call ipic_check(ipic_init_solver(ipic_h, 0.0_c_double, 0.0_c_double, solver%RF_rad_frequency / (2.0d0 * pi), 0.0_c_double), 'ipic_init_solver')
+        ! wall voltages as the constructor received them (NGP mod_potentialSolver.f90:54-84, CIC :56-90): a Dirichlet wall keeps its
+        ! voltage in phi (NGP) / boundPhi (CIC), the RF wall in RF_half_amplitude
+        call ipic_check(ipic_init_solver(ipic_h, ipic_wall_voltage(solver, world, 1), ipic_wall_voltage(solver, world, 2), &
+            solver%RF_rad_frequency / (2.0d0 * pi), 0.0_c_double), 'ipic_init_solver')
         do j = 1, size(particleList)
             call ipic_check(ipic_add_species(ipic_h, particleList(j)%mass, particleList(j)%q, particleList(j)%w_p, sp), 'ipic_add_species')
         end do
     end subroutine ipic_attach
+
+    function ipic_wall_voltage(solver, world, side) result(v)
+        class(potentialSolver), intent(in) :: solver
+        type(Domain), intent(in) :: world
+        integer, intent(in) :: side
+        real(c_double) :: v
+        integer :: bc
+        bc = world%boundaryConditions(merge(1, size(world%boundaryConditions), side == 1))
+        if (bc == 4) then
+            v = solver%RF_half_amplitude
+        else if (bc == 1) then
+#if IPIC_SCHEME == 1
+            v = solver%boundPhi(side)
+#else
+            v = solver%phi(merge(1, NumberXNodes, side == 1))
+#endif
+        else
+            v = 0.0d0
+        end if
+    end function ipic_wall_voltage
 
     subroutine ipic_push_state(solver, particleList)
         class(potentialSolver), intent(in) :: solver
@@ -53,6 +76,10 @@ contains
         integer :: j
         call ipic_check(ipic_set_field(ipic_h, IPIC_F_PHI, solver%phi, NumberXNodes), 'set phi')
         call ipic_check(ipic_set_field(ipic_h, IPIC_F_PHI_F, solver%phi_f, NumberXNodes), 'set phi_f')
+#if IPIC_SCHEME == 1
+        ! CIC keeps its walls outside phi; the host's setRFVoltage / resetVoltage have just updated them
+        call ipic_check(ipic_set_cic_walls(ipic_h, solver%boundPhi, solver%RF_voltage, solver%sourceTermVals), 'ipic_set_cic_walls')
+#endif
         if (.not. particlesOnDevice) then
             do j = 1, size(particleList)
                 call ipic_check(ipic_set_weight(ipic_h, j - 1, particleList(j)%w_p), 'ipic_set_weight')
@@ -75,18 +102,13 @@ contains
         call ipic_check(ipic_get_field(ipic_h, IPIC_F_EFIELD, solver%EField, NumberXHalfNodes), 'get EField')
     end subroutine depositJ
 
-    subroutine moveParticles(solver, particleList, world, del_t)
-        class(potentialSolver), intent(in out) :: solver
-        type(Domain), intent(in) :: world
+    subroutine ipic_pull_particles(particleList)
+        ! the mover's outputs (mod_particleMover.f90:162-270): moved and compacted phaseSpace, N_p, loss sums, reflux bookkeeping, counters
         type(Particle), intent(in out) :: particleList(:)
-        real(real64), intent(in) :: del_t
         type(ipic_move_stats) :: st
         integer :: j, k, iThread
         integer(c_int64_t) :: nRef, slabEnd
         integer(c_int32_t), allocatable :: refGlobal(:)
-        call ipic_attach(solver, particleList, world)
-        call ipic_push_state(solver, particleList)
-        call ipic_check(ipic_move_particles(ipic_h, del_t), 'ipic_move_particles')
         do j = 1, size(particleList)
             call ipic_check(ipic_download_particles(ipic_h, j - 1, particleList(j)%phaseSpace, particleList(j)%N_p, numThread, &
                 particleList(j)%finalIdx), 'ipic_download_particles')
@@ -126,6 +148,17 @@ contains
             particleList(j)%accumEnergyLoss = particleList(j)%accumEnergyLoss + st%energyLoss
             particleList(j)%accumWallLoss = particleList(j)%accumWallLoss + int(st%wallLoss, int32)
         end do
+    end subroutine ipic_pull_particles
+
+    subroutine moveParticles(solver, particleList, world, del_t)
+        class(potentialSolver), intent(in out) :: solver
+        type(Domain), intent(in) :: world
+        type(Particle), intent(in out) :: particleList(:)
+        real(real64), intent(in) :: del_t
+        call ipic_attach(solver, particleList, world)
+        call ipic_push_state(solver, particleList)
+        call ipic_check(ipic_move_particles(ipic_h, del_t), 'ipic_move_particles')
+        call ipic_pull_particles(particleList)
         particlesOnDevice = .false.     ! collisions / injection run on the host before the next step
     end subroutine moveParticles
 

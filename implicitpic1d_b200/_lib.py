@@ -74,6 +74,7 @@ SIGNATURES = {
     "ipic_solve_tridiag_ampere": (_i, [_p, _d]),
     "ipic_set_rf_voltage": (_i, [_p, _d]),
     "ipic_reset_voltage": (_i, [_p]),
+    "ipic_set_cic_walls": (_i, [_p, _dp, _d, _dp]),
     "ipic_deposit_J": (_i, [_p, _d]),
     "ipic_move_particles": (_i, [_p, _d]),
     "ipic_get_move_stats": (_i, [_p, _i32, C.POINTER(MoveStats)]),

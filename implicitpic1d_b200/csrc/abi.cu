@@ -592,6 +592,17 @@ int ipic_get_ref_record(ipic_handle h, int32_t sp, int32_t *idx, int64_t cap, in
     }
     return IPIC_OK;
 }
+// CIC carries its walls outside phi: boundPhi(2), RF_voltage, sourceTermVals(2) (CIC mod_potentialSolver.f90:19,69-85,458-478).  A host that
+// keeps owning the solver object (level-1 integration) pushes them with phi / phi_f before depositJ / moveParticles.
+int ipic_set_cic_walls(ipic_handle h, const double *boundPhi2, double RF_voltage, const double *sourceTermVals2) {
+    CTX(h); NEED_SOLVER;
+    if (c->scheme != IPIC_SCHEME_CIC) { set_error("ipic_set_cic_walls: CIC scheme only"); return IPIC_ERR_ARG; }
+    if (!boundPhi2 || !sourceTermVals2) return IPIC_ERR_ARG;
+    c->boundPhi[0] = boundPhi2[0]; c->boundPhi[1] = boundPhi2[1];
+    c->sourceTermVals[0] = sourceTermVals2[0]; c->sourceTermVals[1] = sourceTermVals2[1];
+    c->RF_voltage = RF_voltage;
+    return IPIC_OK;
+}
 int ipic_get_deposit_substeps(ipic_handle h, int32_t sp, int64_t *n) { CTX(h); SPECIES(sp); *n = c->sp[sp].depositSubsteps; return IPIC_OK; }
 
 // initializeSolver  mod_nonLinSolvers.f90:41-81

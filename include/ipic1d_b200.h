@@ -127,6 +127,9 @@ int ipic_make_half_time_efield(ipic_handle h);
 int ipic_solve_tridiag_ampere(ipic_handle h, double del_t);
 int ipic_set_rf_voltage(ipic_handle h, double timeFuture);
 int ipic_reset_voltage(ipic_handle h);
+/* CIC only: the wall state the reference keeps outside phi -- boundPhi(2), RF_voltage, sourceTermVals(2)
+ * (CIC mod_potentialSolver.f90:19,69-85; written by setRFVoltage :458-470 and resetVoltage :472-478) -- for a host that owns the solver object */
+int ipic_set_cic_walls(ipic_handle h, const double *boundPhi2, double RF_voltage, const double *sourceTermVals2);
 int ipic_deposit_J(ipic_handle h, double del_t);
 int ipic_move_particles(ipic_handle h, double del_t);
 

@@ -456,3 +456,30 @@ def test_empty_and_ragged_slabs(name):
     o.depositRho()
     assert relerr(solver.rho, o.get("rho")) < TOL_GRID
     solver.close()
+
+
+def test_cic_walls_pushed_by_the_host():
+    """level-1 integration of the CIC tree: the host's setRFVoltage / resetVoltage own boundPhi, RF_voltage and sourceTermVals
+    (CIC mod_potentialSolver.f90:458-478); ipic_set_cic_walls carries them to the device before depositJ"""
+    import ctypes as C
+    d = DECKS["cic_rf"]
+    o = build_oracle(d)
+    world, solver, plist = build_cuda_from_oracle(d, o, tridiag_mode=_lib.TRIDIAG_THOMAS)
+    del_t = deck_del_t(d)
+    t_future = 0.3 / d["rf"]                                       # well into the RF period: walls differ from their t = 0 values
+    o.setRFVoltage(t_future)
+    o.resetVoltage()
+    o.setRFVoltage(t_future + del_t)
+    wl = o.cic_walls()
+    assert abs(wl["RF_voltage"]) > 1.0 and abs(wl["boundPhi"]).max() > 1.0
+    solver.phi, solver.phi_f, solver.rho = o.get("phi"), o.get("phi_f"), o.get("rho")
+    bp, stv = np.ascontiguousarray(wl["boundPhi"]), np.ascontiguousarray(wl["sourceTermVals"])
+    _lib.check(_lib.load().ipic_set_cic_walls(solver._h, bp.ctypes.data_as(_lib._dp), float(wl["RF_voltage"]), stv.ctypes.data_as(_lib._dp)))
+    o.makeHalfTimeEField(); solver.makeHalfTimeEField()
+    assert relerr(solver.EField, o.get("EField")) < 1e-13
+    o.depositJ(del_t)
+    ip.depositJ(solver, plist, world, del_t)
+    assert relerr(solver.J, o.get("J")) < TOL_GRID
+    o.solve_tridiag_Ampere(del_t); solver.solve_tridiag_Ampere(world, del_t)
+    assert relerr(solver.phi_f, o.get("phi_f")) < 1e-10
+    solver.close()
