@@ -352,6 +352,12 @@ int ipic_create(ipic_handle *out, int scheme, int32_t Nx, const double *grid, co
     IPIC_CUDA(cudaMalloc(&c->d_bc, (NM + 2) * sizeof(int))); IPIC_CUDA(cudaMemset(c->d_bc, 0, (NM + 2) * sizeof(int)));
     IPIC_CUDA(cudaMemcpy(c->d_grid, grid, Nx * sizeof(double), cudaMemcpyHostToDevice));
     IPIC_CUDA(cudaMemcpy(c->d_dx, dx_dl, c->ndx * sizeof(double), cudaMemcpyHostToDevice));
+    {   // 0.5 / dx_dl: a constant of the grid, so the push-table builder does not divide for it before every sweep
+        std::vector<double> hv(NM, 0.0);
+        for (int i = 0; i < c->ndx; ++i) hv[i] = 0.5 / dx_dl[i];
+        RC(dalloc(&c->d_hinv, NM));
+        IPIC_CUDA(cudaMemcpy(c->d_hinv, hv.data(), c->ndx * sizeof(double), cudaMemcpyHostToDevice));
+    }
     IPIC_CUDA(cudaMemcpy(c->d_bc + 1, bc, c->nbc * sizeof(int), cudaMemcpyHostToDevice));   // d_bc is indexed 1-based (element 0 is padding)
     RC(dalloc(&c->d_phi, NM)); RC(dalloc(&c->d_phi_f, NM)); RC(dalloc(&c->d_rho, NM)); RC(dalloc(&c->d_J, NM)); RC(dalloc(&c->d_E, NM));
     RC(dalloc(&c->d_Ef, NM)); RC(dalloc(&c->d_Eh, NM));
@@ -382,7 +388,7 @@ int ipic_destroy(ipic_handle h) {
     delete static_cast<nitsol::Solver *>(c->nitsol_state);
     collisions_free(*c);
     for (auto &s : c->sp) { if (s.l) cudaFree(s.l); if (s.l2) cudaFree(s.l2); if (s.refl) cudaFree(s.refl); if (s.refList) cudaFree(s.refList); }
-    double *dp[] = {c->d_grid, c->d_dx, c->d_phi, c->d_phi_f, c->d_rho, c->d_J, c->d_E, c->d_a, c->d_b, c->d_c, c->d_cp, c->d_m, c->d_pcr, c->d_work,
+    double *dp[] = {c->d_grid, c->d_dx, c->d_hinv, c->d_phi, c->d_phi_f, c->d_rho, c->d_J, c->d_E, c->d_a, c->d_b, c->d_c, c->d_cp, c->d_m, c->d_pcr, c->d_work,
                     c->d_rho_i, c->d_scal, c->d_phi_k, c->d_res_k, c->d_norms, c->d_loss, c->d_Ef, c->d_Eh};
     for (double *p : dp) if (p) cudaFree(p);
     if (c->d_bc) cudaFree(c->d_bc);

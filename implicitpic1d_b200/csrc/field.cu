@@ -38,7 +38,7 @@ enum : unsigned {
 struct FieldArgs {
     int scheme, Nx, Nh, smooth, nsp, tridiag_mode, pcr_levels, acc_stride, tab_cells, acc_reps;
     unsigned long long acc_rep_stride;
-    const double *grid, *dx;
+    const double *grid, *dx, *hinv;     // hinv = 0.5 / dx_dl
     const int *bc;
     double *phi, *phi_f, *rho, *J, *E, *a, *b, *c, *cp, *m, *pcr, *work, *scal, *rho_i;
     unsigned long long *acc;
@@ -223,8 +223,20 @@ __device__ void dev_tridiag(const FieldArgs &A, double *d, double *tmp) {
     __syncthreads();
 }
 
+#ifdef IPIC_FIELD_PHASES
+// profiling aid (scripts/field_phases.sh): thread 0 stamps the clock at the end of every phase; run_field prints the differences
+__device__ long long g_field_phase[16];
+#define PH(k) do { if (threadIdx.x == 0) g_field_phase[k] = clock64(); } while (0)
+#else
+#define PH(k) do { } while (0)
+#endif
 __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsigned ops) {
     extern __shared__ __align__(16) double sm[];
+#ifdef IPIC_FIELD_PHASES
+    if (threadIdx.x < 16) g_field_phase[threadIdx.x] = 0;
+    __syncthreads();
+#endif
+    PH(0);
     const int Nx = A.Nx, Nh = A.Nh;
     const int NM = max(Nx, Nh) + 2;
     double *s0 = sm, *s1 = sm + NM;   // two shared work vectors
@@ -337,6 +349,7 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
     if (ops & OP_FINALIZE_J) {
         dev_collect(A, s0, Nh, A.scheme == 0, reinterpret_cast<long long *>(s1));
         __syncthreads();
+        PH(1);
         if (A.scheme == 1 && threadIdx.x == 0) {
 #define W(i) s0[(i)-1]
             switch (BC(1)) {
@@ -360,6 +373,7 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
             for (int i = threadIdx.x; i < Nh; i += FT) A.J[i] = s0[i] / A.del_t;
         }
         __syncthreads();
+        PH(2);
     }
 
     // ---------------- solve_tridiag_Ampere: NGP :288-330 ; CIC :272-301 ----------------
@@ -382,9 +396,11 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
             s0[i - 1] = d;
         }
         __syncthreads();
+        PH(3);
         dev_tridiag(A, s0, s1);
         for (int i = threadIdx.x; i < Nx; i += FT) A.phi_f[i] = s0[i];
         __syncthreads();
+        PH(4);
     }
 
 
@@ -457,6 +473,7 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
         const double nrm = sqrt(block_sum(part));
         if (threadIdx.x == 0) { A.norms[index - 1] = nrm; A.scal[0] = nrm; }
         __syncthreads();
+        PH(5);
     }
     if (ops & OP_AND_MIX) {
         const int i = A.and_i, m = A.and_m;
@@ -466,59 +483,73 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
         double *An = s0;                 // m_k x m_k column-major
         double *bn = s0 + 32 * 32;       // m_k
         double *alpha = bn + 64;         // m_k + 1
+        int *col = reinterpret_cast<int *>(alpha + 64);   // history column of fitMat column j (the MODULO of :139 evaluated once)
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const int npairs = m_k * m_k + m_k;
+        if (threadIdx.x <= m_k) col[threadIdx.x] = fmodulo(i - m_k + (int)threadIdx.x, M1) + 1;
+        __syncthreads();
+        // MATMUL(A^T, A) is symmetric and each entry is the same sum of the same products either way round, so only j <= k is
+        // computed (one warp per entry, lanes stride the rows, shuffle tree) and mirrored: bit-identical to computing all m_k^2
+        const int ntri = m_k * (m_k + 1) / 2, npairs = ntri + m_k;
         for (int p = warp; p < npairs; p += FT / 32) {
             int j, k;
-            if (p < m_k * m_k) { j = p % m_k; k = p / m_k; } else { j = p - m_k * m_k; k = -1; }
-            const int cj = fmodulo(i - m_k + j, M1) + 1;
-            const int ck = (k >= 0) ? fmodulo(i - m_k + k, M1) + 1 : 0;
+            if (p < ntri) { k = 0; int q = p; while (q > k) { q -= k + 1; ++k; } j = q; }     // p = k (k + 1) / 2 + j, j <= k
+            else { j = p - ntri; k = -1; }
+            const double *Ri = A.res_k + (size_t)(index - 1) * NU, *Rj = A.res_k + (size_t)(col[j] - 1) * NU;
+            const double *Rk = (k >= 0) ? A.res_k + (size_t)(col[k] - 1) * NU : Ri;
             double acc = 0.0;
-            for (int r = 1 + lane; r <= NU; r += 32) {
-                const double ri = RK(r, index);
-                const double fj = ri - RK(r, cj);
-                const double fk = (k >= 0) ? (ri - RK(r, ck)) : ri;
-                acc += fj * fk;
+            if (k >= 0) {
+#pragma unroll 8
+                for (int r = lane; r < NU; r += 32) { const double ri = Ri[r]; acc += (ri - Rj[r]) * (ri - Rk[r]); }
+            } else {
+#pragma unroll 8
+                for (int r = lane; r < NU; r += 32) { const double ri = Ri[r]; acc += (ri - Rj[r]) * ri; }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-            if (lane == 0) { if (k >= 0) An[j + m_k * k] = acc; else bn[j] = acc; }
+            if (lane == 0) { if (k >= 0) { An[j + m_k * k] = acc; An[k + m_k * j] = acc; } else bn[j] = acc; }
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            // solveGaussElimination, no pivoting (mod_BasicFunctions.f90:218-254)
+        PH(6);
+        if (warp == 0) {
+            // solveGaussElimination, no pivoting (mod_BasicFunctions.f90:218-254).  The elimination runs on one warp, lane = row: every
+            // entry sees the reference's operations in the reference's order (its updates are independent across rows and columns
+            // within a pivot step); the two substitutions stay sequential.
             const int n = m_k;
 #define AA(r, c) An[((r)-1) + n * ((c)-1)]
+            const int r = lane + 1;
             for (int k = 1; k <= n - 1; ++k) {
                 const double k1 = AA(k, k);
-                for (int r = k + 1; r <= n; ++r) AA(r, k) = AA(r, k) / k1;
-                for (int j = k + 1; j <= n; ++j) {
-                    const double k2 = AA(k, j);
-                    for (int r = k + 1; r <= n; ++r) AA(r, j) = AA(r, j) - AA(r, k) * k2;
+                if (r > k && r <= n) AA(r, k) = AA(r, k) / k1;
+                __syncwarp();
+                if (r > k && r <= n) {
+                    const double ark = AA(r, k);
+                    for (int j = k + 1; j <= n; ++j) AA(r, j) = AA(r, j) - ark * AA(k, j);
                 }
+                __syncwarp();
             }
-            for (int r = 1; r <= n; ++r) for (int j = 1; j <= r - 1; ++j) bn[r - 1] = bn[r - 1] - AA(r, j) * bn[j - 1];
-            for (int r = n; r >= 1; --r) {
-                for (int j = r + 1; j <= n; ++j) bn[r - 1] = bn[r - 1] - AA(r, j) * bn[j - 1];
-                bn[r - 1] = bn[r - 1] / AA(r, r);
+            if (lane == 0) {
+                for (int rr = 1; rr <= n; ++rr) for (int j = 1; j <= rr - 1; ++j) bn[rr - 1] = bn[rr - 1] - AA(rr, j) * bn[j - 1];
+                for (int rr = n; rr >= 1; --rr) {
+                    for (int j = rr + 1; j <= n; ++j) bn[rr - 1] = bn[rr - 1] - AA(rr, j) * bn[j - 1];
+                    bn[rr - 1] = bn[rr - 1] / AA(rr, rr);
+                }
+                double sa = 0.0;
+                for (int j = 0; j < n; ++j) { alpha[j] = bn[j]; sa += bn[j]; }
+                alpha[n] = 1.0 - sa;
             }
 #undef AA
-            double sa = 0.0;
-            for (int j = 0; j < n; ++j) { alpha[j] = bn[j]; sa += bn[j]; }
-            alpha[n] = 1.0 - sa;
         }
         __syncthreads();
-        const int cn = fmodulo(i + 1, M1) + 1, c0 = fmodulo(i - m_k, M1) + 1;
+        PH(7);
+        const int cn = fmodulo(i + 1, M1) + 1;
         for (int r = 1 + threadIdx.x; r <= NU; r += FT) {
-            double x = alpha[0] * (A.beta * RK(r, c0) + PK(r, c0));
-            for (int j = 1; j <= m_k; ++j) {
-                const int cj = fmodulo(i - m_k + j, M1) + 1;
-                x = x + alpha[j] * (A.beta * RK(r, cj) + PK(r, cj));
-            }
+            double x = alpha[0] * (A.beta * RK(r, col[0]) + PK(r, col[0]));
+            for (int j = 1; j <= m_k; ++j) x = x + alpha[j] * (A.beta * RK(r, col[j]) + PK(r, col[j]));
             PK(r, cn) = x;
             UNK(r) = x;
         }
         __syncthreads();
+        PH(8);
     }
 #undef PK
 #undef RK
@@ -548,7 +579,7 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
                 for (int cI = 1 + threadIdx.x; cI <= Nh; cI += FT) {
                     const double a = A.qm[s] * EF(cI), dx = DX(cI);
                     CellTabNGP t;
-                    t.a = a; t.hinv = 0.5 / dx; t.two_a_dx = 2.0 * a * dx; t.inv_a = 1.0 / a;
+                    t.a = a; t.hinv = A.hinv[cI - 1]; t.two_a_dx = 2.0 * a * dx; t.inv_a = 1.0 / a;
                     T[cI] = t;
                     // wall cells are not transited by the lean loop: NaN makes a lane that reaches one fail its next time test
                     TT[cI] = (cI == 1 || cI == Nh) ? make_double2(__longlong_as_double(0x7ff8000000000000ll), 0.0) : make_double2(t.two_a_dx, t.inv_a);
@@ -599,6 +630,7 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
     }
 
 
+    PH(9);
     // EField_half = 0.5 (EField + EField_f) (NGP_Periodic/src/mod_particleMover.f90:72) + push tables
     if (ops & OP_P_HALF_E) {
         for (int i = threadIdx.x; i < Nh; i += FT) A.Eh[i] = 0.5 * (A.E[i] + A.Ef[i]);
@@ -609,7 +641,7 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
             for (int cI = 1 + threadIdx.x; cI <= Nh; cI += FT) {
                 const double a = A.qm[s] * A.Eh[cI - 1], dx = DX(cI);
                 CellTabNGP t;
-                t.a = a; t.hinv = 0.5 / dx; t.two_a_dx = 2.0 * a * dx; t.inv_a = 1.0 / a;
+                t.a = a; t.hinv = A.hinv[cI - 1]; t.two_a_dx = 2.0 * a * dx; t.inv_a = 1.0 / a;
                 T[cI] = t;
                 TT[cI] = (cI == 1 || cI == Nh) ? make_double2(__longlong_as_double(0x7ff8000000000000ll), 0.0) : make_double2(t.two_a_dx, t.inv_a);
             }
@@ -764,7 +796,7 @@ static FieldArgs make_args(Ctx &c) {
     A.acc_stride = 2 * (std::max(c.Nx, c.Nh) + 2);
     A.acc_reps = std::max(1, c.acc_reps); A.acc_rep_stride = c.acc_rep_stride;
     A.tab_cells = ((c.scheme == IPIC_SCHEME_CIC) ? c.Nx : c.Nh) + 2;
-    A.grid = c.d_grid; A.dx = c.d_dx; A.bc = c.d_bc;
+    A.grid = c.d_grid; A.dx = c.d_dx; A.hinv = c.d_hinv; A.bc = c.d_bc;
     A.phi = c.d_phi; A.phi_f = c.d_phi_f; A.rho = c.d_rho; A.J = c.d_J; A.E = c.d_E;
     A.a = c.d_a; A.b = c.d_b; A.c = c.d_c; A.cp = c.d_cp; A.m = c.d_m; A.pcr = c.d_pcr;
     A.work = c.d_work; A.scal = c.d_scal; A.rho_i = c.d_rho_i; A.acc = c.d_acc; A.tab = c.d_tab; A.ttab = c.d_ttab;
@@ -790,6 +822,18 @@ static int run_field(Ctx &c, const FieldArgs &A, unsigned ops) {
     }
     c.launches += 1; k_field<<<1, FT, smem, c.stream>>>(A, ops);
     IPIC_CUDA(cudaGetLastError());
+#ifdef IPIC_FIELD_PHASES
+    {
+        long long h[16];
+        cudaStreamSynchronize(c.stream);
+        cudaMemcpyFromSymbol(h, g_field_phase, sizeof h);
+        static const char *nm[10] = {"start", "collect", "smooth+J", "rhs", "tridiag", "resid+norm", "normal-eq", "gauss", "mix", "halfE+tables"};
+        fprintf(stderr, "k_field ops=%05x:", ops);
+        long long prev = h[0];
+        for (int k = 1; k < 10; ++k) if (h[k]) { fprintf(stderr, " %s %.1fus", nm[k], (double)(h[k] - prev) / 1965.0); prev = h[k]; }
+        fprintf(stderr, "\n");
+    }
+#endif
     return IPIC_OK;
 }
 

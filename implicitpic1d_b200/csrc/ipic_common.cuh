@@ -110,7 +110,7 @@ struct Ctx {
     cudaStream_t stream = nullptr, own_stream = nullptr;
     long long launches = 0;                                       // kernels launched by this context
     // device tables
-    double *d_grid = nullptr, *d_dx = nullptr;
+    double *d_grid = nullptr, *d_dx = nullptr, *d_hinv = nullptr;   // d_hinv = 0.5 / dx_dl
     int *d_bc = nullptr;                                          // boundaryConditions, 1-based (d_bc[k] = bc(k))
     std::vector<double> h_grid, h_dx;
     std::vector<int> h_bc;
