@@ -652,20 +652,29 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
                 }
             }
             bool cont = false;
-            if (valid) {
+            if (SCHEME != 1) {
+                // Branch-free: the whole first (and for most particles only) sub-step in straight-line code.  An invalid lane reads table
+                // entry 0 (zeros) and is masked out of every effect.  Sorted input puts a sub-tile inside one or two cells, so the deposit
+                // is two warp-uniform cases on the register accumulators before the general per-lane routine.
+                const int cellc = valid ? cell : 0;
+                const double2 t0 = __ldg(reinterpret_cast<const double2 *>(reinterpret_cast<const CellTabNGP *>(A.tab) + cellc));
+                const double lc = (SCHEME == 2) ? (double)cell : 0.0;
+                const double lw = l - lc;
+                const double v_f = fma(t0.x, del_t, v);
+                const double l_fw = fma((v + v_f) * del_t, t0.y, lw);
+                const bool done = valid && ((SCHEME == 2) ? ((int)(l_fw + 1.0) == 1) : ((int)l_fw == cell)) && ((v > 0.0) == (v_f > 0.0));
+                cont = valid && !done;
+                if (!MOVE) {
+                    const unsigned long long q = done ? (unsigned long long)fx_from_double(l_fw - lw) : 0ull;
+                    const int k = cell - D.base;
+                    if (__all_sync(FULL, !done || k == 0)) D.r0 += q;
+                    else if (__all_sync(FULL, !done || (unsigned)k < 2u)) { D.r0 += (k == 0) ? q : 0ull; D.r1 += (k == 1) ? q : 0ull; }
+                    else if (done) deposit_add(W, D, lane, gacc, cell, (long long)q);
+                } else if (done) { A.l_out[gi] = l_fw + lc; A.vx_out[gi] = v_f; }
+                nsub += done ? 1u : 0u;
+            } else if (valid) {
                 bool done;
-                if (SCHEME != 1) {
-                    const double2 t0 = __ldg(reinterpret_cast<const double2 *>(reinterpret_cast<const CellTabNGP *>(A.tab) + cell));
-                    const double lc = (SCHEME == 2) ? (double)cell : 0.0;
-                    const double lw = l - lc;
-                    const double v_f = fma(t0.x, del_t, v);
-                    const double l_fw = fma((v + v_f) * del_t, t0.y, lw);
-                    done = ((SCHEME == 2) ? ((int)(l_fw + 1.0) == 1) : ((int)l_fw == cell)) && ((v > 0.0) == (v_f > 0.0));
-                    if (done) {
-                        if (!MOVE) deposit_add(W, D, lane, gacc, cell, fx_from_double(l_fw - lw));
-                        else { A.l_out[gi] = l_fw + lc; A.vx_out[gi] = v_f; }
-                    }
-                } else {
+                {
                     const double2 *tp2 = reinterpret_cast<const double2 *>(reinterpret_cast<const CellTabCIC *>(A.tab) + cell);
                     const double2 t0 = __ldg(tp2), t1 = __ldg(tp2 + 1);
                     const double cap = __ldg(reinterpret_cast<const double *>(tp2 + 2));
