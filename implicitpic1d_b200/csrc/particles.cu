@@ -662,7 +662,19 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
                 const double lw = l - lc;
                 const double v_f = fma(t0.x, del_t, v);
                 const double l_fw = fma((v + v_f) * del_t, t0.y, lw);
-                const bool done = valid && ((SCHEME == 2) ? ((int)(l_fw + 1.0) == 1) : ((int)l_fw == cell)) && ((v > 0.0) == (v_f > 0.0));
+                const bool inCell = (SCHEME == 2) ? ((int)(l_fw + 1.0) == 1) : ((int)l_fw == cell);
+                const bool eqSign = (v > 0.0) == (v_f > 0.0);
+                bool done = valid && inCell && eqSign;
+                // A particle that turns round inside its cell (slow ions in any field, electrons near their turning point) is finished too
+                // unless it can still reach the face ahead first (mod_particleMover.f90:39-47: FutureAtBoundaryBool = diff_PE > -v_i_sqr;
+                // otherwise, being in the cell, it keeps the unconstrained l_f, v_f).  Same operands as the general sub-step below.
+                const bool turn = valid && inCell && !eqSign;
+                if (__any_sync(FULL, turn)) {
+                    const double two_a_dx = __ldg(reinterpret_cast<const double *>(reinterpret_cast<const CellTabNGP *>(A.tab) + cellc) + 2);
+                    const int lb = cell + ((v > 0.0) ? 1 : 0);
+                    const double diff_PE = __dmul_rn(two_a_dx, ((double)lb - lc) - lw);
+                    done = done || (turn && !(diff_PE > -__dmul_rn(v, v)));
+                }
                 cont = valid && !done;
                 if (!MOVE) {
                     const unsigned long long q = done ? (unsigned long long)fx_from_double(l_fw - lw) : 0ull;
