@@ -1,0 +1,12 @@
+#!/bin/bash
+# usage (GPU box): scripts/variant_bench.sh "<EXTRA flags variant 1>" "<variant 2>" ...  -- rebuilds the push kernels per variant, runs the bench
+mkdir -p gpurun_out
+for v in "$@"; do
+  touch implicitpic1d_b200/csrc/particles.cu
+  make -s -C implicitpic1d_b200/csrc EXTRA="$v" 2>&1 | grep -E "error"
+  python bench.py --steps 6 --warmup 3 --no-e2e --no-cpu 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('variant [%s]: ms/step %.1f value %.3e dep %s' % (sys.argv[1], d['ms_per_step'], d['value'], d['roofline']['per_species_ms']))" "$v" | tee -a gpurun_out/variants.log
+done
+touch implicitpic1d_b200/csrc/particles.cu; make -s -C implicitpic1d_b200/csrc 2>&1 | grep -E "error"
