@@ -304,9 +304,13 @@ def run_cuda_arm(args, w):
     state = dict(t=0.0, remain=del_t, curr=del_t, nstep=0)
 
     def one_step():
-        if args.sort_every > 0 and state["nstep"] > 0 and state["nstep"] % args.sort_every == 0:
-            for p in plist:
-                _lib.check(L.ipic_sort_particles(solver._h, p._index))
+        if args.sort_every > 0 and state["nstep"] > 0:
+            # periodic cell sort: electrons cross a cell or two per step and lose their order within a few steps;
+            # ions move ~1e-3 cells per step and keep it for hundreds, so they are re-sorted 8 times less often
+            for k, p in enumerate(plist):
+                period = args.sort_every * (1 if k == 0 else args.sort_ion_factor)
+                if state["nstep"] % period == 0:
+                    _lib.check(L.ipic_sort_particles(solver._h, p._index))
         try:
             state["remain"], state["curr"] = ip.solvePotential(solver, plist, world, del_t, state["remain"], state["curr"], state["t"])
         except _lib.IpicError:
@@ -486,7 +490,7 @@ def run_cuda_arm(args, w):
                 "config": {"workload": w["name"], "particles_per_gpu": 2 * n_sp, "particles_total": 2 * n_sp * world_size, "cells": world.NumberXHalfNodes,
                            "del_t": del_t, "residual_evaluations_per_step": sum(iters) / len(iters),
                            "substeps_per_particle_per_sweep": substeps / max(particle_sweeps, 1),
-                           "sort_every_steps": args.sort_every, "tridiag": "thomas" if args.thomas else "pcr",
+                           "sort_every_steps": args.sort_every, "sort_every_steps_ions": args.sort_every * args.sort_ion_factor, "tridiag": "thomas" if args.thomas else "pcr",
                            "l2": "inputs larger than L2: %.2f GB particle stream per sweep per GPU vs 126 MB L2" % (32.0 * n_sp / 1e9),
                            "parallelism": "particles sharded over %d GPU(s); int64 fixed-point J grid all-reduced (NCCL) per residual evaluation; "
                                           "field solve replicated" % world_size},
@@ -510,7 +514,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS), help="c5 (default, the bench line) | c1 | c2 | c3 | c4: the other BASELINE configs")
     ap.add_argument("--particles-per-species", type=int, default=0, help="override particles per species per GPU (debug)")
-    ap.add_argument("--sort-every", type=int, default=5, help="cell-sort the particles every this many steps inside the timed region (0 = never)")
+    ap.add_argument("--sort-every", type=int, default=None, help="cell-sort the electrons every this many steps inside the timed region (0 = never); default: the workload's own period -- 1 where a step holds tens of sweeps (c1, c3, c5), 5 where it holds two to four (c2, c4)")
+    ap.add_argument("--sort-ion-factor", type=int, default=8, help="the ion species is sorted every sort-every x this many steps")
     ap.add_argument("--thomas", action="store_true", help="sequential Thomas solve (bit-parity mode) instead of PCR")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -523,6 +528,8 @@ def main():
     if args.warmup < 3 and args.impl == "b200":
         print("bench.py: note: fewer than 3 warm-up steps requested", file=sys.stderr)
     w = WORKLOADS[args.workload]
+    if args.sort_every is None:
+        args.sort_every = 5 if args.workload in ("c2", "c4") else 1
     if args.traffic_bytes_per_particle is None:
         # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json), if recorded
         try:
