@@ -96,6 +96,7 @@ SIGNATURES = {
     "ipic_get_charge_continuity_error": (_i, [_p, _dp, _d, _dp]),
     "ipic_get_total_KE": (_i, [_p, _i32, _dp]),
     "ipic_get_total_momentum": (_i, [_p, _i32, _dp]),
+    "ipic_local_temperature": (_i, [_p, _i32, _i32, _dp]),
     "ipic_add_target_particle": (_i, [_p, _d, _d, _d, _ip]),
     "ipic_null_collision_create": (_i, [_p, _i32, _i32, _d, _d, _d, _dp, _dp, _dp, _ip, _ip, _ip, _ip, C.c_uint64, _ip]),
     "ipic_generate_collision": (_i, [_p, _i32, _d]),

@@ -721,6 +721,17 @@ int ipic_get_total_KE(ipic_handle h, int32_t sp, double *out) {
     *out = m4[0] * c->sp[sp].mass * 0.5 * c->sp[sp].w_p;   // mod_particle.f90:228
     return IPIC_OK;
 }
+// writeLocalTemperature (mod_particle.f90:251-283): EHist(j) = SUM(v^2) mass / count / 3 / e per cell j = INT(l) < N_x, 0 where the cell is empty
+int ipic_local_temperature(ipic_handle h, int32_t sp, int32_t numCells, double *EHist) {
+    CTX(h); SPECIES(sp);
+    if (!EHist) return IPIC_ERR_ARG;
+    std::vector<double> sm((size_t)std::max(numCells, 1));
+    std::vector<long long> cn((size_t)std::max(numCells, 1));
+    RC(local_temperature(*c, sp, numCells, sm.data(), cn.data()));
+    constexpr double e_charge = 1.602176634e-19;     // constants.f90:12
+    for (int j = 0; j < numCells; ++j) EHist[j] = cn[j] > 0 ? sm[j] * c->sp[sp].mass / (double)cn[j] / 3.0 / e_charge : 0.0;
+    return IPIC_OK;
+}
 int ipic_get_total_momentum(ipic_handle h, int32_t sp, double *out3) {
     CTX(h); SPECIES(sp);
     double m4[4]; RC(particle_moments(*c, sp, m4));

@@ -197,6 +197,7 @@ int launch_move(Ctx &c, int sp, double del_t);
 int launch_deposit_pair(Ctx &c, int a, int b, double del_t);
 int launch_deposit_rho(Ctx &c, int sp);
 int compact_species(Ctx &c, int sp);
+int local_temperature(Ctx &c, int sp, int numCells, double *sumV2_host, long long *count_host);
 int fold_acc(Ctx &c, size_t count);                    // CTA copies of the deposition grids -> copy 0
 int collect_reflected(Ctx &c, int sp);                 // flagged pre-compaction indices -> refList
 int map_reflected(Ctx &c, int sp, bool compacted);     // -> post-compaction indices (absorbed ones dropped)

@@ -1047,6 +1047,50 @@ int particle_moments(Ctx &c, int sp, double out4[4]) {
     return IPIC_OK;
 }
 
+// writeLocalTemperature (mod_particle.f90:251-283): per cell INT(l) < N_x, the sum of v^2 and the particle count.  Sorted input puts a
+// warp inside one or two cells, so the lanes of a cell are combined with a match before one atomic per (warp, cell).
+__global__ void __launch_bounds__(256) k_local_temperature(const double *__restrict__ l, const double *__restrict__ vx, const double *__restrict__ vy,
+                                                           const double *__restrict__ vz, long long n, int Nx, int numCells, double *sumV2,
+                                                           unsigned long long *count) {
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long nround = (n + 31) / 32 * 32;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+        int cell = 0;
+        double e = 0.0;
+        if (i < n) {
+            const double ll = l[i];
+            if (ll >= 0.0) {
+                const int idx = (int)ll;
+                if (idx < Nx && idx >= 1 && idx <= numCells) { cell = idx; const double a = vx[i], b = vy[i], c = vz[i]; e = a * a + b * b + c * c; }
+            }
+        }
+        const unsigned peers = __match_any_sync(FULL, cell);
+        const int leader = __ffs(peers) - 1;
+        double tot = 0.0;                                   // fixed order within the group: ascending lane
+        for (unsigned m = peers; m; m &= m - 1) tot += __shfl_sync(FULL, e, __ffs(m) - 1);
+        if (cell > 0 && lane == leader) { atomicAdd(sumV2 + cell - 1, tot); atomicAdd(count + cell - 1, (unsigned long long)__popc(peers)); }
+    }
+}
+
+int local_temperature(Ctx &c, int sp, int numCells, double *sumV2_host, long long *count_host) {
+    SpeciesDev &s = c.sp[sp];
+    if (numCells < 1 || numCells > std::max(c.Nx, c.Nh)) { set_error("local temperature: numCells out of range"); return IPIC_ERR_ARG; }
+    double *d_sum = c.d_work;                                                    // numCells doubles + numCells counters
+    unsigned long long *d_cnt = reinterpret_cast<unsigned long long *>(c.d_work + (std::max(c.Nx, c.Nh) + 2));
+    IPIC_CUDA(cudaMemsetAsync(d_sum, 0, (size_t)numCells * sizeof(double), c.stream));
+    IPIC_CUDA(cudaMemsetAsync(d_cnt, 0, (size_t)numCells * sizeof(unsigned long long), c.stream));
+    if (s.n > 0) {
+        c.launches += 1;
+        k_local_temperature<<<c.num_sms * 8, 256, 0, c.stream>>>(s.l, s.vx, s.vy, s.vz, s.n, c.Nx, numCells, d_sum, d_cnt);
+        IPIC_CUDA(cudaGetLastError());
+    }
+    IPIC_CUDA(cudaMemcpyAsync(sumV2_host, d_sum, (size_t)numCells * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    IPIC_CUDA(cudaMemcpyAsync(count_host, d_cnt, (size_t)numCells * sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
+    IPIC_CUDA(cudaStreamSynchronize(c.stream));
+    return IPIC_OK;
+}
+
 // =====================================================================================================
 // Stable compaction after moveParticles (mod_particleMover.f90:252-256: survivors keep their order).
 // Pass 1: per-tile survivor counts + wall-loss partial sums.  Pass 2: scan.  Pass 3: stable scatter.

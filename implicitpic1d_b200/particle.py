@@ -125,6 +125,25 @@ class Particle:
         _lib.check(_lib.load().ipic_get_total_momentum(self._solver._h, self._index, out.ctypes.data_as(_lib._dp)))
         return out
 
+    def localTemperature(self, numCells):
+        """the array writeLocalTemperature writes (mod_particle.f90:251-283): per cell j = INT(l) < N_x the temperature
+        SUM(v^2) mass / count / 3 / e in eV, 0 where the cell holds no particle"""
+        out = np.zeros(int(numCells))
+        _lib.check(_lib.load().ipic_local_temperature(self._solver._h, self._index, int(numCells), out.ctypes.data_as(_lib._dp)))
+        return out
+
+    def writeLocalTemperature(self, CurrentDiagStep, dirName, numCells):
+        """writeLocalTemperature (mod_particle.f90:251-283): Temperature/Temp_<name>_<step>.dat, one Fortran unformatted sequential
+        record (4-byte length, numCells float64, 4-byte length) -- what Analysis/dataSet.py reads"""
+        import os
+        EHist = self.localTemperature(numCells)
+        os.makedirs(os.path.join(dirName, "Temperature"), exist_ok=True)
+        fn = os.path.join(dirName, "Temperature", "Temp_%s_%d.dat" % (self.name, int(CurrentDiagStep)))
+        with open(fn, "wb") as f:
+            marker = np.array([EHist.nbytes], dtype="<i4").tobytes()
+            f.write(marker + EHist.astype("<f8").tobytes() + marker)
+        return EHist
+
     def refRecord(self):
         """refIdx(T), refRecordIdx(:, T) of the last moveParticles (mod_particle.f90:18-19; mod_particleMover.f90:226-231): per thread slab, the
         1-based post-compaction indices of the particles first reflected at a Neumann wall in the step, in particle order.  The slabs are

@@ -201,6 +201,9 @@ int ipic_get_energy_from_boundary(ipic_handle h, double del_t, double *out);
 int ipic_get_error_tridiag_poisson(ipic_handle h, double *out);
 int ipic_get_charge_continuity_error(ipic_handle h, const double *rho_i, double del_t, double *out);
 int ipic_get_total_KE(ipic_handle h, int32_t species, double *out);
+/* writeLocalTemperature (mod_particle.f90:251-283) without the file: EHist[j-1] = SUM(v^2) mass / count / 3 / e over the particles with
+ * INT(l) == j (j < N_x, j <= numCells), in eV; 0 for an empty cell.  The Python mirror writes the reference's unformatted record. */
+int ipic_local_temperature(ipic_handle h, int32_t species, int32_t numCells, double *EHist);
 int ipic_get_total_momentum(ipic_handle h, int32_t species, double *out3);
 
 /* ---- null-collision Monte-Carlo collisions ---------------------------------------------------------

@@ -418,6 +418,25 @@ static double getSumV2(Species &s) {
 static double getTotalKE(Species &s) { return getSumV2(s) * s.mass * 0.5 * s.w_p; }
 // getKEAve :193-204
 static double getKEAve(Species &s) { return getSumV2(s) * s.mass * 0.5 / e_c / (double)s.sumNp(); }
+// writeLocalTemperature :251-283 (the per-cell average it writes, not the file): EHist(j) = SUM(v^2) m / count / 3 / e over the particles with
+// INT(l) == j, for INT(l) < NumberXNodes; per-thread partial sums, then summed over threads in thread order
+static void localTemperature(Species &s, int Nx, int numCells, double *EHist /*0-based numCells*/) {
+    dvec temp((size_t)(numCells + 1) * (s.T + 1), 0.0);
+    std::vector<long long> counter((size_t)(numCells + 1) * (s.T + 1), 0);
+    for (int t = 1; t <= s.T; ++t)
+        for (int j = 1; j <= s.N_p[t]; ++j) {
+            const int index = (int)s.P(1, j, t);
+            if (index < Nx && index >= 1 && index <= numCells) {
+                temp[(size_t)index + (size_t)(numCells + 1) * t] += s.P(2, j, t) * s.P(2, j, t) + s.P(3, j, t) * s.P(3, j, t) + s.P(4, j, t) * s.P(4, j, t);
+                counter[(size_t)index + (size_t)(numCells + 1) * t] += 1;
+            }
+        }
+    for (int j = 1; j <= numCells; ++j) {
+        double sm = 0.0; long long cn = 0;
+        for (int t = 1; t <= s.T; ++t) { sm += temp[(size_t)j + (size_t)(numCells + 1) * t]; cn += counter[(size_t)j + (size_t)(numCells + 1) * t]; }
+        EHist[j - 1] = cn > 0 ? sm * s.mass / (double)cn / 3.0 / e_c : 0.0;
+    }
+}
 // getTotalMomentum :206-216
 static void getTotalMomentum(Species &s, double res[3]) {
     double tmp[3] = {0, 0, 0};
@@ -2203,5 +2222,9 @@ int orc_anderson_fixed_point(void (*G)(int n, const double *x, double *gx, void 
     if (nHist) *nHist = (int)nl.normHist.size();
     for (int i = 0; i < (int)nl.normHist.size() && i < histCap; ++i) normHist[i] = nl.normHist[i];
     return nl.iterNumPicard;
+}
+void orc_local_temperature(void *h, int sp, int numCells, double *EHist) {
+    Oracle *o = (Oracle *)h;
+    localTemperature(o->plist[sp], o->world.Nx, numCells, EHist);
 }
 }  // extern "C"

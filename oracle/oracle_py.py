@@ -329,6 +329,11 @@ class Oracle:
     def aveJ(self): return self.L.orc_p_aveJ(self.h)
     def lostEnergySum(self, sp): return self.L.orc_lost_energy_sum(self.h, sp)
 
+    def localTemperature(self, sp, numCells):
+        out = np.zeros(numCells)
+        self.L.orc_local_temperature(self.h, sp, numCells, _dp(out))
+        return out
+
     def getTotalMomentum(self, sp):
         o = np.zeros(3)
         self.L.orc_total_momentum(self.h, sp, _dp(o))

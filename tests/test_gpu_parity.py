@@ -483,3 +483,30 @@ def test_cic_walls_pushed_by_the_host():
     o.solve_tridiag_Ampere(del_t); solver.solve_tridiag_Ampere(world, del_t)
     assert relerr(solver.phi_f, o.get("phi_f")) < 1e-10
     solver.close()
+
+
+@pytest.mark.parametrize("name", ["ngp_rf", "cic_rf"])
+def test_local_temperature_matches_oracle(name, tmp_path):
+    """writeLocalTemperature (mod_particle.f90:251-283) on the device: the per-cell temperatures equal the oracle's to summation-order
+    round-off, before and after a move; the file is the reference's unformatted sequential record"""
+    d = DECKS[name]
+    o = build_oracle(d)
+    world, solver, plist = build_cuda_from_oracle(d, o, tridiag_mode=_lib.TRIDIAG_THOMAS)
+    numCells = min(world.NumberXNodes, world.NumberXHalfNodes)
+    del_t = deck_del_t(d)
+    for phase in range(2):
+        for sp, p in enumerate(plist):
+            Tg, To = p.localTemperature(numCells), o.localTemperature(sp, numCells)
+            assert np.array_equal(Tg == 0.0, To == 0.0)
+            np.testing.assert_allclose(Tg, To, rtol=1e-12, atol=0)
+        if phase == 0:
+            solver.phi, solver.phi_f, solver.rho = o.get("phi"), o.get("phi_f"), o.get("rho")
+            o.makeHalfTimeEField(); solver.makeHalfTimeEField()
+            o.moveParticles(del_t)
+            ip.moveParticles(solver, plist, world, del_t)
+    E = plist[0].writeLocalTemperature(7, str(tmp_path), numCells)
+    raw = (tmp_path / "Temperature" / "Temp_e_7.dat").read_bytes()
+    assert len(raw) == 8 * numCells + 8
+    assert np.frombuffer(raw[:4], dtype="<i4")[0] == 8 * numCells == np.frombuffer(raw[-4:], dtype="<i4")[0]
+    assert np.array_equal(np.frombuffer(raw[4:-4], dtype="<f8"), E)
+    solver.close()

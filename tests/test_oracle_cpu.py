@@ -248,3 +248,23 @@ def test_restart_phase_space_files_round_trip(tmp_path):
     (tmp_path / "PhaseSpace" / "phaseSpace_e_thread2.dat").unlink()
     with pytest.raises(FileNotFoundError):
         q.readPhaseSpace(str(tmp_path), upload=False)
+
+
+def test_local_temperature_oracle_known_answer():
+    """writeLocalTemperature (mod_particle.f90:251-283): per cell SUM(v^2) m / count / 3 / e.  A Maxwellian loaded at T_e gives T_e in every
+    cell to sampling noise; a hand-made slab gives the exact per-cell averages."""
+    d = DECKS["ngp_rf"]
+    o = build_oracle(d)
+    Nh = d["Nx"] - 1
+    T = o.localTemperature(0, Nh)
+    assert T.shape == (Nh,) and np.all(T > 0)
+    assert abs(T.mean() - d["T_e"]) < 0.05 * d["T_e"]
+    ps = o.phase_space(0)
+    n0 = o.N_p(0)
+    # exact check against numpy on the same particles
+    cells = np.concatenate([ps[t, :n0[t], 0].astype(int) for t in range(d["T"])])
+    v2 = np.concatenate([(ps[t, :n0[t], 1:] ** 2).sum(axis=1) for t in range(d["T"])])
+    sc = o.species_scalars(0)
+    for j in (1, Nh // 2, Nh):
+        m = cells == j
+        assert abs(T[j - 1] - v2[m].sum() * sc["mass"] / m.sum() / 3.0 / op.e) <= 1e-12 * T[j - 1]
