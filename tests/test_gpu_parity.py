@@ -510,3 +510,26 @@ def test_local_temperature_matches_oracle(name, tmp_path):
     assert np.frombuffer(raw[:4], dtype="<i4")[0] == 8 * numCells == np.frombuffer(raw[-4:], dtype="<i4")[0]
     assert np.array_equal(np.frombuffer(raw[4:-4], dtype="<f8"), E)
     solver.close()
+
+
+def test_cell_sort_is_a_stable_sort():
+    """ipic_sort_particles orders by INT(l) and keeps the original order inside a cell, i.e. it equals numpy's stable argsort --
+    deterministic, which the seeded MCC relies on"""
+    d = DECKS["cic_rf"]
+    o = build_oracle(d)
+    world, solver, plist = build_cuda_from_oracle(d, o)
+    try:
+        L = ip.load_library()
+        for step in range(2):                               # second round: an already sorted input
+            for p in plist:
+                ps = p.download()
+                before = np.concatenate([ps[t, :p.N_p[t]] for t in range(p.numThread)])
+                _lib.check(L.ipic_sort_particles(solver._h, p._index))
+                ps = p.download()
+                after = np.concatenate([ps[t, :p.N_p[t]] for t in range(p.numThread)])
+                order = np.argsort(before[:, 0].astype(np.int64), kind="stable")
+                assert np.array_equal(after, before[order])
+            if step == 0:
+                ip.moveParticles(solver, plist, world, deck_del_t(d))    # shuffle the cells a little
+    finally:
+        solver.close()
