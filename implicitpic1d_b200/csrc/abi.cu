@@ -814,6 +814,7 @@ int ipic_set_option(ipic_handle h, const char *name, double value) {
     else if (k == "push_blocks") c->push_blocks = (int)value;
     else if (k == "transit_min") c->transit_min = (int)value;
     else if (k == "pair_species") c->pair_species = (int)value;
+    else if (k == "sort_subbins") c->sort_subbins = (int)value;
     else if (k == "pair_warps") c->pair_warps = (int)value;
     else if (k == "tile_order") c->tile_order = (int)value;
     else if (k == "timing") c->timing_on = value != 0.0;

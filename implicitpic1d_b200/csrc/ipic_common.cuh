@@ -159,6 +159,7 @@ struct Ctx {
     // options
     int stay_min = 20;
     int transit_min = 12;
+    int sort_subbins = 0;      // cell sort key = INT(l * sub); 0 = automatic (8, or what 16 key bits allow)
     int pair_species = 0;      // 1 = depositJ of a two-species plasma in one launch (k_push_pair).  Off: measured slower (C5: 2.34 ms per
                                // sweep against 1.88 + 0.32 ms) -- both species' sweeps are issue-bound, so running them side by side frees nothing
     int pair_warps = 4;        // warps per CTA (of 32) that start with the second species

@@ -1485,11 +1485,11 @@ int generate_species(Ctx &c, int sp, long long n, double T_eV, double v_drift, u
 // =====================================================================================================
 // Cell sort: stable LSD radix sort of (cell key, index) + gather.  Maintenance op, not on the hot path.
 // =====================================================================================================
-__global__ void k_sort_keys(const double *__restrict__ l, long long n, unsigned *keys, unsigned *vals) {
+__global__ void k_sort_keys(const double *__restrict__ l, long long n, unsigned *keys, unsigned *vals, double sub) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const double ll = l[i];
-        keys[i] = ll >= 0.0 ? (unsigned)(int)ll : 0xFFFFu;   // dead particles sort to the end
+        keys[i] = ll >= 0.0 ? (unsigned)(int)(ll * sub) : 0xFFFFu;   // dead particles sort to the end
         vals[i] = (unsigned)i;
     }
 }
@@ -1514,9 +1514,12 @@ int sort_species(Ctx &c, int sp) {
     }
     unsigned *keys = c.d_sort, *keys2 = keys + c.cap_sort, *vals = keys2 + c.cap_sort, *vals2 = vals + c.cap_sort;
     size_t tmp_bytes = 0;
-    c.launches += 1; k_sort_keys<<<c.num_sms * 8, 256, 0, c.stream>>>(s.l, n, keys, vals);
-    int bits = 1; while ((1 << bits) <= std::max(c.Nx, c.Nh) + 1) ++bits;
-    bits = std::max(bits, 16);
+    // key = INT(l * sub): cells cut into `sub` slices (8 unless that needs more than 16 key bits).  The finer order costs nothing -- the
+    // radix sort runs two 8-bit passes either way -- and puts neighbours in space into the same warp: C5 step 99.1 -> 97.1 ms
+    const int cells = std::max(c.Nx, c.Nh) + 2;
+    const int sub = std::max(1, std::min(c.sort_subbins > 0 ? c.sort_subbins : 8, 65534 / cells));
+    c.launches += 1; k_sort_keys<<<c.num_sms * 8, 256, 0, c.stream>>>(s.l, n, keys, vals, (double)sub);
+    const int bits = 16;                                      // keys < 65535 = the key of absorbed, not yet compacted particles
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, vals, vals2, (int)n, 0, bits, c.stream);
     if (tmp_bytes > c.cap_sort_tmp) {
         if (c.d_sort_tmp) cudaFree(c.d_sort_tmp);

@@ -513,8 +513,8 @@ def test_local_temperature_matches_oracle(name, tmp_path):
 
 
 def test_cell_sort_is_a_stable_sort():
-    """ipic_sort_particles orders by INT(l) and keeps the original order inside a cell, i.e. it equals numpy's stable argsort --
-    deterministic, which the seeded MCC relies on"""
+    """ipic_sort_particles orders by cell -- by INT(l * sub), cells cut into sub = min(8, 65534 // (max(N_x, N_h) + 2)) slices -- and keeps
+    the original order inside a slice, i.e. it equals numpy's stable argsort of that key: deterministic, which the seeded MCC relies on"""
     d = DECKS["cic_rf"]
     o = build_oracle(d)
     world, solver, plist = build_cuda_from_oracle(d, o)
@@ -527,8 +527,10 @@ def test_cell_sort_is_a_stable_sort():
                 _lib.check(L.ipic_sort_particles(solver._h, p._index))
                 ps = p.download()
                 after = np.concatenate([ps[t, :p.N_p[t]] for t in range(p.numThread)])
-                order = np.argsort(before[:, 0].astype(np.int64), kind="stable")
+                sub = min(8, 65534 // (max(world.NumberXNodes, world.NumberXHalfNodes) + 2))
+                order = np.argsort((before[:, 0] * float(sub)).astype(np.int64), kind="stable")
                 assert np.array_equal(after, before[order])
+                assert np.all(np.diff(after[:, 0].astype(np.int64)) >= 0)
             if step == 0:
                 ip.moveParticles(solver, plist, world, deck_del_t(d))    # shuffle the cells a little
     finally:
