@@ -103,6 +103,12 @@ SIGNATURES = {
     "ipic_get_collision_stats": (_i, [_p, _i32, C.POINTER(CollisionStats)]),
     "ipic_reset_collision_stats": (_i, [_p, _i32]),
     "ipic_set_num_to_collide": (_i, [_p, _i32, _i64]),
+    "ipic_set_injection_seed": (_i, [_p, C.c_uint64]),
+    "ipic_add_maxwellian_lost_particles": (_i, [_p, _d, _d, _dp, C.POINTER(_i64)]),
+    "ipic_reflux_particles": (_i, [_p, _d, _d, _dp]),
+    "ipic_inject_at_boundary": (_i, [_p, _d, _d, _d, _d, C.POINTER(_i64)]),
+    "ipic_inject_uniform_flux": (_i, [_p, _d, _d, _d, C.POINTER(_i64)]),
+    "ipic_maxwellian_heating": (_i, [_p, _i32, _d, _d, C.POINTER(_i64)]),
     "ipic_mcc_permutation": (_i, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
     "ipic_nccl_unique_id": (_i, [_p]),
     "ipic_comm_init": (_i, [_p, _i32, _i32, _p]),

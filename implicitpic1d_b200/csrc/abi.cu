@@ -387,6 +387,7 @@ int ipic_destroy(ipic_handle h) {
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
     delete static_cast<nitsol::Solver *>(c->nitsol_state);
     collisions_free(*c);
+    injection_free(*c);
     for (auto &s : c->sp) { if (s.l) cudaFree(s.l); if (s.l2) cudaFree(s.l2); if (s.refl) cudaFree(s.refl); if (s.refList) cudaFree(s.refList); }
     double *dp[] = {c->d_grid, c->d_dx, c->d_hinv, c->d_phi, c->d_phi_f, c->d_rho, c->d_J, c->d_E, c->d_a, c->d_b, c->d_c, c->d_cp, c->d_m, c->d_pcr, c->d_work,
                     c->d_rho_i, c->d_scal, c->d_phi_k, c->d_res_k, c->d_norms, c->d_loss, c->d_Ef, c->d_Eh};
@@ -786,6 +787,46 @@ int ipic_mcc_permutation(uint64_t n, uint64_t key, uint64_t j0, uint64_t count, 
     if (!out || n == 0 || j0 + count > n) { set_error("mcc permutation: need j0 + count <= n"); return IPIC_ERR_ARG; }
     const int bits = mcc_bits_hd(n);
     for (uint64_t k = 0; k < count; ++k) out[k] = mcc_permute_hd(j0 + k, n, bits, key);
+    return IPIC_OK;
+}
+
+// ---- wall refluxing / injection / heating (injection.cu; mod_particleInjection.f90) -------------------------------
+int ipic_set_injection_seed(ipic_handle h, uint64_t seed) { CTX(h); c->inj_seed = seed; c->inj_calls = 0; return IPIC_OK; }
+int ipic_add_maxwellian_lost_particles(ipic_handle h, double T_e, double T_i, double *energyAdd, int64_t *numAdded) {
+    CTX(h);
+    Timed t(*c, "injection");
+    long long n = 0;
+    RC(add_maxwellian_lost_particles(*c, T_e, T_i, energyAdd, &n));
+    if (numAdded) *numAdded = n;
+    return IPIC_OK;
+}
+int ipic_reflux_particles(ipic_handle h, double T_e, double T_i, double *energyAdd) {
+    CTX(h);
+    Timed t(*c, "injection");
+    return reflux_particles(*c, T_e, T_i, energyAdd);
+}
+int ipic_inject_at_boundary(ipic_handle h, double T_e, double T_i, double del_t, double numFluxPart, int64_t *numInjected) {
+    CTX(h);
+    Timed t(*c, "injection");
+    long long n = 0;
+    RC(inject_at_boundary(*c, T_e, T_i, del_t, numFluxPart, &n));
+    if (numInjected) *numInjected = n;
+    return IPIC_OK;
+}
+int ipic_inject_uniform_flux(ipic_handle h, double T_e, double T_i, double numFluxPart, int64_t *numInjected) {
+    CTX(h);
+    Timed t(*c, "injection");
+    long long n = 0;
+    RC(inject_uniform_flux(*c, T_e, T_i, numFluxPart, &n));
+    if (numInjected) *numInjected = n;
+    return IPIC_OK;
+}
+int ipic_maxwellian_heating(ipic_handle h, int32_t sp, double compValue, double T_eV, int64_t *numHeated) {
+    CTX(h); SPECIES(sp);
+    Timed t(*c, "injection");
+    long long n = 0;
+    RC(maxwellian_heating(*c, sp, compValue, T_eV, &n));
+    if (numHeated) *numHeated = n;
     return IPIC_OK;
 }
 

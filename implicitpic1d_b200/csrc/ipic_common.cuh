@@ -156,6 +156,9 @@ struct Ctx {
     std::vector<CollSet> colls;
     // MCC scratch
     double *d_mcc = nullptr; long long cap_mcc = 0; void *d_mcc_tmp = nullptr; size_t cap_mcc_tmp = 0;
+    // particle injection / refluxing / heating (injection.cu)
+    double *d_inj = nullptr; long long cap_inj = 0;
+    unsigned long long inj_seed = 0x1A2B3C4D5E6F7081ULL, inj_calls = 0;
     // options
     int stay_min = 20;
     int transit_min = 12;
@@ -215,6 +218,14 @@ int collision_set_create(Ctx &c, int nC, int nE, double red_mass, double sumMass
                          unsigned long long seed, int *out);
 int generate_collision(Ctx &c, int set, double del_t);
 void collisions_free(Ctx &c);
+
+// ---- injection.cu (mod_particleInjection.f90) -----------------------------------------------------------
+int add_maxwellian_lost_particles(Ctx &c, double T_e, double T_i, double *energyAdd, long long *numAdded);
+int reflux_particles(Ctx &c, double T_e, double T_i, double *energyAdd);
+int inject_at_boundary(Ctx &c, double T_e, double T_i, double del_t, double numFluxPart, long long *numInjected);
+int inject_uniform_flux(Ctx &c, double T_e, double T_i, double numFluxPart, long long *numInjected);
+int maxwellian_heating(Ctx &c, int sp, double compValue, double T_eV, long long *numHeated);
+void injection_free(Ctx &c);
 
 // ---- launchers implemented in field.cu --------------------------------------------------------------
 int field_setup(Ctx &c);                                   // construct_diagMatrix + Thomas/PCR factor tables

@@ -248,6 +248,29 @@ int ipic_set_num_to_collide(ipic_handle h, int32_t species, int64_t n);
 /* the keyed bijection used to draw collision candidates: out[k] = image of j0 + k in [0, n).  Host function (no GPU needed). */
 int ipic_mcc_permutation(uint64_t n, uint64_t key, uint64_t j0, uint64_t count, uint64_t *out);
 
+/* ---- wall refluxing, particle injection, Maxwellian heating ---------------------------------------------------
+ * replaces: SharedModules/src/mod_particleInjection.f90 -- the routines mod_simulation.f90:158-176 calls right after
+ * moveParticles, on the particles where the mover left them (device resident).  particleList(1) = species 0 (electrons),
+ * particleList(2) = species 1 (ions), as the reference assumes.  Temperatures in eV.  Random numbers come from counter-based
+ * PCG32 streams keyed by (seed, rank, call, work item) instead of the per-thread ran2 states: bit-reproducible for a seed.
+ *   ipic_add_maxwellian_lost_particles  addMaxwellianLostParticles :16-40: appends SUM(electron delIdx of the last move) electron-ion
+ *                                       pairs at one uniform position each; *energyAdd = what the call adds to SUM(energyAddColl)
+ *   ipic_reflux_particles               refluxParticles :42-69: re-draws the particles listed in refRecordIdx (see ipic_get_ref_record)
+ *                                       from a flux Maxwellian pointing away from the Neumann wall; *energyAdd = new - old energy
+ *   ipic_inject_at_boundary             injectAtBoundary :71-130: reflected electrons get a flux Maxwellian, reflected ions the ion sound
+ *                                       speed; then floor(numFluxPart) or floor(numFluxPart) + 1 pairs enter within del_t * c_s of the
+ *                                       Neumann wall.  numFluxPart = injectionFlux * del_t / w_p for this process's share of the wall
+ *                                       (readInjectionInputs :232-236 divides the same number by numThread, one draw per slab; here one
+ *                                       draw per call, the same expectation)
+ *   ipic_inject_uniform_flux            injectUniformFlux :132-158 (electrons at 20 T_e, as the reference)
+ *   ipic_maxwellian_heating             maxwellianHeating :160-177 with compValue = FracFreq * (currDel_t / del_t) / FractionFreqHeating */
+int ipic_set_injection_seed(ipic_handle h, uint64_t seed);
+int ipic_add_maxwellian_lost_particles(ipic_handle h, double T_e, double T_i, double *energyAdd, int64_t *numAdded);
+int ipic_reflux_particles(ipic_handle h, double T_e, double T_i, double *energyAdd);
+int ipic_inject_at_boundary(ipic_handle h, double T_e, double T_i, double del_t, double numFluxPart, int64_t *numInjected);
+int ipic_inject_uniform_flux(ipic_handle h, double T_e, double T_i, double numFluxPart, int64_t *numInjected);
+int ipic_maxwellian_heating(ipic_handle h, int32_t species, double compValue, double T_eV, int64_t *numHeated);
+
 /* ---- multi-GPU: particles sharded over ranks, one all-reduce of the fixed-point J/rho grid per deposit ------
  * (pattern of PIC1D/ExplicitPIC_Cpp/src/potential_solver.cpp:142).  unique_id is the 128-byte ncclUniqueId. */
 int ipic_nccl_unique_id(void *out128);

@@ -1916,6 +1916,142 @@ static int generateCollision(Oracle &o, NullCollision &nc, int32_t *irand, doubl
 // =============================================================================
 // C ABI for the test harness (ctypes).  0-based plain arrays at this boundary.
 // =============================================================================
+// =====================================================================================================
+// mod_particleInjection.f90 (the routines that consume the mover's delIdx / refIdx / refRecordIdx) + the samplers they use
+// =====================================================================================================
+// getMaxwellianSample  mod_BasicFunctions.f90:146-160
+static inline void getMaxwellianSample(double v[3], double M, double T_gas, int32_t &irand) {
+    const double v_therm = std::sqrt(T_gas * e_c / M);
+    const double U1 = ran2(irand), U2 = ran2(irand), U3 = ran2(irand), U4 = ran2(irand);
+    v[0] = v_therm * std::sqrt(-2.0 * std::log(U1)) * std::cos(2.0 * pi * U2);
+    v[1] = v_therm * std::sqrt(-2.0 * std::log(U1)) * std::sin(2.0 * pi * U2);
+    v[2] = v_therm * std::sqrt(-2.0 * std::log(U3)) * std::sin(2.0 * pi * U4);
+}
+// getMaxwellianFluxSample  mod_BasicFunctions.f90:162-176
+static inline void getMaxwellianFluxSample(double v[3], double M, double T_gas, int32_t &irand) {
+    const double v_therm = std::sqrt(T_gas * e_c / M);
+    const double U1 = ran2(irand), U2 = ran2(irand), U3 = ran2(irand), U4 = ran2(irand);
+    v[0] = v_therm * std::sqrt(-2 * std::log(U1)) * ((U2 - 0.5 >= 0.0) ? 1.0 : -1.0);       // SIGN(1.0d0, U(2) - 0.5d0)
+    v[1] = v_therm * std::sqrt(-2 * std::log(U3)) * std::cos(2 * pi * U4);
+    v[2] = v_therm * std::sqrt(-2 * std::log(U3)) * std::sin(2 * pi * U4);
+}
+static inline double sumsq3(Species &s, int i, int t) { return s.P(2, i, t) * s.P(2, i, t) + s.P(3, i, t) * s.P(3, i, t) + s.P(4, i, t) * s.P(4, i, t); }
+
+// addMaxwellianLostParticles  mod_particleInjection.f90:16-40 ; returns nonzero where a slab would overflow
+static int addMaxwellianLostParticles(Oracle &o, double T_e, double T_i, int32_t *irand /*1-based*/, double *energyAddColl /*1-based*/) {
+    Species &el = o.plist[0], &io = o.plist[1];
+    for (int t = 1; t <= o.world.T; ++t) {
+        int32_t ir = irand[t];
+        if (el.N_p[t] + el.delIdx[t] > el.finalIdx || io.N_p[t] + el.delIdx[t] > io.finalIdx) return 1;
+        for (int i = 1; i <= el.delIdx[t]; ++i) {
+            double v[3];
+            getMaxwellianSample(v, el.mass, T_e, ir);
+            for (int k = 0; k < 3; ++k) el.P(k + 2, el.N_p[t] + i, t) = v[k];
+            getMaxwellianFluxSample(v, io.mass, T_i, ir);
+            for (int k = 0; k < 3; ++k) io.P(k + 2, io.N_p[t] + i, t) = v[k];
+            energyAddColl[t] += (sumsq3(el, el.N_p[t] + i, t) * el.mass * el.w_p + sumsq3(io, io.N_p[t] + i, t) * io.mass * io.w_p) * 0.5;
+            const double x_random = ran2(ir) * o.world.L_domain + o.world.startX;
+            el.P(1, el.N_p[t] + i, t) = getLFromX(o.world, x_random);
+            io.P(1, io.N_p[t] + i, t) = el.P(1, el.N_p[t] + i, t);
+        }
+        io.N_p[t] += el.delIdx[t];
+        el.N_p[t] += el.delIdx[t];
+        irand[t] = ir;
+    }
+    return 0;
+}
+// refluxParticles  :42-69
+static void refluxParticles(Oracle &o, double T_e, double T_i, int32_t *irand, double *energyAddColl) {
+    for (int j = 0; j < 2; ++j) {
+        Species &p = o.plist[j];
+        for (int t = 1; t <= o.world.T; ++t) {
+            int32_t ir = irand[t];
+            for (int i = 1; i <= std::min(p.refIdx[t], p.refRecLen); ++i) {     // refRecordIdx(finalIdx/10, T): entries past the end were never stored
+                const int idx = p.refRecordIdx[(size_t)i + (size_t)(p.refRecLen + 1) * t];
+                energyAddColl[t] -= sumsq3(p, idx, t) * p.mass * p.w_p * 0.5;
+                double v[3];
+                getMaxwellianFluxSample(v, p.mass, j == 0 ? T_e : T_i, ir);
+                for (int k = 0; k < 3; ++k) p.P(k + 2, idx, t) = v[k];
+                p.P(2, idx, t) = (o.world.bc[1] == 2) ? std::fabs(p.P(2, idx, t)) : -std::fabs(p.P(2, idx, t));
+                energyAddColl[t] += sumsq3(p, idx, t) * p.mass * p.w_p * 0.5;
+            }
+            irand[t] = ir;
+        }
+    }
+}
+// injectAtBoundary  :71-130 ; numFluxParticlesLow/High, injectionR from readInjectionInputs :232-238
+static int injectAtBoundary(Oracle &o, double T_e, double del_t, int numLow, int numHigh, double injectionR, int32_t *irand) {
+    Species &el = o.plist[0], &io = o.plist[1];
+    const double ionSoundSpeed = std::sqrt(T_e * e_c / io.mass);
+    const bool leftNeumann = (o.world.bc[1] == 2);
+    for (int j = 0; j < 2; ++j) {
+        Species &p = o.plist[j];
+        for (int t = 1; t <= o.world.T; ++t)
+            for (int i = 1; i <= std::min(p.refIdx[t], p.refRecLen); ++i) {
+                const int idx = p.refRecordIdx[(size_t)i + (size_t)(p.refRecLen + 1) * t];
+                if (j == 0) {
+                    double v[3];
+                    getMaxwellianFluxSample(v, p.mass, T_e, irand[t]);
+                    for (int k = 0; k < 3; ++k) p.P(k + 2, idx, t) = v[k];
+                } else { p.P(2, idx, t) = ionSoundSpeed; p.P(3, idx, t) = 0.0; p.P(4, idx, t) = 0.0; }
+                p.P(2, idx, t) = leftNeumann ? std::fabs(p.P(2, idx, t)) : -std::fabs(p.P(2, idx, t));
+            }
+    }
+    const double endX = o.world.startX + o.world.L_domain;
+    for (int t = 1; t <= o.world.T; ++t) {
+        const int numInjected = (ran2(irand[t]) > injectionR) ? numLow : numHigh;
+        if (el.N_p[t] + numInjected > el.finalIdx || io.N_p[t] + numInjected > io.finalIdx) return 1;
+        for (int i = 1; i <= numInjected; ++i) {
+            const double shift_rand = del_t * ran2(irand[t]) * ionSoundSpeed;
+            double v[3];
+            getMaxwellianFluxSample(v, el.mass, T_e, irand[t]);
+            const int ie = el.N_p[t] + i, ii = io.N_p[t] + i;
+            for (int k = 0; k < 3; ++k) el.P(k + 2, ie, t) = v[k];
+            io.P(2, ii, t) = ionSoundSpeed; io.P(3, ii, t) = 0.0; io.P(4, ii, t) = 0.0;
+            if (leftNeumann) {
+                el.P(2, ie, t) = std::fabs(el.P(2, ie, t)); io.P(2, ii, t) = std::fabs(io.P(2, ii, t));
+                el.P(1, ie, t) = getLFromX(o.world, o.world.startX + shift_rand);
+            } else {
+                el.P(2, ie, t) = -std::fabs(el.P(2, ie, t)); io.P(2, ii, t) = -std::fabs(io.P(2, ii, t));
+                el.P(1, ie, t) = getLFromX(o.world, endX - shift_rand);
+            }
+            io.P(1, ii, t) = el.P(1, ie, t);
+        }
+        el.N_p[t] += numInjected; io.N_p[t] += numInjected;
+    }
+    return 0;
+}
+// injectUniformFlux  :132-158
+static int injectUniformFlux(Oracle &o, double T_e, double T_i, int numLow, int numHigh, double injectionR, int32_t *irand) {
+    Species &el = o.plist[0], &io = o.plist[1];
+    for (int t = 1; t <= o.world.T; ++t) {
+        const int numInjected = (ran2(irand[t]) > injectionR) ? numLow : numHigh;
+        if (el.N_p[t] + numInjected > el.finalIdx || io.N_p[t] + numInjected > io.finalIdx) return 1;
+        for (int i = 1; i <= numInjected; ++i) {
+            double v[3];
+            const int ie = el.N_p[t] + i, ii = io.N_p[t] + i;
+            getMaxwellianSample(v, el.mass, 20.0 * T_e, irand[t]);
+            for (int k = 0; k < 3; ++k) el.P(k + 2, ie, t) = v[k];
+            getMaxwellianSample(v, io.mass, T_i, irand[t]);
+            for (int k = 0; k < 3; ++k) io.P(k + 2, ii, t) = v[k];
+            const double x_random = ran2(irand[t]) * o.world.L_domain + o.world.startX;
+            el.P(1, ie, t) = getLFromX(o.world, x_random);
+            io.P(1, ii, t) = el.P(1, ie, t);
+        }
+        el.N_p[t] += numInjected; io.N_p[t] += numInjected;
+    }
+    return 0;
+}
+// maxwellianHeating  :160-177 with compValue = FracFreq * (currDel_t / del_t) / FractionFreqHeating
+static void maxwellianHeating(Oracle &o, int sp, double compValue, double T, int32_t *irand) {
+    Species &p = o.plist[sp];
+    for (int t = 1; t <= o.world.T; ++t)
+        for (int i = 1; i <= p.N_p[t]; ++i) {
+            const double R = ran2(irand[t]);
+            if (R < compValue) { double v[3]; getMaxwellianSample(v, p.mass, T, irand[t]); for (int k = 0; k < 3; ++k) p.P(k + 2, i, t) = v[k]; }
+        }
+}
+
 extern "C" {
 
 void *orc_create(int scheme, int Nx, double L_domain, int gridType, double del_x, int bcL, int bcR, int smooth, int T) {
@@ -2226,5 +2362,46 @@ int orc_anderson_fixed_point(void (*G)(int n, const double *x, double *gx, void 
 void orc_local_temperature(void *h, int sp, int numCells, double *EHist) {
     Oracle *o = (Oracle *)h;
     localTemperature(o->plist[sp], o->world.Nx, numCells, EHist);
+}
+// mod_particleInjection.f90: irand is the caller's per-thread ran2 state (T entries), energyAdd gets SUM(energyAddColl) of this call
+int orc_add_maxwellian_lost_particles(void *h, double T_e, double T_i, int32_t *irand, double *energyAdd) {
+    Oracle *o = (Oracle *)h; const int T = o->world.T;
+    std::vector<int32_t> ir(T + 1); dvec en(T + 1, 0.0);
+    for (int t = 1; t <= T; ++t) ir[t] = irand[t - 1];
+    const int rc = addMaxwellianLostParticles(*o, T_e, T_i, ir.data(), en.data());
+    double sm = 0.0; for (int t = 1; t <= T; ++t) { irand[t - 1] = ir[t]; sm += en[t]; }
+    *energyAdd = sm;
+    return rc;
+}
+void orc_reflux_particles(void *h, double T_e, double T_i, int32_t *irand, double *energyAdd) {
+    Oracle *o = (Oracle *)h; const int T = o->world.T;
+    std::vector<int32_t> ir(T + 1); dvec en(T + 1, 0.0);
+    for (int t = 1; t <= T; ++t) ir[t] = irand[t - 1];
+    refluxParticles(*o, T_e, T_i, ir.data(), en.data());
+    double sm = 0.0; for (int t = 1; t <= T; ++t) { irand[t - 1] = ir[t]; sm += en[t]; }
+    *energyAdd = sm;
+}
+int orc_inject_at_boundary(void *h, double T_e, double del_t, int numLow, int numHigh, double injectionR, int32_t *irand) {
+    Oracle *o = (Oracle *)h; const int T = o->world.T;
+    std::vector<int32_t> ir(T + 1);
+    for (int t = 1; t <= T; ++t) ir[t] = irand[t - 1];
+    const int rc = injectAtBoundary(*o, T_e, del_t, numLow, numHigh, injectionR, ir.data());
+    for (int t = 1; t <= T; ++t) irand[t - 1] = ir[t];
+    return rc;
+}
+int orc_inject_uniform_flux(void *h, double T_e, double T_i, int numLow, int numHigh, double injectionR, int32_t *irand) {
+    Oracle *o = (Oracle *)h; const int T = o->world.T;
+    std::vector<int32_t> ir(T + 1);
+    for (int t = 1; t <= T; ++t) ir[t] = irand[t - 1];
+    const int rc = injectUniformFlux(*o, T_e, T_i, numLow, numHigh, injectionR, ir.data());
+    for (int t = 1; t <= T; ++t) irand[t - 1] = ir[t];
+    return rc;
+}
+void orc_maxwellian_heating(void *h, int sp, double compValue, double T_eV, int32_t *irand) {
+    Oracle *o = (Oracle *)h; const int T = o->world.T;
+    std::vector<int32_t> ir(T + 1);
+    for (int t = 1; t <= T; ++t) ir[t] = irand[t - 1];
+    maxwellianHeating(*o, sp, compValue, T_eV, ir.data());
+    for (int t = 1; t <= T; ++t) irand[t - 1] = ir[t];
 }
 }  // extern "C"

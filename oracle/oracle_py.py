@@ -86,6 +86,11 @@ def lib(native=False):
         "orc_p_solve_potential": (i, [p, d, dp, dp]), "orc_p_solve_div_ampere_anderson": (None, [p, d]),
         "orc_p_total_PE": (d, [p, i]), "orc_p_gauss_error": (d, [p]), "orc_p_charge_error": (d, [p, dp, d]),
         "orc_p_aveJ": (d, [p]), "orc_reset_sweep_counters": (None, [p]),
+        "orc_add_maxwellian_lost_particles": (i, [p, d, d, C.POINTER(C.c_int32), dp]),
+        "orc_reflux_particles": (None, [p, d, d, C.POINTER(C.c_int32), dp]),
+        "orc_inject_at_boundary": (i, [p, d, d, i, i, d, C.POINTER(C.c_int32)]),
+        "orc_inject_uniform_flux": (i, [p, d, d, i, i, d, C.POINTER(C.c_int32)]),
+        "orc_maxwellian_heating": (None, [p, i, d, d, C.POINTER(C.c_int32)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -240,6 +245,34 @@ class Oracle:
         o = np.zeros(5)
         self.L.orc_species_scalars(self.h, sp, _dp(o))
         return dict(mass=o[0], q=o[1], w_p=o[2], q_over_m=o[3], q_times_wp=o[4])
+
+    # ---- mod_particleInjection.f90 (irand: the per-thread ran2 states, int32[T], advanced in place)
+    def _ir(self, irand):
+        assert irand.dtype == np.int32 and irand.size == self.T
+        return irand.ctypes.data_as(C.POINTER(C.c_int32))
+
+    def addMaxwellianLostParticles(self, T_e, T_i, irand):
+        """returns what the call adds to SUM(energyAddColl)"""
+        en = C.c_double()
+        if self.L.orc_add_maxwellian_lost_particles(self.h, T_e, T_i, self._ir(irand), C.byref(en)):
+            raise RuntimeError("oracle: addMaxwellianLostParticles overflows a slab")
+        return en.value
+
+    def refluxParticles(self, T_e, T_i, irand):
+        en = C.c_double()
+        self.L.orc_reflux_particles(self.h, T_e, T_i, self._ir(irand), C.byref(en))
+        return en.value
+
+    def injectAtBoundary(self, T_e, del_t, numLow, numHigh, injectionR, irand):
+        if self.L.orc_inject_at_boundary(self.h, T_e, del_t, numLow, numHigh, injectionR, self._ir(irand)):
+            raise RuntimeError("oracle: injectAtBoundary overflows a slab")
+
+    def injectUniformFlux(self, T_e, T_i, numLow, numHigh, injectionR, irand):
+        if self.L.orc_inject_uniform_flux(self.h, T_e, T_i, numLow, numHigh, injectionR, self._ir(irand)):
+            raise RuntimeError("oracle: injectUniformFlux overflows a slab")
+
+    def maxwellianHeating(self, sp, compValue, T_eV, irand):
+        self.L.orc_maxwellian_heating(self.h, sp, compValue, T_eV, self._ir(irand))
 
     def particle_time_step(self, sp):
         o = np.zeros(self.Nx)
