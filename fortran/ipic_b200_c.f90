@@ -216,6 +216,65 @@ module ipic_b200_c
             type(ipic_solver_stats), intent(out) :: stats
             integer(c_int) :: rc
         end function
+        function ipic_particle_count(handle, species, n) bind(c, name="ipic_particle_count") result(rc)
+            import :: c_ptr, c_int, c_int32_t, c_int64_t
+            type(c_ptr), value :: handle
+            integer(c_int32_t), value :: species
+            integer(c_int64_t), intent(out) :: n
+            integer(c_int) :: rc
+        end function
+        function ipic_generate_collision(handle, collision_set, del_t) bind(c, name="ipic_generate_collision") result(rc)
+            import :: c_ptr, c_int, c_int32_t, c_double
+            type(c_ptr), value :: handle
+            integer(c_int32_t), value :: collision_set
+            real(c_double), value :: del_t
+            integer(c_int) :: rc
+        end function
+        ! ---- mod_particleInjection.f90 on the device (include/ipic1d_b200.h, "wall refluxing, particle injection, Maxwellian heating")
+        function ipic_set_injection_seed(handle, seed) bind(c, name="ipic_set_injection_seed") result(rc)
+            import :: c_ptr, c_int, c_int64_t
+            type(c_ptr), value :: handle
+            integer(c_int64_t), value :: seed
+            integer(c_int) :: rc
+        end function
+        function ipic_add_maxwellian_lost_particles(handle, T_e, T_i, energyAdd, numAdded) &
+                bind(c, name="ipic_add_maxwellian_lost_particles") result(rc)
+            import :: c_ptr, c_int, c_int64_t, c_double
+            type(c_ptr), value :: handle
+            real(c_double), value :: T_e, T_i
+            real(c_double), intent(out) :: energyAdd
+            integer(c_int64_t), intent(out) :: numAdded
+            integer(c_int) :: rc
+        end function
+        function ipic_reflux_particles(handle, T_e, T_i, energyAdd) bind(c, name="ipic_reflux_particles") result(rc)
+            import :: c_ptr, c_int, c_double
+            type(c_ptr), value :: handle
+            real(c_double), value :: T_e, T_i
+            real(c_double), intent(out) :: energyAdd
+            integer(c_int) :: rc
+        end function
+        function ipic_inject_at_boundary(handle, T_e, T_i, del_t, numFluxPart, numInjected) bind(c, name="ipic_inject_at_boundary") result(rc)
+            import :: c_ptr, c_int, c_int64_t, c_double
+            type(c_ptr), value :: handle
+            real(c_double), value :: T_e, T_i, del_t, numFluxPart
+            integer(c_int64_t), intent(out) :: numInjected
+            integer(c_int) :: rc
+        end function
+        function ipic_inject_uniform_flux(handle, T_e, T_i, numFluxPart, numInjected) bind(c, name="ipic_inject_uniform_flux") result(rc)
+            import :: c_ptr, c_int, c_int64_t, c_double
+            type(c_ptr), value :: handle
+            real(c_double), value :: T_e, T_i, numFluxPart
+            integer(c_int64_t), intent(out) :: numInjected
+            integer(c_int) :: rc
+        end function
+        function ipic_maxwellian_heating(handle, species, compValue, T_eV, numHeated) bind(c, name="ipic_maxwellian_heating") result(rc)
+            import :: c_ptr, c_int, c_int32_t, c_int64_t, c_double
+            type(c_ptr), value :: handle
+            integer(c_int32_t), value :: species
+            real(c_double), value :: compValue, T_eV
+            integer(c_int64_t), intent(out) :: numHeated
+            integer(c_int) :: rc
+        end function
     end interface
 
 contains

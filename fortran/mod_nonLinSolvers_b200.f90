@@ -92,7 +92,7 @@ contains
         call ipic_check(ipic_get_field(ipic_h, IPIC_F_J, solver%J, NumberXHalfNodes), 'get J')
         call ipic_check(ipic_get_field(ipic_h, IPIC_F_EFIELD, solver%EField, NumberXHalfNodes), 'get EField')
         call ipic_pull_particles(particleList)
-        particlesOnDevice = .false.      ! collisions / injection run on the host before the next step
+        particlesOnDevice = particlesStayOnDevice      ! level 2: collisions / injection run on the host before the next step
         call ipic_check(ipic_get_solver_stats(ipic_h, st), 'ipic_get_solver_stats')
         iterNumPicard = st%iterNumPicard
         iterNumAdaptiveSteps = st%iterNumAdaptiveSteps

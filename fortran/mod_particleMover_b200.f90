@@ -25,6 +25,10 @@ module mod_particleMover
     ! public: the level-2 shim (mod_nonLinSolvers_b200.f90) drives the same handle
     type(c_ptr) :: ipic_h = c_null_ptr
     logical :: particlesOnDevice = .false.
+    ! level 3 (INTEGRATION.md section 3b): injection (mod_particleInjection_b200.f90) and MCC (ipic_generate_collision) also run on the
+    ! device, so nothing on the host touches phaseSpace between steps: the per-step download / upload is skipped and the host copy is
+    ! refreshed on demand with ipic_sync_host (before diagnostics dumps, writePhaseSpace, restart files)
+    logical :: particlesStayOnDevice = .false.
 
 contains
 
@@ -109,9 +113,17 @@ contains
         integer :: j, k, iThread
         integer(c_int64_t) :: nRef, slabEnd
         integer(c_int32_t), allocatable :: refGlobal(:)
+        integer(c_int64_t) :: nTotal
         do j = 1, size(particleList)
-            call ipic_check(ipic_download_particles(ipic_h, j - 1, particleList(j)%phaseSpace, particleList(j)%N_p, numThread, &
-                particleList(j)%finalIdx), 'ipic_download_particles')
+            if (particlesStayOnDevice) then
+                ! only the count comes back; it is booked on the last slab, where appended particles land on the next download
+                call ipic_check(ipic_particle_count(ipic_h, j - 1, nTotal), 'ipic_particle_count')
+                particleList(j)%N_p = 0
+                particleList(j)%N_p(numThread) = int(nTotal, int32)
+            else
+                call ipic_check(ipic_download_particles(ipic_h, j - 1, particleList(j)%phaseSpace, particleList(j)%N_p, numThread, &
+                    particleList(j)%finalIdx), 'ipic_download_particles')
+            end if
             call ipic_check(ipic_get_move_stats(ipic_h, j - 1, st), 'ipic_get_move_stats')
             ! totals are reported in slab 1; callers only ever use SUM(...) over the thread dimension
             ! (main.f90:79-84, mod_simulation.f90:171-200)
@@ -123,6 +135,8 @@ contains
             if (st%refIdx > 0) then
                 allocate(refGlobal(st%refIdx))
                 call ipic_check(ipic_get_ref_record(ipic_h, j - 1, refGlobal, int(st%refIdx, c_int64_t), nRef), 'ipic_get_ref_record')
+                if (particlesStayOnDevice) nRef = 0      ! the device-side refluxing reads the list where it is; refIdx keeps the total
+                if (particlesStayOnDevice) particleList(j)%refIdx(1) = int(st%refIdx, int32)
                 iThread = 1
                 slabEnd = particleList(j)%N_p(1)
                 do k = 1, int(min(nRef, st%refIdx))
@@ -159,7 +173,18 @@ contains
         call ipic_push_state(solver, particleList)
         call ipic_check(ipic_move_particles(ipic_h, del_t), 'ipic_move_particles')
         call ipic_pull_particles(particleList)
-        particlesOnDevice = .false.     ! collisions / injection run on the host before the next step
+        particlesOnDevice = particlesStayOnDevice     ! level 1/2: collisions / injection run on the host before the next step
     end subroutine moveParticles
+
+    subroutine ipic_sync_host(particleList)
+        ! level 3: bring the host copy of phaseSpace / N_p up to date (diagnostics dumps, writePhaseSpace); the slab split of the
+        ! last upload is kept, particles appended since sit behind the last slab
+        type(Particle), intent(in out) :: particleList(:)
+        integer :: j
+        do j = 1, size(particleList)
+            call ipic_check(ipic_download_particles(ipic_h, j - 1, particleList(j)%phaseSpace, particleList(j)%N_p, numThread, &
+                particleList(j)%finalIdx), 'ipic_download_particles')
+        end do
+    end subroutine ipic_sync_host
 
 end module mod_particleMover
