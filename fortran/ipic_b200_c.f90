@@ -223,6 +223,14 @@ module ipic_b200_c
             integer(c_int64_t), intent(out) :: n
             integer(c_int) :: rc
         end function
+        function ipic_load_particle_density(handle, species, densities) bind(c, name="ipic_load_particle_density") result(rc)
+            ! loadParticleDensity (mod_Scheme.f90) for one species: SUM(part%densities, DIM=2) of a reset load, before w_p
+            import :: c_ptr, c_int, c_int32_t, c_double
+            type(c_ptr), value :: handle
+            integer(c_int32_t), value :: species
+            real(c_double), intent(out) :: densities(*)
+            integer(c_int) :: rc
+        end function
         function ipic_generate_collision(handle, collision_set, del_t) bind(c, name="ipic_generate_collision") result(rc)
             import :: c_ptr, c_int, c_int32_t, c_double
             type(c_ptr), value :: handle

@@ -11,6 +11,7 @@ Host-side mirror of the reference's Fortran modules; all numerical work happens 
     mod_nonLinSolvers     -> initializeSolver, solvePotential, solveDivAmpereAnderson, funcNitsol
     mod_targetParticle    -> targetParticle
     mod_NullCollision     -> nullCollision, readNullCollisionInputs
+    mod_Scheme            -> scheme (loadParticleDensity, WriteParticleDensity)
     mod_particleInjection -> particle_injection (addMaxwellianLostParticles, refluxParticles, injectAtBoundary,
                              injectUniformFlux, maxwellianHeating, readInjectionInputs)
 """
@@ -22,7 +23,8 @@ from .particle_mover import depositJ, moveParticles, allocateParticleMoverData
 from .nonlin_solvers import initializeSolver, solvePotential, solveDivAmpereAnderson, funcNitsol, SolverState, solveJFNK, nitsol, NitsolInfo
 from .null_collision import targetParticle, nullCollision, readNullCollisionInputs
 from . import particle_injection
+from . import scheme
 from ._lib import IpicError, load as load_library, LIB_PATH
 
 __all__ = ["constants", "Domain", "Particle", "potentialSolver", "depositJ", "moveParticles", "allocateParticleMoverData",
-           "initializeSolver", "solvePotential", "solveDivAmpereAnderson", "funcNitsol", "SolverState", "solveJFNK", "nitsol", "NitsolInfo", "targetParticle", "nullCollision", "readNullCollisionInputs", "particle_injection", "IpicError", "load_library", "LIB_PATH"]
+           "initializeSolver", "solvePotential", "solveDivAmpereAnderson", "funcNitsol", "SolverState", "solveJFNK", "nitsol", "NitsolInfo", "targetParticle", "nullCollision", "readNullCollisionInputs", "particle_injection", "scheme", "IpicError", "load_library", "LIB_PATH"]

@@ -556,6 +556,18 @@ int ipic_deposit_rho(ipic_handle h) {
     RC(allreduce_acc(*c));
     return field_finalize_rho(*c);
 }
+int ipic_load_particle_density(ipic_handle h, int32_t sp, double *densities) {
+    CTX(h); SPECIES(sp);
+    if (!densities) return IPIC_ERR_ARG;
+    { Timed t(*c, "depositRho_kernels"); RC(launch_deposit_rho(*c, sp, true)); }
+    if (c->nranks > 1 && c->nccl_comm) {
+        // only this species' grid crosses NVLink (the copies are not in use: the rho kernel deposits into copy 0)
+        unsigned long long *acc = c->d_acc + (size_t)sp * 2 * ((size_t)std::max(c->Nx, c->Nh) + 2);
+        int rc = g_nccl.AllReduce(acc, acc, (size_t)c->Nx + 2, kNcclUint64, kNcclSum, c->nccl_comm, c->stream);
+        if (rc != 0) { set_error("ncclAllReduce (density) failed"); return IPIC_ERR_NCCL; }
+    }
+    return extract_species_grid(*c, sp, c->Nx, densities);
+}
 int ipic_solve_tridiag_poisson(ipic_handle h, double t) { CTX(h); NEED_SOLVER; return field_poisson(*c, t); }
 int ipic_solve_initial_potential(ipic_handle h, double t) {
     RC(ipic_deposit_rho(h));

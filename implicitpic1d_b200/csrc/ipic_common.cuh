@@ -199,7 +199,8 @@ void set_error(const std::string &s);
 int launch_deposit(Ctx &c, int sp, double del_t);
 int launch_move(Ctx &c, int sp, double del_t);
 int launch_deposit_pair(Ctx &c, int a, int b, double del_t);
-int launch_deposit_rho(Ctx &c, int sp);
+int launch_deposit_rho(Ctx &c, int sp, bool density = false);   // density: the diagnostic's weights (differs from rho at CIC Dirichlet walls)
+int extract_species_grid(Ctx &c, int sp, int n, double *host_out);   // int64 grid of one species -> doubles on the host, grid zeroed
 int compact_species(Ctx &c, int sp);
 int local_temperature(Ctx &c, int sp, int numCells, double *sumV2_host, long long *count_host);
 int fold_acc(Ctx &c, size_t count);                    // CTA copies of the deposition grids -> copy 0

@@ -917,7 +917,9 @@ int launch_move(Ctx &c, int sp, double del_t) {
 // =====================================================================================================
 // rho deposition (interpolateParticleToNodes: NGP mod_Scheme.f90:50-65, CIC mod_Scheme.f90:21-66)
 // =====================================================================================================
-template <int SCHEME>
+// DENS (CIC only): interpolateParticleToNodesDensity (CIC mod_Scheme.f90:68-105) -- the density diagnostic folds the weight behind a
+// Dirichlet wall back into the wall cell, as at a Neumann wall, where the charge deposit subtracts it
+template <int SCHEME, bool DENS = false>
 __global__ void __launch_bounds__(1024, 1) k_deposit_rho(const double *__restrict__ lpos, long long n, const int *__restrict__ bc, int Nx,
                                                          unsigned long long *acc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -949,8 +951,8 @@ __global__ void __launch_bounds__(1024, 1) k_deposit_rho(const double *__restric
                 const int bv = bc[lc + 1] - bc[lc];
                 switch (bv) {
                 case 0: break;
-                case -1: case -4: wc -= wl; hl = false; break;                 // Dirichlet to the left
-                case 1: case 4: wc -= wr; hr = false; break;                   // Dirichlet to the right
+                case -1: case -4: wc += DENS ? wl : -wl; hl = false; break;    // Dirichlet to the left
+                case 1: case 4: wc += DENS ? wr : -wr; hr = false; break;      // Dirichlet to the right
                 case -2: wc += wl; hl = false; break;                          // Neumann to the left
                 case 2: wc += wr; hr = false; break;                           // Neumann to the right
                 case -3: il = Nx; break;                                        // periodic to the left
@@ -966,7 +968,7 @@ __global__ void __launch_bounds__(1024, 1) k_deposit_rho(const double *__restric
     limb_grid_flush(G, Nx);
 }
 
-int launch_deposit_rho(Ctx &c, int sp) {
+int launch_deposit_rho(Ctx &c, int sp, bool density) {
     SpeciesDev &s = c.sp[sp];
     if (s.n == 0) return IPIC_OK;
     if (c.Nx > MAX_GRID_SMEM) return IPIC_ERR_UNSUPPORTED;
@@ -977,11 +979,33 @@ int launch_deposit_rho(Ctx &c, int sp) {
     if (c.scheme != IPIC_SCHEME_CIC) {
         if (!cfg0) { IPIC_CUDA(cudaFuncSetAttribute(k_deposit_rho<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (MAX_GRID_SMEM + 2) * 4)); cfg0 = true; }
         c.launches += 1; k_deposit_rho<0><<<c.num_sms, 1024, smem, c.stream>>>(s.l, s.n, c.d_bc, c.Nx, acc);
-    } else {
+    } else if (!density) {
         if (!cfg1) { IPIC_CUDA(cudaFuncSetAttribute(k_deposit_rho<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (MAX_GRID_SMEM + 2) * 4)); cfg1 = true; }
         c.launches += 1; k_deposit_rho<1><<<c.num_sms, 1024, smem, c.stream>>>(s.l, s.n, c.d_bc, c.Nx, acc);
+    } else {
+        static bool cfg2s[64] = {};
+        bool &cfg2 = cfg2s[c.device & 63];
+        if (!cfg2) { IPIC_CUDA(cudaFuncSetAttribute(k_deposit_rho<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (MAX_GRID_SMEM + 2) * 4)); cfg2 = true; }
+        c.launches += 1; k_deposit_rho<1, true><<<c.num_sms, 1024, smem, c.stream>>>(s.l, s.n, c.d_bc, c.Nx, acc);
     }
     IPIC_CUDA(cudaGetLastError());
+    return IPIC_OK;
+}
+
+// one species' deposition grid (all CTA copies) -> doubles (sum of weights, before w_p); the grid is left zeroed
+__global__ void k_acc_extract(unsigned long long *g, int reps, unsigned long long rep_stride, int n, double *out) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        unsigned long long q = 0ull;
+        for (int r = 0; r < reps; ++r) { q += g[(size_t)r * rep_stride + i + 1]; g[(size_t)r * rep_stride + i + 1] = 0ull; }
+        out[i] = (double)(long long)q * FX_INV;
+    }
+}
+int extract_species_grid(Ctx &c, int sp, int n, double *host_out) {
+    unsigned long long *acc = c.d_acc + (size_t)sp * 2 * ((size_t)std::max(c.Nx, c.Nh) + 2);
+    c.launches += 1; k_acc_extract<<<(n + 255) / 256, 256, 0, c.stream>>>(acc, c.acc_reps, (unsigned long long)c.acc_rep_stride, n, c.d_work);
+    IPIC_CUDA(cudaGetLastError());
+    IPIC_CUDA(cudaMemcpyAsync(host_out, c.d_work, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    IPIC_CUDA(cudaStreamSynchronize(c.stream));
     return IPIC_OK;
 }
 

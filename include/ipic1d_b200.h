@@ -120,6 +120,10 @@ int ipic_set_field(ipic_handle h, int which, const double *in, int32_t n);
  * depositJ              NGP/src/mod_particleMover.f90:67-157      CIC/src/mod_particleMoverPicard.f90:77-195
  * moveParticles         NGP/src/mod_particleMover.f90:162-270     CIC/src/mod_particleMoverPicard.f90:198-317 */
 int ipic_deposit_rho(ipic_handle h);
+/* loadParticleDensity (NGP mod_Scheme.f90:68-83, CIC mod_Scheme.f90:107-121) for one species: densities[N_x] receives the sum of the
+ * interpolation weights of this call over all ranks (the reference's SUM(part%densities, DIM=2) of a reset load, before w_p); the host
+ * adds calls up for time averages and applies WriteParticleDensity's scaling / smoothing / normalisation (O(N_x)). */
+int ipic_load_particle_density(ipic_handle h, int32_t species, double *densities);
 int ipic_solve_tridiag_poisson(ipic_handle h, double timeCurrent);
 int ipic_solve_initial_potential(ipic_handle h, double timeCurrent);
 int ipic_make_const_source_term(ipic_handle h);

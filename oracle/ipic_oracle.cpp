@@ -1917,6 +1917,91 @@ static int generateCollision(Oracle &o, NullCollision &nc, int32_t *irand, doubl
 // C ABI for the test harness (ctypes).  0-based plain arrays at this boundary.
 // =============================================================================
 // =====================================================================================================
+// density diagnostic: loadParticleDensity + WriteParticleDensity (NGP mod_Scheme.f90:68-158, CIC mod_Scheme.f90:68-185)
+// =====================================================================================================
+// interpolateParticleToNodesDensity  CIC mod_Scheme.f90:68-105 (NGP uses interpolateParticleToNodes, mod_Scheme.f90:79)
+static void interpolateParticleToNodesDensity(Species &p, const Domain &w, int t) {
+    if (w.scheme != 1) { interpolateParticleToNodes(p, w, t); return; }
+    const int Nx = w.Nx;
+    for (int j = 1; j <= p.N_p[t]; ++j) {
+        const double l = p.P(1, j, t);
+        const int lc = (int)l; const double d = l - (double)lc;
+        p.DN(lc, t) += (-d * d + d + 0.5);
+        const int lr = lc + 1, ll = lc - 1;
+        const double wl = 0.5 * (1.0 - d) * (1.0 - d), wr = 0.5 * d * d;
+        switch (w.bc[lr] - w.bc[lc]) {
+        case 0: p.DN(ll, t) += wl; p.DN(lr, t) += wr; break;
+        case -2: case -1: case -4: p.DN(lc, t) += wl; p.DN(lr, t) += wr; break;
+        case 2: case 1: case 4: p.DN(lc, t) += wr; p.DN(ll, t) += wl; break;
+        case -3: p.DN(Nx, t) += wl; p.DN(lr, t) += wr; break;
+        case 3: p.DN(ll, t) += wl; p.DN(1, t) += wr; break;
+        }
+    }
+}
+static void loadParticleDensity(Oracle &o, bool reset) {
+    const int T = o.world.T;
+#pragma omp parallel for schedule(static, 1)
+    for (int it = 1; it <= T; ++it)
+        for (auto &p : o.plist) {
+            if (reset) for (int i = 0; i <= o.world.Nx + 1; ++i) p.DN(i, it) = 0.0;
+            interpolateParticleToNodesDensity(p, o.world, it);
+        }
+}
+// the array WriteParticleDensity writes for species sp (out[0..Nx-1]); like the reference it leaves the reduced grid in densities(:,1)
+static void particleDensityArray(Oracle &o, int sp, double *out) {
+    Domain &w = o.world; Species &p = o.plist[sp];
+    const int Nx = w.Nx, Nh = w.Nh, T = w.T;
+    for (int i = 1; i <= Nx; ++i) {                       // SUM(densities(i, :), DIM=2) * w_p
+        double s = 0.0;
+        for (int t = 1; t <= T; ++t) s += p.DN(i, t);
+        p.DN(i, 1) = s * p.w_p;
+    }
+    auto D = [&](int i) -> double & { return p.DN(i, 1); };
+    dvec dens(Nx + 2, 0.0);
+    if (w.scheme == 0) {
+        if (w.bc[1] == 3) { D(1) = D(1) + D(Nx); D(Nx) = D(1); }
+        if (w.smooth) {
+            for (int j = 1; j <= Nx; ++j) {
+                switch (w.bc[j]) {
+                case 0: dens[j] = dens[j] + 0.25 * (D(j - 1) + 2.0 * D(j) + D(j + 1)); break;
+                case 1: case 4: case 2:
+                    if (j == 1) { dens[j] = dens[j] + 0.25 * (2.0 * D(1) + D(2)); dens[j + 1] = dens[j + 1] + 0.25 * D(1); }
+                    else { dens[j] = dens[j] + 0.25 * (2.0 * D(Nx) + D(Nh)); dens[j - 1] = dens[j - 1] + 0.25 * D(Nx); }
+                    break;
+                case 3: dens[j] = dens[j] + 0.25 * (D(Nh) + 2.0 * D(1) + D(2)); break;
+                }
+            }
+        } else {
+            for (int j = 1; j <= Nx; ++j) dens[j] = D(j);
+        }
+        switch (w.bc[1]) {
+        case 1: case 2: case 4: dens[1] = 2.0 * dens[1] / w.dx_dl[1]; break;
+        case 3: dens[1] = 2.0 * dens[1] / (w.dx_dl[1] + w.dx_dl[Nh]); break;
+        }
+        for (int j = 2; j <= Nh; ++j) dens[j] = 2.0 * dens[j] / (w.dx_dl[j - 1] + w.dx_dl[j]);
+        switch (w.bc[Nx]) {
+        case 1: case 2: case 4: dens[Nx] = 2.0 * dens[Nx] / w.dx_dl[Nh]; break;
+        case 3: dens[Nx] = dens[1]; break;
+        }
+    } else {
+        if (w.smooth) {
+            for (int j = 1; j <= Nx; ++j) {
+                switch (w.bc[j + 1] - w.bc[j]) {
+                case 0: dens[j] = 0.25 * (D(j - 1) + 2.0 * D(j) + D(j + 1)); break;
+                case -2: case -1: case -4: dens[j] = 0.25 * (D(2) + 3.0 * D(1)); break;
+                case 2: case 1: case 4: dens[j] = 0.25 * (D(Nx - 1) + 3.0 * D(Nx)); break;
+                case -3: dens[j] = 0.25 * (D(Nx) + 2.0 * D(1) + D(2)); break;
+                case 3: dens[j] = 0.25 * (D(1) + 2.0 * D(Nx) + D(Nx - 1)); break;
+                }
+            }
+            for (int j = 1; j <= Nx; ++j) D(j) = dens[j];
+        }
+        for (int j = 1; j <= Nx; ++j) dens[j] = D(j) / w.dx_dl[j];
+    }
+    for (int j = 1; j <= Nx; ++j) out[j - 1] = dens[j];
+}
+
+// =====================================================================================================
 // mod_particleInjection.f90 (the routines that consume the mover's delIdx / refIdx / refRecordIdx) + the samplers they use
 // =====================================================================================================
 // getMaxwellianSample  mod_BasicFunctions.f90:146-160
@@ -2381,6 +2466,8 @@ void orc_reflux_particles(void *h, double T_e, double T_i, int32_t *irand, doubl
     double sm = 0.0; for (int t = 1; t <= T; ++t) { irand[t - 1] = ir[t]; sm += en[t]; }
     *energyAdd = sm;
 }
+void orc_load_particle_density(void *h, int reset) { loadParticleDensity(*(Oracle *)h, reset != 0); }
+void orc_particle_density_array(void *h, int sp, double *out) { particleDensityArray(*(Oracle *)h, sp, out); }
 int orc_inject_at_boundary(void *h, double T_e, double del_t, int numLow, int numHigh, double injectionR, int32_t *irand) {
     Oracle *o = (Oracle *)h; const int T = o->world.T;
     std::vector<int32_t> ir(T + 1);

@@ -86,6 +86,7 @@ def lib(native=False):
         "orc_p_solve_potential": (i, [p, d, dp, dp]), "orc_p_solve_div_ampere_anderson": (None, [p, d]),
         "orc_p_total_PE": (d, [p, i]), "orc_p_gauss_error": (d, [p]), "orc_p_charge_error": (d, [p, dp, d]),
         "orc_p_aveJ": (d, [p]), "orc_reset_sweep_counters": (None, [p]),
+        "orc_load_particle_density": (None, [p, i]), "orc_particle_density_array": (None, [p, i, dp]),
         "orc_add_maxwellian_lost_particles": (i, [p, d, d, C.POINTER(C.c_int32), dp]),
         "orc_reflux_particles": (None, [p, d, d, C.POINTER(C.c_int32), dp]),
         "orc_inject_at_boundary": (i, [p, d, d, i, i, d, C.POINTER(C.c_int32)]),
@@ -245,6 +246,16 @@ class Oracle:
         o = np.zeros(5)
         self.L.orc_species_scalars(self.h, sp, _dp(o))
         return dict(mass=o[0], q=o[1], w_p=o[2], q_over_m=o[3], q_times_wp=o[4])
+
+    # ---- density diagnostic (mod_Scheme.f90: loadParticleDensity, WriteParticleDensity)
+    def loadParticleDensity(self, reset=True):
+        self.L.orc_load_particle_density(self.h, int(bool(reset)))
+
+    def particleDensityArray(self, sp):
+        """the array WriteParticleDensity writes for species sp (consumes the loaded densities, like the reference)"""
+        out = np.zeros(self.Nx)
+        self.L.orc_particle_density_array(self.h, sp, _dp(out))
+        return out
 
     # ---- mod_particleInjection.f90 (irand: the per-thread ran2 states, int32[T], advanced in place)
     def _ir(self, irand):
