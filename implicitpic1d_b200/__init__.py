@@ -12,6 +12,7 @@ Host-side mirror of the reference's Fortran modules; all numerical work happens 
     mod_targetParticle    -> targetParticle
     mod_NullCollision     -> nullCollision, readNullCollisionInputs
     mod_Scheme            -> scheme (loadParticleDensity, WriteParticleDensity)
+    mod_simulation        -> simulation (solveSimulation, solveSimulationFinalAverage, Histograms, writePhi)
     mod_particleInjection -> particle_injection (addMaxwellianLostParticles, refluxParticles, injectAtBoundary,
                              injectUniformFlux, maxwellianHeating, readInjectionInputs)
 """
@@ -24,7 +25,8 @@ from .nonlin_solvers import initializeSolver, solvePotential, solveDivAmpereAnde
 from .null_collision import targetParticle, nullCollision, readNullCollisionInputs
 from . import particle_injection
 from . import scheme
+from . import simulation
 from ._lib import IpicError, load as load_library, LIB_PATH
 
 __all__ = ["constants", "Domain", "Particle", "potentialSolver", "depositJ", "moveParticles", "allocateParticleMoverData",
-           "initializeSolver", "solvePotential", "solveDivAmpereAnderson", "funcNitsol", "SolverState", "solveJFNK", "nitsol", "NitsolInfo", "targetParticle", "nullCollision", "readNullCollisionInputs", "particle_injection", "scheme", "IpicError", "load_library", "LIB_PATH"]
+           "initializeSolver", "solvePotential", "solveDivAmpereAnderson", "funcNitsol", "SolverState", "solveJFNK", "nitsol", "NitsolInfo", "targetParticle", "nullCollision", "readNullCollisionInputs", "particle_injection", "scheme", "simulation", "IpicError", "load_library", "LIB_PATH"]

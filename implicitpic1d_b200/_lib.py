@@ -103,6 +103,8 @@ SIGNATURES = {
     "ipic_get_collision_stats": (_i, [_p, _i32, C.POINTER(CollisionStats)]),
     "ipic_reset_collision_stats": (_i, [_p, _i32]),
     "ipic_set_num_to_collide": (_i, [_p, _i32, _i64]),
+    "ipic_velocity_extrema": (_i, [_p, _i32, _dp]),
+    "ipic_velocity_histograms": (_i, [_p, _i32, _i32, _d, _d, _d, _dp, _dp]),
     "ipic_load_particle_density": (_i, [_p, _i32, _dp]),
     "ipic_set_injection_seed": (_i, [_p, C.c_uint64]),
     "ipic_add_maxwellian_lost_particles": (_i, [_p, _d, _d, _dp, C.POINTER(_i64)]),

@@ -388,6 +388,7 @@ int ipic_destroy(ipic_handle h) {
     delete static_cast<nitsol::Solver *>(c->nitsol_state);
     collisions_free(*c);
     injection_free(*c);
+    diagnostics_free(*c);
     for (auto &s : c->sp) { if (s.l) cudaFree(s.l); if (s.l2) cudaFree(s.l2); if (s.refl) cudaFree(s.refl); if (s.refList) cudaFree(s.refList); }
     double *dp[] = {c->d_grid, c->d_dx, c->d_hinv, c->d_phi, c->d_phi_f, c->d_rho, c->d_J, c->d_E, c->d_a, c->d_b, c->d_c, c->d_cp, c->d_m, c->d_pcr, c->d_work,
                     c->d_rho_i, c->d_scal, c->d_phi_k, c->d_res_k, c->d_norms, c->d_loss, c->d_Ef, c->d_Eh};
@@ -750,6 +751,20 @@ int ipic_get_total_momentum(ipic_handle h, int32_t sp, double *out3) {
     double m4[4]; RC(particle_moments(*c, sp, m4));
     for (int k = 0; k < 3; ++k) out3[k] = m4[k + 1] * c->sp[sp].w_p * c->sp[sp].mass;   // :215
     return IPIC_OK;
+}
+
+// ---- EEDF / velocity histograms of the averaging window (diagnostics.cu; mod_simulation.f90:437-500) -----------------------
+int ipic_velocity_extrema(ipic_handle h, int32_t sp, double *out3) {
+    CTX(h); SPECIES(sp);
+    if (!out3) return IPIC_ERR_ARG;
+    Timed t(*c, "diagnostics");
+    return velocity_extrema(*c, sp, out3);
+}
+int ipic_velocity_histograms(ipic_handle h, int32_t sp, int32_t binNumber, double VMax, double Emin, double EMax, double *VHist, double *EHist) {
+    CTX(h); SPECIES(sp);
+    if (!VHist || !EHist) return IPIC_ERR_ARG;
+    Timed t(*c, "diagnostics");
+    return velocity_histograms(*c, sp, binNumber, VMax, Emin, EMax, VHist, EHist);
 }
 
 // ---- null-collision MCC (collisions.cu) ---------------------------------------------------------------------

@@ -159,6 +159,8 @@ struct Ctx {
     // particle injection / refluxing / heating (injection.cu)
     double *d_inj = nullptr; long long cap_inj = 0;
     unsigned long long inj_seed = 0x1A2B3C4D5E6F7081ULL, inj_calls = 0;
+    // histogram / extrema scratch (diagnostics.cu)
+    unsigned long long *d_diag = nullptr; long long cap_diag = 0;
     // options
     int stay_min = 20;
     int transit_min = 12;
@@ -227,6 +229,11 @@ int inject_at_boundary(Ctx &c, double T_e, double T_i, double del_t, double numF
 int inject_uniform_flux(Ctx &c, double T_e, double T_i, double numFluxPart, long long *numInjected);
 int maxwellian_heating(Ctx &c, int sp, double compValue, double T_eV, long long *numHeated);
 void injection_free(Ctx &c);
+
+// ---- diagnostics.cu (mod_simulation.f90:437-500) -------------------------------------------------------------
+int velocity_extrema(Ctx &c, int sp, double out3[3]);
+int velocity_histograms(Ctx &c, int sp, int bins, double VMax, double Emin, double EMax, double *VHist, double *EHist);
+void diagnostics_free(Ctx &c);
 
 // ---- launchers implemented in field.cu --------------------------------------------------------------
 int field_setup(Ctx &c);                                   // construct_diagMatrix + Thomas/PCR factor tables

@@ -21,6 +21,8 @@ class potentialSolver:
                                  bc.ctypes.data_as(_lib._ip), int(world.gridSmoothBool), device))
         _lib.check(L.ipic_init_solver(self._h, leftVoltage, rightVoltage, RF_frequency, timeCurrent))
         self._particles = []
+        # RF wall (bc 4): solver%RF_rad_frequency (NGP mod_potentialSolver.f90:62-84)
+        self.RF_rad_frequency = 2.0 * np.pi * float(RF_frequency) if 4 in (int(bc[0]), int(bc[-1])) else 0.0
 
     def close(self):
         if getattr(self, "_h", None):

@@ -209,6 +209,15 @@ int ipic_get_total_KE(ipic_handle h, int32_t species, double *out);
  * INT(l) == j (j < N_x, j <= numCells), in eV; 0 for an empty cell.  The Python mirror writes the reference's unformatted record. */
 int ipic_local_temperature(ipic_handle h, int32_t species, int32_t numCells, double *EHist);
 int ipic_get_total_momentum(ipic_handle h, int32_t species, double *out3);
+/* EEDF / velocity histograms of solveSimulationFinalAverage (SharedModules/src/mod_simulation.f90), per species, for THIS process's
+ * particles (a multi-GPU host combines ranks with max / min / sum, as the reference's OpenMP reduction clauses do over threads):
+ *   ipic_velocity_extrema     :437-452  out3 = { VMax = max |v_x|, EMax = max v^2, Emin = min(v^2, 0.1 e 2 / m) }
+ *   ipic_velocity_histograms  :480-500  ADDS one pass over the particles to VHist[2 * binNumber] (v_x on linear bins over [-VMax, VMax])
+ *                             and EHist[binNumber] (v^2 on logarithmic bins E_grid(i) = Emin exp((i-1) diffE), diffE = (ln EMax - ln Emin) /
+ *                             (binNumber - 1)), linear weights on the two neighbouring bins; binNumber 2..2048 (the reference uses 100) */
+int ipic_velocity_extrema(ipic_handle h, int32_t species, double *out3);
+int ipic_velocity_histograms(ipic_handle h, int32_t species, int32_t binNumber, double VMax, double Emin, double EMax, double *VHist,
+                             double *EHist);
 
 /* ---- null-collision Monte-Carlo collisions ---------------------------------------------------------
  * replaces: type(targetParticle) + constructor          SharedModules/src/mod_targetParticle.f90:13-37

@@ -2002,6 +2002,51 @@ static void particleDensityArray(Oracle &o, int sp, double *out) {
 }
 
 // =====================================================================================================
+// EEDF / velocity histograms of solveSimulationFinalAverage  mod_simulation.f90:433-500 (one species)
+// =====================================================================================================
+// extrema pass :437-452 ; out3 = {VMax, EMax, Emin}
+static void velocityExtrema(Oracle &o, int sp, double out3[3]) {
+    Species &p = o.plist[sp];
+    double VMax = 0.0, EMax = 0.0, Emin = 0.1 * e_c * 2.0 / p.mass;
+    for (int t = 1; t <= o.world.T; ++t)
+        for (int i = 1; i <= p.N_p[t]; ++i) {
+            double partV = std::fabs(p.P(2, i, t));
+            VMax = std::max(VMax, partV);
+            partV = p.P(2, i, t) * p.P(2, i, t) + p.P(3, i, t) * p.P(3, i, t) + p.P(4, i, t) * p.P(4, i, t);
+            EMax = std::max(EMax, partV);
+            Emin = std::min(Emin, partV);
+        }
+    out3[0] = VMax; out3[1] = EMax; out3[2] = Emin;
+}
+// histogram pass :480-500 ; VHist(2*binNumber), EHist(binNumber) 1-based in the reference, 0-based arrays here; E_grid :453-461
+static void velocityHistograms(Oracle &o, int sp, int binNumber, double VMax, double Emin, double EMax, double *VHist, double *EHist, double *E_grid) {
+    Species &p = o.plist[sp];
+    const double Emin_log = std::log(Emin);
+    const double diffE = (std::log(EMax) - std::log(Emin)) / (double)(float)(binNumber - 1);
+    if (E_grid) {
+        double partV = std::log(Emin);
+        for (int i = 1; i <= binNumber; ++i) { E_grid[i - 1] = std::exp(partV); partV = partV + diffE; }
+    }
+    for (int t = 1; t <= o.world.T; ++t)
+        for (int k = 1; k <= p.N_p[t]; ++k) {
+            double partV = p.P(2, k, t) * (2.0 * binNumber - 1) / 2.0 / VMax + binNumber + 0.5;
+            if (partV > 1 && partV < binNumber * 2) {
+                const int intPartV = (int)partV;
+                VHist[intPartV - 1] += (1.0 - (partV - intPartV));
+                VHist[intPartV] += partV - intPartV;
+            }
+            const double partE = p.P(2, k, t) * p.P(2, k, t) + p.P(3, k, t) * p.P(3, k, t) + p.P(4, k, t) * p.P(4, k, t);
+            if (partE > Emin && partE < EMax) {
+                partV = (std::log(partE) - Emin_log) / diffE + 1.0;
+                const int intPartV = (int)partV;
+                partV = partV - intPartV;
+                EHist[intPartV - 1] += (1.0 - partV);
+                EHist[intPartV] += partV;
+            }
+        }
+}
+
+// =====================================================================================================
 // mod_particleInjection.f90 (the routines that consume the mover's delIdx / refIdx / refRecordIdx) + the samplers they use
 // =====================================================================================================
 // getMaxwellianSample  mod_BasicFunctions.f90:146-160
@@ -2465,6 +2510,10 @@ void orc_reflux_particles(void *h, double T_e, double T_i, int32_t *irand, doubl
     refluxParticles(*o, T_e, T_i, ir.data(), en.data());
     double sm = 0.0; for (int t = 1; t <= T; ++t) { irand[t - 1] = ir[t]; sm += en[t]; }
     *energyAdd = sm;
+}
+void orc_velocity_extrema(void *h, int sp, double *out3) { velocityExtrema(*(Oracle *)h, sp, out3); }
+void orc_velocity_histograms(void *h, int sp, int binNumber, double VMax, double Emin, double EMax, double *VHist, double *EHist, double *E_grid) {
+    velocityHistograms(*(Oracle *)h, sp, binNumber, VMax, Emin, EMax, VHist, EHist, E_grid);
 }
 void orc_load_particle_density(void *h, int reset) { loadParticleDensity(*(Oracle *)h, reset != 0); }
 void orc_particle_density_array(void *h, int sp, double *out) { particleDensityArray(*(Oracle *)h, sp, out); }

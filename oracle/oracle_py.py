@@ -86,6 +86,7 @@ def lib(native=False):
         "orc_p_solve_potential": (i, [p, d, dp, dp]), "orc_p_solve_div_ampere_anderson": (None, [p, d]),
         "orc_p_total_PE": (d, [p, i]), "orc_p_gauss_error": (d, [p]), "orc_p_charge_error": (d, [p, dp, d]),
         "orc_p_aveJ": (d, [p]), "orc_reset_sweep_counters": (None, [p]),
+        "orc_velocity_extrema": (None, [p, i, dp]), "orc_velocity_histograms": (None, [p, i, i, d, d, d, dp, dp, dp]),
         "orc_load_particle_density": (None, [p, i]), "orc_particle_density_array": (None, [p, i, dp]),
         "orc_add_maxwellian_lost_particles": (i, [p, d, d, C.POINTER(C.c_int32), dp]),
         "orc_reflux_particles": (None, [p, d, d, C.POINTER(C.c_int32), dp]),
@@ -246,6 +247,18 @@ class Oracle:
         o = np.zeros(5)
         self.L.orc_species_scalars(self.h, sp, _dp(o))
         return dict(mass=o[0], q=o[1], w_p=o[2], q_over_m=o[3], q_times_wp=o[4])
+
+    # ---- EEDF / velocity histograms (mod_simulation.f90:433-500)
+    def velocityExtrema(self, sp):
+        o = np.zeros(3)
+        self.L.orc_velocity_extrema(self.h, sp, _dp(o))
+        return o                                       # VMax, EMax, Emin
+
+    def velocityHistograms(self, sp, binNumber, VMax, Emin, EMax, VHist, EHist):
+        """adds one pass to VHist[2*binNumber], EHist[binNumber]; returns E_grid"""
+        E_grid = np.zeros(binNumber)
+        self.L.orc_velocity_histograms(self.h, sp, binNumber, VMax, Emin, EMax, _dp(VHist), _dp(EHist), _dp(E_grid))
+        return E_grid
 
     # ---- density diagnostic (mod_Scheme.f90: loadParticleDensity, WriteParticleDensity)
     def loadParticleDensity(self, reset=True):

@@ -50,3 +50,28 @@ def test_density_accumulates_without_reset():
     o.loadParticleDensity(False)
     two = o.particleDensityArray(0)
     assert np.allclose(two, 2.0 * one, rtol=1e-13, atol=0.0)
+
+
+def test_oracle_velocity_histograms_known_answers():
+    """mod_simulation.f90:433-500 restated: every particle strictly inside a range puts total weight 1 on two neighbouring bins;
+    the v_x histogram of a Maxwellian load is symmetric and its second moment is v_th^2; the energy grid is logarithmic from
+    Emin to EMax; Emin never exceeds 0.1 eV (0.1 e 2 / m)"""
+    from oracle import oracle_py as op
+    d = DECKS["ngp_rf"]
+    o = build_oracle(d)
+    bins = 100
+    VMax, EMax, Emin = o.velocityExtrema(0)
+    m = o.species_scalars(0)["mass"]
+    assert Emin <= 0.1 * op.e * 2.0 / m and EMax > Emin and VMax > 0
+    VH, EH = np.zeros(2 * bins), np.zeros(bins)
+    E_grid = o.velocityHistograms(0, bins, VMax, Emin, EMax, VH, EH)
+    N = int(o.N_p(0).sum())
+    assert N - 2 <= VH.sum() <= N and N - 2 <= EH.sum() <= N              # the extreme particles sit on the open ends
+    assert E_grid[0] == np.exp(np.log(Emin)) and E_grid[-1] == pytest.approx(EMax, rel=1e-12)
+    assert np.allclose(np.diff(np.log(E_grid)), (np.log(EMax) - np.log(Emin)) / (bins - 1), rtol=1e-10)
+    centers = (np.arange(1, 2 * bins + 1) - bins - 0.5) * 2.0 * VMax / (2.0 * bins - 1)     # v_x of bin k (inverse of :483)
+    mean = np.sum(VH * centers) / VH.sum()
+    var = np.sum(VH * centers ** 2) / VH.sum()
+    vth2 = d["T_e"] * op.e / m
+    assert abs(mean) < 5.0 * np.sqrt(vth2 / N)
+    assert var / vth2 == pytest.approx(1.0, abs=0.03)
