@@ -152,6 +152,50 @@ class nullCollision:
         _lib.check(_lib.load().ipic_generate_collision(solver._h, self._set, float(del_t)))
         self._refresh()
 
+    # ---- diagnostics files (mod_NullCollision.f90:564-632); collisions are numbered in the constructor's order (largest sigma*v first)
+    def _order(self):
+        """the constructor's permutation (:55-70): ascending stable sort of max(sigma * v), reversed"""
+        v = np.sqrt(2.0 * self._energy * K.e / self.reducedMass)
+        svmax = np.max(self._sigma * v[:, None], axis=0)
+        return np.argsort(svmax, kind="stable")[::-1]
+
+    def _dir(self, particleList, targetParticleList, dirName):
+        return os.path.join(dirName, "BinaryCollisions", "%s_on_%s" % (particleList[self.reactantsIndx[0] - 1].name,
+                                                                      targetParticleList[self.reactantsIndx[1] - 1].name))
+
+    def writeCollisionCrossSection(self, part, dirName):
+        """:564-577: raw stream files of energyArray and sigmaArray (column-major, constructor order)"""
+        os.makedirs(os.path.join(dirName, "CrossSections"), exist_ok=True)
+        self._energy.astype("<f8").tofile(os.path.join(dirName, "CrossSections", "IncidentPart_%s_energy.dat" % part.name))
+        np.asfortranarray(self._sigma[:, self._order()]).astype("<f8").T.tofile(os.path.join(dirName, "CrossSections", "IncidentPart_%s_sigma.dat" % part.name))
+
+    def writeCollisionProperties(self, particleList, targetParticleList, dirName):
+        """:579-609"""
+        d = self._dir(particleList, targetParticleList, dirName)
+        os.makedirs(d, exist_ok=True)
+        order = self._order()
+        with open(os.path.join(d, "CollisionProperties.dat"), "w") as f:
+            f.write("Coll #, collType, E_thres (eV), maxSigma (m^2), EatMaxSigma (eV)\n")
+            for i, j in enumerate(order):
+                k = int(np.argmax(self._sigma[:, j]))
+                f.write("%3d %3d %16.8E %16.8E %16.8E\n" % (i + 1, self._type[j], self._thr[j], self._sigma[k, j], self._energy[k]))
+        for i in range(self.numberCollisions):
+            with open(os.path.join(d, "CollisionDiag_%d.dat" % (i + 1)), "w") as f:
+                f.write("CollRatio, AveEnergyLoss (eV), AveIncidentEnergy (eV), P_loss(W/m^2), aveCollFreq (Hz/m^2)\n")
+
+    def writeCollisionDiag(self, particleList, targetParticleList, dirName, timeInterval):
+        """:611-632: one line per collision appended to its CollisionDiag_<i>.dat"""
+        d = self._dir(particleList, targetParticleList, dirName)
+        p = particleList[self.reactantsIndx[0] - 1]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            for i in range(self.numberCollisions):
+                n = float(self.totalAmountCollisions[i])
+                vals = (n / float(self.totalNumberCollidableParticles), self.totalEnergyLoss[i] * 0.5 / K.e / np.float64(n),
+                        self.totalIncidentEnergy[i] * p.mass * 0.5 / K.e / np.float64(n), self.totalEnergyLoss[i] * 0.5 * p.w_p / timeInterval,
+                        n * p.w_p / timeInterval)
+                with open(os.path.join(d, "CollisionDiag_%d.dat" % (i + 1)), "a") as f:
+                    f.write(" ".join("%16.8E" % v for v in vals) + "\n")
+
     def reset_totals(self):
         _lib.check(_lib.load().ipic_reset_collision_stats(self._solver._h, self._set))
         self._refresh()

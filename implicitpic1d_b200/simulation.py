@@ -119,6 +119,7 @@ def solveSimulation(st, solver, particleList, targetParticleList, nullCollisionL
     _bind_collisions(solver, targetParticleList, nullCollisionList)
     for nc in nullCollisionList:
         nc.reset_totals()
+        nc.writeCollisionProperties(particleList, targetParticleList, d)
     diagTimeDivision = (simulationTime - st.startSimulationTime) / float(st.numDiagnosticSteps)
     diagTime = diagTimeDivision + st.startSimulationTime
     sch.loadParticleDensity(particleList, world, True)
@@ -176,6 +177,8 @@ def solveSimulation(st, solver, particleList, targetParticleList, nullCollisionL
                 accumE[j][:] = 0.0
                 accumW[j][:] = 0.0
             st.inelasticEnergyLoss += _collision_loss(nullCollisionList, particleList)
+            for nc in nullCollisionList:
+                nc.writeCollisionDiag(particleList, targetParticleList, d, span)
             row = (st.currentTime + currDel_t, st.inelasticEnergyLoss / span, chargeTotal / span, energyLoss / span, Etotal, momentum,
                    st.gaussError, st.chargeError, st.energyError, SolverState(solver).iterNumPicard)
             gf.write(" ".join(es(x) for x in row[:9]) + " %4d\n" % row[9])

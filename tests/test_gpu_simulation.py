@@ -116,3 +116,29 @@ def test_final_average_with_argon_collisions_on_the_device(tmp_path):
     assert 7.0 < npass < 9.5
     assert read_record(os.path.join(str(tmp_path), "Temperature", "TempEnergy_e_average.dat")).size == 200
     solver.close()
+
+
+def test_solveSimulation_with_argon_collisions_writes_the_collision_diagnostics(tmp_path):
+    d = dict(scheme=0, Nx=65, L=0.025 / 4, n_ave=1.0e16, T_e=2.59, T_i=0.025, ppt=10000, T=4, bcL=1, bcR=4, Vl=0.0, Vr=250.0, rf=13.56e6,
+             smooth=True, frac=1.5, dt_deck=7.845352413230403e-12, eps_a=1e-4, m=10, beta=0.5, maxIter=100, ion_amu=39.948)
+    o = build_oracle(d, factor=2)
+    world, solver, plist = build_cuda_from_oracle(d, o)
+    plist[0].name, plist[1].name = "e", "Ar+"
+    tl = [ip.targetParticle("Ar", M_AR, 2.4e21, 300.0)]
+    ncs = ip.readNullCollisionInputs(["Ar_electron_table.dat"], plist, tl, collision_dir=DATA, seed=3)
+    del_t = deck_del_t(d)
+    st = sim.SimulationState(d["T_e"], d["T_i"], d["n_ave"], d["frac"], numDiagnosticSteps=2, directoryName=str(tmp_path), numThread=d["T"])
+    rows = sim.solveSimulation(st, solver, plist, tl, ncs, world, del_t, None, 8.0 * del_t)
+    assert len(rows) == 2 and all(r[1] > 0.0 for r in rows)                 # collision loss (W/m^2) over each diagnostic interval
+    for nc in ncs:
+        # the host-side permutation equals the device-side constructor order (mod_NullCollision.f90:55-70)
+        assert np.array_equal(nc._type[nc._order()], nc.collisionType)
+        assert np.array_equal(nc._thr[nc._order()], nc.energyThreshold)
+        cd = os.path.join(str(tmp_path), "BinaryCollisions", "e_on_Ar")
+        props = open(os.path.join(cd, "CollisionProperties.dat")).read().splitlines()
+        assert len(props) == 1 + nc.numberCollisions and int(props[1].split()[1]) == int(nc.collisionType[0])
+        for i in range(nc.numberCollisions):
+            lines = open(os.path.join(cd, "CollisionDiag_%d.dat" % (i + 1))).read().splitlines()
+            assert len(lines) == 3 and len(lines[1].split()) == 5
+        break
+    solver.close()
