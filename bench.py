@@ -392,40 +392,6 @@ def run_cuda_arm(args, w):
         ms_max, substeps_all = ms, float(substeps)
     value = substeps_all / (ms_max * 1e-3)
 
-    # ---- e2e_resident: the level-3 integration (INTEGRATION.md 3b) -- injection / MCC / diagnostics also run on the device, so the host
-    # never touches phaseSpace between steps; per step it pushes its field state and pulls the new fields and the mover's statistics
-    e2e_resident = None
-    if not args.no_e2e:
-        unk = "EField_f" if w["scheme"] == 2 else "phi_f"
-        res_steps = max(1, min(args.steps, args.e2e_steps))
-        barrier()
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        r0.record(stream)
-        sub3, h2d3, d2h3 = 0, 0, 0
-        phi_h, phi_f_h = solver.phi, getattr(solver, unk)
-        for _ in range(res_steps):
-            solver.phi = phi_h                                           # host -> device: phi, phi_f (pinned staging inside the library)
-            setattr(solver, unk, phi_f_h)
-            h2d3 += phi_h.nbytes + phi_f_h.nbytes
-            st = one_step()
-            sub3 += st.substeps
-            phi_h, phi_f_h, J_h = solver.phi, getattr(solver, unk), solver.J     # device -> host: fields + per-species move statistics
-            d2h3 += phi_h.nbytes + phi_f_h.nbytes + J_h.nbytes + len(plist) * C.sizeof(_lib.MoveStats)
-        r1.record(stream)
-        barrier()
-        ms3 = r0.elapsed_time(r1)
-        v3 = torch.tensor([ms3, float(sub3)], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            mx = v3.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-            sm = v3.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-            ms3_max, sub3_all = mx[0].item(), sm[1].item()
-        else:
-            ms3_max, sub3_all = ms3, float(sub3)
-        e2e_resident = {"value": sub3_all / (ms3_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d3 // res_steps, "d2h_bytes_per_step": d2h3 // res_steps,
-                        "steps": res_steps, "ms_per_step": ms3_max / res_steps,
-                        "path": "particles resident (injection / MCC / diagnostics on the device): ipic_set_field(phi, phi_f) -> ipic_solve_potential -> "
-                                "ipic_get_field(phi, phi_f, J) + ipic_get_move_stats"}
-
     # ---- e2e: the same step through the reference-facing call with HOST phase-space buffers (mod_particle.f90:23 layout) ----
     e2e = None
     if not args.no_e2e:
@@ -477,6 +443,41 @@ def run_cuda_arm(args, w):
             p.phaseSpace = None
         for ptr in host:
             L.ipic_host_free(ptr)
+
+    # ---- e2e_resident: the level-3 integration (INTEGRATION.md 3b) -- injection / MCC / diagnostics also run on the device, so the host
+    # never touches phaseSpace between steps; per step it pushes its field state and pulls the new fields and the mover's statistics
+    e2e_resident = None
+    if not args.no_e2e:
+        unk = "EField_f" if w["scheme"] == 2 else "phi_f"
+        res_steps = max(1, min(args.steps, args.e2e_steps))
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record(stream)
+        sub3, h2d3, d2h3 = 0, 0, 0
+        phi_h, phi_f_h = solver.phi, getattr(solver, unk)
+        for _ in range(res_steps):
+            solver.phi = phi_h                                           # host -> device: phi, phi_f (pinned staging inside the library)
+            setattr(solver, unk, phi_f_h)
+            h2d3 += phi_h.nbytes + phi_f_h.nbytes
+            st = one_step()
+            sub3 += st.substeps
+            phi_h, phi_f_h, J_h = solver.phi, getattr(solver, unk), solver.J     # device -> host: fields + per-species move statistics
+            d2h3 += phi_h.nbytes + phi_f_h.nbytes + J_h.nbytes + len(plist) * C.sizeof(_lib.MoveStats)
+        r1.record(stream)
+        barrier()
+        ms3 = r0.elapsed_time(r1)
+        v3 = torch.tensor([ms3, float(sub3)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            mx = v3.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = v3.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            ms3_max, sub3_all = mx[0].item(), sm[1].item()
+        else:
+            ms3_max, sub3_all = ms3, float(sub3)
+        e2e_resident = {"value": sub3_all / (ms3_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d3 // res_steps, "d2h_bytes_per_step": d2h3 // res_steps,
+                        "steps": res_steps, "ms_per_step": ms3_max / res_steps,
+                        "path": "particles resident (injection / MCC / diagnostics on the device): ipic_set_field(phi, phi_f) -> ipic_solve_potential -> "
+                                "ipic_get_field(phi, phi_f, J) + ipic_get_move_stats"}
+
 
     # ---- roofline of the dominant kernel (the depositJ push sweep) ----
     peak, peak_src = measured_peak_gbs()

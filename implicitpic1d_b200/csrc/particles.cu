@@ -1092,7 +1092,8 @@ __global__ void __launch_bounds__(256) k_local_temperature(const double *__restr
         const unsigned peers = __match_any_sync(FULL, cell);
         const int leader = __ffs(peers) - 1;
         double tot = 0.0;                                   // fixed order within the group: ascending lane
-        for (unsigned m = peers; m; m &= m - 1) tot += __shfl_sync(FULL, e, __ffs(m) - 1);
+        // the shuffles are synchronised over the GROUP (mask = peers): groups of different sizes run different trip counts
+        for (unsigned m = peers; m; m &= m - 1) tot += __shfl_sync(peers, e, __ffs(m) - 1);
         if (cell > 0 && lane == leader) { atomicAdd(sumV2 + cell - 1, tot); atomicAdd(count + cell - 1, (unsigned long long)__popc(peers)); }
     }
 }

@@ -512,6 +512,23 @@ def test_local_temperature_matches_oracle(name, tmp_path):
     solver.close()
 
 
+@pytest.mark.timeout(120)
+def test_local_temperature_on_cell_sorted_particles():
+    """cell-sorted input puts lanes of one warp into groups of DIFFERENT sizes (two or three cells per warp): the per-group lane sums of
+    k_local_temperature must synchronise over the group, not the warp (a full-mask shuffle inside the group loop dead-locks here).
+    Result against the oracle's on the same (unsorted) particles: the per-cell sums do not depend on the particle order beyond round-off."""
+    d = DECKS["ngp_rf"]
+    o = build_oracle(d)
+    world, solver, plist = build_cuda_from_oracle(d, o)
+    numCells = min(world.NumberXNodes, world.NumberXHalfNodes)
+    for sp, p in enumerate(plist):
+        _lib.check(_lib.load().ipic_sort_particles(solver._h, p._index))
+        Tg, To = p.localTemperature(numCells), o.localTemperature(sp, numCells)
+        assert np.array_equal(Tg == 0.0, To == 0.0)
+        np.testing.assert_allclose(Tg, To, rtol=1e-11, atol=0)
+    solver.close()
+
+
 def test_cell_sort_is_a_stable_sort():
     """ipic_sort_particles orders by cell -- by INT(l * sub), cells cut into sub = min(8, 65534 // (max(N_x, N_h) + 2)) slices -- and keeps
     the original order inside a slice, i.e. it equals numpy's stable argsort of that key: deterministic, which the seeded MCC relies on"""
