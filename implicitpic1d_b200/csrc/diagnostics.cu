@@ -10,6 +10,7 @@
 // bit-identical run to run and for any launch geometry.  Extrema are integer atomics on the bit patterns of non-negative doubles
 // (which order like the doubles).
 #include "ipic_common.cuh"
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -53,12 +54,15 @@ __global__ void __launch_bounds__(HIST_THREADS) k_velocity_extrema(const double 
 
 __global__ void __launch_bounds__(HIST_THREADS) k_velocity_histograms(const double *__restrict__ l, const double *__restrict__ vx,
                                                                       const double *__restrict__ vy, const double *__restrict__ vz, long long n,
-                                                                      int bins, double VMax, double Emin, double EMax, double Emin_log, double diffE,
+                                                                      int bins, int copies, double VMax, double Emin, double EMax, double Emin_log, double diffE,
                                                                       unsigned long long *ghist /* [2*bins] VHist, [bins] EHist */) {
+    // `copies` private histograms per CTA (warp w deposits into copy w % copies): the hot bins of a Maxwellian otherwise serialise every
+    // warp of the CTA on the same few shared-memory words
     extern __shared__ unsigned long long sh[];
-    for (int k = threadIdx.x; k < 3 * bins; k += HIST_THREADS) sh[k] = 0ull;
+    const int hb = 3 * bins;
+    for (int k = threadIdx.x; k < copies * hb; k += HIST_THREADS) sh[k] = 0ull;
     __syncthreads();
-    unsigned long long *vh = sh, *eh = sh + 2 * bins;       // 0-based: vh[k-1] = VHist(k)
+    unsigned long long *vh = sh + ((threadIdx.x >> 5) % copies) * hb, *eh = vh + 2 * bins;       // 0-based: vh[k-1] = VHist(k)
     const long long stride = (long long)gridDim.x * HIST_THREADS;
     for (long long i = (long long)blockIdx.x * HIST_THREADS + threadIdx.x; i < n; i += stride) {
         if (l[i] < 0.0) continue;
@@ -81,8 +85,11 @@ __global__ void __launch_bounds__(HIST_THREADS) k_velocity_histograms(const doub
         }
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < 3 * bins; k += HIST_THREADS)
-        if (sh[k]) atomicAdd(ghist + k, sh[k]);
+    for (int k = threadIdx.x; k < hb; k += HIST_THREADS) {
+        unsigned long long t = 0ull;
+        for (int c = 0; c < copies; ++c) t += sh[c * hb + k];
+        if (t) atomicAdd(ghist + k, t);
+    }
 }
 
 static int diag_scratch(Ctx &c, size_t words, unsigned long long **out) {
@@ -137,8 +144,10 @@ int velocity_histograms(Ctx &c, int sp, int bins, double VMax, double Emin, doub
         IPIC_CUDA(cudaFuncSetAttribute(k_velocity_histograms, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * HIST_MAX_BINS * 8));
         cfgs[c.device & 63] = true;
     }
+    const int copies = std::max(1, std::min(HIST_THREADS / 32, (3 * HIST_MAX_BINS) / (3 * bins)));     // as many as fit the 48 KB of the largest histogram
     c.launches += 1;
-    k_velocity_histograms<<<c.num_sms * 2, HIST_THREADS, (size_t)3 * bins * 8, c.stream>>>(S.l, S.vx, S.vy, S.vz, S.n, bins, VMax, Emin, EMax, Emin_log, diffE, d);
+    k_velocity_histograms<<<c.num_sms * 2, HIST_THREADS, (size_t)copies * 3 * bins * 8, c.stream>>>(S.l, S.vx, S.vy, S.vz, S.n, bins, copies, VMax, Emin, EMax, Emin_log,
+                                                                                                    diffE, d);
     IPIC_CUDA(cudaGetLastError());
     std::vector<unsigned long long> h((size_t)3 * bins);
     IPIC_CUDA(cudaMemcpyAsync(h.data(), d, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));

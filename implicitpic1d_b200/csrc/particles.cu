@@ -932,36 +932,43 @@ __global__ void __launch_bounds__(1024, 1) k_deposit_rho(const double *__restric
     G.gacc = acc;
     limb_grid_zero(G, ng);
     __syncthreads();
+    // four independent loads in flight per thread before the (warp-synchronous) deposits: one load per trip left the kernel latency-bound
+    constexpr int U = 4;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long nround = ((n + stride - 1) / stride) * stride;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
-        bool has = false;
-        double l = 0.0;
-        if (i < n) { l = lpos[i]; has = (l >= 0.0); }
-        const int lc = (int)l;
-        const double d = l - (double)lc;
-        if (SCHEME == 0) {
-            warp_deposit2<2>(G, has, lc, fx_from_double(1.0 - d), fx_from_double(d), lane);
-        } else {
-            // quadratic-spline weights with wall folding
-            double wc = -d * d + d + 0.5, wl = 0.5 * (1.0 - d) * (1.0 - d), wr = 0.5 * d * d;
-            int il = lc - 1, ir = lc + 1;
-            bool hl = has, hr = has;
-            if (has) {
-                const int bv = bc[lc + 1] - bc[lc];
-                switch (bv) {
-                case 0: break;
-                case -1: case -4: wc += DENS ? wl : -wl; hl = false; break;    // Dirichlet to the left
-                case 1: case 4: wc += DENS ? wr : -wr; hr = false; break;      // Dirichlet to the right
-                case -2: wc += wl; hl = false; break;                          // Neumann to the left
-                case 2: wc += wr; hr = false; break;                           // Neumann to the right
-                case -3: il = Nx; break;                                        // periodic to the left
-                case 3: ir = 1; break;                                          // periodic to the right
+    const long long nround = ((n + U * stride - 1) / (U * stride)) * (U * stride);
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < nround; i0 += U * stride) {
+        double lv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const long long i = i0 + u * stride; lv[u] = (i < n) ? lpos[i] : -1.0; }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool has = (lv[u] >= 0.0);
+            const double l = has ? lv[u] : 0.0;
+            const int lc = (int)l;
+            const double d = l - (double)lc;
+            if (SCHEME == 0) {
+                warp_deposit2<2>(G, has, lc, fx_from_double(1.0 - d), fx_from_double(d), lane);
+            } else {
+                // quadratic-spline weights with wall folding
+                double wc = -d * d + d + 0.5, wl = 0.5 * (1.0 - d) * (1.0 - d), wr = 0.5 * d * d;
+                int il = lc - 1, ir = lc + 1;
+                bool hl = has, hr = has;
+                if (has) {
+                    const int bv = bc[lc + 1] - bc[lc];
+                    switch (bv) {
+                    case 0: break;
+                    case -1: case -4: wc += DENS ? wl : -wl; hl = false; break;    // Dirichlet to the left
+                    case 1: case 4: wc += DENS ? wr : -wr; hr = false; break;      // Dirichlet to the right
+                    case -2: wc += wl; hl = false; break;                          // Neumann to the left
+                    case 2: wc += wr; hr = false; break;                           // Neumann to the right
+                    case -3: il = Nx; break;                                        // periodic to the left
+                    case 3: ir = 1; break;                                          // periodic to the right
+                    }
                 }
+                warp_deposit<2>(G, has, lc, fx_from_double(wc), lane);
+                warp_deposit<2>(G, hl, il, fx_from_double(wl), lane);
+                warp_deposit<2>(G, hr, ir, fx_from_double(wr), lane);
             }
-            warp_deposit<2>(G, has, lc, fx_from_double(wc), lane);
-            warp_deposit<2>(G, hl, il, fx_from_double(wl), lane);
-            warp_deposit<2>(G, hr, ir, fx_from_double(wr), lane);
         }
     }
     __syncthreads();

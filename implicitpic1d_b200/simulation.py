@@ -209,6 +209,20 @@ def _lib_e():
     return K.e
 
 
+def _allreduce_np(dist, arr, op=None):
+    """in-place all-reduce of a float64 numpy array over the ranks (NCCL needs device tensors, gloo takes host ones)"""
+    import torch
+    t = torch.from_numpy(arr)
+    op = dist.ReduceOp.SUM if op is None else op
+    if dist.get_backend() == "nccl":
+        g = t.cuda()
+        dist.all_reduce(g, op=op)
+        arr[...] = g.cpu().numpy()
+    else:
+        dist.all_reduce(t, op=op)
+    return arr
+
+
 # ---- EEDF / velocity histograms of the final averaging window (:433-510) -------------------------------------------------
 class Histograms:
     """VMax, EMax, Emin, E_grid, diffE per species and the accumulating VHist(2*binNumber), EHist(binNumber)"""
@@ -223,10 +237,8 @@ class Histograms:
             _lib.check(L.ipic_velocity_extrema(p._solver._h, p._index, o.ctypes.data_as(_lib._dp)))
             self.VMax[j], self.EMax[j], self.Emin[j] = o
         if dist is not None:                                  # ranks combine like the OpenMP reduction(max / min) clauses (:442)
-            import torch
             for arr, op in ((self.VMax, dist.ReduceOp.MAX), (self.EMax, dist.ReduceOp.MAX), (self.Emin, dist.ReduceOp.MIN)):
-                t = torch.from_numpy(arr)
-                dist.all_reduce(t, op=op)
+                _allreduce_np(dist, arr, op)
         self.diffE = (np.log(self.EMax) - np.log(self.Emin)) / float(np.float32(self.binNumber - 1))
         self.E_grid = np.zeros((n, self.binNumber))
         for j in range(n):
@@ -249,10 +261,7 @@ class Histograms:
         K_e = _lib_e()
         VH, EH = self.VHist, self.EHist
         if dist is not None:
-            import torch
-            VH, EH = VH.copy(), EH.copy()
-            for arr in (VH, EH):
-                dist.all_reduce(torch.from_numpy(arr))
+            VH, EH = _allreduce_np(dist, VH.copy()), _allreduce_np(dist, EH.copy())
         os.makedirs(os.path.join(directoryName, "Temperature"), exist_ok=True)
         for j, p in enumerate(particleList):
             _record(os.path.join(directoryName, "Temperature", "Temp_%s_average.dat" % p.name), VH[j], np.array([self.VMax[j]]))

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 import implicitpic1d_b200 as ip
-from implicitpic1d_b200 import _lib, distributed as D
+from implicitpic1d_b200 import _lib, distributed as D, scheme as sch, simulation as sim
 from implicitpic1d_b200.domain import readWorld
 from common import DECKS, build_oracle, build_cuda_from_oracle, deck_del_t, relerr
 
@@ -32,6 +32,11 @@ def main():
         r1 = ip.solvePotential(s1, p1, w1, del_t, del_t, del_t, 0.0)
         st1 = ip.SolverState(s1)
         phi_single = s1.phi_f
+        # diagnostics of the moved particles on one GPU: density dump arrays, histogram extrema and bins
+        sch.loadParticleDensity(p1, w1, True)
+        dens_single = [sch.particleDensityArray(p, w1) for p in p1]
+        h1 = sim.Histograms(p1, 100)
+        h1.accumulate(p1)
         s1.close()
         # sharded
         world_dom = readWorld(d["scheme"], d["Nx"], d["L"], d.get("gridType", 0), d.get("del_x", 0.0), d["bcL"], d["bcR"], int(d["smooth"]),
@@ -57,12 +62,22 @@ def main():
         r = ip.solvePotential(solver, plist, world_dom, del_t, del_t, del_t, 0.0)
         st = ip.SolverState(solver)
         bit_phi = np.array_equal(solver.phi_f, phi_single)
+        # the density load all-reduces its integer grid inside the library: every rank holds the single-GPU arrays bit for bit;
+        # histogram extrema / bins are combined over ranks by the host (max, min, sum) and equal the single-GPU ones
+        sch.loadParticleDensity(plist, world_dom, True)
+        bit_dens = all(np.array_equal(sch.particleDensityArray(p, world_dom), dens_single[k]) for k, p in enumerate(plist))
+        h = sim.Histograms(plist, 100, dist=dist)
+        h.accumulate(plist)
+        VH = h.VHist.copy(); EH = h.EHist.copy()
+        sim._allreduce_np(dist, VH); sim._allreduce_np(dist, EH)
+        bit_hist = (np.array_equal(h.VMax, h1.VMax) and np.array_equal(h.EMax, h1.EMax) and np.array_equal(h.Emin, h1.Emin)
+                    and np.allclose(VH, h1.VHist, rtol=0, atol=1e-6) and np.allclose(EH, h1.EHist, rtol=0, atol=1e-6))
         n_local = sum(p.count() for p in plist)
         n_all = D.allreduce_scalars(dist, [n_local], device="cuda")[0]
-        good = (e_or < 1e-12) and bit and bit_phi and (st.iterNumPicard == st1.iterNumPicard)
+        good = (e_or < 1e-12) and bit and bit_phi and (st.iterNumPicard == st1.iterNumPicard) and bit_dens and bit_hist
         ok = ok and good
-        print("rank %d %-12s J vs oracle %.2e | J bitwise == 1-GPU: %s | phi_f bitwise: %s | iters %d (1-GPU %d) | particles after move %d"
-              % (rank, name, e_or, bit, bit_phi, st.iterNumPicard, st1.iterNumPicard, int(n_all)), flush=True)
+        print("rank %d %-12s J vs oracle %.2e | J bitwise == 1-GPU: %s | phi_f bitwise: %s | iters %d (1-GPU %d) | density bitwise: %s | histograms: %s | particles after move %d"
+              % (rank, name, e_or, bit, bit_phi, st.iterNumPicard, st1.iterNumPicard, bit_dens, bit_hist, int(n_all)), flush=True)
         solver.close()
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

@@ -66,6 +66,51 @@ def test_two_rank_J_allreduce_matches_single_process(deck):
     assert out["err"] < 1e-12, out["err"]       # same tolerance as the GPU path: floating-point order differs, integers would not
 
 
+def _worker_diag(rank, world, port, out):
+    """the rank combination of the time loop's diagnostics (simulation.Histograms): histogram extrema by max / min, bins by sum -- what
+    the reference's OpenMP reduction(max: VMax, EMax) reduction(min: Emin) reduction(+: VHist, EHist) clauses do over threads
+    (mod_simulation.f90:442, :479), here over ranks with the oracle's per-shard results"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from implicitpic1d_b200 import simulation as sim
+        d = DECKS["ngp_rf"]
+        o = build_oracle(d)
+        full_ex = o.velocityExtrema(0)
+        VH_full, EH_full = np.zeros(200), np.zeros(100)
+        o.velocityHistograms(0, 100, full_ex[0], full_ex[2], full_ex[1], VH_full, EH_full)
+        mine = D.shard_slabs(d["T"], world, rank)
+        n = o.N_p(0)
+        keep = np.zeros_like(n)
+        keep[mine] = n[mine]
+        o.set_N_p(0, keep)
+        ex = o.velocityExtrema(0)
+        VMax, EMax, Emin = np.array([ex[0]]), np.array([ex[1]]), np.array([ex[2]])
+        sim._allreduce_np(dist, VMax, dist.ReduceOp.MAX)
+        sim._allreduce_np(dist, EMax, dist.ReduceOp.MAX)
+        sim._allreduce_np(dist, Emin, dist.ReduceOp.MIN)
+        VH, EH = np.zeros(200), np.zeros(100)
+        o.velocityHistograms(0, 100, VMax[0], Emin[0], EMax[0], VH, EH)
+        sim._allreduce_np(dist, VH)
+        sim._allreduce_np(dist, EH)
+        if rank == 0:
+            out["extrema"] = bool(VMax[0] == full_ex[0] and EMax[0] == full_ex[1] and Emin[0] == full_ex[2])
+            out["hist"] = max(float(np.max(np.abs(VH - VH_full))), float(np.max(np.abs(EH - EH_full))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_histogram_reductions_match_single_process():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_diag, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert out["extrema"]
+    assert out["hist"] < 1e-9                    # sums of weights in [0, 1]: only the summation order differs
+
+
 def test_shard_helpers():
     for T in (1, 2, 7, 32):
         for w in (1, 2, 3, 8):
