@@ -286,3 +286,56 @@ def test_reinjection_keeps_the_electron_count_over_a_time_loop():
         assert plist[1].count() == Ni
         t += del_t
     solver.close()
+
+
+def test_injection_edge_cases_and_error_codes():
+    """no-op and error behaviour of the entry points: nothing to reflux without a Neumann wall, nothing injected at zero flux, the heated
+    fraction at compValue 0 and 1, argument errors as status codes with a message (never a crash, never a silent fallback)"""
+    import ctypes as C
+    L = _lib.load()
+    d = DECKS["ngp_rf"]                                            # Dirichlet / RF walls: the mover records no reflections
+    o = build_oracle(d, factor=2)
+    world, solver, plist = build_cuda_from_oracle(d, o)
+    del_t = deck_del_t(d)
+    ip.moveParticles(solver, plist, world, del_t)
+    before = [alive(p) for p in plist]
+    e0 = pinj.energyAddColl
+    pinj.refluxParticles(plist, d["T_e"], d["T_i"], None, world)
+    assert pinj.energyAddColl == e0
+    pinj.setInjectionInputs(injection=True, flux=0.0, del_t=del_t, w_p=plist[0].w_p, numThread=d["T"])
+    assert pinj.injectAtBoundary(plist, d["T_e"], d["T_i"], None, world, del_t) == 0
+    pinj.setInjectionInputs(uniformInjection=True, flux=0.0, del_t=del_t, w_p=plist[0].w_p, numThread=d["T"])
+    assert pinj.injectUniformFlux(plist, d["T_e"], d["T_i"], None, world) == 0
+    pinj.setInjectionInputs(heating=True, fractionFreqHeating=1.0)
+    assert pinj.maxwellianHeating(plist[0], None, 0.0, d["T_e"], 1.0, 1.0) == 0
+    for b, p in zip(before, plist):
+        assert np.array_equal(alive(p), b)
+    N = plist[0].count()
+    assert pinj.maxwellianHeating(plist[0], None, 1.0, d["T_e"], 1.0, 1.0) == N      # R in (0, 1) < compValue = 1 for every particle
+    pinj.setInjectionInputs()
+    # argument errors
+    n = C.c_int64()
+    out = np.zeros(3)
+    assert L.ipic_maxwellian_heating(solver._h, 7, 0.1, 1.0, C.byref(n)) == _lib.ERR_ARG
+    assert L.ipic_velocity_extrema(solver._h, -1, out.ctypes.data_as(_lib._dp)) == _lib.ERR_ARG
+    VH, EH = np.zeros(4), np.zeros(2)
+    assert L.ipic_velocity_histograms(solver._h, 0, 1, 1.0, 1.0, 2.0, VH.ctypes.data_as(_lib._dp), EH.ctypes.data_as(_lib._dp)) == _lib.ERR_ARG
+    assert L.ipic_velocity_histograms(solver._h, 0, 2, 0.0, 1.0, 2.0, VH.ctypes.data_as(_lib._dp), EH.ctypes.data_as(_lib._dp)) == _lib.ERR_ARG
+    assert b"histograms" in L.ipic_last_error()
+    assert L.ipic_load_particle_density(solver._h, 0, None) == _lib.ERR_ARG
+    solver.close()
+    # a one-species context cannot re-inject electron-ion pairs
+    world1 = ip.domain.readWorld(0, 33, 0.05, 0, 0.0, 1, 1, 0, 2.0, 1e15)
+    s1 = ip.potentialSolver(world1, 0.0, 0.0, 0.0, 0.0)
+    p1 = ip.Particle(op.m_e, -op.e, 1.0, 0, 16, "e", 1)
+    p1.set_phase_space(np.zeros((1, 16, 4)), np.zeros(1, dtype=np.int32))
+    s1._bind([p1])
+    en = C.c_double()
+    assert L.ipic_add_maxwellian_lost_particles(s1._h, 1.0, 1.0, C.byref(en), C.byref(n)) == _lib.ERR_ARG
+    # an empty species: density zeros, extrema at their initial values
+    dens = np.ones(33)
+    _lib.check(L.ipic_load_particle_density(s1._h, 0, dens.ctypes.data_as(_lib._dp)))
+    assert not dens.any()
+    _lib.check(L.ipic_velocity_extrema(s1._h, 0, out.ctypes.data_as(_lib._dp)))
+    assert out[0] == 0.0 and out[1] == 0.0 and out[2] == 0.1 * op.e * 2.0 / op.m_e
+    s1.close()
