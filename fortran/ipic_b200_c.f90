@@ -231,6 +231,46 @@ module ipic_b200_c
             real(c_double), intent(out) :: densities(*)
             integer(c_int) :: rc
         end function
+        function ipic_velocity_extrema(handle, species, out3) bind(c, name="ipic_velocity_extrema") result(rc)
+            ! mod_simulation.f90:437-452: out3 = (VMax, EMax, Emin) of this process's particles
+            import :: c_ptr, c_int, c_int32_t, c_double
+            type(c_ptr), value :: handle
+            integer(c_int32_t), value :: species
+            real(c_double), intent(out) :: out3(3)
+            integer(c_int) :: rc
+        end function
+        function ipic_velocity_histograms(handle, species, binNumber, VMax, Emin, EMax, VHist, EHist) &
+                bind(c, name="ipic_velocity_histograms") result(rc)
+            ! mod_simulation.f90:480-500: adds one pass to VHist(2*binNumber), EHist(binNumber)
+            import :: c_ptr, c_int, c_int32_t, c_double
+            type(c_ptr), value :: handle
+            integer(c_int32_t), value :: species, binNumber
+            real(c_double), value :: VMax, Emin, EMax
+            real(c_double), intent(in out) :: VHist(*), EHist(*)
+            integer(c_int) :: rc
+        end function
+        function ipic_local_temperature(handle, species, numCells, EHist) bind(c, name="ipic_local_temperature") result(rc)
+            ! writeLocalTemperature (mod_particle.f90:251-283): the array it writes
+            import :: c_ptr, c_int, c_int32_t, c_double
+            type(c_ptr), value :: handle
+            integer(c_int32_t), value :: species, numCells
+            real(c_double), intent(out) :: EHist(*)
+            integer(c_int) :: rc
+        end function
+        function ipic_get_total_KE(handle, species, res) bind(c, name="ipic_get_total_KE") result(rc)
+            import :: c_ptr, c_int, c_int32_t, c_double
+            type(c_ptr), value :: handle
+            integer(c_int32_t), value :: species
+            real(c_double), intent(out) :: res
+            integer(c_int) :: rc
+        end function
+        function ipic_get_total_momentum(handle, species, res3) bind(c, name="ipic_get_total_momentum") result(rc)
+            import :: c_ptr, c_int, c_int32_t, c_double
+            type(c_ptr), value :: handle
+            integer(c_int32_t), value :: species
+            real(c_double), intent(out) :: res3(3)
+            integer(c_int) :: rc
+        end function
         function ipic_generate_collision(handle, collision_set, del_t) bind(c, name="ipic_generate_collision") result(rc)
             import :: c_ptr, c_int, c_int32_t, c_double
             type(c_ptr), value :: handle
