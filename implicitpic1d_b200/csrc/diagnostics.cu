@@ -34,8 +34,8 @@ __global__ void __launch_bounds__(HIST_THREADS) k_velocity_extrema(const double 
     double vmax = 0.0, emax = 0.0, emin = __longlong_as_double((long long)out[2]);
     const long long stride = (long long)gridDim.x * HIST_THREADS;
     for (long long i = (long long)blockIdx.x * HIST_THREADS + threadIdx.x; i < n; i += stride) {
-        if (l[i] < 0.0) continue;
-        const double x = vx[i], y = vy[i], z = vz[i];
+        const double ll = l[i], x = vx[i], y = vy[i], z = vz[i];
+        if (ll < 0.0) continue;
         const double e2 = v2_exact(x, y, z);
         vmax = fmax(vmax, fabs(x)); emax = fmax(emax, e2); emin = fmin(emin, e2);
     }
@@ -65,8 +65,8 @@ __global__ void __launch_bounds__(HIST_THREADS) k_velocity_histograms(const doub
     unsigned long long *vh = sh + ((threadIdx.x >> 5) % copies) * hb, *eh = vh + 2 * bins;       // 0-based: vh[k-1] = VHist(k)
     const long long stride = (long long)gridDim.x * HIST_THREADS;
     for (long long i = (long long)blockIdx.x * HIST_THREADS + threadIdx.x; i < n; i += stride) {
-        if (l[i] < 0.0) continue;
-        const double x = vx[i], y = vy[i], z = vz[i];
+        const double ll = l[i], x = vx[i], y = vy[i], z = vz[i];      // one memory round trip: the velocities of a dead particle are read and dropped
+        if (ll < 0.0) continue;
         const double partV = x * (2.0 * bins - 1) / 2.0 / VMax + bins + 0.5;      // :483, in the reference's operation order
         if (partV > 1.0 && partV < (double)(bins * 2)) {
             const int ip = (int)partV;

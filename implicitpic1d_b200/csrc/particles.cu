@@ -1080,28 +1080,50 @@ int particle_moments(Ctx &c, int sp, double out4[4]) {
 
 // writeLocalTemperature (mod_particle.f90:251-283): per cell INT(l) < N_x, the sum of v^2 and the particle count.  Sorted input puts a
 // warp inside one or two cells, so the lanes of a cell are combined with a match before one atomic per (warp, cell).
-__global__ void __launch_bounds__(256) k_local_temperature(const double *__restrict__ l, const double *__restrict__ vx, const double *__restrict__ vy,
+__global__ void __launch_bounds__(512) k_local_temperature(const double *__restrict__ l, const double *__restrict__ vx, const double *__restrict__ vy,
                                                            const double *__restrict__ vz, long long n, int Nx, int numCells, double *sumV2,
                                                            unsigned long long *count) {
+    // Every CTA owns one contiguous range of the particle arrays and a private copy of the per-cell sums in shared memory: cell-sorted
+    // input keeps a CTA inside a few cells, so the global atomics drop from one per (warp, cell) -- all running warps on the same few
+    // addresses -- to one per (CTA, touched cell).
+    extern __shared__ __align__(16) unsigned char lt_smem[];
+    double *s_sum = reinterpret_cast<double *>(lt_smem);
+    unsigned *s_cnt = reinterpret_cast<unsigned *>(s_sum + numCells);
+    for (int k = threadIdx.x; k < numCells; k += blockDim.x) { s_sum[k] = 0.0; s_cnt[k] = 0u; }
+    __syncthreads();
     const int lane = threadIdx.x & 31;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long nround = (n + 31) / 32 * 32;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+    const long long chunk = ((n + gridDim.x - 1) / gridDim.x + 31) / 32 * 32;       // multiple of 32: whole warps stay inside one range
+    const long long first = (long long)blockIdx.x * chunk, last = min(n, first + chunk);
+    for (long long i = first + threadIdx.x; i - lane < last; i += blockDim.x) {
         int cell = 0;
         double e = 0.0;
-        if (i < n) {
-            const double ll = l[i];
+        if (i < last) {
+            // all four loads issued together (the velocities of a dead or out-of-range particle are read and dropped): one memory round
+            // trip per trip instead of two
+            const double ll = l[i], a = vx[i], b = vy[i], c = vz[i];
             if (ll >= 0.0) {
                 const int idx = (int)ll;
-                if (idx < Nx && idx >= 1 && idx <= numCells) { cell = idx; const double a = vx[i], b = vy[i], c = vz[i]; e = a * a + b * b + c * c; }
+                if (idx < Nx && idx >= 1 && idx <= numCells) { cell = idx; e = a * a + b * b + c * c; }
             }
         }
         const unsigned peers = __match_any_sync(FULL, cell);
         const int leader = __ffs(peers) - 1;
-        double tot = 0.0;                                   // fixed order within the group: ascending lane
-        // the shuffles are synchronised over the GROUP (mask = peers): groups of different sizes run different trip counts
-        for (unsigned m = peers; m; m &= m - 1) tot += __shfl_sync(peers, e, __ffs(m) - 1);
-        if (cell > 0 && lane == leader) { atomicAdd(sumV2 + cell - 1, tot); atomicAdd(count + cell - 1, (unsigned long long)__popc(peers)); }
+        double tot;
+        if (peers == FULL) {                                // the usual case on sorted input: the whole warp in one cell, fixed xor tree
+            tot = e;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
+        } else {
+            tot = 0.0;                                      // fixed order within the group: ascending lane
+            // the shuffles are synchronised over the GROUP (mask = peers): groups of different sizes run different trip counts
+            for (unsigned m = peers; m; m &= m - 1) tot += __shfl_sync(peers, e, __ffs(m) - 1);
+        }
+        if (cell > 0 && lane == leader) { atomicAdd(s_sum + cell - 1, tot); atomicAdd(s_cnt + cell - 1, (unsigned)__popc(peers)); }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < numCells; k += blockDim.x) {
+        const unsigned cn = s_cnt[k];
+        if (cn) { atomicAdd(sumV2 + k, s_sum[k]); atomicAdd(count + k, (unsigned long long)cn); }
     }
 }
 
@@ -1113,8 +1135,15 @@ int local_temperature(Ctx &c, int sp, int numCells, double *sumV2_host, long lon
     IPIC_CUDA(cudaMemsetAsync(d_sum, 0, (size_t)numCells * sizeof(double), c.stream));
     IPIC_CUDA(cudaMemsetAsync(d_cnt, 0, (size_t)numCells * sizeof(unsigned long long), c.stream));
     if (s.n > 0) {
+        const size_t smem = (size_t)numCells * (sizeof(double) + sizeof(unsigned));
+        static bool cfgs[64] = {};
+        if (!cfgs[c.device & 63]) {
+            IPIC_CUDA(cudaFuncSetAttribute(k_local_temperature, cudaFuncAttributeMaxDynamicSharedMemorySize, (MAX_GRID_SMEM + 2) * 12));
+            cfgs[c.device & 63] = true;
+        }
+        // a CTA's range must hold < 2^32 particles for the 32-bit shared counters: n < 2^32 per GPU is already required by the sort
         c.launches += 1;
-        k_local_temperature<<<c.num_sms * 8, 256, 0, c.stream>>>(s.l, s.vx, s.vy, s.vz, s.n, c.Nx, numCells, d_sum, d_cnt);
+        k_local_temperature<<<c.num_sms * (smem <= 56 * 1024 ? 4 : 2), 512, smem, c.stream>>>(s.l, s.vx, s.vy, s.vz, s.n, c.Nx, numCells, d_sum, d_cnt);
         IPIC_CUDA(cudaGetLastError());
     }
     IPIC_CUDA(cudaMemcpyAsync(sumV2_host, d_sum, (size_t)numCells * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
