@@ -497,6 +497,14 @@ def run_cuda_arm(args, w):
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": 16.0 * units, "avg_launch_ms": dep_ms / max(dep_launches, 1),
                 "per_species_ms": {"both": t_pair / max(n_pair, 1)} if paired else {"electrons": t_dep0 / max(n_dep0, 1), "ions": t_dep1 / max(n_dep1, 1)},
                 "kernel_share_of_step": dep_ms / max(ms, 1e-9)}
+    # the mover proper (moveParticles: k_push<*, move>, one launch per species per step): 32 B per particle (read l, v_x; write l, v_x)
+    if t_move > 0:
+        mv = 32.0 * (n_e + n_i) * args.steps / (t_move * 1e-3) / 1e9
+        roofline["move_kernel"] = {"kernel": "k_push<%s,move> (moveParticles, one launch per species per step)" % kname, "achieved": mv, "peak": peak,
+                                   "unit": "GB/s", "frac": mv / peak, "algorithmic_bytes_per_step": 32.0 * (n_e + n_i), "ms_per_step": t_move / args.steps}
+    if not paired and n_dep1 > 0:
+        ion = 16.0 * n_i / (t_dep1 / n_dep1 * 1e-3) / 1e9                  # the ion sweeps (s = 1 sub-step per particle) are the bytes-bound launches
+        roofline["ion_sweeps"] = {"achieved": ion, "peak": peak, "unit": "GB/s", "frac": ion / peak, "avg_launch_ms": t_dep1 / n_dep1}
     # second bound of the same kernel: the sub-step loop of the electrons is FP64 work, not bytes.  One face-to-face crossing is 14 FP64 + 15 other
     # instructions per warp; FP64 instructions issue every other cycle on sm_100 (scripts/micro/fp64_tput.cu), and the loop in isolation at 8 warps
     # per sub-partition runs at 46.5 cycles per crossing (scripts/micro/transit_bench.cu) -- that is the floor quoted here.
