@@ -271,3 +271,33 @@ def test_collisional_time_loop_moments_match_oracle():
         ke_g, ke_o = plist[s].getTotalKE() / ng, o.getTotalKE(s) / no
         assert abs(ke_g - ke_o) < 1e-2 * ke_o, (s, ke_g, ke_o)
     solver.close()
+
+
+def test_library_constructor_matches_the_reference_run_log():
+    """the library's nullCollision constructor (collision_set_create) on the He table of the reference's default decks reproduces what
+    the REAL reference binary printed (OpenMP/NGP/src/output.txt -> tests/golden/reference_run_logs.json): max sigma*v to the digits
+    printed, reduced masses, collision order by descending max sigma*v"""
+    import json
+    from implicitpic1d_b200 import constants as K
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_run_logs.json")))["ngp"]
+    m_ion, m_He = 4.002602 * K.m_amu - K.m_e, 4.002602 * K.m_amu
+    world = readWorld(0, 33, 0.05, 0, 0.0, 1, 1, 0, 4.0, 1e15)
+    solver = ip.potentialSolver(world, 0.0, 0.0, 0.0, 0.0)
+    plist = []
+    for nm, m, q in (("e", K.m_e, -K.e), ("He+", m_ion, K.e)):
+        p = ip.Particle(m, q, 1.0, 0, 8, nm, 1)
+        p.set_phase_space(np.zeros((1, 8, 4)), np.zeros(1, dtype=np.int32))
+        plist.append(p)
+    solver._bind(plist)
+    tl = [ip.targetParticle("He", m_He, g["target"]["density"], g["target"]["temperature"])]
+    ncs = ip.readNullCollisionInputs(["turner_benchmark_he_electron_table.dat"], plist, tl, collision_dir=DATA)
+    assert len(ncs) == 2
+    for t in tl:
+        t._bind(solver)
+    for nc, ref in zip(ncs, g["nullCollisions"]):
+        nc._bind(solver)
+        assert nc.sigmaVMax == pytest.approx(ref["sigmaVMax"], rel=5e-15)
+        assert nc.collisionType.tolist() == [c["collisionType"] for c in ref["collisions"]]
+        assert nc.energyThreshold.tolist() == [c["energyThreshold"] for c in ref["collisions"]]
+        assert nc.lengthArrays == ref["lengthArrays"]
+    solver.close()
