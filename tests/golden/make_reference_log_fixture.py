@@ -62,9 +62,10 @@ def parse(path):
         sets.append(s)
     out["nullCollisions"] = sets
     m = re.search(r"Absolute error:\s*" + NUM + r"\s*\n\s*Relative error:\s*" + NUM, txt)
-    out["eps_a"], out["eps_r"] = float(m.group(1)), float(m.group(2))
-    out["m_Anderson"] = first(txt, "Anderson number m is:", int)
-    out["Beta_k"] = first(txt, "Relaxation parameter is:")
+    if m:                                                  # older logs print the solver inputs differently
+        out["eps_a"], out["eps_r"] = float(m.group(1)), float(m.group(2))
+        out["m_Anderson"] = first(txt, "Anderson number m is:", int)
+        out["Beta_k"] = first(txt, "Relaxation parameter is:")
     # the diagnostic dumps: particle counts as the plasma relaxes (statistical: the reference seeds from the clock)
     out["electrons_at_dumps"] = [int(x) for x in re.findall(r"Number of electrons is:\s*(\d+)", txt)]
     out["ions_at_dumps"] = [int(x) for x in re.findall(r"Number of ions is:\s*(\d+)", txt)]
@@ -72,7 +73,9 @@ def parse(path):
 
 
 if __name__ == "__main__":
-    data = dict(ngp=parse(os.path.join(REF, "NGP/src/output.txt")), cic=parse(os.path.join(REF, "CIC/src/output.txt")))
+    # the third log (left in the NGP_Periodic source directory) is another bounded NGP run, on 2001 nodes
+    data = dict(ngp=parse(os.path.join(REF, "NGP/src/output.txt")), cic=parse(os.path.join(REF, "CIC/src/output.txt")),
+                ngp_2001=parse(os.path.join(REF, "NGP_Periodic/src/output.txt")))
     with open(os.path.join(HERE, "reference_run_logs.json"), "w") as f:
         json.dump(data, f, indent=1)
     print(json.dumps(data["ngp"], indent=1)[:1500])

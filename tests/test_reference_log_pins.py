@@ -21,7 +21,7 @@ TABLE = "turner_benchmark_he_electron_table.dat"
 P15 = 2e-15          # a value printed with 15-16 significant digits
 
 
-@pytest.mark.parametrize("tree", ["ngp", "cic"])
+@pytest.mark.parametrize("tree", ["ngp", "cic", "ngp_2001"])
 def test_startup_constants_match_the_reference_log(tree):
     g = LOGS[tree]
     # constants.f90:106-117: plasmaFreqTemp = SQRT(n_ave e^2 / m_e / eps_0); the log prints del_t * plasmaFreqTemp
@@ -40,12 +40,12 @@ def test_startup_constants_match_the_reference_log(tree):
         assert abs(p["mean_KE_eV"] - 1.5 * T) < 5.0 * np.sqrt(1.5) * T / np.sqrt(p["macroparticles"])
 
 
-@pytest.mark.parametrize("tree", ["ngp", "cic"])
+@pytest.mark.parametrize("tree", ["ngp", "cic", "ngp_2001"])
 def test_grid_spacing_matches_the_reference_log(tree):
     """'smallest delX' = MINVAL(dx_dl) of the uniform grid (NGP mod_domain.f90:104-110, CIC :103-110): the rounding of the node positions
     shows in the 13th digit (6.699999999999762E-005, not 6.7E-005), so this pins the construction order of the grid, not just L / N"""
     g = LOGS[tree]
-    scheme = 0 if tree == "ngp" else 1
+    scheme = 1 if tree == "cic" else 0
     world = readWorld(scheme, g["NumberXNodes"], g["L_domain"], g["gridType"], 0.0, g["bcL"], g["bcR"], 1, g["T_e"], g["n_ave"])
     assert world.NumberXHalfNodes == g["NumberXHalfNodes"]
     assert float(np.min(world.dx_dl)) == pytest.approx(g["smallest_delX"], rel=P15)
@@ -60,7 +60,7 @@ def test_null_collision_sets_match_the_reference_log():
     (turner_benchmark_he_electron_table.dat holds the e + He and the He+ + He reactions): two reactant pairs, merged energy axes of 773
     and 101 points, reduced masses, max sigma*v and the constructor's collision order as the Fortran program printed them"""
     g = LOGS["ngp"]
-    assert LOGS["cic"]["nullCollisions"] == g["nullCollisions"]                 # both trees print the same sets
+    assert LOGS["cic"]["nullCollisions"] == g["nullCollisions"] == LOGS["ngp_2001"]["nullCollisions"]      # every logged run prints the same sets
     m_ion, m_He = 4.002602 * K.m_amu - K.m_e, 4.002602 * K.m_amu
     # (1) the oracle's reader + constructor
     o = op.Oracle(op.NGP, 33, 0.05, T=1)
