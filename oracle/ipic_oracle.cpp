@@ -12,7 +12,12 @@
 // compiler, Intel-only modules, MKL) and seeds its RNG from the OS.  The
 // oracle is pinned instead on the reference's own acceptance invariants
 // (main.f90:93-114: energy error, Gauss error, charge-continuity error) and on
-// analytic known-answer tests (tests/test_oracle_*.py).
+// analytic known-answer tests (tests/test_oracle_*.py).  The only outputs of
+// the real binary available -- the start-up lines of the run logs it ships
+// (OpenMP/{NGP,CIC,NGP_Periodic}/src/output.txt: time step, grid spacing,
+// species constants, null-collision sets) -- ARE pinned, to the digits printed
+// (tests/golden/reference_run_logs.json, tests/test_reference_log_pins.py);
+// the mover / deposition / solver results stay unpinned.
 //
 // Conventions: arrays are 1-based like the Fortran (index 0 is padding) so
 // that every loop bound and stencil reads like the file:line it restates.
