@@ -54,6 +54,9 @@ struct FieldArgs {
     double beta;
     int diag_which;
     const double *xin; double *fout;
+    // residual norm straight into pinned host memory (UVA: the pinned mirror is device-addressable): value, then a sequence number the
+    // host spins on -- no D2H copy, no driver synchronisation on the critical path of a nonlinear iteration
+    double *h_norm; unsigned long long *h_seq; unsigned long long seq;
 };
 
 // 1-based accessors so that every stencil reads like the reference line it restates
@@ -471,7 +474,14 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
             part += r * r;
         }
         const double nrm = sqrt(block_sum(part));
-        if (threadIdx.x == 0) { A.norms[index - 1] = nrm; A.scal[0] = nrm; }
+        if (threadIdx.x == 0) {
+            A.norms[index - 1] = nrm; A.scal[0] = nrm;
+            if (A.h_seq) {
+                *reinterpret_cast<volatile double *>(A.h_norm) = nrm;
+                __threadfence_system();
+                *reinterpret_cast<volatile unsigned long long *>(A.h_seq) = A.seq;
+            }
+        }
         __syncthreads();
         PH(5);
     }
@@ -995,9 +1005,24 @@ int field_anderson_step(Ctx &c, int i, int phase, double del_t, int *status, dou
     else if (phase == 1) ops = fj | am | OP_AND_RESID;
     else if (phase == 2) ops = OP_AND_MIX | he;
     else ops = he;
+    // h_scal[48] receives the norm, h_scal[49] the sequence number of this launch
+    volatile unsigned long long *h_seq = reinterpret_cast<volatile unsigned long long *>(c.h_scal + 49);
+    const bool flag = c.norm_flag && phase <= 1;
+    if (flag) { A.h_norm = c.h_scal + 48; A.h_seq = reinterpret_cast<unsigned long long *>(c.h_scal + 49); A.seq = ++c.norm_seq; }
     int rc = run_field(c, A, ops);
     if (rc) return rc;
-    if (phase <= 1) {
+    if (flag) {
+        // spin on the sequence number; the stream is polled now and then so that a failed launch cannot hang the host
+        for (unsigned spins = 1;; ++spins) {
+            if (*h_seq == A.seq) break;
+            if ((spins & 0x3FFF) == 0) {
+                const cudaError_t q = cudaStreamQuery(c.stream);
+                if (q == cudaSuccess) { if (*h_seq == A.seq) break; set_error("k_field finished without publishing the residual norm"); return IPIC_ERR_CUDA; }
+                if (q != cudaErrorNotReady) { set_error(std::string("k_field: ") + cudaGetErrorString(q)); return IPIC_ERR_CUDA; }
+            }
+        }
+        *norm = *reinterpret_cast<volatile double *>(c.h_scal + 48);
+    } else if (phase <= 1) {
         IPIC_CUDA(cudaMemcpyAsync(c.h_scal, c.d_scal, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
         IPIC_CUDA(cudaStreamSynchronize(c.stream));
         *norm = c.h_scal[0];

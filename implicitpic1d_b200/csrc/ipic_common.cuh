@@ -171,6 +171,9 @@ struct Ctx {
     int tile_order = 1;           // 1 = stride-permuted tile order, 0 = in array order
     int push_blocks = 0;          // 0 = one CTA per SM
     int lazy_compaction = 0;
+    int norm_flag = 1;            // 1 = k_field publishes the residual norm into pinned host memory and the host spins on a sequence number;
+                                  // 0 = D2H copy + cudaStreamSynchronize per nonlinear iteration
+    unsigned long long norm_seq = 0;
     // multi-GPU
     void *nccl_comm = nullptr; int nranks = 1, rank = 0;
     // timing
