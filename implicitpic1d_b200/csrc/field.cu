@@ -57,6 +57,7 @@ struct FieldArgs {
     // residual norm straight into pinned host memory (UVA: the pinned mirror is device-addressable): value, then a sequence number the
     // host spins on -- no D2H copy, no driver synchronisation on the critical path of a nonlinear iteration
     double *h_norm; unsigned long long *h_seq; unsigned long long seq;
+    unsigned long long *counters;   // [nsp][8]: slot 6 of a species is the tile counter of its push launch, zeroed by the half-E op that precedes a sweep
 };
 
 // 1-based accessors so that every stencil reads like the reference line it restates
@@ -572,6 +573,7 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
 
     // ---------------- makeHalfTimeEField (+ push tables): NGP :392-406 ; CIC :333-366, Picard :92-94 ----------------
     if (ops & OP_HALF_E) {
+        if (A.counters && threadIdx.x < A.nsp) A.counters[(size_t)threadIdx.x * 8 + 6] = 0ull;      // tile schedulers of the sweeps that follow
         if (A.scheme == 0) {
             for (int i = 1 + threadIdx.x; i <= Nh; i += FT) s0[i - 1] = 0.5 * (PHIF(i) + PHI(i) - PHIF(i + 1) - PHI(i + 1));
             __syncthreads();
@@ -643,6 +645,7 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
     PH(9);
     // EField_half = 0.5 (EField + EField_f) (NGP_Periodic/src/mod_particleMover.f90:72) + push tables
     if (ops & OP_P_HALF_E) {
+        if (A.counters && threadIdx.x < A.nsp) A.counters[(size_t)threadIdx.x * 8 + 6] = 0ull;      // tile schedulers of the sweeps that follow
         for (int i = threadIdx.x; i < Nh; i += FT) A.Eh[i] = 0.5 * (A.E[i] + A.Ef[i]);
         __syncthreads();
         for (int s = 0; s < A.nsp; ++s) {
@@ -809,6 +812,7 @@ static FieldArgs make_args(Ctx &c) {
     A.grid = c.d_grid; A.dx = c.d_dx; A.hinv = c.d_hinv; A.bc = c.d_bc;
     A.phi = c.d_phi; A.phi_f = c.d_phi_f; A.rho = c.d_rho; A.J = c.d_J; A.E = c.d_E;
     A.a = c.d_a; A.b = c.d_b; A.c = c.d_c; A.cp = c.d_cp; A.m = c.d_m; A.pcr = c.d_pcr;
+    A.counters = c.d_counters;
     A.work = c.d_work; A.scal = c.d_scal; A.rho_i = c.d_rho_i; A.acc = c.d_acc; A.tab = c.d_tab; A.ttab = c.d_ttab;
     for (int s = 0; s < A.nsp && s < NSP_MAX; ++s) { A.qw[s] = c.sp[s].q_times_wp; A.qm[s] = c.sp[s].q_over_m; }
     A.rho_const = c.rho_const; A.RF_voltage = c.RF_voltage;
@@ -828,10 +832,14 @@ static int run_field(Ctx &c, const FieldArgs &A, unsigned ops) {
     size_t &configured = configured_dev[c.device & 63];
     if (smem > configured) {
         IPIC_CUDA(cudaFuncSetAttribute(k_field, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // the same shared-memory / L1 split as the push kernels it alternates with (particles.cu): a different carve-out makes every
+        // push -> field -> push transition re-partition the SMs
+        IPIC_CUDA(cudaFuncSetAttribute(k_field, cudaFuncAttributePreferredSharedMemoryCarveout, 52));
         configured = smem;
     }
     c.launches += 1; k_field<<<1, FT, smem, c.stream>>>(A, ops);
     IPIC_CUDA(cudaGetLastError());
+    if (ops & (OP_HALF_E | OP_P_HALF_E)) c.tile_zero_mask = ~0u;      // every species' tile counter is zero behind this launch
 #ifdef IPIC_FIELD_PHASES
     {
         long long h[16];

@@ -174,6 +174,8 @@ struct Ctx {
     int norm_flag = 1;            // 1 = k_field publishes the residual norm into pinned host memory and the host spins on a sequence number;
                                   // 0 = D2H copy + cudaStreamSynchronize per nonlinear iteration
     unsigned long long norm_seq = 0;
+    unsigned tile_zero_mask = 0;  // bit s set: species s' tile counter was zeroed on the stream by the last half-E op and not consumed yet, so the
+                                  // push launch skips its own memset (one stream operation less between two kernels)
     // multi-GPU
     void *nccl_comm = nullptr; int nranks = 1, rank = 0;
     // timing

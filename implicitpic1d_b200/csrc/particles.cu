@@ -795,6 +795,7 @@ static int launch_push_pair_v(Ctx &c, const PushArgs &A, const PushArgs &B) {
     }
     IPIC_CUDA(cudaMemsetAsync(A.tile_counter, 0, sizeof(unsigned), c.stream));
     IPIC_CUDA(cudaMemsetAsync(B.tile_counter, 0, sizeof(unsigned), c.stream));
+    c.tile_zero_mask = 0;
     const int blocks = c.push_blocks > 0 ? c.push_blocks : c.num_sms;
     const int wb = std::min(PUSH_WARPS - 1, std::max(1, c.pair_warps));
     c.launches += 1; k_push_pair<SCHEME><<<blocks, PUSH_THREADS, smem, c.stream>>>(A, B, wb);
@@ -812,7 +813,11 @@ static int launch_push_v(Ctx &c, const PushArgs &A) {
         IPIC_CUDA(cudaFuncSetAttribute(k_push<SCHEME, MOVE>, cudaFuncAttributePreferredSharedMemoryCarveout, 52));
         configured[c.device & 63] = true;
     }
-    IPIC_CUDA(cudaMemsetAsync(A.tile_counter, 0, sizeof(unsigned), c.stream));
+    {
+        const int sp = (int)((A.counters - c.d_counters) / 8);
+        if (c.tile_zero_mask & (1u << sp)) c.tile_zero_mask &= ~(1u << sp);        // zeroed by the half-E op in front of this sweep
+        else IPIC_CUDA(cudaMemsetAsync(A.tile_counter, 0, sizeof(unsigned), c.stream));
+    }
     const int blocks = c.push_blocks > 0 ? c.push_blocks : c.num_sms;
     c.launches += 1; k_push<SCHEME, MOVE><<<blocks, PUSH_THREADS, smem, c.stream>>>(A);
     IPIC_CUDA(cudaGetLastError());
