@@ -2,7 +2,6 @@
 cell sort, density load, local temperature, KE / momentum reduction, velocity extrema + histograms, Maxwellian heating,
 re-injection of lost particles -- each with its algorithmic bytes and the fraction of the measured HBM peak.
 usage (GPU box): python scripts/aux_ops_bench.py [particles_per_species] > profiles/rN_aux_ops_c5.txt"""
-import ctypes as C
 import json
 import os
 import sys
@@ -12,7 +11,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 import implicitpic1d_b200 as ip
-from implicitpic1d_b200 import _lib, constants as K, particle_injection as pinj, scheme as sch, simulation as sim
+from implicitpic1d_b200 import _lib, constants as K, particle_injection as pinj, simulation as sim
 from implicitpic1d_b200.domain import readWorld
 import bench
 
