@@ -174,6 +174,13 @@ module ipic_b200_c
             integer(c_int64_t), intent(out) :: n
             integer(c_int) :: rc
         end function
+        function ipic_get_ref_record_counts(handle, species, refIdx, numThread) bind(c, name="ipic_get_ref_record_counts") result(rc)
+            import :: c_ptr, c_int, c_int32_t
+            type(c_ptr), value :: handle
+            integer(c_int32_t), value :: species, numThread
+            integer(c_int32_t), intent(out) :: refIdx(*)
+            integer(c_int) :: rc
+        end function
         function ipic_initialize_solver(handle, eps_a, eps_r, solverType, m_Anderson, Beta_k, maxIter) &
                 bind(c, name="ipic_initialize_solver") result(rc)
             import :: c_ptr, c_int, c_double

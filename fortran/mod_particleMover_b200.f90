@@ -110,8 +110,9 @@ contains
         ! the mover's outputs (mod_particleMover.f90:162-270): moved and compacted phaseSpace, N_p, loss sums, reflux bookkeeping, counters
         type(Particle), intent(in out) :: particleList(:)
         type(ipic_move_stats) :: st
-        integer :: j, k, iThread
-        integer(c_int64_t) :: nRef, slabEnd
+        integer :: i, j, k, iThread
+        integer(c_int64_t) :: nRef, slabStart
+        integer(c_int32_t) :: refCount(numThread)
         integer(c_int32_t), allocatable :: refGlobal(:)
         integer(c_int64_t) :: nTotal
         do j = 1, size(particleList)
@@ -135,20 +136,25 @@ contains
             if (st%refIdx > 0) then
                 allocate(refGlobal(st%refIdx))
                 call ipic_check(ipic_get_ref_record(ipic_h, j - 1, refGlobal, int(st%refIdx, c_int64_t), nRef), 'ipic_get_ref_record')
-                if (particlesStayOnDevice) nRef = 0      ! the device-side refluxing reads the list where it is; refIdx keeps the total
-                if (particlesStayOnDevice) particleList(j)%refIdx(1) = int(st%refIdx, int32)
-                iThread = 1
-                slabEnd = particleList(j)%N_p(1)
-                do k = 1, int(min(nRef, st%refIdx))
-                    do while (refGlobal(k) >= slabEnd .and. iThread < numThread)
-                        iThread = iThread + 1
-                        slabEnd = slabEnd + particleList(j)%N_p(iThread)
+                if (particlesStayOnDevice) then
+                    ! the device-side refluxing reads the list where it is; refIdx keeps the total
+                    particleList(j)%refIdx(1) = int(st%refIdx, int32)
+                else
+                ! refIdx(T) comes from the library (the slab each reflection was recorded in); the list splits in that order, and an
+                ! entry is turned into the slab's 1-based index by subtracting the slab's first global index
+                call ipic_check(ipic_get_ref_record_counts(ipic_h, j - 1, refCount, numThread), 'ipic_get_ref_record_counts')
+                k = 0
+                slabStart = 0
+                do iThread = 1, numThread
+                    particleList(j)%refIdx(iThread) = refCount(iThread)
+                    do i = 1, refCount(iThread)
+                        k = k + 1
+                        if (i <= size(particleList(j)%refRecordIdx, 1) .and. k <= nRef) &
+                            particleList(j)%refRecordIdx(i, iThread) = int(refGlobal(k) - slabStart + 1, int32)
                     end do
-                    particleList(j)%refIdx(iThread) = particleList(j)%refIdx(iThread) + 1
-                    if (particleList(j)%refIdx(iThread) <= size(particleList(j)%refRecordIdx, 1)) &
-                        particleList(j)%refRecordIdx(particleList(j)%refIdx(iThread), iThread) = &
-                            int(refGlobal(k) - (slabEnd - particleList(j)%N_p(iThread)) + 1, int32)
+                    slabStart = slabStart + particleList(j)%N_p(iThread)
                 end do
+                end if
                 deallocate(refGlobal)
             end if
             particleList(j)%wallLoss = 0

@@ -80,6 +80,7 @@ SIGNATURES = {
     "ipic_get_move_stats": (_i, [_p, _i32, C.POINTER(MoveStats)]),
     "ipic_get_deposit_substeps": (_i, [_p, _i32, C.POINTER(_i64)]),
     "ipic_get_ref_record": (_i, [_p, _i32, _ip, _i64, C.POINTER(_i64)]),
+    "ipic_get_ref_record_counts": (_i, [_p, _i32, _ip, _i32]),
     "ipic_initialize_solver": (_i, [_p, _d, _d, _i, _i, _d, _i]),
     "ipic_solve_div_ampere_anderson": (_i, [_p, _d]),
     "ipic_solve_potential": (_i, [_p, _d, _dp, _dp, _d]),

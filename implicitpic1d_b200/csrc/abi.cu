@@ -155,6 +155,8 @@ static int move_all(Ctx &c, double del_t) {
             st.wallLoss[0] = (double)k[2]; st.wallLoss[1] = (double)k[3];
             st.delIdx = (int64_t)(k[2] + k[3]); st.refIdx = (int64_t)k[4];
             st.energyLoss[0] = st.energyLoss[1] = 0.0;
+            S.slab_off_prev = S.slab_off;
+            S.refSlabCount.assign(std::max<size_t>(1, S.slab_off.size() > 0 ? S.slab_off.size() - 1 : 1), 0);
             if (st.refIdx > 0) RC(collect_reflected(c, s));
             if (st.delIdx > 0) RC(compact_species(c, s));
             if (st.refIdx > 0) RC(map_reflected(c, s, st.delIdx > 0));
@@ -629,6 +631,15 @@ int ipic_get_ref_record(ipic_handle h, int32_t sp, int32_t *idx, int64_t cap, in
         IPIC_CUDA(cudaMemcpyAsync(idx, S.refList, (size_t)m * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
         IPIC_CUDA(cudaStreamSynchronize(c->stream));
     }
+    return IPIC_OK;
+}
+int ipic_get_ref_record_counts(ipic_handle h, int32_t sp, int32_t *refIdx, int32_t numThread) {
+    CTX(h); SPECIES(sp);
+    if (!refIdx || numThread < 1) return IPIC_ERR_ARG;
+    const SpeciesDev &S = c->sp[sp];
+    for (int t = 0; t < numThread; ++t) refIdx[t] = 0;
+    if ((int)S.refSlabCount.size() == numThread) for (int t = 0; t < numThread; ++t) refIdx[t] = S.refSlabCount[t];
+    else for (int v : S.refSlabCount) refIdx[0] += v;          // the host's slab split is not the device's: the total goes to slab 1
     return IPIC_OK;
 }
 // CIC carries its walls outside phi: boundPhi(2), RF_voltage, sourceTermVals(2) (CIC mod_potentialSolver.f90:19,69-85,458-478).  A host that

@@ -88,6 +88,8 @@ struct SpeciesDev {
     unsigned char *refl = nullptr; long long refl_cap = 0;      // per-particle flags written by the move kernel
     unsigned *refList = nullptr; long long refList_cap = 0;     // flagged indices, ascending; after the move: post-compaction indices
     long long nRef = 0;
+    std::vector<long long> slab_off_prev;  // thread-slab offsets before the last compaction: the slab a reflection was recorded in
+    std::vector<int> refSlabCount;         // refIdx(T): entries of refList per thread slab, in list order
 };
 
 // ---- null-collision MCC (collisions.cu) -------------------------------------------------------------

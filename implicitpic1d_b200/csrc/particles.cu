@@ -1343,7 +1343,8 @@ int compact_species(Ctx &c, int sp) {
 // refRecordIdx: the reference stores, per thread slab, the post-compaction index `i - delIdx` of every particle at its first
 // reflection in the step (mod_particleMover.f90:226-231), in particle order.  Here: the move kernel flags the particle, the flagged
 // (pre-compaction) indices are selected in ascending order, and after the stable compaction each is mapped to
-// tileOffset[tile] + (alive particles of the tile before it); a flagged particle that was absorbed later in the same step is dropped.
+// tileOffset[tile] + (alive particles of the tile before it); a flagged particle that was absorbed later in the same step keeps its
+// entry, which then names the slot of its successor, exactly as the reference's `i - delIdx` does.
 __global__ void k_map_reflected(const unsigned *__restrict__ pre, long long nref, const double *__restrict__ l_old,
                                 const long long *__restrict__ tileOffset, unsigned *post) {
     const int lane = threadIdx.x & 31;
@@ -1354,7 +1355,9 @@ __global__ void k_map_reflected(const unsigned *__restrict__ pre, long long nref
     unsigned cnt = 0;
     for (long long j = base + lane; j < (long long)i; j += 32) cnt += (l_old[j] >= 0.0) ? 1u : 0u;
     cnt = __reduce_add_sync(FULL, cnt);
-    if (lane == 0) post[w] = (l_old[i] >= 0.0) ? (unsigned)(tileOffset[tile] + cnt) : 0xffffffffu;
+    // A particle absorbed later in the same step keeps its entry: the reference stored `i - delIdx` at the reflection, which after the
+    // compaction is the slot of the next surviving particle (mod_particleMover.f90:226-231 records before the particle's fate is known).
+    if (lane == 0) post[w] = (unsigned)(tileOffset[tile] + cnt);
 }
 
 int collect_reflected(Ctx &c, int sp) {
@@ -1386,22 +1389,31 @@ int collect_reflected(Ctx &c, int sp) {
 
 int map_reflected(Ctx &c, int sp, bool compacted) {
     SpeciesDev &s = c.sp[sp];
-    if (s.nRef == 0 || !compacted) return IPIC_OK;            // nothing absorbed: indices are already final
+    const int nslab = std::max(1, (int)s.slab_off_prev.size() - 1);
+    s.refSlabCount.assign(nslab, 0);
+    if (s.nRef == 0) return IPIC_OK;
+    // refIdx(T): the slab every reflection was recorded in, from the pre-compaction indices (ascending, so the list splits in slab order)
+    std::vector<unsigned> hpre((size_t)s.nRef);
+    IPIC_CUDA(cudaMemcpyAsync(hpre.data(), s.refList, (size_t)s.nRef * sizeof(unsigned), cudaMemcpyDeviceToHost, c.stream));
+    IPIC_CUDA(cudaStreamSynchronize(c.stream));
+    if (s.slab_off_prev.size() < 2) s.refSlabCount[0] = (int)s.nRef;
+    else {
+        int t = 0;
+        for (unsigned i : hpre) {
+            while (t + 1 < nslab && (long long)i >= s.slab_off_prev[t + 1]) ++t;
+            s.refSlabCount[t] += 1;
+        }
+    }
+    if (!compacted) return IPIC_OK;                            // nothing absorbed: indices are already final
     unsigned *post = s.refList + s.refList_cap / 2;
     const long long warps_per_block = 8;
     c.launches += 1;
     k_map_reflected<<<(unsigned)((s.nRef + warps_per_block - 1) / warps_per_block), 256, 0, c.stream>>>(s.refList, s.nRef, s.l2 /* pre-compaction bank */,
                                                                                                           c.d_tileOffset, post);
     IPIC_CUDA(cudaGetLastError());
-    // drop the entries of particles absorbed after their reflection (0xffffffff), keep the order
-    std::vector<unsigned> h((size_t)s.nRef);
-    IPIC_CUDA(cudaMemcpyAsync(h.data(), post, (size_t)s.nRef * sizeof(unsigned), cudaMemcpyDeviceToHost, c.stream));
-    IPIC_CUDA(cudaStreamSynchronize(c.stream));
-    size_t k = 0;
-    for (size_t j = 0; j < h.size(); ++j) if (h[j] != 0xffffffffu) h[k++] = h[j];
-    s.nRef = (long long)k;
-    if (k) IPIC_CUDA(cudaMemcpyAsync(s.refList, h.data(), k * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
-    IPIC_CUDA(cudaStreamSynchronize(c.stream));
+    // every entry is kept, in order; one that names the slot behind the last survivor of its slab (the reflected particle was the last of
+    // the slab and was absorbed) is what the reference holds too -- consumers skip indices >= N_p
+    IPIC_CUDA(cudaMemcpyAsync(s.refList, post, (size_t)s.nRef * sizeof(unsigned), cudaMemcpyDeviceToDevice, c.stream));
     return IPIC_OK;
 }
 

@@ -154,9 +154,12 @@ class Particle:
         idx = np.zeros(max(n.value, 1), dtype=np.int32)
         _lib.check(L.ipic_get_ref_record(self._solver._h, self._index, idx.ctypes.data_as(_lib._ip), n.value, C.byref(n)))
         idx = idx[:n.value].astype(np.int64)
+        cnt = np.zeros(self.numThread, dtype=np.int32)
+        _lib.check(L.ipic_get_ref_record_counts(self._solver._h, self._index, cnt.ctypes.data_as(_lib._ip), self.numThread))
         off = np.concatenate([[0], np.cumsum(self.N_p.astype(np.int64))])
-        rec = [(idx[(idx >= off[t]) & (idx < off[t + 1])] - off[t] + 1).astype(np.int32) for t in range(self.numThread)]
-        return np.array([r.size for r in rec], dtype=np.int32), rec
+        start = np.concatenate([[0], np.cumsum(cnt.astype(np.int64))])
+        rec = [(idx[start[t]:start[t + 1]] - off[t] + 1).astype(np.int32) for t in range(self.numThread)]
+        return cnt, rec
 
     def _refresh_stats(self):
         st = _lib.MoveStats()

@@ -157,8 +157,13 @@ int ipic_get_move_stats(ipic_handle h, int32_t species, ipic_move_stats *out);
 /* refRecordIdx (mod_particle.f90:19; written by moveParticles, NGP mod_particleMover.f90:226-231, CIC mod_particleMoverPicard.f90:276-281):
  * the particles first reflected at a Neumann wall during the last ipic_move_particles / converged ipic_solve_potential, as ascending
  * 0-based indices into the species' particle order after compaction (the order ipic_download_particles writes, slab after slab).
- * *n receives the count; at most cap indices are written.  A particle reflected and then absorbed in the same step is not listed. */
+ * *n receives the count; at most cap indices are written.  A particle reflected and then absorbed in the same step is listed with the slot
+ * of the next surviving particle, as the reference's `i - delIdx` (recorded at the reflection) comes out after its compaction. */
 int ipic_get_ref_record(ipic_handle h, int32_t species, int32_t *idx, int64_t cap, int64_t *n);
+/* refIdx(numThread) of the same move: how many consecutive entries of the list above belong to each thread slab (the slab the particle
+ * was in when it was reflected).  Entry k of slab t is the 0-based global index; its refRecordIdx value is index - (first index of slab t
+ * after the compaction) + 1, which is N_p(t) + 1 when the reflected particle was the last of its slab and was absorbed. */
+int ipic_get_ref_record_counts(ipic_handle h, int32_t species, int32_t *refIdx, int32_t numThread);
 /* executed sub-steps of a species in the last depositJ sweep, or, after ipic_solve_potential, in all depositJ sweeps of that step
  * (instrumentation for the throughput metric) */
 int ipic_get_deposit_substeps(ipic_handle h, int32_t species, int64_t *n);
