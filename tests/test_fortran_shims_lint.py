@@ -84,3 +84,9 @@ def test_bound_functions_exist_in_the_header_with_the_same_arity():
             for m in re.finditer(r"\b(ipic_[a-z0-9_]+)\s*\(", ln):
                 f = m.group(1)
                 assert f in bound or f in defined or f in ("ipic_check",), "%s: %s has no interface" % (name, f)
+
+
+def test_every_abi_entry_is_mapped_to_the_reference_in_INTEGRATION_md():
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = sorted(f for f in header_functions() if f not in doc)
+    assert not missing, "INTEGRATION.md (section 6) does not map: %s" % missing
