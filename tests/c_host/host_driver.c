@@ -2,11 +2,14 @@
  * fortran/mod_particleMover_b200.f90 does (ipic_attach -> ipic_push_state -> depositJ -> moveParticles).
  * Stands in for the Fortran host, which cannot be compiled in this image (no Fortran compiler).
  *
- * usage: host_driver <in.bin> <out.bin>
+ * usage: host_driver <in.bin> <out.bin> [level3]
  * in.bin : int32 scheme, Nx, smooth, nsp, T, finalIdx ; double del_t, Vl, Vr, rf ;
  *          double grid[Nx], dx[ndx] ; int32 bc[nbc] ; double phi[Nx], phi_f[Nx] ;
  *          per species: double mass, q, w_p ; int32 N_p[T] ; double phaseSpace[T][finalIdx][4]
  * out.bin: double J[Nh] ; per species: int32 N_p[T] ; double phaseSpace[T][finalIdx][4] ; ipic_move_stats
+ * With a third argument (level-3 integration) what mod_simulation.f90:161-168 and a diagnostics dump run
+ * between two steps happens on the device before the download: addMaxwellianLostParticles (T_e = 3, T_i = 0.1 eV), loadParticleDensity and
+ * the EEDF extrema of the electrons; out.bin then ends with int64 numAdded ; double energyAdd ; double density[Nx] ; double extrema[3].
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -67,6 +70,15 @@ int main(int argc, char **argv) {
     CHECK(ipic_get_field(h, IPIC_F_J, J, Nh));
     /* moveParticles */
     CHECK(ipic_move_particles(h, sc[0]));
+    int64_t numAdded = 0;
+    double energyAdd = 0.0, extrema[3] = {0, 0, 0};
+    double *dens = calloc((size_t)Nx, sizeof(double));
+    if (argc > 3) {
+        CHECK(ipic_set_injection_seed(h, 2026u));
+        CHECK(ipic_add_maxwellian_lost_particles(h, 3.0, 0.1, &energyAdd, &numAdded));
+        CHECK(ipic_load_particle_density(h, 0, dens));
+        CHECK(ipic_velocity_extrema(h, 0, extrema));
+    }
 
     FILE *fo = fopen(argv[2], "wb");
     if (!fo) return 8;
@@ -80,6 +92,12 @@ int main(int argc, char **argv) {
         fwrite(ps[s], sizeof(double), psz, fo);
         fwrite(&st, sizeof st, 1, fo);
         CHECK(ipic_host_free(ps[s]));
+    }
+    if (argc > 3) {
+        fwrite(&numAdded, sizeof numAdded, 1, fo);
+        fwrite(&energyAdd, sizeof energyAdd, 1, fo);
+        fwrite(dens, sizeof(double), (size_t)Nx, fo);
+        fwrite(extrema, sizeof(double), 3, fo);
     }
     fclose(fo);
     CHECK(ipic_destroy(h));
