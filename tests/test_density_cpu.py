@@ -75,3 +75,59 @@ def test_oracle_velocity_histograms_known_answers():
     vth2 = d["T_e"] * op.e / m
     assert abs(mean) < 5.0 * np.sqrt(vth2 / N)
     assert var / vth2 == pytest.approx(1.0, abs=0.03)
+
+
+def _raw_density_weights(o, d, sp):
+    """SUM(densities, DIM=2) of loadParticleDensity in plain numpy / Python from the oracle's particle positions: NGP (1 - d, d) onto the
+    two nodes (mod_Scheme.f90:50-65), CIC the quadratic spline with the weight behind a wall folded into the wall cell (:68-105)"""
+    Nx = d["Nx"]
+    ps, Np = o.phase_space(sp), o.N_p(sp)
+    l = np.concatenate([ps[t, :Np[t], 0] for t in range(o.T)])
+    raw = np.zeros(Nx + 2)
+    lc = l.astype(np.int64)
+    f = l - lc
+    if d["scheme"] == 0:
+        np.add.at(raw, lc, 1.0 - f)
+        np.add.at(raw, lc + 1, f)
+        return raw[1:Nx + 1]
+    bc = o.grid()[2]                                            # boundaryConditions(1:N_h), 0-based array
+    for c, x in zip(lc, f):
+        raw[c] += -x * x + x + 0.5
+        wl, wr = 0.5 * (1.0 - x) ** 2, 0.5 * x * x
+        b = int(bc[c]) - int(bc[c - 1])                         # bc(l_center + 1) - bc(l_center)
+        if b == 0:
+            raw[c - 1] += wl; raw[c + 1] += wr
+        elif b < 0 and b != -3:
+            raw[c] += wl; raw[c + 1] += wr
+        elif b > 0 and b != 3:
+            raw[c] += wr; raw[c - 1] += wl
+        elif b == -3:
+            raw[Nx] += wl; raw[c + 1] += wr
+        else:
+            raw[c - 1] += wl; raw[1] += wr
+    return raw[1:Nx + 1]
+
+
+@pytest.mark.parametrize("name", sorted(DECKS))
+def test_host_epilogue_of_WriteParticleDensity_matches_the_oracle(name, tmp_path):
+    """implicitpic1d_b200/scheme.py (host logic of the product: weight, periodic fold, smoothing, normalisation, record writer) on raw
+    weights computed independently in numpy, against the oracle's C++ restatement of the whole routine"""
+    from implicitpic1d_b200 import scheme as sch
+    from implicitpic1d_b200.domain import readWorld
+    from implicitpic1d_b200.particle import Particle
+    d = DECKS[name]
+    o = build_oracle(d)
+    world = readWorld(d["scheme"], d["Nx"], d["L"], d.get("gridType", 0), d.get("del_x", 0.0), d["bcL"], d["bcR"], int(d["smooth"]), d["T_e"], d["n_ave"])
+    o.loadParticleDensity(True)
+    plist = []
+    for sp in range(2):
+        sc = o.species_scalars(sp)
+        p = Particle(sc["mass"], sc["q"], sc["w_p"], 0, 8, "e" if sp == 0 else "ion", d["T"])
+        p.densities = _raw_density_weights(o, d, sp)
+        plist.append(p)
+    out = sch.WriteParticleDensity(plist, world, 3, False, str(tmp_path))
+    for sp in range(2):
+        want = o.particleDensityArray(sp)
+        assert np.max(np.abs(out[sp] - want)) <= 1e-12 * np.max(np.abs(want))
+        raw = np.fromfile(str(tmp_path / "Density" / ("density_%s_3.dat" % plist[sp].name)), dtype=np.uint8)
+        assert raw.size == 8 * d["Nx"] + 8 and np.array_equal(np.frombuffer(raw[4:-4].tobytes(), dtype="<f8"), out[sp])
