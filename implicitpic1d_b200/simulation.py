@@ -223,6 +223,19 @@ def _allreduce_np(dist, arr, op=None):
     return arr
 
 
+def energy_grid(Emin, EMax, binNumber):
+    """diffE and E_grid(1:binNumber) of mod_simulation.f90:453-461: logarithmic bins, the grid built by repeated addition of diffE
+    (real(binNumber - 1) is a single-precision conversion in the reference, exact for these integers)"""
+    import math                                    # libm scalars: numpy's vectorised log / exp may differ from them in the last bit
+    diffE = (math.log(EMax) - math.log(Emin)) / float(np.float32(binNumber - 1))
+    grid = np.zeros(binNumber)
+    partV = math.log(Emin)
+    for i in range(binNumber):
+        grid[i] = math.exp(partV)
+        partV = partV + diffE
+    return diffE, grid
+
+
 # ---- EEDF / velocity histograms of the final averaging window (:433-510) -------------------------------------------------
 class Histograms:
     """VMax, EMax, Emin, E_grid, diffE per species and the accumulating VHist(2*binNumber), EHist(binNumber)"""
@@ -239,13 +252,10 @@ class Histograms:
         if dist is not None:                                  # ranks combine like the OpenMP reduction(max / min) clauses (:442)
             for arr, op in ((self.VMax, dist.ReduceOp.MAX), (self.EMax, dist.ReduceOp.MAX), (self.Emin, dist.ReduceOp.MIN)):
                 _allreduce_np(dist, arr, op)
-        self.diffE = (np.log(self.EMax) - np.log(self.Emin)) / float(np.float32(self.binNumber - 1))
+        self.diffE = np.zeros(n)
         self.E_grid = np.zeros((n, self.binNumber))
         for j in range(n):
-            partV = np.log(self.Emin[j])
-            for i in range(self.binNumber):
-                self.E_grid[j, i] = np.exp(partV)
-                partV = partV + self.diffE[j]
+            self.diffE[j], self.E_grid[j] = energy_grid(self.Emin[j], self.EMax[j], self.binNumber)
         self.VHist = np.zeros((n, 2 * self.binNumber))
         self.EHist = np.zeros((n, self.binNumber))
 

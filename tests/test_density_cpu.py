@@ -131,3 +131,20 @@ def test_host_epilogue_of_WriteParticleDensity_matches_the_oracle(name, tmp_path
         assert np.max(np.abs(out[sp] - want)) <= 1e-12 * np.max(np.abs(want))
         raw = np.fromfile(str(tmp_path / "Density" / ("density_%s_3.dat" % plist[sp].name)), dtype=np.uint8)
         assert raw.size == 8 * d["Nx"] + 8 and np.array_equal(np.frombuffer(raw[4:-4].tobytes(), dtype="<f8"), out[sp])
+
+
+def test_host_energy_grid_and_record_writer_match_the_oracle(tmp_path):
+    """simulation.energy_grid (host logic: mod_simulation.f90:453-461) against the oracle's E_grid, and the unformatted-record writer"""
+    from implicitpic1d_b200 import simulation as sim
+    d = DECKS["cic_rf"]
+    o = build_oracle(d)
+    VMax, EMax, Emin = o.velocityExtrema(1)
+    VH, EH = np.zeros(200), np.zeros(100)
+    E_grid = o.velocityHistograms(1, 100, VMax, Emin, EMax, VH, EH)
+    diffE, grid = sim.energy_grid(Emin, EMax, 100)
+    assert np.array_equal(grid, E_grid)
+    sim._record(str(tmp_path / "r.dat"), VH, np.array([VMax]))
+    raw = np.fromfile(str(tmp_path / "r.dat"), dtype=np.uint8)
+    assert raw.size == 8 * 201 + 8 and int(np.frombuffer(raw[:4].tobytes(), dtype="<i4")[0]) == 8 * 201
+    assert np.array_equal(np.frombuffer(raw[4:-4].tobytes(), dtype="<f8"), np.concatenate([VH, [VMax]]))
+    assert sim.es(1.6e18) == "  1.60000000E+18" and sim.es(-2.5e-11) == " -2.50000000E-11"      # Fortran es16.8
