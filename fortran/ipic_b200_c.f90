@@ -33,6 +33,19 @@ module ipic_b200_c
         real(c_double) :: moverSeconds, potSeconds, lastResidualNorm
     end type ipic_solver_stats
 
+    integer(c_int), parameter :: IPIC_MAX_COLLISIONS = 16
+    type, bind(c) :: ipic_collision_stats
+        integer(c_int32_t) :: numberCollisions, lengthArrays
+        integer(c_int32_t) :: collisionType(IPIC_MAX_COLLISIONS)
+        real(c_double) :: energyThreshold(IPIC_MAX_COLLISIONS)
+        real(c_double) :: sigmaVMax, reducedMass, sumMass, reducedMassIonization, minEnergy, maxEnergy
+        real(c_double) :: P_null
+        integer(c_int64_t) :: numberSelected, ionizations
+        integer(c_int64_t) :: totalAmountCollisions(IPIC_MAX_COLLISIONS)
+        real(c_double) :: totalEnergyLoss(IPIC_MAX_COLLISIONS), totalIncidentEnergy(IPIC_MAX_COLLISIONS)
+        integer(c_int64_t) :: totalNumberCollidableParticles
+    end type ipic_collision_stats
+
     interface
         function ipic_last_error() bind(c, name="ipic_last_error") result(msg)
             import :: c_ptr
@@ -276,6 +289,40 @@ module ipic_b200_c
             type(c_ptr), value :: handle
             integer(c_int32_t), value :: species
             real(c_double), intent(out) :: res3(3)
+            integer(c_int) :: rc
+        end function
+        function ipic_add_target_particle(handle, mass, density, temperature, target) bind(c, name="ipic_add_target_particle") result(rc)
+            import :: c_ptr, c_int, c_int32_t, c_double
+            type(c_ptr), value :: handle
+            real(c_double), value :: mass, density, temperature
+            integer(c_int32_t), intent(out) :: target
+            integer(c_int) :: rc
+        end function
+        function ipic_null_collision_create(handle, numberCollisions, lengthArrays, red_mass, sumMass, redMassTripleProducts, energyArray, &
+                sigmaArray, energyThreshold, collisionType, reactantsIndx, numberProducts, productsIndx, seed, collision_set) &
+                bind(c, name="ipic_null_collision_create") result(rc)
+            ! the arguments of nullCollision_constructor (mod_NullCollision.f90:44), arrays in the reference's own (column-major) layout
+            import :: c_ptr, c_int, c_int32_t, c_int64_t, c_double
+            type(c_ptr), value :: handle
+            integer(c_int32_t), value :: numberCollisions, lengthArrays
+            real(c_double), value :: red_mass, sumMass, redMassTripleProducts
+            real(c_double), intent(in) :: energyArray(*), sigmaArray(*), energyThreshold(*)
+            integer(c_int32_t), intent(in) :: collisionType(*), reactantsIndx(*), numberProducts(*), productsIndx(*)
+            integer(c_int64_t), value :: seed
+            integer(c_int32_t), intent(out) :: collision_set
+            integer(c_int) :: rc
+        end function
+        function ipic_get_collision_stats(handle, collision_set, stats) bind(c, name="ipic_get_collision_stats") result(rc)
+            import :: c_ptr, c_int, c_int32_t, ipic_collision_stats
+            type(c_ptr), value :: handle
+            integer(c_int32_t), value :: collision_set
+            type(ipic_collision_stats), intent(out) :: stats
+            integer(c_int) :: rc
+        end function
+        function ipic_reset_collision_stats(handle, collision_set) bind(c, name="ipic_reset_collision_stats") result(rc)
+            import :: c_ptr, c_int, c_int32_t
+            type(c_ptr), value :: handle
+            integer(c_int32_t), value :: collision_set
             integer(c_int) :: rc
         end function
         function ipic_generate_collision(handle, collision_set, del_t) bind(c, name="ipic_generate_collision") result(rc)
