@@ -90,3 +90,38 @@ def test_every_abi_entry_is_mapped_to_the_reference_in_INTEGRATION_md():
     doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     missing = sorted(f for f in header_functions() if f not in doc)
     assert not missing, "INTEGRATION.md (section 6) does not map: %s" % missing
+
+
+def test_bind_c_types_match_the_c_structs():
+    """field order, kinds and array lengths of the bind(c) derived types against the ctypes mirrors of the header's structs (which the GPU
+    tests exercise against the library)"""
+    import ctypes as C
+    from implicitpic1d_b200 import _lib
+    lines = code_lines(os.path.join(ROOT, "fortran", "ipic_b200_c.f90"))
+    params = {"ipic_max_collisions": _lib.MAX_COLLISIONS}
+    kinds = {"c_int32_t": C.c_int32, "c_int64_t": C.c_int64, "c_double": C.c_double, "c_int": C.c_int}
+    types, cur = {}, None
+    for ln in lines:
+        m = re.match(r"type\s*,\s*bind\(c\)\s*::\s*(\w+)", ln)
+        if m:
+            cur = m.group(1); types[cur] = []
+            continue
+        if cur and re.match(r"end\s+type", ln):
+            cur = None
+            continue
+        if cur:
+            m = re.match(r"(?:integer|real)\((\w+)\)\s*::\s*(.*)", ln)
+            assert m, ln
+            for item in re.findall(r"(\w+)(?:\(([^)]*)\))?", m.group(2)):
+                n = item[1].strip()
+                count = 1 if not n else (int(n) if n.isdigit() else params[n])
+                types[cur].append((item[0], kinds[m.group(1)], count))
+    for fname, struct in (("ipic_move_stats", _lib.MoveStats), ("ipic_solver_stats", _lib.SolverStats), ("ipic_collision_stats", _lib.CollisionStats)):
+        got = types[fname]
+        want = []
+        for name, ct in struct._fields_:
+            if hasattr(ct, "_length_"):
+                want.append((name.lower(), ct._type_, ct._length_))
+            else:
+                want.append((name.lower(), ct, 1))
+        assert [(a, b, c) for a, b, c in got] == want, fname
