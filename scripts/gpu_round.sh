@@ -13,3 +13,5 @@ python scripts/launch_summary.py gpurun_out/${tag}_launches.csv > gpurun_out/${t
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_push -o gpurun_out/${tag}_push_full -f \
    python scripts/gpu_probe.py prof 4097 62500000 0 1.0 1 3 > gpurun_out/${tag}_ncu_full.log 2>&1
 python scripts/ncu_summary.py gpurun_out/${tag}_push_full.ncu-rep > gpurun_out/${tag}_push_ncu_full.txt 2>&1; cat gpurun_out/${tag}_push_ncu_full.txt
+# between-step particle operations at the C5 shard's size: CUDA-event times against the measured HBM peak
+timeout 300 python scripts/aux_ops_bench.py > gpurun_out/${tag}_aux_ops_c5.json 2> gpurun_out/${tag}_aux_ops.err; tail -12 gpurun_out/${tag}_aux_ops.err
