@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libipic1d_b200.so")
+# IPIC1D_B200_LIB: another build of the same library (A/B measurements of kernel variants); default: the in-tree build
+LIB_PATH = os.environ.get("IPIC1D_B200_LIB") or os.path.join(_HERE, "lib", "libipic1d_b200.so")
 
 OK, ERR_ARG, ERR_CUDA, ERR_STOP, ERR_NOT_CONVERGED, ERR_UNSUPPORTED, ERR_NCCL = range(7)
 SCHEME_NGP, SCHEME_CIC, SCHEME_NGP_PERIODIC = 0, 1, 2

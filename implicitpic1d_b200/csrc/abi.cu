@@ -389,7 +389,7 @@ int ipic_create(ipic_handle *out, int scheme, int32_t Nx, const double *grid, co
     IPIC_CUDA(cudaMemset(c->d_acc, 0, c->acc_reps * c->acc_rep_stride * sizeof(unsigned long long)));
     const size_t tabsz = std::max(sizeof(CellTabNGP), sizeof(CellTabCIC));
     IPIC_CUDA(cudaMalloc(&c->d_tab, NSP_MAX * NM * tabsz)); IPIC_CUDA(cudaMemset(c->d_tab, 0, NSP_MAX * NM * tabsz));
-    IPIC_CUDA(cudaMalloc(&c->d_ttab, NSP_MAX * NM * sizeof(double2))); IPIC_CUDA(cudaMemset(c->d_ttab, 0, NSP_MAX * NM * sizeof(double2)));
+    IPIC_CUDA(cudaMalloc(&c->d_ttab, NSP_MAX * 2 * NM * sizeof(double2))); IPIC_CUDA(cudaMemset(c->d_ttab, 0, NSP_MAX * 2 * NM * sizeof(double2)));
     IPIC_CUDA(cudaMalloc(&c->d_counters, NSP_MAX * 8 * sizeof(unsigned long long)));
     IPIC_CUDA(cudaMemset(c->d_counters, 0, NSP_MAX * 8 * sizeof(unsigned long long)));
     IPIC_CUDA(cudaMallocHost(&c->h_scal, 64 * sizeof(double)));
@@ -402,6 +402,7 @@ int ipic_create(ipic_handle *out, int scheme, int32_t Nx, const double *grid, co
 int ipic_destroy(ipic_handle h) {
     CTX(h);
     cudaStreamSynchronize(c->stream);
+    push_stats_dump();
     resolve_timing(*c);
     for (auto &e : g_pool[c]) cudaEventDestroy(e);
     g_pool.erase(c); g_pending.erase(c); g_chain.erase(c);

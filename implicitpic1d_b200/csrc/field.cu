@@ -587,14 +587,18 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
             __syncthreads();
             for (int s = 0; s < A.nsp; ++s) {
                 CellTabNGP *T = reinterpret_cast<CellTabNGP *>(A.tab) + (size_t)s * A.tab_cells;
-                double2 *TT = A.ttab + (size_t)s * A.tab_cells;
+                double2 *TT = A.ttab + (size_t)s * 2 * A.tab_cells;
                 for (int cI = 1 + threadIdx.x; cI <= Nh; cI += FT) {
                     const double a = A.qm[s] * EF(cI), dx = DX(cI);
                     CellTabNGP t;
                     t.a = a; t.hinv = A.hinv[cI - 1]; t.two_a_dx = 2.0 * a * dx; t.inv_a = 1.0 / a;
                     T[cI] = t;
-                    // wall cells are not transited by the lean loop: NaN makes a lane that reaches one fail its next time test
-                    TT[cI] = (cI == 1 || cI == Nh) ? make_double2(__longlong_as_double(0x7ff8000000000000ll), 0.0) : make_double2(t.two_a_dx, t.inv_a);
+                    // wall cells are not transited by the lean loop: NaN makes a lane that reaches one fail its next time test.
+                    // Right-movers read entry cI, left-movers the mirrored, negated copy (every lane walks upwards)
+                    const bool wall = (cI == 1 || cI == Nh);
+                    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+                    TT[cI] = wall ? make_double2(qnan, 0.0) : make_double2(t.two_a_dx, t.inv_a);
+                    TT[2 * A.tab_cells - 1 - cI] = wall ? make_double2(qnan, 0.0) : make_double2(-t.two_a_dx, -t.inv_a);
                 }
             }
         } else {
@@ -650,13 +654,16 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
         __syncthreads();
         for (int s = 0; s < A.nsp; ++s) {
             CellTabNGP *T = reinterpret_cast<CellTabNGP *>(A.tab) + (size_t)s * A.tab_cells;
-            double2 *TT = A.ttab + (size_t)s * A.tab_cells;
+            double2 *TT = A.ttab + (size_t)s * 2 * A.tab_cells;
             for (int cI = 1 + threadIdx.x; cI <= Nh; cI += FT) {
                 const double a = A.qm[s] * A.Eh[cI - 1], dx = DX(cI);
                 CellTabNGP t;
                 t.a = a; t.hinv = A.hinv[cI - 1]; t.two_a_dx = 2.0 * a * dx; t.inv_a = 1.0 / a;
                 T[cI] = t;
-                TT[cI] = (cI == 1 || cI == Nh) ? make_double2(__longlong_as_double(0x7ff8000000000000ll), 0.0) : make_double2(t.two_a_dx, t.inv_a);
+                const bool wall = (cI == 1 || cI == Nh);
+                const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+                TT[cI] = wall ? make_double2(qnan, 0.0) : make_double2(t.two_a_dx, t.inv_a);
+                TT[2 * A.tab_cells - 1 - cI] = wall ? make_double2(qnan, 0.0) : make_double2(-t.two_a_dx, -t.inv_a);
             }
         }
         __syncthreads();

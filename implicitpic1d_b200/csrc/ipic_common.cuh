@@ -55,7 +55,8 @@ struct PushArgs {
     double *l_out, *vx_out;    // MOVE: in-place outputs
     long long n;               // particles in the arrays (alive or marked dead)
     const void *tab;           // CellTabNGP* / CellTabCIC* for this species
-    const double2 *ttab;       // NGP: compact transit table {2 a dx, 1/a} per cell for this species (16 B: the lean loop's only gather)
+    const double2 *ttab;       // NGP: transit tables of this species, 16 B per cell (the lean loop's only gather): [0, Nh+2) = {2 a dx, 1/a} by cell for
+                               // right-movers, [Nh+2, 2 Nh+4) = {-2 a dx, -1/a} in reverse cell order for left-movers
     int bcL, bcR;              // boundaryConditions at the two walls (zero everywhere else)
     unsigned *tile_counter;    // dynamic tile scheduler (zeroed before the launch)
     unsigned long long *acc;   // !MOVE: int64 fixed-point grid [Nh] for this species
@@ -68,6 +69,8 @@ struct PushArgs {
     int NB;                    // wall index on the right: N_x (NGP) or N_h (CIC)
     double del_t, f_tol;
     double t_lim;              // smallest double t with !(del_t - t > f_tol): `t < t_lim` is the reference's `del_t - t > f_tol`
+    unsigned long long tlim_bits;   // bit pattern of t_lim (0 when t_lim <= 0): for t >= 0, `bits(t) < tlim_bits` as unsigned integers is `t < t_lim`,
+                               // and NaN, -0 and negative t compare high
     unsigned char *refl;       // MOVE, Neumann walls only: per-particle flag "reflected during this step" (refRecordIdx), else null
     int stay_min;              // a queued batch keeps looping in registers while at least this many lanes continue
     int transit_min;           // the lean face-to-face loop runs while at least this many lanes are in transit
@@ -130,7 +133,7 @@ struct Ctx {
     // the split changes nothing in the result; the field kernel adds the copies when it collects.
     unsigned long long *d_acc = nullptr;
     int acc_reps = 1; size_t acc_rep_stride = 0;
-    double2 *d_ttab = nullptr;                                    // [nsp_max][cells] NGP transit table
+    double2 *d_ttab = nullptr;                                    // [nsp_max][2][cells] NGP transit tables (by direction of travel)
     void *d_tab = nullptr;                                        // [nsp_max][cells] CellTab*
     unsigned long long *d_counters = nullptr;                     // [nsp_max][8]
     double *d_scal = nullptr;                                     // small device scalar outputs (64 doubles)
@@ -206,6 +209,7 @@ void set_error(const std::string &s);
 
 // ---- launchers implemented in particles.cu ---------------------------------------------------------
 int launch_deposit(Ctx &c, int sp, double del_t);
+void push_stats_dump();                                 // measurement builds (-DIPIC_PUSH_STATS) only: prints and clears the lane-utilisation counters
 int launch_move(Ctx &c, int sp, double del_t);
 int launch_deposit_pair(Ctx &c, int a, int b, double del_t);
 int launch_deposit_rho(Ctx &c, int sp, bool density = false);   // density: the diagnostic's weights (differs from rho at CIC Dirichlet walls)

@@ -9,6 +9,7 @@
 #include <cub/iterator/counting_input_iterator.cuh>
 #include <vector>
 #include <algorithm>
+#include <cstring>
 
 namespace ipic {
 
@@ -237,6 +238,14 @@ __device__ __forceinline__ void deposit_add(WarpSmem &W, DepositState &D, int la
 
 constexpr long long FX_ONE = 1ll << FX_BITS;
 
+#ifdef IPIC_PUSH_STATS
+// measurement build only (scripts/variant_bench.sh "-DIPIC_PUSH_STATS"): lane utilisation of the deposit sweeps, printed by ipic_destroy
+__device__ unsigned long long g_push_stats[16];
+#define PSTAT(i, x) do { st_[(i)] += (unsigned)(x); } while (0)
+#else
+#define PSTAT(i, x) do { } while (0)
+#endif
+
 // ends a run of fully traversed cells; `cend` is the cell the particle is in now (not part of the run)
 __device__ __forceinline__ void close_run(WarpSmem &W, DepositState &D, int lane, unsigned long long *gacc, unsigned long long *gdacc, int pend, int cend) {
     if (pend > 0) {                                          // moving right: cells pend .. cend-1 got +1 each
@@ -255,78 +264,112 @@ __device__ __forceinline__ void close_run(WarpSmem &W, DepositState &D, int lane
     }
 }
 
-// One face-to-face crossing of an interior cell in the lean transit loop (NGP sub-step, mod_particleMover.f90:36-60, for a particle
-// that sits on the entry face): s = u^2 +- 2 a dx, u_f = sqrt(s), t_f = t +- (u_f - u)/a, committed when t_f < t_lim.  Same operations and
-// roundings as the general sub-step (the +-1 multipliers are exact, so the two fma are a plain add/sub), written in PTX to pin the
-// instruction sequence: 12 FP64 arithmetic instructions + 1 compare, everything unconditional except the two result writes (predicated
-// on `alive`), no branches.  The square root is CUDA's own sqrt(double) sequence for normal operands (MUFU.RSQ64H seed, one refinement
-// of 1/sqrt, one residual correction of the root) with the refinement taken to second instead of third order -- the residual
-// correction squares the remaining 2^-45 error, so the result is still the correctly rounded root: bit-identical to sqrt() on 5e9
-// random and near-square operands (scripts/micro/sqrt_check.cu) -- and without the special-operand slow path:
-// s <= 0 (the particle turns around inside the cell) gives NaN or Inf*0, the compare fails and the lane is left to the general sub-step.
-// Software-pipelined form of that crossing (the one the kernel uses): the time update and test of crossing j (t_j = t_{j-1} +- (u_j - u_{j-1})/a_j, t_j < t_lim)
-// is issued between the square-root chain of crossing j+1 (candidate speed from u_j and the next cell's 2 a dx), so that the in-order
-// issue of one warp always has two independent dependency chains to draw from.  `u_cur` was committed under `alive` (crossing j is
-// attempted by this lane); a lane whose test fails keeps (u_prev, t_prev) as its state.  Returns ok_j; the candidate u_{j+1} is
-// returned raw in `u_cand` and committed by the caller once the lane is known to attempt crossing j+1.
-__device__ __forceinline__ int transit_step(double u_prev, double u_cur, double t_prev, double &t_cur, double inv_a, double dpe_next, double sgn,
-                                            double t_lim, bool alive, double &u_cand) {
-    int ok;
-    asm("{\n\t"
-        ".reg .pred pa, pk;\n\t"
-        ".reg .f64 uu, s, y, y1, t, nt, e, c, p, g, ng, h, r, d;\n\t"
-        ".reg .b32 lo, hi;\n\t"
-        "setp.ne.s32 pa, %10, 0;\n\t"
-        "mul.rn.f64 uu, %4, %4;\n\t"
-        "sub.rn.f64 d, %4, %3;\n\t"
-        "fma.rn.f64 s, %8, %7, uu;\n\t"
-        "mul.rn.f64 d, d, %6;\n\t"
-        "rsqrt.approx.ftz.f64 y, s;\n\t"
-        "@pa fma.rn.f64 %0, %8, d, %5;\n\t"
-        "mul.rn.f64 t, y, y;\n\t"
-        "neg.f64 nt, t;\n\t"
-        "setp.lt.and.f64 pk, %0, %9, pa;\n\t"
-        "fma.rn.f64 e, s, nt, 0d3FF0000000000000;\n\t"
-        "selp.s32 %2, 1, 0, pk;\n\t"
-        "mul.rn.f64 p, y, e;\n\t"
-        "fma.rn.f64 y1, p, 0d3FE0000000000000, y;\n\t"
-        "mul.rn.f64 g, s, y1;\n\t"
-        "mov.b64 {lo, hi}, y1;\n\t"
-        "add.s32 hi, hi, -1048576;\n\t"
-        "mov.b64 h, {lo, hi};\n\t"
-        "neg.f64 ng, g;\n\t"
-        "fma.rn.f64 r, g, ng, s;\n\t"
-        "fma.rn.f64 %1, r, h, g;\n\t"
-        "}"
-        : "+d"(t_cur), "=d"(u_cand), "=r"(ok)
-        : "d"(u_prev), "d"(u_cur), "d"(t_prev), "d"(inv_a), "d"(dpe_next), "d"(sgn), "d"(t_lim), "r"((int)alive));
-    return ok;
+// sqrt(s) for a normal positive operand: MUFU.RSQ64H seed (2^-20), one coupled Goldschmidt step on (g ~ sqrt(s), h ~ 1/(2 sqrt(s))) and the
+// residual correction g1 + (s - g1^2) h1 -- 6 FP64 instructions, error 2^-81 before the final rounding, so the result is the correctly
+// rounded root: bit-identical to sqrt() on 5e9 random and near-square operands (scripts/micro/transit_bench2.cu).  No special-operand
+// path: s <= 0 gives NaN (callers select it away or rely on it).  The same sequence is inlined in the PTX of transit_loop.
+__device__ __forceinline__ double lean_sqrt(double s) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+    const double hs = __hiloint2double(__double2hiint(y) - 0x100000, 0);
+    const double g = __dmul_rn(s, y);
+    const double r = fma(-g, hs, 0.5);
+    const double g1 = fma(g, r, g), h1 = fma(hs, r, hs);
+    const double r1 = fma(-g1, g1, s);
+    return fma(r1, h1, g1);
 }
 
-// candidate speed after crossing a cell: sqrt(u^2 +- 2 a dx), the same instruction sequence as in transit_step
-__device__ __forceinline__ double transit_speed(double u, double dpe, double sgn) {
-    double uf;
-    asm("{\n\t"
-        ".reg .f64 uu, s, y, y1, t, nt, e, c, p, g, ng, h, r;\n\t"
-        ".reg .b32 lo, hi;\n\t"
-        "mul.rn.f64 uu, %1, %1;\n\t"
-        "fma.rn.f64 s, %3, %2, uu;\n\t"
+// The lean transit loop: face-to-face crossings of interior cells (NGP sub-step, mod_particleMover.f90:36-60, for a particle that sits on
+// the entry face and moves inward).  Per crossing: s = u^2 + sdpe, u_f = sqrt(s), t_f = t + (u_f - u) * sinv, committed while t_f < t_lim,
+// with u = |v| and {sdpe, sinv} = {+-2 a dx, +-1/a} read from the table of the lane's direction of travel (the table of the left-movers is
+// stored mirrored and negated, so every lane walks its table upwards in 16-byte steps).  These are the general sub-step's own operations
+// on the same operands: l_sub on the face makes diff_PE = +-two_a_dx exactly, sign flips are exact, and both paths use lean_sqrt and the
+// fused time update, so a crossing gives the same bits whichever path runs it.
+// The whole loop is one PTX block: 10 FP64 instructions per crossing (DMUL, DADD, 6 for the root, DADD, DFMA), an integer time test
+// (positive doubles order like their bit patterns; NaN from a turning particle, a = 0 or a wall cell's NaN entry, and negative values,
+// compare high and fail), and real branches instead of selects: the two state copies A and B alternate as source and destination, a lane
+// that fails a test leaves the divergent region with its last committed copy intact (A after an even number of crossings, B after an odd
+// one) and costs nothing further.  The loop runs while at least `tmin` lanes are in transit.  The table entries of the next two cells
+// are loaded one crossing ahead.  u, t: in/out (state of the last committed crossing); off0: byte offset of the lane's first entry in
+// `tab`; returns the number of committed crossings.
+__device__ __forceinline__ int transit_loop(double &u, double &t, const double2 *tab, unsigned off0, unsigned long long tlim_bits, bool alive, unsigned tmin) {
+    // off: byte offset of the lane's current entry in `tab` (a 32-bit add per committed crossing, one IMAD.WIDE per two loads)
+    unsigned off = off0;
+    double uB, tB;
+    asm volatile("{\n\t"
+        ".reg .pred pd, pv;\n\t"
+        ".reg .f64 s, y, hs, g, ng, r, g1, ng1, h1, r1, d, e0x, e0y, e1x, e1y;\n\t"
+        ".reg .b32 lo, hi, hi2, m, c;\n\t"
+        ".reg .b64 tb, ad;\n\t"
+        "setp.eq.s32 pd, %7, 0;\n\t"                          // pd: the lane is out (not in transit, or a test failed)
+        "mov.f64 e0x, 0d0000000000000000;\n\t"
+        "mov.f64 e0y, 0d0000000000000000;\n\t"
+        "mov.f64 e1x, 0d0000000000000000;\n\t"
+        "mov.f64 e1y, 0d0000000000000000;\n\t"
+        "mad.wide.u32 ad, %2, 1, %5;\n\t"
+        "@!pd ld.global.nc.v2.f64 {e0x, e0y}, [ad];\n\t"
+        "@!pd ld.global.nc.v2.f64 {e1x, e1y}, [ad+16];\n\t"
+        "mov.f64 %3, %0;\n\t"
+        "mov.f64 %4, %1;\n\t"
+        "TLOOP:\n\t"
+        "@pd bra TSKIP;\n\t"
+        // crossing: A -> B with e0
+        "mul.rn.f64 s, %0, %0;\n\t"
+        "add.rn.f64 s, s, e0x;\n\t"
         "rsqrt.approx.ftz.f64 y, s;\n\t"
-        "mul.rn.f64 t, y, y;\n\t"
-        "neg.f64 nt, t;\n\t"
-        "fma.rn.f64 e, s, nt, 0d3FF0000000000000;\n\t"
-        "mul.rn.f64 p, y, e;\n\t"
-        "fma.rn.f64 y1, p, 0d3FE0000000000000, y;\n\t"
-        "mul.rn.f64 g, s, y1;\n\t"
-        "mov.b64 {lo, hi}, y1;\n\t"
-        "add.s32 hi, hi, -1048576;\n\t"
-        "mov.b64 h, {lo, hi};\n\t"
+        "mov.b64 {lo, hi}, y;\n\t"
+        "add.s32 hi2, hi, -1048576;\n\t"
+        "mov.b64 hs, {lo, hi2};\n\t"
+        "mul.rn.f64 g, s, y;\n\t"
         "neg.f64 ng, g;\n\t"
-        "fma.rn.f64 r, g, ng, s;\n\t"
-        "fma.rn.f64 %0, r, h, g;\n\t"
+        "fma.rn.f64 r, ng, hs, 0d3FE0000000000000;\n\t"
+        "fma.rn.f64 g1, g, r, g;\n\t"
+        "fma.rn.f64 h1, hs, r, hs;\n\t"
+        "neg.f64 ng1, g1;\n\t"
+        "fma.rn.f64 r1, ng1, g1, s;\n\t"
+        "fma.rn.f64 %3, r1, h1, g1;\n\t"
+        "sub.rn.f64 d, %3, %0;\n\t"
+        "fma.rn.f64 %4, d, e0y, %1;\n\t"
+        "mov.b64 tb, %4;\n\t"
+        "setp.ge.u64 pd, tb, %6;\n\t"
+        "@pd bra TSKIP;\n\t"
+        "add.u32 %2, %2, 16;\n\t"
+        "mad.wide.u32 ad, %2, 1, %5;\n\t"
+        "ld.global.nc.v2.f64 {e0x, e0y}, [ad+16];\n\t"
+        // crossing: B -> A with e1
+        "mul.rn.f64 s, %3, %3;\n\t"
+        "add.rn.f64 s, s, e1x;\n\t"
+        "rsqrt.approx.ftz.f64 y, s;\n\t"
+        "mov.b64 {lo, hi}, y;\n\t"
+        "add.s32 hi2, hi, -1048576;\n\t"
+        "mov.b64 hs, {lo, hi2};\n\t"
+        "mul.rn.f64 g, s, y;\n\t"
+        "neg.f64 ng, g;\n\t"
+        "fma.rn.f64 r, ng, hs, 0d3FE0000000000000;\n\t"
+        "fma.rn.f64 g1, g, r, g;\n\t"
+        "fma.rn.f64 h1, hs, r, hs;\n\t"
+        "neg.f64 ng1, g1;\n\t"
+        "fma.rn.f64 r1, ng1, g1, s;\n\t"
+        "fma.rn.f64 %0, r1, h1, g1;\n\t"
+        "sub.rn.f64 d, %0, %3;\n\t"
+        "fma.rn.f64 %1, d, e1y, %4;\n\t"
+        "mov.b64 tb, %1;\n\t"
+        "setp.ge.u64 pd, tb, %6;\n\t"
+        "@pd bra TSKIP;\n\t"
+        "add.u32 %2, %2, 16;\n\t"
+        "ld.global.nc.v2.f64 {e1x, e1y}, [ad+32];\n\t"
+        "TSKIP:\n\t"
+        "vote.sync.ballot.b32 m, !pd, 0xffffffff;\n\t"
+        "popc.b32 c, m;\n\t"
+        "setp.ge.u32 pv, c, %8;\n\t"
+        "@pv bra TLOOP;\n\t"
         "}"
-        : "=d"(uf) : "d"(u), "d"(dpe), "d"(sgn));
-    return uf;
+        : "+d"(u), "+d"(t), "+r"(off), "=&d"(uB), "=&d"(tB)
+        : "l"(tab), "l"(tlim_bits), "r"((int)alive), "r"(tmin)
+        : "memory");
+    const int k = (int)((off - off0) >> 4);
+    if (k & 1) { u = uB; t = tB; }
+    return k;
 }
 
 // The whole sweep of one species by one warp: claims tiles until the species has none left, drains its queue, flushes its deposits
@@ -349,6 +392,9 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
     const int stay_min = A.stay_min;
     int qcount = 0;
     unsigned nsub = 0, nfev = 0, nabsL = 0, nabsR = 0, nrefl = 0;
+#ifdef IPIC_PUSH_STATS
+    unsigned st_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
 
     // tile claims run one ahead so that the atomic's latency is never exposed
     auto claim = [&]() -> unsigned {
@@ -390,6 +436,7 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
         while (qcount >= 32 || (drain_all && qcount > 0)) {
             const int take = min(qcount, 32);
             qcount -= take;
+            PSTAT(6, 1);
             bool valid = lane < take;
             const int q = qcount + (valid ? lane : 0);
             double l = W.ql[q], v = W.qv[q], tp = W.qt[q];
@@ -413,55 +460,28 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
                     bool tr = valid && (v != 0.0) && (l == (double)(cell + (vpos ? 0 : 1))) && ((unsigned)(cell - 2) < tr_span);
                     if (!MOVE) tr = tr && (pend == 0 || ((pend > 0) == vpos));
                     if (__popc(__ballot_sync(FULL, tr)) >= A.transit_min) {
-                        const int step = vpos ? 1 : -1;
-                        const double sgn = vpos ? 1.0 : -1.0;
-                        const int cell0 = cell;
-                        // two register copies of (|v|, t): a crossing reads one and writes the other, so committing costs no moves;
-                        // after k committed crossings the valid copy is A (k even) or B (k odd)
-                        // Crossing j reads state j-1 and writes state j into the other register copy (no commit moves).  Pipelined: the
-                        // speed after crossing j is committed as soon as the lane is known to attempt crossing j, its time test runs
-                        // one stage later, interleaved with the square root of crossing j+1.
-                        double uA = fabs(v), tA = tp, uB, tB = tp;
-                        double2 ttB = __ldg(A.ttab + cell), ttA = __ldg(A.ttab + (cell + step));
-                        {   // stage 0: speed of crossing 1
-                            const double c0 = transit_speed(uA, ttB.x, sgn);
-                            uB = tr ? c0 : uA;
-                        }
-                        // The wall cells of the transit table hold NaN: a lane that reaches one fails its next test and is out, so the
-                        // loop needs no range check.  Two crossings per vote (four measured slower: more trips with few lanes left).
-                        do {
-#pragma unroll
-                            for (int rep = 0; rep < 1; ++rep) {
-                                // crossing j (state A -> B): time test; candidate for crossing j+1 from uB and the next cell
-                                double cand;
-                                int ok = transit_step(uA, uB, tA, tB, ttB.y, ttA.x, sgn, A.t_lim, tr, cand);
-                                cell += ok ? step : 0;
-                                tr = ok;
-                                ttB = __ldg(A.ttab + (cell + step));
-                                uA = tr ? cand : uA;
-                                // crossing j+1 (state B -> A)
-                                ok = transit_step(uB, uA, tB, tA, ttA.y, ttB.x, sgn, A.t_lim, tr, cand);
-                                cell += ok ? step : 0;
-                                tr = ok;
-                                ttA = __ldg(A.ttab + (cell + step));
-                                uB = tr ? cand : uB;
-                            }
-                        } while (__popc(__ballot_sync(FULL, tr)) >= A.transit_min);
-                        if (cell != cell0) {
-                            const int k = (cell - cell0) * step;
-                            const double u = (k & 1) ? uB : uA;
-                            tp = (k & 1) ? tB : tA;
+                        // right-movers walk the table of their species upwards from entry `cell`, left-movers the mirrored, negated copy
+                        // (entry tab_cells - 1 - cell); a lane that is not in transit points at a valid entry and never loads
+                        const unsigned toff = 16u * (unsigned)(tr ? (vpos ? cell : 2 * A.Nh + 3 - cell) : 0);
+                        double u = fabs(v);
+                        PSTAT(7, 1);
+                        const int k = transit_loop(u, tp, A.ttab, toff, A.tlim_bits, tr, (unsigned)A.transit_min);
+                        if (k) {
                             nsub += (unsigned)k;
+                            PSTAT(1, k);
+                            if (!MOVE && pend == 0) pend = vpos ? cell : -cell;
+                            cell += vpos ? k : -k;
                             v = vpos ? u : -u;
                             l = (double)(cell + (vpos ? 0 : 1));
-                            if (!MOVE && pend == 0) pend = vpos ? cell0 : -cell0;
                         }
                     }
                 }
                 bool cont = false;
                 double l_f = l, v_f = v;
+                PSTAT(2, 1);
                 if (valid) {
                     nsub += 1;
+                    PSTAT(3, 1);
                     double dtau = del_t - tp;
                     bool atB;
                     int lb = 0;
@@ -497,9 +517,10 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
                         double l_fw = l_f0;
                         if (atB) {
                             l_fw = (double)lb - lc;
-                            v_f = copysign(sqrt(__dadd_rn(diff_PE, v2)), sgn);
-                            dtau = __dmul_rn(__dsub_rn(v_f, v), inv_a);
+                            v_f = copysign(lean_sqrt(__dadd_rn(diff_PE, v2)), sgn);
                         }
+                        // time used: the crossing time (v_f - v) / a is added fused, here and in the transit loop
+                        tp = atB ? fma(__dsub_rn(v_f, v), inv_a, tp) : __dadd_rn(tp, dtau);
                         l_f = l_fw + lc;
                         if (!MOVE) {
                             const double dl = l_fw - lw;
@@ -578,7 +599,7 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
                             }
                         }
                     }
-                    tp = __dadd_rn(tp, dtau);
+                    if (SCHEME == 1) tp = __dadd_rn(tp, dtau);
                     const double rem = del_t - tp;
                     if (absorbed) {
                         if (MOVE) {
@@ -684,6 +705,7 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
                     else if (done) deposit_add(W, D, lane, gacc, cell, (long long)q);
                 } else if (done) { A.l_out[gi] = l_fw + lc; A.vx_out[gi] = v_f; }
                 nsub += done ? 1u : 0u;
+                PSTAT(4, 1); PSTAT(5, done ? 1 : 0);
             } else if (valid) {
                 bool done;
                 {
@@ -739,6 +761,18 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
 
     // ---------------- epilogue: accumulators, counters ----------------
     if (!MOVE) deposit_flush(W, D, lane, gacc);
+#ifdef IPIC_PUSH_STATS
+    if (!MOVE) {
+        // [0] transit crossings issued per warp (x32 = lane slots)  [1] committed lane crossings  [2] general sub-steps issued per warp
+        // [3] valid lanes in them  [4] fresh batches per warp  [5] lanes finished in them  [6] queue pops  [7] transit loop entries
+        const int warp_only[8] = {1, 0, 1, 0, 1, 0, 1, 1};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const unsigned s_ = warp_only[k] ? st_[k] : __reduce_add_sync(FULL, st_[k]);
+            if (lane == 0 && s_) atomicAdd(&g_push_stats[k], (unsigned long long)s_);
+        }
+    }
+#endif
     {
         const unsigned s0 = __reduce_add_sync(FULL, nsub);
         if (lane == 0 && s0) atomicAdd(&A.counters[MOVE ? 5 : 0], (unsigned long long)s0);
@@ -864,11 +898,27 @@ static int make_push_args(Ctx &c, int sp, double del_t, PushArgs &A) {
             while (!(A.del_t - std::nextafter(t, -INFINITY) > A.f_tol)) t = std::nextafter(t, -INFINITY);
         }
         A.t_lim = t;
+        A.tlim_bits = 0ull;
+        if (t > 0.0) std::memcpy(&A.tlim_bits, &t, sizeof(double));
     }
-    A.ttab = c.d_ttab + (size_t)sp * (cells + 2);
+    A.ttab = c.d_ttab + (size_t)sp * 2 * (cells + 2);
     A.stay_min = std::min(32, std::max(1, c.stay_min));
     A.transit_min = std::min(33, std::max(1, c.transit_min));   // 33 disables the transit loop
     return IPIC_OK;
+}
+
+void push_stats_dump() {
+#ifdef IPIC_PUSH_STATS
+    unsigned long long h[16] = {};
+    if (cudaMemcpyFromSymbol(h, g_push_stats, sizeof(h)) != cudaSuccess) return;
+    fprintf(stderr, "[push stats] transit: %llu warp-crossings issued (%llu lane slots), %llu committed lane crossings -> utilisation %.3f; entries %llu\n",
+            h[0], h[0] * 32, h[1], h[0] ? (double)h[1] / (double)(h[0] * 32) : 0.0, h[7]);
+    fprintf(stderr, "[push stats] general sub-step: %llu issued per warp, %llu valid lanes -> utilisation %.3f; queue pops %llu\n", h[2], h[3],
+            h[2] ? (double)h[3] / (double)(h[2] * 32) : 0.0, h[6]);
+    fprintf(stderr, "[push stats] fresh: %llu batches, %llu lanes finished (%.3f of slots)\n", h[4], h[5], h[4] ? (double)h[5] / (double)(h[4] * 32) : 0.0);
+    unsigned long long z[16] = {};
+    cudaMemcpyToSymbol(g_push_stats, z, sizeof(z));
+#endif
 }
 
 int launch_deposit(Ctx &c, int sp, double del_t) {
