@@ -292,21 +292,23 @@ __device__ __forceinline__ double lean_sqrt(double s) {
 // one) and costs nothing further.  The loop runs while at least `tmin` lanes are in transit.  The table entries of the next two cells
 // are loaded one crossing ahead.  u, t: in/out (state of the last committed crossing); off0: byte offset of the lane's first entry in
 // `tab`; returns the number of committed crossings.
-__device__ __forceinline__ int transit_loop(double &u, double &t, const double2 *tab, unsigned off0, unsigned long long tlim_bits, bool alive, unsigned tmin) {
+__device__ __forceinline__ int transit_loop(double &u, double &t, const double2 *tab, unsigned off0, unsigned long long tlim_bits, bool alive, unsigned tmin,
+                                            bool &out, double &t_fail) {
     // off: byte offset of the lane's current entry in `tab` (a 32-bit add per committed crossing, one IMAD.WIDE per two loads)
     unsigned off = off0;
     double uB, tB;
+    int dead;
     asm volatile("{\n\t"
         ".reg .pred pd, pv;\n\t"
         ".reg .f64 s, y, hs, g, ng, r, g1, ng1, h1, r1, d, e0x, e0y, e1x, e1y;\n\t"
         ".reg .b32 lo, hi, hi2, m, c;\n\t"
         ".reg .b64 tb, ad;\n\t"
-        "setp.eq.s32 pd, %7, 0;\n\t"                          // pd: the lane is out (not in transit, or a test failed)
+        "setp.eq.s32 pd, %8, 0;\n\t"                          // pd: the lane is out (not in transit, or a test failed)
         "mov.f64 e0x, 0d0000000000000000;\n\t"
         "mov.f64 e0y, 0d0000000000000000;\n\t"
         "mov.f64 e1x, 0d0000000000000000;\n\t"
         "mov.f64 e1y, 0d0000000000000000;\n\t"
-        "mad.wide.u32 ad, %2, 1, %5;\n\t"
+        "mad.wide.u32 ad, %2, 1, %6;\n\t"
         "@!pd ld.global.nc.v2.f64 {e0x, e0y}, [ad];\n\t"
         "@!pd ld.global.nc.v2.f64 {e1x, e1y}, [ad+16];\n\t"
         "mov.f64 %3, %0;\n\t"
@@ -331,10 +333,10 @@ __device__ __forceinline__ int transit_loop(double &u, double &t, const double2 
         "sub.rn.f64 d, %3, %0;\n\t"
         "fma.rn.f64 %4, d, e0y, %1;\n\t"
         "mov.b64 tb, %4;\n\t"
-        "setp.ge.u64 pd, tb, %6;\n\t"
+        "setp.ge.u64 pd, tb, %7;\n\t"
         "@pd bra TSKIP;\n\t"
         "add.u32 %2, %2, 16;\n\t"
-        "mad.wide.u32 ad, %2, 1, %5;\n\t"
+        "mad.wide.u32 ad, %2, 1, %6;\n\t"
         "ld.global.nc.v2.f64 {e0x, e0y}, [ad+16];\n\t"
         // crossing: B -> A with e1
         "mul.rn.f64 s, %3, %3;\n\t"
@@ -354,21 +356,24 @@ __device__ __forceinline__ int transit_loop(double &u, double &t, const double2 
         "sub.rn.f64 d, %0, %3;\n\t"
         "fma.rn.f64 %1, d, e1y, %4;\n\t"
         "mov.b64 tb, %1;\n\t"
-        "setp.ge.u64 pd, tb, %6;\n\t"
+        "setp.ge.u64 pd, tb, %7;\n\t"
         "@pd bra TSKIP;\n\t"
         "add.u32 %2, %2, 16;\n\t"
         "ld.global.nc.v2.f64 {e1x, e1y}, [ad+32];\n\t"
         "TSKIP:\n\t"
         "vote.sync.ballot.b32 m, !pd, 0xffffffff;\n\t"
         "popc.b32 c, m;\n\t"
-        "setp.ge.u32 pv, c, %8;\n\t"
+        "setp.ge.u32 pv, c, %9;\n\t"
         "@pv bra TLOOP;\n\t"
+        "selp.s32 %5, 1, 0, pd;\n\t"
         "}"
-        : "+d"(u), "+d"(t), "+r"(off), "=&d"(uB), "=&d"(tB)
+        : "+d"(u), "+d"(t), "+r"(off), "=&d"(uB), "=&d"(tB), "=r"(dead)
         : "l"(tab), "l"(tlim_bits), "r"((int)alive), "r"(tmin)
         : "memory");
     const int k = (int)((off - off0) >> 4);
-    if (k & 1) { u = uB; t = tB; }
+    // the copy that is not the committed one holds the attempt that failed its test
+    if (k & 1) { t_fail = t; u = uB; t = tB; } else t_fail = tB;
+    out = dead != 0;
     return k;
 }
 
@@ -454,6 +459,7 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
                 // for the general sub-step below.  "Reaches the far face within the time left" is decided from the crossing time
                 // instead of from the end-of-step position l_f0 the reference tests first (mod_particleMover.f90:36-44): the same
                 // decision except within the rounding of that formula itself.  ~2x fewer instructions than the general sub-step.
+                bool requeue = false;
                 if (SCHEME != 1) {
                     const bool vpos = v > 0.0;
                     const unsigned tr_span = (unsigned)max(A.NB - 3, 0);          // interior cells 2 .. N_cells-1
@@ -465,7 +471,8 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
                         const unsigned toff = 16u * (unsigned)(tr ? (vpos ? cell : 2 * A.Nh + 3 - cell) : 0);
                         double u = fabs(v);
                         PSTAT(7, 1);
-                        const int k = transit_loop(u, tp, A.ttab, toff, A.tlim_bits, tr, (unsigned)A.transit_min);
+                        bool out; double t_fail;
+                        const int k = transit_loop(u, tp, A.ttab, toff, A.tlim_bits, tr, (unsigned)A.transit_min, out, t_fail);
                         if (k) {
                             nsub += (unsigned)k;
                             PSTAT(1, k);
@@ -474,12 +481,44 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
                             v = vpos ? u : -u;
                             l = (double)(cell + (vpos ? 0 : 1));
                         }
+                        // a lane still in transit when the loop ended goes on as it is (back to the top in registers, or to the queue)
+                        requeue = tr && !out;
+                        // ---- finish stage: a lane whose next crossing would outlast the step ends its sweep inside this cell, almost
+                        // always: the general sub-step's own first branch (stays in the cell, keeps its direction; mod_particleMover.f90:
+                        // 36-47) on the same operands, everything else is left to the general sub-step below
+#ifndef IPIC_FINISH_STAGE
+#define IPIC_FINISH_STAGE 1
+#endif
+                        bool fin = IPIC_FINISH_STAGE && tr && out && (t_fail == t_fail);
+                        if (__any_sync(FULL, fin)) {
+                            const double2 t0 = __ldg(reinterpret_cast<const double2 *>(reinterpret_cast<const CellTabNGP *>(A.tab) + (fin ? cell : 0)));
+                            const double lc = (SCHEME == 2) ? (double)cell : 0.0;
+                            const double lw = l - lc;
+                            const double dtau = del_t - tp;
+                            const double v_f0 = fma(t0.x, dtau, v);
+                            const double l_f0 = fma(__dmul_rn(__dadd_rn(v, v_f0), dtau), t0.y, lw);
+                            const bool inCell = (SCHEME == 2) ? ((int)(l_f0 + 1.0) == 1) : ((int)l_f0 == cell);
+                            fin = fin && inCell && (vpos == (v_f0 > 0.0));
+                            if (fin) {
+                                nsub += 1;
+                                PSTAT(3, 1);
+                                if (MOVE) {
+                                    const unsigned gi = idx & 0x7fffffffu;
+                                    A.l_out[gi] = l_f0 + lc;
+                                    A.vx_out[gi] = v_f0;
+                                } else {
+                                    if (pend != 0) close_run(W, D, lane, gacc, gdacc, pend, cell);
+                                    deposit_add(W, D, lane, gacc, cell, fx_from_double(l_f0 - lw));
+                                }
+                            }
+                        }
+                        valid = valid && !fin;
                     }
                 }
-                bool cont = false;
+                bool cont = requeue;
                 double l_f = l, v_f = v;
-                PSTAT(2, 1);
-                if (valid) {
+                if (__any_sync(FULL, valid && !requeue)) PSTAT(2, 1);
+                if (valid && !requeue) {
                     nsub += 1;
                     PSTAT(3, 1);
                     double dtau = del_t - tp;
@@ -524,7 +563,7 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
                         l_f = l_fw + lc;
                         if (!MOVE) {
                             const double dl = l_fw - lw;
-                            const bool full = (fabs(dl) == 1.0);
+                            const bool full = atB && (fabs(dl) == 1.0);      // a whole cell AND moving on: part of a run
                             const bool right = dl > 0.0;
                             if (pend != 0 && !(full && ((pend > 0) == right))) { close_run(W, D, lane, gacc, gdacc, pend, cell); pend = 0; }
                             if (full) pend = (pend != 0) ? pend : (right ? cell : -cell);
