@@ -74,6 +74,9 @@ static cudaEvent_t chain_start(Ctx &c, bool &own) {
     return e;
 }
 static void chain_close(Ctx &c, cudaEvent_t e1) { ChainMark &m = g_chain[&c]; m.ev = e1; m.launches = c.launches; }
+constexpr size_t kPendingDrainAt = 512, kPendingHardCap = 1 << 16;
+static void drain_completed_timing(Ctx &c);
+static void resolve_timing_blocking(Ctx &c);
 struct Timed {
     Ctx &c; const char *name; cudaEvent_t e0 = nullptr, e1 = nullptr; bool own0 = true;
     Timed(Ctx &c_, const char *n) : c(c_), name(n) {
@@ -84,10 +87,35 @@ struct Timed {
         cudaEventRecord(e1, c.stream);
         PendingTiming pt{name, e0, e1};
         pt.own0 = own0;
-        g_pending[&c].push_back(pt);
+        auto &pend = g_pending[&c];
+        pend.push_back(pt);
         chain_close(c, e1);
+        if (pend.size() >= kPendingDrainAt && (pend.size() % 64) == 0) drain_completed_timing(c);
+        if (pend.size() >= kPendingHardCap) resolve_timing_blocking(c);      // the device is > 65536 brackets behind: wait for it
     }
 };
+// Brackets whose closing mark has already completed are folded into the totals and their events recycled, without waiting for anything:
+// a host that never asks for timings (the level-1 Fortran drop-in calls depositJ / moveParticles for millions of steps) would otherwise
+// grow the pending list and the event pool without bound.  The newest entry stays pending: the next bracket may chain on its closing mark.
+static void drain_completed_timing(Ctx &c) {
+    auto &pend = g_pending[&c];
+    if (pend.size() < 2) return;
+    size_t m = 0;
+    while (m + 1 < pend.size() && cudaEventQuery(pend[m].e1) == cudaSuccess) ++m;
+    if (m == 0) return;
+    for (size_t i = 0; i < m; ++i) {
+        PendingTiming &p = pend[i];
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) { Timing &t = c.timing[p.name]; t.ms += ms; t.launches += 1; }
+        if (p.own0) g_pool[&c].push_back(p.e0);
+        // an entry left behind that chains on this closing mark takes it over (the last one, should several share it)
+        long owner = -1;
+        for (size_t j = m; j < pend.size() && j < m + 8; ++j) if (!pend[j].own0 && pend[j].e0 == p.e1) owner = (long)j;
+        if (owner >= 0) pend[(size_t)owner].own0 = true;
+        else g_pool[&c].push_back(p.e1);
+    }
+    pend.erase(pend.begin(), pend.begin() + (long)m);
+}
 static void resolve_timing(Ctx &c) {
     auto &pend = g_pending[&c];
     if (pend.empty()) return;
@@ -101,6 +129,8 @@ static void resolve_timing(Ctx &c) {
     }
     pend.clear();
 }
+
+static void resolve_timing_blocking(Ctx &c) { resolve_timing(c); }
 
 static int check(Ctx *c) { if (!c) { set_error("null handle"); return IPIC_ERR_ARG; } cudaSetDevice(c->device); return IPIC_OK; }
 #define CTX(h) Ctx *c = reinterpret_cast<Ctx *>(h); { int _rc = check(c); if (_rc) return _rc; }
@@ -162,6 +192,7 @@ static int move_all(Ctx &c, double del_t) {
             if (st.refIdx > 0) RC(map_reflected(c, s, st.delIdx > 0));
             st.N_p = S.n;
             S.n_collide = S.n;                            // numToCollide = N_p (mod_particleMover.f90:263)
+            S.coll_taken = 0; S.coll_epoch += 1;
             if (c.nranks > 1) { /* per-rank statistics; callers all-reduce the scalars they need */ }
             // real(int)/real(int): single-precision division as in mod_particleMover.f90:265-266
             const float denom = (float)(int)(st.N_p + st.delIdx);
@@ -411,7 +442,7 @@ int ipic_destroy(ipic_handle h) {
     collisions_free(*c);
     injection_free(*c);
     diagnostics_free(*c);
-    for (auto &s : c->sp) { if (s.l) cudaFree(s.l); if (s.l2) cudaFree(s.l2); if (s.refl) cudaFree(s.refl); if (s.refList) cudaFree(s.refList); }
+    for (auto &s : c->sp) { if (s.l) cudaFree(s.l); if (s.l2) cudaFree(s.l2); if (s.refl) cudaFree(s.refl); if (s.refList) cudaFree(s.refList); if (s.refLive) cudaFree(s.refLive); }
     double *dp[] = {c->d_grid, c->d_dx, c->d_hinv, c->d_phi, c->d_phi_f, c->d_rho, c->d_J, c->d_E, c->d_a, c->d_b, c->d_c, c->d_cp, c->d_m, c->d_pcr, c->d_work,
                     c->d_rho_i, c->d_scal, c->d_phi_k, c->d_res_k, c->d_norms, c->d_loss, c->d_Ef, c->d_Eh};
     for (double *p : dp) if (p) cudaFree(p);
@@ -841,7 +872,12 @@ int ipic_reset_collision_stats(ipic_handle h, int32_t set) {
     st.totalNumberCollidableParticles = 0;
     return IPIC_OK;
 }
-int ipic_set_num_to_collide(ipic_handle h, int32_t sp, int64_t n) { CTX(h); SPECIES(sp); c->sp[sp].n_collide = n; return IPIC_OK; }
+int ipic_set_num_to_collide(ipic_handle h, int32_t sp, int64_t n) {
+    CTX(h); SPECIES(sp);
+    SpeciesDev &S = c->sp[sp];
+    S.n_collide = n; S.coll_taken = 0; S.coll_epoch += 1;      // a new step: nothing selected yet
+    return IPIC_OK;
+}
 int ipic_mcc_permutation(uint64_t n, uint64_t key, uint64_t j0, uint64_t count, uint64_t *out) {
     if (!out || n == 0 || j0 + count > n) { set_error("mcc permutation: need j0 + count <= n"); return IPIC_ERR_ARG; }
     const int bits = mcc_bits_hd(n);
@@ -940,6 +976,10 @@ int ipic_host_alloc(void **out, uint64_t bytes) {
 int ipic_host_free(void *p) { if (p) IPIC_CUDA(cudaFreeHost(p)); return IPIC_OK; }
 int ipic_get_timing(ipic_handle h, const char *name, double *ms, int64_t *launches) {
     CTX(h);
+    if (name && std::string(name) == "__pending") {                 // brackets not folded into the totals yet, events parked in the pool (no sync)
+        *ms = (double)g_pool[c].size(); *launches = (int64_t)g_pending[c].size();
+        return IPIC_OK;
+    }
     resolve_timing(*c);
     if (name && std::string(name) == "depositJ_kernels") {         // the sum of the per-species (or paired) sweep entries
         *ms = 0.0; *launches = 0;

@@ -28,7 +28,8 @@ constexpr double k_B_c = 1.380649e-23;
 
 struct CollArgs {
     double *l, *vx, *vy, *vz;                  // primary species
-    long long N, k;                            // numToCollide, numberSelected
+    long long N, k;                            // the step's collidable range (permutation domain), numberSelected of this set
+    long long j0;                              // candidates of earlier sets of the same primary in this step: this set's are j0 .. j0+k-1
     int bits; unsigned long long key;          // candidate -> particle bijection
     unsigned long long seed, stream0;          // PCG stream of candidate j: (seed, stream0 + j)
     int nC, nE;
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(MCC_THREADS) k_collide(const CollArgs A) {
     int cdone = -1;                 // collision that happened (index in the set), -1 = null collision
     double incE = 0.0, loss = 0.0;
     if (j < A.k) {
-        const unsigned long long pidx = mcc_permute_hd((unsigned long long)j, (unsigned long long)A.N, A.bits, A.key);
+        const unsigned long long pidx = mcc_permute_hd((unsigned long long)(A.j0 + j), (unsigned long long)A.N, A.bits, A.key);
         unsigned long long st, inc;
         pcg_seed(st, inc, A.seed, A.stream0 + (unsigned long long)j);
         const double loc = A.l[pidx];
@@ -224,6 +225,7 @@ int collision_set_create(Ctx &c, int nC, int nE, double red_mass, double sumMass
     CollSet S;
     S.nC = nC; S.nE = nE; S.primary = prim; S.target = targ;
     S.reducedMass = red_mass; S.sumMass = sumMass; S.redMassIon = redMassTriple; S.seed = seed;
+    if (c.sp[prim].coll_seed == 0) c.sp[prim].coll_seed = seed ^ 0x2545F4914F6CDD1DULL;
     auto SIG = [&](int j, int i) { return sigmaArray[(size_t)j + (size_t)nE * (size_t)i]; };   // 0-based (lengthArrays, numberCollisions)
     std::vector<double> svmax(nC, 0.0);
     for (int i = 0; i < nC; ++i)
@@ -294,7 +296,9 @@ int generate_collision(Ctx &c, int set, double del_t) {
     st.P_null = P_null;
     st.numberSelected = 0; st.ionizations = 0;
     if (P_null > 0.5) { set_error("P_null greater than 50%"); return IPIC_ERR_STOP; }      // :126-129
-    const long long N = (P.n_collide < 0) ? P.n : std::min(P.n_collide, P.n);
+    const long long Nrange = (P.n_collide < 0) ? P.n : std::min(P.n_collide, P.n);     // the step's collidable range (permutation domain)
+    const long long taken = std::min(P.coll_taken, Nrange);
+    const long long N = Nrange - taken;                                                  // numToCollide as this set sees it (:221-231)
     st.totalNumberCollidableParticles += N;
     const unsigned long long seed = S.seed + 0x632BE59BD9B4E019ULL * (unsigned long long)(c.rank + 1);
     const unsigned long long call = S.calls++;
@@ -336,9 +340,11 @@ int generate_collision(Ctx &c, int set, double del_t) {
 
     CollArgs A{};
     A.l = P.l; A.vx = P.vx; A.vy = P.vy; A.vz = P.vz;
-    A.N = N; A.k = k;
-    A.bits = mcc_bits_hd((unsigned long long)N);
-    A.key = seed ^ (0xA0761D6478BD642FULL * (call + 1));
+    A.N = Nrange; A.k = k; A.j0 = taken;
+    A.bits = mcc_bits_hd((unsigned long long)Nrange);
+    // one permutation per primary species and step: sets that share the primary walk through it one after the other
+    A.key = (P.coll_seed + 0x632BE59BD9B4E019ULL * (unsigned long long)(c.rank + 1)) ^ (0xA0761D6478BD642FULL * (P.coll_epoch + 1));
+    P.coll_taken = taken + k;
     A.seed = seed; A.stream0 = call << 36;
     A.nC = S.nC; A.nE = S.nE; A.energy = S.d_energy; A.sigma = S.d_sigma;
     for (int i = 0; i < S.nC; ++i) { A.thr[i] = S.thr[i]; A.type[i] = S.type[i]; }

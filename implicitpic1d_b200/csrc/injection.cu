@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(INJ_THREADS) k_inject_pairs(const PairArgs A) 
 struct RedrawArgs {
     double *vx, *vy, *vz;
     const unsigned *list; long long n;     // refRecordIdx (post-compaction, 0-based)
+    const unsigned char *live;             // 0: the reflected particle was absorbed later in the step -- the entry names another particle: skipped
     long long n_alive;                     // entries >= N_p name no particle (reflected, then absorbed, last of the array)
     unsigned long long seed, stream0;
     double vth, cs, half_mw;
@@ -126,7 +127,8 @@ __global__ void __launch_bounds__(INJ_THREADS) k_redraw_reflected(const RedrawAr
     double en = 0.0;
     if (j < A.n) {
         const unsigned idx = A.list[j];
-        if ((long long)idx < A.n_alive) {
+        // entries are distinct particles once the absorbed ones are dropped (two threads never share an idx)
+        if ((long long)idx < A.n_alive && (!A.live || A.live[j])) {
         unsigned long long st, inc;
         pcg_seed(st, inc, A.seed, A.stream0 + (unsigned long long)j);
         double v[3] = {A.vx[idx], A.vy[idx], A.vz[idx]};
@@ -253,7 +255,7 @@ static int redraw_reflected(Ctx &c, int sp, int mode, double vth, double cs, uns
     double *partial, *out;
     int rc = inj_scratch(c, blocks, &partial, &out); if (rc) return rc;
     RedrawArgs A{};
-    A.vx = S.vx; A.vy = S.vy; A.vz = S.vz; A.list = S.refList; A.n = n; A.n_alive = S.n;
+    A.vx = S.vx; A.vy = S.vy; A.vz = S.vz; A.list = S.refList; A.live = S.refLive; A.n = n; A.n_alive = S.n;
     A.seed = inj_seed(c); A.stream0 = (call << 36) | ((unsigned long long)(sp + 1) << 32);
     A.vth = vth; A.cs = cs; A.half_mw = 0.5 * S.mass * S.w_p; A.bcL = c.h_bc[0]; A.mode = mode; A.ion = (sp == 1);
     A.partial = partial;

@@ -87,10 +87,19 @@ struct SpeciesDev {
     ipic_move_stats stats{};
     long long depositSubsteps = 0;
     long long n_collide = -1;              // numToCollide (mod_particle.f90:17); < 0 = all
+    // null-collision sets that share this primary within one step draw their candidates from ONE keyed permutation of the collidable
+    // range, one after the other: a particle is selected at most once per step, as in the reference, whose serial loop swaps every
+    // selected particle behind the range and stores the reduced numToCollide (mod_NullCollision.f90:221-231)
+    long long coll_taken = 0;              // candidates already drawn since numToCollide was last set
+    unsigned long long coll_epoch = 0;     // bumped whenever numToCollide is set: keys the permutation of the step
+    unsigned long long coll_seed = 0;      // seed of the first collision set created with this primary
     // refRecordIdx (mod_particle.f90:19, mod_particleMover.f90:226-231): particles first reflected at a Neumann wall in the last move
     unsigned char *refl = nullptr; long long refl_cap = 0;      // per-particle flags written by the move kernel
     unsigned *refList = nullptr; long long refList_cap = 0;     // flagged indices, ascending; after the move: post-compaction indices
     long long nRef = 0;
+    // refLive[j] = 1: entry j names the reflected particle itself; 0: that particle was absorbed later in the same step, so the entry
+    // (kept for parity with the reference's list) names its successor's slot -- the refluxing kernels skip it
+    unsigned char *refLive = nullptr; long long refLive_cap = 0;
     std::vector<long long> slab_off_prev;  // thread-slab offsets before the last compaction: the slab a reflection was recorded in
     std::vector<int> refSlabCount;         // refIdx(T): entries of refList per thread slab, in list order
 };

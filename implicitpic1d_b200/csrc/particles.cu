@@ -1435,7 +1435,7 @@ int compact_species(Ctx &c, int sp) {
 // tileOffset[tile] + (alive particles of the tile before it); a flagged particle that was absorbed later in the same step keeps its
 // entry, which then names the slot of its successor, exactly as the reference's `i - delIdx` does.
 __global__ void k_map_reflected(const unsigned *__restrict__ pre, long long nref, const double *__restrict__ l_old,
-                                const long long *__restrict__ tileOffset, unsigned *post) {
+                                const long long *__restrict__ tileOffset, unsigned *post, unsigned char *live) {
     const int lane = threadIdx.x & 31;
     const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;    // one warp per entry
     if (w >= nref) return;
@@ -1446,7 +1446,7 @@ __global__ void k_map_reflected(const unsigned *__restrict__ pre, long long nref
     cnt = __reduce_add_sync(FULL, cnt);
     // A particle absorbed later in the same step keeps its entry: the reference stored `i - delIdx` at the reflection, which after the
     // compaction is the slot of the next surviving particle (mod_particleMover.f90:226-231 records before the particle's fate is known).
-    if (lane == 0) post[w] = (unsigned)(tileOffset[tile] + cnt);
+    if (lane == 0) { post[w] = (unsigned)(tileOffset[tile] + cnt); live[w] = (l_old[i] >= 0.0) ? 1 : 0; }
 }
 
 int collect_reflected(Ctx &c, int sp) {
@@ -1493,12 +1493,18 @@ int map_reflected(Ctx &c, int sp, bool compacted) {
             s.refSlabCount[t] += 1;
         }
     }
-    if (!compacted) return IPIC_OK;                            // nothing absorbed: indices are already final
+    if (s.refLive_cap < s.nRef) {
+        if (s.refLive) cudaFree(s.refLive);
+        s.refLive_cap = s.nRef + s.nRef / 4 + 1024;
+        IPIC_CUDA(cudaMalloc(&s.refLive, (size_t)s.refLive_cap));
+    }
+    IPIC_CUDA(cudaMemsetAsync(s.refLive, 1, (size_t)s.nRef, c.stream));
+    if (!compacted) return IPIC_OK;                            // nothing absorbed: indices are already final, every entry is its own particle
     unsigned *post = s.refList + s.refList_cap / 2;
     const long long warps_per_block = 8;
     c.launches += 1;
     k_map_reflected<<<(unsigned)((s.nRef + warps_per_block - 1) / warps_per_block), 256, 0, c.stream>>>(s.refList, s.nRef, s.l2 /* pre-compaction bank */,
-                                                                                                          c.d_tileOffset, post);
+                                                                                                          c.d_tileOffset, post, s.refLive);
     IPIC_CUDA(cudaGetLastError());
     // every entry is kept, in order; one that names the slot behind the last survivor of its slab (the reflected particle was the last of
     // the slab and was absorbed) is what the reference holds too -- consumers skip indices >= N_p
@@ -1543,7 +1549,7 @@ int upload_species(Ctx &c, int sp, const double *ps, const int32_t *N_p, int T, 
     }
     s.slab_off[T] = off;
     s.n = n;
-    s.n_collide = n;
+    s.n_collide = n; s.coll_taken = 0; s.coll_epoch += 1;
     if (n > 0) {
         c.launches += 1; k_aos_to_soa<<<c.num_sms * 4, 256, 0, c.stream>>>(reinterpret_cast<const double4 *>(stage), n, s.l, s.vx, s.vy, s.vz);
         IPIC_CUDA(cudaGetLastError());
@@ -1643,7 +1649,7 @@ int generate_species(Ctx &c, int sp, long long n, double T_eV, double v_drift, u
                                                      seed + 0x1000003ULL * (unsigned long long)sp, alpha, distType);
     IPIC_CUDA(cudaGetLastError());
     s.n = n;
-    s.n_collide = n;
+    s.n_collide = n; s.coll_taken = 0; s.coll_epoch += 1;
     s.slab_off.clear();
     IPIC_CUDA(cudaStreamSynchronize(c.stream));
     return IPIC_OK;
@@ -1673,7 +1679,11 @@ int sort_species(Ctx &c, int sp) {
     SpeciesDev &s = c.sp[sp];
     const long long n = s.n;
     if (n <= 1) return IPIC_OK;
-    if (n >= (1ll << 32)) { set_error("sort: more than 2^32 particles per GPU"); return IPIC_ERR_UNSUPPORTED; }
+    if (n >= (1ll << 31)) { set_error("sort: more than 2^31-1 particles of one species per GPU"); return IPIC_ERR_UNSUPPORTED; }
+    // refRecordIdx (post-compaction indices of the last move) does not survive a permutation: a sort between ipic_move_particles and the
+    // refluxing / injection calls that consume the list would redraw the wrong particles, so the list is dropped here (ipic1d_b200.h)
+    s.nRef = 0;
+    std::fill(s.refSlabCount.begin(), s.refSlabCount.end(), 0);
     if (n > c.cap_sort) {
         if (c.d_sort) cudaFree(c.d_sort);
         c.cap_sort = n + n / 8 + 4096;
@@ -1699,6 +1709,7 @@ int sort_species(Ctx &c, int sp) {
     IPIC_CUDA(cudaStreamSynchronize(c.stream));
     swap_banks(s);
     s.slab_off.clear();   // slab identity is not preserved by a sort
+    s.n_collide = s.n; s.coll_taken = 0; s.coll_epoch += 1;   // nor is the prefix that excluded this step's newborn: every particle is collidable again
     return IPIC_OK;
 }
 

@@ -196,6 +196,21 @@ class nullCollision:
                 with open(os.path.join(d, "CollisionDiag_%d.dat" % (i + 1)), "a") as f:
                     f.write(" ".join("%16.8E" % v for v in vals) + "\n")
 
+    def writeAveCollisionDiag(self, particleList, targetParticleList, dirName, timeInterval):
+        """AveCollisionDiag.dat of solveSimulationFinalAverage (mod_simulation.f90:401-412): one line per collision over the averaging window,
+        format (I3, 1x), 5(es16.8, 1x)"""
+        d = self._dir(particleList, targetParticleList, dirName)
+        os.makedirs(d, exist_ok=True)
+        p = particleList[self.reactantsIndx[0] - 1]
+        with np.errstate(divide="ignore", invalid="ignore"), open(os.path.join(d, "AveCollisionDiag.dat"), "w") as f:
+            f.write("Coll #, CollRatio, AveEnergyLoss (eV), AveIncidentEnergy (eV), P_loss(W/m^2), aveCollFreq (Hz/m^2)\n")
+            for i in range(self.numberCollisions):
+                n = np.float64(self.totalAmountCollisions[i])
+                vals = (n / np.float64(self.totalNumberCollidableParticles), self.totalEnergyLoss[i] * 0.5 / K.e / n,
+                        self.totalIncidentEnergy[i] * p.mass * 0.5 / K.e / n, self.totalEnergyLoss[i] * 0.5 * p.w_p / timeInterval,
+                        n * p.w_p / timeInterval)
+                f.write("%3d " % (i + 1) + " ".join("%16.8E" % v for v in vals) + " \n")
+
     def reset_totals(self):
         _lib.check(_lib.load().ipic_reset_collision_stats(self._solver._h, self._set))
         self._refresh()

@@ -26,6 +26,13 @@ class SimulationState:
         self.schemeNum, self.numThread, self.Power, self.nu_h = int(schemeNum), int(numThread), float(Power), float(nu_h)
         self.inelasticEnergyLoss = self.energyError = self.chargeError = self.gaussError = 0.0
         self.steps = 0
+        self.nranks = 1                      # ranks the particles are sharded over (flux-type injections are divided by it)
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self.nranks = dist.get_world_size()
+        except Exception:
+            pass
 
 
 def es(x):
@@ -46,6 +53,25 @@ def generateSaveDirectory(dirName, numberBinaryCollisions=0):
         os.makedirs(os.path.join(dirName, sub), exist_ok=True)
 
 
+def writeDomain(world, dirName):
+    """Domain%writeDomain (NGP mod_domain.f90:327-343: grid, dx_dl, nodeVol, boundaryConditions; CIC mod_domain.f90:314-328: no nodeVol),
+    one unformatted record each"""
+    def rec(name, a, dt):
+        payload = np.ascontiguousarray(a, dtype=dt).tobytes()
+        marker = np.array([len(payload)], dtype="<i4").tobytes()
+        with open(os.path.join(dirName, name), "wb") as f:
+            f.write(marker + payload + marker)
+    rec("domainGrid.dat", world.grid, "<f8")
+    rec("domainDxDl.dat", world.dx_dl, "<f8")
+    if world.scheme != sch.CIC:
+        dx = np.asarray(world.dx_dl, dtype=np.float64)
+        nodeVol = np.empty(world.NumberXNodes)                  # makeArraysFromGrid (NGP mod_domain.f90:257-261)
+        nodeVol[1:-1] = (dx[:-1] + dx[1:]) / 2.0
+        nodeVol[0], nodeVol[-1] = 0.5 * dx[0], 0.5 * dx[-1]
+        rec("domainNodeVol.dat", nodeVol, "<f8")
+    rec("domainBoundaryConditions.dat", world.boundaryConditions, "<i4")
+
+
 def writePhi(phi, CurrentDiagStep, boolAverage, dirName):
     """:28-46"""
     os.makedirs(os.path.join(dirName, "Phi"), exist_ok=True)
@@ -54,7 +80,19 @@ def writePhi(phi, CurrentDiagStep, boolAverage, dirName):
 
 
 def _interstep(st, solver, particleList, targetParticleList, nullCollisionList, world, del_t, currDel_t):
-    """what runs between two implicit steps (:161-168): all of it on the device"""
+    """what runs between two implicit steps (:161-168): all of it on the device.  `pinj.numFluxPart` is the whole plasma's figure
+    (numThread x the reference's per-thread one); under torch.distributed every rank injects its 1 / world_size share of it."""
+    nranks = getattr(st, "nranks", 1)
+    flux_all = pinj.numFluxPart
+    if nranks > 1:
+        pinj.numFluxPart = flux_all / float(nranks)
+    try:
+        _interstep_body(st, solver, particleList, targetParticleList, nullCollisionList, world, del_t, currDel_t)
+    finally:
+        pinj.numFluxPart = flux_all
+
+
+def _interstep_body(st, solver, particleList, targetParticleList, nullCollisionList, world, del_t, currDel_t):
     if pinj.heatingBool:
         pinj.maxwellianHeating(particleList[0], None, st.fractionFreq, st.T_e, currDel_t, del_t)
     if pinj.addLostPartBool:
@@ -125,6 +163,7 @@ def solveSimulation(st, solver, particleList, targetParticleList, nullCollisionL
     sch.loadParticleDensity(particleList, world, True)
     sch.WriteParticleDensity(particleList, world, 0, False, d)
     writePhi(solver.phi, 0, False, d)
+    writeDomain(world, d)                                                  # :147
     st.currentTime = pastDiagTime = st.startSimulationTime
     currDel_t = remainDel_t = del_t
     CurrentDiagStep = 1
@@ -164,6 +203,8 @@ def solveSimulation(st, solver, particleList, targetParticleList, nullCollisionL
             chargeTotal = energyLoss = momentum = 0.0
             for j, p in enumerate(particleList):
                 p.writeLocalTemperature(CurrentDiagStep, d, numCells)
+                if getattr(st, "writeRestartFiles", True):
+                    p.writePhaseSpace(d)                                   # :229: the restart files, rewritten at every dump
                 momentum += p.getTotalMomentum()[0] + float(np.sum(p.momentumLoss)) * p.mass * p.w_p
                 chargeTotal += float(np.sum(accumW[j])) * p.q * p.w_p
                 ke = p.getTotalKE()
@@ -291,27 +332,67 @@ def solveSimulationFinalAverage(st, solver, particleList, targetParticleList, nu
     accumE = [np.zeros(2) for _ in particleList]
     accumW = [np.zeros(2) for _ in particleList]
     phi_average = np.zeros(world.NumberXNodes)
+    for p in particleList:
+        p.densities = np.zeros(world.NumberXNodes)                              # :331-335; every load below accumulates (reset = .false.)
     startTime = st.currentTime
     currDel_t = remainDel_t = del_t
     i = 0
+    # wall-loss convergence check (:348-352, 379-386): every 200 del_t / fractionFreq the running mean power to the walls is tested for
+    # a relative standard deviation below 1e-6 over the window
+    lastCheckTime = startTime
+    checkTimeDivision = 200.0 * del_t / st.fractionFreq
+    window_loss = []
+    RF_ave = 0.0
+    bc = world.boundaryConditions
     while st.currentTime - startTime < averagingTime:
         remainDel_t, currDel_t = solvePotential(solver, particleList, world, del_t, remainDel_t, currDel_t, st.currentTime)
         for j, p in enumerate(particleList):
             accumE[j] += p.energyLoss
             accumW[j] += p.wallLoss
         _interstep(st, solver, particleList, targetParticleList, nullCollisionList, world, del_t, currDel_t)
-        sch.loadParticleDensity(particleList, world, i == 0)
-        phi_average += solver.phi_f
+        sch.loadParticleDensity(particleList, world, False)
+        phi_f = solver.phi_f                                                    # aveRFVoltage(.true., ...) (NGP mod_potentialSolver.f90:469-475)
+        phi_average += phi_f
+        if bc[0] == 4:
+            RF_ave += phi_f[0]
+        elif bc[-1] == 4:
+            RF_ave += phi_f[-1]
         st.currentTime += currDel_t
         i += 1
+        window_loss.append(sum(float(np.sum(p.energyLoss)) for p in particleList) / (st.currentTime - startTime))
+        if st.currentTime - lastCheckTime > checkTimeDivision:
+            w = np.array(window_loss)
+            meanLoss = w.sum() / float(w.size)
+            stdLoss = np.sqrt(np.sum((w - meanLoss) ** 2) / float(w.size))
+            if meanLoss != 0.0 and stdLoss / meanLoss < 1e-6:
+                break
+            window_loss = []
+            lastCheckTime = st.currentTime
     for p in particleList:
         p.densities = p.densities / float(i)                                    # :389
-    writePhi(phi_average / float(i), 0, True, d)
+    phi_average = phi_average / float(i)                                        # aveRFVoltage(.false., ...): phi_f becomes the average (:477-481)
+    solver.phi_f = phi_average
+    st.RF_ave = RF_ave / float(i) if getattr(solver, "RF_rad_frequency", 0.0) else RF_ave
+    writePhi(phi_average, 0, True, d)
     span = st.currentTime - startTime
     chargeLossTotal = sum(float(np.sum(accumW[j])) * p.q_times_wp for j, p in enumerate(particleList))
     ELossTotal = sum(float(np.sum(accumE[j])) * p.mass * p.w_p * 0.5 for j, p in enumerate(particleList))
     st.inelasticEnergyLoss = _collision_loss(nullCollisionList, particleList)
+    for nc in nullCollisionList:                                                # BinaryCollisions/<a>_on_<b>/AveCollisionDiag.dat (:401-412)
+        nc.writeAveCollisionDiag(particleList, targetParticleList, d, span)
     dens = sch.WriteParticleDensity(particleList, world, 0, True, d)
+    # gaussError of the averaged state (:413-417): rho from the averaged densities against the averaged potential
+    # (WriteParticleDensity leaves densities(:, 1) = thread-summed weights * w_p, periodic ends folded -- NGP mod_Scheme.f90:102-108, CIC alike)
+    rho_ave = np.zeros(world.NumberXNodes)
+    for p in particleList:
+        D = np.asarray(p.densities, dtype=np.float64) * p.w_p
+        if world.scheme != sch.CIC and world.boundaryConditions[0] == 3:
+            D = D.copy()
+            D[0] = D[0] + D[-1]
+            D[-1] = D[0]
+        rho_ave = rho_ave + D * p.q
+    solver.rho = rho_ave
+    st.gaussError = solver.getError_tridiag_Poisson(world)
     with open(os.path.join(d, "GlobalDiagnosticDataAveraged.dat"), "w") as f:
         f.write("Steps Averaged, Averaging Time, Collision Loss (W/m^2), ParticleCurrentLoss (A/m^2), ParticlePowerLoss(W/m^2), gaussError\n")
         f.write("%10d " % i + " ".join(es(x) for x in (span, st.inelasticEnergyLoss / span, chargeLossTotal / span, ELossTotal / span, st.gaussError)) + "\n")

@@ -101,7 +101,11 @@ int ipic_generate_particles(ipic_handle h, int32_t species, int64_t n, double T_
  * density perturbation of amplitude alpha (rejection sampling) and the matching position-dependent drift. */
 int ipic_generate_particles_dist(ipic_handle h, int32_t species, int64_t n, double T_eV, double v_drift, double alpha, int distType,
                                  uint64_t seed);
-/* periodic cell sort (counting sort on INT(l)); does not change any deposited quantity. */
+/* periodic cell sort (stable radix sort on INT(l * subbins) + gather); does not change any deposited quantity.
+ * Ordering contract: call it at a step boundary, i.e. BEFORE ipic_move_particles / ipic_solve_potential of the step, never between the
+ * move and the calls that consume the move's per-particle records.  A sort permutes the arrays, so it drops refRecordIdx (the list
+ * ipic_reflux_particles / ipic_inject_at_boundary / ipic_get_ref_record read: empty afterwards) and resets numToCollide to N_p (the
+ * prefix that excluded particles born during the step no longer exists).  At most 2^31 - 1 particles of one species per GPU. */
 int ipic_sort_particles(ipic_handle h, int32_t species);
 
 /* ---- field state -----------------------------------------------------------*/
@@ -236,8 +240,11 @@ int ipic_velocity_histograms(ipic_handle h, int32_t species, int32_t binNumber, 
  * Random numbers: a counter-based PCG32 stream per (seed, rank, call, collision candidate) instead of the reference's
  * per-thread ran2 states, and the `numberSelected` collision candidates are drawn without replacement through a keyed
  * bijection of [0, numToCollide) instead of the swap-to-end loop (:222-227) -- the same uniform subset statistically,
- * with no serial dependence.  Particles keep their array positions; products of ionization are appended in candidate order,
- * so a run is bit-reproducible for a given seed.  Results agree with the reference statistically (moments), not bit-wise. */
+ * with no serial dependence.  Collision sets that share a primary species draw from ONE such bijection per step, one after the other
+ * (the second set's candidates start where the first set's ended, and its numToCollide is the reduced one, :221-231), so a particle is
+ * selected at most once per step however many sets name its species; a "step" starts whenever numToCollide is set (by the mover, by
+ * ipic_set_num_to_collide, by an upload / load / sort).  Particles keep their array positions; products of ionization are appended in
+ * candidate order, so a run is bit-reproducible for a given seed.  Results agree with the reference statistically (moments), not bit-wise. */
 #define IPIC_MAX_COLLISIONS 16
 int ipic_add_target_particle(ipic_handle h, double mass, double density, double temperature, int32_t *target);
 int ipic_null_collision_create(ipic_handle h, int32_t numberCollisions, int32_t lengthArrays, double red_mass, double sumMass,
@@ -305,6 +312,10 @@ int ipic_get_launch_count(ipic_handle h, int64_t *n);
  * maps them with c_f_pointer.  Plain (pageable) memory works too, only slower. */
 int ipic_host_alloc(void **out, uint64_t bytes);
 int ipic_host_free(void *p);
+/* device time and bracket count of a named section since the last reset (CUDA events on the library's stream; "depositJ_kernels" is the
+ * sum of the per-species sweep entries).  The call waits for the stream.  Brackets are folded into the totals as their events complete,
+ * so a host that never asks keeps a bounded list (name "__pending": launches = brackets not folded in yet, ms = events parked for
+ * re-use; no wait). */
 int ipic_get_timing(ipic_handle h, const char *name, double *ms, int64_t *launches);
 int ipic_reset_timing(ipic_handle h);
 int ipic_synchronize(ipic_handle h);

@@ -339,3 +339,47 @@ def test_injection_edge_cases_and_error_codes():
     _lib.check(L.ipic_velocity_extrema(s1._h, 0, out.ctypes.data_as(_lib._dp)))
     assert out[0] == 0.0 and out[1] == 0.0 and out[2] == 0.1 * op.e * 2.0 / op.m_e
     s1.close()
+
+
+@pytest.mark.parametrize("name", NEUMANN)
+def test_refluxParticles_after_a_domain_crossing_step(name):
+    """A step long enough for electrons to be reflected at the Neumann wall AND absorbed at the other wall: their refRecordIdx entries name
+    the successor's slot (reference: i - delIdx), which may itself be listed -- two entries, one particle.  The device redraws every
+    reflected particle that survived exactly once and skips the entries of absorbed ones: no particle outside the list changes, the
+    energy tally equals the actual change of sum(m w v^2 / 2) (it would not if two threads raced on one particle), and the result is
+    bit-reproducible."""
+    runs = []
+    for rep in range(2):
+        d, o, world, solver, plist, del_t = moved_states(name, mult=400.0)
+        T_e, T_i = d["T_e"], d["T_i"]
+        before = [alive(p) for p in plist]
+        listed, dup = [], 0
+        for sp, p in enumerate(plist):
+            refIdx, rec = p.refRecord()
+            assert np.array_equal(refIdx, o.counters(sp)["refIdx"])
+            off = np.concatenate([[0], np.cumsum(p.N_p.astype(np.int64))])
+            ent = np.concatenate([rec[t].astype(np.int64) - 1 + off[t] for t in range(p.numThread)]) if refIdx.sum() else np.zeros(0, dtype=np.int64)
+            dup += ent.size - np.unique(ent).size
+            listed.append(ent)
+        assert o.counters(0)["delIdx"].sum() > 0 and listed[0].size > 0
+        e0 = pinj.energyAddColl
+        pinj.refluxParticles(plist, T_e, T_i, None, world)
+        en_gpu = pinj.energyAddColl - e0
+        after = [alive(p) for p in plist]
+        want, scale = 0.0, 0.0
+        for sp, p in enumerate(plist):
+            b, a = before[sp], after[sp]
+            assert a.shape == b.shape
+            changed = np.nonzero(np.any(a != b, axis=1))[0]
+            assert np.all(np.isin(changed, listed[sp]))                    # nothing outside refRecordIdx is touched
+            assert np.array_equal(a[:, 0], b[:, 0])
+            if changed.size:
+                vx = a[changed, 1]
+                assert np.all(vx > 0) if d["bcL"] == 2 else np.all(vx < 0)
+            want += (ke(a, p) - ke(b, p)).sum()
+            scale += ke(a[changed], p).sum() + ke(b[changed], p).sum()
+        assert abs(en_gpu - want) <= 1e-12 * max(scale, 1e-300)
+        runs.append(after)
+        solver.close()
+    for sp in range(2):
+        assert np.array_equal(runs[0][sp], runs[1][sp])

@@ -169,14 +169,17 @@ def test_num_to_collide_excludes_particles_born_this_step():
     n_e, n_i = plist[0].count(), plist[1].count()
     ncs_g[0].generateCollision(plist, tl, del_t=2e-10)
     assert plist[0].count() > n_e
+    k1 = ncs_g[0].numberSelected
     ncs_g[1].generateCollision(plist, tl, del_t=5e-9)
     assert ncs_g[1].totalNumberCollidableParticles == n_i
+    # a second call within the same step sees the range the first one left: the selected particles were taken out of it
+    # (mod_NullCollision.f90:221-231 stores the reduced numToCollide), and the newborn are still excluded
     ncs_g[0].generateCollision(plist, tl, del_t=2e-10)
-    assert ncs_g[0].totalNumberCollidableParticles == 2 * n_e
+    assert ncs_g[0].totalNumberCollidableParticles == n_e + (n_e - k1)
     n_now = plist[0].count()
-    _lib.check(_lib.load().ipic_set_num_to_collide(solver._h, 0, -1))        # < 0: every particle
+    _lib.check(_lib.load().ipic_set_num_to_collide(solver._h, 0, -1))        # < 0: every particle; a new step starts
     ncs_g[0].generateCollision(plist, tl, del_t=2e-10)
-    assert ncs_g[0].totalNumberCollidableParticles == 2 * n_e + n_now
+    assert ncs_g[0].totalNumberCollidableParticles == n_e + (n_e - k1) + n_now
     solver.close()
 
 
@@ -203,6 +206,7 @@ def test_gpu_swarm_reproduces_bolsig_collision_frequency():
         for _ in range(steps):
             vx += accel
             torch.cuda.synchronize()
+            _lib.check(L.ipic_set_num_to_collide(solver._h, 0, -1))          # what the mover does every step (mod_particleMover.f90:263)
             nc.generateCollision(plist, tl, del_t=del_t)
     freq = nc.totalAmountCollisions.sum() / steps / del_t / plist[0].count()
     x = nc.sigmaVMax * n_gas * del_t
@@ -300,4 +304,36 @@ def test_library_constructor_matches_the_reference_run_log():
         assert nc.collisionType.tolist() == [c["collisionType"] for c in ref["collisions"]]
         assert nc.energyThreshold.tolist() == [c["energyThreshold"] for c in ref["collisions"]]
         assert nc.lengthArrays == ref["lengthArrays"]
+    solver.close()
+
+
+def test_two_sets_with_one_primary_never_select_a_particle_twice_in_a_step():
+    """Two nullCollision sets whose primary is the electrons (electrons on two gases): the reference's serial loop swaps every selected
+    particle behind the collidable range and stores the reduced numToCollide (mod_NullCollision.f90:221-231), so the second set cannot
+    pick a particle the first one collided, and its totalNumberCollidableParticles counts the reduced range.  Here both sets walk one
+    keyed permutation of the step's range, one after the other."""
+    o, (e, ion), seeds, ncs_o, solver, plist, tl, ncs_a = ar_states(ppt=20000)
+    ncs_b = ip.readNullCollisionInputs(["Ar_electron_table.dat"], plist, tl, collision_dir=DATA, seed=987654321)
+    a = [g for g in ncs_a if g.reactantsIndx[0] == 1][0]
+    b = [g for g in ncs_b if g.reactantsIndx[0] == 1][0]
+    pe = plist[0]
+    N = pe.count()
+    del_t = 2.5e-10                                                       # P_null ~ 0.28: independent draws would share ~0.08 N particles
+    L = _lib.load()
+    for step in range(2):
+        for p in plist:
+            _lib.check(L.ipic_set_num_to_collide(solver._h, p._index, p.count()))
+        N = pe.count()
+        s0 = alive(pe)[:N, 1:4].copy()
+        tot_b0 = getattr(b, "totalNumberCollidableParticles", 0)
+        a.generateCollision(plist, tl, del_t=del_t)
+        s1 = alive(pe)[:N, 1:4].copy()
+        b.generateCollision(plist, tl, del_t=del_t)
+        s2 = alive(pe)[:N, 1:4].copy()
+        c1 = np.any(s1 != s0, axis=1)
+        c2 = np.any(s2 != s1, axis=1)
+        assert 0.1 * N < c1.sum() <= a.numberSelected and 0.05 * N < c2.sum() <= b.numberSelected
+        assert not np.any(c1 & c2)                                        # disjoint: nobody collides twice in the step
+        assert b.totalNumberCollidableParticles - tot_b0 == N - a.numberSelected
+        assert abs(b.numberSelected - b.P_null * (N - a.numberSelected)) <= 1.0
     solver.close()

@@ -555,3 +555,24 @@ def test_cell_sort_is_a_stable_sort():
                 ip.moveParticles(solver, plist, world, deck_del_t(d))    # shuffle the cells a little
     finally:
         solver.close()
+
+
+def test_timing_state_stays_bounded_without_queries():
+    """The level-1 Fortran drop-in calls depositJ / moveParticles for millions of steps and never reads a timing: brackets whose events have
+    completed are folded into the totals as the run goes (no synchronisation), so the pending list and the event pool stay bounded, and
+    no bracket is lost."""
+    d = DECKS["ngp_rf"]
+    o = build_oracle(d)
+    world, solver, plist = build_cuda_from_oracle(d, o)
+    del_t = deck_del_t(d)
+    solver.reset_timing()
+    n = 3000
+    for _ in range(n):
+        ip.depositJ(solver, plist, world, del_t)
+    _, pending = solver.timing("__pending")
+    assert pending < 1500, pending                                        # two brackets per species per call + field ops: ~15000 opened
+    ms, cnt = solver.timing("depositJ_sp0")
+    assert cnt == n and ms > 0.0
+    parked, pending = solver.timing("__pending")
+    assert pending == 0 and parked < 4000
+    solver.close()

@@ -86,6 +86,14 @@ def test_solveSimulation_with_reinjection_and_reflux_on_the_device(tmp_path):
     dens = read_record(os.path.join(str(tmp_path), "Density", "density_e_3.dat"))
     assert np.mean(dens[2:-2]) == pytest.approx(d["n_ave"], rel=0.1)
     assert os.path.exists(os.path.join(str(tmp_path), "SimulationFinalData.dat"))
+    # the domain files of writeDomain (mod_simulation.f90:147) and the restart files rewritten at every dump (:229)
+    assert read_record(os.path.join(str(tmp_path), "domainGrid.dat")).size == d["Nx"]
+    assert read_record(os.path.join(str(tmp_path), "domainDxDl.dat")).size == d["Nx"] - 1
+    nv = read_record(os.path.join(str(tmp_path), "domainNodeVol.dat"))
+    assert nv.size == d["Nx"] and nv.sum() == pytest.approx(d["L"], rel=1e-12)
+    for t in range(1, d["T"] + 1):
+        f = os.path.join(str(tmp_path), "PhaseSpace", "phaseSpace_%s_thread%d.dat" % (plist[0].name, t))
+        assert os.path.getsize(f) == 32 * int(plist[0].N_p[t - 1])
     solver.close()
 
 
@@ -111,6 +119,12 @@ def test_final_average_with_argon_collisions_on_the_device(tmp_path):
     assert read_record(os.path.join(str(tmp_path), "Phi", "phi_Average.dat")).size == d["Nx"]
     ga = open(os.path.join(str(tmp_path), "GlobalDiagnosticDataAveraged.dat")).read().splitlines()
     assert int(ga[1].split()[0]) == steps and float(ga[1].split()[2]) > 0.0           # collision loss (W/m^2) of the window
+    # gaussError is that of the AVERAGED state (mod_simulation.f90:413-417: rho from the averaged densities, phi_f = the averaged potential)
+    assert float(ga[1].split()[5]) == pytest.approx(st.gaussError, rel=1e-7)
+    assert 0.0 < st.gaussError < 100.0            # averaged net charge against the averaged potential over 10 steps: O(1) particle noise, not O(1e9)
+    ac = open(os.path.join(str(tmp_path), "BinaryCollisions", "e_on_Ar", "AveCollisionDiag.dat")).read().splitlines()   # :401-412
+    nc_e = [nc for nc in ncs if nc.reactantsIndx[0] == 1][0]
+    assert len(ac) == 1 + nc_e.numberCollisions and len(ac[1].split()) == 6 and int(ac[1].split()[0]) == 1
     # 8 steps of histogram passes; each pass puts every electron inside (Emin, EMax) on two bins
     npass = hist.EHist[0].sum() / plist[0].count()
     assert 7.0 < npass < 9.5
