@@ -411,6 +411,7 @@ def run_cuda_arm(args, w):
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        solver.reset_timing()
         f0.record(stream)
         sub2, h2d, d2h = 0, 0, 0
         for _ in range(e2e_steps):
@@ -436,8 +437,11 @@ def run_cuda_arm(args, w):
             ms2_max, sub2_all = mx[0].item(), sm[1].item()
         else:
             ms2_max, sub2_all = ms2, float(sub2)
+        t_up, n_up = solver.timing("upload")
+        t_dn, n_dn = solver.timing("download")
         e2e = {"value": sub2_all / (ms2_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
                "steps": e2e_steps, "ms_per_step": ms2_max / e2e_steps,
+               "upload_ms_per_step": t_up / e2e_steps, "download_ms_per_step": t_dn / e2e_steps,
                "path": "pinned host phaseSpace(4,finalIdx,1) -> ipic_upload_particles -> ipic_solve_potential -> ipic_download_particles"}
         for p in plist:
             p.phaseSpace = None

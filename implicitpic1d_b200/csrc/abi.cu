@@ -147,7 +147,7 @@ static int read_counters(Ctx &c, unsigned long long *out /* NSP_MAX*8 */) {
 }
 
 // one particle sweep of all species into the fixed-point grids (+ all-reduce across ranks)
-static int sweep_deposit(Ctx &c, double del_t) {
+static int sweep_deposit(Ctx &c, double del_t, const int *stop = nullptr) {
     // Event marks are not free: a record between two kernels keeps the second from starting under the tail of the first (measured at C5:
     // 10 records per nonlinear iteration cost 1.7 ms per step).  The species' launches therefore share their marks -- the end of one
     // species' sweep is the start of the next -- and "depositJ_kernels" is the sum of the per-species entries (ipic_get_timing, solver stats).
@@ -157,11 +157,11 @@ static int sweep_deposit(Ctx &c, double del_t) {
     } else {
         for (int s = 0; s < (int)c.sp.size(); ++s) {
             Timed ts(c, s == 0 ? "depositJ_sp0" : (s == 1 ? "depositJ_sp1" : "depositJ_spN"));      // chained: one mark between two sweeps
-            RC(launch_deposit(c, s, del_t));
+            RC(launch_deposit(c, s, del_t, stop));
         }
     }
     if (c.nranks > 1) { Timed t(c, "allreduce_J"); RC(allreduce_acc(c)); }
-    c.sweeps += 1;
+    if (!stop) c.sweeps += 1;                    // sweeps enqueued ahead of the decision are counted once the outcome is known
     return IPIC_OK;
 }
 
@@ -235,48 +235,58 @@ static int reset_voltage(Ctx &c) {
 }
 
 // solveDivAmpereAnderson  mod_nonLinSolvers.f90:85-160
+// The loop's decisions (converged / stagnated / go on, :111-134) are taken on the device by the fused field kernel of every iteration
+// (field.cu OP_AND_DECIDE); the host enqueues `and_chunk` iterations ahead -- two sweeps, the J all-reduce, one field launch each -- and
+// reads the outcome once per chunk from pinned memory.  Iterations enqueued behind the one that ended the solve are no-ops (each kernel
+// reads the state word first).  One hand-off per chunk instead of two per iteration: the GPU no longer idles for a PCIe round trip plus
+// three launches between the residual and the next sweep.
 static int solve_div_ampere_anderson(Ctx &c, double del_t) {
-    const int m = c.m_Anderson, M1 = m + 1;
-    std::vector<double> normResidual(M1 + 1, 0.0);
-    auto fmodulo = [](int a, int p) { int r = a % p; return r < 0 ? r + p : r; };
     c.normHist.clear();
     int status = 0; double norm = 0.0;
+    if (!c.d_and_state) { set_error("ipic_initialize_solver has not been called"); return IPIC_ERR_ARG; }
+    IPIC_CUDA(cudaMemsetAsync(c.d_and_state, 0, 4 * sizeof(int), c.stream));
+    c.h_and[1] = 0; c.h_and[2] = 0;
     { Timed t(c, "field_kernels"); RC(field_anderson_begin(c)); }
     RC(sweep_deposit(c, del_t));
     { Timed t(c, "field_kernels"); RC(field_anderson_step(c, 0, 0, del_t, &status, &norm)); }
-    normResidual[1] = norm;
     c.normHist.push_back(norm);
     // eps_a * SQRT(real(NumberXNodes)): single-precision square root in the reference (:111); NGP_Periodic: N_h (:102)
     const bool ef = (c.scheme == IPIC_SCHEME_NGP_PERIODIC);
-    const double eps_tol = c.eps_r * normResidual[1] + c.eps_a * (double)std::sqrt((float)(ef ? c.Nh : c.Nx));
-    for (int i = 1; i <= c.maxIter; ++i) {
-        const int index = fmodulo(i, M1) + 1;
-        RC(sweep_deposit(c, del_t));
-        { Timed t(c, "field_kernels"); RC(field_anderson_step(c, i, 1, del_t, &status, &norm)); }
-        normResidual[index] = norm;
-        c.normHist.push_back(norm);
-        c.lastNorm = norm;
-        if (norm < eps_tol) {
-            { Timed t(c, "field_kernels"); RC(field_anderson_step(c, i, 3, del_t, &status, &norm)); }
-            RC(move_all(c, del_t));
-            c.iterNumPicard = ef ? i : i + 1;                     // NGP_Periodic :113
-            return IPIC_OK;
+    const double eps_tol = c.eps_r * norm + c.eps_a * (double)std::sqrt((float)(ef ? c.Nh : c.Nx));
+    const int chunk = std::max(1, c.and_chunk);
+    int state = 0, i_end = 0;
+    for (int i0 = 1; i0 <= c.maxIter && state == 0; i0 += chunk) {
+        const int i1 = std::min(c.maxIter, i0 + chunk - 1);
+        unsigned long long seq = 0;
+        for (int i = i0; i <= i1; ++i) {
+            RC(sweep_deposit(c, del_t, c.d_and_state));
+            seq = ++c.norm_seq;
+            { Timed t(c, "field_kernels"); RC(field_anderson_iter(c, i, del_t, eps_tol, seq)); }
         }
-        if (i > m) {
-            double sumPast;
-            if (ef) {                                             // NGP_Periodic :116-123: mean of the last two
-                if (m > 1) sumPast = (normResidual[fmodulo(i - 1, M1) + 1] + normResidual[fmodulo(i - 2, M1) + 1]) / 2.0;
-                else sumPast = normResidual[fmodulo(i - 1, M1) + 1];
-            } else if (m > 3) {
-                sumPast = normResidual[fmodulo(i - 1, M1) + 1] + normResidual[fmodulo(i - 2, M1) + 1] + normResidual[fmodulo(i - 3, M1) + 1];
-                sumPast = sumPast / 3.0;
-            } else {
-                sumPast = normResidual[fmodulo(i - 1, M1) + 1];
+        // wait for the last field kernel of the chunk to report; the stream is polled now and then so that a failed launch cannot hang the host
+        for (unsigned spins = 1;; ++spins) {
+            if ((unsigned long long)c.h_and[0] == seq) break;
+            if ((spins & 0x3FFF) == 0) {
+                const cudaError_t q = cudaStreamQuery(c.stream);
+                if (q == cudaSuccess) { if ((unsigned long long)c.h_and[0] == seq) break; set_error("k_field finished without reporting the iteration"); return IPIC_ERR_CUDA; }
+                if (q != cudaErrorNotReady) { set_error(std::string("k_field: ") + cudaGetErrorString(q)); return IPIC_ERR_CUDA; }
             }
-            if (normResidual[index] > sumPast) { c.iterNumPicard = c.maxIter; return IPIC_OK; }
         }
-        { Timed t(c, "field_kernels"); RC(field_anderson_step(c, i, 2, del_t, &status, &norm)); }
+        state = (int)c.h_and[1];
+        i_end = state ? (int)c.h_and[2] : i1;
+        const int executed = i_end - i0 + 1;
+        for (int i = i0; i <= i_end; ++i) { c.normHist.push_back(c.h_and_norms[i]); c.lastNorm = c.h_and_norms[i]; }
+        c.sweeps += executed;
+        c.noop_sweeps += (i1 - i0 + 1) - executed;
     }
+    if (state == 1) {
+        RC(move_all(c, del_t));
+        c.iterNumPicard = ef ? i_end : i_end + 1;                 // NGP_Periodic :113
+        return IPIC_OK;
+    }
+    // stagnated, or the loop ran out: the push tables / tile counters behind the last launch are not those of a fresh sweep
+    c.tile_zero_mask = 0;
+    if (state == 2) c.iterNumPicard = c.maxIter;
     return IPIC_OK;   // loop exhausted: iterNumPicard left untouched, as in the reference
 }
 
@@ -458,6 +468,9 @@ int ipic_destroy(ipic_handle h) {
     if (c->d_sort) cudaFree(c->d_sort);
     if (c->d_sort_tmp) cudaFree(c->d_sort_tmp);
     if (c->h_scal) cudaFreeHost(c->h_scal);
+    if (c->d_and_state) cudaFree(c->d_and_state);
+    if (c->h_and) cudaFreeHost(const_cast<long long *>(c->h_and));
+    if (c->h_and_norms) cudaFreeHost(c->h_and_norms);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->own_stream);
     delete c;
@@ -698,6 +711,19 @@ int ipic_initialize_solver(ipic_handle h, double eps_a, double eps_r, int solver
     IPIC_CUDA(cudaMalloc(&c->d_phi_k, n * sizeof(double))); IPIC_CUDA(cudaMemset(c->d_phi_k, 0, n * sizeof(double)));
     IPIC_CUDA(cudaMalloc(&c->d_res_k, n * sizeof(double))); IPIC_CUDA(cudaMemset(c->d_res_k, 0, n * sizeof(double)));
     IPIC_CUDA(cudaMalloc(&c->d_norms, (m_Anderson + 2) * sizeof(double)));
+    if (!c->d_and_state) {
+        IPIC_CUDA(cudaMalloc(&c->d_and_state, 4 * sizeof(int))); IPIC_CUDA(cudaMemset(c->d_and_state, 0, 4 * sizeof(int)));
+        void *hp = nullptr;
+        IPIC_CUDA(cudaMallocHost(&hp, 8 * sizeof(long long)));
+        std::memset(hp, 0, 8 * sizeof(long long));
+        c->h_and = static_cast<volatile long long *>(hp);
+    }
+    if (c->cap_and_norms < maxIter + 2) {
+        if (c->h_and_norms) cudaFreeHost(c->h_and_norms);
+        c->cap_and_norms = std::max(maxIter, 0) + 2;
+        IPIC_CUDA(cudaMallocHost(&c->h_and_norms, (size_t)c->cap_and_norms * sizeof(double)));
+        std::memset(c->h_and_norms, 0, (size_t)c->cap_and_norms * sizeof(double));
+    }
     // initializeNitsol(maxIter, m_Anderson, NumberXNodes)  mod_nonLinSolvers.f90:63-65
     delete static_cast<nitsol::Solver *>(c->nitsol_state);
     c->nitsol_state = nullptr;
@@ -954,6 +980,7 @@ int ipic_set_option(ipic_handle h, const char *name, double value) {
     else if (k == "pair_warps") c->pair_warps = (int)value;
     else if (k == "tile_order") c->tile_order = (int)value;
     else if (k == "timing") c->timing_on = value != 0.0;
+    else if (k == "anderson_chunk") c->and_chunk = std::max(1, (int)value);
     else if (k == "use_tma") { /* accepted for compatibility: the streaming path is register-prefetched */ }
     else if (k == "lazy_compaction") c->lazy_compaction = (int)value;
     else if (k == "norm_flag") c->norm_flag = (int)value;
@@ -985,16 +1012,19 @@ int ipic_get_timing(ipic_handle h, const char *name, double *ms, int64_t *launch
         *ms = 0.0; *launches = 0;
         for (const char *k : {"depositJ_sp0", "depositJ_sp1", "depositJ_spN", "depositJ_pair"}) {
             auto f = c->timing.find(k);
-            if (f != c->timing.end()) { *ms += f->second.ms; *launches += f->second.launches; }
+            if (f != c->timing.end()) { *ms += f->second.ms; *launches += f->second.launches - (f->second.launches > 0 ? c->noop_sweeps : 0); }
         }
         return IPIC_OK;
     }
     auto it = c->timing.find(name ? name : "");
     if (it == c->timing.end()) { *ms = 0.0; *launches = 0; return IPIC_OK; }
     *ms = it->second.ms; *launches = it->second.launches;
+    // sweeps enqueued ahead of the nonlinear solve's decision that turned out to be no-ops are not sweeps (their few microseconds stay in ms)
+    const std::string nm(name);
+    if (nm == "depositJ_sp0" || nm == "depositJ_sp1" || nm == "depositJ_pair") *launches -= std::min<long long>(c->noop_sweeps, *launches);
     return IPIC_OK;
 }
-int ipic_reset_timing(ipic_handle h) { CTX(h); resolve_timing(*c); c->timing.clear(); return IPIC_OK; }
+int ipic_reset_timing(ipic_handle h) { CTX(h); resolve_timing(*c); c->timing.clear(); c->noop_sweeps = 0; return IPIC_OK; }
 int ipic_synchronize(ipic_handle h) { CTX(h); IPIC_CUDA(cudaStreamSynchronize(c->stream)); return IPIC_OK; }
 
 }  // extern "C"

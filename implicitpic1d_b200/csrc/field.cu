@@ -27,6 +27,8 @@ enum : unsigned {
     OP_HALF_E = 1u << 9,       // EField + push tables
     OP_DIAG = 1u << 10,
     OP_RESID_F = 1u << 11,     // f = x - unknown  (funcNitsol)
+    OP_AND_DECIDE = 1u << 17,  // after OP_AND_RESID: convergence / stagnation test on the device (mod_nonLinSolvers.f90:111-134); the ops that
+                               // follow in the same launch are chosen by its outcome
     // NGP_Periodic (E-field form), OpenMP/NGP_Periodic/src/mod_potentialSolver.f90 / mod_Scheme.f90
     OP_P_RHO = 1u << 12,       // depositRho epilogue: raw sums, no wall fix-ups, no smoothing
     OP_P_POISSON = 1u << 13,   // solve_tridiag_Poisson + EField = -grad phi, EField_f = EField
@@ -58,6 +60,9 @@ struct FieldArgs {
     // host spins on -- no D2H copy, no driver synchronisation on the critical path of a nonlinear iteration
     double *h_norm; unsigned long long *h_seq; unsigned long long seq;
     unsigned long long *counters;   // [nsp][8]: slot 6 of a species is the tile counter of its push launch, zeroed by the half-E op that precedes a sweep
+    // OP_AND_DECIDE
+    int *and_state; double eps_tol; int eform;
+    volatile long long *h_and; double *h_and_norms;
 };
 
 // 1-based accessors so that every stencil reads like the reference line it restates
@@ -234,8 +239,16 @@ __device__ long long g_field_phase[16];
 #else
 #define PH(k) do { } while (0)
 #endif
-__global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsigned ops) {
+__global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsigned ops_in) {
     extern __shared__ __align__(16) double sm[];
+    unsigned ops = ops_in;
+    if (ops & OP_AND_DECIDE) {
+        // an iteration enqueued ahead of the decision that ended the solve: report and leave (the sweeps in front of it did the same)
+        if (A.and_state[0] != 0) {
+            if (threadIdx.x == 0) { __threadfence_system(); A.h_and[0] = (long long)A.seq; }
+            return;
+        }
+    }
 #ifdef IPIC_FIELD_PHASES
     if (threadIdx.x < 16) g_field_phase[threadIdx.x] = 0;
     __syncthreads();
@@ -475,6 +488,7 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
             part += r * r;
         }
         const double nrm = sqrt(block_sum(part));
+        __shared__ int s_dec;
         if (threadIdx.x == 0) {
             A.norms[index - 1] = nrm; A.scal[0] = nrm;
             if (A.h_seq) {
@@ -482,8 +496,41 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
                 __threadfence_system();
                 *reinterpret_cast<volatile unsigned long long *>(A.h_seq) = A.seq;
             }
+            if (ops & OP_AND_DECIDE) {
+                // solveDivAmpereAnderson :111-134 (NGP_Periodic :102-123): converged below eps_tol; after m iterations, stagnated when the
+                // norm exceeds the mean of the last three (periodic tree: two) -- the same operations in the same order as the host loop
+                const int i = A.and_i, m = A.and_m;
+                int dec = 0;
+                if (nrm < A.eps_tol) dec = 1;
+                else if (i > m) {
+                    double sumPast;
+                    if (A.eform) {
+                        if (m > 1) sumPast = __ddiv_rn(__dadd_rn(A.norms[fmodulo(i - 1, M1)], A.norms[fmodulo(i - 2, M1)]), 2.0);
+                        else sumPast = A.norms[fmodulo(i - 1, M1)];
+                    } else if (m > 3) {
+                        sumPast = __dadd_rn(__dadd_rn(A.norms[fmodulo(i - 1, M1)], A.norms[fmodulo(i - 2, M1)]), A.norms[fmodulo(i - 3, M1)]);
+                        sumPast = __ddiv_rn(sumPast, 3.0);
+                    } else {
+                        sumPast = A.norms[fmodulo(i - 1, M1)];
+                    }
+                    if (nrm > sumPast) dec = 2;
+                }
+                s_dec = dec;
+                if (dec) { A.and_state[0] = dec; A.and_state[1] = i; }
+                // outcome to the host (pinned, device-addressable): norm history, state, then the sequence number it waits on.  Published
+                // here, before the mixing and the push tables, so that the host enqueues the next chunk while this launch finishes
+                A.h_and_norms[i] = nrm;
+                if (dec) { A.h_and[1] = dec; A.h_and[2] = i; }
+                __threadfence_system();
+                A.h_and[0] = (long long)A.seq;
+            }
         }
         __syncthreads();
+        if (ops & OP_AND_DECIDE) {
+            const int dec = s_dec;
+            if (dec == 1) ops &= ~OP_AND_MIX;                                     // converged: E-half + tables of the solved field for the mover
+            else if (dec == 2) ops &= ~(OP_AND_MIX | OP_HALF_E | OP_P_HALF_E);    // stagnated: the caller halves the step and starts over
+        }
         PH(5);
     }
     if (ops & OP_AND_MIX) {
@@ -1044,6 +1091,18 @@ int field_anderson_step(Ctx &c, int i, int phase, double del_t, int *status, dou
     }
     if (status) *status = 0;
     return IPIC_OK;
+}
+
+// One whole Anderson iteration in one launch, decision included: finalize J, Ampere, residual + norm, convergence / stagnation test, then
+// mixing + E-half + push tables (continue), E-half + tables only (converged) or nothing (stagnated).  The launch is a no-op when an
+// earlier iteration ended the solve.  The host does not wait for it (solve_div_ampere_anderson reads the outcome once per chunk).
+int field_anderson_iter(Ctx &c, int i, double del_t, double eps_tol, unsigned long long seq) {
+    FieldArgs A = make_args(c);
+    A.del_t = del_t; A.and_i = i;
+    const unsigned fj = eform(c) ? OP_P_FINALIZE_J : OP_FINALIZE_J, am = eform(c) ? OP_P_AMPERE : OP_AMPERE, he = eform(c) ? OP_P_HALF_E : OP_HALF_E;
+    A.and_state = c.d_and_state; A.eps_tol = eps_tol; A.eform = eform(c) ? 1 : 0;
+    A.h_and = c.h_and; A.h_and_norms = c.h_and_norms; A.seq = seq;
+    return run_field(c, A, fj | am | OP_AND_RESID | OP_AND_DECIDE | OP_AND_MIX | he);
 }
 
 // funcNitsol tail: phi_f already holds G(x); f = x - phi_f

@@ -72,6 +72,7 @@ struct PushArgs {
     unsigned long long tlim_bits;   // bit pattern of t_lim (0 when t_lim <= 0): for t >= 0, `bits(t) < tlim_bits` as unsigned integers is `t < t_lim`,
                                // and NaN, -0 and negative t compare high
     unsigned char *refl;       // MOVE, Neumann walls only: per-particle flag "reflected during this step" (refRecordIdx), else null
+    const int *stop;           // depositJ sweeps enqueued ahead of the nonlinear solve's decision: *stop != 0 (converged / stagnated) makes the launch a no-op
     int stay_min;              // a queued batch keeps looping in registers while at least this many lanes continue
     int transit_min;           // the lean face-to-face loop runs while at least this many lanes are in transit
 };
@@ -150,6 +151,14 @@ struct Ctx {
     // Anderson
     double *d_phi_k = nullptr, *d_res_k = nullptr;                // [m+1][Nx]
     double *d_norms = nullptr;
+    // Anderson loop with the decision on the device (field.cu OP_AND_DECIDE): the host enqueues `and_chunk` iterations ahead -- sweeps, the
+    // J all-reduce, the fused field kernel -- and reads the outcome once per chunk.  d_and_state[0]: 0 running, 1 converged, 2 stagnated;
+    // [1]: the iteration that ended the solve.  h_and (pinned): [0] sequence number of the last field kernel that reported, [1] state,
+    // [2] iteration; h_and_norms[i]: residual norm of iteration i
+    int *d_and_state = nullptr;
+    volatile long long *h_and = nullptr; double *h_and_norms = nullptr; int cap_and_norms = 0;
+    int and_chunk = 6;
+    long long noop_sweeps = 0;                                    // sweeps enqueued ahead that turned out to be no-ops (timing counts exclude them)
     int tridiag_mode = IPIC_TRIDIAG_PCR;
     // solver scalars (host mirror; NGP mod_potentialSolver.f90:17-22, CIC :17-23)
     double rho_const = 0, RF_rad_frequency = 0, RF_half_amplitude = 0, RF_voltage = 0;
@@ -217,7 +226,7 @@ void set_error(const std::string &s);
     } while (0)
 
 // ---- launchers implemented in particles.cu ---------------------------------------------------------
-int launch_deposit(Ctx &c, int sp, double del_t);
+int launch_deposit(Ctx &c, int sp, double del_t, const int *stop = nullptr);
 void push_stats_dump();                                 // measurement builds (-DIPIC_PUSH_STATS) only: prints and clears the lane-utilisation counters
 int launch_move(Ctx &c, int sp, double del_t);
 int launch_deposit_pair(Ctx &c, int a, int b, double del_t);
@@ -266,6 +275,7 @@ int field_ampere(Ctx &c, double del_t);
 int field_diag(Ctx &c, int which, double del_t, double *out);
 int field_anderson_begin(Ctx &c);
 int field_anderson_step(Ctx &c, int i, int phase, double eps_tol, int *status, double *norm);
+int field_anderson_iter(Ctx &c, int i, double del_t, double eps_tol, unsigned long long seq);   // fused iteration, decision on the device
 int field_residual(Ctx &c, const double *d_x, double *d_f);
 
 // ---- counter-based PCG32 (one short stream per work item) ------------------------------------------------

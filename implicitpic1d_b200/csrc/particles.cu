@@ -833,6 +833,8 @@ template <int SCHEME, bool MOVE>
 __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const __grid_constant__ PushArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // a sweep enqueued ahead of the nonlinear solve's decision: the field kernel in front of it ended the solve
+    if (!MOVE && A.stop != nullptr && *A.stop != 0) return;
     push_body<SCHEME, MOVE>(A, reinterpret_cast<WarpSmem *>(smem_raw)[warp], lane);
 }
 
@@ -960,11 +962,12 @@ void push_stats_dump() {
 #endif
 }
 
-int launch_deposit(Ctx &c, int sp, double del_t) {
+int launch_deposit(Ctx &c, int sp, double del_t, const int *stop) {
     PushArgs A;
     int rc = make_push_args(c, sp, del_t, A);
     if (rc) return rc;
     if (A.n == 0) return IPIC_OK;
+    A.stop = stop;
     if (c.scheme == IPIC_SCHEME_NGP) return launch_push_v<0, false>(c, A);
     if (c.scheme == IPIC_SCHEME_NGP_PERIODIC) return launch_push_v<2, false>(c, A);
     return launch_push_v<1, false>(c, A);

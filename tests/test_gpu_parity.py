@@ -576,3 +576,42 @@ def test_timing_state_stays_bounded_without_queries():
     parked, pending = solver.timing("__pending")
     assert pending == 0 and parked < 4000
     solver.close()
+
+
+@pytest.mark.parametrize("name", ["ngp_rf", "cic_rf", "ngp_neumann"])
+def test_anderson_decision_on_the_device_is_independent_of_the_chunk(name):
+    """solveDivAmpereAnderson takes its decisions (converged / stagnated / go on, mod_nonLinSolvers.f90:111-134) on the device and the host
+    enqueues `anderson_chunk` iterations ahead; iterations behind the one that ended the solve are no-ops.  Whatever the chunk -- 1 (the
+    host reads every iteration's outcome), the default, or more than the solve needs -- the step is the same step: iteration counts,
+    sweep counts, sub-step counts, residual history and the fields bit for bit, and the oracle's iteration count."""
+    d = DECKS[name]
+    ref = None
+    for chunk in (1, 6, 64):
+        o = build_oracle(d)
+        world, solver, plist = build_cuda_from_oracle(d, o, tridiag_mode=_lib.TRIDIAG_THOMAS)
+        try:
+            solver.set_option("anderson_chunk", chunk)
+            del_t = deck_del_t(d)
+            res = []
+            t, remain, curr = 0.0, del_t, del_t
+            total_sweeps = 0
+            solver.reset_timing()
+            for step in range(3):
+                remain, curr = ip.solvePotential(solver, plist, world, del_t, remain, curr, t)
+                t += curr
+                st = ip.SolverState(solver)
+                total_sweeps += st.sweeps
+                res.append((remain, curr, st.iterNumPicard, st.sweeps, st.substeps, st.amountTimeSplits, tuple(st.normHistory),
+                            solver.phi_f.tobytes(), solver.J.tobytes(), tuple(p.count() for p in plist)))
+                if step == 0:
+                    o.solvePotential(del_t, del_t, del_t, 0.0)
+                    assert st.iterNumPicard == o.solver_stats()["iterNumPicard"] and st.sweeps == o.solver_stats()["sweeps"]
+            # timing counts name executed sweeps only
+            _, n0 = solver.timing("depositJ_sp0")
+            assert n0 == total_sweeps
+        finally:
+            solver.close()
+        if ref is None:
+            ref = res
+        else:
+            assert res == ref, chunk
