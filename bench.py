@@ -251,6 +251,7 @@ def run_cuda_arm(args, w):
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dist = None
+    peer_on = False
     if world_size > 1:
         # stdout carries exactly one JSON line: whatever NCCL_DEBUG level the environment sets goes to a file
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/ipic_bench_nccl_%h_%p.log")
@@ -277,6 +278,9 @@ def run_cuda_arm(args, w):
         dist.broadcast(uid, 0)
         raw = bytes(uid.cpu().numpy().tobytes())
         _lib.check(L.ipic_comm_init(solver._h, world_size, rank, C.c_char_p(raw)))
+        # one node: the J all-reduce of every residual evaluation through peer memory (NVLink) instead of NCCL (csrc/peer.cu)
+        from implicitpic1d_b200.distributed import peer_init
+        peer_on = peer_init(solver, dist, rank, world_size, device=torch.device("cuda", local_rank)) if not args.no_peer else False
     w_p = w["n_ave"] * world.L_domain / N_total_per_species                 # mod_particle.f90:76-82 with SUM(N_p) over all ranks
     m_ion = w["ion_amu"] * K.m_amu - K.m_e                                   # mod_particle.f90:334
     mcc = w.get("mcc")
@@ -539,8 +543,9 @@ def run_cuda_arm(args, w):
                            "substeps_per_particle_per_sweep": substeps / max(particle_sweeps, 1),
                            "sort_every_steps": args.sort_every, "sort_every_steps_ions": args.sort_every * args.sort_ion_factor, "tridiag": "thomas" if args.thomas else "pcr",
                            "l2": "inputs larger than L2: %.2f GB particle stream per sweep per GPU vs 126 MB L2" % (32.0 * n_sp / 1e9),
-                           "parallelism": "particles sharded over %d GPU(s); int64 fixed-point J grid all-reduced (NCCL) per residual evaluation; "
-                                          "field solve replicated" % world_size},
+                           "parallelism": "particles sharded over %d GPU(s); int64 fixed-point J grid all-reduced (%s) per residual evaluation; "
+                                          "field solve replicated" % (world_size, "peer memory over NVLink, csrc/peer.cu" if (world_size > 1 and peer_on)
+                                                                      else "NCCL")},
                 "e2e": e2e, "e2e_resident": e2e_resident, "gpu_launches": n_launch, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "breakdown_ms_per_step": {"depositJ_kernels": dep_ms / args.steps, "moveParticles_kernel": t_move / args.steps,
                                           "compaction": t_comp / args.steps, "field_kernels": t_field / args.steps,
@@ -565,6 +570,7 @@ def main():
     ap.add_argument("--sort-ion-factor", type=int, default=8, help="the ion species is sorted every sort-every x this many steps")
     ap.add_argument("--thomas", action="store_true", help="sequential Thomas solve (bit-parity mode) instead of PCR")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-peer", action="store_true", help="multi-GPU: all-reduce the J grid with NCCL instead of the peer-memory kernels")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU work budget of the cpu_baseline leg")

@@ -118,6 +118,8 @@ SIGNATURES = {
     "ipic_nccl_unique_id": (_i, [_p]),
     "ipic_comm_init": (_i, [_p, _i32, _i32, _p]),
     "ipic_set_option": (_i, [_p, C.c_char_p, _d]),
+    "ipic_peer_export": (_i, [_p, _p]),
+    "ipic_peer_import": (_i, [_p, _i32, _i32, _p]),
     "ipic_set_stream": (_i, [_p, _p]),
     "ipic_get_launch_count": (_i, [_p, C.POINTER(_i64)]),
     "ipic_host_alloc": (_i, [C.POINTER(_p), C.c_uint64]),

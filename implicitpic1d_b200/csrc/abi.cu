@@ -44,8 +44,11 @@ static int nccl_load() {
 constexpr int kNcclUint64 = 5, kNcclSum = 0;
 
 static int allreduce_acc(Ctx &c) {
-    if (c.nranks <= 1 || !c.nccl_comm) return IPIC_OK;
+    if (c.nranks <= 1) return IPIC_OK;
     const size_t count = (size_t)c.sp.size() * 2 * (std::max(c.Nx, c.Nh) + 2);
+    // one node: fold + all-reduce through peer memory (peer.cu), two launches, no NCCL on the path of a residual evaluation
+    if (c.peer_ready && c.peer_reduce) return peer_allreduce_acc(c, count);
+    if (!c.nccl_comm) return IPIC_OK;
     { int frc = fold_acc(c, count); if (frc) return frc; }   // the CTA copies of the grids -> copy 0, which is what crosses NVLink
     int rc = g_nccl.AllReduce(c.d_acc, c.d_acc, count, kNcclUint64, kNcclSum, c.nccl_comm, c.stream);
     if (rc != 0) { set_error(std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?")); return IPIC_ERR_NCCL; }
@@ -174,6 +177,7 @@ static int move_all(Ctx &c, double del_t) {
         for (int s = 0; s < (int)c.sp.size(); ++s) RC(launch_move(c, s, del_t));
     }
     unsigned long long cnt[NSP_MAX * 8];
+    if (c.nranks > 1) RC(peer_check(c));          // a peer that never showed up in a peer-memory all-reduce (the wait gives up instead of hanging)
     RC(read_counters(c, cnt));
     {
         Timed t(c, "compaction");
@@ -448,6 +452,7 @@ int ipic_destroy(ipic_handle h) {
     for (auto &e : g_pool[c]) cudaEventDestroy(e);
     g_pool.erase(c); g_pending.erase(c); g_chain.erase(c);
     if (c->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl_comm);
+    peer_free(*c);
     delete static_cast<nitsol::Solver *>(c->nitsol_state);
     collisions_free(*c);
     injection_free(*c);
@@ -969,6 +974,9 @@ int ipic_comm_init(ipic_handle h, int32_t nranks, int32_t rank, const void *uid)
     return IPIC_OK;
 }
 
+int ipic_peer_export(ipic_handle h, void *handle64) { CTX(h); return peer_export(*c, handle64); }
+int ipic_peer_import(ipic_handle h, int32_t nranks, int32_t rank, const void *handles) { CTX(h); return peer_import(*c, nranks, rank, handles); }
+
 int ipic_set_option(ipic_handle h, const char *name, double value) {
     CTX(h);
     const std::string k(name ? name : "");
@@ -981,6 +989,7 @@ int ipic_set_option(ipic_handle h, const char *name, double value) {
     else if (k == "tile_order") c->tile_order = (int)value;
     else if (k == "timing") c->timing_on = value != 0.0;
     else if (k == "anderson_chunk") c->and_chunk = std::max(1, (int)value);
+    else if (k == "peer_reduce") c->peer_reduce = (int)value;
     else if (k == "use_tma") { /* accepted for compatibility: the streaming path is register-prefetched */ }
     else if (k == "lazy_compaction") c->lazy_compaction = (int)value;
     else if (k == "norm_flag") c->norm_flag = (int)value;

@@ -201,6 +201,10 @@ struct Ctx {
                                   // push launch skips its own memset (one stream operation less between two kernels)
     // multi-GPU
     void *nccl_comm = nullptr; int nranks = 1, rank = 0;
+    // peer-memory all-reduce of the deposition grids (peer.cu): this rank's window (cudaMalloc, exported through CUDA IPC) and the mapped
+    // windows of all ranks of the node
+    void *peer_window = nullptr; std::vector<void *> peer_ptr; bool peer_ready = false; int peer_reduce = 1;
+    unsigned long long peer_seq = 0;
     // timing
     std::map<std::string, Timing> timing;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -243,6 +247,13 @@ int download_species(Ctx &c, int sp, double *ps, int32_t *N_p, int T, int finalI
 int generate_species(Ctx &c, int sp, long long n, double T_eV, double v_drift, unsigned long long seed, double alpha, int distType);
 int sort_species(Ctx &c, int sp);
 int ensure_capacity(Ctx &c, int sp, long long n);
+
+// ---- peer.cu: all-reduce of the deposition grids through peer memory (NVLink), fused with the fold of the CTA copies ----
+int peer_export(Ctx &c, void *handle64);
+int peer_import(Ctx &c, int nranks, int rank, const void *handles);
+int peer_allreduce_acc(Ctx &c, size_t count);
+int peer_check(Ctx &c);
+void peer_free(Ctx &c);
 
 // ---- collisions.cu -----------------------------------------------------------------------------------
 int collision_set_create(Ctx &c, int nC, int nE, double red_mass, double sumMass, double redMassTriple, const double *energyArray, const double *sigmaArray,

@@ -46,12 +46,56 @@ def exchange_unique_id(dist, rank, make_id=None, device=None):
     return bytes(buf.cpu().numpy().tobytes())
 
 
-def comm_init(solver, dist, rank, world_size, device=None):
-    """ipic_comm_init on every rank with the id made on rank 0"""
+def exchange_peer_handles(dist, world_size, my_handle, device=None):
+    """all-gather of the 64-byte CUDA IPC handles of the ranks' peer windows (ipic_peer_export), in rank order"""
+    import torch
+    mine = torch.frombuffer(bytearray(my_handle), dtype=torch.uint8).clone()
+    if device is not None:
+        mine = mine.to(device)
+    out = [torch.zeros_like(mine) for _ in range(world_size)]
+    dist.all_gather(out, mine)
+    return b"".join(bytes(t.cpu().numpy().tobytes()) for t in out)
+
+
+def peer_init(solver, dist, rank, world_size, device=None):
+    """One node: map every rank's window so that the J all-reduce runs through peer memory (include/ipic1d_b200.h: ipic_peer_export /
+    ipic_peer_import).  Returns True when every rank mapped every window; otherwise all ranks stay on NCCL (the choice must be the same
+    everywhere: the ranks take the same decisions or they dead-lock)."""
+    import torch
     if world_size <= 1:
-        return
+        return False
+    L = _lib.load()
+    h = (C.c_char * 64)()
+    ok = 1
+    try:
+        _lib.check(L.ipic_peer_export(solver._h, h))
+    except _lib.IpicError:
+        ok = 0
+    handles = exchange_peer_handles(dist, world_size, bytes(h.raw), device=device)
+    if ok:
+        try:
+            _lib.check(L.ipic_peer_import(solver._h, world_size, rank, C.c_char_p(handles)))
+        except _lib.IpicError:
+            ok = 0
+    t = torch.tensor([ok], dtype=torch.int32)
+    if device is not None:
+        t = t.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    all_ok = bool(int(t.cpu().item()))
+    solver.set_option("peer_reduce", 1.0 if all_ok else 0.0)
+    return all_ok
+
+
+def comm_init(solver, dist, rank, world_size, device=None, peer=True):
+    """ipic_comm_init on every rank with the id made on rank 0; then (one node) the peer-memory windows.  Returns True when the J
+    all-reduce runs through peer memory, False when it is NCCL's."""
+    if world_size <= 1:
+        return False
     uid = exchange_unique_id(dist, rank, device=device)
     _lib.check(_lib.load().ipic_comm_init(solver._h, world_size, rank, C.c_char_p(uid)))
+    if peer and dist.get_backend() == "nccl":
+        return peer_init(solver, dist, rank, world_size, device=device)
+    return False
 
 
 def allreduce_scalars(dist, values, device=None):

@@ -300,6 +300,14 @@ int ipic_maxwellian_heating(ipic_handle h, int32_t species, double compValue, do
  * (pattern of PIC1D/ExplicitPIC_Cpp/src/potential_solver.cpp:142).  unique_id is the 128-byte ncclUniqueId. */
 int ipic_nccl_unique_id(void *out128);
 int ipic_comm_init(ipic_handle h, int32_t nranks, int32_t rank, const void *unique_id128);
+/* Ranks on ONE node (NVLink / NVSwitch): the all-reduce of the deposition grids runs through peer memory instead of NCCL -- every rank
+ * publishes its folded integer grids in a window, raises a flag on all peers, and adds up all ranks' windows itself (integer sums: the
+ * same bits on every rank whatever the order; two launches per residual evaluation).  ipic_peer_export returns the 64-byte CUDA IPC
+ * handle of this rank's window; the host exchanges the handles (torch.distributed all_gather, MPI_Allgather in a Fortran host) and
+ * hands all of them, in rank order, to ipic_peer_import.  Optional: without it (or with option "peer_reduce" = 0) the all-reduce is
+ * NCCL's.  A peer that never shows up makes the waiting kernel give up after ~3 s and the next ipic_move_particles return IPIC_ERR_NCCL. */
+int ipic_peer_export(ipic_handle h, void *handle64);
+int ipic_peer_import(ipic_handle h, int32_t nranks, int32_t rank, const void *handles64_by_rank);
 
 /* ---- tuning / introspection ----------------------------------------------------*/
 int ipic_set_option(ipic_handle h, const char *name, double value);
