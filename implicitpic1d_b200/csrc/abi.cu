@@ -990,6 +990,7 @@ int ipic_set_option(ipic_handle h, const char *name, double value) {
     else if (k == "timing") c->timing_on = value != 0.0;
     else if (k == "anderson_chunk") c->and_chunk = std::max(1, (int)value);
     else if (k == "peer_reduce") c->peer_reduce = (int)value;
+    else if (k == "dump_push_stats") { cudaStreamSynchronize(c->stream); push_stats_dump(); }      // measurement builds (-DIPIC_PUSH_STATS): print + clear
     else if (k == "use_tma") { /* accepted for compatibility: the streaming path is register-prefetched */ }
     else if (k == "lazy_compaction") c->lazy_compaction = (int)value;
     else if (k == "norm_flag") c->norm_flag = (int)value;

@@ -176,7 +176,10 @@ __device__ __forceinline__ void limb_grid_flush(const LimbGrid &g, int n) {
 // =====================================================================================================
 constexpr int SUB = 2;                       // batches per register-staged sub-tile
 constexpr int SUBTILE = 32 * SUB;            // 64 particles
-constexpr int TILE_SUBS = 8;
+#ifndef IPIC_TILE_SUBS
+#define IPIC_TILE_SUBS 8
+#endif
+constexpr int TILE_SUBS = IPIC_TILE_SUBS;
 constexpr int TILE = SUBTILE * TILE_SUBS;    // 512 particles per scheduled tile = one 4 KB L2 prefetch per array
 constexpr int WIN = 4, WLO = 2;              // window slots hold cells base-2, base-1, base+2, base+3 (base, base+1 live in registers)
 constexpr int QCAP = 32 * (SUB + 1);         // continuation queue entries per warp: at most 31 + 32*SUB live
@@ -399,6 +402,8 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
     unsigned nsub = 0, nfev = 0, nabsL = 0, nabsR = 0, nrefl = 0;
 #ifdef IPIC_PUSH_STATS
     unsigned st_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long st_t0_;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(st_t0_));
 #endif
 
     // tile claims run one ahead so that the atomic's latency is never exposed
@@ -408,11 +413,14 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
         t = __shfl_sync(FULL, t, 0);
         // claims are mapped through a stride permutation so that the tiles in flight are spread over the whole
         // domain: expensive regions are met throughout the kernel and concurrent warps deposit to different cells
-        t = (t < ntiles) ? (unsigned)(((unsigned long long)t * A.tile_stride) % ntiles) : ntiles;
+        if (A.tile_mode == 2) t = (t < ntiles) ? ((t & 1u) ? ntiles - 1u - (t >> 1) : (t >> 1)) : ntiles;      // from both ends inwards
+        else t = (t < ntiles) ? (unsigned)(((unsigned long long)t * A.tile_stride) % ntiles) : ntiles;
         if (t < ntiles) {                                    // pull the tile into L2: 32 lanes x 128 B = 4 KB per array
             const size_t off = (size_t)t * TILE + 16u * lane;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(A.l + off));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(A.vx + off));
+            if (16 * lane < TILE) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(A.l + off));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(A.vx + off));
+            }
         }
         return t;
     };
@@ -804,6 +812,13 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
     if (!MOVE) {
         // [0] transit crossings issued per warp (x32 = lane slots)  [1] committed lane crossings  [2] general sub-steps issued per warp
         // [3] valid lanes in them  [4] fresh batches per warp  [5] lanes finished in them  [6] queue pops  [7] transit loop entries
+        {   // when the warps of this launch ran out of work: [8] sum of end times, [9] latest end, [10] earliest start, [11] warps (ns, globaltimer)
+            unsigned long long tnow;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tnow));
+            if (lane == 0) {
+                atomicAdd(&g_push_stats[8], tnow - st_t0_); atomicMax(&g_push_stats[9], tnow - st_t0_); atomicAdd(&g_push_stats[11], 1ull);
+            }
+        }
         const int warp_only[8] = {1, 0, 1, 0, 1, 0, 1, 1};
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -919,6 +934,7 @@ static int make_push_args(Ctx &c, int sp, double del_t, PushArgs &A) {
         while (ntiles > 1 && gcd(st, ntiles) != 1) st += 2;
         A.tile_stride = (unsigned)(ntiles > 1 ? st % ntiles : 1);
         if (c.tile_order == 0 || A.tile_stride == 0) A.tile_stride = 1;
+        A.tile_mode = c.tile_order;
     }
     A.counters = c.d_counters + (size_t)sp * 8;
     A.tile_counter = reinterpret_cast<unsigned *>(c.d_counters + (size_t)sp * 8 + 6);
@@ -957,6 +973,8 @@ void push_stats_dump() {
     fprintf(stderr, "[push stats] general sub-step: %llu issued per warp, %llu valid lanes -> utilisation %.3f; queue pops %llu\n", h[2], h[3],
             h[2] ? (double)h[3] / (double)(h[2] * 32) : 0.0, h[6]);
     fprintf(stderr, "[push stats] fresh: %llu batches, %llu lanes finished (%.3f of slots)\n", h[4], h[5], h[4] ? (double)h[5] / (double)(h[4] * 32) : 0.0);
+    fprintf(stderr, "[push stats] warps: %llu; mean busy time per warp %.1f us; the latest warp of the LONGEST launch ran %.1f us (every launch's latest >= its mean: tail)\n", h[11],
+            h[11] ? (double)h[8] / (double)h[11] * 1e-3 : 0.0, (double)h[9] * 1e-3);
     unsigned long long z[16] = {};
     cudaMemcpyToSymbol(g_push_stats, z, sizeof(z));
 #endif
