@@ -67,6 +67,9 @@ UNIT = "particle-substeps/s"
 SEED = 20261017
 
 
+TRANSIT_FLOOR_CYCLES = 38.7    # scripts/micro/transit_bench2.cu on B200: the shipped crossing loop alone, 8 warps per SM sub-partition
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -513,17 +516,17 @@ def run_cuda_arm(args, w):
     if not paired and n_dep1 > 0:
         ion = 16.0 * n_i / (t_dep1 / n_dep1 * 1e-3) / 1e9                  # the ion sweeps (s = 1 sub-step per particle) are the bytes-bound launches
         roofline["ion_sweeps"] = {"achieved": ion, "peak": peak, "unit": "GB/s", "frac": ion / peak, "avg_launch_ms": t_dep1 / n_dep1}
-    # second bound of the same kernel: the sub-step loop of the electrons is FP64 work, not bytes.  One face-to-face crossing is 14 FP64 + 15 other
+    # second bound of the same kernel: the sub-step loop of the electrons is FP64 work, not bytes.  One face-to-face crossing is 10 FP64 + 12.5 other
     # instructions per warp; FP64 instructions issue every other cycle on sm_100 (scripts/micro/fp64_tput.cu), and the loop in isolation at 8 warps
-    # per sub-partition runs at 46.5 cycles per crossing (scripts/micro/transit_bench.cu) -- that is the floor quoted here.
+    # per sub-partition runs at 38.7 cycles per crossing (scripts/micro/transit_bench2.cu, profiles/r2_micro_transit_bench2.txt) -- the floor quoted here.
     t_e_sweeps, n_e_sweeps = (t_pair, n_pair) if paired else (t_dep0, n_dep0)     # paired: the electrons share the launch with the ions
     if w["scheme"] != 1 and t_e_sweeps > 0:
         props = torch.cuda.get_device_properties(torch.cuda.current_device())
         sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
-        floor = props.multi_processor_count * 4 * sm_hz / 46.5 * 32.0
+        floor = props.multi_processor_count * 4 * sm_hz / TRANSIT_FLOOR_CYCLES * 32.0
         roofline["issue_bound"] = {"what": "electron sub-steps per second inside the depositJ sweeps vs the measured issue floor of the crossing loop",
                                    "achieved": dep_sub_e / (t_e_sweeps * 1e-3), "peak": floor, "frac": dep_sub_e / (t_e_sweeps * 1e-3) / floor,
-                                   "unit": "sub-steps/s", "floor_cycles_per_crossing_per_sm_subpartition": 46.5,
+                                   "unit": "sub-steps/s", "floor_cycles_per_crossing_per_sm_subpartition": TRANSIT_FLOOR_CYCLES,
                                    "electron_substeps_per_particle_per_sweep": dep_sub_e / max(n_e_sweeps * n_e, 1)}
 
     line = None

@@ -164,35 +164,73 @@ __device__ void block_scan_i64(long long *x, int n) {
 
 // Sum the per-species int64 grids (species order, scaled by q*w_p) into dst[0..n-1]; zero the grids.
 // with_runs: add the prefix sum of the species' difference grid (runs of fully traversed cells, see k_push).
+// One CTA works through arrays that live in L2: what a phase costs is the number of dependent L2 round trips (~0.7 us each), not bytes.
+// The loops below therefore issue the loads of CB cells (all copies of the grid) before the first result is used, and the zeroing
+// stores after the last load.
+constexpr int CB = 4;
+__device__ __forceinline__ void collect_batch(unsigned long long *g, int reps, size_t rep_stride, int base, int n, unsigned long long (&q)[CB]) {
+#pragma unroll
+    for (int k = 0; k < CB; ++k) q[k] = 0ull;
+    if (reps == 4) {
+        unsigned long long v[CB][4];
+#pragma unroll
+        for (int k = 0; k < CB; ++k) {
+            const int i = base + k * FT;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) v[k][r] = (i < n) ? __ldcg(g + (size_t)r * rep_stride + i + 1) : 0ull;
+        }
+#pragma unroll
+        for (int k = 0; k < CB; ++k) {
+            const int i = base + k * FT;
+            q[k] = (v[k][0] + v[k][1]) + (v[k][2] + v[k][3]);
+            if (i < n) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) g[(size_t)r * rep_stride + i + 1] = 0ull;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < CB; ++k) {
+            const int i = base + k * FT;
+            if (i < n) {
+                unsigned long long t = 0ull;
+                for (int r = 0; r < reps; ++r) t += __ldcg(g + (size_t)r * rep_stride + i + 1);
+                for (int r = 0; r < reps; ++r) g[(size_t)r * rep_stride + i + 1] = 0ull;
+                q[k] = t;
+            }
+        }
+    }
+}
+
 __device__ void dev_collect(const FieldArgs &A, double *dst, int n, bool with_runs, long long *scratch) {
     for (int s = 0; s < A.nsp; ++s) {
         unsigned long long *g = A.acc + (size_t)s * A.acc_stride;
         if (with_runs) {
             unsigned long long *d = g + A.acc_stride / 2;
-            for (int i = threadIdx.x; i < n; i += FT) {
-                // loads first (independent, in flight together), then the zeroing stores
-                unsigned long long q = 0ull;
-#pragma unroll 4
-                for (int r = 0; r < A.acc_reps; ++r) q += __ldcg(d + (size_t)r * A.acc_rep_stride + i + 1);
-#pragma unroll 4
-                for (int r = 0; r < A.acc_reps; ++r) d[(size_t)r * A.acc_rep_stride + i + 1] = 0ull;
-                scratch[i] = (long long)q;
+            for (int base = threadIdx.x; base < n; base += CB * FT) {
+                unsigned long long q[CB];
+                collect_batch(d, A.acc_reps, A.acc_rep_stride, base, n, q);
+#pragma unroll
+                for (int k = 0; k < CB; ++k) { const int i = base + k * FT; if (i < n) scratch[i] = (long long)q[k]; }
             }
             if (threadIdx.x < A.acc_reps) d[(size_t)threadIdx.x * A.acc_rep_stride + n + 1] = 0ull;   // closing entry of a run that ends on the last cell
             __syncthreads();
             block_scan_i64(scratch, n);
         }
-        for (int i = threadIdx.x; i < n; i += FT) {
-            unsigned long long qq = 0ull;
-#pragma unroll 4
-            for (int r = 0; r < A.acc_reps; ++r) qq += __ldcg(g + (size_t)r * A.acc_rep_stride + i + 1);
-#pragma unroll 4
-            for (int r = 0; r < A.acc_reps; ++r) g[(size_t)r * A.acc_rep_stride + i + 1] = 0ull;
-            long long q = (long long)qq;
-            if (with_runs) q += scratch[i];
-            const double v = (double)q * FX_INV;
-            if (s == 0) dst[i] = v * A.qw[0];
-            else dst[i] = dst[i] + v * A.qw[s];
+        for (int base = threadIdx.x; base < n; base += CB * FT) {
+            unsigned long long qq[CB];
+            collect_batch(g, A.acc_reps, A.acc_rep_stride, base, n, qq);
+#pragma unroll
+            for (int k = 0; k < CB; ++k) {
+                const int i = base + k * FT;
+                if (i < n) {
+                    long long q = (long long)qq[k];
+                    if (with_runs) q += scratch[i];
+                    const double v = (double)q * FX_INV;
+                    if (s == 0) dst[i] = v * A.qw[0];
+                    else dst[i] = dst[i] + v * A.qw[s];
+                }
+            }
         }
         __syncthreads();
     }
@@ -217,11 +255,20 @@ __device__ void dev_tridiag(const FieldArgs &A, double *d, double *tmp) {
     int stride = 1;
     for (int lev = 0; lev < A.pcr_levels; ++lev) {
         const double *al = A.pcr + (size_t)lev * 2 * n, *ga = al + n;
-        for (int i = threadIdx.x; i < n; i += FT) {
-            double v = src[i];
-            if (i - stride >= 0) v = fma(al[i], src[i - stride], v);
-            if (i + stride < n) v = fma(ga[i], src[i + stride], v);
-            dst[i] = v;
+        for (int base = threadIdx.x; base < n; base += CB * FT) {
+            double al_[CB], ga_[CB];
+#pragma unroll
+            for (int k = 0; k < CB; ++k) { const int i = base + k * FT; al_[k] = (i < n) ? __ldg(al + i) : 0.0; ga_[k] = (i < n) ? __ldg(ga + i) : 0.0; }
+#pragma unroll
+            for (int k = 0; k < CB; ++k) {
+                const int i = base + k * FT;
+                if (i < n) {
+                    double v = src[i];
+                    if (i - stride >= 0) v = fma(al_[k], src[i - stride], v);
+                    if (i + stride < n) v = fma(ga_[k], src[i + stride], v);
+                    dst[i] = v;
+                }
+            }
         }
         __syncthreads();
         double *t = src; src = dst; dst = t;
@@ -230,6 +277,52 @@ __device__ void dev_tridiag(const FieldArgs &A, double *d, double *tmp) {
     const double *inv = A.pcr + (size_t)A.pcr_levels * 2 * n;
     for (int i = threadIdx.x; i < n; i += FT) d[i] = src[i] * inv[i];
     __syncthreads();
+}
+
+// Normal equations of the Anderson step for m_k <= 10 history columns, register-blocked: MATMUL(A^T, A) and A^T r with columns
+// fitMat(:, j+1) = r_index - r_col(j) have 55 + 10 distinct sums over the rows.  One warp per sum (the general path below) reads three
+// history columns per sum, 6.4 MB through one SM at N_x = 4097; here a thread loads the 11 values of a row once, forms the 10 differences
+// in registers and adds their products into the sums its group of 256 threads owns (sums p = 4 s + G of group G: 17 or 16 accumulators),
+// so every history column crosses the SM once per group.  Fixed order: a thread's rows ascending, shuffle tree over the warp, the eight
+// warps of the group ascending.  gram[p]: p = k (k + 1) / 2 + j for j <= k < 10, p = 55 + j for (A^T r)_j.
+template <int G>
+__device__ __forceinline__ void gram_group(const double *__restrict__ res_k, int NU, int index, const int *col, int m_k, double *part /* [32 warps][17] */) {
+    const int t = threadIdx.x & 255, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double acc[17];
+#pragma unroll
+    for (int q = 0; q < 17; ++q) acc[q] = 0.0;
+    const double *Ri = res_k + (size_t)(index - 1) * NU;
+    const double *Rc[10];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) Rc[j] = res_k + (size_t)(col[j < m_k ? j : 0] - 1) * NU;
+    for (int r = t; r < NU; r += 256) {
+        const double ri = __ldcg(Ri + r);
+        double d[10];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) d[j] = __ldcg(Rc[j] + r);
+#pragma unroll
+        for (int j = 0; j < 10; ++j) d[j] = (j < m_k) ? ri - d[j] : 0.0;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+#pragma unroll
+            for (int j = 0; j <= k; ++j) {
+                const int p = k * (k + 1) / 2 + j;
+                if ((p & 3) == G) acc[p >> 2] += d[j] * d[k];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+            const int p = 55 + j;
+            if ((p & 3) == G) acc[p >> 2] += d[j] * ri;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 17; ++q) {
+        double x = acc[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if (lane == 0) part[warp * 17 + q] = x;
+    }
 }
 
 #ifdef IPIC_FIELD_PHASES
@@ -545,6 +638,31 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         if (threadIdx.x <= m_k) col[threadIdx.x] = fmodulo(i - m_k + (int)threadIdx.x, M1) + 1;
         __syncthreads();
+        if (m_k <= 10) {
+            // register-blocked sums (gram_group): four groups of 256 threads, each owning a quarter of the 65 sums
+            double *part = alpha + 128;                    // [32][17]
+            double *gram = part + 32 * 17;                 // [68]
+            switch (threadIdx.x >> 8) {
+            case 0: gram_group<0>(A.res_k, NU, index, col, m_k, part); break;
+            case 1: gram_group<1>(A.res_k, NU, index, col, m_k, part); break;
+            case 2: gram_group<2>(A.res_k, NU, index, col, m_k, part); break;
+            default: gram_group<3>(A.res_k, NU, index, col, m_k, part); break;
+            }
+            __syncthreads();
+            if (threadIdx.x < 65) {
+                const int pp = threadIdx.x, g = pp & 3, q = pp >> 2;
+                double x = 0.0;
+                for (int w = 0; w < 8; ++w) x += part[(g * 8 + w) * 17 + q];
+                gram[pp] = x;
+            }
+            __syncthreads();
+            if (threadIdx.x < m_k * m_k) {
+                const int j = threadIdx.x % m_k, k = threadIdx.x / m_k;
+                const int lo = min(j, k), hi = max(j, k);
+                An[j + m_k * k] = gram[hi * (hi + 1) / 2 + lo];
+            }
+            if (threadIdx.x < m_k) bn[threadIdx.x] = gram[55 + threadIdx.x];
+        } else {
         // MATMUL(A^T, A) is symmetric and each entry is the same sum of the same products either way round, so only j <= k is
         // computed (one warp per entry, lanes stride the rows, shuffle tree) and mirrored: bit-identical to computing all m_k^2
         const int ntri = m_k * (m_k + 1) / 2, npairs = ntri + m_k;
@@ -565,6 +683,7 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
             if (lane == 0) { if (k >= 0) { An[j + m_k * k] = acc; An[k + m_k * j] = acc; } else bn[j] = acc; }
+        }
         }
         __syncthreads();
         PH(6);
@@ -624,28 +743,42 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
         if (A.scheme == 0) {
             for (int i = 1 + threadIdx.x; i <= Nh; i += FT) s0[i - 1] = 0.5 * (PHIF(i) + PHI(i) - PHIF(i + 1) - PHI(i + 1));
             __syncthreads();
+            const double *Esm = s0;
             if (A.smooth) {
                 dev_smooth(A, s0, s1);
                 __syncthreads();
-                for (int i = 1 + threadIdx.x; i <= Nh; i += FT) EF(i) = s1[i - 1] / DX(i);
-            } else {
-                for (int i = 1 + threadIdx.x; i <= Nh; i += FT) EF(i) = s0[i - 1] / DX(i);
+                Esm = s1;
             }
-            __syncthreads();
-            for (int s = 0; s < A.nsp; ++s) {
-                CellTabNGP *T = reinterpret_cast<CellTabNGP *>(A.tab) + (size_t)s * A.tab_cells;
-                double2 *TT = A.ttab + (size_t)s * 2 * A.tab_cells;
-                for (int cI = 1 + threadIdx.x; cI <= Nh; cI += FT) {
-                    const double a = A.qm[s] * EF(cI), dx = DX(cI);
-                    CellTabNGP t;
-                    t.a = a; t.hinv = A.hinv[cI - 1]; t.two_a_dx = 2.0 * a * dx; t.inv_a = 1.0 / a;
-                    T[cI] = t;
+            // EField and the push tables of every species in one pass over the cells (dx_dl and 0.5 / dx_dl of a batch loaded together)
+            const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+            for (int base = 1 + threadIdx.x; base <= Nh; base += CB * FT) {
+                double dx_[CB], hv_[CB];
+#pragma unroll
+                for (int k = 0; k < CB; ++k) {
+                    const int cI = base + k * FT;
+                    dx_[k] = (cI <= Nh) ? __ldg(A.dx + cI - 1) : 1.0;
+                    hv_[k] = (cI <= Nh) ? __ldg(A.hinv + cI - 1) : 0.0;
+                }
+#pragma unroll
+                for (int k = 0; k < CB; ++k) {
+                    const int cI = base + k * FT;
+                    if (cI > Nh) continue;
+                    const double dx = dx_[k];
+                    const double E = Esm[cI - 1] / dx;
+                    EF(cI) = E;
                     // wall cells are not transited by the lean loop: NaN makes a lane that reaches one fail its next time test.
                     // Right-movers read entry cI, left-movers the mirrored, negated copy (every lane walks upwards)
                     const bool wall = (cI == 1 || cI == Nh);
-                    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
-                    TT[cI] = wall ? make_double2(qnan, 0.0) : make_double2(t.two_a_dx, t.inv_a);
-                    TT[2 * A.tab_cells - 1 - cI] = wall ? make_double2(qnan, 0.0) : make_double2(-t.two_a_dx, -t.inv_a);
+                    for (int s = 0; s < A.nsp; ++s) {
+                        CellTabNGP *T = reinterpret_cast<CellTabNGP *>(A.tab) + (size_t)s * A.tab_cells;
+                        double2 *TT = A.ttab + (size_t)s * 2 * A.tab_cells;
+                        const double a = A.qm[s] * E;
+                        CellTabNGP t;
+                        t.a = a; t.hinv = hv_[k]; t.two_a_dx = 2.0 * a * dx; t.inv_a = 1.0 / a;
+                        T[cI] = t;
+                        TT[cI] = wall ? make_double2(qnan, 0.0) : make_double2(t.two_a_dx, t.inv_a);
+                        TT[2 * A.tab_cells - 1 - cI] = wall ? make_double2(qnan, 0.0) : make_double2(-t.two_a_dx, -t.inv_a);
+                    }
                 }
             }
         } else {
