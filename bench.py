@@ -390,13 +390,13 @@ def run_cuda_arm(args, w):
     t_coll, _ = solver.timing("collisions")
     n_e, n_i = plist[0].count(), plist[1].count()
 
-    vals = torch.tensor([ms, float(substeps)], dtype=torch.float64, device="cuda")
+    vals = torch.tensor([ms, float(substeps), float(particle_sweeps)], dtype=torch.float64, device="cuda")
     if dist is not None:
         mx = vals.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = vals.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms_max, substeps_all = mx[0].item(), sm[1].item()
+        ms_max, substeps_all, psweeps_all = mx[0].item(), sm[1].item(), sm[2].item()
     else:
-        ms_max, substeps_all = ms, float(substeps)
+        ms_max, substeps_all, psweeps_all = ms, float(substeps), float(particle_sweeps)
     value = substeps_all / (ms_max * 1e-3)
 
     # ---- e2e: the same step through the reference-facing call with HOST phase-space buffers (mod_particle.f90:23 layout) ----
@@ -549,6 +549,9 @@ def run_cuda_arm(args, w):
                            "parallelism": "particles sharded over %d GPU(s); int64 fixed-point J grid all-reduced (%s) per residual evaluation; "
                                           "field solve replicated" % (world_size, "peer memory over NVLink, csrc/peer.cu" if (world_size > 1 and peer_on)
                                                                       else "NCCL")},
+                # the metric counts sub-steps, and sub-steps per particle per sweep are physics (noise level, RF phase): particles x sweeps per
+                # second says how fast the particles are swept whatever they do inside a sweep (what weak scaling measures here)
+                "particle_sweeps_per_s": psweeps_all / (ms_max * 1e-3),
                 "e2e": e2e, "e2e_resident": e2e_resident, "gpu_launches": n_launch, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "breakdown_ms_per_step": {"depositJ_kernels": dep_ms / args.steps, "moveParticles_kernel": t_move / args.steps,
                                           "compaction": t_comp / args.steps, "field_kernels": t_field / args.steps,

@@ -987,6 +987,7 @@ int ipic_set_option(ipic_handle h, const char *name, double value) {
     else if (k == "sort_subbins") c->sort_subbins = (int)value;
     else if (k == "pair_warps") c->pair_warps = (int)value;
     else if (k == "tile_order") c->tile_order = (int)value;
+    else if (k == "tile_subs") c->tile_subs = (int)value;
     else if (k == "timing") c->timing_on = value != 0.0;
     else if (k == "anderson_chunk") c->and_chunk = std::max(1, (int)value);
     else if (k == "peer_reduce") c->peer_reduce = (int)value;

@@ -64,6 +64,7 @@ struct PushArgs {
     unsigned long long acc_rep_stride;   // !MOVE: the grids exist in acc_reps copies, this many entries apart; CTA b deposits into copy b % acc_reps
     int acc_reps;
     unsigned tile_stride;      // stride permutation of the tile order
+    int tile_subs;             // 64-particle sub-tiles per scheduled tile (1, 2, 4 or 8)
     int tile_mode;             // 0 array order, 1 stride permutation, 2 from both ends of the (cell-sorted) array inwards: the wall regions, whose
                                // electrons take the most sub-steps, are claimed first and the cheap bulk fills the end of the launch
     unsigned long long *counters;  // [0] deposit substeps, [1] func evals, [2] absorbed left, [3] absorbed right, [4] first reflections, [5] move substeps
@@ -194,6 +195,7 @@ struct Ctx {
                                // sweep against 1.88 + 0.32 ms) -- both species' sweeps are issue-bound, so running them side by side frees nothing
     int pair_warps = 4;        // warps per CTA (of 32) that start with the second species
     int tile_order = 1;           // 1 = stride-permuted tile order, 0 = in array order, 2 = from both ends inwards
+    int tile_subs = 0;            // 0 = automatic (8 sub-tiles of 64 particles, fewer for small loads)
     int push_blocks = 0;          // 0 = one CTA per SM
     int lazy_compaction = 0;
     int norm_flag = 1;            // 1 = k_field publishes the residual norm into pinned host memory and the host spins on a sequence number;

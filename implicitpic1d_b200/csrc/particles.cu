@@ -179,8 +179,9 @@ constexpr int SUBTILE = 32 * SUB;            // 64 particles
 #ifndef IPIC_TILE_SUBS
 #define IPIC_TILE_SUBS 8
 #endif
-constexpr int TILE_SUBS = IPIC_TILE_SUBS;
-constexpr int TILE = SUBTILE * TILE_SUBS;    // 512 particles per scheduled tile = one 4 KB L2 prefetch per array
+constexpr int TILE_SUBS = IPIC_TILE_SUBS;   // sub-tiles per scheduled tile for loads that keep every warp busy: 512 particles = one 4 KB L2 prefetch per
+                                            // array; small loads get smaller tiles (make_push_args: at least ~3 tiles per resident warp)
+constexpr int TILE_MAX = SUBTILE * TILE_SUBS;
 constexpr int WIN = 4, WLO = 2;              // window slots hold cells base-2, base-1, base+2, base+3 (base, base+1 live in registers)
 constexpr int QCAP = 32 * (SUB + 1);         // continuation queue entries per warp: at most 31 + 32*SUB live
 
@@ -382,7 +383,7 @@ __device__ __forceinline__ int transit_loop(double &u, double &t, const double2 
 
 // The whole sweep of one species by one warp: claims tiles until the species has none left, drains its queue, flushes its deposits
 // and counters.  `A` is always a kernel parameter (constant bank), so the body can be instantiated for several species in one kernel.
-template <int SCHEME, bool MOVE>
+template <int SCHEME, bool MOVE, int TS = TILE_SUBS>
 __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const int lane) {
     DepositState D;
     // this CTA's copy of the deposition grids (see Ctx::d_acc)
@@ -395,6 +396,8 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
     __syncwarp();
 
     const unsigned n = (unsigned)A.n;                       // n < 2^31 (checked on the host)
+    constexpr int tile_subs = TS;                          // compile-time: 8 for loads that fill the GPU, 1 for small ones (make_push_args)
+    constexpr unsigned TILE = (unsigned)SUBTILE * (unsigned)TS;
     const unsigned ntiles = (n + TILE - 1) / TILE;
     const double del_t = A.del_t, f_tol = A.f_tol;
     const int stay_min = A.stay_min;
@@ -417,7 +420,7 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
         else t = (t < ntiles) ? (unsigned)(((unsigned long long)t * A.tile_stride) % ntiles) : ntiles;
         if (t < ntiles) {                                    // pull the tile into L2: 32 lanes x 128 B = 4 KB per array
             const size_t off = (size_t)t * TILE + 16u * lane;
-            if (16 * lane < TILE) {
+            if (16u * (unsigned)lane < TILE) {
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(A.l + off));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(A.vx + off));
             }
@@ -692,7 +695,7 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
 #pragma unroll
         for (int b = 0; b < SUB; ++b) { cl[b] = nl[b]; cv[b] = nv[b]; }
         const unsigned g0 = next_g0;
-        if (++sub == TILE_SUBS) {
+        if (++sub == tile_subs) {
             sub = 0;
             tile = tile_next;
             if (tile < ntiles) tile_next = claim();
@@ -844,13 +847,13 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
     __syncwarp();
 }
 
-template <int SCHEME, bool MOVE>
+template <int SCHEME, bool MOVE, int TS = TILE_SUBS>
 __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const __grid_constant__ PushArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // a sweep enqueued ahead of the nonlinear solve's decision: the field kernel in front of it ended the solve
     if (!MOVE && A.stop != nullptr && *A.stop != 0) return;
-    push_body<SCHEME, MOVE>(A, reinterpret_cast<WarpSmem *>(smem_raw)[warp], lane);
+    push_body<SCHEME, MOVE, TS>(A, reinterpret_cast<WarpSmem *>(smem_raw)[warp], lane);
 }
 
 // depositJ sweep of TWO species in one launch.  Each warp works through one species' tiles and then through the other's; the first
@@ -893,14 +896,15 @@ static int launch_push_pair_v(Ctx &c, const PushArgs &A, const PushArgs &B) {
     return IPIC_OK;
 }
 
-template <int SCHEME, bool MOVE>
+template <int SCHEME, bool MOVE, int TS = TILE_SUBS>
 static int launch_push_v(Ctx &c, const PushArgs &A) {
+    if (TS == TILE_SUBS && A.tile_subs == 1) return launch_push_v<SCHEME, MOVE, 1>(c, A);      // small load: 64-particle tiles
     const size_t smem = (size_t)PUSH_WARPS * sizeof(WarpSmem);
     static bool configured[64] = {};          // function attributes are per device
     if (!configured[c.device & 63]) {
-        IPIC_CUDA(cudaFuncSetAttribute(k_push<SCHEME, MOVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IPIC_CUDA(cudaFuncSetAttribute(k_push<SCHEME, MOVE, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // leave the rest of the 256 KB to L1: the per-cell tables are gathered through it
-        IPIC_CUDA(cudaFuncSetAttribute(k_push<SCHEME, MOVE>, cudaFuncAttributePreferredSharedMemoryCarveout, 52));
+        IPIC_CUDA(cudaFuncSetAttribute(k_push<SCHEME, MOVE, TS>, cudaFuncAttributePreferredSharedMemoryCarveout, 52));
         configured[c.device & 63] = true;
     }
     {
@@ -909,7 +913,7 @@ static int launch_push_v(Ctx &c, const PushArgs &A) {
         else IPIC_CUDA(cudaMemsetAsync(A.tile_counter, 0, sizeof(unsigned), c.stream));
     }
     const int blocks = c.push_blocks > 0 ? c.push_blocks : c.num_sms;
-    c.launches += 1; k_push<SCHEME, MOVE><<<blocks, PUSH_THREADS, smem, c.stream>>>(A);
+    c.launches += 1; k_push<SCHEME, MOVE, TS><<<blocks, PUSH_THREADS, smem, c.stream>>>(A);
     IPIC_CUDA(cudaGetLastError());
     return IPIC_OK;
 }
@@ -928,6 +932,16 @@ static int make_push_args(Ctx &c, int sp, double del_t, PushArgs &A) {
     A.dacc = A.acc + NM;
     A.acc_reps = std::max(1, c.acc_reps); A.acc_rep_stride = c.acc_rep_stride;
     {   // stride permutation of the tile order: an odd multiplier near the golden ratio, coprime with the tile count
+        // tile size: 512 particles, or 64 when that would leave resident warps without work (the default deck's 7.7e5 particles per species are
+        // 1500 tiles of 512 for 4736 warps: C1 electron sweep 0.117 -> 0.066 ms with 64-particle tiles; at 5e6 particles per species the
+        // large tile is still the faster one)
+        const unsigned long long warps = (unsigned long long)(c.push_blocks > 0 ? c.push_blocks : c.num_sms) * PUSH_WARPS;
+        int subs = TILE_SUBS;
+        if (2ull * (((unsigned long long)s.n + TILE_MAX - 1) / TILE_MAX) < 3ull * warps) subs = 1;     // fewer than 1.5 tiles of 512 per resident warp
+        if (c.tile_subs > 0) subs = (c.tile_subs < TILE_SUBS) ? 1 : TILE_SUBS;
+        if (c.pair_species && c.sp.size() == 2) subs = TILE_SUBS;       // k_push_pair exists for the large tile only
+        A.tile_subs = subs;
+        const unsigned long long TILE = (unsigned long long)SUBTILE * subs;
         const unsigned long long ntiles = ((unsigned long long)s.n + TILE - 1) / TILE;
         unsigned long long st = (unsigned long long)(0.6180339887498949 * (double)ntiles) | 1ull;
         auto gcd = [](unsigned long long a, unsigned long long b) { while (b) { unsigned long long t = a % b; a = b; b = t; } return a; };
