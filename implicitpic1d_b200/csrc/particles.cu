@@ -243,6 +243,11 @@ __device__ __forceinline__ void deposit_add(WarpSmem &W, DepositState &D, int la
 constexpr long long FX_ONE = 1ll << FX_BITS;
 
 #ifdef IPIC_PUSH_STATS
+#define IPIC_TRIPS_INC "add.u32 %6, %6, 1;\n\t"
+#else
+#define IPIC_TRIPS_INC
+#endif
+#ifdef IPIC_PUSH_STATS
 // measurement build only (scripts/variant_bench.sh "-DIPIC_PUSH_STATS"): lane utilisation of the deposit sweeps, printed by ipic_destroy
 __device__ unsigned long long g_push_stats[16];
 #define PSTAT(i, x) do { st_[(i)] += (unsigned)(x); } while (0)
@@ -297,27 +302,29 @@ __device__ __forceinline__ double lean_sqrt(double s) {
 // are loaded one crossing ahead.  u, t: in/out (state of the last committed crossing); off0: byte offset of the lane's first entry in
 // `tab`; returns the number of committed crossings.
 __device__ __forceinline__ int transit_loop(double &u, double &t, const double2 *tab, unsigned off0, unsigned long long tlim_bits, bool alive, unsigned tmin,
-                                            bool &out, double &t_fail) {
+                                            bool &out, double &t_fail, unsigned &trips) {
     // off: byte offset of the lane's current entry in `tab` (a 32-bit add per committed crossing, one IMAD.WIDE per two loads)
     unsigned off = off0;
     double uB, tB;
     int dead;
+    unsigned g_transit_trips_ = 0;       // measurement builds: passes of the two-crossing loop body
     asm volatile("{\n\t"
         ".reg .pred pd, pv;\n\t"
         ".reg .f64 s, y, hs, g, ng, r, g1, ng1, h1, r1, d, e0x, e0y, e1x, e1y;\n\t"
         ".reg .b32 lo, hi, hi2, m, c;\n\t"
         ".reg .b64 tb, ad;\n\t"
-        "setp.eq.s32 pd, %8, 0;\n\t"                          // pd: the lane is out (not in transit, or a test failed)
+        "setp.eq.s32 pd, %9, 0;\n\t"                          // pd: the lane is out (not in transit, or a test failed)
         "mov.f64 e0x, 0d0000000000000000;\n\t"
         "mov.f64 e0y, 0d0000000000000000;\n\t"
         "mov.f64 e1x, 0d0000000000000000;\n\t"
         "mov.f64 e1y, 0d0000000000000000;\n\t"
-        "mad.wide.u32 ad, %2, 1, %6;\n\t"
+        "mad.wide.u32 ad, %2, 1, %7;\n\t"
         "@!pd ld.global.nc.v2.f64 {e0x, e0y}, [ad];\n\t"
         "@!pd ld.global.nc.v2.f64 {e1x, e1y}, [ad+16];\n\t"
         "mov.f64 %3, %0;\n\t"
         "mov.f64 %4, %1;\n\t"
         "TLOOP:\n\t"
+        IPIC_TRIPS_INC
         "@pd bra TSKIP;\n\t"
         // crossing: A -> B with e0
         "mul.rn.f64 s, %0, %0;\n\t"
@@ -337,10 +344,10 @@ __device__ __forceinline__ int transit_loop(double &u, double &t, const double2 
         "sub.rn.f64 d, %3, %0;\n\t"
         "fma.rn.f64 %4, d, e0y, %1;\n\t"
         "mov.b64 tb, %4;\n\t"
-        "setp.ge.u64 pd, tb, %7;\n\t"
+        "setp.ge.u64 pd, tb, %8;\n\t"
         "@pd bra TSKIP;\n\t"
         "add.u32 %2, %2, 16;\n\t"
-        "mad.wide.u32 ad, %2, 1, %6;\n\t"
+        "mad.wide.u32 ad, %2, 1, %7;\n\t"
         "ld.global.nc.v2.f64 {e0x, e0y}, [ad+16];\n\t"
         // crossing: B -> A with e1
         "mul.rn.f64 s, %3, %3;\n\t"
@@ -360,24 +367,27 @@ __device__ __forceinline__ int transit_loop(double &u, double &t, const double2 
         "sub.rn.f64 d, %0, %3;\n\t"
         "fma.rn.f64 %1, d, e1y, %4;\n\t"
         "mov.b64 tb, %1;\n\t"
-        "setp.ge.u64 pd, tb, %7;\n\t"
+        "setp.ge.u64 pd, tb, %8;\n\t"
         "@pd bra TSKIP;\n\t"
         "add.u32 %2, %2, 16;\n\t"
         "ld.global.nc.v2.f64 {e1x, e1y}, [ad+32];\n\t"
         "TSKIP:\n\t"
         "vote.sync.ballot.b32 m, !pd, 0xffffffff;\n\t"
         "popc.b32 c, m;\n\t"
-        "setp.ge.u32 pv, c, %9;\n\t"
+        "setp.ge.u32 pv, c, %10;\n\t"
         "@pv bra TLOOP;\n\t"
         "selp.s32 %5, 1, 0, pd;\n\t"
         "}"
-        : "+d"(u), "+d"(t), "+r"(off), "=&d"(uB), "=&d"(tB), "=r"(dead)
+        : "+d"(u), "+d"(t), "+r"(off), "=&d"(uB), "=&d"(tB), "=r"(dead), "+r"(g_transit_trips_)
         : "l"(tab), "l"(tlim_bits), "r"((int)alive), "r"(tmin)
         : "memory");
     const int k = (int)((off - off0) >> 4);
     // the copy that is not the committed one holds the attempt that failed its test
     if (k & 1) { t_fail = t; u = uB; t = tB; } else t_fail = tB;
     out = dead != 0;
+#ifdef IPIC_PUSH_STATS
+    trips = g_transit_trips_;
+#endif
     return k;
 }
 
@@ -483,7 +493,9 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
                         double u = fabs(v);
                         PSTAT(7, 1);
                         bool out; double t_fail;
-                        const int k = transit_loop(u, tp, A.ttab, toff, A.tlim_bits, tr, (unsigned)A.transit_min, out, t_fail);
+                        unsigned trips = 0;
+                        const int k = transit_loop(u, tp, A.ttab, toff, A.tlim_bits, tr, (unsigned)A.transit_min, out, t_fail, trips);
+                        PSTAT(0, 2 * trips);
                         if (k) {
                             nsub += (unsigned)k;
                             PSTAT(1, k);

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #define FULL 0xffffffffu
 
+#define IPIC_TRIPS_INC
 // ---- from particles.cu ----
 __device__ __forceinline__ double lean_sqrt(double s) {
     double y;
@@ -35,27 +36,29 @@ __device__ __forceinline__ double lean_sqrt(double s) {
 // are loaded one crossing ahead.  u, t: in/out (state of the last committed crossing); off0: byte offset of the lane's first entry in
 // `tab`; returns the number of committed crossings.
 __device__ __forceinline__ int transit_loop(double &u, double &t, const double2 *tab, unsigned off0, unsigned long long tlim_bits, bool alive, unsigned tmin,
-                                            bool &out, double &t_fail) {
+                                            bool &out, double &t_fail, unsigned &trips) {
     // off: byte offset of the lane's current entry in `tab` (a 32-bit add per committed crossing, one IMAD.WIDE per two loads)
     unsigned off = off0;
     double uB, tB;
     int dead;
+    unsigned g_transit_trips_ = 0;       // measurement builds: passes of the two-crossing loop body
     asm volatile("{\n\t"
         ".reg .pred pd, pv;\n\t"
         ".reg .f64 s, y, hs, g, ng, r, g1, ng1, h1, r1, d, e0x, e0y, e1x, e1y;\n\t"
         ".reg .b32 lo, hi, hi2, m, c;\n\t"
         ".reg .b64 tb, ad;\n\t"
-        "setp.eq.s32 pd, %8, 0;\n\t"                          // pd: the lane is out (not in transit, or a test failed)
+        "setp.eq.s32 pd, %9, 0;\n\t"                          // pd: the lane is out (not in transit, or a test failed)
         "mov.f64 e0x, 0d0000000000000000;\n\t"
         "mov.f64 e0y, 0d0000000000000000;\n\t"
         "mov.f64 e1x, 0d0000000000000000;\n\t"
         "mov.f64 e1y, 0d0000000000000000;\n\t"
-        "mad.wide.u32 ad, %2, 1, %6;\n\t"
+        "mad.wide.u32 ad, %2, 1, %7;\n\t"
         "@!pd ld.global.nc.v2.f64 {e0x, e0y}, [ad];\n\t"
         "@!pd ld.global.nc.v2.f64 {e1x, e1y}, [ad+16];\n\t"
         "mov.f64 %3, %0;\n\t"
         "mov.f64 %4, %1;\n\t"
         "TLOOP:\n\t"
+        IPIC_TRIPS_INC
         "@pd bra TSKIP;\n\t"
         // crossing: A -> B with e0
         "mul.rn.f64 s, %0, %0;\n\t"
@@ -75,10 +78,10 @@ __device__ __forceinline__ int transit_loop(double &u, double &t, const double2 
         "sub.rn.f64 d, %3, %0;\n\t"
         "fma.rn.f64 %4, d, e0y, %1;\n\t"
         "mov.b64 tb, %4;\n\t"
-        "setp.ge.u64 pd, tb, %7;\n\t"
+        "setp.ge.u64 pd, tb, %8;\n\t"
         "@pd bra TSKIP;\n\t"
         "add.u32 %2, %2, 16;\n\t"
-        "mad.wide.u32 ad, %2, 1, %6;\n\t"
+        "mad.wide.u32 ad, %2, 1, %7;\n\t"
         "ld.global.nc.v2.f64 {e0x, e0y}, [ad+16];\n\t"
         // crossing: B -> A with e1
         "mul.rn.f64 s, %3, %3;\n\t"
@@ -98,24 +101,27 @@ __device__ __forceinline__ int transit_loop(double &u, double &t, const double2 
         "sub.rn.f64 d, %0, %3;\n\t"
         "fma.rn.f64 %1, d, e1y, %4;\n\t"
         "mov.b64 tb, %1;\n\t"
-        "setp.ge.u64 pd, tb, %7;\n\t"
+        "setp.ge.u64 pd, tb, %8;\n\t"
         "@pd bra TSKIP;\n\t"
         "add.u32 %2, %2, 16;\n\t"
         "ld.global.nc.v2.f64 {e1x, e1y}, [ad+32];\n\t"
         "TSKIP:\n\t"
         "vote.sync.ballot.b32 m, !pd, 0xffffffff;\n\t"
         "popc.b32 c, m;\n\t"
-        "setp.ge.u32 pv, c, %9;\n\t"
+        "setp.ge.u32 pv, c, %10;\n\t"
         "@pv bra TLOOP;\n\t"
         "selp.s32 %5, 1, 0, pd;\n\t"
         "}"
-        : "+d"(u), "+d"(t), "+r"(off), "=&d"(uB), "=&d"(tB), "=r"(dead)
+        : "+d"(u), "+d"(t), "+r"(off), "=&d"(uB), "=&d"(tB), "=r"(dead), "+r"(g_transit_trips_)
         : "l"(tab), "l"(tlim_bits), "r"((int)alive), "r"(tmin)
         : "memory");
     const int k = (int)((off - off0) >> 4);
     // the copy that is not the committed one holds the attempt that failed its test
     if (k & 1) { t_fail = t; u = uB; t = tB; } else t_fail = tB;
     out = dead != 0;
+#ifdef IPIC_PUSH_STATS
+    trips = g_transit_trips_;
+#endif
     return k;
 }
 
@@ -129,7 +135,7 @@ __global__ void __launch_bounds__(1024, 1) k_transit(const double2 *__restrict__
     const long long t0 = clock64();
     for (int rep = 0; rep < reps; ++rep) {
         double u = v0 + rep, t = 0.0, t_fail; bool o;
-        crossings += transit_loop(u, t, ttab, 16u * (unsigned)cell, tlim_bits, true, 12u, o, t_fail);
+        unsigned trips = 0; crossings += transit_loop(u, t, ttab, 16u * (unsigned)cell, tlim_bits, true, 12u, o, t_fail, trips);
         acc += u + t;
     }
     const long long t1 = clock64();

@@ -9,9 +9,10 @@ def num(x):
 
 src = sys.argv[2] if len(sys.argv) > 2 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "implicitpic1d_b200", "csrc", "particles.cu")
 lines = open(src).read().split("\n")
-markers = [("deposit helpers", r"^struct DepositState"), ("transit asm", r"transit_step\(double|^// One face-to-face crossing"),
-           ("push prologue / claim / loads", r"^template <int SCHEME, bool MOVE>"), ("queue pop", r"the general sub-step: runs batches"),
-           ("transit loop", r"---- transit phase"), ("general sub-step", r"^\s+bool cont = false;"), ("requeue", r"const unsigned cm = __ballot_sync\(FULL, cont\);"),
+markers = [("deposit helpers", r"^struct DepositState"), ("transit loop (PTX)", r"^__device__ __forceinline__ double lean_sqrt"),
+           ("push prologue / claim / loads", r"^template <int SCHEME, bool MOVE"), ("queue pop", r"the general sub-step: runs batches"),
+           ("transit set-up / bookkeeping", r"---- transit phase"), ("finish stage", r"---- finish stage"), ("general sub-step", r"^\s+bool cont = requeue;"),
+           ("requeue", r"const unsigned cm = __ballot_sync\(FULL, cont\);"),
            ("fresh path", r"fresh batches of the next sub-tile"), ("epilogue", r"epilogue: accumulators"), ("other kernels", r"^__global__ void __launch_bounds__\(PUSH_THREADS, 1\) k_push\(")]
 bounds = []
 for name, pat in markers:
