@@ -72,7 +72,8 @@ def test_depositJ(pair):
     # grid size): the deposits are exact integers
     ip.depositJ(solver, plist, world, del_t)
     assert np.array_equal(solver.J, Jg)
-    for name, vals, default in (("stay_min", (1, 32), 20), ("tile_order", (0,), 1), ("push_blocks", (1, 7), 0), ("transit_min", (1, 33), 12)):
+    for name, vals, default in (("stay_min", (1, 32), 20), ("tile_order", (0, 2), 1), ("push_blocks", (1, 7), 0), ("transit_min", (1, 33), 12),
+                                ("tile_subs", (1, 8), 0)):
         for v in vals:
             solver.set_option(name, v)
             ip.depositJ(solver, plist, world, del_t)
