@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("IPIC1D_B200_LIB") or os.path.join(_HERE, "lib", "libi
 OK, ERR_ARG, ERR_CUDA, ERR_STOP, ERR_NOT_CONVERGED, ERR_UNSUPPORTED, ERR_NCCL = range(7)
 SCHEME_NGP, SCHEME_CIC, SCHEME_NGP_PERIODIC = 0, 1, 2
 F_PHI, F_PHI_F, F_J, F_RHO, F_EFIELD, F_A_TRI, F_B_TRI, F_C_TRI, F_EFIELD_F, F_EFIELD_HALF = range(10)
-TRIDIAG_PCR, TRIDIAG_THOMAS = 0, 1
+TRIDIAG_PCR, TRIDIAG_THOMAS, TRIDIAG_SCAN = 0, 1, 2
 
 
 class MoveStats(C.Structure):

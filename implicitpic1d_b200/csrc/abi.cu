@@ -458,6 +458,7 @@ int ipic_destroy(ipic_handle h) {
     injection_free(*c);
     diagnostics_free(*c);
     for (auto &s : c->sp) { if (s.l) cudaFree(s.l); if (s.l2) cudaFree(s.l2); if (s.refl) cudaFree(s.refl); if (s.refList) cudaFree(s.refList); if (s.refLive) cudaFree(s.refLive); }
+    if (c->d_gu) cudaFree(c->d_gu); if (c->d_gv) cudaFree(c->d_gv); if (c->d_gs) cudaFree(c->d_gs);
     double *dp[] = {c->d_grid, c->d_dx, c->d_hinv, c->d_phi, c->d_phi_f, c->d_rho, c->d_J, c->d_E, c->d_a, c->d_b, c->d_c, c->d_cp, c->d_m, c->d_pcr, c->d_work,
                     c->d_rho_i, c->d_scal, c->d_phi_k, c->d_res_k, c->d_norms, c->d_loss, c->d_Ef, c->d_Eh};
     for (double *p : dp) if (p) cudaFree(p);
@@ -537,7 +538,8 @@ int ipic_init_solver(ipic_handle h, double leftVoltage, double rightVoltage, dou
 
 int ipic_set_tridiag_mode(ipic_handle h, int mode) {
     CTX(h);
-    if (mode != IPIC_TRIDIAG_PCR && mode != IPIC_TRIDIAG_THOMAS) return IPIC_ERR_ARG;
+    if (mode != IPIC_TRIDIAG_PCR && mode != IPIC_TRIDIAG_THOMAS && mode != IPIC_TRIDIAG_SCAN) return IPIC_ERR_ARG;
+    if (mode == IPIC_TRIDIAG_SCAN && !c->scan_ok) { set_error("IPIC_TRIDIAG_SCAN: the inverse of this deck's matrix has no usable generators (periodic / singular)"); return IPIC_ERR_UNSUPPORTED; }
     c->tridiag_mode = mode;
     return IPIC_OK;
 }

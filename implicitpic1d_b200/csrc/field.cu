@@ -60,6 +60,8 @@ struct FieldArgs {
     // host spins on -- no D2H copy, no driver synchronisation on the critical path of a nonlinear iteration
     double *h_norm; unsigned long long *h_seq; unsigned long long seq;
     unsigned long long *counters;   // [nsp][8]: slot 6 of a species is the tile counter of its push launch, zeroed by the half-E op that precedes a sweep
+    // IPIC_TRIDIAG_SCAN
+    const double *gu, *gv, *gs; double gWinv; int giL, giR;
     // OP_AND_DECIDE
     int *and_state; double eps_tol; int eform;
     volatile long long *h_and; double *h_and_norms;
@@ -162,6 +164,32 @@ __device__ void block_scan_i64(long long *x, int n) {
     __syncthreads();
 }
 
+// in-place inclusive prefix sum (or, reverse = true, inclusive suffix sum) of n doubles in shared memory: every thread sums a contiguous
+// chunk in order, the chunk totals are scanned over the warp and over the warps in order -- a fixed order, so the result is deterministic
+__device__ void block_scan_f64(double *x, int n, bool reverse) {
+    __shared__ double wtot[FT / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per = (n + FT - 1) / FT;
+    const int b = min(threadIdx.x * per, n), e = min(b + per, n);
+    double run = 0.0;
+    if (!reverse) { for (int i = b; i < e; ++i) { run += x[i]; x[i] = run; } }
+    else { for (int i = b; i < e; ++i) { const int k = n - 1 - i; run += x[k]; x[k] = run; } }
+    double inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    double off = __shfl_up_sync(0xffffffffu, inc, 1);     // exclusive within the warp
+    if (lane == 0) off = 0.0;
+    for (int w = 0; w < warp; ++w) off += wtot[w];
+    if (!reverse) { for (int i = b; i < e; ++i) x[i] += off; }
+    else { for (int i = b; i < e; ++i) x[n - 1 - i] += off; }
+    __syncthreads();
+}
+
 // Sum the per-species int64 grids (species order, scaled by q*w_p) into dst[0..n-1]; zero the grids.
 // with_runs: add the prefix sum of the species' difference grid (runs of fully traversed cells, see k_push).
 // One CTA works through arrays that live in L2: what a phase costs is the number of dependent L2 round trips (~0.7 us each), not bytes.
@@ -246,6 +274,34 @@ __device__ void dev_tridiag(const FieldArgs &A, double *d, double *tmp) {
             for (int i = 2; i <= n; ++i)
                 d[i - 1] = __ddiv_rn(__dsub_rn(d[i - 1], __dmul_rn(d[i - 2], A.a[i - 2])), A.m[i - 1]);
             for (int i = n - 1; i >= 1; --i) d[i - 1] = __dsub_rn(d[i - 1], __dmul_rn(A.cp[i - 1], d[i]));
+        }
+        __syncthreads();
+        return;
+    }
+    if (A.tridiag_mode == IPIC_TRIDIAG_SCAN) {
+        // x = T^-1 d with (S^-1)_ij = u_i v_j / W (i <= j) for the row-scaled symmetric matrix S on the unknowns [iL, iR] (Dirichlet rows are
+        // x = d and go to their neighbours' right-hand sides): x_i = (v_i sum_{j<=i} u_j d_j + u_i sum_{j>i} v_j d_j) / W -- two scans.
+        // tmp needs 2 n doubles (field.cu reserves them behind the two work vectors).
+        const int iL = A.giL, iR = A.giR;                 // 1-based
+        double *P = tmp, *Q = tmp + n;
+        const double dL = d[0], dR = d[n - 1];
+        for (int i = threadIdx.x; i < n; i += FT) {
+            const int r = i + 1;
+            double dd = 0.0;
+            if (r >= iL && r <= iR) {
+                dd = d[i];
+                if (iL == 2 && r == 2) dd -= A.a[0] * dL;
+                if (iR == n - 1 && r == n - 1) dd -= A.c[n - 2] * dR;
+                dd *= A.gs[i];
+            }
+            P[i] = A.gu[i] * dd; Q[i] = A.gv[i] * dd;
+        }
+        __syncthreads();
+        block_scan_f64(P, n, false);
+        block_scan_f64(Q, n, true);
+        for (int i = threadIdx.x; i < n; i += FT) {
+            const int r = i + 1;
+            if (r >= iL && r <= iR) d[i] = (A.gv[i] * P[i] + A.gu[i] * ((i + 1 < n) ? Q[i + 1] : 0.0)) * A.gWinv;
         }
         __syncthreads();
         return;
@@ -1008,13 +1064,15 @@ static FieldArgs make_args(Ctx &c) {
     A.unk = (c.scheme == IPIC_SCHEME_NGP_PERIODIC) ? c.d_Ef : c.d_phi_f;
     A.nunk = (c.scheme == IPIC_SCHEME_NGP_PERIODIC) ? c.Nh : c.Nx;
     A.L_domain = c.L_domain; A.globJ = 0;
+    A.gu = c.d_gu; A.gv = c.d_gv; A.gs = c.d_gs; A.gWinv = (c.gW != 0.0) ? 1.0 / c.gW : 0.0; A.giL = c.giL; A.giR = c.giR;
     A.phi_k = c.d_phi_k; A.res_k = c.d_res_k; A.norms = c.d_norms;
     A.and_m = c.m_Anderson; A.beta = c.Beta_k;
     return A;
 }
 
 static int run_field(Ctx &c, const FieldArgs &A, unsigned ops) {
-    const size_t smem = (size_t)2 * (std::max(c.Nx, c.Nh) + 2) * sizeof(double) + 4096 * sizeof(double);
+    // two work vectors + scratch behind them (the scan solve uses the second vector and the scratch as 2 N_x doubles)
+    const size_t smem = (size_t)2 * (std::max(c.Nx, c.Nh) + 2) * sizeof(double) + std::max<size_t>(4096, (size_t)std::max(c.Nx, c.Nh) + 2) * sizeof(double);
     static size_t configured_dev[64] = {};    // function attributes are per device
     size_t &configured = configured_dev[c.device & 63];
     if (smem > configured) {
@@ -1138,6 +1196,70 @@ int field_setup(Ctx &c) {
         double *inv = &pcr[(size_t)levels * 2 * Nx];
         for (int i = 0; i < Nx; ++i) inv[i] = 1.0 / lb[i];
     }
+    // ---- IPIC_TRIDIAG_SCAN: generators of the inverse (long double), checked against a long-double Thomas solve on a rough right-hand side ----
+    c.scan_ok = false;
+    if (c.scheme != IPIC_SCHEME_NGP_PERIODIC && Nx >= 8) {
+        typedef long double ld;
+        auto ident = [&](int i) { return b[i] == 1.0 && cc[i] == 0.0 && (i == 1 || a[i - 1] == 0.0); };
+        const int iL = ident(1) ? 2 : 1, iR = ident(Nx) ? Nx - 1 : Nx;
+        std::vector<ld> u(Nx + 2, 0.0L), v(Nx + 2, 0.0L), sc(Nx + 2, 0.0L);
+        bool ok = (iR - iL >= 3);
+        for (int i = iL; ok && i < iR; ++i) ok = (cc[i] != 0.0 && a[i] != 0.0);
+        if (ok) {
+            // row scales that make the matrix symmetric: s_i c_i = s_{i+1} a_i (Neumann rows of the NGP matrix carry a factor 2)
+            sc[iL] = 1.0L;
+            for (int i = iL; i < iR; ++i) sc[i + 1] = sc[i] * (ld)cc[i] / (ld)a[i];
+            u[iL] = 1.0L;
+            u[iL + 1] = -((ld)b[iL] * u[iL]) / (ld)cc[iL];
+            for (int i = iL + 1; i < iR; ++i) u[i + 1] = -((ld)a[i - 1] * u[i - 1] + (ld)b[i] * u[i]) / (ld)cc[i];
+            v[iR] = 1.0L;
+            v[iR - 1] = -((ld)b[iR] * v[iR]) / (ld)a[iR - 1];
+            for (int i = iR - 1; i > iL; --i) v[i - 1] = -((ld)cc[i] * v[i + 1] + (ld)b[i] * v[i]) / (ld)a[i - 1];
+            const int j = (iL + iR) / 2;
+            const ld W = sc[j] * (ld)cc[j] * (u[j] * v[j + 1] - u[j + 1] * v[j]);
+            ok = std::isfinite((double)W) && W != 0.0L;
+            if (ok) {
+                // check: a rough right-hand side through the generators against Thomas, both in long double
+                std::vector<ld> d(Nx + 2), x(Nx + 2), ref(Nx + 2), cpl(Nx + 2), ml(Nx + 2);
+                unsigned long long st = 88172645463325252ull;
+                for (int i = 1; i <= Nx; ++i) { st ^= st << 13; st ^= st >> 7; st ^= st << 17; d[i] = (ld)((double)(st >> 11) / 9007199254740992.0 - 0.5) * 1.0e3L; }
+                ref = d;
+                cpl[1] = (ld)cc[1] / (ld)b[1]; ml[1] = (ld)b[1]; ref[1] = ref[1] / ml[1];
+                for (int i = 2; i <= Nx; ++i) {
+                    ml[i] = (ld)b[i] - cpl[i - 1] * (ld)a[i - 1];
+                    cpl[i] = (i < Nx) ? (ld)cc[i] / ml[i] : 0.0L;
+                    ref[i] = (ref[i] - ref[i - 1] * (ld)a[i - 1]) / ml[i];
+                }
+                for (int i = Nx - 1; i >= 1; --i) ref[i] = ref[i] - cpl[i] * ref[i + 1];
+                std::vector<ld> dd(Nx + 2, 0.0L), P(Nx + 2, 0.0L), Q(Nx + 3, 0.0L);
+                for (int i = iL; i <= iR; ++i) {
+                    dd[i] = d[i];
+                    if (iL == 2 && i == 2) dd[i] -= (ld)a[1] * d[1];
+                    if (iR == Nx - 1 && i == Nx - 1) dd[i] -= (ld)cc[Nx - 1] * d[Nx];
+                    dd[i] *= sc[i];
+                }
+                for (int i = iL; i <= iR; ++i) P[i] = P[i - 1] + u[i] * dd[i];
+                for (int i = iR; i >= iL; --i) Q[i] = Q[i + 1] + v[i] * dd[i];
+                ld err = 0.0L, big = 0.0L;
+                for (int i = iL; i <= iR; ++i) {
+                    x[i] = (v[i] * P[i] + u[i] * Q[i + 1]) / W;
+                    err = std::max(err, fabsl(x[i] - ref[i])); big = std::max(big, fabsl(ref[i]));
+                }
+                ok = std::isfinite((double)err) && err <= 1.0e-12L * big;
+            }
+            if (ok) {
+                std::vector<double> hu(Nx, 0.0), hv(Nx, 0.0), hs(Nx, 0.0);
+                for (int i = iL; i <= iR; ++i) { hu[i - 1] = (double)u[i]; hv[i - 1] = (double)v[i]; hs[i - 1] = (double)sc[i]; }
+                for (double **pp : {&c.d_gu, &c.d_gv, &c.d_gs}) { if (*pp) cudaFree(*pp); *pp = nullptr; IPIC_CUDA(cudaMalloc(pp, Nx * sizeof(double))); }
+                IPIC_CUDA(cudaMemcpy(c.d_gu, hu.data(), Nx * sizeof(double), cudaMemcpyHostToDevice));
+                IPIC_CUDA(cudaMemcpy(c.d_gv, hv.data(), Nx * sizeof(double), cudaMemcpyHostToDevice));
+                IPIC_CUDA(cudaMemcpy(c.d_gs, hs.data(), Nx * sizeof(double), cudaMemcpyHostToDevice));
+                c.gW = (double)W; c.giL = iL; c.giR = iR; c.scan_ok = true;
+            }
+        }
+    }
+    if (c.tridiag_mode == IPIC_TRIDIAG_PCR && c.scan_ok) c.tridiag_mode = IPIC_TRIDIAG_SCAN;     // the default where the matrix allows it
+    if (c.tridiag_mode == IPIC_TRIDIAG_SCAN && !c.scan_ok) c.tridiag_mode = IPIC_TRIDIAG_PCR;
     c.pcr_levels = levels;
     if (c.d_pcr) cudaFree(c.d_pcr);
     IPIC_CUDA(cudaMalloc(&c.d_pcr, pcr.size() * sizeof(double)));

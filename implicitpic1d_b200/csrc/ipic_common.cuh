@@ -139,6 +139,10 @@ struct Ctx {
     double *d_a = nullptr, *d_b = nullptr, *d_c = nullptr;       // tridiagonal
     double *d_cp = nullptr, *d_m = nullptr;                       // Thomas: c' and pivots m_i (constant matrix)
     double *d_pcr = nullptr; int pcr_levels = 0;                  // PCR level coefficients [levels][2][Nx] + inv diag [Nx]
+    // IPIC_TRIDIAG_SCAN: generators of the inverse of the (row-scaled, symmetric) tridiagonal matrix on the unknowns [iL, iR] -- u solves the
+    // homogeneous recurrence from the left end, v from the right end, gs are the row scales, gW = s_j c_j (u_j v_j+1 - u_j+1 v_j) -- built
+    // in long double by field_setup and checked against the Thomas solve; scan_ok = false (periodic / singular matrices) keeps PCR
+    double *d_gu = nullptr, *d_gv = nullptr, *d_gs = nullptr; double gW = 0.0; int giL = 1, giR = 0; bool scan_ok = false;
     double *d_work = nullptr;                                     // scratch (4 * max(Nx,Nh))
     double *d_rho_i = nullptr;
     // [acc_reps][nsp_max][2][max(Nx,Nh)+2] int64 accumulators: grid, difference grid.  The copies spread the global RED traffic of the

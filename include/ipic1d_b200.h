@@ -61,8 +61,10 @@ typedef struct ipic_ctx *ipic_handle;
 #define IPIC_F_EFIELD_HALF 9 /* solver%EField_half (N_h)  NGP_Periodic */
 
 /* linear-solve modes for the tridiagonal Ampere/Poisson systems */
-#define IPIC_TRIDIAG_PCR 0    /* single-block parallel cyclic reduction, cached level coefficients (default) */
+#define IPIC_TRIDIAG_PCR 0    /* single-block parallel cyclic reduction, cached level coefficients */
 #define IPIC_TRIDIAG_THOMAS 1 /* sequential Thomas sweep in the reference's operation order (parity mode) */
+#define IPIC_TRIDIAG_SCAN 2   /* x = T^-1 d through the generators of the constant matrix's inverse, (T^-1)_ij = u_i v_j / W for i <= j: two
+                               * block scans instead of log2(N_x) reduction levels.  Default where the matrix allows it (bounded decks) */
 
 const char *ipic_version(void);
 const char *ipic_last_error(void);

@@ -34,6 +34,24 @@ def test_deposit_rho_and_initial_potential(pair):
         assert relerr(getattr(solver, name), o.get(name)) < 1e-15
 
 
+def test_scan_solve_matches_thomas(pair):
+    """IPIC_TRIDIAG_SCAN (the default on bounded decks): x = T^-1 d through the generators of the constant matrix's inverse, two block scans.
+    Against the Thomas sweep on the same right-hand side: 1e-11 of max|phi| (on a realistic right-hand side the generators are closer to
+    the exact solution than the double-precision Thomas sweep is)."""
+    d, o, world, solver, plist = pair
+    solver.set_tridiag_mode(_lib.TRIDIAG_THOMAS)
+    solver.solve_tridiag_Poisson(world, 0.0)
+    phi_t = solver.phi.copy()
+    try:
+        solver.set_tridiag_mode(_lib.TRIDIAG_SCAN)
+    except _lib.IpicError:
+        assert d["bcL"] == 3 or d["bcR"] == 3 or (d["bcL"] == 2 and d["bcR"] == 2)       # periodic / singular: no generators, PCR stays
+        return
+    solver.solve_tridiag_Poisson(world, 0.0)
+    assert relerr(solver.phi, phi_t) < 1e-11, relerr(solver.phi, phi_t)
+    solver.set_tridiag_mode(_lib.TRIDIAG_THOMAS)
+
+
 def test_pcr_matches_thomas(pair):
     d, o, world, solver, plist = pair
     phi_t = solver.phi
@@ -186,12 +204,13 @@ def test_solvePotential_iteration_parity(pair):
     assert abs(solver.getJdotE(world, r["cg"]) - o.getJdotE(r["co"])) <= 1e-8 * abs(o.getJdotE(r["co"])) + 1e-30
 
 
+@pytest.mark.parametrize("mode", [_lib.TRIDIAG_PCR, _lib.TRIDIAG_SCAN])
 @pytest.mark.parametrize("name", ["ngp_rf", "cic_rf"])
-def test_solvePotential_pcr_mode(name):
-    """production mode (PCR field solve): same iteration count as the oracle on the default decks"""
+def test_solvePotential_pcr_mode(name, mode):
+    """production modes (scan solve through the inverse's generators, the default; PCR): same iteration count as the oracle on the default decks"""
     d = DECKS[name]
     o = build_oracle(d)
-    world, solver, plist = build_cuda_from_oracle(d, o, tridiag_mode=_lib.TRIDIAG_PCR)
+    world, solver, plist = build_cuda_from_oracle(d, o, tridiag_mode=mode)
     try:
         r = _one_step(d, o, world, solver, plist)
         assert r["sg"].iterNumPicard == r["so"]["iterNumPicard"]
