@@ -475,6 +475,8 @@ int ipic_destroy(ipic_handle h) {
     if (c->d_sort_tmp) cudaFree(c->d_sort_tmp);
     if (c->h_scal) cudaFreeHost(c->h_scal);
     if (c->d_and_state) cudaFree(c->d_and_state);
+    if (c->d_cmp) cudaFree(c->d_cmp);
+    if (c->d_gram_part) cudaFree(c->d_gram_part);
     if (c->h_and) cudaFreeHost(const_cast<long long *>(c->h_and));
     if (c->h_and_norms) cudaFreeHost(c->h_and_norms);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -718,6 +720,11 @@ int ipic_initialize_solver(ipic_handle h, double eps_a, double eps_r, int solver
     IPIC_CUDA(cudaMalloc(&c->d_phi_k, n * sizeof(double))); IPIC_CUDA(cudaMemset(c->d_phi_k, 0, n * sizeof(double)));
     IPIC_CUDA(cudaMalloc(&c->d_res_k, n * sizeof(double))); IPIC_CUDA(cudaMemset(c->d_res_k, 0, n * sizeof(double)));
     IPIC_CUDA(cudaMalloc(&c->d_norms, (m_Anderson + 2) * sizeof(double)));
+    if (!c->d_cmp) {
+        const size_t half = (size_t)std::max(c->Nx, c->Nh) + 2;
+        IPIC_CUDA(cudaMalloc(&c->d_cmp, NSP_MAX * 2 * half * sizeof(long long))); IPIC_CUDA(cudaMemset(c->d_cmp, 0, NSP_MAX * 2 * half * sizeof(long long)));
+        IPIC_CUDA(cudaMalloc(&c->d_gram_part, 16 * 68 * sizeof(double))); IPIC_CUDA(cudaMemset(c->d_gram_part, 0, 16 * 68 * sizeof(double)));
+    }
     if (!c->d_and_state) {
         IPIC_CUDA(cudaMalloc(&c->d_and_state, 4 * sizeof(int))); IPIC_CUDA(cudaMemset(c->d_and_state, 0, 4 * sizeof(int)));
         void *hp = nullptr;
@@ -993,6 +1000,7 @@ int ipic_set_option(ipic_handle h, const char *name, double value) {
     else if (k == "timing") c->timing_on = value != 0.0;
     else if (k == "anderson_chunk") c->and_chunk = std::max(1, (int)value);
     else if (k == "peer_reduce") c->peer_reduce = (int)value;
+    else if (k == "field_cluster") c->field_cluster = std::max(1, std::min(8, (int)value));
     else if (k == "dump_push_stats") { cudaStreamSynchronize(c->stream); push_stats_dump(); }      // measurement builds (-DIPIC_PUSH_STATS): print + clear
     else if (k == "use_tma") { /* accepted for compatibility: the streaming path is register-prefetched */ }
     else if (k == "lazy_compaction") c->lazy_compaction = (int)value;

@@ -60,6 +60,9 @@ struct FieldArgs {
     // host spins on -- no D2H copy, no driver synchronisation on the critical path of a nonlinear iteration
     double *h_norm; unsigned long long *h_seq; unsigned long long seq;
     unsigned long long *counters;   // [nsp][8]: slot 6 of a species is the tile counter of its push launch, zeroed by the half-E op that precedes a sweep
+    // thread-block cluster (the fused Anderson iteration): compact copies of the collected integer grids [nsp][2][acc_stride / 2] and the
+    // per-CTA partial sums of the normal equations [cluster size][68]
+    long long *cmp; double *gram_part;
     // IPIC_TRIDIAG_SCAN
     const double *gu, *gv, *gs; double gWinv; int giL, giR;
     // OP_AND_DECIDE
@@ -230,6 +233,58 @@ __device__ __forceinline__ void collect_batch(unsigned long long *g, int reps, s
     }
 }
 
+// ---- thread-block cluster helpers -------------------------------------------------------------------------------------------
+// The fused Anderson iteration is launched as a cluster of CLUSTER CTAs (run_field).  CTA 0 runs the kernel as it always did; the phases
+// that move the most bytes and are independent per cell -- adding up the copies of the deposition grids, the sums of the normal equations,
+// the push tables -- are split over all CTAs of the cluster (one SM's load/store path is what bounds them), with a cluster barrier between
+// a phase and its consumer.  Launched without a cluster the same code runs with rank 0 of 1.
+__device__ __forceinline__ unsigned cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_size() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// this CTA's share of the collect: for its slice of cells, every species, both grids: sum of the copies -> compact array, copies zeroed
+__device__ void dev_collect_slice(const FieldArgs &A, int n, bool with_runs, unsigned crank, unsigned csize) {
+    const int per = (n + (int)csize - 1) / (int)csize;
+    const int lo = (int)crank * per, hi = min(n, lo + per);
+    const int half = A.acc_stride / 2;
+    for (int s = 0; s < A.nsp; ++s) {
+        for (int gsel = with_runs ? 1 : 0; gsel >= 0; --gsel) {
+            unsigned long long *g = A.acc + (size_t)s * A.acc_stride + (gsel ? half : 0);
+            long long *out = A.cmp + ((size_t)s * 2 + gsel) * half;
+            for (int base = lo + threadIdx.x; base < hi; base += CB * FT) {
+                unsigned long long q[CB];
+                collect_batch(g, A.acc_reps, A.acc_rep_stride, base, hi, q);
+#pragma unroll
+                for (int k = 0; k < CB; ++k) { const int i = base + k * FT; if (i < hi) out[i] = (long long)q[k]; }
+            }
+            if (gsel && crank == csize - 1 && threadIdx.x < A.acc_reps) g[(size_t)threadIdx.x * A.acc_rep_stride + n + 1] = 0ull;   // closing entry of a run
+        }
+    }
+}
+
+// CTA 0 after the barrier: the compact arrays -> dst (species order, scaled by q*w_p), difference grids prefix-summed
+__device__ void dev_collect_compact(const FieldArgs &A, double *dst, int n, bool with_runs, long long *scratch) {
+    const int half = A.acc_stride / 2;
+    for (int s = 0; s < A.nsp; ++s) {
+        const long long *jm = A.cmp + ((size_t)s * 2) * half, *jd = jm + half;
+        if (with_runs) {
+            for (int i = threadIdx.x; i < n; i += FT) scratch[i] = __ldcg(jd + i);
+            __syncthreads();
+            block_scan_i64(scratch, n);
+        }
+        for (int i = threadIdx.x; i < n; i += FT) {
+            long long q = __ldcg(jm + i);
+            if (with_runs) q += scratch[i];
+            const double v = (double)q * FX_INV;
+            if (s == 0) dst[i] = v * A.qw[0];
+            else dst[i] = dst[i] + v * A.qw[s];
+        }
+        __syncthreads();
+    }
+}
+
 __device__ void dev_collect(const FieldArgs &A, double *dst, int n, bool with_runs, long long *scratch) {
     for (int s = 0; s < A.nsp; ++s) {
         unsigned long long *g = A.acc + (size_t)s * A.acc_stride;
@@ -342,7 +397,8 @@ __device__ void dev_tridiag(const FieldArgs &A, double *d, double *tmp) {
 // so every history column crosses the SM once per group.  Fixed order: a thread's rows ascending, shuffle tree over the warp, the eight
 // warps of the group ascending.  gram[p]: p = k (k + 1) / 2 + j for j <= k < 10, p = 55 + j for (A^T r)_j.
 template <int G>
-__device__ __forceinline__ void gram_group(const double *__restrict__ res_k, int NU, int index, const int *col, int m_k, double *part /* [32 warps][17] */) {
+__device__ __forceinline__ void gram_group(const double *__restrict__ res_k, int NU, int r0, int r1, int index, const int *col, int m_k,
+                                           double *part /* [32 warps][17] */) {
     const int t = threadIdx.x & 255, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double acc[17];
 #pragma unroll
@@ -351,7 +407,7 @@ __device__ __forceinline__ void gram_group(const double *__restrict__ res_k, int
     const double *Rc[10];
 #pragma unroll
     for (int j = 0; j < 10; ++j) Rc[j] = res_k + (size_t)(col[j < m_k ? j : 0] - 1) * NU;
-    for (int r = t; r < NU; r += 256) {
+    for (int r = r0 + t; r < r1; r += 256) {
         const double ri = __ldcg(Ri + r);
         double d[10];
 #pragma unroll
@@ -391,13 +447,16 @@ __device__ long long g_field_phase[16];
 __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsigned ops_in) {
     extern __shared__ __align__(16) double sm[];
     unsigned ops = ops_in;
+    const unsigned crank = cluster_rank(), csize = cluster_size();     // 0 of 1 unless run_field launched a cluster
     if (ops & OP_AND_DECIDE) {
         // an iteration enqueued ahead of the decision that ended the solve: report and leave (the sweeps in front of it did the same)
         if (A.and_state[0] != 0) {
-            if (threadIdx.x == 0) { __threadfence_system(); A.h_and[0] = (long long)A.seq; }
+            if (threadIdx.x == 0 && crank == 0) { __threadfence_system(); A.h_and[0] = (long long)A.seq; }
             return;
         }
     }
+    const bool clustered = csize > 1;                  // run_field launches clusters for the fused Anderson iteration only
+    if (crank != 0) ops &= (OP_AND_DECIDE | OP_AND_MIX | OP_HALF_E);     // helper CTAs take part in the split phases only
 #ifdef IPIC_FIELD_PHASES
     if (threadIdx.x < 16) g_field_phase[threadIdx.x] = 0;
     __syncthreads();
@@ -512,8 +571,14 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
     }
 
     // ---------------- depositJ epilogue: NGP mod_particleMover.f90:145-156 ; CIC mod_particleMoverPicard.f90:165-194 ----------------
+    if (clustered) {
+        // every CTA adds up the copies of the deposition grids for its slice of cells; CTA 0 goes on from the compact arrays
+        dev_collect_slice(A, Nh, A.scheme == 0, crank, csize);
+        cluster_barrier();
+    }
     if (ops & OP_FINALIZE_J) {
-        dev_collect(A, s0, Nh, A.scheme == 0, reinterpret_cast<long long *>(s1));
+        if (clustered) dev_collect_compact(A, s0, Nh, A.scheme == 0, reinterpret_cast<long long *>(s1));
+        else dev_collect(A, s0, Nh, A.scheme == 0, reinterpret_cast<long long *>(s1));
         __syncthreads();
         PH(1);
         if (A.scheme == 1 && threadIdx.x == 0) {
@@ -682,6 +747,15 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
         }
         PH(5);
     }
+    if (clustered) {
+        // the helper CTAs waited here for the residual and the decision (and_state: 0 go on, 1 converged, 2 stagnated)
+        cluster_barrier();
+        if (crank != 0) {
+            const int dec = __ldcg(A.and_state);
+            if (dec == 1) ops &= ~OP_AND_MIX;
+            else if (dec == 2) ops &= ~(OP_AND_MIX | OP_HALF_E | OP_P_HALF_E);
+        }
+    }
     if (ops & OP_AND_MIX) {
         const int i = A.and_i, m = A.and_m;
         const int index = fmodulo(i, M1) + 1;
@@ -698,18 +772,30 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
             // register-blocked sums (gram_group): four groups of 256 threads, each owning a quarter of the 65 sums
             double *part = alpha + 128;                    // [32][17]
             double *gram = part + 32 * 17;                 // [68]
+            // rows of this CTA (all of them without a cluster)
+            const int rper = (NU + (int)csize - 1) / (int)csize;
+            const int r0 = (int)crank * rper, r1 = min(NU, r0 + rper);
             switch (threadIdx.x >> 8) {
-            case 0: gram_group<0>(A.res_k, NU, index, col, m_k, part); break;
-            case 1: gram_group<1>(A.res_k, NU, index, col, m_k, part); break;
-            case 2: gram_group<2>(A.res_k, NU, index, col, m_k, part); break;
-            default: gram_group<3>(A.res_k, NU, index, col, m_k, part); break;
+            case 0: gram_group<0>(A.res_k, NU, r0, r1, index, col, m_k, part); break;
+            case 1: gram_group<1>(A.res_k, NU, r0, r1, index, col, m_k, part); break;
+            case 2: gram_group<2>(A.res_k, NU, r0, r1, index, col, m_k, part); break;
+            default: gram_group<3>(A.res_k, NU, r0, r1, index, col, m_k, part); break;
             }
             __syncthreads();
             if (threadIdx.x < 65) {
                 const int pp = threadIdx.x, g = pp & 3, q = pp >> 2;
                 double x = 0.0;
                 for (int w = 0; w < 8; ++w) x += part[(g * 8 + w) * 17 + q];
-                gram[pp] = x;
+                if (clustered) A.gram_part[crank * 68 + pp] = x;
+                else gram[pp] = x;
+            }
+            if (clustered) {
+                cluster_barrier();
+                if (crank == 0 && threadIdx.x < 65) {      // the CTAs' partial sums in rank order
+                    double x = 0.0;
+                    for (unsigned k = 0; k < csize; ++k) x += __ldcg(A.gram_part + k * 68 + threadIdx.x);
+                    gram[threadIdx.x] = x;
+                }
             }
             __syncthreads();
             if (threadIdx.x < m_k * m_k) {
@@ -743,6 +829,7 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
         }
         __syncthreads();
         PH(6);
+        if (crank == 0) {
         if (warp == 0) {
             // solveGaussElimination, no pivoting (mod_BasicFunctions.f90:218-254).  The elimination runs on one warp, lane = row: every
             // entry sees the reference's operations in the reference's order (its updates are independent across rows and columns
@@ -782,6 +869,7 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
             UNK(r) = x;
         }
         __syncthreads();
+        }
         PH(8);
     }
 #undef PK
@@ -795,33 +883,46 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
 
     // ---------------- makeHalfTimeEField (+ push tables): NGP :392-406 ; CIC :333-366, Picard :92-94 ----------------
     if (ops & OP_HALF_E) {
-        if (A.counters && threadIdx.x < A.nsp) A.counters[(size_t)threadIdx.x * 8 + 6] = 0ull;      // tile schedulers of the sweeps that follow
+        if (crank == 0 && A.counters && threadIdx.x < A.nsp) A.counters[(size_t)threadIdx.x * 8 + 6] = 0ull;      // tile schedulers of the sweeps that follow
+        // cells of this CTA for the push tables (all of them without a cluster)
+        const int tcells = (A.scheme == 1) ? Nx : Nh;
+        const int tper = (tcells + (int)csize - 1) / (int)csize;
+        const int c_lo = 1 + (int)crank * tper, c_hi = min(tcells, (int)(crank + 1) * tper);
+        const double qnan = __longlong_as_double(0x7ff8000000000000ll);
         if (A.scheme == 0) {
-            for (int i = 1 + threadIdx.x; i <= Nh; i += FT) s0[i - 1] = 0.5 * (PHIF(i) + PHI(i) - PHIF(i + 1) - PHI(i + 1));
-            __syncthreads();
+            if (crank == 0) {
+                for (int i = 1 + threadIdx.x; i <= Nh; i += FT) s0[i - 1] = 0.5 * (PHIF(i) + PHI(i) - PHIF(i + 1) - PHI(i + 1));
+                __syncthreads();
+            }
             const double *Esm = s0;
-            if (A.smooth) {
+            if (crank == 0 && A.smooth) {
                 dev_smooth(A, s0, s1);
                 __syncthreads();
                 Esm = s1;
             }
+            if (clustered) {
+                // CTA 0 publishes EField, every CTA builds the tables of its cells from it
+                if (crank == 0) for (int i = 1 + threadIdx.x; i <= Nh; i += FT) EF(i) = Esm[i - 1] / __ldg(A.dx + i - 1);
+                cluster_barrier();
+            }
             // EField and the push tables of every species in one pass over the cells (dx_dl and 0.5 / dx_dl of a batch loaded together)
-            const double qnan = __longlong_as_double(0x7ff8000000000000ll);
-            for (int base = 1 + threadIdx.x; base <= Nh; base += CB * FT) {
-                double dx_[CB], hv_[CB];
+            for (int base = c_lo + threadIdx.x; base <= c_hi; base += CB * FT) {
+                double dx_[CB], hv_[CB], e_[CB];
 #pragma unroll
                 for (int k = 0; k < CB; ++k) {
                     const int cI = base + k * FT;
-                    dx_[k] = (cI <= Nh) ? __ldg(A.dx + cI - 1) : 1.0;
-                    hv_[k] = (cI <= Nh) ? __ldg(A.hinv + cI - 1) : 0.0;
+                    dx_[k] = (cI <= c_hi) ? __ldg(A.dx + cI - 1) : 1.0;
+                    hv_[k] = (cI <= c_hi) ? __ldg(A.hinv + cI - 1) : 0.0;
+                    e_[k] = (clustered && cI <= c_hi) ? __ldcg(A.E + cI - 1) : 0.0;
                 }
 #pragma unroll
                 for (int k = 0; k < CB; ++k) {
                     const int cI = base + k * FT;
-                    if (cI > Nh) continue;
+                    if (cI > c_hi) continue;
                     const double dx = dx_[k];
-                    const double E = Esm[cI - 1] / dx;
-                    EF(cI) = E;
+                    double E;
+                    if (clustered) E = e_[k];
+                    else { E = Esm[cI - 1] / dx; EF(cI) = E; }
                     // wall cells are not transited by the lean loop: NaN makes a lane that reaches one fail its next time test.
                     // Right-movers read entry cI, left-movers the mirrored, negated copy (every lane walks upwards)
                     const bool wall = (cI == 1 || cI == Nh);
@@ -838,6 +939,7 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
                 }
             }
         } else {
+            if (crank == 0) {
             for (int i = 1 + threadIdx.x; i <= Nh; i += FT) {
                 double w;
                 if (i == 1) {
@@ -866,10 +968,12 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
                 for (int i = threadIdx.x; i < Nh; i += FT) A.E[i] = s0[i];
             }
             __syncthreads();
+            }
+            if (clustered) cluster_barrier();      // EField is complete; every CTA builds the tables of its cells
             for (int s = 0; s < A.nsp; ++s) {
                 CellTabCIC *T = reinterpret_cast<CellTabCIC *>(A.tab) + (size_t)s * A.tab_cells;
-                for (int cI = 1 + threadIdx.x; cI <= Nx; cI += FT) {
-                    const double dx = DX(cI), el = EF(cI), er = EF(cI + 1);
+                for (int cI = c_lo + threadIdx.x; cI <= c_hi; cI += FT) {
+                    const double dx = DX(cI), el = __ldcg(A.E + cI - 1), er = __ldcg(A.E + cI);
                     CellTabCIC t;
                     t.A0 = A.qm[s] * el; t.A1 = A.qm[s] * (er - el); t.inv_dx = 1.0 / dx; t.dx = dx;
                     t.cap = 0.1 * dx / sqrt(fabs(A.qm[s] * (el - er)));
@@ -1064,6 +1168,7 @@ static FieldArgs make_args(Ctx &c) {
     A.unk = (c.scheme == IPIC_SCHEME_NGP_PERIODIC) ? c.d_Ef : c.d_phi_f;
     A.nunk = (c.scheme == IPIC_SCHEME_NGP_PERIODIC) ? c.Nh : c.Nx;
     A.L_domain = c.L_domain; A.globJ = 0;
+    A.cmp = c.d_cmp; A.gram_part = c.d_gram_part;
     A.gu = c.d_gu; A.gv = c.d_gv; A.gs = c.d_gs; A.gWinv = (c.gW != 0.0) ? 1.0 / c.gW : 0.0; A.giL = c.giL; A.giR = c.giR;
     A.phi_k = c.d_phi_k; A.res_k = c.d_res_k; A.norms = c.d_norms;
     A.and_m = c.m_Anderson; A.beta = c.Beta_k;
@@ -1082,7 +1187,21 @@ static int run_field(Ctx &c, const FieldArgs &A, unsigned ops) {
         IPIC_CUDA(cudaFuncSetAttribute(k_field, cudaFuncAttributePreferredSharedMemoryCarveout, 52));
         configured = smem;
     }
-    c.launches += 1; k_field<<<1, FT, smem, c.stream>>>(A, ops);
+    // The fused Anderson iteration runs as a thread-block cluster: CTA 0 is the kernel as ever, the others share the collect, the normal
+    // equations and the push tables (k_field).  Everything else is one CTA.
+    const int csz = ((ops & OP_AND_DECIDE) && c.scheme != IPIC_SCHEME_NGP_PERIODIC && c.m_Anderson <= 10 && c.d_cmp) ? std::max(1, std::min(8, c.field_cluster)) : 1;
+    c.launches += 1;
+    if (csz > 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(csz); cfg.blockDim = dim3(FT); cfg.dynamicSmemBytes = smem; cfg.stream = c.stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = csz; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        IPIC_CUDA(cudaLaunchKernelEx(&cfg, k_field, A, ops));
+    } else {
+        k_field<<<1, FT, smem, c.stream>>>(A, ops);
+    }
     IPIC_CUDA(cudaGetLastError());
     if (ops & (OP_HALF_E | OP_P_HALF_E)) c.tile_zero_mask = ~0u;      // every species' tile counter is zero behind this launch
 #ifdef IPIC_FIELD_PHASES

@@ -165,6 +165,9 @@ struct Ctx {
     int *d_and_state = nullptr;
     volatile long long *h_and = nullptr; double *h_and_norms = nullptr; int cap_and_norms = 0;
     int and_chunk = 6;
+    // thread-block cluster of the fused iteration's field kernel (field.cu): compact copies of the collected grids, partial sums of the
+    // normal equations per CTA; field_cluster = CTAs in the cluster (1 = single CTA)
+    long long *d_cmp = nullptr; double *d_gram_part = nullptr; int field_cluster = 8;
     long long noop_sweeps = 0;                                    // sweeps enqueued ahead that turned out to be no-ops (timing counts exclude them)
     int tridiag_mode = IPIC_TRIDIAG_PCR;
     // solver scalars (host mirror; NGP mod_potentialSolver.f90:17-22, CIC :17-23)
