@@ -60,9 +60,9 @@ struct FieldArgs {
     // host spins on -- no D2H copy, no driver synchronisation on the critical path of a nonlinear iteration
     double *h_norm; unsigned long long *h_seq; unsigned long long seq;
     unsigned long long *counters;   // [nsp][8]: slot 6 of a species is the tile counter of its push launch, zeroed by the half-E op that precedes a sweep
-    // thread-block cluster (the fused Anderson iteration): compact copies of the collected integer grids [nsp][2][acc_stride / 2] and the
-    // per-CTA partial sums of the normal equations [cluster size][68]
-    long long *cmp; double *gram_part;
+    // thread-block cluster (the fused Anderson iteration): the collected integer grids [nsp][acc_stride / 2] (slice-local prefix of the difference
+    // grid added), the slices' difference totals [nsp][16], the per-CTA partial sums of the normal equations [cluster size][68]
+    long long *cmp, *cmp_tot; double *gram_part;
     // IPIC_TRIDIAG_SCAN
     const double *gu, *gv, *gs; double gWinv; int giL, giR;
     // OP_AND_DECIDE
@@ -244,45 +244,76 @@ __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-// this CTA's share of the collect: for its slice of cells, every species, both grids: sum of the copies -> compact array, copies zeroed
-__device__ void dev_collect_slice(const FieldArgs &A, int n, bool with_runs, unsigned crank, unsigned csize) {
+// this CTA's share of the collect: for its slice of cells and every species, the sum of the copies of the grid plus the prefix sum, inside
+// the slice, of the sum of the copies of the difference grid -> compact array; the slice's difference total -> cmp_tot[species][rank];
+// the copies are zeroed.  `scratch` holds one slice (shared memory).
+__device__ void dev_collect_slice(const FieldArgs &A, int n, bool with_runs, unsigned crank, unsigned csize, long long *scratch) {
     const int per = (n + (int)csize - 1) / (int)csize;
-    const int lo = (int)crank * per, hi = min(n, lo + per);
+    const int lo = min(n, (int)crank * per), hi = min(n, lo + per);
     const int half = A.acc_stride / 2;
     for (int s = 0; s < A.nsp; ++s) {
-        for (int gsel = with_runs ? 1 : 0; gsel >= 0; --gsel) {
-            unsigned long long *g = A.acc + (size_t)s * A.acc_stride + (gsel ? half : 0);
-            long long *out = A.cmp + ((size_t)s * 2 + gsel) * half;
+        unsigned long long *g = A.acc + (size_t)s * A.acc_stride, *d = g + half;
+        long long *out = A.cmp + (size_t)s * half;
+        if (with_runs) {
             for (int base = lo + threadIdx.x; base < hi; base += CB * FT) {
                 unsigned long long q[CB];
-                collect_batch(g, A.acc_reps, A.acc_rep_stride, base, hi, q);
+                collect_batch(d, A.acc_reps, A.acc_rep_stride, base, hi, q);
 #pragma unroll
-                for (int k = 0; k < CB; ++k) { const int i = base + k * FT; if (i < hi) out[i] = (long long)q[k]; }
+                for (int k = 0; k < CB; ++k) { const int i = base + k * FT; if (i < hi) scratch[i - lo] = (long long)q[k]; }
             }
-            if (gsel && crank == csize - 1 && threadIdx.x < A.acc_reps) g[(size_t)threadIdx.x * A.acc_rep_stride + n + 1] = 0ull;   // closing entry of a run
-        }
-    }
-}
-
-// CTA 0 after the barrier: the compact arrays -> dst (species order, scaled by q*w_p), difference grids prefix-summed
-__device__ void dev_collect_compact(const FieldArgs &A, double *dst, int n, bool with_runs, long long *scratch) {
-    const int half = A.acc_stride / 2;
-    for (int s = 0; s < A.nsp; ++s) {
-        const long long *jm = A.cmp + ((size_t)s * 2) * half, *jd = jm + half;
-        if (with_runs) {
-            for (int i = threadIdx.x; i < n; i += FT) scratch[i] = __ldcg(jd + i);
+            if (crank == csize - 1 && threadIdx.x < A.acc_reps) d[(size_t)threadIdx.x * A.acc_rep_stride + n + 1] = 0ull;   // closing entry of a run
             __syncthreads();
-            block_scan_i64(scratch, n);
+            block_scan_i64(scratch, hi - lo);
+            if (threadIdx.x == 0) A.cmp_tot[s * 16 + crank] = (hi > lo) ? scratch[hi - lo - 1] : 0ll;
         }
-        for (int i = threadIdx.x; i < n; i += FT) {
-            long long q = __ldcg(jm + i);
-            if (with_runs) q += scratch[i];
-            const double v = (double)q * FX_INV;
-            if (s == 0) dst[i] = v * A.qw[0];
-            else dst[i] = dst[i] + v * A.qw[s];
+        for (int base = lo + threadIdx.x; base < hi; base += CB * FT) {
+            unsigned long long q[CB];
+            collect_batch(g, A.acc_reps, A.acc_rep_stride, base, hi, q);
+#pragma unroll
+            for (int k = 0; k < CB; ++k) { const int i = base + k * FT; if (i < hi) out[i] = (long long)q[k] + (with_runs ? scratch[i - lo] : 0ll); }
         }
         __syncthreads();
     }
+}
+
+// CTA 0 after the barrier: compact arrays + the difference totals of the slices to the left -> dst (species order, scaled by q*w_p)
+__device__ void dev_collect_compact(const FieldArgs &A, double *dst, int n, bool with_runs, unsigned csize) {
+    const int half = A.acc_stride / 2;
+    const int per = (n + (int)csize - 1) / (int)csize;
+    __shared__ long long offs[NSP_MAX][16];
+    if (threadIdx.x < A.nsp * 16) {
+        const int s = threadIdx.x >> 4, k = threadIdx.x & 15;
+        long long o = 0;
+        if (with_runs) for (int j = 0; j < k && j < (int)csize; ++j) o += __ldcg(A.cmp_tot + s * 16 + j);
+        offs[s][k] = o;
+    }
+    __syncthreads();
+    for (int base = threadIdx.x; base < n; base += CB * FT) {
+        long long v[NSP_MAX > 2 ? 2 : NSP_MAX][CB];
+        // two species at a time, loads together
+        for (int s0_ = 0; s0_ < A.nsp; s0_ += 2) {
+#pragma unroll
+            for (int k = 0; k < CB; ++k) {
+                const int i = base + k * FT;
+                v[0][k] = (i < n) ? __ldcg(A.cmp + (size_t)s0_ * half + i) : 0ll;
+                v[1][k] = (i < n && s0_ + 1 < A.nsp) ? __ldcg(A.cmp + (size_t)(s0_ + 1) * half + i) : 0ll;
+            }
+#pragma unroll
+            for (int k = 0; k < CB; ++k) {
+                const int i = base + k * FT;
+                if (i >= n) continue;
+                const int sl = i / per;
+                const double x0 = (double)(v[0][k] + offs[s0_][sl]) * FX_INV;
+                if (s0_ == 0) dst[i] = x0 * A.qw[0];
+                else dst[i] = dst[i] + x0 * A.qw[s0_];
+                if (s0_ + 1 < A.nsp) {
+                    const double x1 = (double)(v[1][k] + offs[s0_ + 1][sl]) * FX_INV;
+                    dst[i] = dst[i] + x1 * A.qw[s0_ + 1];
+                }
+            }
+        }
+    }
+    __syncthreads();
 }
 
 __device__ void dev_collect(const FieldArgs &A, double *dst, int n, bool with_runs, long long *scratch) {
@@ -573,11 +604,11 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
     // ---------------- depositJ epilogue: NGP mod_particleMover.f90:145-156 ; CIC mod_particleMoverPicard.f90:165-194 ----------------
     if (clustered) {
         // every CTA adds up the copies of the deposition grids for its slice of cells; CTA 0 goes on from the compact arrays
-        dev_collect_slice(A, Nh, A.scheme == 0, crank, csize);
+        dev_collect_slice(A, Nh, A.scheme == 0, crank, csize, reinterpret_cast<long long *>(s1));
         cluster_barrier();
     }
     if (ops & OP_FINALIZE_J) {
-        if (clustered) dev_collect_compact(A, s0, Nh, A.scheme == 0, reinterpret_cast<long long *>(s1));
+        if (clustered) dev_collect_compact(A, s0, Nh, A.scheme == 0, csize);
         else dev_collect(A, s0, Nh, A.scheme == 0, reinterpret_cast<long long *>(s1));
         __syncthreads();
         PH(1);
@@ -889,40 +920,36 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
         const int tper = (tcells + (int)csize - 1) / (int)csize;
         const int c_lo = 1 + (int)crank * tper, c_hi = min(tcells, (int)(crank + 1) * tper);
         const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+        // cluster: the unknown (mixed by CTA 0, or solved when the iteration converged) is complete behind this barrier; every CTA forms the
+        // half-time differences of the whole grid in its own shared memory (a 3-point smoothing stencil needs its neighbours) and then
+        // EField and the tables of its own cells
+        if (clustered) cluster_barrier();
         if (A.scheme == 0) {
-            if (crank == 0) {
-                for (int i = 1 + threadIdx.x; i <= Nh; i += FT) s0[i - 1] = 0.5 * (PHIF(i) + PHI(i) - PHIF(i + 1) - PHI(i + 1));
-                __syncthreads();
-            }
+            for (int i = 1 + threadIdx.x; i <= Nh; i += FT)
+                s0[i - 1] = 0.5 * (__ldcg(A.phi_f + i - 1) + __ldcg(A.phi + i - 1) - __ldcg(A.phi_f + i) - __ldcg(A.phi + i));
+            __syncthreads();
             const double *Esm = s0;
-            if (crank == 0 && A.smooth) {
+            if (A.smooth) {
                 dev_smooth(A, s0, s1);
                 __syncthreads();
                 Esm = s1;
             }
-            if (clustered) {
-                // CTA 0 publishes EField, every CTA builds the tables of its cells from it
-                if (crank == 0) for (int i = 1 + threadIdx.x; i <= Nh; i += FT) EF(i) = Esm[i - 1] / __ldg(A.dx + i - 1);
-                cluster_barrier();
-            }
             // EField and the push tables of every species in one pass over the cells (dx_dl and 0.5 / dx_dl of a batch loaded together)
             for (int base = c_lo + threadIdx.x; base <= c_hi; base += CB * FT) {
-                double dx_[CB], hv_[CB], e_[CB];
+                double dx_[CB], hv_[CB];
 #pragma unroll
                 for (int k = 0; k < CB; ++k) {
                     const int cI = base + k * FT;
                     dx_[k] = (cI <= c_hi) ? __ldg(A.dx + cI - 1) : 1.0;
                     hv_[k] = (cI <= c_hi) ? __ldg(A.hinv + cI - 1) : 0.0;
-                    e_[k] = (clustered && cI <= c_hi) ? __ldcg(A.E + cI - 1) : 0.0;
                 }
 #pragma unroll
                 for (int k = 0; k < CB; ++k) {
                     const int cI = base + k * FT;
                     if (cI > c_hi) continue;
                     const double dx = dx_[k];
-                    double E;
-                    if (clustered) E = e_[k];
-                    else { E = Esm[cI - 1] / dx; EF(cI) = E; }
+                    const double E = Esm[cI - 1] / dx;
+                    EF(cI) = E;
                     // wall cells are not transited by the lean loop: NaN makes a lane that reaches one fail its next time test.
                     // Right-movers read entry cI, left-movers the mirrored, negated copy (every lane walks upwards)
                     const bool wall = (cI == 1 || cI == Nh);
@@ -939,7 +966,6 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
                 }
             }
         } else {
-            if (crank == 0) {
             for (int i = 1 + threadIdx.x; i <= Nh; i += FT) {
                 double w;
                 if (i == 1) {
@@ -962,18 +988,18 @@ __global__ void __launch_bounds__(FT, 1) k_field(const FieldArgs A, const unsign
                 s0[i - 1] = w;
             }
             __syncthreads();
+            const double *Ec = s0;
             if (A.smooth) {
-                dev_smooth(A, s0, A.E);
-            } else {
-                for (int i = threadIdx.x; i < Nh; i += FT) A.E[i] = s0[i];
+                dev_smooth(A, s0, s1);
+                __syncthreads();
+                Ec = s1;
             }
-            __syncthreads();
-            }
-            if (clustered) cluster_barrier();      // EField is complete; every CTA builds the tables of its cells
+            // EField (N_h faces): this CTA's cells' faces, the last CTA also the closing face
+            for (int i = c_lo + threadIdx.x; i <= ((crank == csize - 1) ? Nh : c_hi); i += FT) A.E[i - 1] = Ec[i - 1];
             for (int s = 0; s < A.nsp; ++s) {
                 CellTabCIC *T = reinterpret_cast<CellTabCIC *>(A.tab) + (size_t)s * A.tab_cells;
                 for (int cI = c_lo + threadIdx.x; cI <= c_hi; cI += FT) {
-                    const double dx = DX(cI), el = __ldcg(A.E + cI - 1), er = __ldcg(A.E + cI);
+                    const double dx = DX(cI), el = Ec[cI - 1], er = Ec[cI];
                     CellTabCIC t;
                     t.A0 = A.qm[s] * el; t.A1 = A.qm[s] * (er - el); t.inv_dx = 1.0 / dx; t.dx = dx;
                     t.cap = 0.1 * dx / sqrt(fabs(A.qm[s] * (el - er)));
@@ -1168,7 +1194,7 @@ static FieldArgs make_args(Ctx &c) {
     A.unk = (c.scheme == IPIC_SCHEME_NGP_PERIODIC) ? c.d_Ef : c.d_phi_f;
     A.nunk = (c.scheme == IPIC_SCHEME_NGP_PERIODIC) ? c.Nh : c.Nx;
     A.L_domain = c.L_domain; A.globJ = 0;
-    A.cmp = c.d_cmp; A.gram_part = c.d_gram_part;
+    A.cmp = c.d_cmp; A.cmp_tot = c.d_cmp ? c.d_cmp + (size_t)NSP_MAX * ((size_t)std::max(c.Nx, c.Nh) + 2) : nullptr; A.gram_part = c.d_gram_part;
     A.gu = c.d_gu; A.gv = c.d_gv; A.gs = c.d_gs; A.gWinv = (c.gW != 0.0) ? 1.0 / c.gW : 0.0; A.giL = c.giL; A.giR = c.giR;
     A.phi_k = c.d_phi_k; A.res_k = c.d_res_k; A.norms = c.d_norms;
     A.and_m = c.m_Anderson; A.beta = c.Beta_k;
