@@ -768,7 +768,12 @@ int ipic_solve_potential(ipic_handle h, double del_t, double *remainDel_t, doubl
     if (rc) return rc;
     unsigned long long cnt[NSP_MAX * 8];
     RC(read_counters(*c, cnt));
-    for (int s = 0; s < (int)c->sp.size(); ++s) { c->substeps += (long long)cnt[s * 8]; c->sp[s].depositSubsteps = (long long)cnt[s * 8]; }
+    for (int s = 0; s < (int)c->sp.size(); ++s) {
+        c->substeps += (long long)cnt[s * 8]; c->sp[s].depositSubsteps = (long long)cnt[s * 8];
+        // what the next step's sweeps of this species look like: picks the push kernel variant (particles.cu: entry stage)
+        const double ps = (double)std::max<long long>(c->sp[s].n + c->sp[s].stats.delIdx, 1) * (double)std::max<long long>(c->sweeps, 1);
+        c->sp[s].sweep_substeps_per_particle = (double)cnt[s * 8] / ps;
+    }
     return IPIC_OK;
 }
 
@@ -992,6 +997,7 @@ int ipic_set_option(ipic_handle h, const char *name, double value) {
     if (k == "stay_min" || k == "refill_min") c->stay_min = (int)value;
     else if (k == "push_blocks") c->push_blocks = (int)value;
     else if (k == "transit_min") c->transit_min = (int)value;
+    else if (k == "entry_min") c->entry_min = (int)value;
     else if (k == "pair_species") c->pair_species = (int)value;
     else if (k == "sort_subbins") c->sort_subbins = (int)value;
     else if (k == "pair_warps") c->pair_warps = (int)value;

@@ -78,6 +78,7 @@ struct PushArgs {
     const int *stop;           // depositJ sweeps enqueued ahead of the nonlinear solve's decision: *stop != 0 (converged / stagnated) makes the launch a no-op
     int stay_min;              // a queued batch keeps looping in registers while at least this many lanes continue
     int transit_min;           // the lean face-to-face loop runs while at least this many lanes are in transit
+    int entry_min;             // ENTRY kernels: a fresh batch takes its first sub-step to the face ahead in place when at least this many lanes leave their cell; 33 = never
 };
 
 // ---- device context -------------------------------------------------------------------------------
@@ -90,6 +91,7 @@ struct SpeciesDev {
     std::vector<long long> slab_off;       // numThread+1 offsets of the reference's thread slabs
     ipic_move_stats stats{};
     long long depositSubsteps = 0;
+    double sweep_substeps_per_particle = 0.0;   // of the last implicit step's depositJ sweeps (0 = not measured yet): picks the push kernel variant
     long long n_collide = -1;              // numToCollide (mod_particle.f90:17); < 0 = all
     // null-collision sets that share this primary within one step draw their candidates from ONE keyed permutation of the collidable
     // range, one after the other: a particle is selected at most once per step, as in the reference, whose serial loop swaps every
@@ -197,6 +199,7 @@ struct Ctx {
     // options
     int stay_min = 20;
     int transit_min = 12;
+    int entry_min = 8;         // 33 = no entry stage for any species
     int sort_subbins = 0;      // cell sort key = INT(l * sub); 0 = automatic (8, or what 16 key bits allow)
     int pair_species = 0;      // 1 = depositJ of a two-species plasma in one launch (k_push_pair).  Off: measured slower (C5: 2.34 ms per
                                // sweep against 1.88 + 0.32 ms) -- both species' sweeps are issue-bound, so running them side by side frees nothing

@@ -393,7 +393,7 @@ __device__ __forceinline__ int transit_loop(double &u, double &t, const double2 
 
 // The whole sweep of one species by one warp: claims tiles until the species has none left, drains its queue, flushes its deposits
 // and counters.  `A` is always a kernel parameter (constant bank), so the body can be instantiated for several species in one kernel.
-template <int SCHEME, bool MOVE, int TS = TILE_SUBS>
+template <int SCHEME, bool MOVE, int TS = TILE_SUBS, bool ENTRY = false>
 __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const int lane) {
     DepositState D;
     // this CTA's copy of the deposition grids (see Ctx::d_acc)
@@ -735,6 +735,8 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
                 }
             }
             bool cont = false;
+            double e_l = l, e_v = v, e_t = 0.0;                 // what goes to the queue: the particle as it is, unless the entry stage moves it to a face
+            int e_cell = cell, e_pend = 0;
             if (SCHEME != 1) {
                 // Branch-free: the whole first (and for most particles only) sub-step in straight-line code.  An invalid lane reads table
                 // entry 0 (zeros) and is masked out of every effect.  Sorted input puts a sub-tile inside one or two cells, so the deposit
@@ -768,6 +770,32 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
                 } else if (done) { A.l_out[gi] = l_fw + lc; A.vx_out[gi] = v_f; }
                 nsub += done ? 1u : 0u;
                 PSTAT(4, 1); PSTAT(5, done ? 1 : 0);
+                // ---- entry stage (ENTRY instantiation, chosen per species by the host): in an electron batch most lanes leave their cell, and
+                // almost all of those through the face ahead.  When at least `entry_min` lanes go on, that first sub-step -- the general
+                // sub-step's `fwd` branch (mod_particleMover.f90:36-60) on the same operands: diff_PE, sqrt(diff_PE + v^2), (v_f - v) / a --
+                // is taken here, with the whole batch, and the lane is queued sitting on the face, ready for the transit loop.  Everything
+                // else (face behind, wall cells, no time left) is queued as it is.
+                if (ENTRY && __popc(__ballot_sync(FULL, cont)) >= A.entry_min) {
+                    const double2 t1 = __ldg(reinterpret_cast<const double2 *>(reinterpret_cast<const CellTabNGP *>(A.tab) + cellc) + 1);
+                    const bool vpos = v > 0.0;
+                    const int lb = cell + (vpos ? 1 : 0);
+                    const double v2 = __dmul_rn(v, v);
+                    const double face = (double)lb - lc;
+                    const double dl = face - lw;
+                    const double diff_PE = __dmul_rn(t1.x, dl);
+                    const double vf2 = copysign(lean_sqrt(__dadd_rn(diff_PE, v2)), v);
+                    const double tpe = fma(__dsub_rn(vf2, v), t1.y, 0.0);
+                    const bool go = cont && (diff_PE > -v2) && (lb != 1) && (lb != A.NB) && ((unsigned long long)__double_as_longlong(tpe) < A.tlim_bits);
+                    if (go) {
+                        nsub += 1;
+                        PSTAT(3, 1);
+                        e_l = face + lc; e_v = vf2; e_t = tpe; e_cell = cell + (vpos ? 1 : -1);
+                        if (!MOVE) {
+                            if (fabs(dl) == 1.0) e_pend = vpos ? cell : -cell;                   // a whole cell: the start of a run
+                            else deposit_add(W, D, lane, gacc, cell, fx_from_double(dl));
+                        }
+                    }
+                }
             } else if (valid) {
                 bool done;
                 {
@@ -812,7 +840,8 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
             if (cm) {
                 if (cont) {
                     const int qq = qcount + __popc(cm & ((1u << lane) - 1u));
-                    W.ql[qq] = l; W.qv[qq] = v; W.qt[qq] = 0.0; W.qcell[qq] = cell; W.qpend[qq] = 0; W.qidx[qq] = gi;
+                    if (ENTRY) { W.ql[qq] = e_l; W.qv[qq] = e_v; W.qt[qq] = e_t; W.qcell[qq] = e_cell; W.qpend[qq] = e_pend; W.qidx[qq] = gi; }
+                    else { W.ql[qq] = l; W.qv[qq] = v; W.qt[qq] = 0.0; W.qcell[qq] = cell; W.qpend[qq] = 0; W.qidx[qq] = gi; }
                 }
                 qcount += __popc(cm);
                 __syncwarp();
@@ -859,13 +888,13 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
     __syncwarp();
 }
 
-template <int SCHEME, bool MOVE, int TS = TILE_SUBS>
+template <int SCHEME, bool MOVE, int TS = TILE_SUBS, bool ENTRY = false>
 __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const __grid_constant__ PushArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // a sweep enqueued ahead of the nonlinear solve's decision: the field kernel in front of it ended the solve
     if (!MOVE && A.stop != nullptr && *A.stop != 0) return;
-    push_body<SCHEME, MOVE, TS>(A, reinterpret_cast<WarpSmem *>(smem_raw)[warp], lane);
+    push_body<SCHEME, MOVE, TS, ENTRY>(A, reinterpret_cast<WarpSmem *>(smem_raw)[warp], lane);
 }
 
 // depositJ sweep of TWO species in one launch.  Each warp works through one species' tiles and then through the other's; the first
@@ -908,15 +937,17 @@ static int launch_push_pair_v(Ctx &c, const PushArgs &A, const PushArgs &B) {
     return IPIC_OK;
 }
 
-template <int SCHEME, bool MOVE, int TS = TILE_SUBS>
+template <int SCHEME, bool MOVE, int TS = TILE_SUBS, bool ENTRY = false>
 static int launch_push_v(Ctx &c, const PushArgs &A) {
     if (TS == TILE_SUBS && A.tile_subs == 1) return launch_push_v<SCHEME, MOVE, 1>(c, A);      // small load: 64-particle tiles
+    // a species whose particles mostly leave their cell (electrons) takes the first sub-step inside the fresh path (push_body: entry stage)
+    if (!ENTRY && !MOVE && SCHEME != 1 && TS == TILE_SUBS && A.entry_min <= 32) return launch_push_v<SCHEME, MOVE, (SCHEME != 1 && !MOVE) ? TILE_SUBS : TS, (SCHEME != 1 && !MOVE)>(c, A);
     const size_t smem = (size_t)PUSH_WARPS * sizeof(WarpSmem);
     static bool configured[64] = {};          // function attributes are per device
     if (!configured[c.device & 63]) {
-        IPIC_CUDA(cudaFuncSetAttribute(k_push<SCHEME, MOVE, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IPIC_CUDA(cudaFuncSetAttribute(k_push<SCHEME, MOVE, TS, ENTRY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // leave the rest of the 256 KB to L1: the per-cell tables are gathered through it
-        IPIC_CUDA(cudaFuncSetAttribute(k_push<SCHEME, MOVE, TS>, cudaFuncAttributePreferredSharedMemoryCarveout, 52));
+        IPIC_CUDA(cudaFuncSetAttribute(k_push<SCHEME, MOVE, TS, ENTRY>, cudaFuncAttributePreferredSharedMemoryCarveout, 52));
         configured[c.device & 63] = true;
     }
     {
@@ -925,7 +956,7 @@ static int launch_push_v(Ctx &c, const PushArgs &A) {
         else IPIC_CUDA(cudaMemsetAsync(A.tile_counter, 0, sizeof(unsigned), c.stream));
     }
     const int blocks = c.push_blocks > 0 ? c.push_blocks : c.num_sms;
-    c.launches += 1; k_push<SCHEME, MOVE, TS><<<blocks, PUSH_THREADS, smem, c.stream>>>(A);
+    c.launches += 1; k_push<SCHEME, MOVE, TS, ENTRY><<<blocks, PUSH_THREADS, smem, c.stream>>>(A);
     IPIC_CUDA(cudaGetLastError());
     return IPIC_OK;
 }
@@ -987,6 +1018,12 @@ static int make_push_args(Ctx &c, int sp, double del_t, PushArgs &A) {
     A.ttab = c.d_ttab + (size_t)sp * 2 * (cells + 2);
     A.stay_min = std::min(32, std::max(1, c.stay_min));
     A.transit_min = std::min(33, std::max(1, c.transit_min));   // 33 disables the transit loop
+    // entry stage: for species whose particles leave their cell in most sweeps -- measured on the previous step (sub-steps per particle per
+    // sweep above 1.5), before the first step guessed from the charge-to-mass ratio (electron-like) -- unless the option switches it off (33)
+    {
+        const bool many = (s.sweep_substeps_per_particle > 0.0) ? (s.sweep_substeps_per_particle > 1.5) : (std::fabs(s.q_over_m) > 1.0e10);
+        A.entry_min = (c.entry_min <= 32 && many) ? std::max(1, c.entry_min) : 33;
+    }
     return IPIC_OK;
 }
 

@@ -91,7 +91,7 @@ def test_depositJ(pair):
     ip.depositJ(solver, plist, world, del_t)
     assert np.array_equal(solver.J, Jg)
     for name, vals, default in (("stay_min", (1, 32), 20), ("tile_order", (0, 2), 1), ("push_blocks", (1, 7), 0), ("transit_min", (1, 33), 12),
-                                ("tile_subs", (1, 8), 0)):
+                                ("tile_subs", (1, 8), 0), ("entry_min", (1, 33), 8)):
         for v in vals:
             solver.set_option(name, v)
             ip.depositJ(solver, plist, world, del_t)
