@@ -512,16 +512,44 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
 #ifndef IPIC_FINISH_STAGE
 #define IPIC_FINISH_STAGE 1
 #endif
-                        bool fin = IPIC_FINISH_STAGE && tr && out && (t_fail == t_fail);
+#ifdef IPIC_PUSH_STATS
+                        if (tr && out && !(t_fail == t_fail)) atomicAdd(&g_push_stats[12], 1ull);      // left the loop on a NaN: turning point, wall cell, a = 0
+                        if (tr && out && (t_fail == t_fail)) atomicAdd(&g_push_stats[13], 1ull);       // left the loop on the clock
+#endif
+                        // A lane that left the loop on a NaN inside an interior cell with a /= 0 cannot reach the face ahead (s = v^2 +- 2 a dx <= 0,
+                        // i.e. the general sub-step's `diff_PE > -v^2` is false, re-checked below on its own operands): it either ends the step
+                        // inside the cell (same formula as above, whatever the sign of v_f) or comes back to the face it entered through --
+                        // the general sub-step's `bwd` branch with l on the face: diff_PE = 0, v_f = -v, dtau = -2 v / a -- and goes on
+                        // from there into the neighbouring cell, in transit again.
+                        const bool outx = tr && out;
+                        const bool clockx = outx && (t_fail == t_fail);
+                        const bool nanx = outx && !(t_fail == t_fail) && ((unsigned)(cell - 2) < tr_span);
+                        bool fin = IPIC_FINISH_STAGE && (clockx || nanx);
+                        bool back = false;
                         if (__any_sync(FULL, fin)) {
-                            const double2 t0 = __ldg(reinterpret_cast<const double2 *>(reinterpret_cast<const CellTabNGP *>(A.tab) + (fin ? cell : 0)));
+                            const double2 *tp2 = reinterpret_cast<const double2 *>(reinterpret_cast<const CellTabNGP *>(A.tab) + (fin ? cell : 0));
+                            const double2 t0 = __ldg(tp2);
                             const double lc = (SCHEME == 2) ? (double)cell : 0.0;
                             const double lw = l - lc;
                             const double dtau = del_t - tp;
                             const double v_f0 = fma(t0.x, dtau, v);
                             const double l_f0 = fma(__dmul_rn(__dadd_rn(v, v_f0), dtau), t0.y, lw);
                             const bool inCell = (SCHEME == 2) ? ((int)(l_f0 + 1.0) == 1) : ((int)l_f0 == cell);
-                            fin = fin && inCell && (vpos == (v_f0 > 0.0));
+                            bool turnable = false;
+                            if (__any_sync(FULL, fin && nanx)) {
+                                const double2 t1 = __ldg(tp2 + 1);                         // two_a_dx, 1 / a
+                                const double dfw = vpos ? t1.x : -t1.x;                    // diff_PE towards the face ahead: two_a_dx * (+-1)
+                                turnable = fin && nanx && (t0.x != 0.0) && !(dfw > -__dmul_rn(v, v));
+                                const double tpb = fma(__dsub_rn(-v, v), t1.y, tp);
+                                back = turnable && !inCell && ((unsigned long long)__double_as_longlong(tpb) < A.tlim_bits);
+                                if (back) {
+                                    nsub += 1;
+                                    PSTAT(3, 1);
+                                    if (!MOVE && pend != 0) { close_run(W, D, lane, gacc, gdacc, pend, cell); pend = 0; }
+                                    tp = tpb; v = -v; cell += vpos ? -1 : 1;               // l stays: the face between the two cells
+                                }
+                            }
+                            fin = fin && inCell && ((clockx && (vpos == (v_f0 > 0.0))) || turnable);
                             if (fin) {
                                 nsub += 1;
                                 PSTAT(3, 1);
@@ -535,6 +563,7 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
                                 }
                             }
                         }
+                        requeue = requeue || back;
                         valid = valid && !fin;
                     }
                 }
@@ -1036,6 +1065,7 @@ void push_stats_dump() {
     fprintf(stderr, "[push stats] general sub-step: %llu issued per warp, %llu valid lanes -> utilisation %.3f; queue pops %llu\n", h[2], h[3],
             h[2] ? (double)h[3] / (double)(h[2] * 32) : 0.0, h[6]);
     fprintf(stderr, "[push stats] fresh: %llu batches, %llu lanes finished (%.3f of slots)\n", h[4], h[5], h[4] ? (double)h[5] / (double)(h[4] * 32) : 0.0);
+    fprintf(stderr, "[push stats] lanes leaving the transit loop: %llu on a NaN (turning point / wall cell / a = 0), %llu on the clock\n", h[12], h[13]);
     fprintf(stderr, "[push stats] warps: %llu; mean busy time per warp %.1f us; the latest warp of the LONGEST launch ran %.1f us (every launch's latest >= its mean: tail)\n", h[11],
             h[11] ? (double)h[8] / (double)h[11] * 1e-3 : 0.0, (double)h[9] * 1e-3);
     unsigned long long z[16] = {};
