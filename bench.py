@@ -13,6 +13,15 @@ plasma, 4096 cells, 1e9 particles over 8 GPUs = 1.25e8 particles per GPU, weak s
 (OpenMP/NGP/InputData) with the cell size kept.  Particles are generated on the device (counter-based PCG32) because 4 GB per
 GPU is too much to draw on the host in a bench; the e2e leg then moves them through HOST buffers every step.
 
+N > 1 (torchrun, one rank per GPU): the J grid is all-reduced once per residual evaluation, through peer memory over NVLink
+(csrc/peer.cu; the CUDA IPC handles of the ranks' windows travel through torch.distributed) or, with --no-peer or when the windows
+cannot be mapped, through NCCL.
+
+Keys beyond the contract: `particle_sweeps_per_s` (particles x sweeps per second: sub-steps per particle per sweep are physics and
+fall with the noise level, i.e. with the GPU count under weak scaling -- DESIGN.md 5), `e2e.upload_ms_per_step` /
+`e2e.download_ms_per_step` (the PCIe share of the e2e leg), `e2e_resident`, `roofline.move_kernel` / `ion_sweeps` / `issue_bound`,
+`breakdown_ms_per_step`.
+
 Prints ONE JSON line (rank 0).  Nothing here reads /root/reference.
 """
 import argparse
