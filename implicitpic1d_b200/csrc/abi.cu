@@ -476,6 +476,7 @@ int ipic_destroy(ipic_handle h) {
     if (c->h_scal) cudaFreeHost(c->h_scal);
     if (c->d_and_state) cudaFree(c->d_and_state);
     if (c->d_cmp) cudaFree(c->d_cmp);
+    if (c->d_fill) cudaFree(c->d_fill);
     if (c->d_gram_part) cudaFree(c->d_gram_part);
     if (c->h_and) cudaFreeHost(const_cast<long long *>(c->h_and));
     if (c->h_and_norms) cudaFreeHost(c->h_and_norms);
@@ -1010,6 +1011,7 @@ int ipic_set_option(ipic_handle h, const char *name, double value) {
     else if (k == "dump_push_stats") { cudaStreamSynchronize(c->stream); push_stats_dump(); }      // measurement builds (-DIPIC_PUSH_STATS): print + clear
     else if (k == "use_tma") { /* accepted for compatibility: the streaming path is register-prefetched */ }
     else if (k == "lazy_compaction") c->lazy_compaction = (int)value;
+    else if (k == "fill_compaction") c->fill_compaction = (int)value;
     else if (k == "norm_flag") c->norm_flag = (int)value;
     else { set_error("unknown option " + k); return IPIC_ERR_ARG; }
     return IPIC_OK;

@@ -208,6 +208,8 @@ struct Ctx {
     int tile_subs = 0;            // 0 = automatic (8 sub-tiles of 64 particles, fewer for small loads)
     int push_blocks = 0;          // 0 = one CTA per SM
     int lazy_compaction = 0;
+    int fill_compaction = 1;      // arrays without slab identity (device loader, sorted): absorbed particles' slots are filled from the tail instead of a stable scatter
+    unsigned *d_fill = nullptr; long long cap_fill = 0;
     int norm_flag = 1;            // 1 = k_field publishes the residual norm into pinned host memory and the host spins on a sequence number;
                                   // 0 = D2H copy + cudaStreamSynchronize per nonlinear iteration
     unsigned long long norm_seq = 0;

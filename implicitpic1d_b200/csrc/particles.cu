@@ -1496,6 +1496,48 @@ static void swap_banks(SpeciesDev &s) {
     std::swap(s.l, s.l2); std::swap(s.vx, s.vx2); std::swap(s.vy, s.vy2); std::swap(s.vz, s.vz2);
 }
 
+// Compaction by filling: the holes among the first `total` slots take the live particles of the tail, both in ascending order (two
+// stream compactions of indices, deterministic).  Touches the absorbed particles only -- a few thousand of 6e7 per step -- where the stable
+// scatter rewrites all 64 B of every particle; the order of the survivors changes, so this is for arrays whose order is not the
+// reference's slab order any more (device loader, after a cell sort) and without recorded reflections.
+struct SelDead { const double *l; __device__ bool operator()(unsigned i) const { return l[i] < 0.0; } };
+struct SelLive { const double *l; __device__ bool operator()(unsigned i) const { return l[i] >= 0.0; } };
+__global__ void k_fill_holes(const unsigned *__restrict__ holes, const unsigned *__restrict__ live, const int *__restrict__ nsel, double *l, double *vx,
+                             double *vy, double *vz) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nsel[0] || k >= nsel[1]) return;
+    const unsigned d = holes[k], sfrom = live[k];
+    l[d] = l[sfrom]; vx[d] = vx[sfrom]; vy[d] = vy[sfrom]; vz[d] = vz[sfrom];
+}
+static int compact_by_filling(Ctx &c, SpeciesDev &s, long long n, long long total) {
+    const long long gone = n - total;
+    if (c.cap_fill < 2 * gone + 64) {
+        if (c.d_fill) cudaFree(c.d_fill);
+        c.cap_fill = 2 * gone + gone / 2 + 4096;
+        IPIC_CUDA(cudaMalloc(&c.d_fill, (size_t)c.cap_fill * sizeof(unsigned)));
+    }
+    unsigned *holes = c.d_fill, *live = c.d_fill + (c.cap_fill / 2);
+    int *d_num = reinterpret_cast<int *>(c.d_total + 4);
+    cub::CountingInputIterator<unsigned> front(0u), tail((unsigned)total);
+    size_t t0 = 0, t1 = 0;
+    cub::DeviceSelect::If(nullptr, t0, front, holes, d_num, (int)total, SelDead{s.l}, c.stream);
+    cub::DeviceSelect::If(nullptr, t1, tail, live, d_num + 1, (int)gone, SelLive{s.l}, c.stream);
+    const size_t tmp = std::max(t0, t1);
+    if (tmp > c.cap_sort_tmp) {
+        if (c.d_sort_tmp) cudaFree(c.d_sort_tmp);
+        c.cap_sort_tmp = tmp + tmp / 8;
+        IPIC_CUDA(cudaMalloc(&c.d_sort_tmp, c.cap_sort_tmp));
+    }
+    size_t tb = c.cap_sort_tmp;
+    c.launches += 1; cub::DeviceSelect::If(c.d_sort_tmp, tb, front, holes, d_num, (int)total, SelDead{s.l}, c.stream);
+    tb = c.cap_sort_tmp;
+    c.launches += 1; cub::DeviceSelect::If(c.d_sort_tmp, tb, tail, live, d_num + 1, (int)gone, SelLive{s.l}, c.stream);
+    c.launches += 1; k_fill_holes<<<(unsigned)((gone + 255) / 256), 256, 0, c.stream>>>(holes, live, d_num, s.l, s.vx, s.vy, s.vz);
+    IPIC_CUDA(cudaGetLastError());
+    s.n = total;
+    return IPIC_OK;
+}
+
 // Runs after the move kernel.  Fills wallLoss/energyLoss/momentumLoss and removes absorbed particles.
 int compact_species(Ctx &c, int sp) {
     SpeciesDev &s = c.sp[sp];
@@ -1529,6 +1571,7 @@ int compact_species(Ctx &c, int sp) {
     s.stats.energyLoss[0] = c.h_scal[0]; s.stats.energyLoss[1] = c.h_scal[1];
     s.stats.momentumLoss[0] += c.h_scal[2]; s.stats.momentumLoss[1] += c.h_scal[3];
     if (total == n) return IPIC_OK;   // nothing absorbed: arrays already compact
+    if (nb == 0 && s.nRef == 0 && c.fill_compaction && (n - total) * 8 < n && n < (1ll << 31)) return compact_by_filling(c, s, n, total);
     if (nb > 0) {
         IPIC_CUDA(cudaMemcpyAsync(d_slab, s.slab_off.data(), nb * sizeof(long long), cudaMemcpyHostToDevice, c.stream));
         c.launches += 1; k_slab_offsets<<<(nb + 7) / 8, 256, 0, c.stream>>>(s.l, d_tileOffset, d_slab, d_slab + cap_slab, nb, n);

@@ -645,3 +645,48 @@ def test_anderson_decision_on_the_device_is_independent_of_the_chunk(name):
                 assert len(a[6]) == len(b[6])
                 pa, pb = np.frombuffer(a[7]), np.frombuffer(b[7])
                 assert np.max(np.abs(pa - pb)) <= 1e-9 * np.max(np.abs(pb))
+
+
+def test_compaction_by_filling_keeps_the_particle_set():
+    """Arrays without slab identity (device loader, after a cell sort) are compacted by moving live particles of the tail into the
+    holes the absorbed ones leave (`fill_compaction`, default) instead of the stable scatter: the same set of survivors, the same loss
+    sums and counts, another order.  Both modes from the same seed; the following step's J (an integer sum: order-independent) is
+    bit-identical."""
+    import torch
+    from implicitpic1d_b200.domain import readWorld
+    from implicitpic1d_b200 import constants as K
+    n_ave, T_e, Nx, L_dom = 1e16, 4.0, 513, 0.02
+    res = []
+    for fill in (1, 0):
+        world = readWorld(0, Nx, L_dom, 0, 0.0, 1, 1, 1, T_e, n_ave)
+        solver = ip.potentialSolver(world, 0.0, 0.0, 0.0, 0.0)
+        try:
+            N = 1_000_000
+            L = ip.load_library()
+            m_ion = 4.002602 * K.m_amu - K.m_e
+            plist = [ip.Particle(K.m_e, -K.e, n_ave * world.L_domain / N, 0, 0, "e", 1),
+                     ip.Particle(m_ion, K.e, n_ave * world.L_domain / N, 0, 0, "He+", 1)]
+            solver._bind(plist)
+            solver.set_option("fill_compaction", fill)
+            _lib.check(L.ipic_generate_particles(solver._h, 0, N, T_e, 0.0, 99))
+            _lib.check(L.ipic_generate_particles(solver._h, 1, N, 0.025, 0.0, 99))
+            for p in plist:
+                _lib.check(L.ipic_sort_particles(solver._h, p._index))
+            ip.initializeSolver(solver, 1e-8, 0.0, 0, 10, 0.5, 100)
+            solver.solveInitialPotential(plist, world, 0.0)
+            del_t = K.del_t_from_deck(n_ave, 1.0, 1.0)
+            out = []
+            for step in range(3):
+                ip.solvePotential(solver, plist, world, del_t, del_t, del_t, step * del_t)
+                for p in plist:
+                    p._refresh_stats()
+                    arr = torch.stack(p.device_arrays(), dim=1).cpu().numpy()
+                    assert arr.shape[0] == p.count() and np.all(arr[:, 0] >= 1.0)
+                    order = np.lexsort((arr[:, 3], arr[:, 2], arr[:, 1], arr[:, 0]))
+                    out.append((p.count(), p.delIdx, p.wallLoss.tobytes(), p.energyLoss.tobytes(), arr[order].tobytes()))
+                out.append(solver.J.tobytes())
+            assert out[0][1] > 0                                        # electrons were absorbed in the first step
+            res.append(out)
+        finally:
+            solver.close()
+    assert res[0] == res[1]
