@@ -76,7 +76,7 @@ UNIT = "particle-substeps/s"
 SEED = 20261017
 
 
-TRANSIT_FLOOR_CYCLES = 38.7    # scripts/micro/transit_bench2.cu on B200: the shipped crossing loop alone, 8 warps per SM sub-partition
+TRANSIT_FLOOR_CYCLES = 29.3    # scripts/micro/transit_bench2.cu 1 on B200: the shipped crossing loop alone, 8 warps per SM sub-partition, the lanes of a warp in one cell (cell-sorted particles); 38.7 with every lane in another line of the table (L1 gather-bound)
 
 
 def measured_peak_gbs():
@@ -527,7 +527,8 @@ def run_cuda_arm(args, w):
         roofline["ion_sweeps"] = {"achieved": ion, "peak": peak, "unit": "GB/s", "frac": ion / peak, "avg_launch_ms": t_dep1 / n_dep1}
     # second bound of the same kernel: the sub-step loop of the electrons is FP64 work, not bytes.  One face-to-face crossing is 10 FP64 + 12.5 other
     # instructions per warp; FP64 instructions issue every other cycle on sm_100 (scripts/micro/fp64_tput.cu), and the loop in isolation at 8 warps
-    # per sub-partition runs at 38.7 cycles per crossing (scripts/micro/transit_bench2.cu, profiles/r2_micro_transit_bench2.txt) -- the floor quoted here.
+    # per sub-partition runs at 29.3 cycles per crossing when a warp's lanes read one line of the table, as cell-sorted particles make them (38.7 with every
+    # lane in another line: L1 gather) (scripts/micro/transit_bench2.cu, profiles/r2_micro_transit_bench2.txt) -- the floor quoted here.
     t_e_sweeps, n_e_sweeps = (t_pair, n_pair) if paired else (t_dep0, n_dep0)     # paired: the electrons share the launch with the ions
     if w["scheme"] != 1 and t_e_sweeps > 0:
         props = torch.cuda.get_device_properties(torch.cuda.current_device())

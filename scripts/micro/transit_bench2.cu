@@ -1,3 +1,4 @@
+#include <cstdlib>
 // Micro-benchmark + numerical check of the round-2 transit loop.  lean_sqrt and transit_loop below are the device functions of
 // implicitpic1d_b200/csrc/particles.cu, verbatim (scripts/micro/sync_transit.py refreshes them).
 //   part 1: cycles per face-to-face crossing per SM sub-partition against resident warps (table of 4096 cells: L1 resident)
@@ -127,8 +128,9 @@ __device__ __forceinline__ int transit_loop(double &u, double &t, const double2 
 
 // ---- end of the copy ----
 
-__global__ void __launch_bounds__(1024, 1) k_transit(const double2 *__restrict__ ttab, int ncell, int reps, unsigned long long tlim_bits, double *out, long long *cyc) {
-    const int cell = 2 + (threadIdx.x * 37 + blockIdx.x * 11) % (ncell / 2);
+__global__ void __launch_bounds__(1024, 1) k_transit(const double2 *__restrict__ ttab, int ncell, int reps, unsigned long long tlim_bits, double *out, long long *cyc, int mode) {
+    // mode 0: every lane of a warp starts in another 128-byte line of the table; 1: one cell per warp (sorted particles); 2: consecutive cells
+    const int cell = mode == 0 ? 2 + (threadIdx.x * 37 + blockIdx.x * 11) % (ncell / 2) : mode == 1 ? 2 + ((threadIdx.x >> 5) * 37 + blockIdx.x * 11) % (ncell / 2) : 2 + (threadIdx.x + blockIdx.x * 11) % (ncell / 2);
     const double v0 = 1.0e6 + threadIdx.x;
     long long crossings = 0;
     double acc = 0.0;
@@ -164,7 +166,8 @@ __global__ void k_check(unsigned long long seed, int iters, int mode, unsigned l
     atomicAdd(bad, b0); atomicAdd(bad + 1, b2);
 }
 
-int main() {
+int main(int argc, char **argv) {
+    const int mode = argc > 1 ? atoi(argv[1]) : 0;
     const int ncell = 4096, reps = 10;
     double2 *tt; double *out; long long *dc;
     cudaMalloc(&tt, ncell * sizeof(double2)); cudaMalloc(&out, 148 * 1024 * 8); cudaMalloc(&dc, 16);
@@ -174,7 +177,7 @@ int main() {
     cudaMemcpy(tt, h, ncell * sizeof(double2), cudaMemcpyHostToDevice);
     const double tl = 1.0e30; unsigned long long tb; memcpy(&tb, &tl, 8);
     for (int threads : {128, 256, 512, 768, 1024}) {
-        for (int rep = 0; rep < 2; ++rep) { k_transit<<<148, threads>>>(tt, ncell, reps, tb, out, dc); cudaDeviceSynchronize(); }
+        for (int rep = 0; rep < 2; ++rep) { k_transit<<<148, threads>>>(tt, ncell, reps, tb, out, dc, mode); cudaDeviceSynchronize(); }
         long long c[2]; cudaMemcpy(c, dc, 16, cudaMemcpyDeviceToHost);
         const double w = threads / 128.0;
         printf("threads %4d (%.0f warps/SMSP): %.1f cycles per crossing per warp, %.1f cycles per crossing per SMSP\n", threads, w, (double)c[0] / c[1], (double)c[0] / c[1] / w);
