@@ -477,6 +477,8 @@ int ipic_destroy(ipic_handle h) {
     if (c->d_and_state) cudaFree(c->d_and_state);
     if (c->d_cmp) cudaFree(c->d_cmp);
     if (c->d_fill) cudaFree(c->d_fill);
+    if (c->d_abs) cudaFree(c->d_abs);
+    if (c->d_abs_count) cudaFree(c->d_abs_count);
     if (c->d_gram_part) cudaFree(c->d_gram_part);
     if (c->h_and) cudaFreeHost(const_cast<long long *>(c->h_and));
     if (c->h_and_norms) cudaFreeHost(c->h_and_norms);

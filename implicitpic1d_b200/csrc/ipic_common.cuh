@@ -48,6 +48,7 @@ struct CellTabCIC {   // OpenMP/CIC/src/mod_particleMoverPicard.f90:17-65,92-94 
 #endif
 constexpr int PUSH_THREADS = IPIC_PUSH_THREADS;
 constexpr int PUSH_WARPS = PUSH_THREADS / 32;
+constexpr unsigned ABS_CAP = 1u << 20;   // absorbed particles per species and move the list holds (more: the array is counted instead)
 constexpr int MAX_GRID_SMEM = 8192;   // largest N_h the shared-memory limb grid supports (12 B per cell)
 
 struct PushArgs {
@@ -74,6 +75,9 @@ struct PushArgs {
     double t_lim;              // smallest double t with !(del_t - t > f_tol): `t < t_lim` is the reference's `del_t - t > f_tol`
     unsigned long long tlim_bits;   // bit pattern of t_lim (0 when t_lim <= 0): for t >= 0, `bits(t) < tlim_bits` as unsigned integers is `t < t_lim`,
                                // and NaN, -0 and negative t compare high
+    unsigned *abs_list;        // MOVE, arrays without slab identity: indices of the particles absorbed in this launch, in no order (null: not recorded)
+    unsigned *abs_count;       // entries appended (may exceed abs_cap: then the list is incomplete and the caller counts the array instead)
+    unsigned abs_cap;
     unsigned char *refl;       // MOVE, Neumann walls only: per-particle flag "reflected during this step" (refRecordIdx), else null
     const int *stop;           // depositJ sweeps enqueued ahead of the nonlinear solve's decision: *stop != 0 (converged / stagnated) makes the launch a no-op
     int stay_min;              // a queued batch keeps looping in registers while at least this many lanes continue
@@ -91,6 +95,7 @@ struct SpeciesDev {
     std::vector<long long> slab_off;       // numThread+1 offsets of the reference's thread slabs
     ipic_move_stats stats{};
     long long depositSubsteps = 0;
+    bool abs_listed = false;               // the last move recorded the indices of the particles it absorbed (Ctx::d_abs)
     double sweep_substeps_per_particle = 0.0;   // of the last implicit step's depositJ sweeps (0 = not measured yet): picks the push kernel variant
     long long n_collide = -1;              // numToCollide (mod_particle.f90:17); < 0 = all
     // null-collision sets that share this primary within one step draw their candidates from ONE keyed permutation of the collidable
@@ -210,6 +215,9 @@ struct Ctx {
     int lazy_compaction = 0;
     int fill_compaction = 1;      // arrays without slab identity (device loader, sorted): absorbed particles' slots are filled from the tail instead of a stable scatter
     unsigned *d_fill = nullptr; long long cap_fill = 0;
+    // indices of the particles the last move absorbed, appended by the move kernel itself (arrays without slab identity): the compaction
+    // then touches the absorbed particles only instead of reading every l.  [NSP_MAX][2][ABS_CAP] (as appended, sorted) + [NSP_MAX] counts
+    unsigned *d_abs = nullptr; unsigned *d_abs_count = nullptr;
     int norm_flag = 1;            // 1 = k_field publishes the residual norm into pinned host memory and the host spins on a sequence number;
                                   // 0 = D2H copy + cudaStreamSynchronize per nonlinear iteration
     unsigned long long norm_seq = 0;

@@ -700,6 +700,10 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
                             const unsigned gi = idx & 0x7fffffffu;
                             A.l_out[gi] = left ? -1.0 : -2.0;
                             A.vx_out[gi] = v_f;
+                            if (A.abs_list) {
+                                const unsigned slot = atomicAdd(A.abs_count, 1u);
+                                if (slot < A.abs_cap) A.abs_list[slot] = gi;
+                            }
                         }
                     } else if (!(rem > f_tol)) {
                         if (MOVE) {
@@ -1116,6 +1120,17 @@ int launch_move(Ctx &c, int sp, double del_t) {
         }
         IPIC_CUDA(cudaMemsetAsync(S.refl, 0, (size_t)A.n, c.stream));
         A.refl = S.refl;
+    }
+    // arrays without slab identity and without recorded reflections are compacted by filling (compact_species): the kernel lists what it absorbs
+    S.abs_listed = false;
+    if (S.slab_off.empty() && !A.refl && c.fill_compaction && sp < NSP_MAX) {
+        if (!c.d_abs) {
+            IPIC_CUDA(cudaMalloc(&c.d_abs, (size_t)NSP_MAX * 2 * ABS_CAP * sizeof(unsigned)));
+            IPIC_CUDA(cudaMalloc(&c.d_abs_count, NSP_MAX * sizeof(unsigned)));
+            IPIC_CUDA(cudaMemsetAsync(c.d_abs_count, 0, NSP_MAX * sizeof(unsigned), c.stream));
+        }
+        A.abs_list = c.d_abs + (size_t)sp * 2 * ABS_CAP; A.abs_count = c.d_abs_count + sp; A.abs_cap = ABS_CAP;
+        S.abs_listed = true;
     }
     if (c.scheme == IPIC_SCHEME_NGP) return launch_push_v<0, true>(c, A);
     if (c.scheme == IPIC_SCHEME_NGP_PERIODIC) return launch_push_v<2, true>(c, A);
@@ -1538,11 +1553,82 @@ static int compact_by_filling(Ctx &c, SpeciesDev &s, long long n, long long tota
     return IPIC_OK;
 }
 
+// ---- compaction from the list of absorbed particles (arrays without slab identity) ----
+// The move kernel appended the index of every particle it absorbed; sorted ascending, the list gives the loss sums in a fixed order and the
+// holes to fill, without a pass over the arrays: the first H entries (index < total = n - gone) are the holes, the others are the dead
+// slots of the tail [total, n), whose live slots -- found by rank -- move into the holes in ascending order, as compact_by_filling does.
+__global__ void __launch_bounds__(RED_THREADS) k_absorbed_loss(const unsigned *__restrict__ idx, unsigned gone, const double *__restrict__ l,
+                                                               const double *__restrict__ vx, const double *__restrict__ vy, const double *__restrict__ vz,
+                                                               double *out4, unsigned *count_to_clear) {
+    double a[4] = {0, 0, 0, 0};   // energy L, energy R, momentum L, momentum R
+    const unsigned per = (gone + RED_THREADS - 1) / RED_THREADS;
+    const unsigned b = threadIdx.x * per, e = min(b + per, gone);
+    for (unsigned k = b; k < e; ++k) {
+        const unsigned i = idx[k];
+        // energyLoss += v_f**2 + SUM(v_y**2 + v_z**2) ; momentumLoss += v_f   (mod_particleMover.f90:206-215)
+        const double vf = vx[i], y = vy[i], z = vz[i];
+        const double en = vf * vf + (y * y + z * z);
+        if (l[i] == -1.0) { a[0] += en; a[2] += vf; } else { a[1] += en; a[3] += vf; }
+    }
+    block_reduce_store<4>(a, out4);
+    if (threadIdx.x == 0) *count_to_clear = 0u;       // ready for the next move
+}
+__device__ __forceinline__ unsigned upper_bound_u(const unsigned *a, unsigned n, unsigned x) {      // entries <= x
+    unsigned lo = 0, hi = n;
+    while (lo < hi) { const unsigned mid = (lo + hi) >> 1; if (a[mid] <= x) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+__global__ void k_absorbed_fill(const unsigned *__restrict__ idx, unsigned gone, unsigned total, double *l, double *vx, double *vy, double *vz) {
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= gone) return;
+    const unsigned H = total ? upper_bound_u(idx, gone, total - 1u) : 0u;      // holes: absorbed particles among the first `total` slots
+    if (k >= H) return;
+    // the (k+1)-th live slot of the tail: smallest x with (x + 1) - (dead slots of the tail up to total + x) = k + 1
+    unsigned lo = 0, hi = gone - 1u;
+    while (lo < hi) {
+        const unsigned mid = (lo + hi) >> 1;
+        const unsigned live = (mid + 1u) - (upper_bound_u(idx, gone, total + mid) - H);
+        if (live >= k + 1u) hi = mid; else lo = mid + 1u;
+    }
+    const unsigned d = idx[k], sfrom = total + lo;
+    l[d] = l[sfrom]; vx[d] = vx[sfrom]; vy[d] = vy[sfrom]; vz[d] = vz[sfrom];
+}
+static int compact_from_list(Ctx &c, int sp, long long gone) {
+    SpeciesDev &s = c.sp[sp];
+    const long long n = s.n, total = n - gone;
+    unsigned *raw = c.d_abs + (size_t)sp * 2 * ABS_CAP, *sorted = raw + ABS_CAP;
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, tmp, raw, sorted, (int)gone, 0, 32, c.stream);
+    if (tmp > c.cap_sort_tmp) {
+        if (c.d_sort_tmp) cudaFree(c.d_sort_tmp);
+        c.cap_sort_tmp = tmp + tmp / 8;
+        IPIC_CUDA(cudaMalloc(&c.d_sort_tmp, c.cap_sort_tmp));
+    }
+    size_t tb = c.cap_sort_tmp;
+    c.launches += 1; cub::DeviceRadixSort::SortKeys(c.d_sort_tmp, tb, raw, sorted, (int)gone, 0, 32, c.stream);
+    c.launches += 1; k_absorbed_loss<<<1, RED_THREADS, 0, c.stream>>>(sorted, (unsigned)gone, s.l, s.vx, s.vy, s.vz, c.d_scal, c.d_abs_count + sp);
+    c.launches += 1; k_absorbed_fill<<<(unsigned)((gone + 255) / 256), 256, 0, c.stream>>>(sorted, (unsigned)gone, (unsigned)total, s.l, s.vx, s.vy, s.vz);
+    IPIC_CUDA(cudaGetLastError());
+    IPIC_CUDA(cudaMemcpyAsync(c.h_scal, c.d_scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    IPIC_CUDA(cudaStreamSynchronize(c.stream));
+    s.stats.energyLoss[0] = c.h_scal[0]; s.stats.energyLoss[1] = c.h_scal[1];
+    s.stats.momentumLoss[0] += c.h_scal[2]; s.stats.momentumLoss[1] += c.h_scal[3];
+    s.n = total;
+    return IPIC_OK;
+}
+
 // Runs after the move kernel.  Fills wallLoss/energyLoss/momentumLoss and removes absorbed particles.
 int compact_species(Ctx &c, int sp) {
     SpeciesDev &s = c.sp[sp];
     const long long n = s.n;
     if (n == 0) return IPIC_OK;
+    if (s.abs_listed) {
+        // the move kernel listed what it absorbed (delIdx entries unless the list overflowed)
+        s.abs_listed = false;
+        const long long gone = s.stats.delIdx;
+        if (gone > 0 && gone <= (long long)ABS_CAP && gone * 8 < n && s.nRef == 0 && n < (1ll << 31)) return compact_from_list(c, sp, gone);
+        IPIC_CUDA(cudaMemsetAsync(c.d_abs_count + sp, 0, sizeof(unsigned), c.stream));      // not used: the array is counted below
+    }
     const long long ntiles = (n + CT_TILE - 1) / CT_TILE;
     if (ntiles > c.cap_tiles) {
         if (c.d_tileCount) { cudaFree(c.d_tileCount); cudaFree(c.d_tileOffset); cudaFree(c.d_loss); }
