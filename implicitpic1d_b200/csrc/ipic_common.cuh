@@ -82,6 +82,7 @@ struct PushArgs {
     const int *stop;           // depositJ sweeps enqueued ahead of the nonlinear solve's decision: *stop != 0 (converged / stagnated) makes the launch a no-op
     int stay_min;              // a queued batch keeps looping in registers while at least this many lanes continue
     int transit_min;           // the lean face-to-face loop runs while at least this many lanes are in transit
+    int exit_stage;            // ENTRY kernels: a lane the entry stage has taken into the next cell is finished there when it stays in that cell
     int entry_min;             // ENTRY kernels: a fresh batch takes its first sub-step to the face ahead in place when at least this many lanes leave their cell; 33 = never
 };
 
@@ -205,6 +206,7 @@ struct Ctx {
     int stay_min = 20;
     int transit_min = 12;
     int entry_min = 8;         // 33 = no entry stage for any species
+    int exit_stage = 1;        // the entry stage also finishes the lanes that end their step in the cell they enter
     int sort_subbins = 0;      // cell sort key = INT(l * sub); 0 = automatic (8, or what 16 key bits allow)
     int pair_species = 0;      // 1 = depositJ of a two-species plasma in one launch (k_push_pair).  Off: measured slower (C5: 2.34 ms per
                                // sweep against 1.88 + 0.32 ms) -- both species' sweeps are issue-bound, so running them side by side frees nothing

@@ -823,10 +823,32 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
                         nsub += 1;
                         PSTAT(3, 1);
                         e_l = face + lc; e_v = vf2; e_t = tpe; e_cell = cell + (vpos ? 1 : -1);
-                        if (!MOVE) {
-                            if (fabs(dl) == 1.0) e_pend = vpos ? cell : -cell;                   // a whole cell: the start of a run
-                            else deposit_add(W, D, lane, gacc, cell, fx_from_double(dl));
+                    }
+                    // ---- exit stage: a lane that has just crossed into the next cell ends its step there more often than not (a thermal electron
+                    // crosses one or two faces per step once the fields have converged): the general sub-step's first branch -- stays in the cell
+                    // and keeps its direction, mod_particleMover.f90:36-47 -- on the same operands as the finish stage behind the transit loop;
+                    // such a lane is done here and never sees the queue.  Everything else is queued sitting on the face.
+                    bool fin2 = false;
+                    if (!MOVE && A.exit_stage && __any_sync(FULL, go)) {
+                        const int c2 = go ? e_cell : 0;
+                        const double2 u0 = __ldg(reinterpret_cast<const double2 *>(reinterpret_cast<const CellTabNGP *>(A.tab) + c2));
+                        const double lw2 = e_l - ((SCHEME == 2) ? (double)c2 : 0.0);
+                        const double dtau = del_t - tpe;
+                        const double v_f0 = fma(u0.x, dtau, vf2);
+                        const double l_f0 = fma(__dmul_rn(__dadd_rn(vf2, v_f0), dtau), u0.y, lw2);
+                        const bool inCell2 = (SCHEME == 2) ? ((int)(l_f0 + 1.0) == 1) : ((int)l_f0 == c2);
+                        fin2 = go && inCell2 && (vpos == (v_f0 > 0.0));
+                        if (fin2) {
+                            nsub += 1;
+                            PSTAT(3, 1);
+                            deposit_add(W, D, lane, gacc, cell, fx_from_double(dl));               // (a whole cell, +-1.0, is +-FX_ONE: the run of one cell)
+                            deposit_add(W, D, lane, gacc, c2, fx_from_double(l_f0 - lw2));
+                            cont = false;
                         }
+                    }
+                    if (go && !fin2 && !MOVE) {
+                        if (fabs(dl) == 1.0) e_pend = vpos ? cell : -cell;                       // a whole cell: the start of a run
+                        else deposit_add(W, D, lane, gacc, cell, fx_from_double(dl));
                     }
                 }
             } else if (valid) {
@@ -1051,6 +1073,7 @@ static int make_push_args(Ctx &c, int sp, double del_t, PushArgs &A) {
     A.ttab = c.d_ttab + (size_t)sp * 2 * (cells + 2);
     A.stay_min = std::min(32, std::max(1, c.stay_min));
     A.transit_min = std::min(33, std::max(1, c.transit_min));   // 33 disables the transit loop
+    A.exit_stage = c.exit_stage;
     // entry stage: for species whose particles leave their cell in most sweeps -- measured on the previous step (sub-steps per particle per
     // sweep above 1.5), before the first step guessed from the charge-to-mass ratio (electron-like) -- unless the option switches it off (33)
     {
