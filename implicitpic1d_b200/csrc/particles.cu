@@ -810,15 +810,22 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
                 // else (face behind, wall cells, no time left) is queued as it is.
                 if (ENTRY && __popc(__ballot_sync(FULL, cont)) >= A.entry_min) {
                     const double2 t1 = __ldg(reinterpret_cast<const double2 *>(reinterpret_cast<const CellTabNGP *>(A.tab) + cellc) + 1);
-                    const bool vpos = v > 0.0;
-                    const int lb = cell + (vpos ? 1 : 0);
+                    // Every lane that goes on leaves through the face ahead (`fwd`: diff_PE > -v^2) or, decelerated to a halt before it, through the
+                    // face behind (`bwd`, mod_particleMover.f90:48-52: the other face, the sign of v flipped) -- in the un-converged iterates of a
+                    // step, whose fields reverse a thermal electron within one cell, a fifth of all electrons.  Same formulas, other face.
+                    const int lb_f = cell + ((v > 0.0) ? 1 : 0);
                     const double v2 = __dmul_rn(v, v);
+                    const double dl_f = ((double)lb_f - lc) - lw;
+                    const double dpe_f = __dmul_rn(t1.x, dl_f);
+                    const bool fwd = dpe_f > -v2;
+                    const int lb = fwd ? lb_f : 2 * cell + 1 - lb_f;
                     const double face = (double)lb - lc;
-                    const double dl = face - lw;
-                    const double diff_PE = __dmul_rn(t1.x, dl);
-                    const double vf2 = copysign(lean_sqrt(__dadd_rn(diff_PE, v2)), v);
+                    const double dl = fwd ? dl_f : face - lw;
+                    const double diff_PE = fwd ? dpe_f : __dmul_rn(t1.x, dl);
+                    const double vf2 = copysign(lean_sqrt(__dadd_rn(diff_PE, v2)), fwd ? v : -v);
+                    const bool vpos = !signbit(vf2);                       // direction of travel behind the face
                     const double tpe = fma(__dsub_rn(vf2, v), t1.y, 0.0);
-                    const bool go = cont && (diff_PE > -v2) && (lb != 1) && (lb != A.NB) && ((unsigned long long)__double_as_longlong(tpe) < A.tlim_bits);
+                    const bool go = cont && (lb != 1) && (lb != A.NB) && ((unsigned long long)__double_as_longlong(tpe) < A.tlim_bits);
                     if (go) {
                         nsub += 1;
                         PSTAT(3, 1);
@@ -838,6 +845,10 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
                         const double l_f0 = fma(__dmul_rn(__dadd_rn(vf2, v_f0), dtau), u0.y, lw2);
                         const bool inCell2 = (SCHEME == 2) ? ((int)(l_f0 + 1.0) == 1) : ((int)l_f0 == c2);
                         fin2 = go && inCell2 && (vpos == (v_f0 > 0.0));
+#ifdef IPIC_PUSH_STATS
+                        if (lane == 0) { atomicAdd(&g_push_stats[14], (unsigned long long)__popc(__ballot_sync(FULL, fin2))); atomicAdd(&g_push_stats[15], (unsigned long long)__popc(__ballot_sync(FULL, go))); }
+                        else { __ballot_sync(FULL, fin2); __ballot_sync(FULL, go); }
+#endif
                         if (fin2) {
                             nsub += 1;
                             PSTAT(3, 1);
@@ -847,7 +858,7 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
                         }
                     }
                     if (go && !fin2 && !MOVE) {
-                        if (fabs(dl) == 1.0) e_pend = vpos ? cell : -cell;                       // a whole cell: the start of a run
+                        if (fabs(dl) == 1.0) e_pend = (dl > 0.0) ? cell : -cell;                 // a whole cell: the start of a run
                         else deposit_add(W, D, lane, gacc, cell, fx_from_double(dl));
                     }
                 }
@@ -1092,6 +1103,7 @@ void push_stats_dump() {
     fprintf(stderr, "[push stats] general sub-step: %llu issued per warp, %llu valid lanes -> utilisation %.3f; queue pops %llu\n", h[2], h[3],
             h[2] ? (double)h[3] / (double)(h[2] * 32) : 0.0, h[6]);
     fprintf(stderr, "[push stats] fresh: %llu batches, %llu lanes finished (%.3f of slots)\n", h[4], h[5], h[4] ? (double)h[5] / (double)(h[4] * 32) : 0.0);
+    fprintf(stderr, "[push stats] entry stage: %llu lanes taken to the face ahead, %llu of them finished in the next cell (exit stage)\n", h[15], h[14]);
     fprintf(stderr, "[push stats] lanes leaving the transit loop: %llu on a NaN (turning point / wall cell / a = 0), %llu on the clock\n", h[12], h[13]);
     fprintf(stderr, "[push stats] warps: %llu; mean busy time per warp %.1f us; the latest warp of the LONGEST launch ran %.1f us (every launch's latest >= its mean: tail)\n", h[11],
             h[11] ? (double)h[8] / (double)h[11] * 1e-3 : 0.0, (double)h[9] * 1e-3);
