@@ -174,7 +174,10 @@ __device__ __forceinline__ void limb_grid_flush(const LimbGrid &g, int n) {
 //   SCHEME 1: CIC Picard sub-step           (mod_particleMoverPicard.f90:17-65)
 //   MOVE false: depositJ sweep (no particle writes, J accumulated)   true: moveParticles (write back)
 // =====================================================================================================
-constexpr int SUB = 2;                       // batches per register-staged sub-tile
+#ifndef IPIC_SUB
+#define IPIC_SUB 2
+#endif
+constexpr int SUB = IPIC_SUB;                       // batches per register-staged sub-tile
 constexpr int SUBTILE = 32 * SUB;            // 64 particles
 #ifndef IPIC_TILE_SUBS
 #define IPIC_TILE_SUBS 8
@@ -451,10 +454,14 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
             nv[b] = __ldcs(A.vx + gi);
         }
     };
+    // The next sub-tile's loads are issued one sub-tile ahead into registers in the kernels whose batches are short (ions, the move: every
+    // particle one sub-step; ion sweep 0.236 -> 0.213 ms at C5) and right before use in the entry-stage kernels (electrons: the four
+    // staging registers cost the long batches more than the exposed L2 latency, 1.171 -> 1.177 ms).  IPIC_REG_PREFETCH = 0 / 1 forces one way.
 #ifndef IPIC_REG_PREFETCH
-#define IPIC_REG_PREFETCH 0
+#define IPIC_REG_PREFETCH 2
 #endif
-    if (IPIC_REG_PREFETCH && next_ok) issue_loads();
+    constexpr bool REGPF = (IPIC_REG_PREFETCH == 1) || (IPIC_REG_PREFETCH == 2 && !ENTRY);
+    if (REGPF && next_ok) issue_loads();
 
     // ---------------- the general sub-step: runs batches popped from the queue ----------------
     bool drain_all = !next_ok;
@@ -736,7 +743,7 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
         // ---------------- fresh batches of the next sub-tile ----------------
         // rotate the staged sub-tile into the working registers and put the following one in flight
         double cl[SUB], cv[SUB];
-        if (!IPIC_REG_PREFETCH) issue_loads();               // variant: load right before use (the tile is already in L2)
+        if (!REGPF) issue_loads();                           // load right before use (the tile is already in L2)
 #pragma unroll
         for (int b = 0; b < SUB; ++b) { cl[b] = nl[b]; cv[b] = nv[b]; }
         const unsigned g0 = next_g0;
@@ -747,7 +754,7 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
         }
         next_ok = tile < ntiles;
         next_g0 = tile * (unsigned)TILE + (unsigned)sub * SUBTILE;
-        if (IPIC_REG_PREFETCH && next_ok) issue_loads();
+        if (REGPF && next_ok) issue_loads();
 
 #pragma unroll
         for (int b = 0; b < SUB; ++b) {
