@@ -1092,10 +1092,11 @@ static int make_push_args(Ctx &c, int sp, double del_t, PushArgs &A) {
     A.stay_min = std::min(32, std::max(1, c.stay_min));
     A.transit_min = std::min(33, std::max(1, c.transit_min));   // 33 disables the transit loop
     A.exit_stage = c.exit_stage;
-    // entry stage: for species whose particles leave their cell in most sweeps -- measured on the previous step (sub-steps per particle per
-    // sweep above 1.5), before the first step guessed from the charge-to-mass ratio (electron-like) -- unless the option switches it off (33)
+    // entry stage: for species whose particles leave their cell in a fair share of the sweeps -- measured on the previous step (sub-steps per
+    // particle per sweep above 1.1: the stage itself only runs in batches with `entry_min` lanes going on, the instantiation costs the others
+    // its registers), before the first step guessed from the charge-to-mass ratio (electron-like) -- unless the option switches it off (33)
     {
-        const bool many = (s.sweep_substeps_per_particle > 0.0) ? (s.sweep_substeps_per_particle > 1.5) : (std::fabs(s.q_over_m) > 1.0e10);
+        const bool many = (s.sweep_substeps_per_particle > 0.0) ? (s.sweep_substeps_per_particle > 1.1) : (std::fabs(s.q_over_m) > 1.0e10);
         A.entry_min = (c.entry_min <= 32 && many) ? std::max(1, c.entry_min) : 33;
     }
     return IPIC_OK;

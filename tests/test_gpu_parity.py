@@ -97,6 +97,18 @@ def test_depositJ(pair):
             ip.depositJ(solver, plist, world, del_t)
             assert np.array_equal(solver.J, Jg), (name, v)
         solver.set_option(name, default)
+    # the entry / exit stages of the fresh path (large-tile kernels of electron-like species): first sub-step to the face ahead or behind and,
+    # where the step ends in the cell entered, the last one as well, taken with the whole batch -- the same J bit for bit and the same
+    # sub-step counts as the general sub-step (and as the oracle)
+    for combo in (dict(tile_subs=8, entry_min=1, exit_stage=1), dict(tile_subs=8, entry_min=1, exit_stage=0), dict(tile_subs=8, entry_min=33, exit_stage=1)):
+        for k, v in combo.items():
+            solver.set_option(k, v)
+        ip.depositJ(solver, plist, world, del_t)
+        assert np.array_equal(solver.J, Jg), combo
+        for sp, p in enumerate(plist):
+            assert depositSubsteps(solver, p) == o.move_stats(sp)["substepsDeposit"], combo
+    for k, v in dict(tile_subs=0, entry_min=8, exit_stage=1).items():
+        solver.set_option(k, v)
 
 
 def test_ampere_solve(pair):
