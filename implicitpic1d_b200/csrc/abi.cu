@@ -1004,6 +1004,7 @@ int ipic_set_option(ipic_handle h, const char *name, double value) {
     else if (k == "pair_species") c->pair_species = (int)value;
     else if (k == "sort_subbins") c->sort_subbins = (int)value;
     else if (k == "exit_stage") c->exit_stage = (int)value;
+    else if (k == "sd_runs") c->sd_runs = (int)value;
     else if (k == "pair_warps") c->pair_warps = (int)value;
     else if (k == "tile_order") c->tile_order = (int)value;
     else if (k == "tile_subs") c->tile_subs = (int)value;

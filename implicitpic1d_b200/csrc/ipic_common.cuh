@@ -49,6 +49,7 @@ struct CellTabCIC {   // OpenMP/CIC/src/mod_particleMoverPicard.f90:17-65,92-94 
 constexpr int PUSH_THREADS = IPIC_PUSH_THREADS;
 constexpr int PUSH_WARPS = PUSH_THREADS / 32;
 constexpr unsigned ABS_CAP = 1u << 20;   // absorbed particles per species and move the list holds (more: the array is counted instead)
+constexpr int SD_CELLS_MAX = 5632;    // 22 KB behind the 141 KB of warp queues: still the 164 KB shared-memory configuration of the SM
 constexpr int MAX_GRID_SMEM = 8192;   // largest N_h the shared-memory limb grid supports (12 B per cell)
 
 struct PushArgs {
@@ -82,6 +83,7 @@ struct PushArgs {
     const int *stop;           // depositJ sweeps enqueued ahead of the nonlinear solve's decision: *stop != 0 (converged / stagnated) makes the launch a no-op
     int stay_min;              // a queued batch keeps looping in registers while at least this many lanes continue
     int transit_min;           // the lean face-to-face loop runs while at least this many lanes are in transit
+    int sd_cells;              // ENTRY kernels: entries of the per-CTA shared-memory copy of the difference grid (0: run ends go to the global grid)
     int exit_stage;            // ENTRY kernels: a lane the entry stage has taken into the next cell is finished there when it stays in that cell
     int entry_min;             // ENTRY kernels: a fresh batch takes its first sub-step to the face ahead in place when at least this many lanes leave their cell; 33 = never
 };
@@ -206,6 +208,7 @@ struct Ctx {
     int stay_min = 20;
     int transit_min = 12;
     int entry_min = 8;         // 33 = no entry stage for any species
+    int sd_runs = 1;           // entry-stage kernels count the ends of runs of traversed cells in shared memory (PushArgs::sd_cells)
     int exit_stage = 1;        // the entry stage also finishes the lanes that end their step in the cell they enter
     int sort_subbins = 0;      // cell sort key = INT(l * sub); 0 = automatic (8, or what 16 key bits allow)
     int pair_species = 0;      // 1 = depositJ of a two-species plasma in one launch (k_push_pair).  Off: measured slower (C5: 2.34 ms per

@@ -212,6 +212,8 @@ struct DepositState {
     unsigned long long r0 = 0ull, r1 = 0ull;   // accumulators for cells base, base+1
     unsigned dirty = 0u;
     int base = 0;
+    int *sd = nullptr;                         // this CTA's shared-memory copy of the difference grid, in units of FX_ONE (entry-stage kernels), or null
+    int sd_cells = 0;                          // entries it holds (cells beyond go to the global grid)
 };
 
 __device__ __forceinline__ void deposit_flush(WarpSmem &W, DepositState &D, int lane, unsigned long long *gacc) {
@@ -258,20 +260,28 @@ __device__ unsigned long long g_push_stats[16];
 #define PSTAT(i, x) do { } while (0)
 #endif
 
+// One end of a run of fully traversed cells: D[cell] += s * FX_ONE, s = +-1.  Run ends are scattered over the domain -- 32 lanes, 32 cells -- and
+// a global RED per lane is 26 wavefronts of the LSU data pipe and one L2 atomic each; the kernels of electron-like species therefore count them
+// in a per-CTA shared-memory copy of the difference grid (32-bit counts, native shared atomics, a few bank conflicts per warp) that the CTA adds
+// to the global grid once, when all its warps are done.  Integer sums either way: the same grid bit for bit.
+__device__ __forceinline__ void run_mark(const DepositState &D, unsigned long long *gdacc, int cell, int s) {
+    if (D.sd != nullptr && cell < D.sd_cells) atomicAdd(D.sd + cell, s);
+    else atomicAdd(gdacc + cell, (unsigned long long)((long long)s * FX_ONE));
+}
 // ends a run of fully traversed cells; `cend` is the cell the particle is in now (not part of the run)
 __device__ __forceinline__ void close_run(WarpSmem &W, DepositState &D, int lane, unsigned long long *gacc, unsigned long long *gdacc, int pend, int cend) {
     if (pend > 0) {                                          // moving right: cells pend .. cend-1 got +1 each
         if (cend - pend == 1) deposit_add(W, D, lane, gacc, pend, FX_ONE);
         else {
-            atomicAdd(gdacc + pend, (unsigned long long)FX_ONE);
-            atomicAdd(gdacc + cend, (unsigned long long)(-FX_ONE));
+            run_mark(D, gdacc, pend, 1);
+            run_mark(D, gdacc, cend, -1);
         }
     } else {                                                 // moving left: cells cend+1 .. -pend got -1 each
         const int start = -pend;
         if (start - cend == 1) deposit_add(W, D, lane, gacc, start, -FX_ONE);
         else {
-            atomicAdd(gdacc + cend + 1, (unsigned long long)(-FX_ONE));
-            atomicAdd(gdacc + start + 1, (unsigned long long)FX_ONE);
+            run_mark(D, gdacc, cend + 1, -1);
+            run_mark(D, gdacc, start + 1, 1);
         }
     }
 }
@@ -397,8 +407,9 @@ __device__ __forceinline__ int transit_loop(double &u, double &t, const double2 
 // The whole sweep of one species by one warp: claims tiles until the species has none left, drains its queue, flushes its deposits
 // and counters.  `A` is always a kernel parameter (constant bank), so the body can be instantiated for several species in one kernel.
 template <int SCHEME, bool MOVE, int TS = TILE_SUBS, bool ENTRY = false>
-__device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const int lane) {
+__device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const int lane, int *sd = nullptr, int sd_cells = 0) {
     DepositState D;
+    D.sd = sd; D.sd_cells = sd_cells;
     // this CTA's copy of the deposition grids (see Ctx::d_acc)
     const size_t rep_off = MOVE ? 0 : (size_t)(blockIdx.x % (unsigned)A.acc_reps) * A.acc_rep_stride;
     unsigned long long *const gacc = A.acc + rep_off, *const gdacc = A.dacc + rep_off;
@@ -967,7 +978,22 @@ __global__ void __launch_bounds__(PUSH_THREADS, 1) k_push(const __grid_constant_
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // a sweep enqueued ahead of the nonlinear solve's decision: the field kernel in front of it ended the solve
     if (!MOVE && A.stop != nullptr && *A.stop != 0) return;
-    push_body<SCHEME, MOVE, TS, ENTRY>(A, reinterpret_cast<WarpSmem *>(smem_raw)[warp], lane);
+    constexpr bool SD = ENTRY && !MOVE;                    // per-CTA copy of the difference grid behind the warps' queues (run_mark)
+    int *const sd = reinterpret_cast<int *>(smem_raw + PUSH_WARPS * sizeof(WarpSmem));
+    const int sdn = SD ? A.sd_cells : 0;
+    if (SD && sdn > 0) {
+        for (int i = threadIdx.x; i < sdn; i += blockDim.x) sd[i] = 0;
+        __syncthreads();
+    }
+    push_body<SCHEME, MOVE, TS, ENTRY>(A, reinterpret_cast<WarpSmem *>(smem_raw)[warp], lane, (SD && sdn > 0) ? sd : nullptr, sdn);
+    if (SD && sdn > 0) {
+        __syncthreads();
+        unsigned long long *const gd = A.dacc + (size_t)(blockIdx.x % (unsigned)A.acc_reps) * A.acc_rep_stride;
+        for (int i = threadIdx.x; i < sdn; i += blockDim.x) {
+            const int v = sd[i];
+            if (v) atomicAdd(gd + i, (unsigned long long)((long long)v * FX_ONE));
+        }
+    }
 }
 
 // depositJ sweep of TWO species in one launch.  Each warp works through one species' tiles and then through the other's; the first
@@ -1015,10 +1041,11 @@ static int launch_push_v(Ctx &c, const PushArgs &A) {
     if (TS == TILE_SUBS && A.tile_subs == 1) return launch_push_v<SCHEME, MOVE, 1>(c, A);      // small load: 64-particle tiles
     // a species whose particles mostly leave their cell (electrons) takes the first sub-step inside the fresh path (push_body: entry stage)
     if (!ENTRY && !MOVE && SCHEME != 1 && TS == TILE_SUBS && A.entry_min <= 32) return launch_push_v<SCHEME, MOVE, (SCHEME != 1 && !MOVE) ? TILE_SUBS : TS, (SCHEME != 1 && !MOVE)>(c, A);
-    const size_t smem = (size_t)PUSH_WARPS * sizeof(WarpSmem);
+    const size_t smem = (size_t)PUSH_WARPS * sizeof(WarpSmem) + ((ENTRY && !MOVE) ? (size_t)A.sd_cells * sizeof(int) : 0);
     static bool configured[64] = {};          // function attributes are per device
     if (!configured[c.device & 63]) {
-        IPIC_CUDA(cudaFuncSetAttribute(k_push<SCHEME, MOVE, TS, ENTRY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        IPIC_CUDA(cudaFuncSetAttribute(k_push<SCHEME, MOVE, TS, ENTRY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)((size_t)PUSH_WARPS * sizeof(WarpSmem) + (size_t)SD_CELLS_MAX * sizeof(int))));
         // leave the rest of the 256 KB to L1: the per-cell tables are gathered through it
         IPIC_CUDA(cudaFuncSetAttribute(k_push<SCHEME, MOVE, TS, ENTRY>, cudaFuncAttributePreferredSharedMemoryCarveout, 52));
         configured[c.device & 63] = true;
@@ -1092,6 +1119,7 @@ static int make_push_args(Ctx &c, int sp, double del_t, PushArgs &A) {
     A.stay_min = std::min(32, std::max(1, c.stay_min));
     A.transit_min = std::min(33, std::max(1, c.transit_min));   // 33 disables the transit loop
     A.exit_stage = c.exit_stage;
+    A.sd_cells = c.sd_runs ? std::min(A.NB + 2, SD_CELLS_MAX) : 0;
     // entry stage: for species whose particles leave their cell in a fair share of the sweeps -- measured on the previous step (sub-steps per
     // particle per sweep above 1.1: the stage itself only runs in batches with `entry_min` lanes going on, the instantiation costs the others
     // its registers), before the first step guessed from the charge-to-mass ratio (electron-like) -- unless the option switches it off (33)
