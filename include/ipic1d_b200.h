@@ -312,6 +312,20 @@ int ipic_peer_export(ipic_handle h, void *handle64);
 int ipic_peer_import(ipic_handle h, int32_t nranks, int32_t rank, const void *handles64_by_rank);
 
 /* ---- tuning / introspection ----------------------------------------------------*/
+/* Scheduling knobs of the kernels; none of them changes a result (J, fields, particles and counters are the same bit for bit -- the
+ * deposits are integers -- except where noted).  Unknown names return IPIC_ERR_ARG.
+ *   stay_min, transit_min, entry_min   lane-count thresholds of the push kernel's register loop / face-to-face loop / entry stage (33 = off)
+ *   exit_stage (1)      the entry stage also finishes the lanes that end their step in the cell they enter
+ *   sd_runs (1)         ends of runs of traversed cells counted in shared memory per CTA instead of global atomics
+ *   tile_order (1), tile_subs (0 = automatic), push_blocks (0 = one CTA per SM)   tile schedule / size / grid of the push kernels
+ *   pair_species (0), pair_warps      both species of a two-species plasma in one launch
+ *   sort_subbins (0 = automatic)      slices of a cell in the key of ipic_sort_particles
+ *   fill_compaction (1) arrays without thread-slab identity (device loader, after a sort): absorbed particles' slots are filled from the tail
+ *                       instead of a stable scatter -- the same survivors and loss sums, another particle ORDER
+ *   anderson_chunk (6)  nonlinear iterations enqueued ahead of the device-side convergence decision
+ *   field_cluster (8)   CTAs of the fused field kernel's thread-block cluster (sums of the normal equations added in another order: last bits)
+ *   peer_reduce (1)     J all-reduce through peer memory (0: NCCL);  norm_flag (1)  residual norm through pinned memory
+ *   timing (1)          CUDA-event brackets of ipic_get_timing */
 int ipic_set_option(ipic_handle h, const char *name, double value);
 /* run all kernels of this context on a caller-owned CUDA stream (cudaStream_t passed as void*), e.g. the
  * host program's / torch's current stream; NULL restores the context's own stream. */
