@@ -1040,7 +1040,7 @@ template <int SCHEME, bool MOVE, int TS = TILE_SUBS, bool ENTRY = false>
 static int launch_push_v(Ctx &c, const PushArgs &A) {
     if (TS == TILE_SUBS && A.tile_subs == 1) return launch_push_v<SCHEME, MOVE, 1>(c, A);      // small load: 64-particle tiles
     // a species whose particles mostly leave their cell (electrons) takes the first sub-step inside the fresh path (push_body: entry stage)
-    if (!ENTRY && !MOVE && SCHEME != 1 && TS == TILE_SUBS && A.entry_min <= 32) return launch_push_v<SCHEME, MOVE, (SCHEME != 1 && !MOVE) ? TILE_SUBS : TS, (SCHEME != 1 && !MOVE)>(c, A);
+    if (!ENTRY && !MOVE && SCHEME != 1 && A.entry_min <= 32) return launch_push_v<SCHEME, MOVE, TS, (SCHEME != 1 && !MOVE)>(c, A);
     const size_t smem = (size_t)PUSH_WARPS * sizeof(WarpSmem) + ((ENTRY && !MOVE) ? (size_t)A.sd_cells * sizeof(int) : 0);
     static bool configured[64] = {};          // function attributes are per device
     if (!configured[c.device & 63]) {
