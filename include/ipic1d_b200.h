@@ -107,7 +107,10 @@ int ipic_generate_particles_dist(ipic_handle h, int32_t species, int64_t n, doub
  * Ordering contract: call it at a step boundary, i.e. BEFORE ipic_move_particles / ipic_solve_potential of the step, never between the
  * move and the calls that consume the move's per-particle records.  A sort permutes the arrays, so it drops refRecordIdx (the list
  * ipic_reflux_particles / ipic_inject_at_boundary / ipic_get_ref_record read: empty afterwards) and resets numToCollide to N_p (the
- * prefix that excluded particles born during the step no longer exists).  At most 2^31 - 1 particles of one species per GPU. */
+ * prefix that excluded particles born during the step no longer exists).  At most 2^31 - 1 particles of one species per GPU.
+ * A sort also ends the reference's thread-slab identity of the arrays (ipic_upload_particles sets it, ipic_download_particles then returns
+ * one slab): from then on ipic_move_particles removes absorbed particles by moving live particles of the tail into their slots (option
+ * "fill_compaction") instead of the stable, slab-wise compaction of mod_particleMover.f90:252-256 -- the same particles, another order. */
 int ipic_sort_particles(ipic_handle h, int32_t species);
 
 /* ---- field state -----------------------------------------------------------*/
