@@ -704,3 +704,40 @@ def test_compaction_by_filling_keeps_the_particle_set():
             solver.close()
     assert res[0][0] == res[1][0]
     assert np.allclose(res[0][1], res[1][1], rtol=1e-12, atol=0.0)
+
+
+def test_run_ends_in_shared_memory_on_a_grid_larger_than_the_copy():
+    """The entry-stage kernels count the ends of runs of traversed cells in a per-CTA shared-memory copy of the difference grid that holds
+    5632 cells; on a larger grid the cells beyond go to the global grid as before.  Same J bit for bit with the copy on or off, for large
+    and small tiles."""
+    from implicitpic1d_b200.domain import readWorld
+    from implicitpic1d_b200 import constants as K
+    n_ave, T_e, Nx = 1e16, 4.0, 7001
+    world = readWorld(0, Nx, 0.05, 0, 0.0, 1, 1, 1, T_e, n_ave)
+    solver = ip.potentialSolver(world, 0.0, 0.0, 0.0, 0.0)
+    try:
+        N = 1_500_000
+        L = ip.load_library()
+        m_ion = 4.002602 * K.m_amu - K.m_e
+        plist = [ip.Particle(K.m_e, -K.e, n_ave * world.L_domain / N, 0, 0, "e", 1), ip.Particle(m_ion, K.e, n_ave * world.L_domain / N, 0, 0, "He+", 1)]
+        solver._bind(plist)
+        _lib.check(L.ipic_generate_particles(solver._h, 0, N, T_e, 0.0, 7))
+        _lib.check(L.ipic_generate_particles(solver._h, 1, N, 0.025, 0.0, 7))
+        for p in plist:
+            _lib.check(L.ipic_sort_particles(solver._h, p._index))
+        ip.initializeSolver(solver, 1e-8, 0.0, 0, 10, 0.5, 100)
+        solver.solveInitialPotential(plist, world, 0.0)
+        del_t = 4.0 * K.del_t_from_deck(n_ave, 1.0, 1.0)            # electrons cross tens of these small cells
+        ref = None
+        for subs in (8, 1):
+            for sd in (0, 1):
+                solver.set_option("tile_subs", subs)
+                solver.set_option("sd_runs", sd)
+                ip.depositJ(solver, plist, world, del_t)
+                if ref is None:
+                    ref = solver.J.copy()
+                    assert np.all(np.isfinite(ref)) and np.max(np.abs(ref)) > 0
+                    assert depositSubsteps(solver, plist[0]) > 5 * N      # runs of several cells
+                assert np.array_equal(ref, solver.J), (subs, sd)
+    finally:
+        solver.close()
