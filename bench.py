@@ -553,6 +553,9 @@ def run_cuda_arm(args, w):
                 "data": "synthetic",
                 "config": {"workload": w["name"], "particles_per_gpu": 2 * n_sp, "particles_total": 2 * n_sp * world_size, "cells": world.NumberXHalfNodes,
                            "del_t": del_t, "residual_evaluations_per_step": sum(iters) / len(iters),
+                           # iterNumPicard is the count of the LAST solve of a step; a step whose solve stagnates is split (mod_nonLinSolvers.f90:162-196) and
+                           # holds the sweeps of every attempt
+                           "sweeps_per_step": sweeps / max(args.steps, 1),
                            "substeps_per_particle_per_sweep": substeps / max(particle_sweeps, 1),
                            "sort_every_steps": args.sort_every, "sort_every_steps_ions": args.sort_every * args.sort_ion_factor, "tridiag": "thomas" if args.thomas else ("pcr" if w["scheme"] == 2 else "scan (generators of the inverse)"),
                            "l2": "inputs larger than L2: %.2f GB particle stream per sweep per GPU vs 126 MB L2" % (32.0 * n_sp / 1e9),
