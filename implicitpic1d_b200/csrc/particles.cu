@@ -880,13 +880,14 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
                         else deposit_add(W, D, lane, gacc, cell, fx_from_double(dl));
                     }
                 }
-            } else if (valid) {
-                bool done;
-                {
+            } else {
+                // CIC: the Picard sub-step of a particle that stays inside its cell for the whole step (every ion, bulk electrons)
+                bool done = false;
+                unsigned long long qa = 0ull, qb = 0ull;             // the two-point deposit: cell, cell + 1
+                if (valid) {
                     const double2 *tp2 = reinterpret_cast<const double2 *>(reinterpret_cast<const CellTabCIC *>(A.tab) + cell);
                     const double2 t0 = __ldg(tp2), t1 = __ldg(tp2 + 1);
                     const double cap = __ldg(reinterpret_cast<const double *>(tp2 + 2));
-                    done = false;
                     if (cap >= del_t) {                      // otherwise the sub-step cap splits the step: general path
                         const double ls = l - (double)cell;
                         const double r = del_t * t1.x;
@@ -911,14 +912,24 @@ __device__ __forceinline__ void push_body(const PushArgs &A, WarpSmem &W, const 
                                 A.l_out[gi] = l_f; A.vx_out[gi] = 2.0 * v_half - v;
                             } else {
                                 const double Jp = l_f - l;
-                                deposit_add(W, D, lane, gacc, cell, fx_from_double((1.0 - d_half) * Jp));
-                                deposit_add(W, D, lane, gacc, cell + 1, fx_from_double(Jp * d_half));
+                                qa = (unsigned long long)fx_from_double((1.0 - d_half) * Jp);
+                                qb = (unsigned long long)fx_from_double(Jp * d_half);
                             }
                         }
                     }
                 }
+                if (!MOVE) {
+                    // sorted input keeps a sub-tile inside the warp's current cell: both points go to the register accumulators without the
+                    // per-lane routine (as the NGP fresh path does)
+                    const int k = cell - D.base;
+                    if (__all_sync(FULL, !done || k == 0)) { D.r0 += qa; D.r1 += qb; }
+                    else if (done) {
+                        deposit_add(W, D, lane, gacc, cell, (long long)qa);
+                        deposit_add(W, D, lane, gacc, cell + 1, (long long)qb);
+                    }
+                }
                 if (done) nsub += 1;
-                cont = !done;
+                cont = valid && !done;
             }
             const unsigned cm = __ballot_sync(FULL, cont);
             if (cm) {
